@@ -1,0 +1,219 @@
+"""Host-side *builder*: nengo-style network declaration -> built parameters.
+
+This is the part of ``nengo.Simulator.__init__`` that the reference relies on at
+``experiments/run_slam.py:198-199`` / ``run_pathint.py:147-148`` (SURVEY.md §3.4 and
+App. A.2-A.8): seed assignment, eval-point / encoder / gain / bias sampling, tuning
+curves, regularised least-squares decoders, ``transform @ decoders`` folding.  It is
+pure NumPy/SciPy host logic and is shared by the CUDA lowering (product) and the
+operator-level oracle (checker) so that both step *the same built model*.
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+
+from . import nengo_shim as ns
+from .nengo_shim import dists as nd
+from .nengo_shim.utils.numpy import maxint
+
+_TYPE_ORDER = ("connections", "ensembles", "networks", "nodes", "probes")  # App. A.2
+
+
+@dataclasses.dataclass
+class BuiltEnsemble:
+    eval_points: np.ndarray
+    encoders: np.ndarray
+    intercepts: np.ndarray
+    max_rates: np.ndarray
+    scaled_encoders: np.ndarray
+    gain: np.ndarray
+    bias: np.ndarray
+
+
+@dataclasses.dataclass
+class BuiltConnection:
+    eval_points: np.ndarray | None
+    solver_info: dict | None
+    transform: np.ndarray | None
+    weights: np.ndarray | float | None  # folded ``transform @ decoders`` (size_out x n) for decoded conns
+
+
+class BuiltModel:
+    """``sim.model``-like container: ``params[obj]``, ``seeds[obj]``, ``dt``."""
+
+    def __init__(self, network, dt):
+        self.toplevel = network
+        self.dt = float(dt)
+        self.seeds: dict = {}
+        self.params: dict = {}
+        self.probe_conns: dict = {}  # probe -> implicit decoded connection weights
+
+    def initial_voltage(self, ens, trial_seed=None):
+        """LIF start voltages ~ U(0,1) from ``RandomState(seed+1)`` (App. A.2/A.4).
+
+        ``trial_seed`` is this backend's batching extension: trial ``s`` re-draws the
+        start state from a trial-specific stream; ``None`` is nengo's own draw.
+        """
+        base = self.seeds[ens] + 1
+        if trial_seed is not None:
+            base = (base + 7919 * (int(trial_seed) + 1)) % maxint
+        rng = np.random.RandomState(base)
+        if isinstance(ens.neuron_type, ns.LIF):
+            return rng.uniform(0.0, 1.0, size=ens.n_neurons)
+        return np.zeros(ens.n_neurons)
+
+
+# ----------------------------------------------------------------------------- seeds
+def _assign_seeds(net, seeds):
+    rng = np.random.RandomState(seeds[net])
+    for attr in _TYPE_ORDER:
+        for obj in getattr(net, attr):
+            drawn = rng.randint(maxint)  # drawn even when the object has its own seed
+            own = getattr(obj, "seed", None)
+            seeds[obj] = drawn if own is None else own
+    for sub in net.networks:
+        _assign_seeds(sub, seeds)
+
+
+def n_eval_points_default(n_neurons, dimensions):
+    return int(max(np.clip(500 * dimensions, 750, 2500), 2 * n_neurons))
+
+
+# ----------------------------------------------------------------------------- ensembles
+def _build_ensemble(model, ens):
+    rng = np.random.RandomState(model.seeds[ens])
+    # draw order: eval points -> encoders -> max_rates -> intercepts (App. A.3)
+    if isinstance(ens.eval_points, nd.Distribution):
+        n_pts = ens.n_eval_points or n_eval_points_default(ens.n_neurons, ens.dimensions)
+        eval_points = ens.eval_points.sample(n_pts, ens.dimensions, rng=rng)
+    else:
+        eval_points = np.array(ens.eval_points, dtype=np.float64)
+    eval_points = eval_points * ens.radius
+
+    if isinstance(ens.encoders, nd.Distribution):
+        encoders = np.asarray(ens.encoders.sample(ens.n_neurons, ens.dimensions, rng=rng), dtype=np.float64)
+    else:
+        encoders = np.array(ens.encoders, dtype=np.float64)
+    if ens.normalize_encoders:
+        encoders = encoders / np.linalg.norm(encoders, axis=1, keepdims=True)
+    if not np.all(np.isfinite(encoders)):
+        raise ns.exceptions.BuildError(f"non-finite encoders in {ens!r}")
+
+    if ens.gain is not None and ens.bias is not None:
+        gain = np.array(ens.gain, dtype=np.float64)
+        bias = np.array(ens.bias, dtype=np.float64)
+        max_rates = intercepts = None
+    else:
+        max_rates = nd.get_samples(ens.max_rates, ens.n_neurons, rng=rng)
+        intercepts = nd.get_samples(ens.intercepts, ens.n_neurons, rng=rng)
+        gain, bias = ens.neuron_type.gain_bias(max_rates, intercepts)
+    if not (np.all(np.isfinite(gain)) and np.all(np.isfinite(bias))):
+        raise ns.exceptions.BuildError(f"non-finite gain/bias in {ens!r}")
+
+    scaled = encoders * (gain / ens.radius)[:, None]
+    model.params[ens] = BuiltEnsemble(eval_points, encoders, intercepts, max_rates, scaled, gain, bias)
+
+
+# ----------------------------------------------------------------------------- decoders
+class _DecoderCache:
+    """Tuning curves and the regularised Gram factor are shared by every decoded
+    connection leaving one ensemble with the same solver (509 solves)."""
+
+    def __init__(self, model):
+        self.model = model
+        self._acts = {}
+        self._factor = {}
+
+    def activities(self, ens):
+        if ens not in self._acts:
+            p = self.model.params[ens]
+            x = p.eval_points @ (p.encoders.T / ens.radius)
+            self._acts[ens] = ens.neuron_type.rates(x, p.gain, p.bias)
+            if np.count_nonzero(self._acts[ens]) == 0:
+                raise ns.exceptions.BuildError(f"all tuning curves of {ens!r} are zero")
+        return self._acts[ens]
+
+    def solve(self, ens, solver, targets):
+        A = self.activities(ens)
+        if not isinstance(solver, ns.solvers.LstsqL2):
+            X, _ = solver(A, targets)
+            return X
+        key = (ens, solver.reg)
+        if key not in self._factor:
+            self._factor[key] = solver.gram(A)
+        return solver.solve(A, targets, self._factor[key])
+
+
+def _targets(conn, eval_points):
+    pts = eval_points[:, conn.pre_slice] if conn.pre_slice != slice(None) else eval_points
+    if pts.ndim == 1:
+        pts = pts[:, None]
+    if conn.function is None:
+        return pts
+    if isinstance(conn.function, np.ndarray):
+        return conn.function
+    out = np.zeros((len(pts), conn.size_mid))
+    for i, p in enumerate(pts):
+        out[i] = np.asarray(conn.function(p), dtype=np.float64).reshape(-1)
+    return out
+
+
+def fold_transform(transform, mat):
+    """``transform * decoders`` with nengo's scalar / diagonal / dense cases (App. A.6)."""
+    if transform is None:
+        return mat
+    t = np.asarray(transform, dtype=np.float64)
+    if t.ndim == 0:
+        return t * mat
+    if t.ndim == 1:
+        return t[:, None] * mat
+    return t @ mat
+
+
+def _build_connection(model, conn, cache):
+    pre = conn.pre_obj
+    if isinstance(pre, ns.Ensemble):
+        if conn.solver.weights:
+            raise NotImplementedError("weight solvers (solver.weights=True) are outside the hot path")
+        if isinstance(pre.neuron_type, ns.Direct):
+            raise NotImplementedError("Direct-mode ensembles are not supported")
+        eval_points = model.params[pre].eval_points if conn.eval_points is None \
+            else np.array(conn.eval_points, dtype=np.float64)
+        if conn.eval_points is not None:
+            raise NotImplementedError("per-connection eval_points are outside the hot path")
+        decoders = cache.solve(pre, conn.solver, _targets(conn, eval_points)).T  # size_mid x n
+        weights = fold_transform(conn.transform, decoders)
+        model.params[conn] = BuiltConnection(eval_points, {}, conn.transform, weights)
+    elif isinstance(pre, ns.Neurons):
+        raise NotImplementedError("connections *from* ens.neurons are outside the hot path")
+    else:
+        if conn.function is not None:
+            raise NotImplementedError("functions on Node->X connections are outside the hot path")
+        model.params[conn] = BuiltConnection(None, None, conn.transform, conn.transform)
+
+
+def _build_probe(model, probe, cache):
+    obj = probe.obj
+    if isinstance(obj, ns.Ensemble) and probe.attr == "decoded_output":
+        dec = cache.solve(obj, probe.solver, model.params[obj].eval_points).T
+        model.probe_conns[probe] = dec[np.arange(obj.dimensions)[probe.slice]]
+    model.params[probe] = None
+
+
+def build_model(network, dt=0.001, seed=None):
+    """Build every ensemble / connection / probe of ``network`` (and sub-networks)."""
+    model = BuiltModel(network, dt)
+    top_seed = getattr(network, "seed", None)
+    if top_seed is None:
+        top_seed = seed if seed is not None else np.random.randint(maxint)
+    model.seeds[network] = int(top_seed)
+    _assign_seeds(network, model.seeds)
+
+    cache = _DecoderCache(model)
+    for ens in network.all_ensembles:
+        _build_ensemble(model, ens)
+    for conn in network.all_connections:
+        _build_connection(model, conn, cache)
+    for probe in network.all_probes:
+        _build_probe(model, probe, cache)
+    return model
