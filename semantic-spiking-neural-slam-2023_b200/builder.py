@@ -49,18 +49,40 @@ class BuiltModel:
         self.probe_conns: dict = {}  # probe -> implicit decoded connection weights
 
     def initial_voltage(self, ens, trial_seed=None):
-        """LIF start voltages ~ U(0,1) from ``RandomState(seed+1)`` (App. A.2/A.4).
+        """LIF start voltages ~ U(0,1) (App. A.2/A.4).
 
-        ``trial_seed`` is this backend's batching extension: trial ``s`` re-draws the
-        start state from a trial-specific stream; ``None`` is nengo's own draw.
-        """
-        base = self.seeds[ens] + 1
-        if trial_seed is not None:
-            base = (base + 7919 * (int(trial_seed) + 1)) % maxint
-        rng = np.random.RandomState(base)
-        if isinstance(ens.neuron_type, ns.LIF):
-            return rng.uniform(0.0, 1.0, size=ens.n_neurons)
-        return np.zeros(ens.n_neurons)
+        ``trial_seed=None`` is nengo's own draw from ``RandomState(seed+1)``.  An integer
+        ``trial_seed`` is this backend's batching extension: a counter-based hash of
+        (ensemble seed, trial seed, neuron index), so a trial's start state does not depend
+        on which other trials share the batch (and thousands of trials cost no RNG set-up)."""
+        if not isinstance(ens.neuron_type, ns.LIF):
+            return np.zeros(ens.n_neurons)
+        if trial_seed is None:
+            return np.random.RandomState(self.seeds[ens] + 1).uniform(0.0, 1.0, size=ens.n_neurons)
+        return self.initial_voltages(ens, [trial_seed])[0]
+
+    def initial_voltages(self, ens, trial_seeds):
+        """[n_trials, n_neurons] start voltages; entries of ``trial_seeds`` may be ``None``."""
+        n = ens.n_neurons
+        out = np.zeros((len(trial_seeds), n))
+        if not isinstance(ens.neuron_type, ns.LIF):
+            return out
+        ints = np.array([-1 if s is None else int(s) for s in trial_seeds], dtype=np.int64)
+        hashed = ints >= 0
+        if hashed.any():
+            with np.errstate(over="ignore"):
+                x = (np.uint64(self.seeds[ens] + 1)
+                     + ints[hashed].astype(np.uint64)[:, None] * np.uint64(0x9E3779B97F4A7C15)
+                     + (np.arange(n, dtype=np.uint64)[None, :] + np.uint64(1)) * np.uint64(0xD1B54A32D192ED03))
+                x ^= x >> np.uint64(30)
+                x *= np.uint64(0xBF58476D1CE4E5B9)
+                x ^= x >> np.uint64(27)
+                x *= np.uint64(0x94D049BB133111EB)
+                x ^= x >> np.uint64(31)
+            out[hashed] = (x >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+        if (~hashed).any():
+            out[~hashed] = self.initial_voltage(ens, None)
+        return out
 
 
 # ----------------------------------------------------------------------------- seeds

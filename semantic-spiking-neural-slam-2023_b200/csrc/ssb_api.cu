@@ -1,0 +1,677 @@
+// Host side of the C-ABI declared in include/sspslam_b200.h: plan upload, arenas,
+// the per-step launch sequence, probes, event timing.  No torch, no Python types.
+#include "ssb_kernels.cuh"
+#include "../../include/sspslam_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define SSB_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(-2, std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
+    } while (0)
+
+enum Kind { K_SMALL = 0, K_WIDE, K_DEC, K_PES, K_SCAN, K_PICK, K_GATE, K_LIN, K_ADV, K_NKINDS };
+
+struct HostArray {
+    std::vector<unsigned char> bytes;
+};
+
+struct CleanupDev {
+    float* cx = nullptr;
+    float* pval = nullptr;
+    int* pidx = nullptr;
+    int* idx = nullptr;
+    const double* s64 = nullptr;
+};
+
+}  // namespace
+
+struct ssb_sim {
+    int device = 0;
+    int n_trials = 0, B = 0, n_groups = 0;
+    cudaStream_t stream = nullptr;
+    bool finalized = false;
+    std::map<std::string, HostArray> arrays;
+    std::map<std::string, double> scalars;
+    // plan (device)
+    int *d_csr_ptr = nullptr, *d_csr_idx = nullptr;
+    float* d_csr_val = nullptr;
+    float* d_W = nullptr;
+    int *d_small = nullptr, *d_big = nullptr, *d_dec = nullptr, *d_pes = nullptr, *d_cleanup = nullptr, *d_gate = nullptr;
+    int* d_lin_rows = nullptr;
+    float* d_lin_ab = nullptr;
+    float* d_ntypes = nullptr;
+    double* d_s64 = nullptr;
+    std::vector<int> h_stages, h_big, h_dec, h_cleanup, h_pes;
+    std::vector<size_t> s64_offsets;
+    int n_levels = 0, n_lin = 0, n_pes = 0, n_small_total = 0;
+    // sizes
+    long long nv = 0, nf = 0, nt = 0, nn = 0, n_act = 0, n_lenc = 0, n_ldec = 0, n_afilt = 0, n_probe = 0;
+    int chunk_cap = 0;
+    // arenas
+    float *vec = nullptr, *tab = nullptr, *v = nullptr, *ref = nullptr, *act = nullptr, *lenc = nullptr, *ldec = nullptr;
+    float *afilt = nullptr, *probe = nullptr;
+    long long* dyn = nullptr;
+    std::vector<CleanupDev> cleanups;
+    int* cidx = nullptr;  // [n_cleanup][B]
+    // host mirrors of dyn
+    long long steps_done = 0, tab_step0 = 0, probe_step0 = 0;
+    int tab_steps = 0;
+    // timing
+    bool profiling = false;
+    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
+    bool run_timed = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, int>> ev_used;  // (kind, index of first event of the pair)
+    float kind_ms[K_NKINDS] = {0};
+    long long kind_launches[K_NKINDS] = {0};
+    long long total_launches = 0;
+    SsbCtx ctx;
+};
+
+namespace {
+
+template <typename T>
+int upload_array(ssb_sim* s, const char* name, T** dst, size_t* count = nullptr) {
+    auto it = s->arrays.find(name);
+    size_t bytes = it == s->arrays.end() ? 0 : it->second.bytes.size();
+    if (count) *count = bytes / sizeof(T);
+    size_t alloc = bytes ? bytes : sizeof(T) * 4;
+    SSB_CUDA(cudaMalloc((void**)dst, alloc));
+    SSB_CUDA(cudaMemset(*dst, 0, alloc));
+    if (bytes) SSB_CUDA(cudaMemcpy(*dst, it->second.bytes.data(), bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+std::vector<int> host_ints(ssb_sim* s, const char* name) {
+    auto it = s->arrays.find(name);
+    if (it == s->arrays.end()) return {};
+    const int* p = reinterpret_cast<const int*>(it->second.bytes.data());
+    return std::vector<int>(p, p + it->second.bytes.size() / sizeof(int));
+}
+
+long long iscalar(ssb_sim* s, const char* name) {
+    auto it = s->scalars.find(name);
+    return it == s->scalars.end() ? 0 : (long long)(it->second + 0.5);
+}
+
+int alloc_rows(float** p, long long rows, int B) {
+    size_t bytes = (size_t)(rows > 0 ? rows : 1) * B * sizeof(float);
+    SSB_CUDA(cudaMalloc((void**)p, bytes));
+    SSB_CUDA(cudaMemset(*p, 0, bytes));
+    return 0;
+}
+
+struct ArenaRef {
+    float* ptr;
+    long long rows;
+};
+
+int arena(ssb_sim* s, const char* name, ArenaRef* out) {
+    std::string n(name);
+    if (n == "v") *out = {s->v, s->nn};
+    else if (n == "ref") *out = {s->ref, s->nn};
+    else if (n == "act") *out = {s->act, s->n_act};
+    else if (n == "lenc") *out = {s->lenc, s->n_lenc};
+    else if (n == "ldec") *out = {s->ldec, s->n_ldec};
+    else if (n == "afilt") *out = {s->afilt, 2 * s->n_afilt};
+    else if (n == "vec") *out = {s->vec, s->nv};
+    else if (n == "cidx") *out = {reinterpret_cast<float*>(s->cidx), (long long)s->cleanups.size()};
+    else return fail(-3, "unknown arena '" + n + "'");
+    return 0;
+}
+
+cudaEvent_t* next_events(ssb_sim* s, int kind) {
+    size_t used = s->ev_used.size() * 2;
+    while (s->ev_pool.size() < used + 2) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s->ev_pool.push_back(e);
+    }
+    s->ev_used.push_back({kind, (int)used});
+    return &s->ev_pool[used];
+}
+
+struct LaunchTimer {
+    ssb_sim* s;
+    cudaEvent_t* ev = nullptr;
+    LaunchTimer(ssb_sim* s_, int kind) : s(s_) {
+        s->kind_launches[kind]++;
+        s->total_launches++;
+        if (s->profiling) {
+            ev = next_events(s, kind);
+            cudaEventRecord(ev[0], s->stream);
+        }
+    }
+    ~LaunchTimer() {
+        if (ev) cudaEventRecord(ev[1], s->stream);
+    }
+};
+
+int collect_profile(ssb_sim* s) {
+    if (s->ev_used.empty()) return 0;
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    for (auto& u : s->ev_used) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->ev_pool[u.second], s->ev_pool[u.second + 1]);
+        s->kind_ms[u.first] += ms;
+    }
+    s->ev_used.clear();
+    return 0;
+}
+
+template <int DP>
+void launch_scan(ssb_sim* s, bool csr, dim3 grid, size_t smem, const SsbCtx& c, const int* desc, const float* S,
+                 const CleanupDev& cd) {
+    if (csr)
+        k_cleanup_scan<DP, true><<<grid, SSB_SCAN_WARPS * 32, smem, s->stream>>>(c, desc, S, cd.cx, cd.pval, cd.pidx);
+    else
+        k_cleanup_scan<DP, false><<<grid, SSB_SCAN_WARPS * 32, smem, s->stream>>>(c, desc, S, cd.cx, cd.pval, cd.pidx);
+}
+
+void dispatch_scan(ssb_sim* s, bool csr, int dpad, int n_groups, const SsbCtx& c, const int* desc, const float* S,
+                   const CleanupDev& cd) {
+    dim3 grid(SSB_SCAN_CHUNKS, n_groups);
+    size_t smem = (size_t)dpad * 32 * sizeof(float);
+    if (dpad == 56) launch_scan<56>(s, csr, grid, smem, c, desc, S, cd);
+    else if (dpad == 100) launch_scan<100>(s, csr, grid, smem, c, desc, S, cd);
+    else launch_scan<0>(s, csr, grid, smem, c, desc, S, cd);
+}
+
+int one_step(ssb_sim* s) {
+    const SsbCtx& c = s->ctx;
+    const int G = s->n_groups;
+    for (int lvl = 0; lvl < s->n_levels; ++lvl) {
+        const int* st = &s->h_stages[lvl * 10];
+        if (st[1] > 0) {
+            LaunchTimer t(s, K_SMALL);
+            const int warps = st[1] * G;
+            k_ens_small<<<(warps + 3) / 4, 128, 0, s->stream>>>(c, s->d_small + st[0] * 9, st[1], G);
+        }
+        if (st[3] > 0) {
+            LaunchTimer t(s, K_WIDE);
+            int max_n = 0, max_sm = 0;
+            for (int i = 0; i < st[3]; ++i) {
+                const int* d = &s->h_big[(st[2] + i) * 16];
+                max_n = std::max(max_n, d[0]);
+                max_sm = std::max(max_sm, (d[2] + d[11]) * 32 * (int)sizeof(float));
+            }
+            const int chunk = 128;
+            dim3 grid((max_n + chunk - 1) / chunk, G, st[3]);
+            k_ens_wide<<<grid, 256, max_sm, s->stream>>>(c, s->d_big, st[2], chunk);
+        }
+        for (int i = 0; i < st[7]; ++i) {
+            const int ci = st[6] + i;
+            const int* d = &s->h_cleanup[ci * 6];
+            const CleanupDev& cd = s->cleanups[ci];
+            {
+                LaunchTimer t(s, K_SCAN);
+                dispatch_scan(s, true, d[2], G, c, s->d_cleanup + ci * 6, s->d_W + d[3], cd);
+            }
+            {
+                LaunchTimer t(s, K_PICK);
+                k_cleanup_pick<<<(s->B + 127) / 128, 128, 0, s->stream>>>(s->B, d[1], d[2], cd.cx, cd.pval, cd.pidx, cd.s64,
+                                                                          s->d_W + d[3], s->vec + (size_t)d[5] * s->B, cd.idx,
+                                                                          nullptr, 0, 0);
+            }
+        }
+        if (st[9] > 0) {
+            LaunchTimer t(s, K_GATE);
+            dim3 grid((s->B + 127) / 128, st[9]);
+            k_gate<<<grid, 128, 0, s->stream>>>(c, s->d_gate, st[8]);
+        }
+        if (st[5] > 0) {
+            LaunchTimer t(s, K_DEC);
+            int max_out = 0;
+            for (int i = 0; i < st[5]; ++i) max_out = std::max(max_out, s->h_dec[(st[4] + i) * 6 + 1]);
+            dim3 grid((max_out + 7) / 8, G, st[5]);
+            k_decode<<<grid, 128, 0, s->stream>>>(c, s->d_dec, st[4]);
+        }
+    }
+    if (s->n_pes > 0) {
+        LaunchTimer t(s, K_PES);
+        int max_out = 0;
+        for (int i = 0; i < s->n_pes; ++i) max_out = std::max(max_out, s->h_pes[i * 10 + 1]);
+        dim3 grid((max_out + 7) / 8, G, s->n_pes);
+        k_pes<<<grid, 128, 0, s->stream>>>(c, s->d_pes, s->n_pes);
+    }
+    if (s->n_lin > 0) {
+        LaunchTimer t(s, K_LIN);
+        dim3 grid((s->n_lin + 3) / 4, G);
+        k_lin<<<grid, 128, 0, s->stream>>>(c, s->d_lin_rows, s->d_lin_ab, s->n_lin);
+    }
+    {
+        LaunchTimer t(s, K_ADV);
+        k_advance<<<1, 1, 0, s->stream>>>(s->dyn);
+    }
+    return 0;
+}
+
+int push_dyn(ssb_sim* s) {
+    long long h[3] = {s->steps_done, s->tab_step0, s->probe_step0};
+    SSB_CUDA(cudaMemcpyAsync(s->dyn, h, sizeof(h), cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ssb_last_error(void) { return g_err.c_str(); }
+const char* ssb_version(void) { return "sspslam_b200 0.1 (sm_100a)"; }
+
+int ssb_create(int device, int n_trials, ssb_sim** out) {
+    if (!out || n_trials <= 0) return fail(-1, "ssb_create: bad arguments");
+    int count = 0;
+    SSB_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(-1, "ssb_create: no such CUDA device");
+    SSB_CUDA(cudaSetDevice(device));
+    ssb_sim* s = new ssb_sim();
+    s->device = device;
+    s->n_trials = n_trials;
+    s->B = (n_trials + 31) / 32 * 32;
+    s->n_groups = s->B / 32;
+    SSB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    SSB_CUDA(cudaEventCreate(&s->ev_run0));
+    SSB_CUDA(cudaEventCreate(&s->ev_run1));
+    *out = s;
+    return 0;
+}
+
+int ssb_set_array(ssb_sim* s, const char* name, const void* data, size_t bytes) {
+    if (!s || !name || (!data && bytes)) return fail(-1, "ssb_set_array: bad arguments");
+    if (s->finalized) return fail(-1, "ssb_set_array: plan already finalized");
+    HostArray& a = s->arrays[name];
+    a.bytes.assign((const unsigned char*)data, (const unsigned char*)data + bytes);
+    return 0;
+}
+
+int ssb_set_scalar(ssb_sim* s, const char* name, double value) {
+    if (!s || !name) return fail(-1, "ssb_set_scalar: bad arguments");
+    s->scalars[name] = value;
+    return 0;
+}
+
+int ssb_finalize(ssb_sim* s) {
+    if (!s) return fail(-1, "ssb_finalize: null handle");
+    if (s->finalized) return fail(-1, "ssb_finalize: already finalized");
+    SSB_CUDA(cudaSetDevice(s->device));
+    s->nv = iscalar(s, "nv");
+    s->nf = iscalar(s, "nf");
+    s->nt = iscalar(s, "nt");
+    s->nn = iscalar(s, "nn");
+    s->n_act = iscalar(s, "n_act");
+    s->n_lenc = iscalar(s, "n_lenc");
+    s->n_ldec = iscalar(s, "n_ldec");
+    s->n_afilt = iscalar(s, "n_afilt");
+    s->n_probe = iscalar(s, "n_probe");
+    s->n_levels = (int)iscalar(s, "n_levels");
+    s->chunk_cap = (int)iscalar(s, "chunk_cap");
+    if (s->nv < 1 || s->chunk_cap < 1 || s->n_levels < 1) return fail(-1, "ssb_finalize: plan scalars missing");
+    const double dt = s->scalars.count("dt") ? s->scalars["dt"] : 0.001;
+
+    size_t cnt = 0;
+    if (upload_array(s, "csr_ptr", &s->d_csr_ptr)) return -2;
+    if (upload_array(s, "csr_idx", &s->d_csr_idx)) return -2;
+    if (upload_array(s, "csr_val", &s->d_csr_val)) return -2;
+    if (upload_array(s, "weights", &s->d_W)) return -2;
+    if (upload_array(s, "ens_small", &s->d_small, &cnt)) return -2;
+    s->n_small_total = (int)(cnt / 9);
+    if (upload_array(s, "ens_big", &s->d_big)) return -2;
+    if (upload_array(s, "dec", &s->d_dec)) return -2;
+    if (upload_array(s, "pes", &s->d_pes, &cnt)) return -2;
+    s->n_pes = (int)(cnt / 10);
+    if (upload_array(s, "cleanup", &s->d_cleanup)) return -2;
+    if (upload_array(s, "gate", &s->d_gate)) return -2;
+    if (upload_array(s, "lin_rows", &s->d_lin_rows, &cnt)) return -2;
+    s->n_lin = (int)(cnt / 3);
+    if (upload_array(s, "lin_ab", &s->d_lin_ab)) return -2;
+    if (upload_array(s, "ntypes", &s->d_ntypes)) return -2;
+    if (upload_array(s, "cleanup_s64", &s->d_s64)) return -2;
+    s->h_stages = host_ints(s, "stages");
+    s->h_big = host_ints(s, "ens_big");
+    s->h_dec = host_ints(s, "dec");
+    s->h_cleanup = host_ints(s, "cleanup");
+    s->h_pes = host_ints(s, "pes");
+    if ((int)s->h_stages.size() != s->n_levels * 10) return fail(-1, "ssb_finalize: stages array has wrong size");
+
+    const int B = s->B;
+    if (alloc_rows(&s->vec, s->nv, B)) return -2;
+    if (alloc_rows(&s->v, s->nn, B)) return -2;
+    if (alloc_rows(&s->ref, s->nn, B)) return -2;
+    if (alloc_rows(&s->act, s->n_act, B)) return -2;
+    if (alloc_rows(&s->lenc, s->n_lenc, B)) return -2;
+    if (alloc_rows(&s->ldec, s->n_ldec, B)) return -2;
+    if (alloc_rows(&s->afilt, 2 * s->n_afilt, B)) return -2;
+    if (alloc_rows(&s->tab, (long long)s->chunk_cap * std::max(1LL, s->nt), B)) return -2;
+    if (alloc_rows(&s->probe, (long long)s->chunk_cap * std::max(1LL, s->n_probe), B)) return -2;
+    SSB_CUDA(cudaMalloc((void**)&s->dyn, 4 * sizeof(long long)));
+    SSB_CUDA(cudaMemset(s->dyn, 0, 4 * sizeof(long long)));
+    {
+        std::vector<float> ones(B, 1.0f);
+        SSB_CUDA(cudaMemcpy(s->vec, ones.data(), B * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    const int n_cleanup = (int)(s->h_cleanup.size() / 6);
+    s->cleanups.resize(n_cleanup);
+    if (n_cleanup) {
+        SSB_CUDA(cudaMalloc((void**)&s->cidx, (size_t)n_cleanup * B * sizeof(int)));
+        SSB_CUDA(cudaMemset(s->cidx, 0, (size_t)n_cleanup * B * sizeof(int)));
+    }
+    size_t s64_off = 0;
+    const size_t s64_total = s->arrays.count("cleanup_s64") ? s->arrays["cleanup_s64"].bytes.size() / sizeof(double) : 0;
+    for (int i = 0; i < n_cleanup; ++i) {
+        const int* d = &s->h_cleanup[i * 6];
+        CleanupDev& cd = s->cleanups[i];
+        if (alloc_rows(&cd.cx, d[2], B)) return -2;
+        if (alloc_rows(&cd.pval, SSB_SCAN_PARTS * SSB_TOPK, B)) return -2;
+        if (alloc_rows(reinterpret_cast<float**>(&cd.pidx), SSB_SCAN_PARTS * SSB_TOPK, B)) return -2;
+        cd.idx = s->cidx + (size_t)i * B;
+        const size_t need = (size_t)d[0] * d[1];
+        if (s64_off + need <= s64_total) {
+            cd.s64 = s->d_s64 + s64_off;
+            s64_off += need;
+        }
+    }
+    // opt-in to large dynamic shared memory for very wide ensembles (d = 649)
+    cudaFuncSetAttribute(k_ens_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_cleanup_scan<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_cleanup_scan<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+
+    SsbCtx& c = s->ctx;
+    c.B = B;
+    c.nf = (int)s->nf;
+    c.nt = (int)s->nt;
+    c.n_probe = (int)s->n_probe;
+    c.n_afilt = (int)s->n_afilt;
+    c.dt = (float)dt;
+    c.vec = s->vec;
+    c.tab = s->tab;
+    c.v = s->v;
+    c.ref = s->ref;
+    c.act = s->act;
+    c.lenc = s->lenc;
+    c.ldec = s->ldec;
+    c.afilt = s->afilt;
+    c.probe = s->probe;
+    c.W = s->d_W;
+    c.csr_ptr = s->d_csr_ptr;
+    c.csr_idx = s->d_csr_idx;
+    c.csr_val = s->d_csr_val;
+    c.ntypes = s->d_ntypes;
+    c.dyn = s->dyn;
+    s->finalized = true;
+    SSB_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+int ssb_upload(ssb_sim* s, const char* name, size_t row0, size_t n_rows, const float* host) {
+    if (!s || !s->finalized || !host) return fail(-1, "ssb_upload: bad arguments");
+    ArenaRef a;
+    if (arena(s, name, &a)) return -3;
+    if ((long long)(row0 + n_rows) > a.rows) return fail(-1, "ssb_upload: rows out of range");
+    SSB_CUDA(cudaSetDevice(s->device));
+    SSB_CUDA(cudaMemcpyAsync(a.ptr + row0 * s->B, host, n_rows * s->B * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int ssb_download(ssb_sim* s, const char* name, size_t row0, size_t n_rows, float* host) {
+    if (!s || !s->finalized || !host) return fail(-1, "ssb_download: bad arguments");
+    ArenaRef a;
+    if (arena(s, name, &a)) return -3;
+    if ((long long)(row0 + n_rows) > a.rows) return fail(-1, "ssb_download: rows out of range");
+    SSB_CUDA(cudaSetDevice(s->device));
+    SSB_CUDA(cudaMemcpyAsync(host, a.ptr + row0 * s->B, n_rows * s->B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int ssb_set_tables(ssb_sim* s, const float* host, long long step0, int n_steps) {
+    if (!s || !s->finalized) return fail(-1, "ssb_set_tables: bad handle");
+    if (n_steps < 0 || n_steps > s->chunk_cap) return fail(-1, "ssb_set_tables: n_steps exceeds chunk_cap");
+    SSB_CUDA(cudaSetDevice(s->device));
+    if (s->nt > 0 && n_steps > 0) {
+        if (!host) return fail(-1, "ssb_set_tables: null host buffer");
+        SSB_CUDA(cudaMemcpyAsync(s->tab, host, (size_t)n_steps * s->nt * s->B * sizeof(float), cudaMemcpyHostToDevice,
+                                 s->stream));
+    }
+    s->tab_step0 = step0;
+    s->tab_steps = n_steps;
+    return 0;
+}
+
+int ssb_rebase_tables(ssb_sim* s, long long step0) {
+    if (!s || !s->finalized) return fail(-1, "ssb_rebase_tables: bad handle");
+    s->tab_step0 = step0;
+    return 0;
+}
+
+int ssb_run_steps(ssb_sim* s, int n_steps) {
+    if (!s || !s->finalized) return fail(-1, "ssb_run_steps: bad handle");
+    if (n_steps <= 0) return 0;
+    if (n_steps > s->chunk_cap) return fail(-1, "ssb_run_steps: n_steps exceeds chunk_cap (probe buffer)");
+    if (s->nt > 0 && (s->steps_done < s->tab_step0 || s->steps_done + n_steps > s->tab_step0 + s->tab_steps))
+        return fail(-4, "ssb_run_steps: resident input tables do not cover the requested steps");
+    SSB_CUDA(cudaSetDevice(s->device));
+    s->probe_step0 = s->steps_done;
+    if (push_dyn(s)) return -2;
+    SSB_CUDA(cudaEventRecord(s->ev_run0, s->stream));
+    for (int i = 0; i < n_steps; ++i) {
+        if (one_step(s)) return -2;
+    }
+    SSB_CUDA(cudaEventRecord(s->ev_run1, s->stream));
+    s->run_timed = true;
+    s->steps_done += n_steps;
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ssb_read_probes(ssb_sim* s, float* host, long long step0, int n_steps) {
+    if (!s || !s->finalized || !host) return fail(-1, "ssb_read_probes: bad arguments");
+    if (step0 < s->probe_step0 || step0 + n_steps > s->steps_done || n_steps < 0)
+        return fail(-4, "ssb_read_probes: steps not in the probe buffer");
+    if (s->n_probe == 0 || n_steps == 0) return 0;
+    SSB_CUDA(cudaSetDevice(s->device));
+    const size_t row = (size_t)s->n_probe * s->B;
+    SSB_CUDA(cudaMemcpyAsync(host, s->probe + (size_t)(step0 - s->probe_step0) * row, (size_t)n_steps * row * sizeof(float),
+                             cudaMemcpyDeviceToHost, s->stream));
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+long long ssb_n_steps(ssb_sim* s) { return s ? s->steps_done : -1; }
+int ssb_n_trials_padded(ssb_sim* s) { return s ? s->B : -1; }
+
+int ssb_sync(ssb_sim* s) {
+    if (!s) return fail(-1, "ssb_sync: null handle");
+    SSB_CUDA(cudaSetDevice(s->device));
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ssb_reset(ssb_sim* s) {
+    if (!s || !s->finalized) return fail(-1, "ssb_reset: bad handle");
+    SSB_CUDA(cudaSetDevice(s->device));
+    const size_t B = s->B;
+    SSB_CUDA(cudaMemsetAsync(s->vec + B, 0, (size_t)(s->nv - 1) * B * sizeof(float), s->stream));
+    SSB_CUDA(cudaMemsetAsync(s->v, 0, (size_t)std::max(1LL, s->nn) * B * sizeof(float), s->stream));
+    SSB_CUDA(cudaMemsetAsync(s->ref, 0, (size_t)std::max(1LL, s->nn) * B * sizeof(float), s->stream));
+    SSB_CUDA(cudaMemsetAsync(s->act, 0, (size_t)std::max(1LL, s->n_act) * B * sizeof(float), s->stream));
+    SSB_CUDA(cudaMemsetAsync(s->lenc, 0, (size_t)std::max(1LL, s->n_lenc) * B * sizeof(float), s->stream));
+    SSB_CUDA(cudaMemsetAsync(s->ldec, 0, (size_t)std::max(1LL, s->n_ldec) * B * sizeof(float), s->stream));
+    SSB_CUDA(cudaMemsetAsync(s->afilt, 0, (size_t)std::max(1LL, 2 * s->n_afilt) * B * sizeof(float), s->stream));
+    s->steps_done = 0;
+    s->probe_step0 = 0;
+    if (push_dyn(s)) return -2;
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+void ssb_destroy(ssb_sim* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    void* ptrs[] = {s->d_csr_ptr, s->d_csr_idx, s->d_csr_val, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
+                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_ntypes, s->d_s64, s->vec, s->tab, s->v, s->ref, s->act,
+                    s->lenc, s->ldec, s->afilt, s->probe, s->dyn, s->cidx};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (auto& cd : s->cleanups) {
+        if (cd.cx) cudaFree(cd.cx);
+        if (cd.pval) cudaFree(cd.pval);
+        if (cd.pidx) cudaFree(cd.pidx);
+    }
+    for (auto e : s->ev_pool) cudaEventDestroy(e);
+    if (s->ev_run0) cudaEventDestroy(s->ev_run0);
+    if (s->ev_run1) cudaEventDestroy(s->ev_run1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int ssb_set_profiling(ssb_sim* s, int on) {
+    if (!s) return fail(-1, "ssb_set_profiling: null handle");
+    if (collect_profile(s)) return -2;
+    s->profiling = on != 0;
+    for (int k = 0; k < K_NKINDS; ++k) {
+        s->kind_ms[k] = 0.f;
+        s->kind_launches[k] = 0;
+    }
+    return 0;
+}
+
+int ssb_last_run_ms(ssb_sim* s, float* ms) {
+    if (!s || !ms) return fail(-1, "ssb_last_run_ms: bad arguments");
+    if (!s->run_timed) return fail(-1, "ssb_last_run_ms: no run recorded");
+    SSB_CUDA(cudaSetDevice(s->device));
+    SSB_CUDA(cudaEventSynchronize(s->ev_run1));
+    SSB_CUDA(cudaEventElapsedTime(ms, s->ev_run0, s->ev_run1));
+    return 0;
+}
+
+int ssb_kernel_times(ssb_sim* s, float* ms_per_kind, long long* launches_per_kind, int n_kinds) {
+    if (!s) return fail(-1, "ssb_kernel_times: null handle");
+    if (collect_profile(s)) return -2;
+    for (int k = 0; k < n_kinds && k < K_NKINDS; ++k) {
+        if (ms_per_kind) ms_per_kind[k] = s->kind_ms[k];
+        if (launches_per_kind) launches_per_kind[k] = s->kind_launches[k];
+    }
+    return 0;
+}
+
+long long ssb_total_launches(ssb_sim* s) { return s ? s->total_launches : -1; }
+
+void* ssb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        g_err = "ssb_host_alloc: cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+
+void ssb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------ stand-alone SSP kernels
+int ssb_ssp_encode(int device, const double* a_scaled, const double* x, double* out, long long n_points, int n, int d) {
+    if (!a_scaled || !x || !out || n_points < 0 || n <= 0 || d <= 0) return fail(-1, "ssb_ssp_encode: bad arguments");
+    if (n_points == 0) return 0;
+    SSB_CUDA(cudaSetDevice(device));
+    double *dA = nullptr, *dx = nullptr, *dout = nullptr;
+    SSB_CUDA(cudaMalloc((void**)&dA, (size_t)d * n * sizeof(double)));
+    SSB_CUDA(cudaMalloc((void**)&dx, (size_t)n_points * n * sizeof(double)));
+    SSB_CUDA(cudaMalloc((void**)&dout, (size_t)n_points * d * sizeof(double)));
+    SSB_CUDA(cudaMemcpy(dA, a_scaled, (size_t)d * n * sizeof(double), cudaMemcpyHostToDevice));
+    SSB_CUDA(cudaMemcpy(dx, x, (size_t)n_points * n * sizeof(double), cudaMemcpyHostToDevice));
+    const long long max_grid = 1 << 30;
+    for (long long p0 = 0; p0 < n_points; p0 += max_grid) {
+        const long long np = std::min(max_grid, n_points - p0);
+        k_ssp_encode<<<(unsigned)np, 128, 2 * d * sizeof(double)>>>(dA, dx + p0 * n, dout + p0 * d, np, n, d);
+    }
+    SSB_CUDA(cudaGetLastError());
+    SSB_CUDA(cudaMemcpy(out, dout, (size_t)n_points * d * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dA);
+    cudaFree(dx);
+    cudaFree(dout);
+    return 0;
+}
+
+int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* queries, int* idx_out, long long n_q,
+                          long long n_samples, int d) {
+    if (!sample_ssps || !queries || !idx_out || n_q < 0 || n_samples <= 0 || d <= 0)
+        return fail(-1, "ssb_ssp_decode_argmax: bad arguments");
+    if (n_q == 0) return 0;
+    if (n_samples >= 0x7fffffff) return fail(-1, "ssb_ssp_decode_argmax: too many samples");
+    SSB_CUDA(cudaSetDevice(device));
+    const int dpad = (d + 3) / 4 * 4;
+    const int G = (int)n_samples;
+    // grid in float32 (padded rows) for the scan, float64 for the near-tie re-score
+    std::vector<float> s32((size_t)G * dpad, 0.f);
+    for (long long g = 0; g < G; ++g)
+        for (int k = 0; k < d; ++k) s32[(size_t)g * dpad + k] = (float)sample_ssps[(size_t)g * d + k];
+    float *dS32 = nullptr, *cx = nullptr, *pval = nullptr;
+    double *dS64 = nullptr, *dq = nullptr;
+    int *pidx = nullptr, *didx = nullptr;
+    const int B = (int)std::min<long long>((n_q + 31) / 32 * 32, 1 << 15);
+    SSB_CUDA(cudaMalloc((void**)&dS32, s32.size() * sizeof(float)));
+    SSB_CUDA(cudaMalloc((void**)&dS64, (size_t)G * d * sizeof(double)));
+    SSB_CUDA(cudaMalloc((void**)&dq, (size_t)n_q * d * sizeof(double)));
+    SSB_CUDA(cudaMalloc((void**)&cx, (size_t)dpad * B * sizeof(float)));
+    SSB_CUDA(cudaMalloc((void**)&pval, (size_t)SSB_SCAN_PARTS * SSB_TOPK * B * sizeof(float)));
+    SSB_CUDA(cudaMalloc((void**)&pidx, (size_t)SSB_SCAN_PARTS * SSB_TOPK * B * sizeof(int)));
+    SSB_CUDA(cudaMalloc((void**)&didx, (size_t)B * sizeof(int)));
+    SSB_CUDA(cudaMemcpy(dS32, s32.data(), s32.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SSB_CUDA(cudaMemcpy(dS64, sample_ssps, (size_t)G * d * sizeof(double), cudaMemcpyHostToDevice));
+    SSB_CUDA(cudaMemcpy(dq, queries, (size_t)n_q * d * sizeof(double), cudaMemcpyHostToDevice));
+    cudaFuncSetAttribute(k_cleanup_scan<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    int hdesc[6] = {G, d, dpad, 0, 0, 0};
+    int* ddesc = nullptr;
+    SSB_CUDA(cudaMalloc((void**)&ddesc, sizeof(hdesc)));
+    SSB_CUDA(cudaMemcpy(ddesc, hdesc, sizeof(hdesc), cudaMemcpyHostToDevice));
+    SsbCtx c;
+    memset(&c, 0, sizeof(c));
+    c.B = B;
+    ssb_sim tmp;  // only for the stream field used by the launcher
+    tmp.stream = nullptr;
+    CleanupDev cd;
+    cd.cx = cx;
+    cd.pval = pval;
+    cd.pidx = pidx;
+    for (long long q0 = 0; q0 < n_q; q0 += B) {
+        const long long nb = std::min<long long>(B, n_q - q0);
+        k_decode_prep<<<(B + 127) / 128, 128>>>(dq, cx, n_q, B, d, dpad, q0);
+        dispatch_scan(&tmp, false, dpad, B / 32, c, ddesc, dS32, cd);
+        // re-score against the float64 grid; cx holds the fp32 unit queries
+        k_cleanup_pick<<<(B + 127) / 128, 128>>>(B, d, dpad, cx, pval, pidx, dS64, dS32, nullptr, didx, dq, q0, n_q);
+        SSB_CUDA(cudaGetLastError());
+        SSB_CUDA(cudaMemcpy(idx_out + q0, didx, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    cudaFree(dS32);
+    cudaFree(dS64);
+    cudaFree(dq);
+    cudaFree(cx);
+    cudaFree(pval);
+    cudaFree(pidx);
+    cudaFree(didx);
+    cudaFree(ddesc);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,621 @@
+"""Lower a built network into the flat device plan executed by the sm_100a kernels.
+
+Host-side counterpart of SURVEY.md §7 step 4.  nengo's builder would emit thousands of
+tiny operators (Reset / Copy / DotInc / ElementwiseInc / SimProcess ...) for the
+SSP-SLAM graphs (App. A.6, App. B).  Here the *vector-level glue* is collapsed
+algebraically instead of being executed:
+
+* every value that exists at the start of a step or is produced by a heavy op is a
+  **source column**: the constant 1, input-table nodes, Lowpass filter states (old
+  value = one-step delay), decoded outputs of ensemble connections, outputs of the
+  device function nodes (grid clean-up, gated correction);
+* every value a heavy op consumes is a **sink row**: ensemble inputs, direct neuron
+  currents, filter inputs, function-node inputs, learning-rule inputs, probes.  Each
+  sink row is a sparse linear combination of source columns, obtained by composing
+  pass-through nodes, slices and transforms with ``scipy.sparse`` (so the 112x55
+  circular-convolution DFT matrices, ``to_Fourier`` / ``to_SSP`` etc. are folded into
+  CSR rows that the kernels evaluate in their prologues);
+* sinks are levelled by data dependency inside a step (level 0 needs only tables and
+  old filter states; OVC -> circular convolution is level 1, ...), giving the kernel
+  launch order.
+
+The per-trial arena uses ``[row][trial]`` layout everywhere (trial is the coalesced axis).
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+import scipy.sparse as sp
+
+from . import nengo_shim as ns
+from . import nodeops
+from .builder import BuiltModel
+
+TAB_BASE = 1 << 24          # CSR column ids >= TAB_BASE address the input-table row of this step
+SMALL_MAX_DIMS = 4
+SMALL_MAX_OUT = 8
+DEC_TILE = 8                # decoder output rows are padded to a multiple of this
+
+NT_LIF, NT_LIFRATE, NT_RELU = 0, 1, 2
+
+
+def _idx(key, size):
+    return np.atleast_1d(np.arange(size)[key])
+
+
+def _place(rows, n_rows, mat):
+    """Scatter the rows of ``mat`` to positions ``rows`` of an (n_rows x ncols) matrix."""
+    sel = sp.csr_matrix((np.ones(len(rows)), (rows, np.arange(len(rows)))), shape=(n_rows, len(rows)))
+    return sel @ mat
+
+
+def _apply_transform(transform, mat):
+    if transform is None:
+        return mat
+    t = np.asarray(transform, dtype=np.float64)
+    if t.ndim == 0:
+        return mat * float(t)
+    if t.ndim == 1:
+        return sp.diags(t) @ mat
+    return sp.csr_matrix(t) @ mat
+
+
+@dataclasses.dataclass
+class ProbeInfo:
+    probe: object
+    kind: str                 # "rows" | "weights" | "scaled_encoders"
+    row0: int = 0             # first row in the probe buffer
+    size: int = 0
+    period: int = 1
+    conn: object = None
+    ens: object = None
+
+
+class DevicePlan:
+    """Numpy arrays + scalars handed to the C-ABI (``ssb_set_array`` / ``ssb_set_scalar``)."""
+
+    def __init__(self):
+        self.arrays: dict[str, np.ndarray] = {}
+        self.scalars: dict[str, float] = {}
+        self.tables: list = []          # [(node, col0, size)]
+        self.probes: list[ProbeInfo] = []
+        self.ens_state: dict = {}       # ens -> (state_row0, n)
+        self.ens_act: dict = {}         # ens -> act_row0 (big ensembles only)
+        self.learned_enc: dict = {}     # ens -> (row0, n, dims)   rows are n*dims + k
+        self.learned_dec: dict = {}     # conn -> (row0, size_out, n) rows are j*n + i
+        self.static_dec: dict = {}      # conn -> (w_off, size_out, jpad, n) for big decoders
+        self.filters: dict = {}         # conn/probe -> (filter_row0, size)
+        self.launches: list = []        # human-readable launch order
+        self.stats: dict = {}
+
+
+class _Lowerer:
+    def __init__(self, network, model: BuiltModel):
+        self.net, self.model, self.dt = network, model, model.dt
+        self.nodes = network.all_nodes
+        self.ensembles = network.all_ensembles
+        self.conns = network.all_connections
+        self.probes = network.all_probes
+        self.owners = [network] + network.all_networks
+        self.incoming: dict = {}
+        for c in self.conns:
+            self.incoming.setdefault(c.post_obj, []).append(c)
+        self.plan = DevicePlan()
+
+    # ------------------------------------------------------------------ classification
+    def classify_nodes(self):
+        self.node_kind, self.node_op = {}, {}
+        for node in self.nodes:
+            out = node.output
+            if out is None:
+                kind = "pass"
+            elif isinstance(out, np.ndarray):
+                kind = "const"
+            elif node.size_in == 0:
+                kind = "table"
+            else:
+                op = nodeops.recognize(node, self.owners)
+                if op is None:
+                    raise NotImplementedError(
+                        f"{node!r}: Python callable with inputs is not a recognised device op "
+                        "(identity / grid clean-up / gated correction); the B200 backend has no host-callback path")
+                self.node_op[node] = op
+                kind = {"identity": "pass", "cleanup": "fn", "gate": "fn"}[op.kind]
+            self.node_kind[node] = kind
+
+    # ------------------------------------------------------------------ source columns
+    def enumerate_sources(self):
+        self.ncol = 1  # column 0 = constant one
+        self.col_kind = ["const"]
+        self.col_owner = [None]
+
+        def alloc(kind, owner, size):
+            c0 = self.ncol
+            self.ncol += size
+            self.col_kind += [kind] * size
+            self.col_owner += [owner] * size
+            return c0
+
+        self.tab_col, self.filt_col, self.dec_col, self.fn_col = {}, {}, {}, {}
+        for node in self.nodes:
+            if self.node_kind[node] == "table":
+                self.tab_col[node] = alloc("tab", node, node.size_out)
+        for conn in self.conns:
+            if conn.synapse is not None:
+                if isinstance(conn.post_obj, ns.Neurons) or isinstance(conn.pre_obj, ns.Neurons):
+                    raise NotImplementedError("filtered neuron-to-neuron connections are outside the hot path")
+                self.filt_col[conn] = alloc("filt", conn, conn.size_out)
+        for probe in self.probes:
+            if isinstance(probe.obj, (ns.Node, ns.Ensemble)) and probe.synapse is not None:
+                self.filt_col[probe] = alloc("filt", probe, probe.size_in)
+        # decoded outputs, grouped per ensemble so that small ensembles own one contiguous slot
+        self.ens_dec_conns = {e: [] for e in self.ensembles}
+        for conn in self.conns:
+            if isinstance(conn.pre_obj, ns.Ensemble):
+                self.ens_dec_conns[conn.pre_obj].append(conn)
+        for probe in self.probes:
+            if isinstance(probe.obj, ns.Ensemble) and probe.attr == "decoded_output":
+                self.ens_dec_conns[probe.obj].append(probe)
+        for ens in self.ensembles:
+            for c in self.ens_dec_conns[ens]:
+                size = c.size_out if isinstance(c, ns.Connection) else c.size_in
+                self.dec_col[c] = alloc("dec", c, size)
+        for node in self.nodes:
+            if self.node_kind[node] == "fn":
+                self.fn_col[node] = alloc("fn", node, node.size_out)
+
+    def _eye(self, c0, size):
+        return sp.csr_matrix((np.ones(size), (np.arange(size), c0 + np.arange(size))), shape=(size, self.ncol))
+
+    # ------------------------------------------------------------------ expressions
+    def expr_out(self, node):
+        memo = self._memo_out
+        if node in memo:
+            if memo[node] is None:
+                raise RuntimeError(f"algebraic loop through pass-through node {node!r} (no synapse in the cycle)")
+            return memo[node]
+        memo[node] = None
+        kind = self.node_kind[node]
+        if kind == "table":
+            m = self._eye(self.tab_col[node], node.size_out)
+        elif kind == "const":
+            vals = np.asarray(node.output, dtype=np.float64)
+            m = sp.csr_matrix((vals, (np.arange(vals.size), np.zeros(vals.size, dtype=int))),
+                              shape=(vals.size, self.ncol))
+        elif kind == "fn":
+            m = self._eye(self.fn_col[node], node.size_out)
+        else:
+            m = self.expr_in(node)
+        memo[node] = m
+        return m
+
+    def expr_in(self, obj):
+        size = obj.size_in
+        total = sp.csr_matrix((size, self.ncol))
+        for conn in self.incoming.get(obj, []):
+            total = total + _place(_idx(conn.post_slice, size), size, self.conn_value(conn))
+        return total.tocsr()
+
+    def conn_value(self, conn):
+        if conn.synapse is not None:
+            return self._eye(self.filt_col[conn], conn.size_out)
+        return self.weighted(conn)
+
+    def weighted(self, conn):
+        pre = conn.pre_obj
+        if isinstance(pre, ns.Ensemble):
+            return self._eye(self.dec_col[conn], conn.size_out)
+        if isinstance(pre, ns.Neurons):
+            raise NotImplementedError("connections from ens.neurons are outside the hot path")
+        src = self.expr_out(pre)
+        rows = _idx(conn.pre_slice, pre.size_out)
+        src = src[rows]
+        return _apply_transform(conn.transform, src).tocsr()
+
+    # ------------------------------------------------------------------ main
+    def lower(self, chunk_cap):
+        plan = self.plan
+        self.classify_nodes()
+        self.enumerate_sources()
+        self._memo_out = {}
+        dt = self.dt
+
+        # ---- sinks
+        ens_in, ens_jn, voja_rule, pes_rule = {}, {}, {}, {}
+        for ens in self.ensembles:
+            ens_in[ens] = self.expr_in(ens)
+            jn = []
+            for conn in self.incoming.get(ens.neurons, []):
+                if conn.transform is None or np.ndim(conn.transform) != 2 or conn.post_slice != slice(None):
+                    raise NotImplementedError("neuron-direct connections need a full (n x m) transform")
+                pre = conn.pre_obj
+                u = self.expr_out(pre)[_idx(conn.pre_slice, pre.size_out)]
+                G = self.model.params[ens].gain[:, None] * np.asarray(conn.transform, dtype=np.float64)
+                jn.append((u.tocsr(), G))
+            if jn:
+                ens_jn[ens] = (sp.vstack([u for u, _ in jn]).tocsr(), np.hstack([G for _, G in jn]))
+        for conn in self.conns:
+            rule = conn.learning_rule
+            if rule is None:
+                continue
+            lrt = rule.learning_rule_type
+            rin = self.expr_in(rule)
+            if isinstance(lrt, ns.Voja):
+                if lrt.post_synapse is not None:
+                    raise NotImplementedError("Voja with a post_synapse is outside the hot path")
+                one = sp.csr_matrix(([1.0], ([0], [0])), shape=(1, self.ncol))
+                voja_rule[conn.post_obj] = (conn, (one + rin).tocsr(), lrt)
+            elif isinstance(lrt, ns.PES):
+                pes_rule[conn] = (rin, lrt)
+            else:
+                raise NotImplementedError(type(lrt).__name__)
+        fn_in = {n: self.expr_in(n) for n in self.nodes if self.node_kind[n] == "fn"}
+        filt_in = {}
+        for key in self.filt_col:
+            if isinstance(key, ns.Connection):
+                filt_in[key] = self.weighted(key)
+            else:  # probe with synapse
+                filt_in[key] = self._probe_expr(key)
+
+        # ---- levels
+        INF = 1 << 20
+        col_level = np.zeros(self.ncol, dtype=np.int64)
+        pending_ens, pending_fn = set(self.ensembles), set(fn_in)
+        for c in pes_rule:
+            col_level[self.dec_col[c]:self.dec_col[c] + c.size_out] = INF
+        unresolved = np.zeros(self.ncol, dtype=bool)
+        for c, col0 in self.dec_col.items():
+            size = c.size_out if isinstance(c, ns.Connection) else c.size_in
+            if not (isinstance(c, ns.Connection) and c in pes_rule):
+                unresolved[col0:col0 + size] = True
+        for n, col0 in self.fn_col.items():
+            unresolved[col0:col0 + n.size_out] = True
+
+        def cols_of(*mats):
+            return np.unique(np.concatenate([m.indices for m in mats if m is not None] + [np.zeros(0, dtype=np.int64)]))
+
+        ens_level, fn_level = {}, {}
+        progress = True
+        while (pending_ens or pending_fn) and progress:
+            progress = False
+            for ens in list(pending_ens):
+                mats = [ens_in[ens]]
+                if ens in ens_jn:
+                    mats.append(ens_jn[ens][0])
+                if ens in voja_rule:
+                    mats.append(voja_rule[ens][1])
+                cols = cols_of(*mats).astype(np.int64)
+                if cols.size and unresolved[cols].any():
+                    continue
+                lvl = int(col_level[cols].max()) if cols.size else 0
+                if lvl >= INF:
+                    raise NotImplementedError("a PES-learned connection feeds an ensemble without a synapse")
+                ens_level[ens] = lvl
+                for c in self.ens_dec_conns[ens]:
+                    if isinstance(c, ns.Connection) and c in pes_rule:
+                        continue
+                    size = c.size_out if isinstance(c, ns.Connection) else c.size_in
+                    col_level[self.dec_col[c]:self.dec_col[c] + size] = lvl + 1
+                    unresolved[self.dec_col[c]:self.dec_col[c] + size] = False
+                pending_ens.discard(ens)
+                progress = True
+            for node in list(pending_fn):
+                cols = cols_of(fn_in[node]).astype(np.int64)
+                if cols.size and unresolved[cols].any():
+                    continue
+                lvl = int(col_level[cols].max()) if cols.size else 0
+                if lvl >= INF:
+                    raise NotImplementedError("a PES-learned connection feeds a function node without a synapse")
+                fn_level[node] = lvl
+                col_level[self.fn_col[node]:self.fn_col[node] + node.size_out] = lvl + 1
+                unresolved[self.fn_col[node]:self.fn_col[node] + node.size_out] = False
+                pending_fn.discard(node)
+                progress = True
+        if pending_ens or pending_fn:
+            raise RuntimeError("same-step dependency cycle between ensembles / function nodes")
+        n_levels = 1 + max(list(ens_level.values()) + list(fn_level.values()) + [0])
+
+        # ---- device column map
+        NF = sum(1 for k in self.col_kind if k == "filt")
+        dev_col = np.zeros(self.ncol, dtype=np.int64)
+        next_filt, next_tab = 1, 0
+        next_scratch = 1 + 2 * NF
+        for c in range(1, self.ncol):
+            k = self.col_kind[c]
+            if k == "filt":
+                dev_col[c] = next_filt
+                next_filt += 1
+            elif k == "tab":
+                dev_col[c] = TAB_BASE + next_tab
+                next_tab += 1
+            else:
+                dev_col[c] = next_scratch
+                next_scratch += 1
+        NV, NT = next_scratch, next_tab
+        self.dev_col = dev_col
+        for node, c0 in self.tab_col.items():
+            plan.tables.append((node, int(dev_col[c0] - TAB_BASE), node.size_out))
+        for key, c0 in self.filt_col.items():
+            size = key.size_out if isinstance(key, ns.Connection) else key.size_in
+            plan.filters[key] = (int(dev_col[c0] - 1), size)
+
+        # ---- CSR program
+        csr_ptr, csr_idx, csr_val = [0], [], []
+
+        def add_rows(mat):
+            mat = mat.tocsr()
+            mat.sum_duplicates()
+            mat.eliminate_zeros()
+            row0 = len(csr_ptr) - 1
+            for r in range(mat.shape[0]):
+                lo, hi = mat.indptr[r], mat.indptr[r + 1]
+                cols = mat.indices[lo:hi]
+                order = np.argsort(cols, kind="stable")
+                csr_idx.extend(dev_col[cols[order]].tolist())
+                csr_val.extend(mat.data[lo:hi][order].tolist())
+                csr_ptr.append(len(csr_idx))
+            return row0
+
+        # ---- weights + descriptors
+        W = []            # static float32 weights (shared by all trials)
+        w_len = 0
+
+        def add_w(arr, align=4):
+            nonlocal w_len
+            pad = (-w_len) % align
+            if pad:
+                W.append(np.zeros(pad, dtype=np.float32))
+                w_len += pad
+            off = w_len
+            a = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
+            W.append(a)
+            w_len += a.size
+            return off
+
+        ntypes, ntype_ids = [], {}
+
+        def ntype_id(nt):
+            if isinstance(nt, ns.LIF):
+                key = (NT_LIF, nt.tau_rc, nt.tau_ref, nt.min_voltage, nt.amplitude)
+            elif isinstance(nt, ns.LIFRate):
+                key = (NT_LIFRATE, nt.tau_rc, nt.tau_ref, 0.0, nt.amplitude)
+            elif isinstance(nt, ns.RectifiedLinear):
+                key = (NT_RELU, 0.0, 0.0, 0.0, nt.amplitude)
+            else:
+                raise NotImplementedError(f"neuron type {type(nt).__name__} is not supported by the B200 backend")
+            if key not in ntype_ids:
+                ntype_ids[key] = len(ntypes)
+                ntypes.append(key)
+            return ntype_ids[key]
+
+        small_desc = [[] for _ in range(n_levels)]
+        big_desc = [[] for _ in range(n_levels)]
+        dec_desc = [[] for _ in range(n_levels)]
+        pes_desc, cleanup_desc, gate_desc = [], [[] for _ in range(n_levels)], [[] for _ in range(n_levels)]
+        pes_trace, cleanup_s64 = [], [[] for _ in range(n_levels)]
+        nn = n_act = n_lenc = n_ldec = n_afilt = 0
+        n_small = n_big = 0
+
+        for ens in self.ensembles:
+            p = self.model.params[ens]
+            n, dims = ens.n_neurons, ens.dimensions
+            lvl = ens_level[ens]
+            outs = self.ens_dec_conns[ens]
+            nout = sum((c.size_out if isinstance(c, ns.Connection) else c.size_in) for c in outs)
+            has_pes = any(isinstance(c, ns.Connection) and c in pes_rule for c in outs)
+            is_small = (dims <= SMALL_MAX_DIMS and nout <= SMALL_MAX_OUT and ens not in voja_rule
+                        and ens not in ens_jn and not has_pes)
+            state0 = nn
+            nn += n
+            plan.ens_state[ens] = (state0, n)
+            tid = ntype_id(ens.neuron_type)
+            in_row0 = add_rows(ens_in[ens])
+            if is_small:
+                n_small += 1
+                decs = [self._dec_weights(c) for c in outs]  # each (size_out x n)
+                stride = 1 + dims + nout
+                stride += (-stride) % 4
+                packed = np.zeros((n, stride))
+                packed[:, 0] = p.bias
+                packed[:, 1:1 + dims] = p.scaled_encoders
+                if decs:
+                    packed[:, 1 + dims:1 + dims + nout] = np.vstack(decs).T
+                w_off = add_w(packed)
+                out_vec = int(dev_col[self.dec_col[outs[0]]]) if outs else 0
+                # decoded slots of one ensemble are contiguous by construction
+                small_desc[lvl].append([n, dims, nout, state0, w_off, in_row0, out_vec, tid, stride])
+                continue
+
+            n_big += 1
+            act0 = n_act
+            n_act += n
+            plan.ens_act[ens] = act0
+            dpad = dims + ((-dims) % 4)
+            flags = 0
+            voja_alpha = 0.0
+            voja_row = scale_off = 0
+            if ens in voja_rule:
+                conn, lrow, lrt = voja_rule[ens]
+                flags |= 1
+                enc_off = n_lenc
+                n_lenc += n * dims
+                plan.learned_enc[ens] = (enc_off, n, dims)
+                voja_alpha = lrt.learning_rate * dt
+                voja_row = add_rows(lrow)
+                scale_off = add_w(p.gain / ens.radius)
+            else:
+                enc = np.zeros((n, dpad))
+                enc[:, :dims] = p.scaled_encoders
+                enc_off = add_w(enc)
+            bias_off = add_w(p.bias)
+            jn_row0 = jn_m = jn_w = 0
+            if ens in ens_jn:
+                u, G = ens_jn[ens]
+                jn_row0, jn_m, jn_w = add_rows(u), u.shape[0], add_w(G)
+                flags |= 2
+            big_desc[lvl].append([n, dims, dpad, state0, act0, enc_off, bias_off, in_row0, tid, flags,
+                                  jn_row0, jn_m, jn_w, voja_row, scale_off,
+                                  int(np.float32(voja_alpha).view(np.int32))])
+            for c in outs:
+                size_out = c.size_out if isinstance(c, ns.Connection) else c.size_in
+                out_vec = int(dev_col[self.dec_col[c]])
+                if isinstance(c, ns.Connection) and c in pes_rule:
+                    rin, lrt = pes_rule[c]
+                    d_off = n_ldec
+                    n_ldec += size_out * n
+                    plan.learned_dec[c] = (d_off, size_out, n)
+                    a_off = n_afilt
+                    n_afilt += n
+                    kinds = {self.col_kind[cc] for cc in np.unique(rin.indices)}
+                    if not kinds <= {"filt", "const"}:
+                        raise NotImplementedError(
+                            "PES error input must arrive through a synapse (the delta of step t-1 is rebuilt "
+                            "from the previous filter values)")
+                    err_row0 = add_rows(rin)
+                    alpha = -lrt.learning_rate * dt / n
+                    if lrt.pre_synapse is None:
+                        decay = 0.0
+                    else:
+                        decay = float(np.exp(-dt / lrt.pre_synapse.tau))
+                    pes_trace.append((act0, a_off, n, np.float32(decay), np.float32(1.0 - decay)))
+                    pes_desc.append([n, size_out, d_off, a_off, act0, err_row0, out_vec,
+                                     int(np.float32(alpha).view(np.int32)),
+                                     int(np.float32(decay).view(np.int32)),
+                                     int(np.float32(1.0 - decay).view(np.int32))])
+                else:
+                    jpad = size_out + ((-size_out) % DEC_TILE)
+                    Wd = np.zeros((n, jpad))
+                    Wd[:, :size_out] = self._dec_weights(c).T
+                    w_off = add_w(Wd)
+                    plan.static_dec[c] = (w_off, size_out, jpad, n)
+                    dec_desc[lvl].append([n, size_out, jpad, act0, w_off, out_vec])
+
+        for node, mat in fn_in.items():
+            op = self.node_op[node]
+            lvl = fn_level[node]
+            in_row0 = add_rows(mat)
+            out_vec = int(dev_col[self.fn_col[node]])
+            if op.kind == "cleanup":
+                S = op.sample_ssps
+                G, d = S.shape
+                dpad = d + ((-d) % 4)
+                Sp = np.zeros((G, dpad))
+                Sp[:, :d] = S
+                s_off = add_w(Sp)
+                cleanup_desc[lvl].append([G, d, dpad, s_off, in_row0, out_vec])
+                cleanup_s64[lvl].append(np.ascontiguousarray(S, dtype=np.float64).reshape(-1))
+            else:
+                gate_desc[lvl].append([op.d, in_row0, out_vec,
+                                       int(np.float32(op.shift_rate).view(np.int32)),
+                                       int(np.float32(op.update_thres).view(np.int32)),
+                                       int(np.float32(op.atol).view(np.int32))])
+
+        # ---- final stage rows: filters then probes
+        lin_rows, lin_ab = [], []
+        for key, mat in filt_in.items():
+            f0, size = plan.filters[key]
+            tau = key.synapse.tau
+            a64 = np.exp(-dt / tau)
+            a, b = np.float32(a64), np.float32(1.0 - a64)
+            r0 = add_rows(mat)
+            if mat.shape[0] != size:
+                raise AssertionError("filter size mismatch")
+            for i in range(size):
+                lin_rows.append([r0 + i, 0, f0 + i])
+                lin_ab.append([a, b])
+        for act0, a_off, n, a, b in pes_trace:  # PES pre-synaptic activity traces (Lowpass of the spikes)
+            for i in range(n):
+                lin_rows.append([act0 + i, 2, a_off + i])
+                lin_ab.append([a, b])
+        n_probe_rows = 0
+        for probe in self.probes:
+            period = 1 if probe.sample_every is None else int(round(probe.sample_every / dt))
+            obj = probe.obj
+            if isinstance(obj, (ns.Node, ns.Ensemble)):
+                if probe in self.filt_col:
+                    mat = self._eye(self.filt_col[probe], probe.size_in)
+                else:
+                    mat = self._probe_expr(probe)
+                r0 = add_rows(mat)
+                info = ProbeInfo(probe, "rows", n_probe_rows, probe.size_in, period)
+                for i in range(probe.size_in):
+                    lin_rows.append([r0 + i, 1, n_probe_rows + i])
+                    lin_ab.append([0.0, 1.0])
+                n_probe_rows += probe.size_in
+            elif isinstance(obj, ns.Connection) and probe.attr == "weights":
+                if obj not in plan.learned_dec:
+                    raise NotImplementedError("'weights' probes are supported on PES-learned connections")
+                info = ProbeInfo(probe, "weights", period=period, conn=obj)
+            elif isinstance(obj, ns.LearningRule) and probe.attr == "scaled_encoders":
+                info = ProbeInfo(probe, "scaled_encoders", period=period, ens=obj.connection.post_obj)
+            else:
+                raise NotImplementedError(f"probe {probe!r} is outside the hot path")
+            plan.probes.append(info)
+
+        # every probe row is written each step; make sure late (PES) columns are only used there
+        # ---- assemble
+        def arr(rows, width):
+            return np.asarray(rows, dtype=np.int32).reshape(-1, width)
+
+        stages = []  # per level counts/offsets into the concatenated descriptor arrays
+        cat = {k: [] for k in ("small", "big", "dec", "cleanup", "gate")}
+        for lvl in range(n_levels):
+            # heavy-first ordering inside a launch evens out the tail
+            small_desc[lvl].sort(key=lambda r: -r[0] * (r[1] + r[2] + 8))
+            entry = []
+            for name, lst in (("small", small_desc[lvl]), ("big", big_desc[lvl]), ("dec", dec_desc[lvl]),
+                              ("cleanup", cleanup_desc[lvl]), ("gate", gate_desc[lvl])):
+                entry += [len(cat[name]), len(lst)]
+                cat[name] += lst
+            stages.append(entry)
+        plan.arrays.update({
+            "csr_ptr": np.asarray(csr_ptr, dtype=np.int32),
+            "csr_idx": np.asarray(csr_idx, dtype=np.int32),
+            "csr_val": np.asarray(csr_val, dtype=np.float32),
+            "weights": np.concatenate(W) if W else np.zeros(4, dtype=np.float32),
+            "ens_small": arr(cat["small"], 9),
+            "ens_big": arr(cat["big"], 16),
+            "dec": arr(cat["dec"], 6),
+            "pes": arr(pes_desc, 10),
+            "cleanup": arr(cat["cleanup"], 6),
+            "gate": arr(cat["gate"], 6),
+            "lin_rows": arr(lin_rows, 3),
+            "lin_ab": np.asarray(lin_ab, dtype=np.float32).reshape(-1, 2),
+            "stages": arr(stages, 10),
+            "ntypes": np.asarray(ntypes, dtype=np.float32).reshape(-1, 5),
+            "cleanup_s64": np.concatenate([a for lvl in cleanup_s64 for a in lvl] + [np.zeros(0)]),
+        })
+        plan.cleanup_nodes = [n for lvl in range(n_levels) for n in fn_in
+                              if self.node_op[n].kind == "cleanup" and fn_level[n] == lvl]
+        plan.scalars.update(dict(dt=dt, nv=NV, nf=NF, nt=NT, nn=nn, n_act=n_act, n_lenc=n_lenc, n_ldec=n_ldec,
+                                 n_afilt=n_afilt, n_probe=n_probe_rows, n_levels=n_levels, chunk_cap=chunk_cap))
+        n_static = int(sum(a.size for a in W))
+        plan.stats = dict(n_neurons=nn, n_filter_states=NF, n_learned=n_lenc + n_ldec, n_static_weights=n_static,
+                          n_table_words=NT, n_probe_words=n_probe_rows, n_small=n_small, n_big=n_big,
+                          n_levels=n_levels, csr_nnz=len(csr_idx), n_afilt=n_afilt, n_act=n_act)
+        return plan
+
+    def _dec_weights(self, c):
+        if isinstance(c, ns.Connection):
+            return np.asarray(self.model.params[c].weights, dtype=np.float64)
+        return np.asarray(self.model.probe_conns[c], dtype=np.float64)
+
+    def _probe_expr(self, probe):
+        obj = probe.obj
+        if isinstance(obj, ns.Ensemble):
+            return self._eye(self.dec_col[probe], probe.size_in)
+        return self.expr_out(obj)[_idx(probe.slice, obj.size_out)].tocsr()
+
+
+def lower(network, model: BuiltModel, chunk_cap=256) -> DevicePlan:
+    """Network + built parameters -> :class:`DevicePlan`."""
+    return _Lowerer(network, model).lower(chunk_cap)
+
+
+def algorithmic_bytes_per_trial_step(stats, per_trial_weights=False):
+    """SURVEY.md §8(d) traffic model (fp32): state R+W, filters R+W, learned R+W, inputs, probes."""
+    b = 16 * stats["n_neurons"] + 8 * (stats["n_filter_states"] + stats["n_afilt"]) + 8 * stats["n_learned"]
+    if per_trial_weights:
+        b += 4 * (stats["n_static_weights"] + stats["n_neurons"])
+    b += 4 * stats["n_table_words"] + 4 * stats["n_probe_words"]
+    return int(b)

@@ -1,0 +1,148 @@
+"""Synthetic workloads that follow the reference drivers (``experiments/run_pathint.py``,
+``run_slam.py``): random 2-D paths, R_d landmarks, hexagonal SSP space,
+the network declaration and per-trial input tables.  Used by ``bench.py``, ``smoke()``
+and the GPU tests (the GPU box has no reference checkout)."""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+
+from . import nengo_shim as nengo
+from . import networks, inputs
+from .sspspace import HexagonalSSPSpace, SPSpace
+
+
+@dataclasses.dataclass
+class Scenario:
+    network: object
+    probe: object
+    trial_inputs: dict
+    ssp_space: object
+    paths: np.ndarray          # [n_trials, T, dim]
+    real_ssp: np.ndarray       # [n_trials, T, d]
+    extra: dict
+    dt: float = 0.001
+
+
+def _neuron_type(name):
+    return {"lif": nengo.LIF, "lifrate": nengo.LIFRate, "relu": nengo.RectifiedLinear}[name]()
+
+
+def make_space(domain_dim=2, ssp_dim=55, length_scale=0.2, radius=1.0, backend="host"):
+    bounds = radius * np.tile([-1.0, 1.0], (domain_dim, 1))
+    return HexagonalSSPSpace(domain_dim, ssp_dim=ssp_dim, domain_bounds=bounds, length_scale=length_scale,
+                             rng=np.random.default_rng(0), backend=backend)
+
+
+def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0, limit=0.1, seed=0,
+                 neuron_type="lif", dt=0.001, tau=0.05):
+    """``run_pathint.py`` workload; trial i uses path seed ``seed + 1000*i``."""
+    space = make_space(2, ssp_dim)
+    d = space.ssp_dim
+    paths, ssps, tabs = [], [], []
+    scale = None
+    for i in range(n_trials):
+        path = inputs.random_path(T, dt, limit, seed + 1000 * i, 2)
+        vels = inputs.velocities(path, dt)
+        if scale is None:
+            scale = inputs.velocity_scale(space.phase_matrix, vels)   # shared static weights => one scale
+        real = space.encode_host(path)
+        tabs.append(inputs.pathint_tables(real, vels * scale, n_steps, dt))
+        paths.append(path[:n_steps])
+        ssps.append(real[:n_steps])
+    vel0, init0 = tabs[0]["vel"], tabs[0]["init"]
+    model = nengo.Network(seed=seed)
+    model.config[nengo.Ensemble].neuron_type = _neuron_type(neuron_type)
+    with model:
+        vel_in = nengo.Node(lambda t: vel0[int(round(t / dt)) - 1], label="vel_input")
+        init = nengo.Node(lambda t: init0[int(round(t / dt)) - 1], label="init_state")
+        pi = networks.PathIntegration(space, pi_n_neurons, tau, scaling_factor=scale, stable=True,
+                                      solver_weights=False)
+        nengo.Connection(vel_in, pi.velocity_input, synapse=None)
+        nengo.Connection(init, pi.input, synapse=None)
+        probe = nengo.Probe(pi.output, synapse=0.05)
+    trial_inputs = {vel_in: np.stack([t["vel"] for t in tabs]), init: np.stack([t["init"] for t in tabs])}
+    return Scenario(model, probe, trial_inputs, space, np.stack(paths), np.stack(ssps),
+                    dict(pathint=pi, vel_scale=scale), dt)
+
+
+def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neurons=970, circonv_n_neurons=100,
+              n_landmarks=50, view_rad=0.2, T=200.0, limit=0.1, seed=0, dt=0.001, length_scale=0.2,
+              shift_rate=0.2, update_thres=0.2, neuron_type="lif", weights_probe=False, view=False,
+              distinct_tables=None):
+    """``run_slam.py`` (or ``run_slamview.py`` when ``view``) workload, batched over trials.
+
+    ``distinct_tables``: synthesise only that many distinct trials' tables and tile them
+    over the batch (bench warm-up economy); state/voltages still differ per trial."""
+    space = make_space(2, ssp_dim, length_scale)
+    d = space.ssp_dim
+    lm_space = SPSpace(n_landmarks, d, seed=seed)
+    n_distinct = n_trials if distinct_tables is None else min(n_trials, distinct_tables)
+    paths, ssps, tabs = [], [], []
+    scale = None
+    for i in range(n_distinct):
+        s_i = seed + 1000 * i
+        path = inputs.random_path(T, dt, limit, s_i, 2)[:max(n_steps + 2, 4)]
+        vels = inputs.velocities(path, dt)
+        if scale is None:
+            scale = inputs.velocity_scale(space.phase_matrix, inputs.velocities(inputs.random_path(T, dt, limit, seed, 2), dt))
+        obj_locs = 1.8 * (inputs.rd_sampling(n_landmarks, 2, seed=s_i) - 0.5)
+        vec_to_lm = obj_locs[None, :, :] - path[:, None, :]
+        real = space.encode_host(path)
+        if view:
+            # run_slamview.py feeds a local-view vector; here: superposed landmark SPs bound with
+            # their displacement SSPs would need the driver's view code — use the SP sum (key) directly
+            tb = inputs.slam_tables(space.encode_host, lm_space.vectors, vels * scale, vec_to_lm, view_rad, n_steps, dt,
+                                    real_ssp=real, none_in_view_value=1.0)
+        else:
+            tb = inputs.slam_tables(space.encode_host, lm_space.vectors, vels * scale, vec_to_lm, view_rad, n_steps, dt,
+                                    real_ssp=real)
+        tabs.append(tb)
+        paths.append(path[:n_steps])
+        ssps.append(real[:n_steps])
+    t0 = tabs[0]
+
+    def tab_fn(name):
+        arr = t0[name]
+        return lambda t: arr[int(round(t / dt)) - 1]
+
+    np.random.seed(seed)  # OVC encoders come from the global stream (slam.py:206)
+    model = nengo.Network(seed=seed)
+    model.config[nengo.Ensemble].neuron_type = _neuron_type(neuron_type)
+    with model:
+        vel_in = nengo.Node(tab_fn("vel"), label="vel_input")
+        init = nengo.Node(tab_fn("init"), label="init_state")
+        lm_id = nengo.Node(tab_fn("lm_sp"), label="lm_sp_input")
+        is_lm = nengo.Node(tab_fn("nolm"), label="lm_in_view_input")
+        if view:
+            slam = networks.SLAMViewNetwork(space, lm_space, view_rad, n_landmarks, pi_n_neurons, mem_n_neurons,
+                                            circonv_n_neurons, tau_pi=0.05, update_thres=update_thres,
+                                            vel_scaling_factor=scale, shift_rate=0.02, voja_learning_rate=5e-4,
+                                            pes_learning_rate=1e-3)
+            nengo.Connection(lm_id, slam.view_input, synapse=None)
+            table_nodes = {"vel": vel_in, "init": init, "lm_sp": lm_id, "nolm": is_lm}
+        else:
+            lm_vec = nengo.Node(tab_fn("lmvec_ssp"), label="lm_vecssp_input")
+            slam = networks.SLAMNetwork(space, lm_space, view_rad, n_landmarks, pi_n_neurons, mem_n_neurons,
+                                        circonv_n_neurons, tau_pi=0.05, update_thres=update_thres,
+                                        vel_scaling_factor=scale, shift_rate=shift_rate, voja_learning_rate=1e-4,
+                                        pes_learning_rate=5e-3, intercept=0.1, seed=seed)
+            nengo.Connection(lm_vec, slam.landmark_vec_ssp, synapse=None)
+            nengo.Connection(lm_id, slam.landmark_id_input, synapse=None)
+            table_nodes = {"vel": vel_in, "init": init, "lm_sp": lm_id, "nolm": is_lm, "lmvec_ssp": lm_vec}
+        nengo.Connection(is_lm, slam.no_landmark_in_view, synapse=None)
+        nengo.Connection(vel_in, slam.velocity_input, synapse=None)
+        nengo.Connection(init, slam.pathintegrator.input, synapse=None)
+        probe = nengo.Probe(slam.pathintegrator.output, synapse=0.05)
+        wprobe = None
+        if weights_probe:
+            wprobe = nengo.Probe(slam.assomemory.conn_out, "weights", sample_every=n_steps * dt)
+    reps = -(-n_trials // n_distinct)
+    trial_inputs = {}
+    for name, node in table_nodes.items():
+        stacked = np.stack([t[name] for t in tabs])
+        trial_inputs[node] = np.tile(stacked, (reps, 1, 1))[:n_trials]
+    paths = np.tile(np.stack(paths), (reps, 1, 1))[:n_trials]
+    ssps = np.tile(np.stack(ssps), (reps, 1, 1))[:n_trials]
+    return Scenario(model, probe, trial_inputs, space, paths, ssps,
+                    dict(slam=slam, vel_scale=scale, weights_probe=wprobe, lm_space=lm_space), dt)

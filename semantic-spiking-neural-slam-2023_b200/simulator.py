@@ -1,0 +1,329 @@
+"""``Simulator(network, dt)`` — drop-in for ``nengo.Simulator`` on the SSP-SLAM graphs.
+
+Mirrors the surface the reference drivers use:
+``experiments/run_slam.py:198-199`` (construction), ``:232-233`` (``with sim: sim.run(T)``),
+``:243,250`` (``sim.trange()``, ``sim.data[probe]`` read *after* the ``with`` block),
+``:265-266`` (``sim.data[Probe(conn,'weights')]``, ``sim.data[ensemble]``), plus
+``run_steps`` / ``step`` / ``reset`` / ``n_steps`` / ``time`` / ``dt`` from nengo's convention.
+
+Batching extension (not in the reference, which has no batch axis):
+``Simulator(network, n_trials=B, trial_inputs={node: array[B, T, size]}, trial_seeds=[...])``
+runs B independent trials that share the static weights; learned PES/Voja matrices and
+all state are per trial.  ``sim.data[probe]`` then has a leading trial axis.
+
+Everything that is stepped runs in the CUDA library behind ``include/sspslam_b200.h``;
+if the library or a GPU is missing, construction raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import cabi, lowering
+from . import nengo_shim as ns
+from .builder import build_model, BuiltModel
+
+
+class _SimData:
+    def __init__(self, sim):
+        self._sim = sim
+
+    def __getitem__(self, key):
+        sim = self._sim
+        if key in sim._probe_infos:
+            return sim._probe_array(key)
+        if key in sim.model.params:
+            return sim.model.params[key]
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return key in self._sim._probe_infos or key in self._sim.model.params
+
+    def keys(self):
+        return list(self._sim._probe_infos) + list(self._sim.model.params)
+
+
+class Simulator:
+    def __init__(self, network, dt=0.001, seed=None, model: BuiltModel | None = None, progress_bar=True,
+                 optimize=True, n_trials=None, trial_inputs=None, trial_seeds=None, device=0, chunk_steps=256):
+        self.network = network
+        self.dt = float(dt)
+        self.closed = False
+        self._lib = cabi.load()  # raises if the CUDA library has not been built
+        self.model = model if model is not None else build_model(network, dt=self.dt, seed=seed)
+        self._batched = n_trials is not None
+        self.n_trials = int(n_trials) if self._batched else 1
+        self.chunk_steps = int(chunk_steps)
+        self.plan = lowering.lower(network, self.model, chunk_cap=self.chunk_steps)
+        self._trial_inputs = dict(trial_inputs or {})
+        if trial_seeds is None:
+            trial_seeds = [None] + list(range(self.n_trials - 1)) if self._batched else [None]
+        if len(trial_seeds) != self.n_trials:
+            raise ValueError("trial_seeds must have one entry per trial")
+        self.trial_seeds = list(trial_seeds)
+        for node, arr in self._trial_inputs.items():
+            arr = np.asarray(arr)
+            if arr.ndim != 3 or arr.shape[0] != self.n_trials or arr.shape[2] != node.size_out:
+                raise ValueError(f"trial_inputs[{node!r}] must have shape (n_trials, n_steps, {node.size_out})")
+
+        import ctypes as C
+        handle = C.c_void_p()
+        cabi.check(self._lib.ssb_create(int(device), self.n_trials, C.byref(handle)), "ssb_create")
+        self._h = handle
+        self._keep = []
+        for name, arr in self.plan.arrays.items():
+            a = np.ascontiguousarray(arr)
+            self._keep.append(a)
+            cabi.check(self._lib.ssb_set_array(self._h, name.encode(), cabi._ptr(a), a.nbytes), f"set_array {name}")
+        for name, val in self.plan.scalars.items():
+            cabi.check(self._lib.ssb_set_scalar(self._h, name.encode(), float(val)), f"set_scalar {name}")
+        cabi.check(self._lib.ssb_finalize(self._h), "ssb_finalize")
+        self.B = int(self._lib.ssb_n_trials_padded(self._h))
+        self._nt = int(self.plan.scalars["nt"])
+        self._np = int(self.plan.scalars["n_probe"])
+        self._tab_buf = cabi.PinnedBuffer(max(1, self.chunk_steps * self._nt * self.B))
+        self._probe_buf = cabi.PinnedBuffer(max(1, self.chunk_steps * self._np * self.B))
+        self._probe_infos = {info.probe: info for info in self.plan.probes}
+        self._n_steps = 0
+        self._init_state()
+
+    # ------------------------------------------------------------------ state
+    def _rows(self, per_trial):
+        """[n_trials, rows] (or [rows] broadcast) -> float32 [rows, B] with zero padding."""
+        a = np.asarray(per_trial, dtype=np.float32)
+        if a.ndim == 1:
+            a = np.broadcast_to(a[None, :], (self.n_trials, a.shape[0]))
+        out = np.zeros((a.shape[1], self.B), dtype=np.float32)
+        out[:, :self.n_trials] = a.T
+        return out
+
+    def _upload(self, arena, row0, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        cabi.check(self._lib.ssb_upload(self._h, arena.encode(), int(row0), int(rows.shape[0]), cabi._ptr(rows)),
+                   f"upload {arena}")
+
+    def _download(self, arena, row0, n_rows):
+        out = np.empty((int(n_rows), self.B), dtype=np.float32)
+        cabi.check(self._lib.ssb_download(self._h, arena.encode(), int(row0), int(n_rows), cabi._ptr(out)),
+                   f"download {arena}")
+        return out
+
+    def _init_state(self):
+        m, plan = self.model, self.plan
+        nn = int(plan.scalars["nn"])
+        if nn:
+            v0 = np.zeros((nn, self.B), dtype=np.float32)
+            for ens, (row0, n) in plan.ens_state.items():
+                v0[row0:row0 + n, :self.n_trials] = m.initial_voltages(ens, self.trial_seeds).T
+                if self.B > self.n_trials:
+                    v0[row0:row0 + n, self.n_trials:] = v0[row0:row0 + n, :1]
+            self._upload("v", 0, v0)
+        for ens, (row0, n, dims) in plan.learned_enc.items():
+            self._upload("lenc", row0, self._rows(m.params[ens].scaled_encoders.reshape(-1)))
+        for conn, (row0, size_out, n) in plan.learned_dec.items():
+            self._upload("ldec", row0, self._rows(np.asarray(m.params[conn].weights).reshape(-1)))
+        self._probe_rows = []      # list of [steps, n_probe, n_trials] float32 chunks
+        self._snap = {info.probe: [] for info in plan.probes if info.kind != "rows"}
+        self._table_cache = {}
+
+    # ------------------------------------------------------------------ nengo surface
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self):
+        """Release device memory; probe data stays readable (run_slam.py:242-252)."""
+        if not self.closed:
+            self.closed = True
+            if self._h:
+                self._launches_at_close = int(self._lib.ssb_total_launches(self._h))
+                self._lib.ssb_sync(self._h)
+                self._lib.ssb_destroy(self._h)
+                self._h = None
+            self._tab_buf.free()
+            self._probe_buf.free()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_steps(self):
+        return self._n_steps
+
+    @property
+    def time(self):
+        return self._n_steps * self.dt
+
+    @property
+    def data(self):
+        return _SimData(self)
+
+    def trange(self, sample_every=None, dt=None):
+        period = 1 if sample_every is None else int(round(sample_every / self.dt))
+        n = self._n_steps // period
+        return self.dt * period * np.arange(1, n + 1)
+
+    def run(self, time_in_seconds, progress_bar=None):
+        if time_in_seconds < 0:
+            raise ValueError("run time must be positive")
+        self.run_steps(int(np.round(float(time_in_seconds) / self.dt)))
+
+    def step(self):
+        self.run_steps(1)
+
+    def reset(self, seed=None):
+        self._check_open()
+        cabi.check(self._lib.ssb_reset(self._h), "ssb_reset")
+        self._n_steps = 0
+        self._init_state()
+
+    def _check_open(self):
+        if self.closed:
+            raise ns.exceptions.SimulatorClosed("Simulator is closed")
+
+    # ------------------------------------------------------------------ input tables
+    def _node_table(self, node, step0, n):
+        """Values of a ``t``-only node for steps step0+1 .. step0+n -> [n_trials|1, n, size]."""
+        if node in self._trial_inputs:
+            arr = np.asarray(self._trial_inputs[node])
+            if step0 + n > arr.shape[1]:
+                raise ValueError(f"trial_inputs[{node!r}] holds {arr.shape[1]} steps, need {step0 + n}")
+            return arr[:, step0:step0 + n, :]
+        out = np.empty((1, n, node.size_out), dtype=np.float64)
+        fn = node.output
+        for i in range(n):
+            t = (step0 + i + 1) * self.dt   # nengo: time = step * dt after the increment (App. A.1)
+            out[0, i] = np.asarray(fn(t), dtype=np.float64).reshape(-1)
+        if not np.all(np.isfinite(out)):
+            raise ns.exceptions.SimulationError(f"{node!r} returned a non-finite value")
+        return out
+
+    def _fill_tables(self, step0, n):
+        if self._nt == 0:
+            return
+        buf = self._tab_buf.array[:n * self._nt * self.B].reshape(n, self._nt, self.B)
+        for node, col0, size in self.plan.tables:
+            vals = self._node_table(node, step0, n)              # [T|1, n, size]
+            block = np.transpose(vals, (1, 2, 0))                 # [n, size, T|1]
+            buf[:, col0:col0 + size, :self.n_trials] = block
+            if self.B > self.n_trials:
+                buf[:, col0:col0 + size, self.n_trials:] = 0.0
+
+    # ------------------------------------------------------------------ stepping
+    def run_steps(self, n_steps, progress_bar=None):
+        self._check_open()
+        n_steps = int(n_steps)
+        lib = self._lib
+        periods = [info.period for info in self.plan.probes if info.kind != "rows"]
+        done = 0
+        while done < n_steps:
+            n = min(self.chunk_steps, n_steps - done)
+            for p in periods:  # stop exactly on snapshot steps of weight / encoder probes
+                to_next = p - (self._n_steps % p)
+                n = min(n, to_next)
+            self._fill_tables(self._n_steps, n)
+            cabi.check(lib.ssb_set_tables(self._h, self._tab_buf.ptr, self._n_steps, n), "ssb_set_tables")
+            cabi.check(lib.ssb_run_steps(self._h, n), "ssb_run_steps")
+            if self._np:
+                cabi.check(lib.ssb_read_probes(self._h, self._probe_buf.ptr, self._n_steps, n), "ssb_read_probes")
+                chunk = self._probe_buf.array[:n * self._np * self.B].reshape(n, self._np, self.B)
+                self._probe_rows.append(chunk[:, :, :self.n_trials].copy())
+            else:
+                cabi.check(lib.ssb_sync(self._h), "ssb_sync")
+            self._n_steps += n
+            done += n
+            for info in self.plan.probes:
+                if info.kind != "rows" and self._n_steps % info.period == 0:
+                    self._snap[info.probe].append(self._snapshot(info))
+
+    def _snapshot(self, info):
+        if info.kind == "weights":
+            row0, size_out, n = self.plan.learned_dec[info.conn]
+            w = self._download("ldec", row0, size_out * n)[:, :self.n_trials]
+            return w.T.reshape(self.n_trials, size_out, n).astype(np.float64)
+        row0, n, dims = self.plan.learned_enc[info.ens]
+        e = self._download("lenc", row0, n * dims)[:, :self.n_trials]
+        return e.T.reshape(self.n_trials, n, dims).astype(np.float64)
+
+    def _probe_array(self, probe):
+        info = self._probe_infos[probe]
+        if info.kind == "rows":
+            if self._probe_rows:
+                allrows = np.concatenate(self._probe_rows, axis=0) if len(self._probe_rows) > 1 else self._probe_rows[0]
+                self._probe_rows = [allrows]
+                data = allrows[:, info.row0:info.row0 + info.size, :]
+            else:
+                data = np.zeros((0, info.size, self.n_trials), dtype=np.float32)
+            if info.period > 1:
+                data = data[info.period - 1::info.period]
+            data = np.transpose(data, (2, 0, 1)).astype(np.float64)   # [trial, sample, size]
+        else:
+            snaps = self._snap[probe]
+            if snaps:
+                data = np.stack(snaps, axis=1)                        # [trial, sample, ...]
+            else:
+                shape = (self.n_trials, 0)
+                data = np.zeros(shape)
+        return data if self._batched else data[0]
+
+    # ------------------------------------------------------------------ checker / bench conveniences
+    def neuron_state(self, ens):
+        """(voltage, refractory_time) arrays [n_trials, n_neurons] of an ensemble."""
+        row0, n = self.plan.ens_state[ens]
+        v = self._download("v", row0, n)[:, :self.n_trials].T
+        r = self._download("ref", row0, n)[:, :self.n_trials].T
+        return v, r
+
+    def activities(self, ens):
+        """Last-step output of a wide ensemble [n_trials, n_neurons] (0 or 1/dt when spiking)."""
+        row0 = self.plan.ens_act[ens]
+        return self._download("act", row0, ens.n_neurons)[:, :self.n_trials].T
+
+    def learned_encoders(self, ens):
+        row0, n, dims = self.plan.learned_enc[ens]
+        return self._download("lenc", row0, n * dims)[:, :self.n_trials].T.reshape(self.n_trials, n, dims)
+
+    def learned_decoders(self, conn):
+        row0, size_out, n = self.plan.learned_dec[conn]
+        return self._download("ldec", row0, size_out * n)[:, :self.n_trials].T.reshape(self.n_trials, size_out, n)
+
+    def cleanup_indices(self):
+        """Last grid clean-up argmax per clean-up node: int array [n_nodes, n_trials]."""
+        n = len(getattr(self.plan, "cleanup_nodes", []))
+        if n == 0:
+            return np.zeros((0, self.n_trials), dtype=np.int64)
+        raw = self._download("cidx", 0, n)
+        return raw.view(np.int32)[:, :self.n_trials].astype(np.int64)
+
+    def filter_state(self, key):
+        """Current Lowpass state of a filtered connection / probe: [n_trials, size]."""
+        f0, size = self.plan.filters[key]
+        nf = int(self.plan.scalars["nf"])
+        half = nf if (self._n_steps & 1) else 0   # values the *next* step will read
+        return self._download("vec", 1 + half + f0, size)[:, :self.n_trials].T
+
+    def set_profiling(self, on=True):
+        cabi.check(self._lib.ssb_set_profiling(self._h, int(bool(on))), "ssb_set_profiling")
+
+    def kernel_times(self):
+        import ctypes as C
+        n = len(cabi.KERNEL_KINDS)
+        ms = (C.c_float * n)()
+        cnt = (C.c_longlong * n)()
+        cabi.check(self._lib.ssb_kernel_times(self._h, ms, cnt, n), "ssb_kernel_times")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(cabi.KERNEL_KINDS)}
+
+    def last_run_ms(self):
+        import ctypes as C
+        ms = C.c_float()
+        cabi.check(self._lib.ssb_last_run_ms(self._h, C.byref(ms)), "ssb_last_run_ms")
+        return float(ms.value)
+
+    def total_launches(self):
+        if self._h is None:
+            return getattr(self, "_launches_at_close", 0)
+        return int(self._lib.ssb_total_launches(self._h))
