@@ -37,7 +37,23 @@ struct CleanupDev {
     int* pidx = nullptr;
     int* idx = nullptr;
     const double* s64 = nullptr;
+    int n_chunks = 0, rows_per_chunk = 0, tile_rows = 0;
 };
+
+// Grid-scan geometry: shared-memory tiles of <= 48 KB of grid rows; enough chunks to fill the
+// machine at small batches, at most SSB_SCAN_MAX_CHUNKS (each chunk leaves TOPK candidates per trial).
+void scan_geometry(int G, int dpad, int n_groups, CleanupDev* cd) {
+    int tile_rows = std::max(1, (48 * 1024) / (dpad * (int)sizeof(float)));
+    tile_rows = std::min(tile_rows, G);
+    const int n_tiles = (G + tile_rows - 1) / tile_rows;
+    const int group_ctas = (n_groups + 3) / 4;
+    int want = std::max(1, (148 * 4 + group_ctas - 1) / group_ctas);   // ~4 CTAs per SM
+    int n_chunks = std::min(std::min(n_tiles, want), SSB_SCAN_MAX_CHUNKS);
+    int tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
+    cd->rows_per_chunk = tiles_per_chunk * tile_rows;
+    cd->n_chunks = (G + cd->rows_per_chunk - 1) / cd->rows_per_chunk;
+    cd->tile_rows = tile_rows;
+}
 
 }  // namespace
 
@@ -57,7 +73,11 @@ struct ssb_sim {
     float* d_lin_ab = nullptr;
     float* d_ntypes = nullptr;
     double* d_s64 = nullptr;
-    std::vector<int> h_stages, h_big, h_dec, h_cleanup, h_pes;
+    std::vector<int> h_stages, h_small, h_big, h_dec, h_cleanup, h_pes;
+    cudaGraphExec_t step_graph = nullptr;   // graph_steps consecutive steps (the step counter lives on the device)
+    int graph_steps = 0;
+    bool use_graph = true;
+    long long kind_per_step[16] = {0};      // launches per step by kind (counted while capturing)
     std::vector<size_t> s64_offsets;
     int n_levels = 0, n_lin = 0, n_pes = 0, n_small_total = 0;
     // sizes
@@ -176,21 +196,41 @@ int collect_profile(ssb_sim* s) {
 }
 
 template <int DP>
-void launch_scan(ssb_sim* s, bool csr, dim3 grid, size_t smem, const SsbCtx& c, const int* desc, const float* S,
-                 const CleanupDev& cd) {
+void launch_scan(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const float* S, const CleanupDev& cd,
+                 int dpad, int n_groups) {
+    dim3 grid(cd.n_chunks, (n_groups + 3) / 4);
+    size_t smem = (size_t)cd.tile_rows * dpad * sizeof(float);
+    if (DP == 0) smem += (size_t)4 * dpad * 32 * sizeof(float);
     if (csr)
-        k_cleanup_scan<DP, true><<<grid, SSB_SCAN_WARPS * 32, smem, s->stream>>>(c, desc, S, cd.cx, cd.pval, cd.pidx);
+        k_cleanup_scan<DP, true><<<grid, 128, smem, st>>>(c, desc, S, cd.cx, cd.pval, cd.pidx, cd.rows_per_chunk,
+                                                           cd.tile_rows, n_groups);
     else
-        k_cleanup_scan<DP, false><<<grid, SSB_SCAN_WARPS * 32, smem, s->stream>>>(c, desc, S, cd.cx, cd.pval, cd.pidx);
+        k_cleanup_scan<DP, false><<<grid, 128, smem, st>>>(c, desc, S, cd.cx, cd.pval, cd.pidx, cd.rows_per_chunk,
+                                                            cd.tile_rows, n_groups);
 }
 
-void dispatch_scan(ssb_sim* s, bool csr, int dpad, int n_groups, const SsbCtx& c, const int* desc, const float* S,
+void dispatch_scan(cudaStream_t st, bool csr, int dpad, int n_groups, const SsbCtx& c, const int* desc, const float* S,
                    const CleanupDev& cd) {
-    dim3 grid(SSB_SCAN_CHUNKS, n_groups);
-    size_t smem = (size_t)dpad * 32 * sizeof(float);
-    if (dpad == 56) launch_scan<56>(s, csr, grid, smem, c, desc, S, cd);
-    else if (dpad == 100) launch_scan<100>(s, csr, grid, smem, c, desc, S, cd);
-    else launch_scan<0>(s, csr, grid, smem, c, desc, S, cd);
+    if (dpad == 56) launch_scan<56>(st, csr, c, desc, S, cd, dpad, n_groups);
+    else if (dpad == 100) launch_scan<100>(st, csr, c, desc, S, cd, dpad, n_groups);
+    else launch_scan<0>(st, csr, c, desc, S, cd, dpad, n_groups);
+}
+
+void scan_smem_optin() {
+    const int lim = 200 * 1024;
+    cudaFuncSetAttribute(k_cleanup_scan<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_cleanup_scan<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_cleanup_scan<56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_cleanup_scan<56, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_cleanup_scan<100, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_cleanup_scan<100, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+}
+
+template <int DP>
+void launch_wide(ssb_sim* s, int item0, int n_items, int max_n, int smem) {
+    const int chunk = 64;   // neurons per CTA: 4 warps x 16
+    dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, n_items);
+    k_ens_wide<DP><<<grid, 128, smem, s->stream>>>(s->ctx, s->d_big, item0, chunk);
 }
 
 int one_step(ssb_sim* s) {
@@ -200,20 +240,25 @@ int one_step(ssb_sim* s) {
         const int* st = &s->h_stages[lvl * 10];
         if (st[1] > 0) {
             LaunchTimer t(s, K_SMALL);
-            const int warps = st[1] * G;
-            k_ens_small<<<(warps + 3) / 4, 128, 0, s->stream>>>(c, s->d_small + st[0] * 9, st[1], G);
+            // items are sorted by neuron count (descending): the leading ones get a whole CTA per trial group
+            int n_split = 0;
+            while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
+            const int packed_warps = (st[1] - n_split) * G;
+            const int blocks = n_split * G + (packed_warps + 3) / 4;
+            k_ens_small<<<blocks, 128, 0, s->stream>>>(c, s->d_small + st[0] * 9, st[1], n_split, G);
         }
         if (st[3] > 0) {
             LaunchTimer t(s, K_WIDE);
-            int max_n = 0, max_sm = 0;
+            int max_n[3] = {0, 0, 0}, max_sm[3] = {0, 0, 0};   // classes: dpad 56, dpad 100, generic
             for (int i = 0; i < st[3]; ++i) {
                 const int* d = &s->h_big[(st[2] + i) * 16];
-                max_n = std::max(max_n, d[0]);
-                max_sm = std::max(max_sm, (d[2] + d[11]) * 32 * (int)sizeof(float));
+                const int cls = d[2] == 56 ? 0 : (d[2] == 100 ? 1 : 2);
+                max_n[cls] = std::max(max_n[cls], d[0]);
+                max_sm[cls] = std::max(max_sm[cls], (d[2] + d[11]) * 32 * (int)sizeof(float));
             }
-            const int chunk = 128;
-            dim3 grid((max_n + chunk - 1) / chunk, G, st[3]);
-            k_ens_wide<<<grid, 256, max_sm, s->stream>>>(c, s->d_big, st[2], chunk);
+            if (max_n[0]) launch_wide<56>(s, st[2], st[3], max_n[0], max_sm[0]);
+            if (max_n[1]) launch_wide<100>(s, st[2], st[3], max_n[1], max_sm[1]);
+            if (max_n[2]) launch_wide<0>(s, st[2], st[3], max_n[2], max_sm[2]);
         }
         for (int i = 0; i < st[7]; ++i) {
             const int ci = st[6] + i;
@@ -221,34 +266,40 @@ int one_step(ssb_sim* s) {
             const CleanupDev& cd = s->cleanups[ci];
             {
                 LaunchTimer t(s, K_SCAN);
-                dispatch_scan(s, true, d[2], G, c, s->d_cleanup + ci * 6, s->d_W + d[3], cd);
+                dispatch_scan(s->stream, true, d[2], G, c, s->d_cleanup + ci * 6, s->d_W + d[3], cd);
             }
             {
                 LaunchTimer t(s, K_PICK);
-                k_cleanup_pick<<<(s->B + 127) / 128, 128, 0, s->stream>>>(s->B, d[1], d[2], cd.cx, cd.pval, cd.pidx, cd.s64,
-                                                                          s->d_W + d[3], s->vec + (size_t)d[5] * s->B, cd.idx,
-                                                                          nullptr, 0, 0);
+                k_cleanup_pick<<<G, 256, 0, s->stream>>>(s->B, d[1], d[2], cd.n_chunks * SSB_TOPK, cd.cx, cd.pval, cd.pidx,
+                                                         cd.s64, s->d_W + d[3], s->vec + (size_t)d[5] * s->B, cd.idx,
+                                                         nullptr, 0, 0);
             }
         }
         if (st[9] > 0) {
             LaunchTimer t(s, K_GATE);
-            dim3 grid((s->B + 127) / 128, st[9]);
-            k_gate<<<grid, 128, 0, s->stream>>>(c, s->d_gate, st[8]);
+            dim3 grid(G, st[9]);
+            k_gate<<<grid, 256, 0, s->stream>>>(c, s->d_gate, st[8]);
         }
         if (st[5] > 0) {
             LaunchTimer t(s, K_DEC);
-            int max_out = 0;
-            for (int i = 0; i < st[5]; ++i) max_out = std::max(max_out, s->h_dec[(st[4] + i) * 6 + 1]);
-            dim3 grid((max_out + 7) / 8, G, st[5]);
-            k_decode<<<grid, 128, 0, s->stream>>>(c, s->d_dec, st[4]);
+            int max_out = 0, max_chunks = 1;
+            for (int i = 0; i < st[5]; ++i) {
+                max_out = std::max(max_out, s->h_dec[(st[4] + i) * 7 + 1]);
+                max_chunks = std::max(max_chunks, s->h_dec[(st[4] + i) * 7 + 6]);
+            }
+            dim3 grid((max_out + 7) / 8, G, st[5] * max_chunks);
+            k_decode<<<grid, 128, 0, s->stream>>>(c, s->d_dec, st[4], max_chunks);
         }
     }
     if (s->n_pes > 0) {
         LaunchTimer t(s, K_PES);
-        int max_out = 0;
-        for (int i = 0; i < s->n_pes; ++i) max_out = std::max(max_out, s->h_pes[i * 10 + 1]);
-        dim3 grid((max_out + 7) / 8, G, s->n_pes);
-        k_pes<<<grid, 128, 0, s->stream>>>(c, s->d_pes, s->n_pes);
+        int max_out = 0, max_chunks = 1;
+        for (int i = 0; i < s->n_pes; ++i) {
+            max_out = std::max(max_out, s->h_pes[i * 11 + 1]);
+            max_chunks = std::max(max_chunks, s->h_pes[i * 11 + 10]);
+        }
+        dim3 grid((max_out + 7) / 8, G, s->n_pes * max_chunks);
+        k_pes<<<grid, 128, 0, s->stream>>>(c, s->d_pes, max_chunks);
     }
     if (s->n_lin > 0) {
         LaunchTimer t(s, K_LIN);
@@ -259,6 +310,30 @@ int one_step(ssb_sim* s) {
         LaunchTimer t(s, K_ADV);
         k_advance<<<1, 1, 0, s->stream>>>(s->dyn);
     }
+    return 0;
+}
+
+// Capture `n` consecutive steps into an executable graph.  Step parity, table row and probe row are
+// derived on the device from dyn[], so one graph is valid for any starting step.
+int build_graph(ssb_sim* s, int n) {
+    cudaGraph_t g = nullptr;
+    const bool prof = s->profiling;
+    s->profiling = false;
+    long long saved[K_NKINDS];
+    memcpy(saved, s->kind_launches, sizeof(saved));
+    const long long saved_total = s->total_launches;
+    SSB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < n; ++i) one_step(s);
+    cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    for (int k = 0; k < K_NKINDS; ++k) s->kind_per_step[k] = (s->kind_launches[k] - saved[k]) / n;
+    memcpy(s->kind_launches, saved, sizeof(saved));
+    s->total_launches = saved_total;
+    s->profiling = prof;
+    if (e != cudaSuccess) return fail(-2, std::string("graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&s->step_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(-2, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    s->graph_steps = n;
     return 0;
 }
 
@@ -335,7 +410,7 @@ int ssb_finalize(ssb_sim* s) {
     if (upload_array(s, "ens_big", &s->d_big)) return -2;
     if (upload_array(s, "dec", &s->d_dec)) return -2;
     if (upload_array(s, "pes", &s->d_pes, &cnt)) return -2;
-    s->n_pes = (int)(cnt / 10);
+    s->n_pes = (int)(cnt / 11);
     if (upload_array(s, "cleanup", &s->d_cleanup)) return -2;
     if (upload_array(s, "gate", &s->d_gate)) return -2;
     if (upload_array(s, "lin_rows", &s->d_lin_rows, &cnt)) return -2;
@@ -344,6 +419,7 @@ int ssb_finalize(ssb_sim* s) {
     if (upload_array(s, "ntypes", &s->d_ntypes)) return -2;
     if (upload_array(s, "cleanup_s64", &s->d_s64)) return -2;
     s->h_stages = host_ints(s, "stages");
+    s->h_small = host_ints(s, "ens_small");
     s->h_big = host_ints(s, "ens_big");
     s->h_dec = host_ints(s, "dec");
     s->h_cleanup = host_ints(s, "cleanup");
@@ -377,9 +453,10 @@ int ssb_finalize(ssb_sim* s) {
     for (int i = 0; i < n_cleanup; ++i) {
         const int* d = &s->h_cleanup[i * 6];
         CleanupDev& cd = s->cleanups[i];
+        scan_geometry(d[0], d[2], s->n_groups, &cd);
         if (alloc_rows(&cd.cx, d[2], B)) return -2;
-        if (alloc_rows(&cd.pval, SSB_SCAN_PARTS * SSB_TOPK, B)) return -2;
-        if (alloc_rows(reinterpret_cast<float**>(&cd.pidx), SSB_SCAN_PARTS * SSB_TOPK, B)) return -2;
+        if (alloc_rows(&cd.pval, cd.n_chunks * SSB_TOPK, B)) return -2;
+        if (alloc_rows(reinterpret_cast<float**>(&cd.pidx), cd.n_chunks * SSB_TOPK, B)) return -2;
         cd.idx = s->cidx + (size_t)i * B;
         const size_t need = (size_t)d[0] * d[1];
         if (s64_off + need <= s64_total) {
@@ -388,9 +465,8 @@ int ssb_finalize(ssb_sim* s) {
         }
     }
     // opt-in to large dynamic shared memory for very wide ensembles (d = 649)
-    cudaFuncSetAttribute(k_ens_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_cleanup_scan<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_cleanup_scan<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_ens_wide<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    scan_smem_optin();
 
     SsbCtx& c = s->ctx;
     c.B = B;
@@ -471,7 +547,21 @@ int ssb_run_steps(ssb_sim* s, int n_steps) {
     s->probe_step0 = s->steps_done;
     if (push_dyn(s)) return -2;
     SSB_CUDA(cudaEventRecord(s->ev_run0, s->stream));
-    for (int i = 0; i < n_steps; ++i) {
+    int i = 0;
+    if (s->use_graph && !s->profiling) {
+        const int gs = 16;
+        if (n_steps >= gs && !s->step_graph) {
+            if (build_graph(s, gs)) return -2;
+        }
+        if (s->step_graph) {
+            for (; i + s->graph_steps <= n_steps; i += s->graph_steps) SSB_CUDA(cudaGraphLaunch(s->step_graph, s->stream));
+            for (int k = 0; k < K_NKINDS; ++k) {   // account the replayed kernel launches
+                s->kind_launches[k] += (long long)i * s->kind_per_step[k];
+                s->total_launches += (long long)i * s->kind_per_step[k];
+            }
+        }
+    }
+    for (; i < n_steps; ++i) {
         if (one_step(s)) return -2;
     }
     SSB_CUDA(cudaEventRecord(s->ev_run1, s->stream));
@@ -537,6 +627,7 @@ void ssb_destroy(ssb_sim* s) {
         if (cd.pval) cudaFree(cd.pval);
         if (cd.pidx) cudaFree(cd.pidx);
     }
+    if (s->step_graph) cudaGraphExecDestroy(s->step_graph);
     for (auto e : s->ev_pool) cudaEventDestroy(e);
     if (s->ev_run0) cudaEventDestroy(s->ev_run0);
     if (s->ev_run1) cudaEventDestroy(s->ev_run1);
@@ -629,18 +720,20 @@ int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* q
     float *dS32 = nullptr, *cx = nullptr, *pval = nullptr;
     double *dS64 = nullptr, *dq = nullptr;
     int *pidx = nullptr, *didx = nullptr;
-    const int B = (int)std::min<long long>((n_q + 31) / 32 * 32, 1 << 15);
+    const int B = (int)std::min<long long>((n_q + 31) / 32 * 32, 1 << 14);
+    CleanupDev cd;
+    scan_geometry(G, dpad, B / 32, &cd);
     SSB_CUDA(cudaMalloc((void**)&dS32, s32.size() * sizeof(float)));
     SSB_CUDA(cudaMalloc((void**)&dS64, (size_t)G * d * sizeof(double)));
     SSB_CUDA(cudaMalloc((void**)&dq, (size_t)n_q * d * sizeof(double)));
     SSB_CUDA(cudaMalloc((void**)&cx, (size_t)dpad * B * sizeof(float)));
-    SSB_CUDA(cudaMalloc((void**)&pval, (size_t)SSB_SCAN_PARTS * SSB_TOPK * B * sizeof(float)));
-    SSB_CUDA(cudaMalloc((void**)&pidx, (size_t)SSB_SCAN_PARTS * SSB_TOPK * B * sizeof(int)));
+    SSB_CUDA(cudaMalloc((void**)&pval, (size_t)cd.n_chunks * SSB_TOPK * B * sizeof(float)));
+    SSB_CUDA(cudaMalloc((void**)&pidx, (size_t)cd.n_chunks * SSB_TOPK * B * sizeof(int)));
     SSB_CUDA(cudaMalloc((void**)&didx, (size_t)B * sizeof(int)));
     SSB_CUDA(cudaMemcpy(dS32, s32.data(), s32.size() * sizeof(float), cudaMemcpyHostToDevice));
     SSB_CUDA(cudaMemcpy(dS64, sample_ssps, (size_t)G * d * sizeof(double), cudaMemcpyHostToDevice));
     SSB_CUDA(cudaMemcpy(dq, queries, (size_t)n_q * d * sizeof(double), cudaMemcpyHostToDevice));
-    cudaFuncSetAttribute(k_cleanup_scan<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    scan_smem_optin();
     int hdesc[6] = {G, d, dpad, 0, 0, 0};
     int* ddesc = nullptr;
     SSB_CUDA(cudaMalloc((void**)&ddesc, sizeof(hdesc)));
@@ -648,18 +741,16 @@ int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* q
     SsbCtx c;
     memset(&c, 0, sizeof(c));
     c.B = B;
-    ssb_sim tmp;  // only for the stream field used by the launcher
-    tmp.stream = nullptr;
-    CleanupDev cd;
     cd.cx = cx;
     cd.pval = pval;
     cd.pidx = pidx;
     for (long long q0 = 0; q0 < n_q; q0 += B) {
         const long long nb = std::min<long long>(B, n_q - q0);
         k_decode_prep<<<(B + 127) / 128, 128>>>(dq, cx, n_q, B, d, dpad, q0);
-        dispatch_scan(&tmp, false, dpad, B / 32, c, ddesc, dS32, cd);
-        // re-score against the float64 grid; cx holds the fp32 unit queries
-        k_cleanup_pick<<<(B + 127) / 128, 128>>>(B, d, dpad, cx, pval, pidx, dS64, dS32, nullptr, didx, dq, q0, n_q);
+        dispatch_scan(nullptr, false, dpad, B / 32, c, ddesc, dS32, cd);
+        // near-ties are re-scored against the float64 grid with the float64 query
+        k_cleanup_pick<<<B / 32, 256>>>(B, d, dpad, cd.n_chunks * SSB_TOPK, cx, pval, pidx, dS64, dS32, nullptr, didx, dq,
+                                        q0, n_q);
         SSB_CUDA(cudaGetLastError());
         SSB_CUDA(cudaMemcpy(idx_out + q0, didx, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));
     }

@@ -35,6 +35,8 @@ TAB_BASE = 1 << 24          # CSR column ids >= TAB_BASE address the input-table
 SMALL_MAX_DIMS = 4
 SMALL_MAX_OUT = 8
 DEC_TILE = 8                # decoder output rows are padded to a multiple of this
+TARGET_CTAS = 148 * 8       # decode / PES launches are split until they offer ~8 CTAs per SM
+MAX_DEC_CHUNKS = 32
 
 NT_LIF, NT_LIFRATE, NT_RELU = 0, 1, 2
 
@@ -90,8 +92,9 @@ class DevicePlan:
 
 
 class _Lowerer:
-    def __init__(self, network, model: BuiltModel):
+    def __init__(self, network, model: BuiltModel, n_trials=1):
         self.net, self.model, self.dt = network, model, model.dt
+        self.n_groups = max(1, -(-int(n_trials) // 32))
         self.nodes = network.all_nodes
         self.ensembles = network.all_ensembles
         self.conns = network.all_connections
@@ -123,6 +126,50 @@ class _Lowerer:
                 kind = {"identity": "pass", "cleanup": "fn", "gate": "fn"}[op.kind]
             self.node_kind[node] = kind
 
+    # ------------------------------------------------------------------ ensemble classes
+    def classify_ensembles(self):
+        """Narrow ensembles (VCOs, product squares) are fused encode->neuron->decode items; wide ones
+        write activities and are decoded by separate launches whose neuron range is split into chunks
+        (one partial-sum slot per chunk; the consumers' CSR rows add the slots up)."""
+        self.ens_dec_conns = {e: [] for e in self.ensembles}
+        for conn in self.conns:
+            if isinstance(conn.pre_obj, ns.Ensemble):
+                self.ens_dec_conns[conn.pre_obj].append(conn)
+        for probe in self.probes:
+            if isinstance(probe.obj, ns.Ensemble) and probe.attr == "decoded_output":
+                self.ens_dec_conns[probe.obj].append(probe)
+        voja_posts = {c.post_obj for c in self.conns
+                      if c.learning_rule is not None and isinstance(c.learning_rule.learning_rule_type, ns.Voja)}
+        pes_conns = {c for c in self.conns
+                     if c.learning_rule is not None and isinstance(c.learning_rule.learning_rule_type, ns.PES)}
+        jn_posts = {c.post_obj.ensemble for c in self.conns if isinstance(c.post_obj, ns.Neurons)}
+        self.is_small, self.dec_chunks = {}, {}
+        for ens in self.ensembles:
+            outs = self.ens_dec_conns[ens]
+            nout = sum(self._out_size(c) for c in outs)
+            has_pes = any(c in pes_conns for c in outs)
+            small = (ens.dimensions <= SMALL_MAX_DIMS and nout <= SMALL_MAX_OUT and ens not in voja_posts
+                     and ens not in jn_posts and not has_pes)
+            self.is_small[ens] = small
+            for c in outs:
+                if small:
+                    self.dec_chunks[c] = 1
+                else:
+                    jtiles = -(-self._out_size(c) // DEC_TILE)
+                    want = -(-TARGET_CTAS // (jtiles * self.n_groups))
+                    self.dec_chunks[c] = int(max(1, min(want, ens.n_neurons // 32, MAX_DEC_CHUNKS)))
+
+    @staticmethod
+    def _out_size(c):
+        return c.size_out if isinstance(c, ns.Connection) else c.size_in
+
+    def _dec_expr(self, c):
+        """Decoded value of connection/probe ``c`` = sum of its partial-sum slots."""
+        size, k = self._out_size(c), self.dec_chunks[c]
+        rows = np.tile(np.arange(size), k)
+        cols = self.dec_col[c] + np.arange(size * k)
+        return sp.csr_matrix((np.ones(size * k), (rows, cols)), shape=(size, self.ncol))
+
     # ------------------------------------------------------------------ source columns
     def enumerate_sources(self):
         self.ncol = 1  # column 0 = constant one
@@ -149,17 +196,9 @@ class _Lowerer:
             if isinstance(probe.obj, (ns.Node, ns.Ensemble)) and probe.synapse is not None:
                 self.filt_col[probe] = alloc("filt", probe, probe.size_in)
         # decoded outputs, grouped per ensemble so that small ensembles own one contiguous slot
-        self.ens_dec_conns = {e: [] for e in self.ensembles}
-        for conn in self.conns:
-            if isinstance(conn.pre_obj, ns.Ensemble):
-                self.ens_dec_conns[conn.pre_obj].append(conn)
-        for probe in self.probes:
-            if isinstance(probe.obj, ns.Ensemble) and probe.attr == "decoded_output":
-                self.ens_dec_conns[probe.obj].append(probe)
         for ens in self.ensembles:
             for c in self.ens_dec_conns[ens]:
-                size = c.size_out if isinstance(c, ns.Connection) else c.size_in
-                self.dec_col[c] = alloc("dec", c, size)
+                self.dec_col[c] = alloc("dec", c, self._out_size(c) * self.dec_chunks[c])
         for node in self.nodes:
             if self.node_kind[node] == "fn":
                 self.fn_col[node] = alloc("fn", node, node.size_out)
@@ -204,7 +243,7 @@ class _Lowerer:
     def weighted(self, conn):
         pre = conn.pre_obj
         if isinstance(pre, ns.Ensemble):
-            return self._eye(self.dec_col[conn], conn.size_out)
+            return self._dec_expr(conn)
         if isinstance(pre, ns.Neurons):
             raise NotImplementedError("connections from ens.neurons are outside the hot path")
         src = self.expr_out(pre)
@@ -216,6 +255,7 @@ class _Lowerer:
     def lower(self, chunk_cap):
         plan = self.plan
         self.classify_nodes()
+        self.classify_ensembles()
         self.enumerate_sources()
         self._memo_out = {}
         dt = self.dt
@@ -261,11 +301,12 @@ class _Lowerer:
         INF = 1 << 20
         col_level = np.zeros(self.ncol, dtype=np.int64)
         pending_ens, pending_fn = set(self.ensembles), set(fn_in)
+        dec_width = {c: self._out_size(c) * self.dec_chunks[c] for c in self.dec_col}
         for c in pes_rule:
-            col_level[self.dec_col[c]:self.dec_col[c] + c.size_out] = INF
+            col_level[self.dec_col[c]:self.dec_col[c] + dec_width[c]] = INF
         unresolved = np.zeros(self.ncol, dtype=bool)
         for c, col0 in self.dec_col.items():
-            size = c.size_out if isinstance(c, ns.Connection) else c.size_in
+            size = dec_width[c]
             if not (isinstance(c, ns.Connection) and c in pes_rule):
                 unresolved[col0:col0 + size] = True
         for n, col0 in self.fn_col.items():
@@ -294,7 +335,7 @@ class _Lowerer:
                 for c in self.ens_dec_conns[ens]:
                     if isinstance(c, ns.Connection) and c in pes_rule:
                         continue
-                    size = c.size_out if isinstance(c, ns.Connection) else c.size_in
+                    size = dec_width[c]
                     col_level[self.dec_col[c]:self.dec_col[c] + size] = lvl + 1
                     unresolved[self.dec_col[c]:self.dec_col[c] + size] = False
                 pending_ens.discard(ens)
@@ -402,9 +443,7 @@ class _Lowerer:
             lvl = ens_level[ens]
             outs = self.ens_dec_conns[ens]
             nout = sum((c.size_out if isinstance(c, ns.Connection) else c.size_in) for c in outs)
-            has_pes = any(isinstance(c, ns.Connection) and c in pes_rule for c in outs)
-            is_small = (dims <= SMALL_MAX_DIMS and nout <= SMALL_MAX_OUT and ens not in voja_rule
-                        and ens not in ens_jn and not has_pes)
+            is_small = self.is_small[ens]
             state0 = nn
             nn += n
             plan.ens_state[ens] = (state0, n)
@@ -481,14 +520,14 @@ class _Lowerer:
                     pes_desc.append([n, size_out, d_off, a_off, act0, err_row0, out_vec,
                                      int(np.float32(alpha).view(np.int32)),
                                      int(np.float32(decay).view(np.int32)),
-                                     int(np.float32(1.0 - decay).view(np.int32))])
+                                     int(np.float32(1.0 - decay).view(np.int32)), self.dec_chunks[c]])
                 else:
                     jpad = size_out + ((-size_out) % DEC_TILE)
                     Wd = np.zeros((n, jpad))
                     Wd[:, :size_out] = self._dec_weights(c).T
                     w_off = add_w(Wd)
                     plan.static_dec[c] = (w_off, size_out, jpad, n)
-                    dec_desc[lvl].append([n, size_out, jpad, act0, w_off, out_vec])
+                    dec_desc[lvl].append([n, size_out, jpad, act0, w_off, out_vec, self.dec_chunks[c]])
 
         for node, mat in fn_in.items():
             op = self.node_op[node]
@@ -561,7 +600,7 @@ class _Lowerer:
         cat = {k: [] for k in ("small", "big", "dec", "cleanup", "gate")}
         for lvl in range(n_levels):
             # heavy-first ordering inside a launch evens out the tail
-            small_desc[lvl].sort(key=lambda r: -r[0] * (r[1] + r[2] + 8))
+            small_desc[lvl].sort(key=lambda r: (-r[0], -(r[1] + r[2])))
             entry = []
             for name, lst in (("small", small_desc[lvl]), ("big", big_desc[lvl]), ("dec", dec_desc[lvl]),
                               ("cleanup", cleanup_desc[lvl]), ("gate", gate_desc[lvl])):
@@ -575,8 +614,8 @@ class _Lowerer:
             "weights": np.concatenate(W) if W else np.zeros(4, dtype=np.float32),
             "ens_small": arr(cat["small"], 9),
             "ens_big": arr(cat["big"], 16),
-            "dec": arr(cat["dec"], 6),
-            "pes": arr(pes_desc, 10),
+            "dec": arr(cat["dec"], 7),
+            "pes": arr(pes_desc, 11),
             "cleanup": arr(cat["cleanup"], 6),
             "gate": arr(cat["gate"], 6),
             "lin_rows": arr(lin_rows, 3),
@@ -603,13 +642,13 @@ class _Lowerer:
     def _probe_expr(self, probe):
         obj = probe.obj
         if isinstance(obj, ns.Ensemble):
-            return self._eye(self.dec_col[probe], probe.size_in)
+            return self._dec_expr(probe)
         return self.expr_out(obj)[_idx(probe.slice, obj.size_out)].tocsr()
 
 
-def lower(network, model: BuiltModel, chunk_cap=256) -> DevicePlan:
-    """Network + built parameters -> :class:`DevicePlan`."""
-    return _Lowerer(network, model).lower(chunk_cap)
+def lower(network, model: BuiltModel, chunk_cap=256, n_trials=1) -> DevicePlan:
+    """Network + built parameters -> :class:`DevicePlan` (``n_trials`` only tunes launch geometry)."""
+    return _Lowerer(network, model, n_trials).lower(chunk_cap)
 
 
 def algorithmic_bytes_per_trial_step(stats, per_trial_weights=False):

@@ -53,7 +53,7 @@ class Simulator:
         self._batched = n_trials is not None
         self.n_trials = int(n_trials) if self._batched else 1
         self.chunk_steps = int(chunk_steps)
-        self.plan = lowering.lower(network, self.model, chunk_cap=self.chunk_steps)
+        self.plan = lowering.lower(network, self.model, chunk_cap=self.chunk_steps, n_trials=self.n_trials)
         self._trial_inputs = dict(trial_inputs or {})
         if trial_seeds is None:
             trial_seeds = [None] + list(range(self.n_trials - 1)) if self._batched else [None]
