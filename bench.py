@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Throughput of the batched SSP-SLAM step on B200 (BASELINE.json metric: trial-timesteps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload = BASELINE.json configs[1]: ``run_slam.py --domain-dim 2 --ssp-dim 55 --pi-n-neurons 500``
+(mem 970, circonv 100, 50 landmarks, dt 1 ms, spiking LIF, PES + Voja learning), random band-limited
+2-D paths, batched over ``--trials`` independent trials per GPU with shared static weights.
+
+One bench *step* = ``--chunk`` simulator timesteps of the whole batch (one ``run_steps`` call).
+* ``value``  — device-timed (CUDA events on the library stream), input tables for every timed
+  timestep already resident in HBM, probes written to the device probe buffer.
+* ``e2e``    — the same work through ``Simulator.run_steps`` with HOST buffers: per step the
+  tables are copied from page-locked host memory and the probe block is read back to the host.
+* ``roofline`` — dominant kernel kind: algorithmic bytes (SURVEY.md §8d model) / CUDA-event time.
+* ``cpu_baseline`` — the operator-level NumPy port of the nengo reference simulator
+  (``oracle/nengo_ref_sim.py``) on the same built network, one trial, one host core.
+
+``--impl reference`` times that CPU port on all host cores (one independent trial per process).
+Multi-GPU: one process per GPU (torchrun), trials sharded, no data-path collective; one NCCL
+all_gather of per-trial error statistics after the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "run_slam d=55 pi_n_neurons=500 mem=970 circonv=100 landmarks=50 LIF PES+Voja (BASELINE configs[1])"
+METRIC = "trial-timesteps/sec (SSP-SLAM)"
+UNIT = "trial-timesteps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--trials", type=int, default=1024, help="trials per GPU")
+    ap.add_argument("--chunk", type=int, default=64, help="simulator timesteps per bench step")
+    ap.add_argument("--ref-chunk", type=int, default=40, help="timesteps per bench step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=400)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def slam_scenario(n_trials, n_steps, seed, distinct):
+    from sspslam_b200 import scenarios
+    return scenarios.make_slam(n_trials=n_trials, n_steps=n_steps, ssp_dim=55, pi_n_neurons=500, mem_n_neurons=970,
+                               circonv_n_neurons=100, n_landmarks=50, T=200.0, seed=seed, neuron_type="lif",
+                               distinct_tables=distinct)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        if sm:
+            busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def _oracle_for_trial(sc, model, trial):
+    from oracle.nengo_ref_sim import RefSimulator
+    tabs = {node: arr[trial] for node, arr in sc.trial_inputs.items()}
+    return RefSimulator(sc.network, dt=sc.dt, model=model, node_tables=tabs)
+
+
+def cpu_baseline_single(sc, model, n_steps, warm=40):
+    """One trial of the CPU port on one core (BLAS threads as NumPy finds them; ops are tiny)."""
+    ref = _oracle_for_trial(sc, model, 0)
+    ref.run_steps(warm)
+    t0 = time.perf_counter()
+    ref.run_steps(n_steps)
+    dt = time.perf_counter() - t0
+    return {"value": n_steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"1 trial x {n_steps} timesteps of the same built network after {warm} warm-up steps "
+                      f"(oracle/nengo_ref_sim.py, float64, unmerged operators)"}
+
+
+def _ref_worker(args):
+    sc, model, trial, warm, chunk, k, barrier, q = args
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
+    ref = _oracle_for_trial(sc, model, trial)
+    ref.run_steps(warm * chunk)
+    barrier.wait()
+    t0 = time.perf_counter()
+    ref.run_steps(k * chunk)
+    t1 = time.perf_counter()
+    q.put((t0, t1))
+    del limiter
+
+
+def run_reference(args):
+    """CPU arm: the NumPy port of the reference simulator, one independent trial per host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from sspslam_b200.builder import build_model
+    cores = len(os.sched_getaffinity(0))
+    n_steps = (args.warmup + args.steps) * args.ref_chunk
+    sc = slam_scenario(cores, n_steps + 2, args.seed, distinct=cores)
+    model = build_model(sc.network, dt=sc.dt)
+    ctx = mp.get_context("fork")
+    barrier, q = ctx.Barrier(cores), ctx.Queue()
+    procs = [ctx.Process(target=_ref_worker, args=((sc, model, i, args.warmup, args.ref_chunk, args.steps, barrier, q),))
+             for i in range(cores)]
+    for p in procs:
+        p.start()
+    spans = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = max(t1 for _, t1 in spans) - min(t0 for t0, _ in spans)
+    total = cores * args.steps * args.ref_chunk
+    value = total / wall
+    sample = (f"{cores} processes x 1 trial x {args.steps}x{args.ref_chunk} timesteps "
+              f"(after {args.warmup}x{args.ref_chunk} warm-up), float64 NumPy operator port of nengo's reference simulator")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "timesteps_per_step": args.ref_chunk, "trials": cores},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(kind):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f).get(kind)
+    return None
+
+
+def run_b200(args):
+    import torch
+    import __graft_entry__ as entry
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    entry.build()
+    from sspslam_b200 import lowering, sharding
+    from sspslam_b200.simulator import Simulator
+
+    B, chunk, K, W = args.trials, args.chunk, args.steps, args.warmup
+    n_phase = (W + K) * chunk
+    total_steps = 2 * n_phase + chunk
+    # trial ids are global: rank r owns [r*B, (r+1)*B); static weights are shared (one network seed)
+    sc = slam_scenario(B, total_steps + 2, args.seed + 8000 * rank, distinct=8)
+    trial_seeds = sharding.trial_seeds(world * B, rank, world)
+    sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, trial_seeds=trial_seeds,
+                    device=local, chunk_steps=n_phase)
+    stats = sim.plan.stats
+    bytes_ts = lowering.algorithmic_bytes_per_trial_step(stats)
+    sim.stage_inputs(0, total_steps)
+
+    def barrier():
+        sim.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        return sharding.max_over_ranks(x, device="cuda")
+
+    # ---------------- value: every table of the phase is resident in HBM before the timed region
+    sim.load_tables(0, n_phase)
+    for _ in range(W):
+        sim.run_resident(chunk)
+    barrier()
+    clocks = ClockSampler(local)
+    launches0 = sim.total_launches()
+    sim.mark(0)
+    for _ in range(K):
+        sim.run_resident(chunk)
+    sim.mark(1)
+    barrier()
+    value_ms = max_over_ranks(sim.mark_elapsed_ms(0, 1))
+    launches = sim.total_launches() - launches0
+
+    # ---------------- e2e: public API with host buffers (pinned tables -> device, probes -> host) every step
+    h2d = chunk * int(sim.plan.scalars["nt"]) * sim.B * 4
+    d2h = chunk * int(sim.plan.scalars["n_probe"]) * sim.B * 4
+    for _ in range(W):
+        sim.run_steps(chunk)
+    barrier()
+    sim.mark(2)
+    for _ in range(K):
+        sim.run_steps(chunk)
+    sim.mark(3)
+    barrier()
+    e2e_ms = max_over_ranks(sim.mark_elapsed_ms(2, 3))
+    clock_info = clocks.stop()
+
+    # ---------------- per-kernel CUDA-event times (one more chunk with an event pair around every launch)
+    sim.set_profiling(True)
+    sim.run_steps(chunk)
+    kt = sim.kernel_times()
+    sim.set_profiling(False)
+    tot_ms = sum(ms for ms, _ in kt.values()) or 1.0
+    by_kind = stats["bytes_by_kind"]
+    dom = max((k for k in kt if by_kind.get(k, 0) > 0), key=lambda k: kt[k][0])
+    dom_ms, dom_cnt = kt[dom]
+    peak, peak_src = load_peaks()
+    per_launch_bytes = by_kind[dom] * sim.B * chunk / max(dom_cnt, 1)
+    achieved = per_launch_bytes / (dom_ms / max(dom_cnt, 1) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": load_traffic(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_us": dom_ms / max(dom_cnt, 1) * 1e3,
+                "share_of_step": dom_ms / tot_ms,
+                "kernel_shares": {k: round(ms / tot_ms, 4) for k, (ms, c) in kt.items() if c}}
+    step_gbs = bytes_ts * B * chunk * K / (value_ms * 1e-3) / 1e9
+
+    # ---------------- error statistics: one small collective at the very end
+    probe = sim.data[sc.probe]                                  # [B, samples, d] of the e2e + profile phases
+    n_have = probe.shape[1]
+    real = sc.real_ssp[:, n_phase:n_phase + n_have]
+    num = np.sum(probe * real, axis=2)
+    den = np.linalg.norm(probe, axis=2) * np.linalg.norm(real, axis=2) + 1e-12
+    cos_last = (num / den)[:, -1].astype(np.float32)
+    gathered = sharding.gather_trial_stats(cos_last[:, None], world * B, device="cuda")[:, 0]
+    sim.close()
+
+    if rank == 0:
+        tsteps = world * B * chunk * K
+        line = {
+            "metric": METRIC, "value": tsteps / (value_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": value_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "trials_per_gpu": B, "timesteps_per_step": chunk, "weights": "shared",
+                       "neurons_per_trial": stats["n_neurons"], "learned_per_trial": stats["n_learned"],
+                       "algorithmic_bytes_per_trial_timestep": bytes_ts,
+                       "l2": f"per-step working set {bytes_ts * B / 1e6:.0f} MB streams through HBM (> 126 MB L2)",
+                       "parallelism": f"trials sharded over {world} GPU(s), no data-path collective"},
+            "e2e": {"value": tsteps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches),
+            "clocks": {k: clock_info[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+            "roofline": roofline,
+            "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
+            "final_cosine_similarity": {"mean": float(np.mean(gathered)), "min": float(np.min(gathered)),
+                                        "n_trials": int(gathered.size)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single(sc, sim.model, args.cpu_baseline_steps)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,10 @@ int ssb_last_run_ms(ssb_sim* s, float* ms);
 /* kinds: 0 ens_small 1 ens_wide 2 decode 3 pes 4 cleanup_scan 5 cleanup_pick 6 gate 7 lin 8 advance */
 int ssb_kernel_times(ssb_sim* s, float* ms_per_kind, long long* launches_per_kind, int n_kinds);
 long long ssb_total_launches(ssb_sim* s);
+/* CUDA-event marks on the library stream (4 slots) and the device time between two of them:
+ * brackets a timed region that spans several ssb_run_steps / table / probe calls. */
+int ssb_mark(ssb_sim* s, int slot);
+int ssb_mark_elapsed_ms(ssb_sim* s, int slot_a, int slot_b, float* ms);
 
 /* Stand-alone SSP kernels.
  * Replaces SSPSpace.encode (sspspace.py:252-273): out[N][d] = IFFT(exp(i A_scaled x)).real,

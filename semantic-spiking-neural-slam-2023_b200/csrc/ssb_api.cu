@@ -95,6 +95,7 @@ struct ssb_sim {
     // timing
     bool profiling = false;
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
+    cudaEvent_t ev_mark[4] = {nullptr, nullptr, nullptr, nullptr};
     bool run_timed = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, int>> ev_used;  // (kind, index of first event of the pair)
@@ -629,6 +630,8 @@ void ssb_destroy(ssb_sim* s) {
     }
     if (s->step_graph) cudaGraphExecDestroy(s->step_graph);
     for (auto e : s->ev_pool) cudaEventDestroy(e);
+    for (auto e : s->ev_mark)
+        if (e) cudaEventDestroy(e);
     if (s->ev_run0) cudaEventDestroy(s->ev_run0);
     if (s->ev_run1) cudaEventDestroy(s->ev_run1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -666,6 +669,23 @@ int ssb_kernel_times(ssb_sim* s, float* ms_per_kind, long long* launches_per_kin
 }
 
 long long ssb_total_launches(ssb_sim* s) { return s ? s->total_launches : -1; }
+
+int ssb_mark(ssb_sim* s, int slot) {
+    if (!s || slot < 0 || slot >= 4) return fail(-1, "ssb_mark: bad arguments");
+    SSB_CUDA(cudaSetDevice(s->device));
+    if (!s->ev_mark[slot]) SSB_CUDA(cudaEventCreate(&s->ev_mark[slot]));
+    SSB_CUDA(cudaEventRecord(s->ev_mark[slot], s->stream));
+    return 0;
+}
+
+int ssb_mark_elapsed_ms(ssb_sim* s, int slot_a, int slot_b, float* ms) {
+    if (!s || !ms || slot_a < 0 || slot_a >= 4 || slot_b < 0 || slot_b >= 4 || !s->ev_mark[slot_a] || !s->ev_mark[slot_b])
+        return fail(-1, "ssb_mark_elapsed_ms: bad arguments or unrecorded mark");
+    SSB_CUDA(cudaSetDevice(s->device));
+    SSB_CUDA(cudaEventSynchronize(s->ev_mark[slot_b]));
+    SSB_CUDA(cudaEventElapsedTime(ms, s->ev_mark[slot_a], s->ev_mark[slot_b]));
+    return 0;
+}
 
 void* ssb_host_alloc(size_t bytes) {
     void* p = nullptr;

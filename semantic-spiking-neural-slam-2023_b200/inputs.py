@@ -40,9 +40,9 @@ def rd_sampling(n, d, seed=0.5):
     """R_d low-discrepancy points with an additive offset (``sspslam/utils/utils.py:41-55``)."""
     g = 2.0
     for _ in range(10):
-        g = (1 + g) ** (1.0 / (d + 1))
-    alpha = np.mod((1.0 / g) ** np.arange(1, d + 1), 1.0)
-    return np.mod(seed + alpha[None, :] * np.arange(1, n + 1)[:, None], 1.0)
+        g = pow(1 + g, 1 / (d + 1))
+    alpha = np.array([pow(1 / g, j + 1) % 1 for j in range(d)])   # Python-float pow: bit-identical to the reference
+    return (seed + alpha[None, :] * np.arange(1, n + 1)[:, None]) % 1
 
 
 def velocity_scale(phase_matrix, vels):

@@ -632,6 +632,16 @@ class _Lowerer:
         plan.stats = dict(n_neurons=nn, n_filter_states=NF, n_learned=n_lenc + n_ldec, n_static_weights=n_static,
                           n_table_words=NT, n_probe_words=n_probe_rows, n_small=n_small, n_big=n_big,
                           n_levels=n_levels, csr_nnz=len(csr_idx), n_afilt=n_afilt, n_act=n_act)
+        n_small_neurons = int(sum(e.n_neurons for e in self.ensembles if self.is_small[e]))
+        # SURVEY.md §8(d) traffic model split by the kernel that owns each stream (bytes per trial-step)
+        plan.stats["n_small_neurons"] = n_small_neurons
+        plan.stats["bytes_by_kind"] = {
+            "ens_small": 16 * n_small_neurons,
+            "ens_wide": 16 * (nn - n_small_neurons) + 8 * n_lenc,
+            "pes": 8 * n_ldec,
+            "lin": 8 * (NF + n_afilt) + 4 * n_probe_rows,
+            "inputs": 4 * NT,
+        }
         return plan
 
     def _dec_weights(self, c):

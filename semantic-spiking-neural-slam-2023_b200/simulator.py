@@ -143,6 +143,8 @@ class Simulator:
                 self._h = None
             self._tab_buf.free()
             self._probe_buf.free()
+            if getattr(self, "_staged", None) is not None:
+                self._staged.free()
 
     def __del__(self):
         try:
@@ -202,10 +204,36 @@ class Simulator:
             raise ns.exceptions.SimulationError(f"{node!r} returned a non-finite value")
         return out
 
-    def _fill_tables(self, step0, n):
+    def stage_inputs(self, step0, n_steps):
+        """Pre-pack the input tables of steps [step0, step0+n_steps) into page-locked host memory in
+        the device layout ``[step][row][trial]``.  ``run_steps`` then copies straight from this
+        staging area (host -> device per chunk) instead of transposing NumPy tables chunk by chunk."""
+        self._check_open()
         if self._nt == 0:
             return
-        buf = self._tab_buf.array[:n * self._nt * self.B].reshape(n, self._nt, self.B)
+        n_steps = int(n_steps)
+        self._staged = cabi.PinnedBuffer(n_steps * self._nt * self.B)
+        self._staged_step0 = int(step0)
+        self._staged_steps = n_steps
+        view = self._staged.array.reshape(n_steps, self._nt, self.B)
+        blk = 256
+        for s0 in range(0, n_steps, blk):
+            n = min(blk, n_steps - s0)
+            self._fill_tables(step0 + s0, n, view[s0:s0 + n])
+
+    def _staged_ptr(self, step0, n):
+        st = getattr(self, "_staged", None)
+        if st is None or st.ptr is None:
+            return None
+        if step0 < self._staged_step0 or step0 + n > self._staged_step0 + self._staged_steps:
+            return None
+        return st.ptr + (step0 - self._staged_step0) * self._nt * self.B * 4
+
+    def _fill_tables(self, step0, n, buf=None):
+        if self._nt == 0:
+            return
+        if buf is None:
+            buf = self._tab_buf.array[:n * self._nt * self.B].reshape(n, self._nt, self.B)
         for node, col0, size in self.plan.tables:
             vals = self._node_table(node, step0, n)              # [T|1, n, size]
             block = np.transpose(vals, (1, 2, 0))                 # [n, size, T|1]
@@ -225,8 +253,11 @@ class Simulator:
             for p in periods:  # stop exactly on snapshot steps of weight / encoder probes
                 to_next = p - (self._n_steps % p)
                 n = min(n, to_next)
-            self._fill_tables(self._n_steps, n)
-            cabi.check(lib.ssb_set_tables(self._h, self._tab_buf.ptr, self._n_steps, n), "ssb_set_tables")
+            src = self._staged_ptr(self._n_steps, n)
+            if src is None:
+                self._fill_tables(self._n_steps, n)
+                src = self._tab_buf.ptr
+            cabi.check(lib.ssb_set_tables(self._h, src, self._n_steps, n), "ssb_set_tables")
             cabi.check(lib.ssb_run_steps(self._h, n), "ssb_run_steps")
             if self._np:
                 cabi.check(lib.ssb_read_probes(self._h, self._probe_buf.ptr, self._n_steps, n), "ssb_read_probes")
@@ -322,6 +353,34 @@ class Simulator:
         ms = C.c_float()
         cabi.check(self._lib.ssb_last_run_ms(self._h, C.byref(ms)), "ssb_last_run_ms")
         return float(ms.value)
+
+    def mark(self, slot):
+        """Record a CUDA event on the library stream (bench timing; 4 slots)."""
+        cabi.check(self._lib.ssb_mark(self._h, int(slot)), "ssb_mark")
+
+    def mark_elapsed_ms(self, a, b):
+        import ctypes as C
+        ms = C.c_float()
+        cabi.check(self._lib.ssb_mark_elapsed_ms(self._h, int(a), int(b), C.byref(ms)), "ssb_mark_elapsed_ms")
+        return float(ms.value)
+
+    def run_resident(self, n_steps):
+        """Advance ``n_steps`` using input tables that are already resident on the device
+        (``load_tables``); asynchronous, probes stay in the device probe buffer."""
+        self._check_open()
+        cabi.check(self._lib.ssb_run_steps(self._h, int(n_steps)), "ssb_run_steps")
+        self._n_steps += int(n_steps)
+
+    def load_tables(self, step0, n_steps):
+        """Copy the staged input tables of steps [step0, step0+n_steps) to the device."""
+        self._check_open()
+        src = self._staged_ptr(step0, n_steps)
+        if src is None:
+            raise ValueError("load_tables: range not staged (call stage_inputs first)")
+        cabi.check(self._lib.ssb_set_tables(self._h, src, int(step0), int(n_steps)), "ssb_set_tables")
+
+    def sync(self):
+        cabi.check(self._lib.ssb_sync(self._h), "ssb_sync")
 
     def total_launches(self):
         if self._h is None:

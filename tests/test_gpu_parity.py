@@ -1,0 +1,243 @@
+"""Parity tests proper (``-m gpu``): the CUDA path, called through the C-ABI (ctypes ->
+``libssb.so``), against the CPU oracle on the same built model, seeds and inputs.
+
+Tolerances (BASELINE.json north_star): integer / index work (grid argmax, decode indices) is
+bit-exact; decoded SSP trajectories agree within 1e-4 relative in rate mode over the stated horizon;
+spiking (LIF) runs are fp32 vs fp64 and chaotic, so they are held to 2e-3 over 200 steps and to
+identical spike masks over the first steps."""
+import numpy as np
+import pytest
+
+from oracle import ssp_ref
+from oracle.nengo_ref_sim import RefSimulator
+from sspslam_b200 import scenarios, cabi
+from sspslam_b200.sspspace import HexagonalSSPSpace
+
+pytestmark = pytest.mark.gpu
+BOUNDS2 = np.tile([-1.0, 1.0], (2, 1))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(lib):
+    return lib
+
+
+def _Simulator():
+    from sspslam_b200.simulator import Simulator
+    return Simulator
+
+
+def _oracle(sc, sim, trial, n_steps):
+    tabs = {node: arr[trial] for node, arr in sc.trial_inputs.items()}
+    ref = RefSimulator(sc.network, dt=sc.dt, model=sim.model, node_tables=tabs, trial_seed=sim.trial_seeds[trial])
+    ref.run_steps(n_steps)
+    return ref
+
+
+def _rel(got, want):
+    return np.max(np.abs(got - want)) / max(1e-12, np.max(np.abs(want)))
+
+
+# ------------------------------------------------------------------------------- SSP kernels
+def test_ssp_encode_kernel_matches_oracle_and_reference(golden):
+    sp = HexagonalSSPSpace(2, ssp_dim=55, domain_bounds=BOUNDS2, length_scale=0.2)        # backend='cuda'
+    got = sp.encode(golden["enc_pts"])
+    np.testing.assert_allclose(got, golden["enc55"], rtol=0, atol=1e-13)                  # unmodified reference output
+    np.testing.assert_allclose(got, ssp_ref.encode(sp.phase_matrix, sp.length_scale, golden["enc_pts"]), atol=1e-13)
+    sp3 = HexagonalSSPSpace(3, ssp_dim=55, domain_bounds=np.tile([-1.0, 1.0], (3, 1)), length_scale=0.3,
+                            rng=np.random.default_rng(0))
+    np.testing.assert_allclose(sp3.encode(golden["enc3d_pts"]), golden["enc3d"], rtol=0, atol=1e-13)
+    one = sp.encode(np.array([[0.25, -0.5]]))
+    assert one.shape == (1, 55) and abs(np.linalg.norm(one) - 1) < 1e-12
+    assert cabi.ssp_encode(sp._scaled_phases(), np.zeros((0, 2))).shape == (0, 55)        # empty input
+
+
+def test_ssp_decode_kernel_indices_are_bit_exact(golden):
+    sp = HexagonalSSPSpace(2, ssp_dim=55, domain_bounds=BOUNDS2, length_scale=0.2)
+    ssps, pts = sp.get_sample_pts_and_ssps(100, "grid")
+    q = golden["dec55_in"]                                     # noisy, scaled, an all-zero row, a tiny-norm row
+    idx = cabi.ssp_decode_argmax(ssps, q)
+    assert np.array_equal(idx, golden["dec55_idx"])
+    assert np.array_equal(pts[idx], golden["dec55_out"])
+    assert np.array_equal(sp.decode(q, "from-set", "grid", 100), golden["dec55_out"])
+    rng = np.random.default_rng(5)
+    big = sp.encode_host(rng.uniform(-1, 1, (3001, 2))) + 0.2 * rng.standard_normal((3001, 55))   # ragged: 3001 rows
+    assert np.array_equal(cabi.ssp_decode_argmax(ssps, big), ssp_ref.decode_indices(ssps, big))
+    assert np.array_equal(cabi.ssp_decode_argmax(ssps, big[:1]), ssp_ref.decode_indices(ssps, big[:1]))
+    assert cabi.ssp_decode_argmax(ssps, np.zeros((0, 55))).shape == (0,)
+
+
+def test_ssp_decode_ties_first_maximum_wins():
+    sp = HexagonalSSPSpace(2, ssp_dim=55, domain_bounds=BOUNDS2, length_scale=0.2, backend="host")
+    ssps, _ = sp.get_sample_pts_and_ssps(30, "grid")
+    dup = np.vstack([ssps, ssps[[17, 400, 899]]])              # exact duplicates later in the set
+    q = ssps[[899, 17, 400, 5]] * 2.5
+    assert list(cabi.ssp_decode_argmax(dup, q)) == [899, 17, 400, 5]
+    assert list(ssp_ref.decode_indices(dup, q)) == [899, 17, 400, 5]
+    # near ties: neighbouring grid rows, query exactly between them perturbed by 1e-9
+    mid = 0.5 * (ssps[100] + ssps[101])
+    qs = np.stack([mid + 1e-9 * (ssps[100] - ssps[101]), mid - 1e-9 * (ssps[100] - ssps[101])])
+    assert np.array_equal(cabi.ssp_decode_argmax(ssps, qs), ssp_ref.decode_indices(ssps, qs))
+
+
+def test_ssp_decode_generic_width_3d():
+    sp = HexagonalSSPSpace(3, ssp_dim=55, domain_bounds=np.tile([-1.0, 1.0], (3, 1)), length_scale=0.3,
+                           rng=np.random.default_rng(0), backend="host")       # d = 33 -> generic-width kernels
+    ssps, pts = sp.get_sample_pts_and_ssps(12, "grid")
+    rng = np.random.default_rng(1)
+    q = sp.encode_host(rng.uniform(-1, 1, (257, 3))) + 0.05 * rng.standard_normal((257, sp.ssp_dim))
+    assert np.array_equal(cabi.ssp_decode_argmax(ssps, q), ssp_ref.decode_indices(ssps, q))
+
+
+# ------------------------------------------------------------------------------- stepped path
+@pytest.mark.parametrize("neuron_type,tol", [("lifrate", 1e-4), ("relu", 1e-4), ("lif", 2e-3)])
+def test_pathintegration_matches_oracle(neuron_type, tol):
+    n_steps = 300 if neuron_type != "lif" else 200
+    sc = scenarios.make_pathint(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=200, neuron_type=neuron_type)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        sim.run_steps(n_steps)
+        assert sim.total_launches() > 0
+    got = sim.data[sc.probe]                       # readable after close (run_slam.py:242-252)
+    assert got.shape == (3, n_steps, 55)
+    for trial in (0, 2):
+        want = _oracle(sc, sim, trial, n_steps).data[sc.probe]
+        assert np.max(np.abs(want)) > 0.1
+        assert _rel(got[trial], want) < tol
+
+
+def test_slam_rate_mode_matches_oracle_and_cleanup_indices_are_exact():
+    n_steps = 200
+    sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=100, mem_n_neurons=200,
+                             circonv_n_neurons=30, n_landmarks=20, T=20.0, neuron_type="lifrate")
+    slam = sc.extra["slam"]
+    sim = _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs)
+    idx_trace = []
+    for _ in range(4):
+        sim.run_steps(n_steps // 4)
+        idx_trace.append(sim.cleanup_indices()[0].copy())
+    got = sim.data[sc.probe]
+    dec = sim.learned_decoders(slam.assomemory.conn_out)
+    enc = sim.learned_encoders(slam.assomemory.memory)
+    sim.close()
+    for trial in (0, 1):
+        tabs = {node: arr[trial] for node, arr in sc.trial_inputs.items()}
+        ref = RefSimulator(sc.network, dt=sc.dt, model=sim.model, node_tables=tabs, trial_seed=sim.trial_seeds[trial])
+        for k in range(4):
+            ref.run_steps(n_steps // 4)
+            x = ref.signals[slam.gridcells, "in"].a
+            assert idx_trace[k][trial] == ssp_ref.cleanup_index(slam.sample_ssps, x)       # bit-exact index
+        assert _rel(got[trial], ref.data[sc.probe]) < 1e-4
+        # learned matrices: the device applies the delta of step t at step t+1, like nengo's Copy(inc)
+        want_enc = ref.scaled_encoders(slam.assomemory.memory)
+        assert _rel(enc[trial], want_enc) < 1e-4
+        want_dec = ref.learned_weights(slam.assomemory.conn_out)
+        assert np.max(np.abs(want_dec)) > 0
+        assert np.max(np.abs(dec[trial] - want_dec)) < 1e-4 * np.max(np.abs(want_dec)) + 1e-9
+
+
+def test_slam_spiking_matches_oracle_short_horizon():
+    n_steps = 200
+    sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=100, mem_n_neurons=200,
+                             circonv_n_neurons=30, n_landmarks=20, T=20.0, neuron_type="lif", weights_probe=True)
+    slam = sc.extra["slam"]
+    sim = _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs)
+    sim.run_steps(12)
+    spikes12 = sim.activities(slam.ovc_ens) > 0
+    sim.run_steps(n_steps - 12)
+    got = sim.data[sc.probe]
+    w = sim.data[sc.extra["weights_probe"]]
+    sim.close()
+    assert w.shape == (3, 1, 55, 200)                       # Probe(conn,'weights',sample_every=T): (1, 55, n) per trial
+    for trial in (0, 1):
+        tabs = {node: arr[trial] for node, arr in sc.trial_inputs.items()}
+        ref = RefSimulator(sc.network, dt=sc.dt, model=sim.model, node_tables=tabs, trial_seed=sim.trial_seeds[trial])
+        ref.run_steps(12)
+        assert np.array_equal(spikes12[trial], ref.spikes(slam.ovc_ens))                   # identical spike mask
+        ref.run_steps(n_steps - 12)
+        assert _rel(got[trial], ref.data[sc.probe]) < 2e-3
+
+
+def test_slamview_rate_mode_matches_oracle():
+    n_steps = 150
+    sc = scenarios.make_slam(n_trials=2, n_steps=n_steps, ssp_dim=55, pi_n_neurons=100, mem_n_neurons=200,
+                             circonv_n_neurons=30, n_landmarks=20, T=20.0, neuron_type="lifrate", view=True)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=2, trial_inputs=sc.trial_inputs) as sim:
+        sim.run_steps(n_steps)
+    got = sim.data[sc.probe]
+    for trial in (0, 1):
+        assert _rel(got[trial], _oracle(sc, sim, trial, n_steps).data[sc.probe]) < 1e-4
+
+
+def test_generic_width_network_matches_oracle():
+    """d = 31 is neither of the register-specialised widths (56 / 100): generic kernels."""
+    sc = scenarios.make_slam(n_trials=2, n_steps=120, ssp_dim=31, pi_n_neurons=60, mem_n_neurons=120,
+                             circonv_n_neurons=20, n_landmarks=8, T=20.0, neuron_type="lifrate")
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=2, trial_inputs=sc.trial_inputs) as sim:
+        sim.run_steps(120)
+    got = sim.data[sc.probe]
+    assert _rel(got[1], _oracle(sc, sim, 1, 120).data[sc.probe]) < 1e-4
+
+
+# ------------------------------------------------------------------------------- simulator surface
+def test_simulator_surface_run_trange_reset_unbatched():
+    sc = scenarios.make_pathint(n_trials=1, n_steps=120, ssp_dim=19, pi_n_neurons=50, neuron_type="lif")
+    sim = _Simulator()(sc.network, dt=sc.dt)                      # unbatched: nengo's own API, closures evaluated
+    with sim:
+        sim.run(0.05)
+        assert sim.n_steps == 50 and abs(sim.time - 0.05) < 1e-12
+        first = sim.data[sc.probe].copy()
+        assert first.shape == (50, 19)
+        np.testing.assert_allclose(sim.trange(), 0.001 * np.arange(1, 51))
+        sim.step()
+        assert sim.n_steps == 51
+        sim.reset()
+        assert sim.n_steps == 0
+        sim.run(0.05)
+        assert np.array_equal(sim.data[sc.probe], first)         # reset reproduces the run bit for bit
+    assert np.array_equal(sim.data[sc.probe], first)
+    with pytest.raises(Exception):
+        sim.run_steps(1)                                         # closed
+    ref = RefSimulator(sc.network, dt=sc.dt, model=sim.model)     # oracle calls the same closures
+    ref.run_steps(50)
+    assert _rel(first, ref.data[sc.probe]) < 2e-3
+    built = sim.data[sc.extra["pathint"].oscillators.ea_ensembles[1]]
+    assert built.encoders.shape == (50, 3) and built.gain.shape == (50,)
+
+
+def test_batch_independence_and_determinism():
+    """A trial's trajectory does not depend on the batch it runs in (ragged batch sizes, chunking)."""
+    sc = scenarios.make_slam(n_trials=40, n_steps=64, ssp_dim=55, pi_n_neurons=60, mem_n_neurons=128,
+                             circonv_n_neurons=20, n_landmarks=10, T=20.0, neuron_type="lif", distinct_tables=5)
+    S = _Simulator()
+    seeds = list(range(100, 140))
+    with S(sc.network, dt=sc.dt, n_trials=40, trial_inputs=sc.trial_inputs, trial_seeds=seeds, chunk_steps=64) as a:
+        a.run_steps(64)
+    with S(sc.network, dt=sc.dt, n_trials=40, trial_inputs=sc.trial_inputs, trial_seeds=seeds, chunk_steps=10) as b:
+        b.run_steps(64)                                           # different chunking (graph replay vs direct launches)
+    assert np.array_equal(a.data[sc.probe], b.data[sc.probe])
+    sub = [3, 17, 39]
+    sub_inputs = {n: arr[sub] for n, arr in sc.trial_inputs.items()}
+    with S(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sub_inputs, trial_seeds=[seeds[i] for i in sub],
+           model=a.model) as c:
+        c.run_steps(64)
+    got, want = c.data[sc.probe], a.data[sc.probe][sub]
+    assert _rel(got, want) < 2e-3     # decoder chunking differs with batch size -> fp32 summation order, not bits
+    assert np.all(np.isfinite(a.data[sc.probe]))
+
+
+def test_full_size_config2_properties():
+    """BASELINE configs[1] sizes (40 280 neurons / trial): finite, learning active, tracks the true SSP."""
+    sc = scenarios.make_slam(n_trials=32, n_steps=300, T=200.0, distinct_tables=4)
+    slam = sc.extra["slam"]
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=32, trial_inputs=sc.trial_inputs) as sim:
+        assert sim.plan.stats["n_neurons"] == 40280 and sim.plan.stats["n_learned"] == 106700
+        sim.run_steps(300)
+        dec = sim.learned_decoders(slam.assomemory.conn_out)
+        idx = sim.cleanup_indices()
+    out = sim.data[sc.probe]
+    assert np.all(np.isfinite(out)) and np.all(np.isfinite(dec))
+    assert np.max(np.abs(dec)) > 0
+    assert np.all((idx >= 0) & (idx < 10000))
+    real = sc.real_ssp[:, :300]
+    cos = np.sum(out[:, -1] * real[:, -1], axis=1) / (np.linalg.norm(out[:, -1], axis=1) * np.linalg.norm(real[:, -1], axis=1))
+    assert np.mean(cos) > 0.6

