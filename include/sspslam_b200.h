@@ -11,8 +11,8 @@
  * Conventions: every function returns 0 on success and a negative code on failure;
  * `ssb_last_error()` gives the message (thread-local).  The caller owns all host
  * buffers; the library owns device memory.  One handle = one GPU + one stream; a
- * handle is not thread-safe.  All per-trial device arrays are laid out
- * [row][trial] with `trial` contiguous and padded to a multiple of 32.
+ * handle is not thread-safe.  Trials are padded to a multiple of 32; host-side per-trial
+ * arrays are [row][trial] with `trial` contiguous.
  */
 #ifndef SSPSLAM_B200_H
 #define SSPSLAM_B200_H
@@ -29,17 +29,19 @@ typedef struct ssb_sim ssb_sim;
  * batching extension: independent trials sharing the static weights. */
 int ssb_create(int device, int n_trials, ssb_sim** out);
 
-/* Plan upload (output of the Python lowering).  Array names: csr_ptr csr_idx csr_val
+/* Plan upload (output of the Python lowering).  Array names: csr_ptr csr_ent0 csr_ent1
  * weights ens_small ens_big dec pes cleanup gate lin_rows lin_ab stages ntypes
- * cleanup_s64.  Scalar names: dt nv nf nt nn n_act n_lenc n_ldec n_afilt n_probe
- * n_levels chunk_cap. */
+ * cleanup_s64.  Scalar names: dt nv nf nt tab_row0 nn n_act n_lenc n_ldec n_afilt n_probe
+ * n_levels chunk_cap n_part n_jtiles. */
 int ssb_set_array(ssb_sim* s, const char* name, const void* data, size_t bytes);
 int ssb_set_scalar(ssb_sim* s, const char* name, double value);
 /* Allocates the per-trial arenas (zero-filled) and uploads the plan. */
 int ssb_finalize(ssb_sim* s);
 
-/* Arena access, rows are [n_rows][n_trials_padded] float32.  Arena names:
- * "v" "ref" (neuron state), "lenc" (Voja-learned scaled encoders, row = n*dims+k),
+/* Arena access, host rows are [n_rows][n_trials_padded] float32 (the device keeps them tiled
+ * [trial_group][row][32]; the library converts).  Arena names:
+ * "st" (packed LIF state: s >= 0 voltage, s < 0 minus the remaining refractory time),
+ * "lenc" (Voja-learned scaled encoders, row = n*dims+k),
  * "ldec" (PES-learned decoders, row = j*n_pre+i), "afilt" (PES pre-synaptic trace),
  * "vec" (filter states and scratch), "act" (last activities of the wide ensembles),
  * "cidx" (int32 bits: last clean-up argmax per clean-up node).
@@ -68,7 +70,7 @@ void ssb_destroy(ssb_sim* s);
  * library stream; with profiling on, per-kernel-kind accumulated event times. */
 int ssb_set_profiling(ssb_sim* s, int on);
 int ssb_last_run_ms(ssb_sim* s, float* ms);
-/* kinds: 0 ens_small 1 ens_wide 2 decode 3 pes 4 cleanup_scan 5 cleanup_pick 6 gate 7 lin 8 advance */
+/* kinds: 0 ens_small 1 ens_wide 2 decode 3 pes 4 cleanup_scan 5 cleanup_pick 6 gate 7 lin 8 advance 9 begin */
 int ssb_kernel_times(ssb_sim* s, float* ms_per_kind, long long* launches_per_kind, int n_kinds);
 long long ssb_total_launches(ssb_sim* s);
 /* CUDA-event marks on the library stream (4 slots) and the device time between two of them:

@@ -4,6 +4,7 @@
 #include "../../include/sspslam_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -25,7 +26,7 @@ int fail(int code, const std::string& msg) {
             return fail(-2, std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
     } while (0)
 
-enum Kind { K_SMALL = 0, K_WIDE, K_DEC, K_PES, K_SCAN, K_PICK, K_GATE, K_LIN, K_ADV, K_NKINDS };
+enum Kind { K_SMALL = 0, K_WIDE, K_DEC, K_PES, K_SCAN, K_PICK, K_GATE, K_LIN, K_ADV, K_BEGIN, K_NKINDS };
 
 struct HostArray {
     std::vector<unsigned char> bytes;
@@ -40,19 +41,19 @@ struct CleanupDev {
     int n_chunks = 0, rows_per_chunk = 0, tile_rows = 0;
 };
 
-// Grid-scan geometry: shared-memory tiles of <= 48 KB of grid rows; enough chunks to fill the
-// machine at small batches, at most SSB_SCAN_MAX_CHUNKS (each chunk leaves TOPK candidates per trial).
+// Grid-scan geometry: a CTA scans rows_per_chunk grid rows in shared-memory tiles of tile_rows rows for 4 trial
+// groups.  Enough chunks for ~8 CTAs per SM (the scan is FFMA-bound and needs resident warps), at most
+// SSB_SCAN_MAX_CHUNKS (each chunk leaves TOPK candidates per trial); tiles of at most 24 KB.
 void scan_geometry(int G, int dpad, int n_groups, CleanupDev* cd) {
-    int tile_rows = std::max(1, (48 * 1024) / (dpad * (int)sizeof(float)));
-    tile_rows = std::min(tile_rows, G);
-    const int n_tiles = (G + tile_rows - 1) / tile_rows;
     const int group_ctas = (n_groups + 3) / 4;
-    int want = std::max(1, (148 * 4 + group_ctas - 1) / group_ctas);   // ~4 CTAs per SM
-    int n_chunks = std::min(std::min(n_tiles, want), SSB_SCAN_MAX_CHUNKS);
-    int tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
-    cd->rows_per_chunk = tiles_per_chunk * tile_rows;
-    cd->n_chunks = (G + cd->rows_per_chunk - 1) / cd->rows_per_chunk;
-    cd->tile_rows = tile_rows;
+    int want = std::max(1, (148 * 8 + group_ctas - 1) / group_ctas);
+    want = std::min(std::min(want, SSB_SCAN_MAX_CHUNKS), std::max(1, G / 16));
+    int rows = (G + want - 1) / want;
+    rows = (rows + 1) & ~1;                              // two rows per iteration
+    cd->rows_per_chunk = rows;
+    cd->n_chunks = (G + rows - 1) / rows;
+    const int max_tile = std::max(2, ((24 * 1024) / (dpad * (int)sizeof(float))) & ~1);
+    cd->tile_rows = std::min(rows, max_tile);
 }
 
 }  // namespace
@@ -65,8 +66,8 @@ struct ssb_sim {
     std::map<std::string, HostArray> arrays;
     std::map<std::string, double> scalars;
     // plan (device)
-    int *d_csr_ptr = nullptr, *d_csr_idx = nullptr;
-    float* d_csr_val = nullptr;
+    int* d_csr_ptr = nullptr;
+    int2 *d_ent0 = nullptr, *d_ent1 = nullptr;
     float* d_W = nullptr;
     int *d_small = nullptr, *d_big = nullptr, *d_dec = nullptr, *d_pes = nullptr, *d_cleanup = nullptr, *d_gate = nullptr;
     int* d_lin_rows = nullptr;
@@ -77,18 +78,21 @@ struct ssb_sim {
     cudaGraphExec_t step_graph = nullptr;   // graph_steps consecutive steps (the step counter lives on the device)
     int graph_steps = 0;
     bool use_graph = true;
-    long long kind_per_step[16] = {0};      // launches per step by kind (counted while capturing)
+    bool debug_sync = false, debug_failed = false;
+    long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
     std::vector<size_t> s64_offsets;
     int n_levels = 0, n_lin = 0, n_pes = 0, n_small_total = 0;
     // sizes
     long long nv = 0, nf = 0, nt = 0, nn = 0, n_act = 0, n_lenc = 0, n_ldec = 0, n_afilt = 0, n_probe = 0;
+    long long tab_row0 = 0, n_part = 0, n_counters = 0;
     int chunk_cap = 0;
     // arenas
-    float *vec = nullptr, *tab = nullptr, *v = nullptr, *ref = nullptr, *act = nullptr, *lenc = nullptr, *ldec = nullptr;
-    float *afilt = nullptr, *probe = nullptr;
+    float *vec = nullptr, *tab = nullptr, *st = nullptr, *act = nullptr, *lenc = nullptr, *ldec = nullptr;
+    float *afilt = nullptr, *probe = nullptr, *part = nullptr;
+    int* counters = nullptr;
     long long* dyn = nullptr;
     std::vector<CleanupDev> cleanups;
-    int* cidx = nullptr;  // [n_cleanup][B]
+    int* cidx = nullptr;  // [n_cleanup][B] (trial-major, not tiled)
     // host mirrors of dyn
     long long steps_done = 0, tab_step0 = 0, probe_step0 = 0;
     int tab_steps = 0;
@@ -141,19 +145,34 @@ int alloc_rows(float** p, long long rows, int B) {
 struct ArenaRef {
     float* ptr;
     long long rows;
+    bool tiled;
 };
 
 int arena(ssb_sim* s, const char* name, ArenaRef* out) {
     std::string n(name);
-    if (n == "v") *out = {s->v, s->nn};
-    else if (n == "ref") *out = {s->ref, s->nn};
-    else if (n == "act") *out = {s->act, s->n_act};
-    else if (n == "lenc") *out = {s->lenc, s->n_lenc};
-    else if (n == "ldec") *out = {s->ldec, s->n_ldec};
-    else if (n == "afilt") *out = {s->afilt, 2 * s->n_afilt};
-    else if (n == "vec") *out = {s->vec, s->nv};
-    else if (n == "cidx") *out = {reinterpret_cast<float*>(s->cidx), (long long)s->cleanups.size()};
+    if (n == "st") *out = {s->st, s->nn, true};
+    else if (n == "act") *out = {s->act, s->n_act, true};
+    else if (n == "lenc") *out = {s->lenc, s->n_lenc, true};
+    else if (n == "ldec") *out = {s->ldec, s->n_ldec, true};
+    else if (n == "afilt") *out = {s->afilt, 2 * s->n_afilt, true};
+    else if (n == "vec") *out = {s->vec, s->nv, true};
+    else if (n == "cidx") *out = {reinterpret_cast<float*>(s->cidx), (long long)s->cleanups.size(), false};
     else return fail(-3, "unknown arena '" + n + "'");
+    return 0;
+}
+
+// Host rows are [n_rows][B] (trial contiguous); device arenas are tiled [G][arena_rows][32].
+// One strided 2-D copy per trial group moves n_rows lines of 128 bytes.
+int copy_rows(ssb_sim* s, float* dev_base, long long arena_rows, size_t row0, size_t n_rows, float* host, bool to_device) {
+    const size_t B = s->B;
+    for (int g = 0; g < s->n_groups; ++g) {
+        float* d = dev_base + ((size_t)g * arena_rows + row0) * 32;
+        float* h = host + (size_t)g * 32;
+        if (to_device)
+            SSB_CUDA(cudaMemcpy2DAsync(d, 128, h, B * sizeof(float), 128, n_rows, cudaMemcpyHostToDevice, s->stream));
+        else
+            SSB_CUDA(cudaMemcpy2DAsync(h, B * sizeof(float), d, 128, 128, n_rows, cudaMemcpyDeviceToHost, s->stream));
+    }
     return 0;
 }
 
@@ -171,7 +190,8 @@ cudaEvent_t* next_events(ssb_sim* s, int kind) {
 struct LaunchTimer {
     ssb_sim* s;
     cudaEvent_t* ev = nullptr;
-    LaunchTimer(ssb_sim* s_, int kind) : s(s_) {
+    int kind;
+    LaunchTimer(ssb_sim* s_, int kind_) : s(s_), kind(kind_) {
         s->kind_launches[kind]++;
         s->total_launches++;
         if (s->profiling) {
@@ -181,6 +201,14 @@ struct LaunchTimer {
     }
     ~LaunchTimer() {
         if (ev) cudaEventRecord(ev[1], s->stream);
+        if (s->debug_sync && !s->debug_failed) {   // SSB_DEBUG_SYNC=1: find the launch that faults
+            cudaError_t e = cudaStreamSynchronize(s->stream);
+            if (e != cudaSuccess) {
+                s->debug_failed = true;
+                fprintf(stderr, "[ssb] kernel kind %d (launch #%lld) failed: %s\n", kind, s->total_launches,
+                        cudaGetErrorString(e));
+            }
+        }
     }
 };
 
@@ -198,45 +226,49 @@ int collect_profile(ssb_sim* s) {
 
 template <int DP>
 void launch_scan(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const float* S, const CleanupDev& cd,
-                 int dpad, int n_groups) {
+                 int dpad, int n_groups, int i_rel) {
     dim3 grid(cd.n_chunks, (n_groups + 3) / 4);
     size_t smem = (size_t)cd.tile_rows * dpad * sizeof(float);
     if (DP == 0) smem += (size_t)4 * dpad * 32 * sizeof(float);
+    const int n_cand = cd.n_chunks * SSB_TOPK;
     if (csr)
         k_cleanup_scan<DP, true><<<grid, 128, smem, st>>>(c, desc, S, cd.cx, cd.pval, cd.pidx, cd.rows_per_chunk,
-                                                           cd.tile_rows, n_groups);
+                                                           cd.tile_rows, n_groups, n_cand, i_rel);
     else
         k_cleanup_scan<DP, false><<<grid, 128, smem, st>>>(c, desc, S, cd.cx, cd.pval, cd.pidx, cd.rows_per_chunk,
-                                                            cd.tile_rows, n_groups);
+                                                            cd.tile_rows, n_groups, n_cand, i_rel);
 }
 
 void dispatch_scan(cudaStream_t st, bool csr, int dpad, int n_groups, const SsbCtx& c, const int* desc, const float* S,
-                   const CleanupDev& cd) {
-    if (dpad == 56) launch_scan<56>(st, csr, c, desc, S, cd, dpad, n_groups);
-    else if (dpad == 100) launch_scan<100>(st, csr, c, desc, S, cd, dpad, n_groups);
-    else launch_scan<0>(st, csr, c, desc, S, cd, dpad, n_groups);
+                   const CleanupDev& cd, int i_rel) {
+    if (dpad == 56) launch_scan<56>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
+    else if (dpad == 100) launch_scan<100>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
+    else launch_scan<0>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
 }
 
 void scan_smem_optin() {
     const int lim = 200 * 1024;
     cudaFuncSetAttribute(k_cleanup_scan<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_cleanup_scan<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_cleanup_scan<56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_cleanup_scan<56, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_cleanup_scan<100, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_cleanup_scan<100, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
 }
 
 template <int DP>
-void launch_wide(ssb_sim* s, int item0, int n_items, int max_n, int smem) {
+void launch_wide(ssb_sim* s, int item0, int n_items, int max_n, int smem, int i_rel) {
     const int chunk = 64;   // neurons per CTA: 4 warps x 16
     dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, n_items);
-    k_ens_wide<DP><<<grid, 128, smem, s->stream>>>(s->ctx, s->d_big, item0, chunk);
+    k_ens_wide<DP><<<grid, 128, smem, s->stream>>>(s->ctx, s->d_big, item0, chunk, i_rel);
 }
 
-int one_step(ssb_sim* s) {
+// One simulator step = this launch sequence; `i_rel` is the step's offset from the device-side step
+// counter dyn[0], which ssb_run_steps advances once per call (or once per replayed graph).
+int one_step(ssb_sim* s, int i_rel) {
     const SsbCtx& c = s->ctx;
     const int G = s->n_groups;
+    if (s->nt > 0) {
+        LaunchTimer t(s, K_BEGIN);
+        dim3 grid(((int)s->nt + 3) / 4, G);
+        k_begin<<<grid, 128, 0, s->stream>>>(c, i_rel);
+    }
     for (int lvl = 0; lvl < s->n_levels; ++lvl) {
         const int* st = &s->h_stages[lvl * 10];
         if (st[1] > 0) {
@@ -246,7 +278,7 @@ int one_step(ssb_sim* s) {
             while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
             const int packed_warps = (st[1] - n_split) * G;
             const int blocks = n_split * G + (packed_warps + 3) / 4;
-            k_ens_small<<<blocks, 128, 0, s->stream>>>(c, s->d_small + st[0] * 9, st[1], n_split, G);
+            k_ens_small<<<blocks, 128, 0, s->stream>>>(c, s->d_small + st[0] * 9, st[1], n_split, i_rel);
         }
         if (st[3] > 0) {
             LaunchTimer t(s, K_WIDE);
@@ -257,9 +289,9 @@ int one_step(ssb_sim* s) {
                 max_n[cls] = std::max(max_n[cls], d[0]);
                 max_sm[cls] = std::max(max_sm[cls], (d[2] + d[11]) * 32 * (int)sizeof(float));
             }
-            if (max_n[0]) launch_wide<56>(s, st[2], st[3], max_n[0], max_sm[0]);
-            if (max_n[1]) launch_wide<100>(s, st[2], st[3], max_n[1], max_sm[1]);
-            if (max_n[2]) launch_wide<0>(s, st[2], st[3], max_n[2], max_sm[2]);
+            if (max_n[0]) launch_wide<56>(s, st[2], st[3], max_n[0], max_sm[0], i_rel);
+            if (max_n[1]) launch_wide<100>(s, st[2], st[3], max_n[1], max_sm[1], i_rel);
+            if (max_n[2]) launch_wide<0>(s, st[2], st[3], max_n[2], max_sm[2], i_rel);
         }
         for (int i = 0; i < st[7]; ++i) {
             const int ci = st[6] + i;
@@ -267,26 +299,25 @@ int one_step(ssb_sim* s) {
             const CleanupDev& cd = s->cleanups[ci];
             {
                 LaunchTimer t(s, K_SCAN);
-                dispatch_scan(s->stream, true, d[2], G, c, s->d_cleanup + ci * 6, s->d_W + d[3], cd);
+                dispatch_scan(s->stream, true, d[2], G, c, s->d_cleanup + ci * 6, s->d_W + d[3], cd, i_rel);
             }
             {
                 LaunchTimer t(s, K_PICK);
-                k_cleanup_pick<<<G, 256, 0, s->stream>>>(s->B, d[1], d[2], cd.n_chunks * SSB_TOPK, cd.cx, cd.pval, cd.pidx,
-                                                         cd.s64, s->d_W + d[3], s->vec + (size_t)d[5] * s->B, cd.idx,
-                                                         nullptr, 0, 0);
+                k_cleanup_pick<<<G, 256, 0, s->stream>>>(d[1], d[2], cd.n_chunks * SSB_TOPK, cd.cx, cd.pval, cd.pidx, cd.s64,
+                                                         s->d_W + d[3], s->vec, (int)s->nv, d[5], cd.idx, nullptr, 0, 0);
             }
         }
         if (st[9] > 0) {
             LaunchTimer t(s, K_GATE);
             dim3 grid(G, st[9]);
-            k_gate<<<grid, 256, 0, s->stream>>>(c, s->d_gate, st[8]);
+            k_gate<<<grid, 256, 0, s->stream>>>(c, s->d_gate, st[8], i_rel);
         }
         if (st[5] > 0) {
             LaunchTimer t(s, K_DEC);
             int max_out = 0, max_chunks = 1;
             for (int i = 0; i < st[5]; ++i) {
-                max_out = std::max(max_out, s->h_dec[(st[4] + i) * 7 + 1]);
-                max_chunks = std::max(max_chunks, s->h_dec[(st[4] + i) * 7 + 6]);
+                max_out = std::max(max_out, s->h_dec[(st[4] + i) * 9 + 1]);
+                max_chunks = std::max(max_chunks, s->h_dec[(st[4] + i) * 9 + 6]);
             }
             dim3 grid((max_out + 7) / 8, G, st[5] * max_chunks);
             k_decode<<<grid, 128, 0, s->stream>>>(c, s->d_dec, st[4], max_chunks);
@@ -296,26 +327,27 @@ int one_step(ssb_sim* s) {
         LaunchTimer t(s, K_PES);
         int max_out = 0, max_chunks = 1;
         for (int i = 0; i < s->n_pes; ++i) {
-            max_out = std::max(max_out, s->h_pes[i * 11 + 1]);
-            max_chunks = std::max(max_chunks, s->h_pes[i * 11 + 10]);
+            max_out = std::max(max_out, s->h_pes[i * 13 + 1]);
+            max_chunks = std::max(max_chunks, s->h_pes[i * 13 + 10]);
         }
         dim3 grid((max_out + 7) / 8, G, s->n_pes * max_chunks);
-        k_pes<<<grid, 128, 0, s->stream>>>(c, s->d_pes, max_chunks);
+        k_pes<<<grid, 128, 0, s->stream>>>(c, s->d_pes, max_chunks, i_rel);
     }
-    if (s->n_lin > 0) {
+    if (s->n_lin > 0 && !getenv("SSB_SKIP_LIN")) {
         LaunchTimer t(s, K_LIN);
         dim3 grid((s->n_lin + 3) / 4, G);
-        k_lin<<<grid, 128, 0, s->stream>>>(c, s->d_lin_rows, s->d_lin_ab, s->n_lin);
-    }
-    {
-        LaunchTimer t(s, K_ADV);
-        k_advance<<<1, 1, 0, s->stream>>>(s->dyn);
+        k_lin<<<grid, 128, 0, s->stream>>>(c, s->d_lin_rows, s->d_lin_ab, s->n_lin, i_rel);
     }
     return 0;
 }
 
-// Capture `n` consecutive steps into an executable graph.  Step parity, table row and probe row are
-// derived on the device from dyn[], so one graph is valid for any starting step.
+void advance(ssb_sim* s, int n) {
+    LaunchTimer t(s, K_ADV);
+    k_advance<<<1, 1, 0, s->stream>>>(s->dyn, n);
+}
+
+// Capture `n` consecutive steps (+ one counter advance) into an executable graph.  Step parity, table
+// row and probe row are derived on the device from dyn[], so one graph is valid for any starting step.
 int build_graph(ssb_sim* s, int n) {
     cudaGraph_t g = nullptr;
     const bool prof = s->profiling;
@@ -324,9 +356,10 @@ int build_graph(ssb_sim* s, int n) {
     memcpy(saved, s->kind_launches, sizeof(saved));
     const long long saved_total = s->total_launches;
     SSB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-    for (int i = 0; i < n; ++i) one_step(s);
+    for (int i = 0; i < n; ++i) one_step(s, i);
+    advance(s, n);
     cudaError_t e = cudaStreamEndCapture(s->stream, &g);
-    for (int k = 0; k < K_NKINDS; ++k) s->kind_per_step[k] = (s->kind_launches[k] - saved[k]) / n;
+    for (int k = 0; k < K_NKINDS; ++k) s->kind_per_graph[k] = s->kind_launches[k] - saved[k];
     memcpy(s->kind_launches, saved, sizeof(saved));
     s->total_launches = saved_total;
     s->profiling = prof;
@@ -362,6 +395,8 @@ int ssb_create(int device, int n_trials, ssb_sim** out) {
     s->n_trials = n_trials;
     s->B = (n_trials + 31) / 32 * 32;
     s->n_groups = s->B / 32;
+    if (const char* e = getenv("SSB_DEBUG_SYNC")) s->debug_sync = e[0] == '1';
+    if (s->debug_sync) s->use_graph = false;
     SSB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     SSB_CUDA(cudaEventCreate(&s->ev_run0));
     SSB_CUDA(cudaEventCreate(&s->ev_run1));
@@ -390,12 +425,15 @@ int ssb_finalize(ssb_sim* s) {
     s->nv = iscalar(s, "nv");
     s->nf = iscalar(s, "nf");
     s->nt = iscalar(s, "nt");
+    s->tab_row0 = iscalar(s, "tab_row0");
     s->nn = iscalar(s, "nn");
     s->n_act = iscalar(s, "n_act");
     s->n_lenc = iscalar(s, "n_lenc");
     s->n_ldec = iscalar(s, "n_ldec");
     s->n_afilt = iscalar(s, "n_afilt");
     s->n_probe = iscalar(s, "n_probe");
+    s->n_part = iscalar(s, "n_part");
+    s->n_counters = iscalar(s, "n_jtiles") * s->n_groups;
     s->n_levels = (int)iscalar(s, "n_levels");
     s->chunk_cap = (int)iscalar(s, "chunk_cap");
     if (s->nv < 1 || s->chunk_cap < 1 || s->n_levels < 1) return fail(-1, "ssb_finalize: plan scalars missing");
@@ -403,15 +441,15 @@ int ssb_finalize(ssb_sim* s) {
 
     size_t cnt = 0;
     if (upload_array(s, "csr_ptr", &s->d_csr_ptr)) return -2;
-    if (upload_array(s, "csr_idx", &s->d_csr_idx)) return -2;
-    if (upload_array(s, "csr_val", &s->d_csr_val)) return -2;
+    if (upload_array(s, "csr_ent0", &s->d_ent0)) return -2;
+    if (upload_array(s, "csr_ent1", &s->d_ent1)) return -2;
     if (upload_array(s, "weights", &s->d_W)) return -2;
     if (upload_array(s, "ens_small", &s->d_small, &cnt)) return -2;
     s->n_small_total = (int)(cnt / 9);
     if (upload_array(s, "ens_big", &s->d_big)) return -2;
     if (upload_array(s, "dec", &s->d_dec)) return -2;
     if (upload_array(s, "pes", &s->d_pes, &cnt)) return -2;
-    s->n_pes = (int)(cnt / 11);
+    s->n_pes = (int)(cnt / 13);
     if (upload_array(s, "cleanup", &s->d_cleanup)) return -2;
     if (upload_array(s, "gate", &s->d_gate)) return -2;
     if (upload_array(s, "lin_rows", &s->d_lin_rows, &cnt)) return -2;
@@ -426,22 +464,28 @@ int ssb_finalize(ssb_sim* s) {
     s->h_cleanup = host_ints(s, "cleanup");
     s->h_pes = host_ints(s, "pes");
     if ((int)s->h_stages.size() != s->n_levels * 10) return fail(-1, "ssb_finalize: stages array has wrong size");
+    for (size_t i = 0; i + 8 < s->h_small.size(); i += 9)
+        if (s->h_small[i + 8] > SSB_SM_WMAX || (s->h_small[i + 8] & 3))
+            return fail(-1, "ssb_finalize: narrow-ensemble weight stride out of range");
 
     const int B = s->B;
     if (alloc_rows(&s->vec, s->nv, B)) return -2;
-    if (alloc_rows(&s->v, s->nn, B)) return -2;
-    if (alloc_rows(&s->ref, s->nn, B)) return -2;
+    if (alloc_rows(&s->st, s->nn, B)) return -2;
     if (alloc_rows(&s->act, s->n_act, B)) return -2;
     if (alloc_rows(&s->lenc, s->n_lenc, B)) return -2;
     if (alloc_rows(&s->ldec, s->n_ldec, B)) return -2;
     if (alloc_rows(&s->afilt, 2 * s->n_afilt, B)) return -2;
+    if (alloc_rows(&s->part, s->n_part, B)) return -2;
     if (alloc_rows(&s->tab, (long long)s->chunk_cap * std::max(1LL, s->nt), B)) return -2;
     if (alloc_rows(&s->probe, (long long)s->chunk_cap * std::max(1LL, s->n_probe), B)) return -2;
+    SSB_CUDA(cudaMalloc((void**)&s->counters, (size_t)std::max(1LL, s->n_counters) * sizeof(int)));
+    SSB_CUDA(cudaMemset(s->counters, 0, (size_t)std::max(1LL, s->n_counters) * sizeof(int)));
     SSB_CUDA(cudaMalloc((void**)&s->dyn, 4 * sizeof(long long)));
     SSB_CUDA(cudaMemset(s->dyn, 0, 4 * sizeof(long long)));
-    {
-        std::vector<float> ones(B, 1.0f);
-        SSB_CUDA(cudaMemcpy(s->vec, ones.data(), B * sizeof(float), cudaMemcpyHostToDevice));
+    {   // vec row 0 = ones, for every trial group
+        std::vector<float> ones(32, 1.0f);
+        for (int g = 0; g < s->n_groups; ++g)
+            SSB_CUDA(cudaMemcpy(s->vec + (size_t)g * s->nv * 32, ones.data(), 32 * sizeof(float), cudaMemcpyHostToDevice));
     }
     const int n_cleanup = (int)(s->h_cleanup.size() / 6);
     s->cleanups.resize(n_cleanup);
@@ -470,25 +514,35 @@ int ssb_finalize(ssb_sim* s) {
     scan_smem_optin();
 
     SsbCtx& c = s->ctx;
-    c.B = B;
+    c.G = s->n_groups;
+    c.nv = (int)s->nv;
     c.nf = (int)s->nf;
     c.nt = (int)s->nt;
-    c.n_probe = (int)s->n_probe;
+    c.tab_row0 = (int)s->tab_row0;
+    c.nn = (int)std::max(1LL, s->nn);
+    c.n_act = (int)std::max(1LL, s->n_act);
+    c.n_lenc = (int)std::max(1LL, s->n_lenc);
+    c.n_ldec = (int)std::max(1LL, s->n_ldec);
     c.n_afilt = (int)s->n_afilt;
+    c.n_probe = (int)s->n_probe;
+    c.n_part = (int)std::max(1LL, s->n_part);
+    c.tab_cap = s->chunk_cap;
+    c.probe_cap = s->chunk_cap;
     c.dt = (float)dt;
     c.vec = s->vec;
     c.tab = s->tab;
-    c.v = s->v;
-    c.ref = s->ref;
+    c.st = s->st;
     c.act = s->act;
     c.lenc = s->lenc;
     c.ldec = s->ldec;
     c.afilt = s->afilt;
     c.probe = s->probe;
+    c.part = s->part;
+    c.counters = s->counters;
     c.W = s->d_W;
     c.csr_ptr = s->d_csr_ptr;
-    c.csr_idx = s->d_csr_idx;
-    c.csr_val = s->d_csr_val;
+    c.ent0 = s->d_ent0;
+    c.ent1 = s->d_ent1;
     c.ntypes = s->d_ntypes;
     c.dyn = s->dyn;
     s->finalized = true;
@@ -502,7 +556,11 @@ int ssb_upload(ssb_sim* s, const char* name, size_t row0, size_t n_rows, const f
     if (arena(s, name, &a)) return -3;
     if ((long long)(row0 + n_rows) > a.rows) return fail(-1, "ssb_upload: rows out of range");
     SSB_CUDA(cudaSetDevice(s->device));
-    SSB_CUDA(cudaMemcpyAsync(a.ptr + row0 * s->B, host, n_rows * s->B * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    if (a.tiled) {
+        if (copy_rows(s, a.ptr, std::max(1LL, a.rows), row0, n_rows, const_cast<float*>(host), true)) return -2;
+    } else {
+        SSB_CUDA(cudaMemcpyAsync(a.ptr + row0 * s->B, host, n_rows * s->B * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    }
     SSB_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -513,7 +571,11 @@ int ssb_download(ssb_sim* s, const char* name, size_t row0, size_t n_rows, float
     if (arena(s, name, &a)) return -3;
     if ((long long)(row0 + n_rows) > a.rows) return fail(-1, "ssb_download: rows out of range");
     SSB_CUDA(cudaSetDevice(s->device));
-    SSB_CUDA(cudaMemcpyAsync(host, a.ptr + row0 * s->B, n_rows * s->B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (a.tiled) {
+        if (copy_rows(s, a.ptr, std::max(1LL, a.rows), row0, n_rows, host, false)) return -2;
+    } else {
+        SSB_CUDA(cudaMemcpyAsync(host, a.ptr + row0 * s->B, n_rows * s->B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    }
     SSB_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -524,8 +586,9 @@ int ssb_set_tables(ssb_sim* s, const float* host, long long step0, int n_steps) 
     SSB_CUDA(cudaSetDevice(s->device));
     if (s->nt > 0 && n_steps > 0) {
         if (!host) return fail(-1, "ssb_set_tables: null host buffer");
-        SSB_CUDA(cudaMemcpyAsync(s->tab, host, (size_t)n_steps * s->nt * s->B * sizeof(float), cudaMemcpyHostToDevice,
-                                 s->stream));
+        // host [n_steps][nt][B] -> device [G][chunk_cap][nt][32]: one strided copy per trial group
+        if (copy_rows(s, s->tab, (long long)s->chunk_cap * s->nt, 0, (size_t)n_steps * s->nt, const_cast<float*>(host), true))
+            return -2;
     }
     s->tab_step0 = step0;
     s->tab_steps = n_steps;
@@ -555,15 +618,21 @@ int ssb_run_steps(ssb_sim* s, int n_steps) {
             if (build_graph(s, gs)) return -2;
         }
         if (s->step_graph) {
-            for (; i + s->graph_steps <= n_steps; i += s->graph_steps) SSB_CUDA(cudaGraphLaunch(s->step_graph, s->stream));
+            int replays = 0;
+            for (; i + s->graph_steps <= n_steps; i += s->graph_steps, ++replays)
+                SSB_CUDA(cudaGraphLaunch(s->step_graph, s->stream));
             for (int k = 0; k < K_NKINDS; ++k) {   // account the replayed kernel launches
-                s->kind_launches[k] += (long long)i * s->kind_per_step[k];
-                s->total_launches += (long long)i * s->kind_per_step[k];
+                s->kind_launches[k] += (long long)replays * s->kind_per_graph[k];
+                s->total_launches += (long long)replays * s->kind_per_graph[k];
             }
         }
     }
-    for (; i < n_steps; ++i) {
-        if (one_step(s)) return -2;
+    if (i < n_steps) {
+        const int rest = n_steps - i;
+        for (int r = 0; r < rest; ++r) {
+            if (one_step(s, r)) return -2;
+        }
+        advance(s, rest);
     }
     SSB_CUDA(cudaEventRecord(s->ev_run1, s->stream));
     s->run_timed = true;
@@ -578,9 +647,10 @@ int ssb_read_probes(ssb_sim* s, float* host, long long step0, int n_steps) {
         return fail(-4, "ssb_read_probes: steps not in the probe buffer");
     if (s->n_probe == 0 || n_steps == 0) return 0;
     SSB_CUDA(cudaSetDevice(s->device));
-    const size_t row = (size_t)s->n_probe * s->B;
-    SSB_CUDA(cudaMemcpyAsync(host, s->probe + (size_t)(step0 - s->probe_step0) * row, (size_t)n_steps * row * sizeof(float),
-                             cudaMemcpyDeviceToHost, s->stream));
+    // device [G][chunk_cap][n_probe][32] -> host [n_steps][n_probe][B]
+    if (copy_rows(s, s->probe, (long long)s->chunk_cap * s->n_probe, (size_t)(step0 - s->probe_step0) * s->n_probe,
+                  (size_t)n_steps * s->n_probe, host, false))
+        return -2;
     SSB_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -600,13 +670,23 @@ int ssb_reset(ssb_sim* s) {
     if (!s || !s->finalized) return fail(-1, "ssb_reset: bad handle");
     SSB_CUDA(cudaSetDevice(s->device));
     const size_t B = s->B;
-    SSB_CUDA(cudaMemsetAsync(s->vec + B, 0, (size_t)(s->nv - 1) * B * sizeof(float), s->stream));
-    SSB_CUDA(cudaMemsetAsync(s->v, 0, (size_t)std::max(1LL, s->nn) * B * sizeof(float), s->stream));
-    SSB_CUDA(cudaMemsetAsync(s->ref, 0, (size_t)std::max(1LL, s->nn) * B * sizeof(float), s->stream));
-    SSB_CUDA(cudaMemsetAsync(s->act, 0, (size_t)std::max(1LL, s->n_act) * B * sizeof(float), s->stream));
-    SSB_CUDA(cudaMemsetAsync(s->lenc, 0, (size_t)std::max(1LL, s->n_lenc) * B * sizeof(float), s->stream));
-    SSB_CUDA(cudaMemsetAsync(s->ldec, 0, (size_t)std::max(1LL, s->n_ldec) * B * sizeof(float), s->stream));
-    SSB_CUDA(cudaMemsetAsync(s->afilt, 0, (size_t)std::max(1LL, 2 * s->n_afilt) * B * sizeof(float), s->stream));
+    auto zero = [&](float* p, long long rows) {
+        return cudaMemsetAsync(p, 0, (size_t)std::max(1LL, rows) * B * sizeof(float), s->stream);
+    };
+    SSB_CUDA(zero(s->vec, s->nv));
+    SSB_CUDA(zero(s->st, s->nn));
+    SSB_CUDA(zero(s->act, s->n_act));
+    SSB_CUDA(zero(s->lenc, s->n_lenc));
+    SSB_CUDA(zero(s->ldec, s->n_ldec));
+    SSB_CUDA(zero(s->afilt, 2 * s->n_afilt));
+    SSB_CUDA(cudaMemsetAsync(s->counters, 0, (size_t)std::max(1LL, s->n_counters) * sizeof(int), s->stream));
+    {
+        std::vector<float> ones(32, 1.0f);
+        for (int g = 0; g < s->n_groups; ++g)
+            SSB_CUDA(cudaMemcpyAsync(s->vec + (size_t)g * s->nv * 32, ones.data(), 32 * sizeof(float), cudaMemcpyHostToDevice,
+                                     s->stream));
+        SSB_CUDA(cudaStreamSynchronize(s->stream));
+    }
     s->steps_done = 0;
     s->probe_step0 = 0;
     if (push_dyn(s)) return -2;
@@ -618,9 +698,9 @@ void ssb_destroy(ssb_sim* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    void* ptrs[] = {s->d_csr_ptr, s->d_csr_idx, s->d_csr_val, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
-                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_ntypes, s->d_s64, s->vec, s->tab, s->v, s->ref, s->act,
-                    s->lenc, s->ldec, s->afilt, s->probe, s->dyn, s->cidx};
+    void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
+                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& cd : s->cleanups) {
@@ -760,16 +840,16 @@ int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* q
     SSB_CUDA(cudaMemcpy(ddesc, hdesc, sizeof(hdesc), cudaMemcpyHostToDevice));
     SsbCtx c;
     memset(&c, 0, sizeof(c));
-    c.B = B;
+    c.G = B / 32;
     cd.cx = cx;
     cd.pval = pval;
     cd.pidx = pidx;
     for (long long q0 = 0; q0 < n_q; q0 += B) {
         const long long nb = std::min<long long>(B, n_q - q0);
         k_decode_prep<<<(B + 127) / 128, 128>>>(dq, cx, n_q, B, d, dpad, q0);
-        dispatch_scan(nullptr, false, dpad, B / 32, c, ddesc, dS32, cd);
+        dispatch_scan(nullptr, false, dpad, B / 32, c, ddesc, dS32, cd, 0);
         // near-ties are re-scored against the float64 grid with the float64 query
-        k_cleanup_pick<<<B / 32, 256>>>(B, d, dpad, cd.n_chunks * SSB_TOPK, cx, pval, pidx, dS64, dS32, nullptr, didx, dq,
+        k_cleanup_pick<<<B / 32, 256>>>(d, dpad, cd.n_chunks * SSB_TOPK, cx, pval, pidx, dS64, dS32, nullptr, 0, 0, didx, dq,
                                         q0, n_q);
         SSB_CUDA(cudaGetLastError());
         SSB_CUDA(cudaMemcpy(idx_out + q0, didx, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));

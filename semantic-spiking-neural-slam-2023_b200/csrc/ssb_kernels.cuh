@@ -1,139 +1,161 @@
 // sm_100a kernels of the SSP-SLAM step engine (device side).
 //
-// Layout rule: every per-trial array is [row][trial]; a warp's 32 lanes are 32
-// consecutive trials, so state loads/stores are 128-byte coalesced and everything
-// indexed by neuron / weight is warp-uniform (broadcast from L1/L2).  Static weights
-// are shared by all trials; learned matrices (Voja encoders, PES decoders) are
-// per-trial rows of the same [row][trial] form.
+// Layout rule: every per-trial arena is tiled by trial group, arena[g][row][32]: a warp's 32
+// lanes are the 32 trials of one group, a row is one 128-byte line, and consecutive rows of one
+// group are contiguous, so each warp streams a sequential address range (DRAM-page friendly) and
+// whole neuron ranges can be moved by 1-D TMA bulk copies.  Everything indexed by neuron /
+// weight is warp-uniform (broadcast from shared memory or L1/L2).  Static weights are shared by
+// all trials; learned matrices (Voja encoders, PES decoders) are per-trial rows of the same form.
 //
-// Semantics restate nengo's operators, executed in
-// dependency levels instead of one operator at a time; the CPU checker is
-// oracle/nengo_ref_sim.py.
+// LIF state is ONE word per neuron: s >= 0 is the membrane voltage of a neuron that is not
+// refractory, s < 0 is minus the remaining refractory time (the voltage is exactly 0 then).  With
+// nengo's default min_voltage = 0 this is equivalent to the (voltage, refractory_time) pair: the
+// refractory time only matters while it is >= dt, and the voltage is pinned to 0 exactly then.
+//
+// Semantics restate nengo's operators, executed in dependency
+// levels instead of one operator at a time; the CPU checker is oracle/nengo_ref_sim.py.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
-#define SSB_TAB_BASE (1 << 24)
 #define SSB_TOPK 4
-#define SSB_SCAN_MAX_CHUNKS 256
+#define SSB_SCAN_MAX_CHUNKS 512
+#define SSB_SM_CH 16          // neurons per TMA-staged chunk of the narrow-ensemble kernel
+#define SSB_SM_WMAX 16        // max packed weight stride (floats) of a narrow ensemble
 
 struct SsbCtx {
-    int B, nf, nt, n_probe, n_afilt;
+    int G;                    // trial groups (32 trials each)
+    int nv, nf, nt, tab_row0, nn, n_act, n_lenc, n_ldec, n_afilt, n_probe, n_part;
+    int tab_cap, probe_cap;
     float dt;
-    float* vec;          // [nv][B]   0: ones | 1..nf: filters A | nf+1..2nf: filters B | scratch
-    const float* tab;    // [tab_cap][nt][B]
-    float* v;            // [nn][B]
-    float* ref;          // [nn][B]
-    float* act;          // [n_act][B]
-    float* lenc;         // [n_lenc][B]
-    float* ldec;         // [n_ldec][B]
-    float* afilt;        // [2][n_afilt][B]
-    float* probe;        // [probe_cap][n_probe][B]
-    const float* W;      // shared static weights
+    float* vec;               // [G][nv][32]   0: ones | 1..nf: filters A | nf+1..2nf: filters B | tables | scratch
+    const float* tab;         // [G][tab_cap][nt][32]
+    float* st;                // [G][nn][32]   packed LIF state
+    float* act;               // [G][n_act][32]
+    float* lenc;              // [G][n_lenc][32]
+    float* ldec;              // [G][n_ldec][32]
+    float* afilt;             // [G][2*n_afilt][32]
+    float* probe;             // [G][probe_cap][n_probe][32]
+    float* part;              // [G][n_part][32] split-K partial sums of decode / PES launches
+    int* counters;            // split-K arrival counters, self-resetting
+    const float* W;           // shared static weights
     const int* csr_ptr;
-    const int* csr_idx;
-    const float* csr_val;
-    const float* ntypes; // [n][5] = type, tau_rc, tau_ref, min_voltage, amplitude
-    const long long* dyn;  // [0] completed steps, [1] first step of resident tables, [2] first step of probe buffer
+    const int2* ent0;         // CSR entries (vec row, coefficient bits) resolved for even steps
+    const int2* ent1;         //   ... and for odd steps (filter columns point at the other half)
+    const float* ntypes;      // [n][8] = type, tau_rc, tau_ref, min_voltage, amplitude, fast_math, -, -
+    const long long* dyn;     // [0] completed steps, [1] first step of resident tables, [2] first step of probe buffer
 };
 
 struct SsbStep {
     long long step;
-    int par_old, par_new;     // row offset added to filter columns (0 or nf)
-    const float* tabrow;      // table rows of this step
+    int odd;
+    const int2* ent_old;      // rows evaluated on the values this step reads (old filter states)
+    const int2* ent_new;      // ... on the half the previous step read (PES error of step-1)
+    int par_old, par_new;     // row offset of the filter half read / written this step
 };
 
-__device__ __forceinline__ SsbStep ssb_step(const SsbCtx& c) {
+__device__ __forceinline__ SsbStep ssb_step(const SsbCtx& c, int i_rel) {
     SsbStep s;
-    s.step = c.dyn[0];
-    const int odd = (int)(s.step & 1);
-    s.par_old = odd ? c.nf : 0;
-    s.par_new = odd ? 0 : c.nf;
-    s.tabrow = c.tab + (size_t)(s.step - c.dyn[1]) * (size_t)c.nt * (size_t)c.B;
+    s.step = c.dyn[0] + i_rel;
+    s.odd = (int)(s.step & 1);
+    s.ent_old = s.odd ? c.ent1 : c.ent0;
+    s.ent_new = s.odd ? c.ent0 : c.ent1;
+    s.par_old = s.odd ? c.nf : 0;
+    s.par_new = s.odd ? 0 : c.nf;
     return s;
 }
 
-// One sink row: sparse linear combination of source columns for one trial.
-// Warp-cooperative: all 32 lanes (= 32 trials) evaluate the same row, so the (column, coef)
-// pairs are fetched 32 at a time with one coalesced load and broadcast by shuffle; the
-// per-trial source loads of a batch are independent, so 8 of them are in flight at once.
-// MUST be called by all 32 lanes of a warp with the same `row`.
-__device__ __forceinline__ const float* ssb_src(const SsbCtx& c, const SsbStep& s, int idx, int par) {
-    if (idx >= SSB_TAB_BASE) return s.tabrow + (size_t)(idx - SSB_TAB_BASE) * c.B;
-    if (idx >= 1 && idx <= c.nf) idx += par;
-    return c.vec + (size_t)idx * c.B;
+// Group base pointers (lane already added): element of row r is p[r * 32].
+__device__ __forceinline__ float* ssb_grp(float* base, int rows, int g, int lane) {
+    return base + ((size_t)g * rows) * 32 + lane;
 }
 
-__device__ __forceinline__ float ssb_row(const SsbCtx& c, const SsbStep& s, int row, int trial, int par) {
-    const int lo = __ldg(c.csr_ptr + row), hi = __ldg(c.csr_ptr + row + 1);
-    const int lane = threadIdx.x & 31;
+// One sink row: sparse linear combination of vec rows for the 32 trials of a group.  Entries are
+// warp-uniform 8-byte loads; the host pads every row to a multiple of 8 entries with (row 0,
+// coefficient 0), so the loop has no tail and the 8 per-trial source loads of a batch are independent.
+__device__ __forceinline__ float ssb_row(const int* __restrict__ ptr, const int2* __restrict__ ent, int row,
+                                         const float* vg) {
+    const int lo = __ldg(ptr + row), hi = __ldg(ptr + row + 1);
     float acc = 0.f;
-    for (int base = lo; base < hi; base += 32) {
-        const int cnt = min(32, hi - base);
-        int my_idx = 0;
-        float my_val = 0.f;
-        if (lane < cnt) {
-            my_idx = __ldg(c.csr_idx + base + lane);
-            my_val = __ldg(c.csr_val + base + lane);
-        }
-        int j = 0;
-        for (; j + 8 <= cnt; j += 8) {
-            float xv[8], cv[8];
+    for (int p = lo; p < hi; p += 8) {
+        int2 e[8];
+        float x[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int idx = __shfl_sync(0xffffffffu, my_idx, j + u);
-                cv[u] = __shfl_sync(0xffffffffu, my_val, j + u);
-                xv[u] = ssb_src(c, s, idx, par)[trial];
-            }
+        for (int u = 0; u < 8; ++u) e[u] = __ldg(ent + p + u);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc = fmaf(cv[u], xv[u], acc);
-        }
-        for (; j < cnt; ++j) {
-            const int idx = __shfl_sync(0xffffffffu, my_idx, j);
-            const float cv = __shfl_sync(0xffffffffu, my_val, j);
-            acc = fmaf(cv, ssb_src(c, s, idx, par)[trial], acc);
-        }
+        for (int u = 0; u < 8; ++u) x[u] = vg[(size_t)e[u].x * 32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(__int_as_float(e[u].y), x[u], acc);
     }
     return acc;
 }
 
+// --------------------------------------------------------------------------------------
+// Neuron models.
 struct SsbNeuron {
     int type;
-    float tau_rc, tau_ref, min_v, amp_dt, amp, em1_full, dt;
+    bool fast;
+    float tau_rc, tau_ref, amp_dt, amp, dt, inv_tau;
 };
 
 __device__ __forceinline__ SsbNeuron ssb_neuron(const SsbCtx& c, int tid) {
-    const float* p = c.ntypes + tid * 5;
+    const float* p = c.ntypes + tid * 8;
     SsbNeuron n;
     n.type = (int)p[0];
     n.tau_rc = p[1];
     n.tau_ref = p[2];
-    n.min_v = p[3];
     n.amp = p[4];
+    n.fast = p[5] != 0.f;
     n.dt = c.dt;
     n.amp_dt = p[4] / c.dt;
-    n.em1_full = (n.type == 0) ? expm1f(-c.dt / p[1]) : 0.f;
+    n.inv_tau = (n.type == 0) ? 1.0f / p[1] : 0.f;
     return n;
 }
 
-// nengo LIF.step / LIFRate.step / RectifiedLinear.step (App. A.4), fp32.
-__device__ __forceinline__ float ssb_neuron_step(const SsbNeuron& n, float J, float& v, float& r) {
-    if (n.type == 0) {
-        r -= n.dt;
-        const float delta = fminf(fmaxf(n.dt - r, 0.f), n.dt);
-        const float em1 = (delta == n.dt) ? n.em1_full : expm1f(-delta / n.tau_rc);
-        v = v - (J - v) * em1;
-        float out = 0.f;
-        if (v > 1.f) {
-            const float t_spike = n.dt + n.tau_rc * log1pf(-(v - 1.f) / (J - 1.f));
-            r = n.tau_ref + t_spike;
-            v = 0.f;
-            out = n.amp_dt;
-        } else if (v < n.min_v) {
-            v = n.min_v;
-        }
-        return out;
-    } else if (n.type == 1) {
+// expm1(x) for -0.125 <= x <= 0 (x = -delta/tau_rc with delta <= dt): degree-6 Taylor, rel. error < 1e-9.
+__device__ __forceinline__ float ssb_expm1_small(float x) {
+    float p = 1.f / 720.f;
+    p = fmaf(p, x, 1.f / 120.f);
+    p = fmaf(p, x, 1.f / 24.f);
+    p = fmaf(p, x, 1.f / 6.f);
+    p = fmaf(p, x, 0.5f);
+    p = fmaf(p, x, 1.f);
+    return p * x;
+}
+
+// log1p(-z) for 0 <= z <= 0.125 (z = overshoot / (J - 1) <= 1 - exp(-dt/tau_rc)): 8 terms, rel. error < 1e-8.
+__device__ __forceinline__ float ssb_log1p_neg_small(float z) {
+    float p = 1.f / 8.f;
+    p = fmaf(p, z, 1.f / 7.f);
+    p = fmaf(p, z, 1.f / 6.f);
+    p = fmaf(p, z, 0.2f);
+    p = fmaf(p, z, 0.25f);
+    p = fmaf(p, z, 1.f / 3.f);
+    p = fmaf(p, z, 0.5f);
+    p = fmaf(p, z, 1.f);
+    return -(p * z);
+}
+
+// nengo LIF.step on the packed state (App. A.4), branch-free.  Returns the output (0 or amplitude/dt).
+__device__ __forceinline__ float ssb_lif_packed(const SsbNeuron& n, float J, float& s) {
+    const bool refr = s < 0.f;
+    const float rp = refr ? (-s - n.dt) : -n.dt;          // refractory_time after "-= dt"
+    float v = refr ? 0.f : s;
+    const float delta = fminf(fmaxf(n.dt - rp, 0.f), n.dt);
+    const float em1 = n.fast ? ssb_expm1_small(-delta * n.inv_tau) : expm1f(-delta / n.tau_rc);
+    v = fmaf(-(J - v), em1, v);                            // v -= (J - v) * expm1(-delta / tau_rc)
+    const bool spiked = v > 1.f;
+    const float z = __fdividef(v - 1.f, J - 1.f);          // used only when spiked (then J > v > 1)
+    const float lp = n.fast ? ssb_log1p_neg_small(z) : log1pf(-z);
+    const float r_new = n.tau_ref + (n.dt + n.tau_rc * lp);
+    const float keep = (rp >= n.dt) ? -rp : fmaxf(v, 0.f);
+    s = spiked ? ((r_new >= n.dt) ? -r_new : 0.f) : keep;
+    return spiked ? n.amp_dt : 0.f;
+}
+
+__device__ __forceinline__ float ssb_rate(const SsbNeuron& n, float J) {
+    if (n.type == 1) {
         const float j = J - 1.f;
         return j > 0.f ? n.amp / (n.tau_ref + n.tau_rc * log1pf(1.f / j)) : 0.f;
     }
@@ -141,158 +163,239 @@ __device__ __forceinline__ float ssb_neuron_step(const SsbNeuron& n, float J, fl
 }
 
 // --------------------------------------------------------------------------------------
-// Narrow ensembles (VCO 3-D x 500, product squares 1-D x 50).  Input vector and decoded
-// sums live in registers; packed per-neuron weights [bias, enc[DIMS], dec[nout]] are
-// warp-uniform float4 loads.  One launch, two block ranges:
-//   blocks [0, n_split*G)  "split":  a CTA of 4 warps owns one (ensemble, trial-group); warps take
-//                                    interleaved neurons, partial decodes are reduced in shared memory
-//                                    (a single warp streaming 500 neurons is a 150 us latency chain);
-//   remaining blocks       "packed": each warp owns one (ensemble, trial-group) of a small ensemble.
+// TMA 1-D bulk copies + mbarriers (one elected lane issues; the warp waits on the barrier).
+__device__ __forceinline__ uint32_t ssb_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ssb_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ssb_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ssb_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ssb_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ssb_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(ssb_smem(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void ssb_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     ssb_smem(dst)),
+                 "l"(src), "r"(bytes), "r"(ssb_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ssb_bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ssb_smem(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void ssb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ssb_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void ssb_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ssb_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// --------------------------------------------------------------------------------------
+// Start of a step: the input-table rows of this step become ordinary vec rows, so every CSR entry
+// addresses one arena.  grid (ceil(nt/4), G) x 128
+__global__ void __launch_bounds__(128) k_begin(SsbCtx c, int i_rel) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * 4 + warp, g = blockIdx.y;
+    if (row >= c.nt) return;
+    const long long s_loc = c.dyn[0] + i_rel - c.dyn[1];
+    const float* src = c.tab + (((size_t)g * c.tab_cap + (size_t)s_loc) * c.nt + row) * 32 + lane;
+    ssb_grp(c.vec, c.nv, g, lane)[(size_t)(c.tab_row0 + row) * 32] = __ldcs(src);
+}
+
+// --------------------------------------------------------------------------------------
+// Narrow ensembles (VCO 3-D x 500, product squares 1-D x 50): fused encode -> neuron -> decode.
+// Each warp walks a contiguous neuron range of one (ensemble, trial group) in chunks of SSB_SM_CH
+// neurons.  A chunk's packed weights [bias, enc[DIMS], dec[nout]] and its 128-byte state rows are
+// staged in shared memory by TMA bulk copies (double-buffered per warp, mbarrier completion); the
+// updated state goes back with a bulk store.  Input vector and decoded sums live in registers.
+//   blocks [0, n_split*G)  "split":  a CTA of 4 warps owns one (ensemble, group); the neuron range is
+//                                    quartered and the partial decodes are reduced in shared memory;
+//   remaining blocks       "packed": each warp owns one (ensemble, group) of a small ensemble.
 // desc: n, dims, nout, state0, w_off, in_row0, out_vec, ntype, stride
+struct __align__(128) SsbSmallSmem {
+    float st[4][2][SSB_SM_CH * 32];
+    float w[4][2][SSB_SM_CH * SSB_SM_WMAX];
+    float red[4][8][32];
+    float xs[4][32];
+    unsigned long long bar[4][2];
+};
+
 template <int DIMS, int S4>
-__device__ __forceinline__ void ssb_small_stream(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt,
-                                                 const float (&x)[DIMS], int trial, int i_begin, int i_step,
-                                                 float (&acc)[8]) {
-    const int n = d[0], nout = d[2], state0 = d[3], w_off = d[4];
-    const size_t B = c.B;
-    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(c.W + w_off);
-    float* __restrict__ vp = c.v + (size_t)state0 * B + trial;
-    float* __restrict__ rp = c.ref + (size_t)state0 * B + trial;
+__device__ __forceinline__ void ssb_small_range(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt,
+                                                const float (&x)[DIMS], int g, int i_begin, int i_end, float (&acc)[8],
+                                                SsbSmallSmem& sm, uint32_t& phases) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nout = d[2], state0 = d[3], w_off = d[4];
     const bool stateful = nt.type == 0;
-    constexpr int U = 4;
-    for (int i0 = i_begin; i0 < n; i0 += U * i_step) {
-        float vv[U], rr[U], wl[U][4 * S4];
+    const float* wsrc = c.W + w_off;
+    float* sg = c.st + ((size_t)g * c.nn + state0) * 32;
+    const int n_chunks = (i_end - i_begin + SSB_SM_CH - 1) / SSB_SM_CH;
+    auto issue = [&](int ck) {
+        if (lane == 0) {
+            const int b = ck & 1, i0 = i_begin + ck * SSB_SM_CH, cnt = min(SSB_SM_CH, i_end - i0);
+            const uint32_t bw = (uint32_t)cnt * S4 * 16, bs = stateful ? (uint32_t)cnt * 128 : 0u;
+            ssb_mbar_expect_tx(&sm.bar[warp][b], bw + bs);
+            ssb_bulk_g2s(sm.w[warp][b], wsrc + (size_t)i0 * 4 * S4, bw, &sm.bar[warp][b]);
+            if (stateful) ssb_bulk_g2s(sm.st[warp][b], sg + (size_t)i0 * 32, bs, &sm.bar[warp][b]);
+        }
+    };
+    if (n_chunks > 0) issue(0);
+    if (n_chunks > 1) issue(1);
+    for (int ck = 0; ck < n_chunks; ++ck) {
+        const int b = ck & 1, i0 = i_begin + ck * SSB_SM_CH, cnt = min(SSB_SM_CH, i_end - i0);
+        ssb_mbar_wait(&sm.bar[warp][b], (phases >> b) & 1u);
+        phases ^= 1u << b;
+        float* ss = sm.st[warp][b] + lane;
+        const float4* ww = reinterpret_cast<const float4*>(sm.w[warp][b]);
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            float wl[4 * S4];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * i_step;
-            vv[u] = 0.f;
-            rr[u] = 0.f;
-            if (i < n) {
-                if (stateful) {
-                    vv[u] = vp[(size_t)i * B];
-                    rr[u] = rp[(size_t)i * B];
-                }
+            for (int q = 0; q < S4; ++q) {
+                const float4 t = ww[k * S4 + q];
+                wl[4 * q + 0] = t.x;
+                wl[4 * q + 1] = t.y;
+                wl[4 * q + 2] = t.z;
+                wl[4 * q + 3] = t.w;
+            }
+            float J = wl[0];
 #pragma unroll
-                for (int q = 0; q < S4; ++q) {
-                    const float4 t = __ldg(w4 + (size_t)i * S4 + q);
-                    wl[u][4 * q + 0] = t.x;
-                    wl[u][4 * q + 1] = t.y;
-                    wl[u][4 * q + 2] = t.z;
-                    wl[u][4 * q + 3] = t.w;
-                }
+            for (int kk = 0; kk < DIMS; ++kk) J = fmaf(wl[1 + kk], x[kk], J);
+            float out;
+            if (stateful) {
+                float s = ss[k * 32];
+                out = ssb_lif_packed(nt, J, s);
+                ss[k * 32] = s;
+            } else {
+                out = ssb_rate(nt, J);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (1 + DIMS + j < 4 * S4 && j < nout) acc[j] = fmaf(wl[1 + DIMS + j], out, acc[j]);
+        }
+        if (stateful) {
+            ssb_fence_async();     // generic-proxy writes of this chunk -> visible to the bulk store
+            __syncwarp();
+            if (lane == 0) {
+                ssb_bulk_s2g(sg + (size_t)i0 * 32, sm.st[warp][b], (uint32_t)cnt * 128);
+                ssb_bulk_commit();
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * i_step;
-            if (i < n) {
-                float J = wl[u][0];
-#pragma unroll
-                for (int k = 0; k < DIMS; ++k) J = fmaf(wl[u][1 + k], x[k], J);
-                const float out = ssb_neuron_step(nt, J, vv[u], rr[u]);
-                if (stateful) {
-                    vp[(size_t)i * B] = vv[u];
-                    rp[(size_t)i * B] = rr[u];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (1 + DIMS + j < 4 * S4 && j < nout) acc[j] = fmaf(wl[u][1 + DIMS + j], out, acc[j]);
-            }
+        if (ck + 2 < n_chunks) {
+            if (stateful && lane == 0) ssb_bulk_wait_read0();   // the store has drained this buffer
+            __syncwarp();
+            issue(ck + 2);
         }
     }
 }
 
 template <int DIMS, int S4>
-__device__ __forceinline__ void ssb_small_item(const SsbCtx& c, const SsbStep& s, const int* __restrict__ d, int trial,
-                                               bool split, float* xs, float (*red)[8][32]) {
-    const int nout = d[2], in_row0 = d[5], out_vec = d[6];
+__device__ __forceinline__ void ssb_small_item(const SsbCtx& c, const SsbStep& s, const int* __restrict__ d, int g,
+                                               bool split, SsbSmallSmem& sm, uint32_t& phases) {
+    const int n = d[0], nout = d[2], in_row0 = d[5], out_vec = d[6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const SsbNeuron nt = ssb_neuron(c, d[7]);
-    const size_t B = c.B;
+    float* vg = ssb_grp(c.vec, c.nv, g, lane);
     float x[DIMS], acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (split) {
-        for (int k = warp; k < DIMS; k += 4) xs[k * 32 + lane] = ssb_row(c, s, in_row0 + k, trial, s.par_old);
+        for (int k = warp; k < DIMS; k += 4) sm.xs[k][lane] = ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg);
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < DIMS; ++k) x[k] = xs[k * 32 + lane];
-        ssb_small_stream<DIMS, S4>(c, d, nt, x, trial, warp, 4, acc);
+        for (int k = 0; k < DIMS; ++k) x[k] = sm.xs[k][lane];
+        const int q = (n + 3) >> 2;
+        ssb_small_range<DIMS, S4>(c, d, nt, x, g, min(n, warp * q), min(n, (warp + 1) * q), acc, sm, phases);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
+        for (int j = 0; j < 8; ++j) sm.red[warp][j][lane] = acc[j];
         __syncthreads();
         for (int j = warp; j < nout; j += 4) {
-            const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
-            c.vec[(size_t)(out_vec + j) * B + trial] = t;
+            const float t = (sm.red[0][j][lane] + sm.red[1][j][lane]) + (sm.red[2][j][lane] + sm.red[3][j][lane]);
+            vg[(size_t)(out_vec + j) * 32] = t;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < DIMS; ++k) x[k] = ssb_row(c, s, in_row0 + k, trial, s.par_old);
-        ssb_small_stream<DIMS, S4>(c, d, nt, x, trial, 0, 1, acc);
+        for (int k = 0; k < DIMS; ++k) x[k] = ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg);
+        ssb_small_range<DIMS, S4>(c, d, nt, x, g, 0, n, acc, sm, phases);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (j < nout) c.vec[(size_t)(out_vec + j) * B + trial] = acc[j];
+            if (j < nout) vg[(size_t)(out_vec + j) * 32] = acc[j];
     }
 }
 
 __global__ void __launch_bounds__(128) k_ens_small(SsbCtx c, const int* __restrict__ desc, int n_items, int n_split,
-                                                    int n_groups) {
-    __shared__ float xs[4 * 32];
-    __shared__ float red[4][8][32];
+                                                    int i_rel) {
+    __shared__ SsbSmallSmem sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int split_blocks = n_split * n_groups;
-    int item, group;
-    bool split;
+    if (lane == 0) {
+        ssb_mbar_init(&sm.bar[warp][0], 1);
+        ssb_mbar_init(&sm.bar[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int G = c.G;
+    const int split_blocks = n_split * G;
+    int item, g;
+    bool split, live = true;
     if ((int)blockIdx.x < split_blocks) {
         split = true;
-        item = blockIdx.x / n_groups;
-        group = blockIdx.x - item * n_groups;
+        item = blockIdx.x / G;
+        g = blockIdx.x - item * G;
     } else {
         split = false;
         const int w = (blockIdx.x - split_blocks) * 4 + warp;
-        if (w >= (n_items - n_split) * n_groups) return;
-        item = n_split + w / n_groups;
-        group = w % n_groups;
+        live = w < (n_items - n_split) * G;
+        item = live ? n_split + w / G : 0;
+        g = live ? w % G : 0;
     }
-    const int* d = desc + item * 9;
-    const int trial = group * 32 + lane;
-    const SsbStep s = ssb_step(c);
-    const int key = d[1] * 8 + (d[8] >> 2);
-    switch (key) {
+    if (live) {
+        const int* d = desc + item * 9;
+        const SsbStep s = ssb_step(c, i_rel);
+        uint32_t phases = 0;
+        const int key = d[1] * 8 + (d[8] >> 2);
+        switch (key) {
 #define SSB_CASE(D, S) \
-    case (D) * 8 + (S): ssb_small_item<D, S>(c, s, d, trial, split, xs, red); break;
-        SSB_CASE(1, 1) SSB_CASE(1, 2) SSB_CASE(1, 3)
-        SSB_CASE(2, 1) SSB_CASE(2, 2) SSB_CASE(2, 3)
-        SSB_CASE(3, 1) SSB_CASE(3, 2) SSB_CASE(3, 3)
-        SSB_CASE(4, 2) SSB_CASE(4, 3) SSB_CASE(4, 4)
+    case (D) * 8 + (S): ssb_small_item<D, S>(c, s, d, g, split, sm, phases); break;
+            SSB_CASE(1, 1) SSB_CASE(1, 2) SSB_CASE(1, 3)
+            SSB_CASE(2, 1) SSB_CASE(2, 2) SSB_CASE(2, 3)
+            SSB_CASE(3, 1) SSB_CASE(3, 2) SSB_CASE(3, 3)
+            SSB_CASE(4, 2) SSB_CASE(4, 3) SSB_CASE(4, 4)
 #undef SSB_CASE
-        default: break;  // excluded by the host-side lowering (dims <= 4, dims + nout <= 11)
+            default: break;  // excluded by the host-side lowering (dims <= 4, dims + nout <= 11)
+        }
     }
+    if (lane == 0) ssb_bulk_wait0();   // bulk stores complete before the CTA's shared memory is released
 }
 
 // --------------------------------------------------------------------------------------
-// Wide ensembles (OVC / memory / recall / error: 970 x 55).  A CTA owns (ensemble, trial-group,
-// neuron chunk); the input vector is staged once in shared memory and (for the templated
-// widths) copied to registers.  Each warp walks its neurons two at a time.  Output
-// activities go to act[n][trial] for the decode / PES kernels.  Voja-learned encoders are
-// per-trial rows (lenc), all loads of a row are issued before use, and rows that spiked are
-// updated in place (post_synapse=None => the delta is row-sparse).
+// Wide ensembles (OVC / memory / recall / error: 970 x 55).  A CTA owns (ensemble, trial group,
+// neuron chunk); the input vector is staged once in shared memory and (for the templated widths)
+// copied to registers.  Output activities go to act[n] for the decode / PES kernels.  Voja-learned
+// encoders are per-trial rows (lenc; the 55 rows of one neuron are 7 KB contiguous), all loads of a
+// neuron are issued before use, and only lanes that spiked write their row back
+// (post_synapse=None => the delta is row-sparse).
 // desc: n dims dpad state0 act0 enc_off bias_off in_row0 ntype flags jn_row0 jn_m jn_w voja_row scale_off alpha_bits
 template <int DP>
 __device__ __forceinline__ void ssb_wide_neuron(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt, int i,
-                                                int trial, const float* xs, const float* us, const float (&x)[DP > 0 ? DP : 1],
-                                                float aL) {
+                                                int g, const float* xs, const float* us,
+                                                const float (&x)[DP > 0 ? DP : 1], float aL) {
     const int dims = d[1], dpad = d[2], state0 = d[3], act0 = d[4], enc_off = d[5], bias_off = d[6], flags = d[9];
     const int jn_m = d[11], jn_w = d[12], scale_off = d[14];
     const int lane = threadIdx.x & 31;
-    const size_t B = c.B;
     const bool voja = flags & 1, stateful = nt.type == 0;
-    const size_t so = (size_t)(state0 + i) * B + trial;
-    float v = 0.f, r = 0.f;
-    if (stateful) {
-        v = c.v[so];
-        r = c.ref[so];
-    }
+    float* sp = ssb_grp(c.st, c.nn, g, lane) + (size_t)(state0 + i) * 32;
+    float s = 0.f;
+    if (stateful) s = __ldcs(sp);
     float J = __ldg(c.W + bias_off + i);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     float* erow = nullptr;
@@ -319,10 +422,10 @@ __device__ __forceinline__ void ssb_wide_neuron(const SsbCtx& c, const int* __re
             }
         }
     } else {
-        erow = c.lenc + ((size_t)enc_off + (size_t)i * dims) * B + trial;
+        erow = ssb_grp(c.lenc, c.n_lenc, g, lane) + ((size_t)enc_off + (size_t)i * dims) * 32;
         if (DP > 0) {
 #pragma unroll
-            for (int k = 0; k < DP; ++k) ev[k] = (k < dims) ? erow[(size_t)k * B] : 0.f;
+            for (int k = 0; k < DP; ++k) ev[k] = (k < dims) ? erow[(size_t)k * 32] : 0.f;
 #pragma unroll
             for (int k = 0; k < DP; k += 4) {
                 a0 = fmaf(ev[k + 0], x[k + 0], a0);
@@ -333,42 +436,44 @@ __device__ __forceinline__ void ssb_wide_neuron(const SsbCtx& c, const int* __re
         } else {
             int k = 0;
             for (; k + 4 <= dims; k += 4) {
-                const float e0 = erow[(size_t)k * B], e1 = erow[(size_t)(k + 1) * B];
-                const float e2 = erow[(size_t)(k + 2) * B], e3 = erow[(size_t)(k + 3) * B];
+                const float e0 = erow[(size_t)k * 32], e1 = erow[(size_t)(k + 1) * 32];
+                const float e2 = erow[(size_t)(k + 2) * 32], e3 = erow[(size_t)(k + 3) * 32];
                 a0 = fmaf(e0, xs[k * 32 + lane], a0);
                 a1 = fmaf(e1, xs[(k + 1) * 32 + lane], a1);
                 a2 = fmaf(e2, xs[(k + 2) * 32 + lane], a2);
                 a3 = fmaf(e3, xs[(k + 3) * 32 + lane], a3);
             }
-            for (; k < dims; ++k) a0 = fmaf(erow[(size_t)k * B], xs[k * 32 + lane], a0);
+            for (; k < dims; ++k) a0 = fmaf(erow[(size_t)k * 32], xs[k * 32 + lane], a0);
         }
     }
     J += (a0 + a1) + (a2 + a3);
     for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + i * jn_m + m), us[m * 32 + lane], J);
-    const float out = ssb_neuron_step(nt, J, v, r);
+    float out;
     if (stateful) {
-        c.v[so] = v;
-        c.ref[so] = r;
+        out = ssb_lif_packed(nt, J, s);
+        __stcs(sp, s);
+    } else {
+        out = ssb_rate(nt, J);
     }
-    c.act[(size_t)(act0 + i) * B + trial] = out;
+    ssb_grp(c.act, c.n_act, g, lane)[(size_t)(act0 + i) * 32] = out;
     if (voja && out != 0.f) {
         // SimVoja: delta = alpha*L*(scale*outer(post, x) - post[:,None]*E), applied to E for the next step
         const float sc = __ldg(c.W + scale_off + i);
         if (DP > 0) {
 #pragma unroll
             for (int k = 0; k < DP; ++k)
-                if (k < dims) erow[(size_t)k * B] = ev[k] + aL * (sc * (out * x[k]) - out * ev[k]);
+                if (k < dims) erow[(size_t)k * 32] = ev[k] + aL * (sc * (out * x[k]) - out * ev[k]);
         } else {
             for (int k = 0; k < dims; ++k) {
-                const float e = erow[(size_t)k * B];
-                erow[(size_t)k * B] = e + aL * (sc * (out * xs[k * 32 + lane]) - out * e);
+                const float e = erow[(size_t)k * 32];
+                erow[(size_t)k * 32] = e + aL * (sc * (out * xs[k * 32 + lane]) - out * e);
             }
         }
     }
 }
 
 template <int DP>
-__global__ void __launch_bounds__(128) k_ens_wide(SsbCtx c, const int* __restrict__ desc, int item0, int chunk) {
+__global__ void __launch_bounds__(128) k_ens_wide(SsbCtx c, const int* __restrict__ desc, int item0, int chunk, int i_rel) {
     extern __shared__ float sm[];
     const int* d = desc + (item0 + blockIdx.z) * 16;
     const int n = d[0], dims = d[1], dpad = d[2];
@@ -379,107 +484,131 @@ __global__ void __launch_bounds__(128) k_ens_wide(SsbCtx c, const int* __restric
     if (DP == 0 && (dpad == 56 || dpad == 100)) return;
     const int n1 = min(n, n0 + chunk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int trial = blockIdx.y * 32 + lane;
-    const SsbStep s = ssb_step(c);
+    const int g = blockIdx.y;
+    const SsbStep s = ssb_step(c, i_rel);
     const SsbNeuron nt = ssb_neuron(c, d[8]);
+    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
     float* xs = sm;                 // [dpad][32]
     float* us = sm + dpad * 32;     // [jn_m][32]
     for (int k = warp; k < dpad; k += nwarps)
-        xs[k * 32 + lane] = (k < dims) ? ssb_row(c, s, in_row0 + k, trial, s.par_old) : 0.f;
-    for (int m = warp; m < jn_m; m += nwarps) us[m * 32 + lane] = ssb_row(c, s, jn_row0 + m, trial, s.par_old);
+        xs[k * 32 + lane] = (k < dims) ? ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg) : 0.f;
+    for (int m = warp; m < jn_m; m += nwarps) us[m * 32 + lane] = ssb_row(c.csr_ptr, s.ent_old, jn_row0 + m, vg);
     float aL = 0.f;
-    if (flags & 1) aL = __int_as_float(d[15]) * ssb_row(c, s, voja_row, trial, s.par_old);
+    if (flags & 1) aL = __int_as_float(d[15]) * ssb_row(c.csr_ptr, s.ent_old, voja_row, vg);
     __syncthreads();
     float x[DP > 0 ? DP : 1];
     if (DP > 0) {
 #pragma unroll
         for (int k = 0; k < DP; ++k) x[k] = xs[k * 32 + lane];
     }
-    for (int i = n0 + warp; i < n1; i += nwarps) ssb_wide_neuron<DP>(c, d, nt, i, trial, xs, us, x, aL);
+    for (int i = n0 + warp; i < n1; i += nwarps) ssb_wide_neuron<DP>(c, d, nt, i, g, xs, us, x, aL);
 }
 
 // --------------------------------------------------------------------------------------
-// Static decoders of wide ensembles: out[j][trial] = sum_n Wd[n][j] * act[n][trial].
-// CTA = (decoder, trial-group, 8-row output tile, neuron chunk); warps split the chunk, shared-
-// memory reduce; each neuron chunk writes its own partial slot (the consumers' CSR rows sum the
-// partial slots, so there are no atomics and the result is deterministic).
-// desc: n size_out jpad act0 w_off out_vec n_chunks
+// Split-K epilogue shared by the decode and PES kernels.  The neuron range of one (decoder,
+// 8-row tile, trial group) is split over n_chunks CTAs; each CTA reduces its 4 warps in shared
+// memory and, if it is not alone, parks its partial sums in the `part` arena.  The CTA that
+// arrives last (atomic counter, self-resetting) adds the partials in chunk order — a fixed order,
+// so the result does not depend on scheduling — and writes the single output slot.
+__device__ __forceinline__ void ssb_splitk_finish(const SsbCtx& c, float (*red)[8][32], int* flag, const float (&acc)[8],
+                                                  int g, int j0, int size_out, int out_vec, int n_chunks, int chunk,
+                                                  int part_off, int counter) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
+    __syncthreads();
+    float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    float* pg = ssb_grp(c.part, c.n_part, g, lane);
+    for (int j = warp; j < 8; j += 4) {
+        if (j0 + j < size_out) {
+            const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
+            if (n_chunks == 1) vg[(size_t)(out_vec + j0 + j) * 32] = t;
+            else pg[(size_t)(part_off + chunk * size_out + j0 + j) * 32] = t;
+        }
+    }
+    if (n_chunks == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(c.counters + counter, 1);
+        const int last = old == n_chunks - 1;
+        if (last) c.counters[counter] = 0;
+        *flag = last;
+    }
+    __syncthreads();
+    if (!*flag) return;
+    __threadfence();
+    for (int j = warp; j < 8; j += 4) {
+        if (j0 + j < size_out) {
+            float t = 0.f;
+            for (int ck = 0; ck < n_chunks; ++ck) t += __ldcg(pg + (size_t)(part_off + ck * size_out + j0 + j) * 32);
+            vg[(size_t)(out_vec + j0 + j) * 32] = t;
+        }
+    }
+}
+
+// Static decoders of wide ensembles: out[j] = sum_n Wd[n][j] * act[n].  CTA = (decoder, trial group,
+// 8-row output tile, neuron chunk); warps interleave the chunk's neurons; a neuron whose activity is
+// zero in all 32 trials is skipped (spiking activity is sparse).
+// desc: n size_out jpad act0 w_off out_vec n_chunks part_off counter0
 __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict__ desc, int item0, int max_chunks) {
     __shared__ float red[4][8][32];
+    __shared__ int flag;
     const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
-    const int* d = desc + (item0 + item) * 7;
+    const int* d = desc + (item0 + item) * 9;
     const int n = d[0], size_out = d[1], jpad = d[2], act0 = d[3], w_off = d[4], out_vec = d[5], n_chunks = d[6];
     const int j0 = blockIdx.x * 8;
     if (j0 >= size_out || chunk >= n_chunks) return;
     const int per = (n + n_chunks - 1) / n_chunks;
     const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int trial = blockIdx.y * 32 + lane;
-    const size_t B = c.B;
+    const int g = blockIdx.y;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const float* __restrict__ ap = c.act + (size_t)act0 * B + trial;
-    int i = i_lo + warp;
-    for (; i + 4 < i_hi; i += 8) {
-        const float a0 = ap[(size_t)i * B], a1 = ap[(size_t)(i + 4) * B];
-        const float4* __restrict__ w0 = reinterpret_cast<const float4*>(c.W + w_off + (size_t)i * jpad + j0);
-        const float4* __restrict__ w1 = reinterpret_cast<const float4*>(c.W + w_off + (size_t)(i + 4) * jpad + j0);
-        const float4 wa = __ldg(w0), wb = __ldg(w0 + 1), wc = __ldg(w1), wd = __ldg(w1 + 1);
-        acc[0] = fmaf(wa.x, a0, acc[0]);
-        acc[1] = fmaf(wa.y, a0, acc[1]);
-        acc[2] = fmaf(wa.z, a0, acc[2]);
-        acc[3] = fmaf(wa.w, a0, acc[3]);
-        acc[4] = fmaf(wb.x, a0, acc[4]);
-        acc[5] = fmaf(wb.y, a0, acc[5]);
-        acc[6] = fmaf(wb.z, a0, acc[6]);
-        acc[7] = fmaf(wb.w, a0, acc[7]);
-        acc[0] = fmaf(wc.x, a1, acc[0]);
-        acc[1] = fmaf(wc.y, a1, acc[1]);
-        acc[2] = fmaf(wc.z, a1, acc[2]);
-        acc[3] = fmaf(wc.w, a1, acc[3]);
-        acc[4] = fmaf(wd.x, a1, acc[4]);
-        acc[5] = fmaf(wd.y, a1, acc[5]);
-        acc[6] = fmaf(wd.z, a1, acc[6]);
-        acc[7] = fmaf(wd.w, a1, acc[7]);
-    }
-    for (; i < i_hi; i += 4) {
-        const float a0 = ap[(size_t)i * B];
-        const float4* __restrict__ w0 = reinterpret_cast<const float4*>(c.W + w_off + (size_t)i * jpad + j0);
-        const float4 wa = __ldg(w0), wb = __ldg(w0 + 1);
-        acc[0] = fmaf(wa.x, a0, acc[0]);
-        acc[1] = fmaf(wa.y, a0, acc[1]);
-        acc[2] = fmaf(wa.z, a0, acc[2]);
-        acc[3] = fmaf(wa.w, a0, acc[3]);
-        acc[4] = fmaf(wb.x, a0, acc[4]);
-        acc[5] = fmaf(wb.y, a0, acc[5]);
-        acc[6] = fmaf(wb.z, a0, acc[6]);
-        acc[7] = fmaf(wb.w, a0, acc[7]);
-    }
+    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
+    constexpr int U = 4;
+    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
+        float a[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
-    __syncthreads();
-    for (int j = warp; j < 8; j += 4) {
-        if (j0 + j < size_out) {
-            const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
-            c.vec[(size_t)(out_vec + chunk * size_out + j0 + j) * B + trial] = t;
+        for (int u = 0; u < U; ++u) a[u] = (i + 4 * u < i_hi) ? ap[(size_t)(i + 4 * u) * 32] : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (__any_sync(0xffffffffu, a[u] != 0.f)) {
+                const float4* __restrict__ w4 =
+                    reinterpret_cast<const float4*>(c.W + w_off + (size_t)(i + 4 * u) * jpad + j0);
+                const float4 wa = __ldg(w4), wb = __ldg(w4 + 1);
+                acc[0] = fmaf(wa.x, a[u], acc[0]);
+                acc[1] = fmaf(wa.y, a[u], acc[1]);
+                acc[2] = fmaf(wa.z, a[u], acc[2]);
+                acc[3] = fmaf(wa.w, a[u], acc[3]);
+                acc[4] = fmaf(wb.x, a[u], acc[4]);
+                acc[5] = fmaf(wb.y, a[u], acc[5]);
+                acc[6] = fmaf(wb.z, a[u], acc[6]);
+                acc[7] = fmaf(wb.w, a[u], acc[7]);
+            }
         }
     }
+    ssb_splitk_finish(c, red, &flag, acc, g, j0, size_out, out_vec, n_chunks, chunk, d[7],
+                      (d[8] + (int)blockIdx.x) * c.G + g);
 }
 
 // --------------------------------------------------------------------------------------
-// PES-learned decoders (per trial): one streaming pass that applies the pending rank-1
-// delta, decodes with the updated weights and writes them back:
+// PES-learned decoders (per trial): one streaming pass that applies the pending rank-1 delta,
+// decodes with the updated weights and writes them back:
 //   D <- D + outer(alpha*err_prev, a_prev)     (nengo: Copy(delta->weights, inc) at step start)
 //   out = D . act                               (DotInc)
-// err_prev / a_prev are the filter values the previous step read (the not-yet-overwritten
-// half of the ping-pong buffers), which is exactly SimPES' delta from the previous step.
-// This is the dominant HBM stream of the SLAM step (8 bytes per learned weight per trial-step).
-// desc: n size_out d_off a_off act0 err_row0 out_vec alpha_bits decay_bits onemdecay_bits n_chunks
-__global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ desc, int max_chunks) {
+// err_prev / a_prev are the values the previous step read (the not-yet-overwritten half of the
+// ping-pong buffers), which is exactly SimPES' delta of the previous step.  For a fixed output row
+// the weights of consecutive neurons are consecutive 128-byte lines.  A neuron whose trace and
+// activity are zero in all 32 trials changes nothing and contributes nothing: its weights are
+// neither read nor written (exact, not an approximation).
+// desc: n size_out d_off a_off act0 err_row0 out_vec alpha_bits decay_bits onemdecay_bits n_chunks part_off counter0
+__global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ desc, int max_chunks, int i_rel) {
     __shared__ float red[4][8][32];
+    __shared__ int flag;
     const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
-    const int* d = desc + item * 11;
+    const int* d = desc + item * 13;
     const int n = d[0], size_out = d[1], d_off = d[2], a_off = d[3], act0 = d[4], err_row0 = d[5], out_vec = d[6];
     const int n_chunks = d[10];
     const float alpha = __int_as_float(d[7]);
@@ -488,78 +617,63 @@ __global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ d
     const int per = (n + n_chunks - 1) / n_chunks;
     const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int trial = blockIdx.y * 32 + lane;
-    const size_t B = c.B;
-    const SsbStep s = ssb_step(c);
-    const int prev_buf = 1 - (int)(s.step & 1);  // afilt half that still holds what the previous step read
+    const int g = blockIdx.y;
+    const SsbStep s = ssb_step(c, i_rel);
+    const int prev_buf = 1 - s.odd;  // afilt half that still holds what the previous step read
+    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    const int jn = min(8, size_out - j0);
     float ae[8], acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         acc[j] = 0.f;
         float e = 0.f;
-        if (j0 + j < size_out) e = ssb_row(c, s, err_row0 + j0 + j, trial, s.par_new);
+        if (j < jn) e = ssb_row(c.csr_ptr, s.ent_new, err_row0 + j0 + j, vg);
         ae[j] = s.step > 0 ? alpha * e : 0.f;
     }
-    const float* __restrict__ ap = c.act + (size_t)act0 * B + trial;
-    const float* __restrict__ fp = c.afilt + ((size_t)prev_buf * c.n_afilt + a_off) * B + trial;
-    float* __restrict__ dp = c.ldec + (size_t)d_off * B + trial;
-    const int jn = min(8, size_out - j0);
-    if (jn == 8) {
-        int i = i_lo + warp;
-        for (; i + 4 < i_hi; i += 8) {
-            float w0[8], w1[8];
-            const float a0 = ap[(size_t)i * B], f0 = fp[(size_t)i * B];
-            const float a1 = ap[(size_t)(i + 4) * B], f1 = fp[(size_t)(i + 4) * B];
+    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
+    const float* __restrict__ fp = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)prev_buf * c.n_afilt + a_off) * 32;
+    float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + (size_t)d_off * 32;
+    constexpr int U = 4;
+    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
+        float a[U], f[U], w[U][8];
+        bool on[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                w0[j] = dp[((size_t)(j0 + j) * n + i) * B];
-                w1[j] = dp[((size_t)(j0 + j) * n + i + 4) * B];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                w0[j] = fmaf(ae[j], f0, w0[j]);
-                w1[j] = fmaf(ae[j], f1, w1[j]);
-                acc[j] = fmaf(w0[j], a0, acc[j]);
-                acc[j] = fmaf(w1[j], a1, acc[j]);
-                dp[((size_t)(j0 + j) * n + i) * B] = w0[j];
-                dp[((size_t)(j0 + j) * n + i + 4) * B] = w1[j];
+        for (int u = 0; u < U; ++u) {
+            const int ii = i + 4 * u;
+            a[u] = 0.f;
+            f[u] = 0.f;
+            if (ii < i_hi) {
+                a[u] = ap[(size_t)ii * 32];
+                f[u] = fp[(size_t)ii * 32];
             }
         }
-        for (; i < i_hi; i += 4) {
-            float w0[8];
-            const float a0 = ap[(size_t)i * B], f0 = fp[(size_t)i * B];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w0[j] = dp[((size_t)(j0 + j) * n + i) * B];
+        for (int u = 0; u < U; ++u) {
+            on[u] = __any_sync(0xffffffffu, a[u] != 0.f || f[u] != 0.f);
+            if (on[u]) {
+                const int ii = i + 4 * u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                w0[j] = fmaf(ae[j], f0, w0[j]);
-                acc[j] = fmaf(w0[j], a0, acc[j]);
-                dp[((size_t)(j0 + j) * n + i) * B] = w0[j];
+                for (int j = 0; j < 8; ++j)
+                    if (j < jn) w[u][j] = __ldcs(dp + ((size_t)(j0 + j) * n + ii) * 32);
             }
         }
-    } else {
-        for (int i = i_lo + warp; i < i_hi; i += 4) {
-            const float a0 = ap[(size_t)i * B], f0 = fp[(size_t)i * B];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < jn) {
-                    float w = dp[((size_t)(j0 + j) * n + i) * B];
-                    w = fmaf(ae[j], f0, w);
-                    acc[j] = fmaf(w, a0, acc[j]);
-                    dp[((size_t)(j0 + j) * n + i) * B] = w;
+        for (int u = 0; u < U; ++u) {
+            if (on[u]) {
+                const int ii = i + 4 * u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < jn) {
+                        const float wn = fmaf(ae[j], f[u], w[u][j]);
+                        acc[j] = fmaf(wn, a[u], acc[j]);
+                        __stcs(dp + ((size_t)(j0 + j) * n + ii) * 32, wn);
+                    }
                 }
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
-    __syncthreads();
-    for (int j = warp; j < 8; j += 4) {
-        if (j0 + j < size_out) {
-            const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
-            c.vec[(size_t)(out_vec + chunk * size_out + j0 + j) * B + trial] = t;
-        }
-    }
+    ssb_splitk_finish(c, red, &flag, acc, g, j0, size_out, out_vec, n_chunks, chunk, d[11],
+                      (d[12] + (int)blockIdx.x) * c.G + g);
 }
 
 // --------------------------------------------------------------------------------------
@@ -567,8 +681,8 @@ __global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ d
 // top-4 candidates per (grid chunk, trial); the pick kernel re-scores near-ties in fp64 so
 // that the chosen index equals the float64 NumPy argmax on the same input.
 // A CTA = 4 warps = 4 different trial groups scanning the SAME grid chunk: the chunk of S is
-// staged once in shared memory and read back as warp-uniform (broadcast) float4s, the query
-// vector sits in registers.
+// staged in shared memory tiles and read back as warp-uniform (broadcast) float4s, the query
+// vector sits in registers; two grid rows are scored per iteration.
 struct SsbTop {
     float v[SSB_TOPK];
     int g[SSB_TOPK];
@@ -600,46 +714,48 @@ __device__ __forceinline__ void ssb_top_push(SsbTop& t, float val, int g) {
     }
 }
 
-// desc: G d dpad s_off in_row0 out_vec ; scratch rows: cx[dpad][B], pval/pidx[n_chunks*TOPK][B]
+// desc: G d dpad s_off in_row0 out_vec ; scratch: cx[G][dpad][32], pval/pidx[G][n_cand][32]
 // A CTA owns grid rows [blockIdx.x*rows_per_chunk, +rows_per_chunk) and walks them in shared-memory
 // tiles of tile_rows rows.  dynamic smem: tile_rows*dpad (S tile) + 4*dpad*32 (x staging, generic width only)
 template <int DP, bool CSR_INPUT>
 __global__ void __launch_bounds__(128)
 k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S, float* __restrict__ cx,
-               float* __restrict__ pval, int* __restrict__ pidx, int rows_per_chunk, int tile_rows, int n_groups) {
+               float* __restrict__ pval, int* __restrict__ pidx, int rows_per_chunk, int tile_rows, int n_groups,
+               int n_cand, int i_rel) {
     extern __shared__ float sm[];
     const int G = d[0], dims = d[1], dpad = d[2], in_row0 = d[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.y * 4 + warp;
     const bool live = group < n_groups;
-    const int trial = (live ? group : 0) * 32 + lane;
-    const size_t B = c.B;
+    const int g = live ? group : 0;
     const int g_lo = blockIdx.x * rows_per_chunk;
     const int g_hi = min(G, g_lo + rows_per_chunk);
     float* tile = sm;                              // [tile_rows][dpad]
     float* xs = sm + (size_t)tile_rows * dpad;     // [4][dpad][32] (generic width only)
+    float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
     float x[DP > 0 ? DP : 1];
     if (CSR_INPUT) {
-        const SsbStep s = ssb_step(c);
+        const SsbStep s = ssb_step(c, i_rel);
+        const float* vg = ssb_grp(c.vec, c.nv, g, lane);
         if (DP > 0) {
 #pragma unroll
             for (int k = 0; k < DP; ++k) {
-                x[k] = (k < dims) ? ssb_row(c, s, in_row0 + k, trial, s.par_old) : 0.f;
-                if (blockIdx.x == 0 && live) cx[(size_t)k * B + trial] = x[k];
+                x[k] = (k < dims) ? ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg) : 0.f;
+                if (blockIdx.x == 0 && live) cxg[(size_t)k * 32] = x[k];
             }
         } else {
             for (int k = 0; k < dpad; ++k) {
-                const float xv = (k < dims) ? ssb_row(c, s, in_row0 + k, trial, s.par_old) : 0.f;
+                const float xv = (k < dims) ? ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg) : 0.f;
                 xs[(warp * dpad + k) * 32 + lane] = xv;
-                if (blockIdx.x == 0 && live) cx[(size_t)k * B + trial] = xv;
+                if (blockIdx.x == 0 && live) cxg[(size_t)k * 32] = xv;
             }
         }
     } else {
         if (DP > 0) {
 #pragma unroll
-            for (int k = 0; k < DP; ++k) x[k] = (k < dims) ? cx[(size_t)k * B + trial] : 0.f;
+            for (int k = 0; k < DP; ++k) x[k] = (k < dims) ? cxg[(size_t)k * 32] : 0.f;
         } else {
-            for (int k = 0; k < dpad; ++k) xs[(warp * dpad + k) * 32 + lane] = (k < dims) ? cx[(size_t)k * B + trial] : 0.f;
+            for (int k = 0; k < dpad; ++k) xs[(warp * dpad + k) * 32 + lane] = (k < dims) ? cxg[(size_t)k * 32] : 0.f;
         }
     }
     SsbTop top;
@@ -656,8 +772,28 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
         __syncthreads();
         if (!live) continue;
         if (DP > 0) {
-            for (int g = g0; g < g1; ++g) {
-                const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(g - g0) * DP);
+            int gg = g0;
+            for (; gg + 2 <= g1; gg += 2) {
+                const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(gg - g0) * DP);
+                const float4* t4 = s4 + DP / 4;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < DP / 4; ++k4) {
+                    const float4 e = s4[k4], f = t4[k4];
+                    a0 = fmaf(e.x, x[4 * k4 + 0], a0);
+                    a1 = fmaf(e.y, x[4 * k4 + 1], a1);
+                    a2 = fmaf(e.z, x[4 * k4 + 2], a2);
+                    a3 = fmaf(e.w, x[4 * k4 + 3], a3);
+                    b0 = fmaf(f.x, x[4 * k4 + 0], b0);
+                    b1 = fmaf(f.y, x[4 * k4 + 1], b1);
+                    b2 = fmaf(f.z, x[4 * k4 + 2], b2);
+                    b3 = fmaf(f.w, x[4 * k4 + 3], b3);
+                }
+                ssb_top_push(top, (a0 + a1) + (a2 + a3), gg);
+                ssb_top_push(top, (b0 + b1) + (b2 + b3), gg + 1);
+            }
+            for (; gg < g1; ++gg) {
+                const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(gg - g0) * DP);
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
                 for (int k4 = 0; k4 < DP / 4; ++k4) {
@@ -667,12 +803,12 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
                     a2 = fmaf(e.z, x[4 * k4 + 2], a2);
                     a3 = fmaf(e.w, x[4 * k4 + 3], a3);
                 }
-                ssb_top_push(top, (a0 + a1) + (a2 + a3), g);
+                ssb_top_push(top, (a0 + a1) + (a2 + a3), gg);
             }
         } else {
             const float* xw = xs + (size_t)warp * dpad * 32 + lane;
-            for (int g = g0; g < g1; ++g) {
-                const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(g - g0) * dpad);
+            for (int gg = g0; gg < g1; ++gg) {
+                const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(gg - g0) * dpad);
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                 for (int k4 = 0; k4 < (dpad >> 2); ++k4) {
                     const float4 e = s4[k4];
@@ -682,46 +818,51 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
                     a2 = fmaf(e.z, xk[64], a2);
                     a3 = fmaf(e.w, xk[96], a3);
                 }
-                ssb_top_push(top, (a0 + a1) + (a2 + a3), g);
+                ssb_top_push(top, (a0 + a1) + (a2 + a3), gg);
             }
         }
     }
     if (!live) return;
+    float* pv = pval + ((size_t)g * n_cand) * 32 + lane;
+    int* pi = pidx + ((size_t)g * n_cand) * 32 + lane;
 #pragma unroll
     for (int i = 0; i < SSB_TOPK; ++i) {
-        pval[(size_t)(blockIdx.x * SSB_TOPK + i) * B + trial] = top.v[i];
-        pidx[(size_t)(blockIdx.x * SSB_TOPK + i) * B + trial] = top.g[i];
+        pv[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = top.v[i];
+        pi[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = top.g[i];
     }
 }
 
-// CTA = 32 trials x 8 warps: warps split the candidate list, merge through shared memory, then
+// CTA = one trial group x 8 warps: warps split the candidate list, merge through shared memory, then
 // candidates within eps of the fp32 maximum are re-scored in fp64 (S64 is the float64 grid) and
-// the winning index / grid row are written.
+// the winning index / grid row are written.  out_base (may be null) is a group-tiled arena.
 __global__ void __launch_bounds__(256)
-k_cleanup_pick(int B, int dims, int dpad, int ncand, const float* __restrict__ cx, const float* __restrict__ pval,
+k_cleanup_pick(int dims, int dpad, int ncand, const float* __restrict__ cx, const float* __restrict__ pval,
                const int* __restrict__ pidx, const double* __restrict__ S64, const float* __restrict__ S32,
-               float* __restrict__ out_rows, int* __restrict__ out_idx, const double* __restrict__ q64, long long q0,
-               long long n_q) {
+               float* __restrict__ out_base, int out_rows_per_group, int out_row0, int* __restrict__ out_idx,
+               const double* __restrict__ q64, long long q0, long long n_q) {
     __shared__ float sv[8][32];
     __shared__ int sg[8][32];
     __shared__ float sn[8][32];
     __shared__ int sc[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int trial = blockIdx.x * 32 + lane;
-    if (trial >= B) return;  // B is a multiple of 32: whole CTAs exit together
+    const int g = blockIdx.x;
+    const int trial = g * 32 + lane;
+    const float* pv = pval + ((size_t)g * ncand) * 32 + lane;
+    const int* pi = pidx + ((size_t)g * ncand) * 32 + lane;
+    const float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
     float best = -INFINITY;
     int best_g = 0x7fffffff;
     for (int i = warp; i < ncand; i += 8) {
-        const float v = pval[(size_t)i * B + trial];
-        const int g = pidx[(size_t)i * B + trial];
-        if (v > best || (v == best && g < best_g)) {
+        const float v = pv[(size_t)i * 32];
+        const int gi = pi[(size_t)i * 32];
+        if (v > best || (v == best && gi < best_g)) {
             best = v;
-            best_g = g;
+            best_g = gi;
         }
     }
     float xn = 0.f;
     for (int k = warp; k < dims; k += 8) {
-        const float xv = cx[(size_t)k * B + trial];
+        const float xv = cxg[(size_t)k * 32];
         xn = fmaf(xv, xv, xn);
     }
     sv[warp][lane] = best;
@@ -733,10 +874,10 @@ k_cleanup_pick(int B, int dims, int dpad, int ncand, const float* __restrict__ c
     xn = sn[0][lane];
     for (int w = 1; w < 8; ++w) {
         const float v = sv[w][lane];
-        const int g = sg[w][lane];
-        if (v > best || (v == best && g < best_g)) {
+        const int gi = sg[w][lane];
+        if (v > best || (v == best && gi < best_g)) {
             best = v;
-            best_g = g;
+            best_g = gi;
         }
         xn += sn[w][lane];
     }
@@ -744,7 +885,7 @@ k_cleanup_pick(int B, int dims, int dpad, int ncand, const float* __restrict__ c
     const float eps = 4.0f * (float)dims * 5.97e-8f * sqrtf(xn) + 1e-30f;
     int n_close = 0;
     for (int i = warp; i < ncand; i += 8)
-        if (pval[(size_t)i * B + trial] >= best - eps) ++n_close;
+        if (pv[(size_t)i * 32] >= best - eps) ++n_close;
     sc[warp][lane] = n_close;
     __syncthreads();
     n_close = 0;
@@ -754,30 +895,31 @@ k_cleanup_pick(int B, int dims, int dpad, int ncand, const float* __restrict__ c
         double dbest = -1e300;
         int dg = 0x7fffffff;
         for (int i = 0; i < ncand; ++i) {
-            if (pval[(size_t)i * B + trial] >= best - eps) {
-                const int g = pidx[(size_t)i * B + trial];
-                if (g == 0x7fffffff) continue;
-                const double* sgp = S64 + (size_t)g * dims;
+            if (pv[(size_t)i * 32] >= best - eps) {
+                const int gi = pi[(size_t)i * 32];
+                if (gi == 0x7fffffff) continue;
+                const double* sgp = S64 + (size_t)gi * dims;
                 double acc = 0.0;
                 // argmax is invariant to the positive normalisation, so the raw float64 query can be used
                 if (q64 != nullptr && q0 + trial < n_q) {
                     const double* qr = q64 + (size_t)(q0 + trial) * dims;
                     for (int k = 0; k < dims; ++k) acc += sgp[k] * qr[k];
                 } else {
-                    for (int k = 0; k < dims; ++k) acc += sgp[k] * (double)cx[(size_t)k * B + trial];
+                    for (int k = 0; k < dims; ++k) acc += sgp[k] * (double)cxg[(size_t)k * 32];
                 }
-                if (acc > dbest || (acc == dbest && g < dg)) {
+                if (acc > dbest || (acc == dbest && gi < dg)) {
                     dbest = acc;
-                    dg = g;
+                    dg = gi;
                 }
             }
         }
         best_g = dg;
     }
     if (out_idx && warp == 0) out_idx[trial] = best_g;
-    if (out_rows) {
+    if (out_base) {
         const float* sgp = S32 + (size_t)best_g * dpad;
-        for (int k = warp; k < dims; k += 8) out_rows[(size_t)k * B + trial] = sgp[k];
+        float* og = out_base + ((size_t)g * out_rows_per_group + out_row0) * 32 + lane;
+        for (int k = warp; k < dims; k += 8) og[(size_t)k * 32] = sgp[k];
     }
 }
 
@@ -785,32 +927,32 @@ k_cleanup_pick(int B, int dims, int dpad, int ncand, const float* __restrict__ c
 // Gated correction node (slam.py:233-237): x = [p ; q ; flag].  CTA = one trial group x 8 warps;
 // warps split the dimensions, the dot product is reduced through shared memory.
 // desc: d in_row0 out_vec rate_bits thres_bits atol_bits
-__global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ desc, int item0) {
+__global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ desc, int item0, int i_rel) {
     __shared__ float part[8][32];
     const int* d = desc + (item0 + blockIdx.y) * 6;
     const int dims = d[0], in_row0 = d[1], out_vec = d[2];
     const float rate = __int_as_float(d[3]), thres = __int_as_float(d[4]), atol = __int_as_float(d[5]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int trial = blockIdx.x * 32 + lane;
-    const size_t B = c.B;
-    const SsbStep s = ssb_step(c);
+    const int g = blockIdx.x;
+    const SsbStep s = ssb_step(c, i_rel);
+    float* vg = ssb_grp(c.vec, c.nv, g, lane);
     // pass 1: p - q goes to the output slot, p.q is reduced over the 8 warps
     float dot = 0.f;
     for (int k = warp; k < dims; k += 8) {
-        const float p = ssb_row(c, s, in_row0 + k, trial, s.par_old);
-        const float q = ssb_row(c, s, in_row0 + dims + k, trial, s.par_old);
+        const float p = ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg);
+        const float q = ssb_row(c.csr_ptr, s.ent_old, in_row0 + dims + k, vg);
         dot = fmaf(p, q, dot);
-        c.vec[(size_t)(out_vec + k) * B + trial] = p - q;
+        vg[(size_t)(out_vec + k) * 32] = p - q;
     }
     part[warp][lane] = dot;
     __syncthreads();
     dot = 0.f;
     for (int w = 0; w < 8; ++w) dot += part[w][lane];
-    const float flag = ssb_row(c, s, in_row0 + 2 * dims, trial, s.par_old);
+    const float flag = ssb_row(c.csr_ptr, s.ent_old, in_row0 + 2 * dims, vg);
     const bool open = (fabsf(flag) <= atol) && (dot > thres);
     // pass 2: each thread rescales the values it wrote itself
     for (int k = warp; k < dims; k += 8) {
-        float* o = c.vec + (size_t)(out_vec + k) * B + trial;
+        float* o = vg + (size_t)(out_vec + k) * 32;
         *o = open ? rate * *o : 0.f;
     }
 }
@@ -819,31 +961,43 @@ __global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ 
 // End-of-step rows: Lowpass updates (y_new = a*y_old + b*u, written to the other half of
 // the ping-pong buffer = nengo's update-after-read), probe samples, PES activity traces.
 // rows: [csr_row | act_row, kind, dst]; kind 0 filter, 1 probe, 2 activity trace
-__global__ void __launch_bounds__(128) k_lin(SsbCtx c, const int* __restrict__ rows, const float* __restrict__ ab, int n_rows) {
+__global__ void __launch_bounds__(128) k_lin(SsbCtx c, const int* __restrict__ rows, const float* __restrict__ ab, int n_rows,
+                                              int i_rel) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x * 4 + warp;
+#ifdef SSB_DEBUG
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        printf("k_lin: vec %p probe %p afilt %p act %p ent0 %p ent1 %p ptr %p rows %p ab %p dyn %p n_rows %d nv %d\n", c.vec,
+               c.probe, c.afilt, c.act, c.ent0, c.ent1, c.csr_ptr, rows, ab, c.dyn, n_rows, c.nv);
+#endif
     if (r >= n_rows) return;
-    const int trial = blockIdx.y * 32 + lane;
-    const size_t B = c.B;
-    const SsbStep s = ssb_step(c);
+    const int g = blockIdx.y;
+    const SsbStep s = ssb_step(c, i_rel);
+    float* vg = ssb_grp(c.vec, c.nv, g, lane);
     const int src = rows[r * 3], kind = rows[r * 3 + 1], dst = rows[r * 3 + 2];
+#ifdef SSB_DEBUG
+    if (lane == 0 && g == 0 && r < 4)
+        printf("k_lin r %d src %d kind %d dst %d lo %d hi %d step %lld\n", r, src, kind, dst, c.csr_ptr[src], c.csr_ptr[src + 1],
+               s.step);
+#endif
     const float a = ab[r * 2], b = ab[r * 2 + 1];
     if (kind == 0) {
-        const float u = ssb_row(c, s, src, trial, s.par_old);
-        const float y = c.vec[(size_t)(1 + dst + s.par_old) * B + trial];
-        c.vec[(size_t)(1 + dst + s.par_new) * B + trial] = fmaf(b, u, a * y);
+        const float u = ssb_row(c.csr_ptr, s.ent_old, src, vg);
+        const float y = vg[(size_t)(1 + dst + s.par_old) * 32];
+        vg[(size_t)(1 + dst + s.par_new) * 32] = fmaf(b, u, a * y);
     } else if (kind == 1) {
-        const float u = ssb_row(c, s, src, trial, s.par_old);
-        c.probe[((size_t)(s.step - c.dyn[2]) * c.n_probe + dst) * B + trial] = u;
+        const float u = ssb_row(c.csr_ptr, s.ent_old, src, vg);
+        float* pg = c.probe + (((size_t)g * c.probe_cap + (size_t)(s.step - c.dyn[2])) * c.n_probe + dst) * 32 + lane;
+        __stcs(pg, u);
     } else {
-        const int old_buf = (int)(s.step & 1);
-        const float y = c.afilt[((size_t)old_buf * c.n_afilt + dst) * B + trial];
-        const float u = c.act[(size_t)src * B + trial];
-        c.afilt[((size_t)(1 - old_buf) * c.n_afilt + dst) * B + trial] = fmaf(b, u, a * y);
+        float* fg = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane);
+        const float y = fg[((size_t)s.odd * c.n_afilt + dst) * 32];
+        const float u = ssb_grp(c.act, c.n_act, g, lane)[(size_t)src * 32];
+        fg[((size_t)(1 - s.odd) * c.n_afilt + dst) * 32] = fmaf(b, u, a * y);
     }
 }
 
-__global__ void k_advance(long long* dyn) { dyn[0] += 1; }
+__global__ void k_advance(long long* dyn, int n) { dyn[0] += n; }
 
 // --------------------------------------------------------------------------------------
 // Stand-alone SSP encode: out[p][m] = (1/d) * sum_k cos(theta_k + 2 pi k m / d), theta = A_scaled x.
@@ -861,7 +1015,6 @@ __global__ void k_ssp_encode(const double* __restrict__ A, const double* __restr
         cs[d + k] = sn;
     }
     __syncthreads();
-    const double w = 6.283185307179586476925286766559 / (double)d;
     for (int m = threadIdx.x; m < d; m += blockDim.x) {
         double acc = 0.0;
         for (int k = 0; k < d; ++k) {
@@ -871,24 +1024,24 @@ __global__ void k_ssp_encode(const double* __restrict__ A, const double* __restr
             sincospi(2.0 * (double)km / (double)d, &sn, &cn);
             acc += cs[k] * cn - cs[d + k] * sn;
         }
-        (void)w;
         out[(size_t)p * d + m] = acc / (double)d;
     }
 }
 
-// Normalise query rows (skip if norm < 1e-6) and transpose to [k][N_pad] float for the scan.
+// Normalise query rows (skip if norm < 1e-6) and write them group-tiled [g][k][32] in float for the scan.
 __global__ void k_decode_prep(const double* __restrict__ q, float* __restrict__ cx, long long n_q, int B, int d, int dpad,
                               long long q0) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B) return;
+    float* cxg = cx + ((size_t)(t >> 5) * dpad) * 32 + (t & 31);
     const long long row = q0 + t;
     if (row >= n_q) {
-        for (int k = 0; k < dpad; ++k) cx[(size_t)k * B + t] = 0.f;
+        for (int k = 0; k < dpad; ++k) cxg[(size_t)k * 32] = 0.f;
         return;
     }
     double nrm = 0.0;
     for (int k = 0; k < d; ++k) nrm += q[(size_t)row * d + k] * q[(size_t)row * d + k];
     nrm = sqrt(nrm);
     const double sc = nrm < 1e-6 ? 1.0 : 1.0 / nrm;
-    for (int k = 0; k < dpad; ++k) cx[(size_t)k * B + t] = k < d ? (float)(q[(size_t)row * d + k] * sc) : 0.f;
+    for (int k = 0; k < dpad; ++k) cxg[(size_t)k * 32] = k < d ? (float)(q[(size_t)row * d + k] * sc) : 0.f;
 }

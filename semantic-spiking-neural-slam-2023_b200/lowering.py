@@ -31,9 +31,9 @@ from . import nengo_shim as ns
 from . import nodeops
 from .builder import BuiltModel
 
-TAB_BASE = 1 << 24          # CSR column ids >= TAB_BASE address the input-table row of this step
 SMALL_MAX_DIMS = 4
 SMALL_MAX_OUT = 8
+CSR_PAD = 8                 # CSR rows are padded to a multiple of this with (row 0, coefficient 0)
 DEC_TILE = 8                # decoder output rows are padded to a multiple of this
 TARGET_CTAS = 148 * 8       # decode / PES launches are split until they offer ~8 CTAs per SM
 MAX_DEC_CHUNKS = 32
@@ -130,7 +130,7 @@ class _Lowerer:
     def classify_ensembles(self):
         """Narrow ensembles (VCOs, product squares) are fused encode->neuron->decode items; wide ones
         write activities and are decoded by separate launches whose neuron range is split into chunks
-        (one partial-sum slot per chunk; the consumers' CSR rows add the slots up)."""
+        (split-K: partial sums are parked in a scratch arena and added up by the last CTA to arrive)."""
         self.ens_dec_conns = {e: [] for e in self.ensembles}
         for conn in self.conns:
             if isinstance(conn.pre_obj, ns.Ensemble):
@@ -164,11 +164,8 @@ class _Lowerer:
         return c.size_out if isinstance(c, ns.Connection) else c.size_in
 
     def _dec_expr(self, c):
-        """Decoded value of connection/probe ``c`` = sum of its partial-sum slots."""
-        size, k = self._out_size(c), self.dec_chunks[c]
-        rows = np.tile(np.arange(size), k)
-        cols = self.dec_col[c] + np.arange(size * k)
-        return sp.csr_matrix((np.ones(size * k), (rows, cols)), shape=(size, self.ncol))
+        """Decoded value of connection/probe ``c`` (split-K partial sums are reduced inside the launch)."""
+        return self._eye(self.dec_col[c], self._out_size(c))
 
     # ------------------------------------------------------------------ source columns
     def enumerate_sources(self):
@@ -198,7 +195,7 @@ class _Lowerer:
         # decoded outputs, grouped per ensemble so that small ensembles own one contiguous slot
         for ens in self.ensembles:
             for c in self.ens_dec_conns[ens]:
-                self.dec_col[c] = alloc("dec", c, self._out_size(c) * self.dec_chunks[c])
+                self.dec_col[c] = alloc("dec", c, self._out_size(c))
         for node in self.nodes:
             if self.node_kind[node] == "fn":
                 self.fn_col[node] = alloc("fn", node, node.size_out)
@@ -301,7 +298,7 @@ class _Lowerer:
         INF = 1 << 20
         col_level = np.zeros(self.ncol, dtype=np.int64)
         pending_ens, pending_fn = set(self.ensembles), set(fn_in)
-        dec_width = {c: self._out_size(c) * self.dec_chunks[c] for c in self.dec_col}
+        dec_width = {c: self._out_size(c) for c in self.dec_col}
         for c in pes_rule:
             col_level[self.dec_col[c]:self.dec_col[c] + dec_width[c]] = INF
         unresolved = np.zeros(self.ncol, dtype=bool)
@@ -356,32 +353,34 @@ class _Lowerer:
             raise RuntimeError("same-step dependency cycle between ensembles / function nodes")
         n_levels = 1 + max(list(ens_level.values()) + list(fn_level.values()) + [0])
 
-        # ---- device column map
+        # ---- device column map: row 0 ones | filters A | filters B | this step's table rows | scratch
         NF = sum(1 for k in self.col_kind if k == "filt")
+        NT = sum(1 for k in self.col_kind if k == "tab")
         dev_col = np.zeros(self.ncol, dtype=np.int64)
         next_filt, next_tab = 1, 0
-        next_scratch = 1 + 2 * NF
+        tab_row0 = 1 + 2 * NF
+        next_scratch = tab_row0 + NT
         for c in range(1, self.ncol):
             k = self.col_kind[c]
             if k == "filt":
                 dev_col[c] = next_filt
                 next_filt += 1
             elif k == "tab":
-                dev_col[c] = TAB_BASE + next_tab
+                dev_col[c] = tab_row0 + next_tab
                 next_tab += 1
             else:
                 dev_col[c] = next_scratch
                 next_scratch += 1
-        NV, NT = next_scratch, next_tab
+        NV = next_scratch
         self.dev_col = dev_col
         for node, c0 in self.tab_col.items():
-            plan.tables.append((node, int(dev_col[c0] - TAB_BASE), node.size_out))
+            plan.tables.append((node, int(dev_col[c0] - tab_row0), node.size_out))
         for key, c0 in self.filt_col.items():
             size = key.size_out if isinstance(key, ns.Connection) else key.size_in
             plan.filters[key] = (int(dev_col[c0] - 1), size)
 
         # ---- CSR program
-        csr_ptr, csr_idx, csr_val = [0], [], []
+        csr_ptr, csr_idx, csr_val = [0], [], []   # csr_idx holds parity-0 vec rows (filter columns in half A)
 
         def add_rows(mat):
             mat = mat.tocsr()
@@ -394,6 +393,9 @@ class _Lowerer:
                 order = np.argsort(cols, kind="stable")
                 csr_idx.extend(dev_col[cols[order]].tolist())
                 csr_val.extend(mat.data[lo:hi][order].tolist())
+                pad = (-(hi - lo)) % CSR_PAD      # the kernels walk rows 8 entries at a time (no tail)
+                csr_idx.extend([0] * pad)
+                csr_val.extend([0.0] * pad)
                 csr_ptr.append(len(csr_idx))
             return row0
 
@@ -417,11 +419,15 @@ class _Lowerer:
 
         def ntype_id(nt):
             if isinstance(nt, ns.LIF):
-                key = (NT_LIF, nt.tau_rc, nt.tau_ref, nt.min_voltage, nt.amplitude)
+                if nt.min_voltage != 0:
+                    raise NotImplementedError("the packed one-word LIF state needs min_voltage == 0 (nengo's default)")
+                # polynomial expm1 / log1p are exact to fp32 for dt / tau_rc <= 1/8 (SSB kernels header)
+                fast = 1.0 if dt / nt.tau_rc <= 0.125 else 0.0
+                key = (NT_LIF, nt.tau_rc, nt.tau_ref, nt.min_voltage, nt.amplitude, fast, 0.0, 0.0)
             elif isinstance(nt, ns.LIFRate):
-                key = (NT_LIFRATE, nt.tau_rc, nt.tau_ref, 0.0, nt.amplitude)
+                key = (NT_LIFRATE, nt.tau_rc, nt.tau_ref, 0.0, nt.amplitude, 0.0, 0.0, 0.0)
             elif isinstance(nt, ns.RectifiedLinear):
-                key = (NT_RELU, 0.0, 0.0, 0.0, nt.amplitude)
+                key = (NT_RELU, 0.0, 0.0, 0.0, nt.amplitude, 0.0, 0.0, 0.0)
             else:
                 raise NotImplementedError(f"neuron type {type(nt).__name__} is not supported by the B200 backend")
             if key not in ntype_ids:
@@ -436,6 +442,17 @@ class _Lowerer:
         pes_trace, cleanup_s64 = [], [[] for _ in range(n_levels)]
         nn = n_act = n_lenc = n_ldec = n_afilt = 0
         n_small = n_big = 0
+        n_part = n_jtiles = 0
+
+        def splitk(c, size_out):
+            """(n_chunks, part_off, counter0) of a decode / PES item."""
+            nonlocal n_part, n_jtiles
+            k = self.dec_chunks[c]
+            part_off, counter0 = n_part, n_jtiles
+            if k > 1:
+                n_part += k * size_out
+            n_jtiles += -(-size_out // DEC_TILE)
+            return [k, part_off, counter0]
 
         for ens in self.ensembles:
             p = self.model.params[ens]
@@ -520,14 +537,14 @@ class _Lowerer:
                     pes_desc.append([n, size_out, d_off, a_off, act0, err_row0, out_vec,
                                      int(np.float32(alpha).view(np.int32)),
                                      int(np.float32(decay).view(np.int32)),
-                                     int(np.float32(1.0 - decay).view(np.int32)), self.dec_chunks[c]])
+                                     int(np.float32(1.0 - decay).view(np.int32))] + splitk(c, size_out))
                 else:
                     jpad = size_out + ((-size_out) % DEC_TILE)
                     Wd = np.zeros((n, jpad))
                     Wd[:, :size_out] = self._dec_weights(c).T
                     w_off = add_w(Wd)
                     plan.static_dec[c] = (w_off, size_out, jpad, n)
-                    dec_desc[lvl].append([n, size_out, jpad, act0, w_off, out_vec, self.dec_chunks[c]])
+                    dec_desc[lvl].append([n, size_out, jpad, act0, w_off, out_vec] + splitk(c, size_out))
 
         for node, mat in fn_in.items():
             op = self.node_op[node]
@@ -609,25 +626,26 @@ class _Lowerer:
             stages.append(entry)
         plan.arrays.update({
             "csr_ptr": np.asarray(csr_ptr, dtype=np.int32),
-            "csr_idx": np.asarray(csr_idx, dtype=np.int32),
-            "csr_val": np.asarray(csr_val, dtype=np.float32),
+            "csr_ent0": self._entries(csr_idx, csr_val, 0, NF),
+            "csr_ent1": self._entries(csr_idx, csr_val, NF, NF),
             "weights": np.concatenate(W) if W else np.zeros(4, dtype=np.float32),
             "ens_small": arr(cat["small"], 9),
             "ens_big": arr(cat["big"], 16),
-            "dec": arr(cat["dec"], 7),
-            "pes": arr(pes_desc, 11),
+            "dec": arr(cat["dec"], 9),
+            "pes": arr(pes_desc, 13),
             "cleanup": arr(cat["cleanup"], 6),
             "gate": arr(cat["gate"], 6),
             "lin_rows": arr(lin_rows, 3),
             "lin_ab": np.asarray(lin_ab, dtype=np.float32).reshape(-1, 2),
             "stages": arr(stages, 10),
-            "ntypes": np.asarray(ntypes, dtype=np.float32).reshape(-1, 5),
+            "ntypes": np.asarray(ntypes, dtype=np.float32).reshape(-1, 8),
             "cleanup_s64": np.concatenate([a for lvl in cleanup_s64 for a in lvl] + [np.zeros(0)]),
         })
         plan.cleanup_nodes = [n for lvl in range(n_levels) for n in fn_in
                               if self.node_op[n].kind == "cleanup" and fn_level[n] == lvl]
-        plan.scalars.update(dict(dt=dt, nv=NV, nf=NF, nt=NT, nn=nn, n_act=n_act, n_lenc=n_lenc, n_ldec=n_ldec,
-                                 n_afilt=n_afilt, n_probe=n_probe_rows, n_levels=n_levels, chunk_cap=chunk_cap))
+        plan.scalars.update(dict(dt=dt, nv=NV, nf=NF, nt=NT, tab_row0=tab_row0, nn=nn, n_act=n_act, n_lenc=n_lenc,
+                                 n_ldec=n_ldec, n_afilt=n_afilt, n_probe=n_probe_rows, n_levels=n_levels,
+                                 chunk_cap=chunk_cap, n_part=n_part, n_jtiles=n_jtiles))
         n_static = int(sum(a.size for a in W))
         plan.stats = dict(n_neurons=nn, n_filter_states=NF, n_learned=n_lenc + n_ldec, n_static_weights=n_static,
                           n_table_words=NT, n_probe_words=n_probe_rows, n_small=n_small, n_big=n_big,
@@ -643,6 +661,17 @@ class _Lowerer:
             "inputs": 4 * NT,
         }
         return plan
+
+    @staticmethod
+    def _entries(idx, val, par, nf):
+        """CSR entries as (vec row, float32 coefficient bits) pairs with the filter columns resolved to
+        the half that is read on steps of this parity (``par`` = 0 for even steps, ``nf`` for odd ones)."""
+        rows = np.asarray(idx, dtype=np.int64)
+        rows = np.where((rows >= 1) & (rows <= nf), rows + par, rows)
+        ent = np.empty((len(rows), 2), dtype=np.int32)
+        ent[:, 0] = rows
+        ent[:, 1] = np.asarray(val, dtype=np.float32).view(np.int32)
+        return ent
 
     def _dec_weights(self, c):
         if isinstance(c, ns.Connection):

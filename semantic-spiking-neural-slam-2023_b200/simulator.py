@@ -116,7 +116,7 @@ class Simulator:
                 v0[row0:row0 + n, :self.n_trials] = m.initial_voltages(ens, self.trial_seeds).T
                 if self.B > self.n_trials:
                     v0[row0:row0 + n, self.n_trials:] = v0[row0:row0 + n, :1]
-            self._upload("v", 0, v0)
+            self._upload("st", 0, v0)   # packed LIF state: s >= 0 is the voltage of a non-refractory neuron
         for ens, (row0, n, dims) in plan.learned_enc.items():
             self._upload("lenc", row0, self._rows(m.params[ens].scaled_encoders.reshape(-1)))
         for conn, (row0, size_out, n) in plan.learned_dec.items():
@@ -303,11 +303,11 @@ class Simulator:
 
     # ------------------------------------------------------------------ checker / bench conveniences
     def neuron_state(self, ens):
-        """(voltage, refractory_time) arrays [n_trials, n_neurons] of an ensemble."""
+        """(voltage, refractory_time) arrays [n_trials, n_neurons] of an ensemble, unpacked from the
+        one-word device state (s >= 0: voltage, not refractory; s < 0: refractory for -s more seconds)."""
         row0, n = self.plan.ens_state[ens]
-        v = self._download("v", row0, n)[:, :self.n_trials].T
-        r = self._download("ref", row0, n)[:, :self.n_trials].T
-        return v, r
+        s = self._download("st", row0, n)[:, :self.n_trials].T
+        return np.maximum(s, 0.0), np.maximum(-s, 0.0)
 
     def activities(self, ens):
         """Last-step output of a wide ensemble [n_trials, n_neurons] (0 or 1/dt when spiking)."""

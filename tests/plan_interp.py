@@ -5,7 +5,7 @@ It executes the same launch sequence and descriptor semantics as the CUDA kernel
 operator-level oracle on a machine without a GPU.  It is never imported by the package."""
 import numpy as np
 
-from sspslam_b200.lowering import TAB_BASE, NT_LIF, NT_LIFRATE
+from sspslam_b200.lowering import NT_LIF, NT_LIFRATE
 
 
 class PlanInterpreter:
@@ -13,7 +13,7 @@ class PlanInterpreter:
         self.p, self.dt_ = plan, dtype
         a, sc = plan.arrays, plan.scalars
         self.dt = dtype(sc["dt"])
-        self.nf, self.nt = int(sc["nf"]), int(sc["nt"])
+        self.nf, self.nt, self.tab_row0 = int(sc["nf"]), int(sc["nt"]), int(sc["tab_row0"])
         self.vec = np.zeros(int(sc["nv"]), dtype)
         self.vec[0] = 1
         self.v = np.zeros(int(sc["nn"]), dtype)
@@ -23,7 +23,10 @@ class PlanInterpreter:
         self.ldec = np.zeros(max(1, int(sc["n_ldec"])), dtype)
         self.afilt = np.zeros((2, max(1, int(sc["n_afilt"]))), dtype)
         self.W = a["weights"].astype(dtype)
-        self.ptr, self.idx, self.val = a["csr_ptr"], a["csr_idx"], a["csr_val"].astype(dtype)
+        self.ptr = a["csr_ptr"]
+        self.ent = [a["csr_ent0"], a["csr_ent1"]]          # (vec row, coefficient bits), per step parity
+        self.val = np.ascontiguousarray(a["csr_ent0"][:, 1]).view(np.float32).astype(dtype)
+        assert np.array_equal(a["csr_ent0"][:, 1], a["csr_ent1"][:, 1])
         self.step = 0
         self.tables = np.zeros((0, self.nt), dtype)
         cols = []
@@ -48,26 +51,20 @@ class PlanInterpreter:
         self.cidx = np.zeros(len(self.grids), np.int64)
         self.probe_rows = []
 
-    # ---- CSR rows
-    def rows(self, row0, n, par):
+    # ---- CSR rows: ``which`` = 0 reads what this step reads, 1 the half the previous step read
+    def rows(self, row0, n, which=0):
+        ent = self.ent[(self.step & 1) ^ which]
         out = np.zeros(n, self.dt_)
         for r in range(n):
             lo, hi = self.ptr[row0 + r], self.ptr[row0 + r + 1]
             acc = self.dt_(0)
             for k in range(lo, hi):
-                i = int(self.idx[k])
-                if i >= TAB_BASE:
-                    x = self.tables[self.step, i - TAB_BASE]
-                elif 1 <= i <= self.nf:
-                    x = self.vec[i + par]
-                else:
-                    x = self.vec[i]
-                acc += self.val[k] * x
+                acc += self.val[k] * self.vec[int(ent[k, 0])]
             out[r] = acc
         return out
 
     def neuron(self, tid, J, s0, n):
-        kind, tau_rc, tau_ref, min_v, amp = self.p.arrays["ntypes"][tid].astype(np.float64)
+        kind, tau_rc, tau_ref, min_v, amp = self.p.arrays["ntypes"][tid].astype(np.float64)[:5]
         dt = self.dt
         if int(kind) == NT_LIF:
             v, r = self.v[s0:s0 + n], self.ref[s0:s0 + n]
@@ -97,69 +94,75 @@ class PlanInterpreter:
         a, W = self.p.arrays, self.W
         s = self.step
         par_old, par_new = (self.nf, 0) if s & 1 else (0, self.nf)
+        if self.nt:
+            self.vec[self.tab_row0:self.tab_row0 + self.nt] = self.tables[s]      # k_begin
         for st in a["stages"]:
             for d in a["ens_small"][st[0]:st[0] + st[1]]:
                 n, dims, nout, s0, w_off, in_row0, out_vec, tid, stride = (int(x) for x in d)
                 pk = W[w_off:w_off + n * stride].reshape(n, stride)
-                x = self.rows(in_row0, dims, par_old)
+                x = self.rows(in_row0, dims)
                 out = self.neuron(tid, pk[:, 0] + pk[:, 1:1 + dims] @ x, s0, n)
                 self.vec[out_vec:out_vec + nout] = pk[:, 1 + dims:1 + dims + nout].T @ out
             for d in a["ens_big"][st[2]:st[2] + st[3]]:
                 (n, dims, dpad, s0, act0, enc_off, bias_off, in_row0, tid, flags, jn_row0, jn_m, jn_w, voja_row,
                  scale_off, alpha_bits) = (int(x) for x in d)
-                x = self.rows(in_row0, dims, par_old)
+                x = self.rows(in_row0, dims)
                 if flags & 1:
                     E = self.lenc[enc_off:enc_off + n * dims].reshape(n, dims)
                 else:
                     E = W[enc_off:enc_off + n * dpad].reshape(n, dpad)[:, :dims]
                 J = W[bias_off:bias_off + n] + E @ x
                 if jn_m:
-                    J = J + W[jn_w:jn_w + n * jn_m].reshape(n, jn_m) @ self.rows(jn_row0, jn_m, par_old)
+                    J = J + W[jn_w:jn_w + n * jn_m].reshape(n, jn_m) @ self.rows(jn_row0, jn_m)
                 out = self.neuron(tid, J, s0, n)
                 self.act[act0:act0 + n] = out
                 if flags & 1:
-                    aL = np.int32(alpha_bits).view(np.float32).astype(self.dt_) * self.rows(voja_row, 1, par_old)[0]
+                    aL = np.int32(alpha_bits).view(np.float32).astype(self.dt_) * self.rows(voja_row, 1)[0]
                     sc = W[scale_off:scale_off + n]
                     E += aL * (sc[:, None] * np.outer(out, x) - out[:, None] * E)   # E is a view of lenc
             for ci in range(st[6], st[6] + st[7]):
                 G, dims, dpad, s_off, in_row0, out_vec = (int(x) for x in a["cleanup"][ci])
-                x = self.rows(in_row0, dims, par_old)
+                x = self.rows(in_row0, dims)
                 g = int(np.argmax(self.grids[ci] @ x.astype(np.float64)))
                 self.cidx[ci] = g
                 self.vec[out_vec:out_vec + dims] = W[s_off + g * dpad:s_off + g * dpad + dims]
             for d in a["gate"][st[8]:st[8] + st[9]]:
                 dims, in_row0, out_vec = int(d[0]), int(d[1]), int(d[2])
                 rate, thres, atol = (np.int32(x).view(np.float32).astype(np.float64) for x in d[3:6])
-                x = self.rows(in_row0, 2 * dims + 1, par_old)
+                x = self.rows(in_row0, 2 * dims + 1)
                 p_, q_ = x[:dims], x[dims:2 * dims]
                 open_ = abs(x[-1]) <= atol and float(p_ @ q_) > thres
                 self.vec[out_vec:out_vec + dims] = rate * (p_ - q_) if open_ else 0.0
             for d in a["dec"][st[4]:st[4] + st[5]]:
-                n, so, jpad, act0, w_off, out_vec, nch = (int(x) for x in d)
+                n, so, jpad, act0, w_off, out_vec, nch = (int(x) for x in d[:7])
                 Wd = W[w_off:w_off + n * jpad].reshape(n, jpad)[:, :so]
                 per = -(-n // nch)
-                for c in range(nch):
+                total = np.zeros(so, self.dt_)
+                for c in range(nch):                       # split-K partial sums, added in chunk order
                     lo, hi = c * per, min(n, (c + 1) * per)
-                    self.vec[out_vec + c * so:out_vec + (c + 1) * so] = Wd[lo:hi].T @ self.act[act0 + lo:act0 + hi]
+                    total = total + Wd[lo:hi].T @ self.act[act0 + lo:act0 + hi]
+                self.vec[out_vec:out_vec + so] = total
         for d in a["pes"]:
             n, so, d_off, a_off, act0, err_row0, out_vec = (int(x) for x in d[:7])
             alpha = np.int32(d[7]).view(np.float32).astype(self.dt_)
             nch = int(d[10])
             D = self.ldec[d_off:d_off + so * n].reshape(so, n)
             if s > 0:
-                err = self.rows(err_row0, so, par_new)
+                err = self.rows(err_row0, so, 1)
                 D += np.outer(alpha * err, self.afilt[1 - (s & 1), a_off:a_off + n])
             per = -(-n // nch)
+            total = np.zeros(so, self.dt_)
             for c in range(nch):
                 lo, hi = c * per, min(n, (c + 1) * per)
-                self.vec[out_vec + c * so:out_vec + (c + 1) * so] = D[:, lo:hi] @ self.act[act0 + lo:act0 + hi]
+                total = total + D[:, lo:hi] @ self.act[act0 + lo:act0 + hi]
+            self.vec[out_vec:out_vec + so] = total
         probe = np.zeros(int(self.p.scalars["n_probe"]), self.dt_)
         new_f = {}
         for (src, kind, dst), (ca, cb) in zip(a["lin_rows"], a["lin_ab"].astype(self.dt_)):
             if kind == 0:
-                new_f[1 + dst + par_new] = cb * self.rows(src, 1, par_old)[0] + ca * self.vec[1 + dst + par_old]
+                new_f[1 + dst + par_new] = cb * self.rows(src, 1)[0] + ca * self.vec[1 + dst + par_old]
             elif kind == 1:
-                probe[dst] = self.rows(src, 1, par_old)[0]
+                probe[dst] = self.rows(src, 1)[0]
             else:
                 ob = s & 1
                 self.afilt[1 - ob, dst] = cb * self.act[src] + ca * self.afilt[ob, dst]

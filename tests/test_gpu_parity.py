@@ -186,7 +186,7 @@ def test_simulator_surface_run_trange_reset_unbatched():
         sim.run(0.05)
         assert sim.n_steps == 50 and abs(sim.time - 0.05) < 1e-12
         first = sim.data[sc.probe].copy()
-        assert first.shape == (50, 19)
+        assert first.shape == (50, sc.ssp_space.ssp_dim)
         np.testing.assert_allclose(sim.trange(), 0.001 * np.arange(1, 51))
         sim.step()
         assert sim.n_steps == 51

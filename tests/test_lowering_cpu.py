@@ -57,6 +57,7 @@ def test_slam_plan_matches_oracle(neuron_type, hint):
     assert plan.stats["n_learned"] == 2 * so * n
     # chunked decoders: the hint for a big batch needs fewer partial slots than a single-trial run
     chunks = int(plan.arrays["pes"][0][10])
+    assert plan.scalars["n_part"] >= (chunks * so if chunks > 1 else 0)
     jtiles = -(-so // lowering.DEC_TILE)
     want_chunks = -(-lowering.TARGET_CTAS // (jtiles * -(-hint // 32)))
     assert chunks == max(1, min(want_chunks, n // 32, lowering.MAX_DEC_CHUNKS))
