@@ -79,6 +79,13 @@ struct ssb_sim {
     int graph_steps = 0;
     bool use_graph = true;
     bool debug_sync = false, debug_failed = false;
+    // independent kernels of one dependency level run on side streams (fork/join with events; under
+    // capture these become parallel branches of the step graph)
+    bool parallel = true;
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> dep_pool;
+    size_t dep_used = 0;
+    int pes_level = -1;
     long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
     std::vector<size_t> s64_offsets;
     int n_levels = 0, n_lin = 0, n_pes = 0, n_small_total = 0;
@@ -252,11 +259,89 @@ void scan_smem_optin() {
     cudaFuncSetAttribute(k_cleanup_scan<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
 }
 
+// Wide ensembles of one level: one launch per (kernel flavour, width class); the items of a launch are
+// passed by value.  The chunk (neurons per CTA) shrinks for very wide ensembles so that the staged
+// encoder tile fits in shared memory.
 template <int DP>
-void launch_wide(ssb_sim* s, int item0, int n_items, int max_n, int smem, int i_rel) {
-    const int chunk = 64;   // neurons per CTA: 4 warps x 16
-    dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, n_items);
-    k_ens_wide<DP><<<grid, 128, smem, s->stream>>>(s->ctx, s->d_big, item0, chunk, i_rel);
+void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int cls, int i_rel) {
+    SsbItemList items;
+    items.n = 0;
+    int max_n = 0, max_dpad = 0, max_dims = 0, max_jn = 0;
+    for (int i = 0; i < stage[3] && items.n < 15; ++i) {
+        const int* d = &s->h_big[(stage[2] + i) * 16];
+        const int c = d[2] == 56 ? 0 : (d[2] == 100 ? 1 : 2);
+        if (c != cls || ((d[9] & 1) != 0) != voja) continue;
+        items.idx[items.n++] = stage[2] + i;
+        max_n = std::max(max_n, d[0]);
+        max_dpad = std::max(max_dpad, d[2]);
+        max_dims = std::max(max_dims, d[1]);
+        max_jn = std::max(max_jn, d[11]);
+    }
+    if (items.n == 0) return;
+    if (!voja) {
+        int chunk = 64;
+        auto smem_of = [&](int ch) {
+            return (size_t)(ch * max_dpad + ch + ch * max_jn + ch * 32 + max_dpad * 32 + max_jn * 32) * sizeof(float);
+        };
+        while (chunk > 8 && smem_of(chunk) > 64 * 1024) chunk >>= 1;
+        dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
+        k_wide_static<DP><<<grid, 128, smem_of(chunk), st>>>(s->ctx, s->d_big, items, chunk, i_rel);
+    } else {
+        int nwarps = 4;
+        auto smem_of = [&](int nw) {
+            return (size_t)(max_dpad * 32 + max_jn * 32 + nw * 2 * max_dims * 32) * sizeof(float);
+        };
+        while (nwarps > 1 && smem_of(nwarps) > 200 * 1024) nwarps >>= 1;
+        const int chunk = 16 * nwarps;
+        dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
+        k_wide_voja<DP><<<grid, 32 * nwarps, smem_of(nwarps), st>>>(s->ctx, s->d_big, items, chunk, i_rel);
+    }
+}
+
+void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, int i_rel) {
+    for (int v = 0; v < 2; ++v) {
+        launch_wide_class<56>(s, st, stage, v != 0, 0, i_rel);
+        launch_wide_class<100>(s, st, stage, v != 0, 1, i_rel);
+        launch_wide_class<0>(s, st, stage, v != 0, 2, i_rel);
+    }
+}
+
+void wide_smem_optin() {
+    const int lim = 200 * 1024;
+    cudaFuncSetAttribute(k_wide_static<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_static<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_static<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_voja<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_voja<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_voja<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+}
+
+cudaEvent_t dep_event(ssb_sim* s) {
+    if (s->dep_used == s->dep_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        s->dep_pool.push_back(e);
+    }
+    return s->dep_pool[s->dep_used++];
+}
+
+// `to` waits for everything enqueued on `from` so far
+void stream_dep(ssb_sim* s, cudaStream_t from, cudaStream_t to) {
+    if (from == to) return;
+    cudaEvent_t e = dep_event(s);
+    cudaEventRecord(e, from);
+    cudaStreamWaitEvent(to, e, 0);
+}
+
+void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
+    LaunchTimer t(s, K_PES);
+    int max_out = 0, max_chunks = 1;
+    for (int i = 0; i < s->n_pes; ++i) {
+        max_out = std::max(max_out, s->h_pes[i * 13 + 1]);
+        max_chunks = std::max(max_chunks, s->h_pes[i * 13 + 10]);
+    }
+    dim3 grid((max_out + 7) / 8, s->n_groups, s->n_pes * max_chunks);
+    k_pes<<<grid, 128, 0, st>>>(s->ctx, s->d_pes, max_chunks, i_rel);
 }
 
 // One simulator step = this launch sequence; `i_rel` is the step's offset from the device-side step
@@ -264,13 +349,20 @@ void launch_wide(ssb_sim* s, int item0, int n_items, int max_n, int smem, int i_
 int one_step(ssb_sim* s, int i_rel) {
     const SsbCtx& c = s->ctx;
     const int G = s->n_groups;
+    const bool par = s->parallel && !s->profiling && !s->debug_sync;
+    cudaStream_t A = s->stream, B = par ? s->aux[0] : A, C = par ? s->aux[1] : A, D = par ? s->aux[2] : A;
     if (s->nt > 0) {
         LaunchTimer t(s, K_BEGIN);
         dim3 grid(((int)s->nt + 3) / 4, G);
-        k_begin<<<grid, 128, 0, s->stream>>>(c, i_rel);
+        k_begin<<<grid, 128, 0, A>>>(c, i_rel);
     }
+    bool pes_done = s->n_pes == 0;
     for (int lvl = 0; lvl < s->n_levels; ++lvl) {
         const int* st = &s->h_stages[lvl * 10];
+        const bool useB = st[3] > 0 || st[5] > 0, useC = st[7] > 0, useD = st[9] > 0;
+        if (useB) stream_dep(s, A, B);
+        if (useC) stream_dep(s, A, C);
+        if (useD) stream_dep(s, A, D);
         if (st[1] > 0) {
             LaunchTimer t(s, K_SMALL);
             // items are sorted by neuron count (descending): the leading ones get a whole CTA per trial group
@@ -278,20 +370,15 @@ int one_step(ssb_sim* s, int i_rel) {
             while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
             const int packed_warps = (st[1] - n_split) * G;
             const int blocks = n_split * G + (packed_warps + 3) / 4;
-            k_ens_small<<<blocks, 128, 0, s->stream>>>(c, s->d_small + st[0] * 9, st[1], n_split, i_rel);
+            k_ens_small<<<blocks, 128, 0, A>>>(c, s->d_small + st[0] * 9, st[1], n_split, i_rel);
         }
         if (st[3] > 0) {
             LaunchTimer t(s, K_WIDE);
-            int max_n[3] = {0, 0, 0}, max_sm[3] = {0, 0, 0};   // classes: dpad 56, dpad 100, generic
-            for (int i = 0; i < st[3]; ++i) {
-                const int* d = &s->h_big[(st[2] + i) * 16];
-                const int cls = d[2] == 56 ? 0 : (d[2] == 100 ? 1 : 2);
-                max_n[cls] = std::max(max_n[cls], d[0]);
-                max_sm[cls] = std::max(max_sm[cls], (d[2] + d[11]) * 32 * (int)sizeof(float));
-            }
-            if (max_n[0]) launch_wide<56>(s, st[2], st[3], max_n[0], max_sm[0], i_rel);
-            if (max_n[1]) launch_wide<100>(s, st[2], st[3], max_n[1], max_sm[1], i_rel);
-            if (max_n[2]) launch_wide<0>(s, st[2], st[3], max_n[2], max_sm[2], i_rel);
+            launch_wide(s, B, st, i_rel);
+        }
+        if (!pes_done && lvl == s->pes_level) {   // every PES pre-ensemble has produced its activities
+            launch_pes(s, B, i_rel);
+            pes_done = true;
         }
         for (int i = 0; i < st[7]; ++i) {
             const int ci = st[6] + i;
@@ -299,18 +386,18 @@ int one_step(ssb_sim* s, int i_rel) {
             const CleanupDev& cd = s->cleanups[ci];
             {
                 LaunchTimer t(s, K_SCAN);
-                dispatch_scan(s->stream, true, d[2], G, c, s->d_cleanup + ci * 6, s->d_W + d[3], cd, i_rel);
+                dispatch_scan(C, true, d[2], G, c, s->d_cleanup + ci * 6, s->d_W + d[3], cd, i_rel);
             }
             {
                 LaunchTimer t(s, K_PICK);
-                k_cleanup_pick<<<G, 256, 0, s->stream>>>(d[1], d[2], cd.n_chunks * SSB_TOPK, cd.cx, cd.pval, cd.pidx, cd.s64,
-                                                         s->d_W + d[3], s->vec, (int)s->nv, d[5], cd.idx, nullptr, 0, 0);
+                k_cleanup_pick<<<G, 256, 0, C>>>(d[1], d[2], cd.n_chunks * SSB_TOPK, cd.cx, cd.pval, cd.pidx, cd.s64,
+                                                 s->d_W + d[3], s->vec, (int)s->nv, d[5], cd.idx, nullptr, 0, 0);
             }
         }
         if (st[9] > 0) {
             LaunchTimer t(s, K_GATE);
             dim3 grid(G, st[9]);
-            k_gate<<<grid, 256, 0, s->stream>>>(c, s->d_gate, st[8], i_rel);
+            k_gate<<<grid, 256, 0, D>>>(c, s->d_gate, st[8], i_rel);
         }
         if (st[5] > 0) {
             LaunchTimer t(s, K_DEC);
@@ -320,23 +407,17 @@ int one_step(ssb_sim* s, int i_rel) {
                 max_chunks = std::max(max_chunks, s->h_dec[(st[4] + i) * 9 + 6]);
             }
             dim3 grid((max_out + 7) / 8, G, st[5] * max_chunks);
-            k_decode<<<grid, 128, 0, s->stream>>>(c, s->d_dec, st[4], max_chunks);
+            k_decode<<<grid, 128, 0, B>>>(c, s->d_dec, st[4], max_chunks);
         }
+        if (useB) stream_dep(s, B, A);
+        if (useC) stream_dep(s, C, A);
+        if (useD) stream_dep(s, D, A);
     }
-    if (s->n_pes > 0) {
-        LaunchTimer t(s, K_PES);
-        int max_out = 0, max_chunks = 1;
-        for (int i = 0; i < s->n_pes; ++i) {
-            max_out = std::max(max_out, s->h_pes[i * 13 + 1]);
-            max_chunks = std::max(max_chunks, s->h_pes[i * 13 + 10]);
-        }
-        dim3 grid((max_out + 7) / 8, G, s->n_pes * max_chunks);
-        k_pes<<<grid, 128, 0, s->stream>>>(c, s->d_pes, max_chunks, i_rel);
-    }
-    if (s->n_lin > 0 && !getenv("SSB_SKIP_LIN")) {
+    if (!pes_done) launch_pes(s, A, i_rel);
+    if (s->n_lin > 0) {
         LaunchTimer t(s, K_LIN);
         dim3 grid((s->n_lin + 3) / 4, G);
-        k_lin<<<grid, 128, 0, s->stream>>>(c, s->d_lin_rows, s->d_lin_ab, s->n_lin, i_rel);
+        k_lin<<<grid, 128, 0, A>>>(c, s->d_lin_rows, s->d_lin_ab, s->n_lin, i_rel);
     }
     return 0;
 }
@@ -355,6 +436,7 @@ int build_graph(ssb_sim* s, int n) {
     long long saved[K_NKINDS];
     memcpy(saved, s->kind_launches, sizeof(saved));
     const long long saved_total = s->total_launches;
+    s->dep_used = 0;
     SSB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < n; ++i) one_step(s, i);
     advance(s, n);
@@ -398,6 +480,8 @@ int ssb_create(int device, int n_trials, ssb_sim** out) {
     if (const char* e = getenv("SSB_DEBUG_SYNC")) s->debug_sync = e[0] == '1';
     if (s->debug_sync) s->use_graph = false;
     SSB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& a : s->aux) SSB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    if (const char* e = getenv("SSB_SERIAL")) s->parallel = e[0] != '1';
     SSB_CUDA(cudaEventCreate(&s->ev_run0));
     SSB_CUDA(cudaEventCreate(&s->ev_run1));
     *out = s;
@@ -435,6 +519,7 @@ int ssb_finalize(ssb_sim* s) {
     s->n_part = iscalar(s, "n_part");
     s->n_counters = iscalar(s, "n_jtiles") * s->n_groups;
     s->n_levels = (int)iscalar(s, "n_levels");
+    s->pes_level = s->scalars.count("pes_level") ? (int)s->scalars["pes_level"] : -1;
     s->chunk_cap = (int)iscalar(s, "chunk_cap");
     if (s->nv < 1 || s->chunk_cap < 1 || s->n_levels < 1) return fail(-1, "ssb_finalize: plan scalars missing");
     const double dt = s->scalars.count("dt") ? s->scalars["dt"] : 0.001;
@@ -510,7 +595,7 @@ int ssb_finalize(ssb_sim* s) {
         }
     }
     // opt-in to large dynamic shared memory for very wide ensembles (d = 649)
-    cudaFuncSetAttribute(k_ens_wide<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    wide_smem_optin();
     scan_smem_optin();
 
     SsbCtx& c = s->ctx;
@@ -629,6 +714,7 @@ int ssb_run_steps(ssb_sim* s, int n_steps) {
     }
     if (i < n_steps) {
         const int rest = n_steps - i;
+        s->dep_used = 0;
         for (int r = 0; r < rest; ++r) {
             if (one_step(s, r)) return -2;
         }
@@ -709,6 +795,9 @@ void ssb_destroy(ssb_sim* s) {
         if (cd.pidx) cudaFree(cd.pidx);
     }
     if (s->step_graph) cudaGraphExecDestroy(s->step_graph);
+    for (auto e : s->dep_pool) cudaEventDestroy(e);
+    for (auto a : s->aux)
+        if (a) cudaStreamDestroy(a);
     for (auto e : s->ev_pool) cudaEventDestroy(e);
     for (auto e : s->ev_mark)
         if (e) cudaEventDestroy(e);

@@ -379,33 +379,75 @@ __global__ void __launch_bounds__(128) k_ens_small(SsbCtx c, const int* __restri
 
 // --------------------------------------------------------------------------------------
 // Wide ensembles (OVC / memory / recall / error: 970 x 55).  A CTA owns (ensemble, trial group,
-// neuron chunk); the input vector is staged once in shared memory and (for the templated widths)
-// copied to registers.  Output activities go to act[n] for the decode / PES kernels.  Voja-learned
-// encoders are per-trial rows (lenc; the 55 rows of one neuron are 7 KB contiguous), all loads of a
-// neuron are issued before use, and only lanes that spiked write their row back
-// (post_synapse=None => the delta is row-sparse).
+// chunk of neurons).  Everything the chunk needs is contiguous in memory and is staged in shared
+// memory by TMA bulk copies issued by one thread while all warps evaluate the input vector:
+// static encoders [chunk][dpad], bias, direct-current weights, the chunk's 128-byte state rows.
+// The input vector is copied to registers (templated widths), each warp walks its quarter of the
+// chunk with broadcast float4 encoder reads, and the updated state goes back with a bulk store.
+// Output activities go to act[n] for the decode / PES kernels.
 // desc: n dims dpad state0 act0 enc_off bias_off in_row0 ntype flags jn_row0 jn_m jn_w voja_row scale_off alpha_bits
+struct SsbItemList {
+    int n;
+    int idx[15];
+};
+
+__device__ __forceinline__ int ssb_r4(int x) { return (x + 3) & ~3; }
+
 template <int DP>
-__device__ __forceinline__ void ssb_wide_neuron(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt, int i,
-                                                int g, const float* xs, const float* us,
-                                                const float (&x)[DP > 0 ? DP : 1], float aL) {
-    const int dims = d[1], dpad = d[2], state0 = d[3], act0 = d[4], enc_off = d[5], bias_off = d[6], flags = d[9];
-    const int jn_m = d[11], jn_w = d[12], scale_off = d[14];
-    const int lane = threadIdx.x & 31;
-    const bool voja = flags & 1, stateful = nt.type == 0;
-    float* sp = ssb_grp(c.st, c.nn, g, lane) + (size_t)(state0 + i) * 32;
-    float s = 0.f;
-    if (stateful) s = __ldcs(sp);
-    float J = __ldg(c.W + bias_off + i);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    float* erow = nullptr;
-    float ev[DP > 0 ? DP : 1];
-    if (!voja) {
-        const float4* __restrict__ e4 = reinterpret_cast<const float4*>(c.W + enc_off + (size_t)i * dpad);
+__global__ void __launch_bounds__(128) k_wide_static(SsbCtx c, const int* __restrict__ desc, SsbItemList items, int chunk,
+                                                      int i_rel) {
+    extern __shared__ __align__(128) float sm[];
+    __shared__ unsigned long long bar;
+    const int* d = desc + items.idx[blockIdx.z] * 16;
+    const int n = d[0], dims = d[1], dpad = d[2], state0 = d[3], act0 = d[4], enc_off = d[5], bias_off = d[6];
+    const int in_row0 = d[7], jn_row0 = d[10], jn_m = d[11], jn_w = d[12];
+    const int n0 = blockIdx.x * chunk;
+    if (n0 >= n) return;
+    const int cnt = min(chunk, n - n0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.y;
+    const SsbNeuron nt = ssb_neuron(c, d[8]);
+    const bool stateful = nt.type == 0;
+    float* s_enc = sm;                                  // [chunk][dpad]
+    float* s_bias = s_enc + (size_t)chunk * dpad;       // [chunk]
+    float* s_jn = s_bias + chunk;                       // [chunk][jn_m]
+    float* s_st = s_jn + (size_t)chunk * jn_m;          // [chunk][32]
+    float* xs = s_st + (size_t)chunk * 32;              // [dpad][32]
+    float* us = xs + (size_t)dpad * 32;                 // [jn_m][32]
+    float* stg = c.st + ((size_t)g * c.nn + state0 + n0) * 32;
+    if (threadIdx.x == 0) {
+        ssb_mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t b_enc = (uint32_t)cnt * dpad * 4, b_bias = (uint32_t)ssb_r4(cnt) * 4;
+        const uint32_t b_jn = jn_m ? (uint32_t)ssb_r4(cnt * jn_m) * 4 : 0u, b_st = stateful ? (uint32_t)cnt * 128 : 0u;
+        ssb_mbar_expect_tx(&bar, b_enc + b_bias + b_jn + b_st);
+        ssb_bulk_g2s(s_enc, c.W + enc_off + (size_t)n0 * dpad, b_enc, &bar);
+        ssb_bulk_g2s(s_bias, c.W + bias_off + n0, b_bias, &bar);
+        if (jn_m) ssb_bulk_g2s(s_jn, c.W + jn_w + (size_t)n0 * jn_m, b_jn, &bar);
+        if (stateful) ssb_bulk_g2s(s_st, stg, b_st, &bar);
+    }
+    const SsbStep s = ssb_step(c, i_rel);
+    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    for (int k = warp; k < dpad; k += 4)
+        xs[k * 32 + lane] = (k < dims) ? ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg) : 0.f;
+    for (int m = warp; m < jn_m; m += 4) us[m * 32 + lane] = ssb_row(c.csr_ptr, s.ent_old, jn_row0 + m, vg);
+    __syncthreads();                 // xs / us complete, barrier initialised for every thread
+    ssb_mbar_wait(&bar, 0);
+    float x[DP > 0 ? DP : 1];
+    if (DP > 0) {
+#pragma unroll
+        for (int k = 0; k < DP; ++k) x[k] = xs[k * 32 + lane];
+    }
+    const int per = chunk >> 2;
+    const int i_lo = warp * per, i_hi = min(cnt, i_lo + per);
+    float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)(act0 + n0) * 32;
+    for (int i = i_lo; i < i_hi; ++i) {
+        const float4* e4 = reinterpret_cast<const float4*>(s_enc + (size_t)i * dpad);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (DP > 0) {
 #pragma unroll
             for (int k4 = 0; k4 < DP / 4; ++k4) {
-                const float4 e = __ldg(e4 + k4);
+                const float4 e = e4[k4];
                 a0 = fmaf(e.x, x[4 * k4 + 0], a0);
                 a1 = fmaf(e.y, x[4 * k4 + 1], a1);
                 a2 = fmaf(e.z, x[4 * k4 + 2], a2);
@@ -413,7 +455,7 @@ __device__ __forceinline__ void ssb_wide_neuron(const SsbCtx& c, const int* __re
             }
         } else {
             for (int k4 = 0; k4 < (dpad >> 2); ++k4) {
-                const float4 e = __ldg(e4 + k4);
+                const float4 e = e4[k4];
                 const float* xk = xs + (k4 * 4) * 32 + lane;
                 a0 = fmaf(e.x, xk[0], a0);
                 a1 = fmaf(e.y, xk[32], a1);
@@ -421,87 +463,155 @@ __device__ __forceinline__ void ssb_wide_neuron(const SsbCtx& c, const int* __re
                 a3 = fmaf(e.w, xk[96], a3);
             }
         }
-    } else {
-        erow = ssb_grp(c.lenc, c.n_lenc, g, lane) + ((size_t)enc_off + (size_t)i * dims) * 32;
-        if (DP > 0) {
-#pragma unroll
-            for (int k = 0; k < DP; ++k) ev[k] = (k < dims) ? erow[(size_t)k * 32] : 0.f;
-#pragma unroll
-            for (int k = 0; k < DP; k += 4) {
-                a0 = fmaf(ev[k + 0], x[k + 0], a0);
-                a1 = fmaf(ev[k + 1], x[k + 1], a1);
-                a2 = fmaf(ev[k + 2], x[k + 2], a2);
-                a3 = fmaf(ev[k + 3], x[k + 3], a3);
-            }
+        float J = s_bias[i] + ((a0 + a1) + (a2 + a3));
+        for (int m = 0; m < jn_m; ++m) J = fmaf(s_jn[i * jn_m + m], us[m * 32 + lane], J);
+        float out;
+        if (stateful) {
+            float sv = s_st[i * 32 + lane];
+            out = ssb_lif_packed(nt, J, sv);
+            s_st[i * 32 + lane] = sv;
         } else {
-            int k = 0;
-            for (; k + 4 <= dims; k += 4) {
-                const float e0 = erow[(size_t)k * 32], e1 = erow[(size_t)(k + 1) * 32];
-                const float e2 = erow[(size_t)(k + 2) * 32], e3 = erow[(size_t)(k + 3) * 32];
-                a0 = fmaf(e0, xs[k * 32 + lane], a0);
-                a1 = fmaf(e1, xs[(k + 1) * 32 + lane], a1);
-                a2 = fmaf(e2, xs[(k + 2) * 32 + lane], a2);
-                a3 = fmaf(e3, xs[(k + 3) * 32 + lane], a3);
-            }
-            for (; k < dims; ++k) a0 = fmaf(erow[(size_t)k * 32], xs[k * 32 + lane], a0);
+            out = ssb_rate(nt, J);
         }
+        ag[(size_t)i * 32] = out;
     }
-    J += (a0 + a1) + (a2 + a3);
-    for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + i * jn_m + m), us[m * 32 + lane], J);
-    float out;
-    if (stateful) {
-        out = ssb_lif_packed(nt, J, s);
-        __stcs(sp, s);
-    } else {
-        out = ssb_rate(nt, J);
-    }
-    ssb_grp(c.act, c.n_act, g, lane)[(size_t)(act0 + i) * 32] = out;
-    if (voja && out != 0.f) {
-        // SimVoja: delta = alpha*L*(scale*outer(post, x) - post[:,None]*E), applied to E for the next step
-        const float sc = __ldg(c.W + scale_off + i);
-        if (DP > 0) {
-#pragma unroll
-            for (int k = 0; k < DP; ++k)
-                if (k < dims) erow[(size_t)k * 32] = ev[k] + aL * (sc * (out * x[k]) - out * ev[k]);
-        } else {
-            for (int k = 0; k < dims; ++k) {
-                const float e = erow[(size_t)k * 32];
-                erow[(size_t)k * 32] = e + aL * (sc * (out * xs[k * 32 + lane]) - out * e);
-            }
+    if (stateful && i_hi > i_lo) {
+        ssb_fence_async();
+        __syncwarp();
+        if (lane == 0) {
+            ssb_bulk_s2g(stg + (size_t)i_lo * 32, s_st + (size_t)i_lo * 32, (uint32_t)(i_hi - i_lo) * 128);
+            ssb_bulk_commit();
+            ssb_bulk_wait0();
         }
     }
 }
 
+// Voja-learned ensemble (associative-memory keys): the scaled encoders are per trial, the `dims` rows
+// of one neuron are `dims` consecutive 128-byte lines.  Each warp streams its neurons' encoder tiles
+// through a double-buffered shared-memory stage with TMA bulk copies; lanes that spiked update their
+// column in place and the tile is written back only if some lane spiked (post_synapse=None => the
+// delta is row-sparse).  SimVoja: delta = alpha*L*(scale*outer(post, x) - post[:,None]*E), visible
+// to the next step.
 template <int DP>
-__global__ void __launch_bounds__(128) k_ens_wide(SsbCtx c, const int* __restrict__ desc, int item0, int chunk, int i_rel) {
-    extern __shared__ float sm[];
-    const int* d = desc + (item0 + blockIdx.z) * 16;
-    const int n = d[0], dims = d[1], dpad = d[2];
-    const int in_row0 = d[7], flags = d[9], jn_row0 = d[10], jn_m = d[11], voja_row = d[13];
+__global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restrict__ desc, SsbItemList items, int chunk,
+                                                    int i_rel) {
+    extern __shared__ __align__(128) float sm[];
+    __shared__ unsigned long long wbar[4][2];
+    const int* d = desc + items.idx[blockIdx.z] * 16;
+    const int n = d[0], dims = d[1], dpad = d[2], state0 = d[3], act0 = d[4], enc_off = d[5], bias_off = d[6];
+    const int in_row0 = d[7], jn_row0 = d[10], jn_m = d[11], jn_w = d[12], voja_row = d[13], scale_off = d[14];
     const int n0 = blockIdx.x * chunk;
     if (n0 >= n) return;
-    if (DP > 0 && dpad != DP) return;  // this instantiation only serves ensembles of its width
-    if (DP == 0 && (dpad == 56 || dpad == 100)) return;
-    const int n1 = min(n, n0 + chunk);
+    const int cnt = min(chunk, n - n0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = blockIdx.y;
-    const SsbStep s = ssb_step(c, i_rel);
     const SsbNeuron nt = ssb_neuron(c, d[8]);
+    const bool stateful = nt.type == 0;
+    float* xs = sm;                                        // [dpad][32]
+    float* us = xs + (size_t)dpad * 32;                    // [jn_m][32]
+    float* ebuf = us + (size_t)jn_m * 32 + (size_t)warp * 2 * dims * 32;   // [2][dims][32] per warp
+    const int per = (chunk + nwarps - 1) / nwarps;
+    const int i_lo = warp * per, i_hi = min(cnt, i_lo + per);
+    float* eg = c.lenc + ((size_t)g * c.n_lenc + enc_off + (size_t)(n0 + i_lo) * dims) * 32;   // tile of neuron i_lo
+    const uint32_t tile_bytes = (uint32_t)dims * 128;
+    if (lane == 0) {
+        ssb_mbar_init(&wbar[warp][0], 1);
+        ssb_mbar_init(&wbar[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int t = 0; t < 2 && i_lo + t < i_hi; ++t) {
+            ssb_mbar_expect_tx(&wbar[warp][t], tile_bytes);
+            ssb_bulk_g2s(ebuf + (size_t)t * dims * 32, eg + (size_t)t * dims * 32, tile_bytes, &wbar[warp][t]);
+        }
+    }
+    const SsbStep s = ssb_step(c, i_rel);
     const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    float* xs = sm;                 // [dpad][32]
-    float* us = sm + dpad * 32;     // [jn_m][32]
     for (int k = warp; k < dpad; k += nwarps)
         xs[k * 32 + lane] = (k < dims) ? ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg) : 0.f;
     for (int m = warp; m < jn_m; m += nwarps) us[m * 32 + lane] = ssb_row(c.csr_ptr, s.ent_old, jn_row0 + m, vg);
-    float aL = 0.f;
-    if (flags & 1) aL = __int_as_float(d[15]) * ssb_row(c.csr_ptr, s.ent_old, voja_row, vg);
+    const float aL = __int_as_float(d[15]) * ssb_row(c.csr_ptr, s.ent_old, voja_row, vg);
     __syncthreads();
     float x[DP > 0 ? DP : 1];
     if (DP > 0) {
 #pragma unroll
         for (int k = 0; k < DP; ++k) x[k] = xs[k * 32 + lane];
     }
-    for (int i = n0 + warp; i < n1; i += nwarps) ssb_wide_neuron<DP>(c, d, nt, i, g, xs, us, x, aL);
+    float* sp = ssb_grp(c.st, c.nn, g, lane) + (size_t)(state0 + n0) * 32;
+    float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)(act0 + n0) * 32;
+    uint32_t phases = 0;
+    for (int i = i_lo; i < i_hi; ++i) {
+        const int t = i - i_lo, b = t & 1;
+        float* E = ebuf + (size_t)b * dims * 32 + lane;
+        float sv = 0.f;
+        if (stateful) sv = __ldcs(sp + (size_t)i * 32);
+        float J = __ldg(c.W + bias_off + n0 + i);
+        for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + (n0 + i) * jn_m + m), us[m * 32 + lane], J);
+        ssb_mbar_wait(&wbar[warp][b], (phases >> b) & 1u);
+        phases ^= 1u << b;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (DP > 0) {
+#pragma unroll
+            for (int k = 0; k < DP; k += 4) {
+                a0 = fmaf(k + 0 < dims ? E[(k + 0) * 32] : 0.f, x[k + 0], a0);
+                a1 = fmaf(k + 1 < dims ? E[(k + 1) * 32] : 0.f, x[k + 1], a1);
+                a2 = fmaf(k + 2 < dims ? E[(k + 2) * 32] : 0.f, x[k + 2], a2);
+                a3 = fmaf(k + 3 < dims ? E[(k + 3) * 32] : 0.f, x[k + 3], a3);
+            }
+        } else {
+            int k = 0;
+            for (; k + 4 <= dims; k += 4) {
+                a0 = fmaf(E[k * 32], xs[k * 32 + lane], a0);
+                a1 = fmaf(E[(k + 1) * 32], xs[(k + 1) * 32 + lane], a1);
+                a2 = fmaf(E[(k + 2) * 32], xs[(k + 2) * 32 + lane], a2);
+                a3 = fmaf(E[(k + 3) * 32], xs[(k + 3) * 32 + lane], a3);
+            }
+            for (; k < dims; ++k) a0 = fmaf(E[k * 32], xs[k * 32 + lane], a0);
+        }
+        J += (a0 + a1) + (a2 + a3);
+        float out;
+        if (stateful) {
+            out = ssb_lif_packed(nt, J, sv);
+            __stcs(sp + (size_t)i * 32, sv);
+        } else {
+            out = ssb_rate(nt, J);
+        }
+        ag[(size_t)i * 32] = out;
+        const bool fired = out != 0.f;
+        if (fired) {
+            const float sc = __ldg(c.W + scale_off + n0 + i);
+            if (DP > 0) {
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    if (k < dims) {
+                        const float e = E[k * 32];
+                        E[k * 32] = e + aL * (sc * (out * x[k]) - out * e);
+                    }
+                }
+            } else {
+                for (int k = 0; k < dims; ++k) {
+                    const float e = E[k * 32];
+                    E[k * 32] = e + aL * (sc * (out * xs[k * 32 + lane]) - out * e);
+                }
+            }
+        }
+        const bool dirty = __any_sync(0xffffffffu, fired);
+        if (dirty) {
+            ssb_fence_async();
+            __syncwarp();
+            if (lane == 0) {
+                ssb_bulk_s2g(eg + (size_t)t * dims * 32, ebuf + (size_t)b * dims * 32, tile_bytes);
+                ssb_bulk_commit();
+            }
+        }
+        if (i + 2 < i_hi) {
+            if (dirty && lane == 0) ssb_bulk_wait_read0();
+            __syncwarp();
+            if (lane == 0) {
+                ssb_mbar_expect_tx(&wbar[warp][b], tile_bytes);
+                ssb_bulk_g2s(ebuf + (size_t)b * dims * 32, eg + (size_t)(t + 2) * dims * 32, tile_bytes, &wbar[warp][b]);
+            }
+        }
+    }
+    if (lane == 0) ssb_bulk_wait0();
 }
 
 // --------------------------------------------------------------------------------------
@@ -852,12 +962,21 @@ k_cleanup_pick(int dims, int dpad, int ncand, const float* __restrict__ cx, cons
     const float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
     float best = -INFINITY;
     int best_g = 0x7fffffff;
-    for (int i = warp; i < ncand; i += 8) {
-        const float v = pv[(size_t)i * 32];
-        const int gi = pi[(size_t)i * 32];
-        if (v > best || (v == best && gi < best_g)) {
-            best = v;
-            best_g = gi;
+    for (int i0 = warp; i0 < ncand; i0 += 64) {   // 8 independent candidate loads in flight per thread
+        float v[8];
+        int gi[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 8 * u;
+            v[u] = (i < ncand) ? pv[(size_t)i * 32] : -INFINITY;
+            gi[u] = (i < ncand) ? pi[(size_t)i * 32] : 0x7fffffff;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (v[u] > best || (v[u] == best && gi[u] < best_g)) {
+                best = v[u];
+                best_g = gi[u];
+            }
         }
     }
     float xn = 0.f;
@@ -884,20 +1003,29 @@ k_cleanup_pick(int dims, int dpad, int ncand, const float* __restrict__ cx, cons
     // fp32 dot-product error bound: ~dims * 2^-24 * |S_g||x| with |S_g| = 1
     const float eps = 4.0f * (float)dims * 5.97e-8f * sqrtf(xn) + 1e-30f;
     int n_close = 0;
-    for (int i = warp; i < ncand; i += 8)
-        if (pv[(size_t)i * 32] >= best - eps) ++n_close;
+    for (int i0 = warp; i0 < ncand; i0 += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i0 + 8 * u < ncand) ? pv[(size_t)(i0 + 8 * u) * 32] : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) n_close += v[u] >= best - eps;
+    }
     sc[warp][lane] = n_close;
     __syncthreads();
     n_close = 0;
     for (int w = 0; w < 8; ++w) n_close += sc[w][lane];
-    if (n_close > 1 && S64 != nullptr) {
-        // rare path (a near-tie): every warp redundantly re-scores the same candidates for its lane's trial
-        double dbest = -1e300;
-        int dg = 0x7fffffff;
-        for (int i = 0; i < ncand; ++i) {
-            if (pv[(size_t)i * 32] >= best - eps) {
-                const int gi = pi[(size_t)i * 32];
-                if (gi == 0x7fffffff) continue;
+    // Near-ties (rare): lanes with more than one candidate inside the fp32 error band re-score those
+    // candidates in fp64.  Every warp re-walks only its own slice of the candidate list, so a tie costs one
+    // more pass instead of a serial scan; the per-warp winners are merged in (value desc, index asc) order.
+    __shared__ double sd[8][32];
+    const bool multi = n_close > 1 && S64 != nullptr;
+    double dbest = -1e300;
+    int dg = 0x7fffffff;
+    if (__any_sync(0xffffffffu, multi)) {
+        for (int i = warp; i < ncand; i += 8) {
+            const float v = pv[(size_t)i * 32];
+            const int gi = pi[(size_t)i * 32];
+            if (multi && v >= best - eps && gi != 0x7fffffff) {
                 const double* sgp = S64 + (size_t)gi * dims;
                 double acc = 0.0;
                 // argmax is invariant to the positive normalisation, so the raw float64 query can be used
@@ -911,6 +1039,22 @@ k_cleanup_pick(int dims, int dpad, int ncand, const float* __restrict__ cx, cons
                     dbest = acc;
                     dg = gi;
                 }
+            }
+        }
+    }
+    __syncthreads();          // sg is re-used for the merge
+    sd[warp][lane] = dbest;
+    sg[warp][lane] = dg;
+    __syncthreads();
+    if (multi) {
+        dbest = sd[0][lane];
+        dg = sg[0][lane];
+        for (int w = 1; w < 8; ++w) {
+            const double v = sd[w][lane];
+            const int gi = sg[w][lane];
+            if (v > dbest || (v == dbest && gi < dg)) {
+                dbest = v;
+                dg = gi;
             }
         }
         best_g = dg;

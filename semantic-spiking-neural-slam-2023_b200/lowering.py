@@ -443,6 +443,7 @@ class _Lowerer:
         nn = n_act = n_lenc = n_ldec = n_afilt = 0
         n_small = n_big = 0
         n_part = n_jtiles = 0
+        pes_level = -1
 
         def splitk(c, size_out):
             """(n_chunks, part_off, counter0) of a decode / PES item."""
@@ -534,6 +535,7 @@ class _Lowerer:
                     else:
                         decay = float(np.exp(-dt / lrt.pre_synapse.tau))
                     pes_trace.append((act0, a_off, n, np.float32(decay), np.float32(1.0 - decay)))
+                    pes_level = max(pes_level, lvl)
                     pes_desc.append([n, size_out, d_off, a_off, act0, err_row0, out_vec,
                                      int(np.float32(alpha).view(np.int32)),
                                      int(np.float32(decay).view(np.int32)),
@@ -628,7 +630,8 @@ class _Lowerer:
             "csr_ptr": np.asarray(csr_ptr, dtype=np.int32),
             "csr_ent0": self._entries(csr_idx, csr_val, 0, NF),
             "csr_ent1": self._entries(csr_idx, csr_val, NF, NF),
-            "weights": np.concatenate(W) if W else np.zeros(4, dtype=np.float32),
+            # 8 floats of slack: bulk copies of bias / current weights round their length up to 16 bytes
+            "weights": np.concatenate(W + [np.zeros(8, dtype=np.float32)]),
             "ens_small": arr(cat["small"], 9),
             "ens_big": arr(cat["big"], 16),
             "dec": arr(cat["dec"], 9),
@@ -645,7 +648,7 @@ class _Lowerer:
                               if self.node_op[n].kind == "cleanup" and fn_level[n] == lvl]
         plan.scalars.update(dict(dt=dt, nv=NV, nf=NF, nt=NT, tab_row0=tab_row0, nn=nn, n_act=n_act, n_lenc=n_lenc,
                                  n_ldec=n_ldec, n_afilt=n_afilt, n_probe=n_probe_rows, n_levels=n_levels,
-                                 chunk_cap=chunk_cap, n_part=n_part, n_jtiles=n_jtiles))
+                                 chunk_cap=chunk_cap, n_part=n_part, n_jtiles=n_jtiles, pes_level=pes_level))
         n_static = int(sum(a.size for a in W))
         plan.stats = dict(n_neurons=nn, n_filter_states=NF, n_learned=n_lenc + n_ldec, n_static_weights=n_static,
                           n_table_words=NT, n_probe_words=n_probe_rows, n_small=n_small, n_big=n_big,
