@@ -88,7 +88,7 @@ struct ssb_sim {
     int pes_level = -1;
     long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
     std::vector<size_t> s64_offsets;
-    int n_levels = 0, n_lin = 0, n_pes = 0, n_small_total = 0;
+    int n_levels = 0, n_lin = 0, lin0 = 0, n_pes = 0, n_small_total = 0;
     // sizes
     long long nv = 0, nf = 0, nt = 0, nn = 0, n_act = 0, n_lenc = 0, n_ldec = 0, n_afilt = 0, n_probe = 0;
     long long tab_row0 = 0, n_part = 0, n_counters = 0;
@@ -358,7 +358,12 @@ int one_step(ssb_sim* s, int i_rel) {
     }
     bool pes_done = s->n_pes == 0;
     for (int lvl = 0; lvl < s->n_levels; ++lvl) {
-        const int* st = &s->h_stages[lvl * 10];
+        const int* st = &s->h_stages[lvl * 12];
+        if (st[11] > 0) {   // materialise this level's sink rows (ensemble / node inputs, PES errors)
+            LaunchTimer t(s, K_LIN);
+            dim3 grid((st[11] + 3) / 4, G);
+            k_lin<<<grid, 128, 0, A>>>(c, s->d_lin_rows + st[10] * 3, s->d_lin_ab + st[10] * 2, st[11], i_rel);
+        }
         const bool useB = st[3] > 0 || st[5] > 0, useC = st[7] > 0, useD = st[9] > 0;
         if (useB) stream_dep(s, A, B);
         if (useC) stream_dep(s, A, C);
@@ -370,7 +375,7 @@ int one_step(ssb_sim* s, int i_rel) {
             while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
             const int packed_warps = (st[1] - n_split) * G;
             const int blocks = n_split * G + (packed_warps + 3) / 4;
-            k_ens_small<<<blocks, 128, 0, A>>>(c, s->d_small + st[0] * 9, st[1], n_split, i_rel);
+            k_ens_small<<<blocks, 128, 0, A>>>(c, s->d_small + st[0] * 9, st[1], n_split);
         }
         if (st[3] > 0) {
             LaunchTimer t(s, K_WIDE);
@@ -401,13 +406,10 @@ int one_step(ssb_sim* s, int i_rel) {
         }
         if (st[5] > 0) {
             LaunchTimer t(s, K_DEC);
-            int max_out = 0, max_chunks = 1;
-            for (int i = 0; i < st[5]; ++i) {
-                max_out = std::max(max_out, s->h_dec[(st[4] + i) * 9 + 1]);
-                max_chunks = std::max(max_chunks, s->h_dec[(st[4] + i) * 9 + 6]);
-            }
-            dim3 grid((max_out + 7) / 8, G, st[5] * max_chunks);
-            k_decode<<<grid, 128, 0, B>>>(c, s->d_dec, st[4], max_chunks);
+            int max_chunks = 1;
+            for (int i = 0; i < st[5]; ++i) max_chunks = std::max(max_chunks, s->h_dec[(st[4] + i) * 9 + 6]);
+            dim3 grid(max_chunks, G, st[5]);
+            k_decode<<<grid, 128, 0, B>>>(c, s->d_dec, st[4]);
         }
         if (useB) stream_dep(s, B, A);
         if (useC) stream_dep(s, C, A);
@@ -417,7 +419,7 @@ int one_step(ssb_sim* s, int i_rel) {
     if (s->n_lin > 0) {
         LaunchTimer t(s, K_LIN);
         dim3 grid((s->n_lin + 3) / 4, G);
-        k_lin<<<grid, 128, 0, A>>>(c, s->d_lin_rows, s->d_lin_ab, s->n_lin, i_rel);
+        k_lin<<<grid, 128, 0, A>>>(c, s->d_lin_rows + s->lin0 * 3, s->d_lin_ab + s->lin0 * 2, s->n_lin, i_rel);
     }
     return 0;
 }
@@ -538,7 +540,9 @@ int ssb_finalize(ssb_sim* s) {
     if (upload_array(s, "cleanup", &s->d_cleanup)) return -2;
     if (upload_array(s, "gate", &s->d_gate)) return -2;
     if (upload_array(s, "lin_rows", &s->d_lin_rows, &cnt)) return -2;
-    s->n_lin = (int)(cnt / 3);
+    s->lin0 = (int)iscalar(s, "lin0");
+    s->n_lin = (int)iscalar(s, "n_lin");
+    if ((size_t)(s->lin0 + s->n_lin) * 3 != cnt) return fail(-1, "ssb_finalize: lin_rows segments do not add up");
     if (upload_array(s, "lin_ab", &s->d_lin_ab)) return -2;
     if (upload_array(s, "ntypes", &s->d_ntypes)) return -2;
     if (upload_array(s, "cleanup_s64", &s->d_s64)) return -2;
@@ -548,7 +552,7 @@ int ssb_finalize(ssb_sim* s) {
     s->h_dec = host_ints(s, "dec");
     s->h_cleanup = host_ints(s, "cleanup");
     s->h_pes = host_ints(s, "pes");
-    if ((int)s->h_stages.size() != s->n_levels * 10) return fail(-1, "ssb_finalize: stages array has wrong size");
+    if ((int)s->h_stages.size() != s->n_levels * 12) return fail(-1, "ssb_finalize: stages array has wrong size");
     for (size_t i = 0; i + 8 < s->h_small.size(); i += 9)
         if (s->h_small[i + 8] > SSB_SM_WMAX || (s->h_small[i + 8] & 3))
             return fail(-1, "ssb_finalize: narrow-ensemble weight stride out of range");

@@ -94,9 +94,9 @@ __device__ __forceinline__ float ssb_row(const int* __restrict__ ptr, const int2
 // --------------------------------------------------------------------------------------
 // Neuron models.
 struct SsbNeuron {
-    int type;
-    bool fast;
-    float tau_rc, tau_ref, amp_dt, amp, dt, inv_tau;
+    int type;                 // 0 LIF, 1 LIFRate, 2 RectifiedLinear
+    bool fast;                // LIF with dt/tau_rc <= 1/16: polynomial expm1 / log1p, exact to fp32
+    float tau_rc, tau_ref, amp_dt, amp, dt, neg_inv_tau, c0;
 };
 
 __device__ __forceinline__ SsbNeuron ssb_neuron(const SsbCtx& c, int tid) {
@@ -109,14 +109,14 @@ __device__ __forceinline__ SsbNeuron ssb_neuron(const SsbCtx& c, int tid) {
     n.fast = p[5] != 0.f;
     n.dt = c.dt;
     n.amp_dt = p[4] / c.dt;
-    n.inv_tau = (n.type == 0) ? 1.0f / p[1] : 0.f;
+    n.neg_inv_tau = (n.type == 0) ? -1.0f / p[1] : 0.f;
+    n.c0 = p[2] + c.dt;       // tau_ref + dt
     return n;
 }
 
-// expm1(x) for -0.125 <= x <= 0 (x = -delta/tau_rc with delta <= dt): degree-6 Taylor, rel. error < 1e-9.
+// expm1(x) for -1/16 <= x <= 0 (x = -delta/tau_rc with delta <= dt): degree-5 Taylor, rel. error < 2e-9.
 __device__ __forceinline__ float ssb_expm1_small(float x) {
-    float p = 1.f / 720.f;
-    p = fmaf(p, x, 1.f / 120.f);
+    float p = 1.f / 120.f;
     p = fmaf(p, x, 1.f / 24.f);
     p = fmaf(p, x, 1.f / 6.f);
     p = fmaf(p, x, 0.5f);
@@ -124,33 +124,32 @@ __device__ __forceinline__ float ssb_expm1_small(float x) {
     return p * x;
 }
 
-// log1p(-z) for 0 <= z <= 0.125 (z = overshoot / (J - 1) <= 1 - exp(-dt/tau_rc)): 8 terms, rel. error < 1e-8.
+// log1p(-z) for 0 <= z <= 1/16 (z = overshoot / (J - 1) <= 1 - exp(-dt/tau_rc)): 6 terms, rel. error < 1e-8.
 __device__ __forceinline__ float ssb_log1p_neg_small(float z) {
-    float p = 1.f / 8.f;
-    p = fmaf(p, z, 1.f / 7.f);
-    p = fmaf(p, z, 1.f / 6.f);
-    p = fmaf(p, z, 0.2f);
-    p = fmaf(p, z, 0.25f);
-    p = fmaf(p, z, 1.f / 3.f);
-    p = fmaf(p, z, 0.5f);
-    p = fmaf(p, z, 1.f);
-    return -(p * z);
+    float p = -1.f / 6.f;
+    p = fmaf(p, z, -0.2f);
+    p = fmaf(p, z, -0.25f);
+    p = fmaf(p, z, -1.f / 3.f);
+    p = fmaf(p, z, -0.5f);
+    p = fmaf(p, z, -1.f);
+    return p * z;
 }
 
 // nengo LIF.step on the packed state (App. A.4), branch-free.  Returns the output (0 or amplitude/dt).
+//   r = max(-s, 0) is the refractory time, v = max(s, 0) the voltage (one of them is always 0).
+template <bool FAST>
 __device__ __forceinline__ float ssb_lif_packed(const SsbNeuron& n, float J, float& s) {
-    const bool refr = s < 0.f;
-    const float rp = refr ? (-s - n.dt) : -n.dt;          // refractory_time after "-= dt"
-    float v = refr ? 0.f : s;
+    const float rp = fmaxf(-s, 0.f) - n.dt;                // refractory_time after "-= dt"
+    float v = fmaxf(s, 0.f);
     const float delta = fminf(fmaxf(n.dt - rp, 0.f), n.dt);
-    const float em1 = n.fast ? ssb_expm1_small(-delta * n.inv_tau) : expm1f(-delta / n.tau_rc);
-    v = fmaf(-(J - v), em1, v);                            // v -= (J - v) * expm1(-delta / tau_rc)
+    const float em1 = FAST ? ssb_expm1_small(delta * n.neg_inv_tau) : expm1f(delta * n.neg_inv_tau);
+    v = fmaf(v - J, em1, v);                               // v -= (J - v) * expm1(-delta / tau_rc)
     const bool spiked = v > 1.f;
     const float z = __fdividef(v - 1.f, J - 1.f);          // used only when spiked (then J > v > 1)
-    const float lp = n.fast ? ssb_log1p_neg_small(z) : log1pf(-z);
-    const float r_new = n.tau_ref + (n.dt + n.tau_rc * lp);
+    const float lp = FAST ? ssb_log1p_neg_small(z) : log1pf(-z);
+    const float r_new = fmaf(n.tau_rc, lp, n.c0);          // tau_ref + dt + tau_rc * log1p(-z) > 0
     const float keep = (rp >= n.dt) ? -rp : fmaxf(v, 0.f);
-    s = spiked ? ((r_new >= n.dt) ? -r_new : 0.f) : keep;
+    s = spiked ? -r_new : keep;
     return spiked ? n.amp_dt : 0.f;
 }
 
@@ -160,6 +159,14 @@ __device__ __forceinline__ float ssb_rate(const SsbNeuron& n, float J) {
         return j > 0.f ? n.amp / (n.tau_ref + n.tau_rc * log1pf(1.f / j)) : 0.f;
     }
     return n.amp * fmaxf(J, 0.f);
+}
+
+// MODE 0: LIF with polynomial transcendental functions; MODE 1: anything else (uniform run-time switch).
+template <int MODE>
+__device__ __forceinline__ float ssb_neuron_apply(const SsbNeuron& n, float J, float& s) {
+    if (MODE == 0) return ssb_lif_packed<true>(n, J, s);
+    if (n.type == 0) return ssb_lif_packed<false>(n, J, s);
+    return ssb_rate(n, J);
 }
 
 // --------------------------------------------------------------------------------------
@@ -226,20 +233,21 @@ struct __align__(128) SsbSmallSmem {
     float st[4][2][SSB_SM_CH * 32];
     float w[4][2][SSB_SM_CH * SSB_SM_WMAX];
     float red[4][8][32];
-    float xs[4][32];
     unsigned long long bar[4][2];
 };
 
-template <int DIMS, int S4>
+template <int DIMS, int S4, int MODE>
 __device__ __forceinline__ void ssb_small_range(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt,
-                                                const float (&x)[DIMS], int g, int i_begin, int i_end, float (&acc)[8],
-                                                SsbSmallSmem& sm, uint32_t& phases) {
+                                                const float* vg, int g, int i_begin, int i_end, float (&acc)[8],
+                                                SsbSmallSmem& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nout = d[2], state0 = d[3], w_off = d[4];
+    const int state0 = d[3], w_off = d[4], in_vec = d[5];
     const bool stateful = nt.type == 0;
+    constexpr int NCOL = (4 * S4 - 1 - DIMS) < 8 ? (4 * S4 - 1 - DIMS) : 8;   // decoder columns present (zero padded)
     const float* wsrc = c.W + w_off;
     float* sg = c.st + ((size_t)g * c.nn + state0) * 32;
     const int n_chunks = (i_end - i_begin + SSB_SM_CH - 1) / SSB_SM_CH;
+    uint32_t phases = 0;
     auto issue = [&](int ck) {
         if (lane == 0) {
             const int b = ck & 1, i0 = i_begin + ck * SSB_SM_CH, cnt = min(SSB_SM_CH, i_end - i0);
@@ -251,6 +259,9 @@ __device__ __forceinline__ void ssb_small_range(const SsbCtx& c, const int* __re
     };
     if (n_chunks > 0) issue(0);
     if (n_chunks > 1) issue(1);
+    float x[DIMS];                       // the materialised input vector (written by k_rows of this level)
+#pragma unroll
+    for (int k = 0; k < DIMS; ++k) x[k] = vg[(size_t)(in_vec + k) * 32];
     for (int ck = 0; ck < n_chunks; ++ck) {
         const int b = ck & 1, i0 = i_begin + ck * SSB_SM_CH, cnt = min(SSB_SM_CH, i_end - i0);
         ssb_mbar_wait(&sm.bar[warp][b], (phases >> b) & 1u);
@@ -271,17 +282,12 @@ __device__ __forceinline__ void ssb_small_range(const SsbCtx& c, const int* __re
             float J = wl[0];
 #pragma unroll
             for (int kk = 0; kk < DIMS; ++kk) J = fmaf(wl[1 + kk], x[kk], J);
-            float out;
-            if (stateful) {
-                float s = ss[k * 32];
-                out = ssb_lif_packed(nt, J, s);
-                ss[k * 32] = s;
-            } else {
-                out = ssb_rate(nt, J);
-            }
+            float sv = 0.f;
+            if (MODE == 0 || stateful) sv = ss[k * 32];
+            const float out = ssb_neuron_apply<MODE>(nt, J, sv);
+            if (MODE == 0 || stateful) ss[k * 32] = sv;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (1 + DIMS + j < 4 * S4 && j < nout) acc[j] = fmaf(wl[1 + DIMS + j], out, acc[j]);
+            for (int j = 0; j < NCOL; ++j) acc[j] = fmaf(wl[1 + DIMS + j], out, acc[j]);
         }
         if (stateful) {
             ssb_fence_async();     // generic-proxy writes of this chunk -> visible to the bulk store
@@ -299,23 +305,18 @@ __device__ __forceinline__ void ssb_small_range(const SsbCtx& c, const int* __re
     }
 }
 
-template <int DIMS, int S4>
-__device__ __forceinline__ void ssb_small_item(const SsbCtx& c, const SsbStep& s, const int* __restrict__ d, int g,
-                                               bool split, SsbSmallSmem& sm, uint32_t& phases) {
-    const int n = d[0], nout = d[2], in_row0 = d[5], out_vec = d[6];
+template <int DIMS, int S4, int MODE>
+__device__ __forceinline__ void ssb_small_item(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt, int g,
+                                               bool split, SsbSmallSmem& sm) {
+    const int n = d[0], nout = d[2], out_vec = d[6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const SsbNeuron nt = ssb_neuron(c, d[7]);
     float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    float x[DIMS], acc[8];
+    float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (split) {
-        for (int k = warp; k < DIMS; k += 4) sm.xs[k][lane] = ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg);
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < DIMS; ++k) x[k] = sm.xs[k][lane];
         const int q = (n + 3) >> 2;
-        ssb_small_range<DIMS, S4>(c, d, nt, x, g, min(n, warp * q), min(n, (warp + 1) * q), acc, sm, phases);
+        ssb_small_range<DIMS, S4, MODE>(c, d, nt, vg, g, min(n, warp * q), min(n, (warp + 1) * q), acc, sm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) sm.red[warp][j][lane] = acc[j];
         __syncthreads();
@@ -324,17 +325,31 @@ __device__ __forceinline__ void ssb_small_item(const SsbCtx& c, const SsbStep& s
             vg[(size_t)(out_vec + j) * 32] = t;
         }
     } else {
-#pragma unroll
-        for (int k = 0; k < DIMS; ++k) x[k] = ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg);
-        ssb_small_range<DIMS, S4>(c, d, nt, x, g, 0, n, acc, sm, phases);
+        ssb_small_range<DIMS, S4, MODE>(c, d, nt, vg, g, 0, n, acc, sm);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             if (j < nout) vg[(size_t)(out_vec + j) * 32] = acc[j];
     }
 }
 
-__global__ void __launch_bounds__(128) k_ens_small(SsbCtx c, const int* __restrict__ desc, int n_items, int n_split,
-                                                    int i_rel) {
+template <int MODE>
+__device__ __forceinline__ void ssb_small_dispatch(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt, int g,
+                                                   bool split, SsbSmallSmem& sm) {
+    const int key = d[1] * 8 + (d[8] >> 2);
+    switch (key) {
+#define SSB_CASE(D, S) \
+    case (D) * 8 + (S): ssb_small_item<D, S, MODE>(c, d, nt, g, split, sm); break;
+        SSB_CASE(1, 1) SSB_CASE(1, 2) SSB_CASE(1, 3)
+        SSB_CASE(2, 1) SSB_CASE(2, 2) SSB_CASE(2, 3)
+        SSB_CASE(3, 1) SSB_CASE(3, 2) SSB_CASE(3, 3)
+        SSB_CASE(4, 2) SSB_CASE(4, 3) SSB_CASE(4, 4)
+#undef SSB_CASE
+        default: break;  // excluded by the host-side lowering (dims <= 4, dims + nout <= 11)
+    }
+}
+
+// desc: n, dims, nout, state0, w_off, in_vec, out_vec, ntype, stride
+__global__ void __launch_bounds__(128) k_ens_small(SsbCtx c, const int* __restrict__ desc, int n_items, int n_split) {
     __shared__ SsbSmallSmem sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
@@ -360,19 +375,9 @@ __global__ void __launch_bounds__(128) k_ens_small(SsbCtx c, const int* __restri
     }
     if (live) {
         const int* d = desc + item * 9;
-        const SsbStep s = ssb_step(c, i_rel);
-        uint32_t phases = 0;
-        const int key = d[1] * 8 + (d[8] >> 2);
-        switch (key) {
-#define SSB_CASE(D, S) \
-    case (D) * 8 + (S): ssb_small_item<D, S>(c, s, d, g, split, sm, phases); break;
-            SSB_CASE(1, 1) SSB_CASE(1, 2) SSB_CASE(1, 3)
-            SSB_CASE(2, 1) SSB_CASE(2, 2) SSB_CASE(2, 3)
-            SSB_CASE(3, 1) SSB_CASE(3, 2) SSB_CASE(3, 3)
-            SSB_CASE(4, 2) SSB_CASE(4, 3) SSB_CASE(4, 4)
-#undef SSB_CASE
-            default: break;  // excluded by the host-side lowering (dims <= 4, dims + nout <= 11)
-        }
+        const SsbNeuron nt = ssb_neuron(c, d[7]);
+        if (nt.type == 0 && nt.fast) ssb_small_dispatch<0>(c, d, nt, g, split, sm);
+        else ssb_small_dispatch<1>(c, d, nt, g, split, sm);
     }
     if (lane == 0) ssb_bulk_wait0();   // bulk stores complete before the CTA's shared memory is released
 }
@@ -426,11 +431,9 @@ __global__ void __launch_bounds__(128) k_wide_static(SsbCtx c, const int* __rest
         if (jn_m) ssb_bulk_g2s(s_jn, c.W + jn_w + (size_t)n0 * jn_m, b_jn, &bar);
         if (stateful) ssb_bulk_g2s(s_st, stg, b_st, &bar);
     }
-    const SsbStep s = ssb_step(c, i_rel);
     const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    for (int k = warp; k < dpad; k += 4)
-        xs[k * 32 + lane] = (k < dims) ? ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg) : 0.f;
-    for (int m = warp; m < jn_m; m += 4) us[m * 32 + lane] = ssb_row(c.csr_ptr, s.ent_old, jn_row0 + m, vg);
+    for (int k = warp; k < dpad; k += 4) xs[k * 32 + lane] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
+    for (int m = warp; m < jn_m; m += 4) us[m * 32 + lane] = vg[(size_t)(jn_row0 + m) * 32];
     __syncthreads();                 // xs / us complete, barrier initialised for every thread
     ssb_mbar_wait(&bar, 0);
     float x[DP > 0 ? DP : 1];
@@ -468,7 +471,7 @@ __global__ void __launch_bounds__(128) k_wide_static(SsbCtx c, const int* __rest
         float out;
         if (stateful) {
             float sv = s_st[i * 32 + lane];
-            out = ssb_lif_packed(nt, J, sv);
+            out = nt.fast ? ssb_lif_packed<true>(nt, J, sv) : ssb_lif_packed<false>(nt, J, sv);
             s_st[i * 32 + lane] = sv;
         } else {
             out = ssb_rate(nt, J);
@@ -523,12 +526,10 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
             ssb_bulk_g2s(ebuf + (size_t)t * dims * 32, eg + (size_t)t * dims * 32, tile_bytes, &wbar[warp][t]);
         }
     }
-    const SsbStep s = ssb_step(c, i_rel);
     const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    for (int k = warp; k < dpad; k += nwarps)
-        xs[k * 32 + lane] = (k < dims) ? ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg) : 0.f;
-    for (int m = warp; m < jn_m; m += nwarps) us[m * 32 + lane] = ssb_row(c.csr_ptr, s.ent_old, jn_row0 + m, vg);
-    const float aL = __int_as_float(d[15]) * ssb_row(c.csr_ptr, s.ent_old, voja_row, vg);
+    for (int k = warp; k < dpad; k += nwarps) xs[k * 32 + lane] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
+    for (int m = warp; m < jn_m; m += nwarps) us[m * 32 + lane] = vg[(size_t)(jn_row0 + m) * 32];
+    const float aL = __int_as_float(d[15]) * vg[(size_t)voja_row * 32];
     __syncthreads();
     float x[DP > 0 ? DP : 1];
     if (DP > 0) {
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
         J += (a0 + a1) + (a2 + a3);
         float out;
         if (stateful) {
-            out = ssb_lif_packed(nt, J, sv);
+            out = nt.fast ? ssb_lif_packed<true>(nt, J, sv) : ssb_lif_packed<false>(nt, J, sv);
             __stcs(sp + (size_t)i * 32, sv);
         } else {
             out = ssb_rate(nt, J);
@@ -658,49 +659,84 @@ __device__ __forceinline__ void ssb_splitk_finish(const SsbCtx& c, float (*red)[
 }
 
 // Static decoders of wide ensembles: out[j] = sum_n Wd[n][j] * act[n].  CTA = (decoder, trial group,
-// 8-row output tile, neuron chunk); warps interleave the chunk's neurons; a neuron whose activity is
-// zero in all 32 trials is skipped (spiking activity is sparse).
+// neuron chunk); each warp keeps a 56-wide accumulator tile in registers and walks every fourth neuron of
+// the chunk; a neuron whose activity is zero in all 32 trials is skipped (spiking activity is sparse), so
+// the weight row (14 broadcast float4 loads) is only fetched for neurons that fired somewhere in the group.
+// Warps are reduced in shared memory, chunks by the split-K semaphore (fixed summation order).
 // desc: n size_out jpad act0 w_off out_vec n_chunks part_off counter0
-__global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict__ desc, int item0, int max_chunks) {
-    __shared__ float red[4][8][32];
+#define SSB_DEC_NJ 56
+__global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict__ desc, int item0) {
+    __shared__ float red[4][SSB_DEC_NJ][32];
     __shared__ int flag;
-    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
-    const int* d = desc + (item0 + item) * 9;
+    const int* d = desc + (item0 + blockIdx.z) * 9;
     const int n = d[0], size_out = d[1], jpad = d[2], act0 = d[3], w_off = d[4], out_vec = d[5], n_chunks = d[6];
-    const int j0 = blockIdx.x * 8;
-    if (j0 >= size_out || chunk >= n_chunks) return;
+    const int part_off = d[7], counter = d[8] * c.G + blockIdx.y;
+    const int chunk = blockIdx.x;
+    if (chunk >= n_chunks) return;
     const int per = (n + n_chunks - 1) / n_chunks;
     const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.y;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
-    constexpr int U = 4;
-    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
-        float a[U];
+    float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    float* pg = ssb_grp(c.part, c.n_part, g, lane);
+    for (int jb = 0; jb < jpad; jb += SSB_DEC_NJ) {
+        const int nq = min(SSB_DEC_NJ, jpad - jb) >> 2;      // float4 columns of this pass (jpad is a multiple of 8)
+        float acc[SSB_DEC_NJ];
 #pragma unroll
-        for (int u = 0; u < U; ++u) a[u] = (i + 4 * u < i_hi) ? ap[(size_t)(i + 4 * u) * 32] : 0.f;
+        for (int j = 0; j < SSB_DEC_NJ; ++j) acc[j] = 0.f;
+        constexpr int U = 4;
+        for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
+            float a[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (__any_sync(0xffffffffu, a[u] != 0.f)) {
-                const float4* __restrict__ w4 =
-                    reinterpret_cast<const float4*>(c.W + w_off + (size_t)(i + 4 * u) * jpad + j0);
-                const float4 wa = __ldg(w4), wb = __ldg(w4 + 1);
-                acc[0] = fmaf(wa.x, a[u], acc[0]);
-                acc[1] = fmaf(wa.y, a[u], acc[1]);
-                acc[2] = fmaf(wa.z, a[u], acc[2]);
-                acc[3] = fmaf(wa.w, a[u], acc[3]);
-                acc[4] = fmaf(wb.x, a[u], acc[4]);
-                acc[5] = fmaf(wb.y, a[u], acc[5]);
-                acc[6] = fmaf(wb.z, a[u], acc[6]);
-                acc[7] = fmaf(wb.w, a[u], acc[7]);
+            for (int u = 0; u < U; ++u) a[u] = (i + 4 * u < i_hi) ? ap[(size_t)(i + 4 * u) * 32] : 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (__any_sync(0xffffffffu, a[u] != 0.f)) {
+                    const float4* __restrict__ w4 =
+                        reinterpret_cast<const float4*>(c.W + w_off + (size_t)(i + 4 * u) * jpad + jb);
+#pragma unroll
+                    for (int q = 0; q < SSB_DEC_NJ / 4; ++q) {
+                        if (q < nq) {
+                            const float4 w = __ldg(w4 + q);
+                            acc[4 * q + 0] = fmaf(w.x, a[u], acc[4 * q + 0]);
+                            acc[4 * q + 1] = fmaf(w.y, a[u], acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(w.z, a[u], acc[4 * q + 2]);
+                            acc[4 * q + 3] = fmaf(w.w, a[u], acc[4 * q + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // red is free (previous pass consumed)
+#pragma unroll
+        for (int j = 0; j < SSB_DEC_NJ; ++j) red[warp][j][lane] = acc[j];
+        __syncthreads();
+        for (int j = warp; j < 4 * nq; j += 4) {
+            if (jb + j < size_out) {
+                const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
+                if (n_chunks == 1) vg[(size_t)(out_vec + jb + j) * 32] = t;
+                else pg[(size_t)(part_off + chunk * size_out + jb + j) * 32] = t;
             }
         }
     }
-    ssb_splitk_finish(c, red, &flag, acc, g, j0, size_out, out_vec, n_chunks, chunk, d[7],
-                      (d[8] + (int)blockIdx.x) * c.G + g);
+    if (n_chunks == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(c.counters + counter, 1);
+        const int last = old == n_chunks - 1;
+        if (last) c.counters[counter] = 0;
+        flag = last;
+    }
+    __syncthreads();
+    if (!flag) return;
+    __threadfence();
+    for (int j = threadIdx.x >> 5; j < size_out; j += 4) {
+        float t = 0.f;
+        for (int ck = 0; ck < n_chunks; ++ck) t += __ldcg(pg + (size_t)(part_off + ck * size_out + j) * 32);
+        vg[(size_t)(out_vec + j) * 32] = t;
+    }
 }
 
 // --------------------------------------------------------------------------------------
@@ -708,41 +744,19 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
 // decodes with the updated weights and writes them back:
 //   D <- D + outer(alpha*err_prev, a_prev)     (nengo: Copy(delta->weights, inc) at step start)
 //   out = D . act                               (DotInc)
-// err_prev / a_prev are the values the previous step read (the not-yet-overwritten half of the
-// ping-pong buffers), which is exactly SimPES' delta of the previous step.  For a fixed output row
-// the weights of consecutive neurons are consecutive 128-byte lines.  A neuron whose trace and
-// activity are zero in all 32 trials changes nothing and contributes nothing: its weights are
-// neither read nor written (exact, not an approximation).
-// desc: n size_out d_off a_off act0 err_row0 out_vec alpha_bits decay_bits onemdecay_bits n_chunks part_off counter0
-__global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ desc, int max_chunks, int i_rel) {
-    __shared__ float red[4][8][32];
-    __shared__ int flag;
-    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
-    const int* d = desc + item * 13;
-    const int n = d[0], size_out = d[1], d_off = d[2], a_off = d[3], act0 = d[4], err_row0 = d[5], out_vec = d[6];
-    const int n_chunks = d[10];
-    const float alpha = __int_as_float(d[7]);
-    const int j0 = blockIdx.x * 8;
-    if (j0 >= size_out || chunk >= n_chunks) return;
-    const int per = (n + n_chunks - 1) / n_chunks;
-    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.y;
-    const SsbStep s = ssb_step(c, i_rel);
-    const int prev_buf = 1 - s.odd;  // afilt half that still holds what the previous step read
-    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    const int jn = min(8, size_out - j0);
-    float ae[8], acc[8];
+// err_prev / a_prev are the values the previous step read (the error rows are materialised from the
+// not-yet-overwritten filter half, the trace comes from the other half of its ping-pong buffer), which
+// is exactly SimPES' delta of the previous step.  For a fixed output row the weights of consecutive
+// neurons are consecutive 128-byte lines.  A neuron whose trace and activity are zero in all 32 trials
+// changes nothing and contributes nothing: its weights are neither read nor written (exact).
+// desc: n size_out d_off a_off act0 err_vec out_vec alpha_bits decay_bits onemdecay_bits n_chunks part_off counter0
+template <bool FULL>
+__device__ __forceinline__ void ssb_pes_body(const float* __restrict__ ap, const float* __restrict__ fp, float* __restrict__ dp,
+                                             int n, int jn, int i_lo, int i_hi, const float (&ae)[8], float (&acc)[8]) {
+    const int warp = threadIdx.x >> 5;
+    float* rowp[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        acc[j] = 0.f;
-        float e = 0.f;
-        if (j < jn) e = ssb_row(c.csr_ptr, s.ent_new, err_row0 + j0 + j, vg);
-        ae[j] = s.step > 0 ? alpha * e : 0.f;
-    }
-    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
-    const float* __restrict__ fp = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)prev_buf * c.n_afilt + a_off) * 32;
-    float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + (size_t)d_off * 32;
+    for (int j = 0; j < 8; ++j) rowp[j] = dp + (size_t)((FULL || j < jn) ? j : 0) * n * 32;
     constexpr int U = 4;
     for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
         float a[U], f[U], w[U][8];
@@ -761,27 +775,60 @@ __global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ d
         for (int u = 0; u < U; ++u) {
             on[u] = __any_sync(0xffffffffu, a[u] != 0.f || f[u] != 0.f);
             if (on[u]) {
-                const int ii = i + 4 * u;
+                const size_t off = (size_t)(i + 4 * u) * 32;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (j < jn) w[u][j] = __ldcs(dp + ((size_t)(j0 + j) * n + ii) * 32);
+                    if (FULL || j < jn) w[u][j] = __ldcs(rowp[j] + off);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (on[u]) {
-                const int ii = i + 4 * u;
+                const size_t off = (size_t)(i + 4 * u) * 32;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (j < jn) {
+                    if (FULL || j < jn) {
                         const float wn = fmaf(ae[j], f[u], w[u][j]);
                         acc[j] = fmaf(wn, a[u], acc[j]);
-                        __stcs(dp + ((size_t)(j0 + j) * n + ii) * 32, wn);
+                        __stcs(rowp[j] + off, wn);
                     }
                 }
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ desc, int max_chunks, int i_rel) {
+    __shared__ float red[4][8][32];
+    __shared__ int flag;
+    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
+    const int* d = desc + item * 13;
+    const int n = d[0], size_out = d[1], d_off = d[2], a_off = d[3], act0 = d[4], err_vec = d[5], out_vec = d[6];
+    const int n_chunks = d[10];
+    const float alpha = __int_as_float(d[7]);
+    const int j0 = blockIdx.x * 8;
+    if (j0 >= size_out || chunk >= n_chunks) return;
+    const int per = (n + n_chunks - 1) / n_chunks;
+    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.y;
+    const SsbStep s = ssb_step(c, i_rel);
+    const int prev_buf = 1 - s.odd;  // afilt half that still holds what the previous step read
+    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    const int jn = min(8, size_out - j0);
+    float ae[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc[j] = 0.f;
+        float e = 0.f;
+        if (j < jn) e = vg[(size_t)(err_vec + j0 + j) * 32];   // error of the previous step, materialised by k_rows
+        ae[j] = s.step > 0 ? alpha * e : 0.f;
+    }
+    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
+    const float* __restrict__ fp = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)prev_buf * c.n_afilt + a_off) * 32;
+    float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
+    if (jn == 8) ssb_pes_body<true>(ap, fp, dp, n, jn, i_lo, i_hi, ae, acc);
+    else ssb_pes_body<false>(ap, fp, dp, n, jn, i_lo, i_hi, ae, acc);
     ssb_splitk_finish(c, red, &flag, acc, g, j0, size_out, out_vec, n_chunks, chunk, d[11],
                       (d[12] + (int)blockIdx.x) * c.G + g);
 }
@@ -844,18 +891,17 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
     float* xs = sm + (size_t)tile_rows * dpad;     // [4][dpad][32] (generic width only)
     float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
     float x[DP > 0 ? DP : 1];
-    if (CSR_INPUT) {
-        const SsbStep s = ssb_step(c, i_rel);
+    if (CSR_INPUT) {   // query = materialised vec rows of this step
         const float* vg = ssb_grp(c.vec, c.nv, g, lane);
         if (DP > 0) {
 #pragma unroll
             for (int k = 0; k < DP; ++k) {
-                x[k] = (k < dims) ? ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg) : 0.f;
+                x[k] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
                 if (blockIdx.x == 0 && live) cxg[(size_t)k * 32] = x[k];
             }
         } else {
             for (int k = 0; k < dpad; ++k) {
-                const float xv = (k < dims) ? ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg) : 0.f;
+                const float xv = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
                 xs[(warp * dpad + k) * 32 + lane] = xv;
                 if (blockIdx.x == 0 && live) cxg[(size_t)k * 32] = xv;
             }
@@ -1078,13 +1124,12 @@ __global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ 
     const float rate = __int_as_float(d[3]), thres = __int_as_float(d[4]), atol = __int_as_float(d[5]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
-    const SsbStep s = ssb_step(c, i_rel);
     float* vg = ssb_grp(c.vec, c.nv, g, lane);
     // pass 1: p - q goes to the output slot, p.q is reduced over the 8 warps
     float dot = 0.f;
     for (int k = warp; k < dims; k += 8) {
-        const float p = ssb_row(c.csr_ptr, s.ent_old, in_row0 + k, vg);
-        const float q = ssb_row(c.csr_ptr, s.ent_old, in_row0 + dims + k, vg);
+        const float p = vg[(size_t)(in_row0 + k) * 32];
+        const float q = vg[(size_t)(in_row0 + dims + k) * 32];
         dot = fmaf(p, q, dot);
         vg[(size_t)(out_vec + k) * 32] = p - q;
     }
@@ -1092,7 +1137,7 @@ __global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ 
     __syncthreads();
     dot = 0.f;
     for (int w = 0; w < 8; ++w) dot += part[w][lane];
-    const float flag = ssb_row(c.csr_ptr, s.ent_old, in_row0 + 2 * dims, vg);
+    const float flag = vg[(size_t)(in_row0 + 2 * dims) * 32];
     const bool open = (fabsf(flag) <= atol) && (dot > thres);
     // pass 2: each thread rescales the values it wrote itself
     for (int k = warp; k < dims; k += 8) {
@@ -1104,7 +1149,9 @@ __global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ 
 // --------------------------------------------------------------------------------------
 // End-of-step rows: Lowpass updates (y_new = a*y_old + b*u, written to the other half of
 // the ping-pong buffer = nengo's update-after-read), probe samples, PES activity traces.
-// rows: [csr_row | act_row, kind, dst]; kind 0 filter, 1 probe, 2 activity trace
+// The same kernel materialises the sink rows of a dependency level into vec scratch before the level's
+// consumers run (kinds 3 / 4), so that no consumer evaluates CSR rows itself.
+// rows: [csr_row | act_row, kind, dst]; kind 0 filter, 1 probe, 2 activity trace, 3 / 4 materialise
 __global__ void __launch_bounds__(128) k_lin(SsbCtx c, const int* __restrict__ rows, const float* __restrict__ ab, int n_rows,
                                               int i_rel) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1129,6 +1176,8 @@ __global__ void __launch_bounds__(128) k_lin(SsbCtx c, const int* __restrict__ r
         const float u = ssb_row(c.csr_ptr, s.ent_old, src, vg);
         const float y = vg[(size_t)(1 + dst + s.par_old) * 32];
         vg[(size_t)(1 + dst + s.par_new) * 32] = fmaf(b, u, a * y);
+    } else if (kind >= 3) {   // materialise a sink row for the consumers of this level (4: previous step's view)
+        vg[(size_t)dst * 32] = ssb_row(c.csr_ptr, kind == 3 ? s.ent_old : s.ent_new, src, vg);
     } else if (kind == 1) {
         const float u = ssb_row(c.csr_ptr, s.ent_old, src, vg);
         float* pg = c.probe + (((size_t)g * c.probe_cap + (size_t)(s.step - c.dyn[2])) * c.n_probe + dst) * 32 + lane;

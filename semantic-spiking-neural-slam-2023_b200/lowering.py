@@ -151,12 +151,18 @@ class _Lowerer:
             small = (ens.dimensions <= SMALL_MAX_DIMS and nout <= SMALL_MAX_OUT and ens not in voja_posts
                      and ens not in jn_posts and not has_pes)
             self.is_small[ens] = small
-            for c in outs:
-                if small:
+        n_static = sum(1 for e in self.ensembles if not self.is_small[e]
+                       for c in self.ens_dec_conns[e] if c not in pes_conns)
+        for ens in self.ensembles:
+            for c in self.ens_dec_conns[ens]:
+                if self.is_small[ens]:
                     self.dec_chunks[c] = 1
-                else:
+                elif c in pes_conns:   # k_pes: CTA = (8-row tile, trial group, neuron chunk)
                     jtiles = -(-self._out_size(c) // DEC_TILE)
                     want = -(-TARGET_CTAS // (jtiles * self.n_groups))
+                    self.dec_chunks[c] = int(max(1, min(want, ens.n_neurons // 32, MAX_DEC_CHUNKS)))
+                else:                  # k_decode: CTA = (decoder, trial group, neuron chunk), all outputs at once
+                    want = -(-TARGET_CTAS // (max(1, n_static) * self.n_groups))
                     self.dec_chunks[c] = int(max(1, min(want, ens.n_neurons // 32, MAX_DEC_CHUNKS)))
 
     @staticmethod
@@ -399,6 +405,19 @@ class _Lowerer:
                 csr_ptr.append(len(csr_idx))
             return row0
 
+        # ---- sink rows are materialised once per level by k_lin-style passes (kinds 3 / 4) into vec scratch;
+        #      the consumers' descriptors carry the vec row of their input
+        mat_rows = [[] for _ in range(n_levels)]
+
+        def materialize(mat, lvl, previous_view=False):
+            nonlocal NV
+            r0, nrow = add_rows(mat), mat.shape[0]
+            v0 = NV
+            NV += nrow
+            for i in range(nrow):
+                mat_rows[lvl].append([r0 + i, 4 if previous_view else 3, v0 + i])
+            return v0
+
         # ---- weights + descriptors
         W = []            # static float32 weights (shared by all trials)
         w_len = 0
@@ -421,8 +440,8 @@ class _Lowerer:
             if isinstance(nt, ns.LIF):
                 if nt.min_voltage != 0:
                     raise NotImplementedError("the packed one-word LIF state needs min_voltage == 0 (nengo's default)")
-                # polynomial expm1 / log1p are exact to fp32 for dt / tau_rc <= 1/8 (SSB kernels header)
-                fast = 1.0 if dt / nt.tau_rc <= 0.125 else 0.0
+                # polynomial expm1 / log1p are exact to fp32 for dt / tau_rc <= 1/16 (SSB kernels header)
+                fast = 1.0 if dt / nt.tau_rc <= 0.0625 else 0.0
                 key = (NT_LIF, nt.tau_rc, nt.tau_ref, nt.min_voltage, nt.amplitude, fast, 0.0, 0.0)
             elif isinstance(nt, ns.LIFRate):
                 key = (NT_LIFRATE, nt.tau_rc, nt.tau_ref, 0.0, nt.amplitude, 0.0, 0.0, 0.0)
@@ -466,7 +485,7 @@ class _Lowerer:
             nn += n
             plan.ens_state[ens] = (state0, n)
             tid = ntype_id(ens.neuron_type)
-            in_row0 = add_rows(ens_in[ens])
+            in_row0 = materialize(ens_in[ens], lvl)
             if is_small:
                 n_small += 1
                 decs = [self._dec_weights(c) for c in outs]  # each (size_out x n)
@@ -498,7 +517,7 @@ class _Lowerer:
                 n_lenc += n * dims
                 plan.learned_enc[ens] = (enc_off, n, dims)
                 voja_alpha = lrt.learning_rate * dt
-                voja_row = add_rows(lrow)
+                voja_row = materialize(lrow, lvl)
                 scale_off = add_w(p.gain / ens.radius)
             else:
                 enc = np.zeros((n, dpad))
@@ -508,7 +527,7 @@ class _Lowerer:
             jn_row0 = jn_m = jn_w = 0
             if ens in ens_jn:
                 u, G = ens_jn[ens]
-                jn_row0, jn_m, jn_w = add_rows(u), u.shape[0], add_w(G)
+                jn_row0, jn_m, jn_w = materialize(u, lvl), u.shape[0], add_w(G)
                 flags |= 2
             big_desc[lvl].append([n, dims, dpad, state0, act0, enc_off, bias_off, in_row0, tid, flags,
                                   jn_row0, jn_m, jn_w, voja_row, scale_off,
@@ -528,7 +547,7 @@ class _Lowerer:
                         raise NotImplementedError(
                             "PES error input must arrive through a synapse (the delta of step t-1 is rebuilt "
                             "from the previous filter values)")
-                    err_row0 = add_rows(rin)
+                    err_row0 = materialize(rin, 0, previous_view=True)   # filter / constant columns only
                     alpha = -lrt.learning_rate * dt / n
                     if lrt.pre_synapse is None:
                         decay = 0.0
@@ -551,7 +570,7 @@ class _Lowerer:
         for node, mat in fn_in.items():
             op = self.node_op[node]
             lvl = fn_level[node]
-            in_row0 = add_rows(mat)
+            in_row0 = materialize(mat, lvl)
             out_vec = int(dev_col[self.fn_col[node]])
             if op.kind == "cleanup":
                 S = op.sample_ssps
@@ -615,6 +634,16 @@ class _Lowerer:
         def arr(rows, width):
             return np.asarray(rows, dtype=np.int32).reshape(-1, width)
 
+        lin_final = lin_rows
+        lin_final_ab = lin_ab
+        lin_rows, lin_ab, level_rows = [], [], []
+        for lvl in range(n_levels):
+            level_rows.append((len(lin_rows), len(mat_rows[lvl])))
+            lin_rows += mat_rows[lvl]
+            lin_ab += [[0.0, 1.0]] * len(mat_rows[lvl])
+        lin0 = len(lin_rows)
+        lin_rows += lin_final
+        lin_ab += lin_final_ab
         stages = []  # per level counts/offsets into the concatenated descriptor arrays
         cat = {k: [] for k in ("small", "big", "dec", "cleanup", "gate")}
         for lvl in range(n_levels):
@@ -625,7 +654,7 @@ class _Lowerer:
                               ("cleanup", cleanup_desc[lvl]), ("gate", gate_desc[lvl])):
                 entry += [len(cat[name]), len(lst)]
                 cat[name] += lst
-            stages.append(entry)
+            stages.append(entry + list(level_rows[lvl]))
         plan.arrays.update({
             "csr_ptr": np.asarray(csr_ptr, dtype=np.int32),
             "csr_ent0": self._entries(csr_idx, csr_val, 0, NF),
@@ -640,7 +669,7 @@ class _Lowerer:
             "gate": arr(cat["gate"], 6),
             "lin_rows": arr(lin_rows, 3),
             "lin_ab": np.asarray(lin_ab, dtype=np.float32).reshape(-1, 2),
-            "stages": arr(stages, 10),
+            "stages": arr(stages, 12),
             "ntypes": np.asarray(ntypes, dtype=np.float32).reshape(-1, 8),
             "cleanup_s64": np.concatenate([a for lvl in cleanup_s64 for a in lvl] + [np.zeros(0)]),
         })
@@ -648,7 +677,8 @@ class _Lowerer:
                               if self.node_op[n].kind == "cleanup" and fn_level[n] == lvl]
         plan.scalars.update(dict(dt=dt, nv=NV, nf=NF, nt=NT, tab_row0=tab_row0, nn=nn, n_act=n_act, n_lenc=n_lenc,
                                  n_ldec=n_ldec, n_afilt=n_afilt, n_probe=n_probe_rows, n_levels=n_levels,
-                                 chunk_cap=chunk_cap, n_part=n_part, n_jtiles=n_jtiles, pes_level=pes_level))
+                                 chunk_cap=chunk_cap, n_part=n_part, n_jtiles=n_jtiles, pes_level=pes_level,
+                                 lin0=lin0, n_lin=len(lin_rows) - lin0))
         n_static = int(sum(a.size for a in W))
         plan.stats = dict(n_neurons=nn, n_filter_states=NF, n_learned=n_lenc + n_ldec, n_static_weights=n_static,
                           n_table_words=NT, n_probe_words=n_probe_rows, n_small=n_small, n_big=n_big,

@@ -97,39 +97,42 @@ class PlanInterpreter:
         if self.nt:
             self.vec[self.tab_row0:self.tab_row0 + self.nt] = self.tables[s]      # k_begin
         for st in a["stages"]:
+            for src, kind, dst in a["lin_rows"][st[10]:st[10] + st[11]]:     # materialise this level's sink rows
+                assert kind in (3, 4)
+                self.vec[dst] = self.rows(src, 1, 1 if kind == 4 else 0)[0]
             for d in a["ens_small"][st[0]:st[0] + st[1]]:
                 n, dims, nout, s0, w_off, in_row0, out_vec, tid, stride = (int(x) for x in d)
                 pk = W[w_off:w_off + n * stride].reshape(n, stride)
-                x = self.rows(in_row0, dims)
+                x = self.vec[in_row0:in_row0 + dims].copy()
                 out = self.neuron(tid, pk[:, 0] + pk[:, 1:1 + dims] @ x, s0, n)
                 self.vec[out_vec:out_vec + nout] = pk[:, 1 + dims:1 + dims + nout].T @ out
             for d in a["ens_big"][st[2]:st[2] + st[3]]:
                 (n, dims, dpad, s0, act0, enc_off, bias_off, in_row0, tid, flags, jn_row0, jn_m, jn_w, voja_row,
                  scale_off, alpha_bits) = (int(x) for x in d)
-                x = self.rows(in_row0, dims)
+                x = self.vec[in_row0:in_row0 + dims].copy()
                 if flags & 1:
                     E = self.lenc[enc_off:enc_off + n * dims].reshape(n, dims)
                 else:
                     E = W[enc_off:enc_off + n * dpad].reshape(n, dpad)[:, :dims]
                 J = W[bias_off:bias_off + n] + E @ x
                 if jn_m:
-                    J = J + W[jn_w:jn_w + n * jn_m].reshape(n, jn_m) @ self.rows(jn_row0, jn_m)
+                    J = J + W[jn_w:jn_w + n * jn_m].reshape(n, jn_m) @ self.vec[jn_row0:jn_row0 + jn_m]
                 out = self.neuron(tid, J, s0, n)
                 self.act[act0:act0 + n] = out
                 if flags & 1:
-                    aL = np.int32(alpha_bits).view(np.float32).astype(self.dt_) * self.rows(voja_row, 1)[0]
+                    aL = np.int32(alpha_bits).view(np.float32).astype(self.dt_) * self.vec[voja_row]
                     sc = W[scale_off:scale_off + n]
                     E += aL * (sc[:, None] * np.outer(out, x) - out[:, None] * E)   # E is a view of lenc
             for ci in range(st[6], st[6] + st[7]):
                 G, dims, dpad, s_off, in_row0, out_vec = (int(x) for x in a["cleanup"][ci])
-                x = self.rows(in_row0, dims)
+                x = self.vec[in_row0:in_row0 + dims].copy()
                 g = int(np.argmax(self.grids[ci] @ x.astype(np.float64)))
                 self.cidx[ci] = g
                 self.vec[out_vec:out_vec + dims] = W[s_off + g * dpad:s_off + g * dpad + dims]
             for d in a["gate"][st[8]:st[8] + st[9]]:
                 dims, in_row0, out_vec = int(d[0]), int(d[1]), int(d[2])
                 rate, thres, atol = (np.int32(x).view(np.float32).astype(np.float64) for x in d[3:6])
-                x = self.rows(in_row0, 2 * dims + 1)
+                x = self.vec[in_row0:in_row0 + 2 * dims + 1].copy()
                 p_, q_ = x[:dims], x[dims:2 * dims]
                 open_ = abs(x[-1]) <= atol and float(p_ @ q_) > thres
                 self.vec[out_vec:out_vec + dims] = rate * (p_ - q_) if open_ else 0.0
@@ -148,7 +151,7 @@ class PlanInterpreter:
             nch = int(d[10])
             D = self.ldec[d_off:d_off + so * n].reshape(so, n)
             if s > 0:
-                err = self.rows(err_row0, so, 1)
+                err = self.vec[err_row0:err_row0 + so].copy()
                 D += np.outer(alpha * err, self.afilt[1 - (s & 1), a_off:a_off + n])
             per = -(-n // nch)
             total = np.zeros(so, self.dt_)
@@ -158,7 +161,8 @@ class PlanInterpreter:
             self.vec[out_vec:out_vec + so] = total
         probe = np.zeros(int(self.p.scalars["n_probe"]), self.dt_)
         new_f = {}
-        for (src, kind, dst), (ca, cb) in zip(a["lin_rows"], a["lin_ab"].astype(self.dt_)):
+        lin0 = int(self.p.scalars["lin0"])
+        for (src, kind, dst), (ca, cb) in zip(a["lin_rows"][lin0:], a["lin_ab"][lin0:].astype(self.dt_)):
             if kind == 0:
                 new_f[1 + dst + par_new] = cb * self.rows(src, 1)[0] + ca * self.vec[1 + dst + par_old]
             elif kind == 1:
