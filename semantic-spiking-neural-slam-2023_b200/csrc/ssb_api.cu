@@ -308,6 +308,7 @@ void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, int i_rel) {
 
 void wide_smem_optin() {
     const int lim = 200 * 1024;
+    cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -407,9 +408,15 @@ int one_step(ssb_sim* s, int i_rel) {
         if (st[5] > 0) {
             LaunchTimer t(s, K_DEC);
             int max_chunks = 1;
-            for (int i = 0; i < st[5]; ++i) max_chunks = std::max(max_chunks, s->h_dec[(st[4] + i) * 9 + 6]);
+            size_t smem = 0;
+            for (int i = 0; i < st[5]; ++i) {
+                const int* d = &s->h_dec[(st[4] + i) * 9];
+                max_chunks = std::max(max_chunks, d[6]);
+                const size_t per = (d[0] + d[6] - 1) / d[6];
+                smem = std::max(smem, (per * d[2] + per * 32 + 56 * 32) * sizeof(float));
+            }
             dim3 grid(max_chunks, G, st[5]);
-            k_decode<<<grid, 128, 0, B>>>(c, s->d_dec, st[4]);
+            k_decode<<<grid, 128, smem, B>>>(c, s->d_dec, st[4]);
         }
         if (useB) stream_dep(s, B, A);
         if (useC) stream_dep(s, C, A);

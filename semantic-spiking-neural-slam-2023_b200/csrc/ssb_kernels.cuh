@@ -74,20 +74,40 @@ __device__ __forceinline__ float* ssb_grp(float* base, int rows, int g, int lane
 // One sink row: sparse linear combination of vec rows for the 32 trials of a group.  Entries are
 // warp-uniform 8-byte loads; the host pads every row to a multiple of 8 entries with (row 0,
 // coefficient 0), so the loop has no tail and the 8 per-trial source loads of a batch are independent.
+// `asm volatile` loads keep program order, so the compiler cannot re-serialise a batch to save registers:
+// all entry loads of a batch are issued, then all source loads, then the multiply-adds.
+__device__ __forceinline__ int2 ssb_ld_ent(const int2* p) {
+    int2 v;
+    asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ssb_ld_src(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+template <int NB>
+__device__ __forceinline__ float ssb_row_batch(const int2* __restrict__ ent, const float* vg, float acc) {
+    int2 e[NB];
+    float x[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) e[u] = ssb_ld_ent(ent + u);
+#pragma unroll
+    for (int u = 0; u < NB; ++u) x[u] = ssb_ld_src(vg + (size_t)e[u].x * 32);
+#pragma unroll
+    for (int u = 0; u < NB; ++u) acc = fmaf(__int_as_float(e[u].y), x[u], acc);
+    return acc;
+}
+
 __device__ __forceinline__ float ssb_row(const int* __restrict__ ptr, const int2* __restrict__ ent, int row,
                                          const float* vg) {
     const int lo = __ldg(ptr + row), hi = __ldg(ptr + row + 1);
     float acc = 0.f;
-    for (int p = lo; p < hi; p += 8) {
-        int2 e[8];
-        float x[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) e[u] = __ldg(ent + p + u);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = vg[(size_t)e[u].x * 32];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc = fmaf(__int_as_float(e[u].y), x[u], acc);
-    }
+    int p = lo;
+    // long rows (dense DFT / product transforms): 32 independent source loads in flight
+    for (; p + 32 <= hi; p += 32) acc = ssb_row_batch<32>(ent + p, vg, acc);
+    for (; p < hi; p += 8) acc = ssb_row_batch<8>(ent + p, vg, acc);
     return acc;
 }
 
@@ -659,14 +679,17 @@ __device__ __forceinline__ void ssb_splitk_finish(const SsbCtx& c, float (*red)[
 }
 
 // Static decoders of wide ensembles: out[j] = sum_n Wd[n][j] * act[n].  CTA = (decoder, trial group,
-// neuron chunk); each warp keeps a 56-wide accumulator tile in registers and walks every fourth neuron of
-// the chunk; a neuron whose activity is zero in all 32 trials is skipped (spiking activity is sparse), so
-// the weight row (14 broadcast float4 loads) is only fetched for neurons that fired somewhere in the group.
-// Warps are reduced in shared memory, chunks by the split-K semaphore (fixed summation order).
+// neuron chunk).  The chunk's weight rows [cnt][jpad] and activity rows [cnt][32] are contiguous and are
+// staged in shared memory by two TMA bulk copies; each warp keeps a 56-wide accumulator tile in registers
+// and walks every fourth neuron of the chunk with broadcast float4 weight reads; a neuron whose activity
+// is zero in all 32 trials is skipped (spiking activity is sparse).  Warps are folded into one shared
+// tile in warp order, chunks by the split-K semaphore (fixed summation order).
 // desc: n size_out jpad act0 w_off out_vec n_chunks part_off counter0
+// dynamic smem: per*jpad (weights) + per*32 (activities) + 56*32 (fold tile) floats, per = ceil(n / n_chunks)
 #define SSB_DEC_NJ 56
 __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict__ desc, int item0) {
-    __shared__ float red[4][SSB_DEC_NJ][32];
+    extern __shared__ __align__(128) float sm[];
+    __shared__ unsigned long long bar;
     __shared__ int flag;
     const int* d = desc + (item0 + blockIdx.z) * 9;
     const int n = d[0], size_out = d[1], jpad = d[2], act0 = d[3], w_off = d[4], out_vec = d[5], n_chunks = d[6];
@@ -674,10 +697,22 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
     const int chunk = blockIdx.x;
     if (chunk >= n_chunks) return;
     const int per = (n + n_chunks - 1) / n_chunks;
-    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
+    const int i_lo = chunk * per, cnt = min(n, i_lo + per) - i_lo;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.y;
-    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
+    float* s_w = sm;                                   // [per][jpad]
+    float* s_a = s_w + (size_t)per * jpad;             // [per][32]
+    float* fold = s_a + (size_t)per * 32;              // [56][32]
+    if (threadIdx.x == 0) {
+        ssb_mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bw = (uint32_t)cnt * jpad * 4, ba = (uint32_t)cnt * 128;
+        ssb_mbar_expect_tx(&bar, bw + ba);
+        ssb_bulk_g2s(s_w, c.W + w_off + (size_t)i_lo * jpad, bw, &bar);
+        ssb_bulk_g2s(s_a, c.act + ((size_t)g * c.n_act + act0 + i_lo) * 32, ba, &bar);
+    }
+    __syncthreads();
+    ssb_mbar_wait(&bar, 0);
     float* vg = ssb_grp(c.vec, c.nv, g, lane);
     float* pg = ssb_grp(c.part, c.n_part, g, lane);
     for (int jb = 0; jb < jpad; jb += SSB_DEC_NJ) {
@@ -685,39 +720,38 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
         float acc[SSB_DEC_NJ];
 #pragma unroll
         for (int j = 0; j < SSB_DEC_NJ; ++j) acc[j] = 0.f;
-        constexpr int U = 4;
-        for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
-            float a[U];
+        for (int i = warp; i < cnt; i += 4) {
+            const float a = s_a[i * 32 + lane];
+            if (__any_sync(0xffffffffu, a != 0.f)) {
+                const float4* w4 = reinterpret_cast<const float4*>(s_w + (size_t)i * jpad + jb);
 #pragma unroll
-            for (int u = 0; u < U; ++u) a[u] = (i + 4 * u < i_hi) ? ap[(size_t)(i + 4 * u) * 32] : 0.f;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (__any_sync(0xffffffffu, a[u] != 0.f)) {
-                    const float4* __restrict__ w4 =
-                        reinterpret_cast<const float4*>(c.W + w_off + (size_t)(i + 4 * u) * jpad + jb);
-#pragma unroll
-                    for (int q = 0; q < SSB_DEC_NJ / 4; ++q) {
-                        if (q < nq) {
-                            const float4 w = __ldg(w4 + q);
-                            acc[4 * q + 0] = fmaf(w.x, a[u], acc[4 * q + 0]);
-                            acc[4 * q + 1] = fmaf(w.y, a[u], acc[4 * q + 1]);
-                            acc[4 * q + 2] = fmaf(w.z, a[u], acc[4 * q + 2]);
-                            acc[4 * q + 3] = fmaf(w.w, a[u], acc[4 * q + 3]);
-                        }
+                for (int q = 0; q < SSB_DEC_NJ / 4; ++q) {
+                    if (q < nq) {
+                        const float4 w = w4[q];
+                        acc[4 * q + 0] = fmaf(w.x, a, acc[4 * q + 0]);
+                        acc[4 * q + 1] = fmaf(w.y, a, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(w.z, a, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(w.w, a, acc[4 * q + 3]);
                     }
                 }
             }
         }
-        __syncthreads();   // red is free (previous pass consumed)
+        // fold the four warps in warp order: ((w0 + w1) + w2) + w3
+        for (int w = 0; w < 4; ++w) {
+            if (warp == w) {
 #pragma unroll
-        for (int j = 0; j < SSB_DEC_NJ; ++j) red[warp][j][lane] = acc[j];
-        __syncthreads();
-        for (int j = warp; j < 4 * nq; j += 4) {
-            if (jb + j < size_out) {
-                const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
-                if (n_chunks == 1) vg[(size_t)(out_vec + jb + j) * 32] = t;
-                else pg[(size_t)(part_off + chunk * size_out + jb + j) * 32] = t;
+                for (int j = 0; j < SSB_DEC_NJ; ++j) {
+                    if (j < 4 * nq) {
+                        const float t = (w == 0) ? acc[j] : fold[j * 32 + lane] + acc[j];
+                        if (w < 3) fold[j * 32 + lane] = t;
+                        else if (jb + j < size_out) {
+                            if (n_chunks == 1) vg[(size_t)(out_vec + jb + j) * 32] = t;
+                            else pg[(size_t)(part_off + chunk * size_out + jb + j) * 32] = t;
+                        }
+                    }
+                }
             }
+            __syncthreads();
         }
     }
     if (n_chunks == 1) return;
@@ -732,7 +766,7 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
     __syncthreads();
     if (!flag) return;
     __threadfence();
-    for (int j = threadIdx.x >> 5; j < size_out; j += 4) {
+    for (int j = warp; j < size_out; j += 4) {
         float t = 0.f;
         for (int ck = 0; ck < n_chunks; ++ck) t += __ldcg(pg + (size_t)(part_off + ck * size_out + j) * 32);
         vg[(size_t)(out_vec + j) * 32] = t;

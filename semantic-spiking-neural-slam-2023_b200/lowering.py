@@ -37,6 +37,7 @@ CSR_PAD = 8                 # CSR rows are padded to a multiple of this with (ro
 DEC_TILE = 8                # decoder output rows are padded to a multiple of this
 TARGET_CTAS = 148 * 8       # decode / PES launches are split until they offer ~8 CTAs per SM
 MAX_DEC_CHUNKS = 32
+DEC_SMEM_BYTES = 96 * 1024  # shared-memory budget of a k_decode chunk (weights + activities)
 
 NT_LIF, NT_LIFRATE, NT_RELU = 0, 1, 2
 
@@ -163,7 +164,10 @@ class _Lowerer:
                     self.dec_chunks[c] = int(max(1, min(want, ens.n_neurons // 32, MAX_DEC_CHUNKS)))
                 else:                  # k_decode: CTA = (decoder, trial group, neuron chunk), all outputs at once
                     want = -(-TARGET_CTAS // (max(1, n_static) * self.n_groups))
-                    self.dec_chunks[c] = int(max(1, min(want, ens.n_neurons // 32, MAX_DEC_CHUNKS)))
+                    jpad = -(-self._out_size(c) // DEC_TILE) * DEC_TILE
+                    per_max = max(1, DEC_SMEM_BYTES // (jpad * 4 + 128))   # weight + activity tile of a chunk
+                    need = -(-ens.n_neurons // per_max)
+                    self.dec_chunks[c] = int(max(need, min(want, max(1, ens.n_neurons // 32), MAX_DEC_CHUNKS)))
 
     @staticmethod
     def _out_size(c):
