@@ -70,7 +70,8 @@ void ssb_destroy(ssb_sim* s);
  * library stream; with profiling on, per-kernel-kind accumulated event times. */
 int ssb_set_profiling(ssb_sim* s, int on);
 int ssb_last_run_ms(ssb_sim* s, float* ms);
-/* kinds: 0 ens_small 1 ens_wide 2 decode 3 pes 4 cleanup_scan 5 cleanup_pick 6 gate 7 lin 8 advance 9 begin */
+/* kinds: 0 ens_small 1 ens_wide 2 decode 3 pes 4 cleanup_scan 5 cleanup_pick 6 gate 7 lin 8 advance 9 begin
+ *        10 ens_voja */
 int ssb_kernel_times(ssb_sim* s, float* ms_per_kind, long long* launches_per_kind, int n_kinds);
 long long ssb_total_launches(ssb_sim* s);
 /* CUDA-event marks on the library stream (4 slots) and the device time between two of them:

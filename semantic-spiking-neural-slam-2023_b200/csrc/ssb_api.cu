@@ -26,7 +26,7 @@ int fail(int code, const std::string& msg) {
             return fail(-2, std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
     } while (0)
 
-enum Kind { K_SMALL = 0, K_WIDE, K_DEC, K_PES, K_SCAN, K_PICK, K_GATE, K_LIN, K_ADV, K_BEGIN, K_NKINDS };
+enum Kind { K_SMALL = 0, K_WIDE, K_DEC, K_PES, K_SCAN, K_PICK, K_GATE, K_LIN, K_ADV, K_BEGIN, K_VOJA, K_NKINDS };
 
 struct HostArray {
     std::vector<unsigned char> bytes;
@@ -39,13 +39,34 @@ struct CleanupDev {
     int* idx = nullptr;
     const double* s64 = nullptr;
     int n_chunks = 0, rows_per_chunk = 0, tile_rows = 0;
+    // tensor-core scan (k_cleanup_scan_tc): pre-tiled 3xTF32 grid, K padded to a multiple of 8
+    bool tc = false;
+    float* stc = nullptr;
+    int kp = 0, n_tiles = 0;
 };
+
+// SSB_SCAN=ffma forces the FFMA scan (the measured comparison in DESIGN.md); default is the tcgen05 scan
+// whenever its operand tiles fit in shared memory.
+bool scan_tc_allowed(int dpad) {
+    const char* e = getenv("SSB_SCAN");
+    if (e && std::string(e) == "ffma") return false;
+    const int kp = (dpad + 7) / 8 * 8;
+    return (size_t)6 * SSB_TC_ROWS * kp * sizeof(float) <= 216 * 1024;
+}
 
 // Grid-scan geometry: a CTA scans rows_per_chunk grid rows in shared-memory tiles of tile_rows rows for 4 trial
 // groups.  Enough chunks for ~8 CTAs per SM (the scan is FFMA-bound and needs resident warps), at most
 // SSB_SCAN_MAX_CHUNKS (each chunk leaves TOPK candidates per trial); tiles of at most 24 KB.
 void scan_geometry(int G, int dpad, int n_groups, CleanupDev* cd) {
     const int group_ctas = (n_groups + 3) / 4;
+    if (scan_tc_allowed(dpad)) {   // one CTA per SM: trial blocks x grid chunks ~ 148
+        cd->tc = true;
+        cd->kp = (dpad + 7) / 8 * 8;
+        cd->n_tiles = (G + SSB_TC_ROWS - 1) / SSB_TC_ROWS;
+        cd->n_chunks = std::max(1, std::min(std::min(cd->n_tiles, SSB_SCAN_MAX_CHUNKS), 148 / std::max(1, group_ctas)));
+        cd->rows_per_chunk = cd->tile_rows = SSB_TC_ROWS;
+        return;
+    }
     int want = std::max(1, (148 * 8 + group_ctas - 1) / group_ctas);
     want = std::min(std::min(want, SSB_SCAN_MAX_CHUNKS), std::max(1, G / 16));
     int rows = (G + want - 1) / want;
@@ -57,6 +78,11 @@ void scan_geometry(int G, int dpad, int n_groups, CleanupDev* cd) {
 }
 
 }  // namespace
+
+struct LevelInfo {
+    int n_static = 0, n_voja = 0;   // wide ensembles of the level by kernel flavour
+    bool dec_needs_voja = false;    // a static decoder of the level reads a Voja ensemble's activities
+};
 
 struct ssb_sim {
     int device = 0;
@@ -86,6 +112,8 @@ struct ssb_sim {
     std::vector<cudaEvent_t> dep_pool;
     size_t dep_used = 0;
     int pes_level = -1;
+    bool pes_needs_static = false;
+    std::vector<LevelInfo> levels;
     long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
     std::vector<size_t> s64_offsets;
     int n_levels = 0, n_lin = 0, lin0 = 0, n_pes = 0, n_small_total = 0;
@@ -231,6 +259,40 @@ int collect_profile(ssb_sim* s) {
     return 0;
 }
 
+// Grid rows -> 3xTF32 operand tiles in UMMA core-matrix order: [tile][hi|lo][k/4][row/8][row%8][k%4].
+int build_scan_tiles(const float* S32, int G, int dpad, CleanupDev* cd) {
+    const int kp = cd->kp, part = SSB_TC_ROWS * kp;
+    std::vector<float> t((size_t)cd->n_tiles * 2 * part, 0.f);
+    for (int g = 0; g < G; ++g) {
+        const int tile = g / SSB_TC_ROWS, r = g % SSB_TC_ROWS;
+        float* hi = &t[(size_t)tile * 2 * part];
+        float* lo = hi + part;
+        for (int k = 0; k < dpad; ++k) {
+            const float x = S32[(size_t)g * dpad + k];
+            const float h = ssb_tf32_round(x);
+            const size_t off = ((size_t)(k / 4) * 16 + r / 8) * 32 + (r % 8) * 4 + k % 4;
+            hi[off] = h;
+            lo[off] = ssb_tf32_round(x - h);
+        }
+    }
+    SSB_CUDA(cudaMalloc((void**)&cd->stc, t.size() * sizeof(float)));
+    SSB_CUDA(cudaMemcpy(cd->stc, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void launch_scan_tc(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const CleanupDev& cd, int n_groups) {
+    dim3 grid(cd.n_chunks, (n_groups + 3) / 4);
+    const size_t smem = (size_t)6 * SSB_TC_ROWS * cd.kp * sizeof(float);
+    const int n_cand = cd.n_chunks * SSB_TOPK;
+    if (csr)
+        k_cleanup_scan_tc<true><<<grid, 128, smem, st>>>(c, desc, cd.stc, cd.cx, cd.pval, cd.pidx, cd.kp, cd.n_tiles, n_groups, n_cand);
+    else
+        k_cleanup_scan_tc<false><<<grid, 128, smem, st>>>(c, desc, cd.stc, cd.cx, cd.pval, cd.pidx, cd.kp, cd.n_tiles, n_groups, n_cand);
+}
+
+// relative near-tie band of the fp64 re-score: fp32 FFMA bound, or the 3xTF32 bound (3 * 2^-22 + accumulation)
+float scan_eps_floor(const CleanupDev& cd) { return cd.tc ? 1.6e-5f : 0.f; }
+
 template <int DP>
 void launch_scan(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const float* S, const CleanupDev& cd,
                  int dpad, int n_groups, int i_rel) {
@@ -248,7 +310,8 @@ void launch_scan(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, co
 
 void dispatch_scan(cudaStream_t st, bool csr, int dpad, int n_groups, const SsbCtx& c, const int* desc, const float* S,
                    const CleanupDev& cd, int i_rel) {
-    if (dpad == 56) launch_scan<56>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
+    if (cd.tc) launch_scan_tc(st, csr, c, desc, cd, n_groups);
+    else if (dpad == 56) launch_scan<56>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
     else if (dpad == 100) launch_scan<100>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
     else launch_scan<0>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
 }
@@ -257,6 +320,8 @@ void scan_smem_optin() {
     const int lim = 200 * 1024;
     cudaFuncSetAttribute(k_cleanup_scan<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_cleanup_scan<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_cleanup_scan_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_cleanup_scan_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 
 // Wide ensembles of one level: one launch per (kernel flavour, width class); the items of a launch are
@@ -298,12 +363,10 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
     }
 }
 
-void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, int i_rel) {
-    for (int v = 0; v < 2; ++v) {
-        launch_wide_class<56>(s, st, stage, v != 0, 0, i_rel);
-        launch_wide_class<100>(s, st, stage, v != 0, 1, i_rel);
-        launch_wide_class<0>(s, st, stage, v != 0, 2, i_rel);
-    }
+void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int i_rel) {
+    launch_wide_class<56>(s, st, stage, voja, 0, i_rel);
+    launch_wide_class<100>(s, st, stage, voja, 1, i_rel);
+    launch_wide_class<0>(s, st, stage, voja, 2, i_rel);
 }
 
 void wide_smem_optin() {
@@ -347,6 +410,14 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
 
 // One simulator step = this launch sequence; `i_rel` is the step's offset from the device-side step
 // counter dyn[0], which ssb_run_steps advances once per call (or once per replayed graph).
+//
+// Dependency streams (parallel branches of the captured graph):
+//   A  k_begin, the level's materialised rows (k_lin), narrow ensembles, final k_lin
+//   B  Voja-learned wide ensembles -> k_pes          (the two HBM-heavy streaming kernels)
+//   C  grid clean-up scan -> pick, gate
+//   D  static wide ensembles -> static decoders
+// A level's successor waits for C and D only: nothing inside a step reads what k_pes writes (its outputs
+// reach consumers through Lowpass filters, i.e. the final k_lin), so B joins A just before that launch.
 int one_step(ssb_sim* s, int i_rel) {
     const SsbCtx& c = s->ctx;
     const int G = s->n_groups;
@@ -357,32 +428,33 @@ int one_step(ssb_sim* s, int i_rel) {
         dim3 grid(((int)s->nt + 3) / 4, G);
         k_begin<<<grid, 128, 0, A>>>(c, i_rel);
     }
-    bool pes_done = s->n_pes == 0;
+    bool pes_done = s->n_pes == 0, b_used = false;
     for (int lvl = 0; lvl < s->n_levels; ++lvl) {
         const int* st = &s->h_stages[lvl * 12];
+        const LevelInfo& li = s->levels[lvl];
         if (st[11] > 0) {   // materialise this level's sink rows (ensemble / node inputs, PES errors)
             LaunchTimer t(s, K_LIN);
             dim3 grid((st[11] + 3) / 4, G);
             k_lin<<<grid, 128, 0, A>>>(c, s->d_lin_rows + st[10] * 3, s->d_lin_ab + st[10] * 2, st[11], i_rel);
         }
-        const bool useB = st[3] > 0 || st[5] > 0, useC = st[7] > 0, useD = st[9] > 0;
+        const bool pes_here = !pes_done && lvl == s->pes_level;
+        const bool useB = li.n_voja > 0 || pes_here;
+        const bool useC = st[7] > 0 || st[9] > 0;
+        const bool useD = li.n_static > 0 || st[5] > 0;
         if (useB) stream_dep(s, A, B);
         if (useC) stream_dep(s, A, C);
         if (useD) stream_dep(s, A, D);
-        if (st[1] > 0) {
-            LaunchTimer t(s, K_SMALL);
-            // items are sorted by neuron count (descending): the leading ones get a whole CTA per trial group
-            int n_split = 0;
-            while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
-            const int packed_warps = (st[1] - n_split) * G;
-            const int blocks = n_split * G + (packed_warps + 3) / 4;
-            k_ens_small<<<blocks, 128, 0, A>>>(c, s->d_small + st[0] * 9, st[1], n_split);
+        b_used = b_used || useB;
+        if (li.n_voja > 0) {
+            LaunchTimer t(s, K_VOJA);
+            launch_wide(s, B, st, true, i_rel);
         }
-        if (st[3] > 0) {
+        if (li.n_static > 0) {
             LaunchTimer t(s, K_WIDE);
-            launch_wide(s, B, st, i_rel);
+            launch_wide(s, D, st, false, i_rel);
         }
-        if (!pes_done && lvl == s->pes_level) {   // every PES pre-ensemble has produced its activities
+        if (pes_here) {   // every PES pre-ensemble has produced its activities
+            if (s->pes_needs_static && li.n_static > 0) stream_dep(s, D, B);
             launch_pes(s, B, i_rel);
             pes_done = true;
         }
@@ -397,15 +469,26 @@ int one_step(ssb_sim* s, int i_rel) {
             {
                 LaunchTimer t(s, K_PICK);
                 k_cleanup_pick<<<G, 256, 0, C>>>(d[1], d[2], cd.n_chunks * SSB_TOPK, cd.cx, cd.pval, cd.pidx, cd.s64,
-                                                 s->d_W + d[3], s->vec, (int)s->nv, d[5], cd.idx, nullptr, 0, 0);
+                                                 s->d_W + d[3], s->vec, (int)s->nv, d[5], cd.idx, nullptr, 0, 0,
+                                                 scan_eps_floor(cd));
             }
         }
         if (st[9] > 0) {
             LaunchTimer t(s, K_GATE);
             dim3 grid(G, st[9]);
-            k_gate<<<grid, 256, 0, D>>>(c, s->d_gate, st[8], i_rel);
+            k_gate<<<grid, 256, 0, C>>>(c, s->d_gate, st[8], i_rel);
+        }
+        if (st[1] > 0) {
+            LaunchTimer t(s, K_SMALL);
+            // items are sorted by neuron count (descending): the leading ones get a whole CTA per trial group
+            int n_split = 0;
+            while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
+            const int packed_warps = (st[1] - n_split) * G;
+            const int blocks = n_split * G + (packed_warps + 3) / 4;
+            k_ens_small<<<blocks, 128, 0, A>>>(c, s->d_small + st[0] * 9, st[1], n_split);
         }
         if (st[5] > 0) {
+            if (li.dec_needs_voja) stream_dep(s, B, D);   // recorded after the Voja kernel (and k_pes, if any)
             LaunchTimer t(s, K_DEC);
             int max_chunks = 1;
             size_t smem = 0;
@@ -416,12 +499,12 @@ int one_step(ssb_sim* s, int i_rel) {
                 smem = std::max(smem, (per * d[2] + per * 32 + 56 * 32) * sizeof(float));
             }
             dim3 grid(max_chunks, G, st[5]);
-            k_decode<<<grid, 128, smem, B>>>(c, s->d_dec, st[4]);
+            k_decode<<<grid, 128, smem, D>>>(c, s->d_dec, st[4]);
         }
-        if (useB) stream_dep(s, B, A);
         if (useC) stream_dep(s, C, A);
         if (useD) stream_dep(s, D, A);
     }
+    if (b_used) stream_dep(s, B, A);
     if (!pes_done) launch_pes(s, A, i_rel);
     if (s->n_lin > 0) {
         LaunchTimer t(s, K_LIN);
@@ -489,7 +572,13 @@ int ssb_create(int device, int n_trials, ssb_sim** out) {
     if (const char* e = getenv("SSB_DEBUG_SYNC")) s->debug_sync = e[0] == '1';
     if (s->debug_sync) s->use_graph = false;
     SSB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    for (auto& a : s->aux) SSB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    {   // the long HBM-streaming chain (B) and the decode chain (D) are scheduled ahead of the rest
+        int pr_lo = 0, pr_hi = 0;
+        SSB_CUDA(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[0], cudaStreamNonBlocking, pr_hi));
+        SSB_CUDA(cudaStreamCreateWithFlags(&s->aux[1], cudaStreamNonBlocking));
+        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[2], cudaStreamNonBlocking, pr_hi));
+    }
     if (const char* e = getenv("SSB_SERIAL")) s->parallel = e[0] != '1';
     SSB_CUDA(cudaEventCreate(&s->ev_run0));
     SSB_CUDA(cudaEventCreate(&s->ev_run1));
@@ -560,6 +649,27 @@ int ssb_finalize(ssb_sim* s) {
     s->h_cleanup = host_ints(s, "cleanup");
     s->h_pes = host_ints(s, "pes");
     if ((int)s->h_stages.size() != s->n_levels * 12) return fail(-1, "ssb_finalize: stages array has wrong size");
+    s->levels.assign(s->n_levels, LevelInfo());
+    for (int lvl = 0; lvl < s->n_levels; ++lvl) {
+        const int* st = &s->h_stages[lvl * 12];
+        LevelInfo& li = s->levels[lvl];
+        auto act_is_voja = [&](int act0) {   // does this activity range belong to a Voja ensemble of the level?
+            for (int i = 0; i < st[3]; ++i) {
+                const int* d = &s->h_big[(st[2] + i) * 16];
+                if (act0 >= d[4] && act0 < d[4] + d[0]) return (d[9] & 1) != 0;
+            }
+            return true;                     // produced at an earlier level: already joined, but stay safe
+        };
+        for (int i = 0; i < st[3]; ++i) {
+            if (s->h_big[(st[2] + i) * 16 + 9] & 1) li.n_voja++;
+            else li.n_static++;
+        }
+        for (int i = 0; i < st[5]; ++i)
+            if (act_is_voja(s->h_dec[(st[4] + i) * 9 + 3])) li.dec_needs_voja = true;
+        if (lvl == s->pes_level)
+            for (int i = 0; i < s->n_pes; ++i)
+                if (!act_is_voja(s->h_pes[i * 13 + 4])) s->pes_needs_static = true;
+    }
     for (size_t i = 0; i + 8 < s->h_small.size(); i += 9)
         if (s->h_small[i + 8] > SSB_SM_WMAX || (s->h_small[i + 8] & 3))
             return fail(-1, "ssb_finalize: narrow-ensemble weight stride out of range");
@@ -603,6 +713,10 @@ int ssb_finalize(ssb_sim* s) {
         if (s64_off + need <= s64_total) {
             cd.s64 = s->d_s64 + s64_off;
             s64_off += need;
+        }
+        if (cd.tc) {
+            const float* hW = reinterpret_cast<const float*>(s->arrays["weights"].bytes.data());
+            if (build_scan_tiles(hW + d[3], d[0], d[2], &cd)) return -2;
         }
     }
     // opt-in to large dynamic shared memory for very wide ensembles (d = 649)
@@ -804,6 +918,7 @@ void ssb_destroy(ssb_sim* s) {
         if (cd.cx) cudaFree(cd.cx);
         if (cd.pval) cudaFree(cd.pval);
         if (cd.pidx) cudaFree(cd.pidx);
+        if (cd.stc) cudaFree(cd.stc);
     }
     if (s->step_graph) cudaGraphExecDestroy(s->step_graph);
     for (auto e : s->dep_pool) cudaEventDestroy(e);
@@ -931,6 +1046,7 @@ int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* q
     SSB_CUDA(cudaMalloc((void**)&pidx, (size_t)cd.n_chunks * SSB_TOPK * B * sizeof(int)));
     SSB_CUDA(cudaMalloc((void**)&didx, (size_t)B * sizeof(int)));
     SSB_CUDA(cudaMemcpy(dS32, s32.data(), s32.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (cd.tc && build_scan_tiles(s32.data(), G, dpad, &cd)) return -2;
     SSB_CUDA(cudaMemcpy(dS64, sample_ssps, (size_t)G * d * sizeof(double), cudaMemcpyHostToDevice));
     SSB_CUDA(cudaMemcpy(dq, queries, (size_t)n_q * d * sizeof(double), cudaMemcpyHostToDevice));
     scan_smem_optin();
@@ -950,10 +1066,11 @@ int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* q
         dispatch_scan(nullptr, false, dpad, B / 32, c, ddesc, dS32, cd, 0);
         // near-ties are re-scored against the float64 grid with the float64 query
         k_cleanup_pick<<<B / 32, 256>>>(d, dpad, cd.n_chunks * SSB_TOPK, cx, pval, pidx, dS64, dS32, nullptr, 0, 0, didx, dq,
-                                        q0, n_q);
+                                        q0, n_q, scan_eps_floor(cd));
         SSB_CUDA(cudaGetLastError());
         SSB_CUDA(cudaMemcpy(idx_out + q0, didx, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));
     }
+    if (cd.stc) cudaFree(cd.stc);
     cudaFree(dS32);
     cudaFree(dS64);
     cudaFree(dq);

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #define SSB_TOPK 4
 #define SSB_SCAN_MAX_CHUNKS 512
@@ -1022,6 +1023,219 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
     }
 }
 
+// --------------------------------------------------------------------------------------
+// Tensor-core grid scan (tcgen05 + TMEM).  The similarity scores of a trial block against the sample
+// grid are a real GEMM with weights shared by every trial: D[trial][grid row] = X[trial][k] . S[grid row][k].
+// One CTA owns 128 trials (4 trial groups = the 128 TMEM lanes) and every n_chunks-th tile of 128 grid rows.
+//   A = X  (128 x KP, K-major)  built once per CTA in shared memory from the materialised vec rows,
+//   B = S  (128 x KP, K-major)  pre-tiled on the host in the UMMA core-matrix order, fetched by one TMA bulk
+//                               copy per tile into a two-stage ring,
+//   D      (128 lanes x 128 columns fp32) double-buffered in TMEM: the MMAs of tile i+1 run while the four
+//                               warps drain tile i with tcgen05.ld and keep a per-trial top-4.
+// fp32 accuracy comes from the 3xTF32 split: x = x_hi + x_lo with both parts exactly representable in
+// TF32, D = X_lo.S_hi + X_hi.S_lo + X_hi.S_hi (the dropped lo.lo term is < 2^-22 relative).  Near-ties are
+// still re-scored in fp64 by k_cleanup_pick, so the chosen index equals the float64 argmax.
+//
+// Shared-memory operand layout (UMMA "interleave" / no-swizzle, K-major): 8 rows x 16 bytes core matrices,
+//   float offset(row r, column k) = ((k / 4) * 16 + r / 8) * 32 + (r % 8) * 4 + k % 4
+// => stride between 8-row groups SBO = 128 B, stride between 16-byte K chunks LBO = 2048 B.
+#define SSB_TC_ROWS 128
+
+__host__ __device__ __forceinline__ float ssb_tf32_round(float x) {   // round-to-nearest-even to a 10-bit mantissa
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(x);
+#else
+    uint32_t u;
+    memcpy(&u, &x, 4);
+#endif
+    u += 0xfffu + ((u >> 13) & 1u);
+    u &= 0xffffe000u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+#endif
+}
+
+__device__ __forceinline__ uint64_t ssb_umma_desc(const void* smem_ptr) {
+    const uint32_t a = ssb_smem(smem_ptr);
+    return (uint64_t)((a >> 4) & 0x3fffu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void ssb_umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void ssb_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    // the registers are valid only after wait::ld; tying them to the wait keeps every use behind it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void ssb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ssb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Stc: [n_tiles][2 (hi, lo)][KP/4][16][8][4] floats.  dynamic smem: (2 + 2*2) * 128 * KP floats.
+// desc: G d dpad s_off in_row0 out_vec
+template <bool CSR_INPUT>
+__global__ void __launch_bounds__(128, 1)
+k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__ Stc, float* __restrict__ cx,
+                  float* __restrict__ pval, int* __restrict__ pidx, int KP, int n_tiles, int n_groups, int n_cand) {
+    extern __shared__ __align__(1024) float sm[];
+    __shared__ unsigned long long full[2], done[2];
+    __shared__ uint32_t tmem_slot;
+    const int G = d[0], dims = d[1], dpad = d[2], in_row0 = d[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int group = blockIdx.y * 4 + warp;
+    const bool live = group < n_groups;
+    const int g = live ? group : 0;
+    const int chunk = blockIdx.x, n_chunks = gridDim.x;
+    const int my_tiles = chunk < n_tiles ? (n_tiles - chunk + n_chunks - 1) / n_chunks : 0;
+    const int part_floats = SSB_TC_ROWS * KP;               // one operand part (hi or lo)
+    const uint32_t tile_bytes = 2u * part_floats * 4u;      // hi + lo
+    float* sA = sm;                                         // [2][part]
+    float* sB = sm + 2 * part_floats;                       // [2 stages][2][part]
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (threadIdx.x == 0) {
+        ssb_mbar_init(&full[0], 1);
+        ssb_mbar_init(&full[1], 1);
+        ssb_mbar_init(&done[0], 1);
+        ssb_mbar_init(&done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 2 && i < my_tiles; ++i) {
+            ssb_mbar_expect_tx(&full[i], tile_bytes);
+            ssb_bulk_g2s(sB + (size_t)i * 2 * part_floats, Stc + (size_t)(chunk + i * n_chunks) * 2 * part_floats, tile_bytes,
+                         &full[i]);
+        }
+    }
+    {   // A operand: this thread's trial is row r of the tile; four K columns per 16-byte store
+        const int r = threadIdx.x;
+        const float* vg = ssb_grp(c.vec, c.nv, g, lane);
+        float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
+        float* a_hi = sA + (r >> 3) * 32 + (r & 7) * 4;
+        float* a_lo = a_hi + part_floats;
+        for (int k4 = 0; k4 < KP / 4; ++k4) {
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = k4 * 4 + e;
+                float xv = 0.f;
+                if (live && k < dims) xv = CSR_INPUT ? vg[(size_t)(in_row0 + k) * 32] : cxg[(size_t)k * 32];
+                if (CSR_INPUT && live && blockIdx.x == 0 && k < dpad) cxg[(size_t)k * 32] = xv;
+                x[e] = xv;
+            }
+            float4 hi, lo;
+            hi.x = ssb_tf32_round(x[0]);
+            hi.y = ssb_tf32_round(x[1]);
+            hi.z = ssb_tf32_round(x[2]);
+            hi.w = ssb_tf32_round(x[3]);
+            lo.x = ssb_tf32_round(x[0] - hi.x);
+            lo.y = ssb_tf32_round(x[1] - hi.y);
+            lo.z = ssb_tf32_round(x[2] - hi.z);
+            lo.w = ssb_tf32_round(x[3] - hi.w);
+            *reinterpret_cast<float4*>(a_hi + (size_t)k4 * 16 * 32) = hi;
+            *reinterpret_cast<float4*>(a_lo + (size_t)k4 * 16 * 32) = lo;
+        }
+    }
+    ssb_fence_async();            // generic-proxy stores of A -> visible to the tensor core (async proxy)
+    ssb_tc_fence_before();
+    __syncthreads();
+    ssb_tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SSB_TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto issue_mma = [&](int i) {   // one thread: wait for the tile, queue its 3 * KP/8 MMAs, commit
+        const int s = i & 1;
+        ssb_mbar_wait(&full[s], (uint32_t)(i >> 1) & 1u);
+        ssb_tc_fence_after();
+        const float* b_hi = sB + (size_t)s * 2 * part_floats;
+        const float* b_lo = b_hi + part_floats;
+        const uint32_t dst = tmem + (uint32_t)s * SSB_TC_ROWS;
+        for (int j = 0; j < KP / 8; ++j) {
+            const size_t off = (size_t)j * 2 * 16 * 32;     // two 16-byte K chunks per MMA
+            const uint64_t ah = ssb_umma_desc(sA + off), al = ssb_umma_desc(sA + part_floats + off);
+            const uint64_t bh = ssb_umma_desc(b_hi + off), bl = ssb_umma_desc(b_lo + off);
+            ssb_umma_tf32(dst, al, bh, idesc, j > 0);
+            ssb_umma_tf32(dst, ah, bl, idesc, 1);
+            ssb_umma_tf32(dst, ah, bh, idesc, 1);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ssb_smem(&done[s]))
+                     : "memory");
+    };
+    SsbTop top;
+    ssb_top_init(top);
+    if (threadIdx.x == 0 && my_tiles > 0) issue_mma(0);
+    __syncwarp();
+    for (int i = 0; i < my_tiles; ++i) {
+        const int s = i & 1;
+        if (threadIdx.x == 0 && i + 1 < my_tiles) issue_mma(i + 1);
+        __syncwarp();
+        ssb_mbar_wait(&done[s], (uint32_t)(i >> 1) & 1u);
+        ssb_tc_fence_after();
+        if (threadIdx.x == 0 && i + 2 < my_tiles) {           // the MMAs of tile i have consumed stage s
+            ssb_mbar_expect_tx(&full[s], tile_bytes);
+            ssb_bulk_g2s(sB + (size_t)s * 2 * part_floats, Stc + (size_t)(chunk + (i + 2) * n_chunks) * 2 * part_floats,
+                         tile_bytes, &full[s]);
+        }
+        __syncwarp();
+        const int row0 = (chunk + i * n_chunks) * SSB_TC_ROWS;
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)s * SSB_TC_ROWS;
+#pragma unroll 1
+        for (int b = 0; b < SSB_TC_ROWS / 32; ++b) {
+            float v[32];
+            ssb_tmem_ld32(taddr + b * 32, v);
+            const int gg0 = row0 + b * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (gg0 + j < G) ssb_top_push(top, v[j], gg0 + j);
+        }
+        ssb_tc_fence_before();
+        __syncthreads();           // every warp has drained TMEM buffer s before tile i+2 is accumulated into it
+        ssb_tc_fence_after();
+    }
+    if (live) {
+        float* pv = pval + ((size_t)g * n_cand) * 32 + lane;
+        int* pi = pidx + ((size_t)g * n_cand) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < SSB_TOPK; ++i) {
+            pv[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = top.v[i];
+            pi[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = top.g[i];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
 // CTA = one trial group x 8 warps: warps split the candidate list, merge through shared memory, then
 // candidates within eps of the fp32 maximum are re-scored in fp64 (S64 is the float64 grid) and
 // the winning index / grid row are written.  out_base (may be null) is a group-tiled arena.
@@ -1029,7 +1243,7 @@ __global__ void __launch_bounds__(256)
 k_cleanup_pick(int dims, int dpad, int ncand, const float* __restrict__ cx, const float* __restrict__ pval,
                const int* __restrict__ pidx, const double* __restrict__ S64, const float* __restrict__ S32,
                float* __restrict__ out_base, int out_rows_per_group, int out_row0, int* __restrict__ out_idx,
-               const double* __restrict__ q64, long long q0, long long n_q) {
+               const double* __restrict__ q64, long long q0, long long n_q, float eps_floor_rel) {
     __shared__ float sv[8][32];
     __shared__ int sg[8][32];
     __shared__ float sn[8][32];
@@ -1081,7 +1295,8 @@ k_cleanup_pick(int dims, int dpad, int ncand, const float* __restrict__ cx, cons
         xn += sn[w][lane];
     }
     // fp32 dot-product error bound: ~dims * 2^-24 * |S_g||x| with |S_g| = 1
-    const float eps = 4.0f * (float)dims * 5.97e-8f * sqrtf(xn) + 1e-30f;
+    // (the 3xTF32 tensor-core scan passes its own relative floor: dropped lo.lo terms + fp32 accumulation)
+    const float eps = fmaxf(4.0f * (float)dims * 5.97e-8f, eps_floor_rel) * sqrtf(xn) + 1e-30f;
     int n_close = 0;
     for (int i0 = warp; i0 < ncand; i0 += 64) {
         float v[8];

@@ -688,11 +688,13 @@ class _Lowerer:
                           n_table_words=NT, n_probe_words=n_probe_rows, n_small=n_small, n_big=n_big,
                           n_levels=n_levels, csr_nnz=len(csr_idx), n_afilt=n_afilt, n_act=n_act)
         n_small_neurons = int(sum(e.n_neurons for e in self.ensembles if self.is_small[e]))
+        n_voja_neurons = int(sum(e.n_neurons for e in voja_rule))
         # SURVEY.md §8(d) traffic model split by the kernel that owns each stream (bytes per trial-step)
         plan.stats["n_small_neurons"] = n_small_neurons
         plan.stats["bytes_by_kind"] = {
             "ens_small": 16 * n_small_neurons,
-            "ens_wide": 16 * (nn - n_small_neurons) + 8 * n_lenc,
+            "ens_wide": 16 * (nn - n_small_neurons - n_voja_neurons),
+            "ens_voja": 16 * n_voja_neurons + 8 * n_lenc,
             "pes": 8 * n_ldec,
             "lin": 8 * (NF + n_afilt) + 4 * n_probe_rows,
             "inputs": 4 * NT,
