@@ -114,6 +114,7 @@ struct ssb_sim {
     int pes_level = -1;
     bool pes_needs_static = false;
     std::vector<LevelInfo> levels;
+    std::map<int, int> wide_chunk_cache;   // launch geometry of the wide-ensemble kernels, decided once
     long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
     std::vector<size_t> s64_offsets;
     int n_levels = 0, n_lin = 0, lin0 = 0, n_pes = 0, n_small_total = 0;
@@ -328,7 +329,7 @@ void scan_smem_optin() {
 // passed by value.  The chunk (neurons per CTA) shrinks for very wide ensembles so that the staged
 // encoder tile fits in shared memory.
 template <int DP>
-void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int cls, int i_rel) {
+void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int cls, int i_rel, bool dry = false) {
     SsbItemList items;
     items.n = 0;
     int max_n = 0, max_dpad = 0, max_dims = 0, max_jn = 0;
@@ -343,12 +344,32 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
         max_jn = std::max(max_jn, d[11]);
     }
     if (items.n == 0) return;
+    const int units = s->n_groups * items.n;          // CTAs per neuron chunk
     if (!voja) {
-        int chunk = 64;
+        // neurons per CTA: the multiple of 4 that wastes the least time on partial waves (resident CTAs per SM
+        // from the occupancy calculator, since the staged encoder tile grows with the chunk)
         auto smem_of = [&](int ch) {
             return (size_t)(ch * max_dpad + ch + ch * max_jn + ch * 32 + max_dpad * 32 + max_jn * 32) * sizeof(float);
         };
-        while (chunk > 8 && smem_of(chunk) > 64 * 1024) chunk >>= 1;
+        const int key = (DP << 20) | (max_n << 6) | (units & 63);
+        auto it = s->wide_chunk_cache.find(key);
+        int chunk = it == s->wide_chunk_cache.end() ? 0 : it->second;
+        if (!chunk) {
+            long long best_cost = -1;
+            for (int ch = 16; ch <= 128; ch += 4) {
+                if (smem_of(ch) > 96 * 1024) break;
+                int occ = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wide_static<DP>, 128, smem_of(ch));
+                if (occ < 1) break;
+                const long long ctas = (long long)((max_n + ch - 1) / ch) * units;
+                const long long waves = (ctas + 148LL * occ - 1) / (148LL * occ);
+                const long long cost = waves * (ch + 12);
+                if (best_cost < 0 || cost < best_cost) best_cost = cost, chunk = ch;
+            }
+            if (!chunk) chunk = 16;
+            s->wide_chunk_cache[key] = chunk;
+        }
+        if (dry) return;
         dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
         k_wide_static<DP><<<grid, 128, smem_of(chunk), st>>>(s->ctx, s->d_big, items, chunk, i_rel);
     } else {
@@ -357,16 +378,29 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
             return (size_t)(max_dpad * 32 + max_jn * 32 + nw * 2 * max_dims * 32) * sizeof(float);
         };
         while (nwarps > 1 && smem_of(nwarps) > 200 * 1024) nwarps >>= 1;
-        const int chunk = 16 * nwarps;
+        // one wave: every resident CTA slot gets one contiguous neuron range of a trial group
+        const int key = (1 << 30) | (DP << 20) | (max_n << 6) | (units & 63);
+        auto it = s->wide_chunk_cache.find(key);
+        int chunk = it == s->wide_chunk_cache.end() ? 0 : it->second;
+        if (!chunk) {
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wide_voja<DP>, 32 * nwarps, smem_of(nwarps));
+            const int slots = 148 * std::max(1, occ);
+            const int per_unit = std::max(1, slots / std::max(1, units));
+            chunk = (max_n + per_unit - 1) / per_unit;
+            chunk = std::max(nwarps, (chunk + nwarps - 1) / nwarps * nwarps);
+            s->wide_chunk_cache[key] = chunk;
+        }
+        if (dry) return;
         dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
         k_wide_voja<DP><<<grid, 32 * nwarps, smem_of(nwarps), st>>>(s->ctx, s->d_big, items, chunk, i_rel);
     }
 }
 
-void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int i_rel) {
-    launch_wide_class<56>(s, st, stage, voja, 0, i_rel);
-    launch_wide_class<100>(s, st, stage, voja, 1, i_rel);
-    launch_wide_class<0>(s, st, stage, voja, 2, i_rel);
+void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int i_rel, bool dry = false) {
+    launch_wide_class<56>(s, st, stage, voja, 0, i_rel, dry);
+    launch_wide_class<100>(s, st, stage, voja, 1, i_rel, dry);
+    launch_wide_class<0>(s, st, stage, voja, 2, i_rel, dry);
 }
 
 void wide_smem_optin() {
@@ -722,6 +756,11 @@ int ssb_finalize(ssb_sim* s) {
     // opt-in to large dynamic shared memory for very wide ensembles (d = 649)
     wide_smem_optin();
     scan_smem_optin();
+
+    for (int lvl = 0; lvl < s->n_levels; ++lvl) {   // decide the wide-ensemble launch geometry now (occupancy queries)
+        launch_wide(s, nullptr, &s->h_stages[lvl * 12], false, 0, true);
+        launch_wide(s, nullptr, &s->h_stages[lvl * 12], true, 0, true);
+    }
 
     SsbCtx& c = s->ctx;
     c.G = s->n_groups;

@@ -1138,33 +1138,44 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
                          &full[i]);
         }
     }
-    {   // A operand: this thread's trial is row r of the tile; four K columns per 16-byte store
+    {   // A operand: this thread's trial is row r of the tile; four K columns per 16-byte store.
+        // Loads are issued 32 at a time (8 chunks of 4 columns) before anything consumes them.
         const int r = threadIdx.x;
         const float* vg = ssb_grp(c.vec, c.nv, g, lane);
         float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
         float* a_hi = sA + (r >> 3) * 32 + (r & 7) * 4;
         float* a_lo = a_hi + part_floats;
-        for (int k4 = 0; k4 < KP / 4; ++k4) {
-            float x[4];
+        const float* src = CSR_INPUT ? vg + (size_t)in_row0 * 32 : cxg;
+        const bool copy_q = CSR_INPUT && live && blockIdx.x == 0;
+        for (int k0 = 0; k0 < KP; k0 += 32) {
+            float x[32];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = k4 * 4 + e;
-                float xv = 0.f;
-                if (live && k < dims) xv = CSR_INPUT ? vg[(size_t)(in_row0 + k) * 32] : cxg[(size_t)k * 32];
-                if (CSR_INPUT && live && blockIdx.x == 0 && k < dpad) cxg[(size_t)k * 32] = xv;
-                x[e] = xv;
+            for (int e = 0; e < 32; ++e) {
+                const int k = k0 + e;
+                x[e] = (live && k < dims) ? src[(size_t)k * 32] : 0.f;
             }
-            float4 hi, lo;
-            hi.x = ssb_tf32_round(x[0]);
-            hi.y = ssb_tf32_round(x[1]);
-            hi.z = ssb_tf32_round(x[2]);
-            hi.w = ssb_tf32_round(x[3]);
-            lo.x = ssb_tf32_round(x[0] - hi.x);
-            lo.y = ssb_tf32_round(x[1] - hi.y);
-            lo.z = ssb_tf32_round(x[2] - hi.z);
-            lo.w = ssb_tf32_round(x[3] - hi.w);
-            *reinterpret_cast<float4*>(a_hi + (size_t)k4 * 16 * 32) = hi;
-            *reinterpret_cast<float4*>(a_lo + (size_t)k4 * 16 * 32) = lo;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = k0 + 4 * q;
+                if (k < KP) {
+                    float4 hi, lo;
+                    hi.x = ssb_tf32_round(x[4 * q + 0]);
+                    hi.y = ssb_tf32_round(x[4 * q + 1]);
+                    hi.z = ssb_tf32_round(x[4 * q + 2]);
+                    hi.w = ssb_tf32_round(x[4 * q + 3]);
+                    lo.x = ssb_tf32_round(x[4 * q + 0] - hi.x);
+                    lo.y = ssb_tf32_round(x[4 * q + 1] - hi.y);
+                    lo.z = ssb_tf32_round(x[4 * q + 2] - hi.z);
+                    lo.w = ssb_tf32_round(x[4 * q + 3] - hi.w);
+                    *reinterpret_cast<float4*>(a_hi + (size_t)(k >> 2) * 16 * 32) = hi;
+                    *reinterpret_cast<float4*>(a_lo + (size_t)(k >> 2) * 16 * 32) = lo;
+                }
+            }
+            if (copy_q) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (k0 + e < dpad) cxg[(size_t)(k0 + e) * 32] = x[e];
+            }
         }
     }
     ssb_fence_async();            // generic-proxy stores of A -> visible to the tensor core (async proxy)
@@ -1192,8 +1203,22 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ssb_smem(&done[s]))
                      : "memory");
     };
-    SsbTop top;
-    ssb_top_init(top);
+    // per-trial top-4 in registers, sorted by (value desc, index asc); scores arrive in ascending index order
+    float tv0 = -INFINITY, tv1 = -INFINITY, tv2 = -INFINITY, tv3 = -INFINITY;
+    int tg0 = 0x7fffffff, tg1 = 0x7fffffff, tg2 = 0x7fffffff, tg3 = 0x7fffffff;
+    auto push = [&](float val, int gi) {
+        if (val > tv3) {
+            const bool b0 = val > tv0, b1 = val > tv1, b2 = val > tv2;
+            tv3 = b2 ? tv2 : val;
+            tg3 = b2 ? tg2 : gi;
+            tv2 = b1 ? tv1 : (b2 ? val : tv2);
+            tg2 = b1 ? tg1 : (b2 ? gi : tg2);
+            tv1 = b0 ? tv0 : (b1 ? val : tv1);
+            tg1 = b0 ? tg0 : (b1 ? gi : tg1);
+            tv0 = b0 ? val : tv0;
+            tg0 = b0 ? gi : tg0;
+        }
+    };
     if (threadIdx.x == 0 && my_tiles > 0) issue_mma(0);
     __syncwarp();
     for (int i = 0; i < my_tiles; ++i) {
@@ -1215,9 +1240,14 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
             float v[32];
             ssb_tmem_ld32(taddr + b * 32, v);
             const int gg0 = row0 + b * 32;
+            if (gg0 + 32 <= G) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (gg0 + j < G) ssb_top_push(top, v[j], gg0 + j);
+                for (int j = 0; j < 32; ++j) push(v[j], gg0 + j);
+            } else {                                   // last tile: rows beyond the grid are padding
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (gg0 + j < G) push(v[j], gg0 + j);
+            }
         }
         ssb_tc_fence_before();
         __syncthreads();           // every warp has drained TMEM buffer s before tile i+2 is accumulated into it
@@ -1226,10 +1256,12 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
     if (live) {
         float* pv = pval + ((size_t)g * n_cand) * 32 + lane;
         int* pi = pidx + ((size_t)g * n_cand) * 32 + lane;
+        const float tv[4] = {tv0, tv1, tv2, tv3};
+        const int tg[4] = {tg0, tg1, tg2, tg3};
 #pragma unroll
         for (int i = 0; i < SSB_TOPK; ++i) {
-            pv[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = top.v[i];
-            pi[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = top.g[i];
+            pv[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = tv[i];
+            pi[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = tg[i];
         }
     }
     __syncthreads();

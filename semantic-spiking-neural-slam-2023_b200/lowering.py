@@ -35,9 +35,25 @@ SMALL_MAX_DIMS = 4
 SMALL_MAX_OUT = 8
 CSR_PAD = 8                 # CSR rows are padded to a multiple of this with (row 0, coefficient 0)
 DEC_TILE = 8                # decoder output rows are padded to a multiple of this
-TARGET_CTAS = 148 * 8       # decode / PES launches are split until they offer ~8 CTAs per SM
+N_SM = 148                  # B200
 MAX_DEC_CHUNKS = 32
 DEC_SMEM_BYTES = 96 * 1024  # shared-memory budget of a k_decode chunk (weights + activities)
+SMEM_PER_SM = 227 * 1024
+PES_CTAS_PER_SM = 4         # k_pes: 116 registers x 128 threads
+DEC_CTAS_PER_SM = 5         # k_decode: 96 registers x 128 threads (before its shared-memory limit)
+
+
+def _best_chunks(n, units, slots_of, k_min, k_max):
+    """Split a neuron range into k chunks so that the launch (units * k CTAs) wastes the least time on
+    partial waves: minimise ceil(CTAs / resident slots) * neurons per chunk."""
+    best, best_cost = k_min, None
+    for k in range(k_min, k_max + 1):
+        per = -(-n // k)
+        waves = -(-(units * k) // max(1, slots_of(per)))
+        cost = waves * (per + 8)            # + a fixed per-CTA cost (prologue, split-K epilogue)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = k, cost
+    return best
 
 NT_LIF, NT_LIFRATE, NT_RELU = 0, 1, 2
 
@@ -160,14 +176,19 @@ class _Lowerer:
                     self.dec_chunks[c] = 1
                 elif c in pes_conns:   # k_pes: CTA = (8-row tile, trial group, neuron chunk)
                     jtiles = -(-self._out_size(c) // DEC_TILE)
-                    want = -(-TARGET_CTAS // (jtiles * self.n_groups))
-                    self.dec_chunks[c] = int(max(1, min(want, ens.n_neurons // 32, MAX_DEC_CHUNKS)))
+                    k_max = int(max(1, min(ens.n_neurons // 32, MAX_DEC_CHUNKS)))
+                    self.dec_chunks[c] = _best_chunks(ens.n_neurons, jtiles * self.n_groups,
+                                                      lambda per: N_SM * PES_CTAS_PER_SM, 1, k_max)
                 else:                  # k_decode: CTA = (decoder, trial group, neuron chunk), all outputs at once
-                    want = -(-TARGET_CTAS // (max(1, n_static) * self.n_groups))
                     jpad = -(-self._out_size(c) // DEC_TILE) * DEC_TILE
                     per_max = max(1, DEC_SMEM_BYTES // (jpad * 4 + 128))   # weight + activity tile of a chunk
                     need = -(-ens.n_neurons // per_max)
-                    self.dec_chunks[c] = int(max(need, min(want, max(1, ens.n_neurons // 32), MAX_DEC_CHUNKS)))
+                    k_max = int(max(need, min(max(1, ens.n_neurons // 32), MAX_DEC_CHUNKS)))
+
+                    def slots(per, jpad=jpad):
+                        smem = per * (jpad * 4 + 128) + 56 * 32 * 4 + 1024
+                        return N_SM * max(1, min(DEC_CTAS_PER_SM, SMEM_PER_SM // smem))
+                    self.dec_chunks[c] = _best_chunks(ens.n_neurons, max(1, n_static) * self.n_groups, slots, need, k_max)
 
     @staticmethod
     def _out_size(c):

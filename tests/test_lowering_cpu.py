@@ -59,8 +59,12 @@ def test_slam_plan_matches_oracle(neuron_type, hint):
     chunks = int(plan.arrays["pes"][0][10])
     assert plan.scalars["n_part"] >= (chunks * so if chunks > 1 else 0)
     jtiles = -(-so // lowering.DEC_TILE)
-    want_chunks = -(-lowering.TARGET_CTAS // (jtiles * -(-hint // 32)))
-    assert chunks == max(1, min(want_chunks, n // 32, lowering.MAX_DEC_CHUNKS))
+    k_max = max(1, min(n // 32, lowering.MAX_DEC_CHUNKS))
+    assert 1 <= chunks <= k_max
+    # the split minimises (waves of resident CTAs) x (neurons per chunk)
+    slots = lowering.N_SM * lowering.PES_CTAS_PER_SM
+    cost = lambda k: -(-(jtiles * -(-hint // 32) * k) // slots) * (-(-n // k) + 8)
+    assert cost(chunks) == min(cost(k) for k in range(1, k_max + 1))
 
 
 def test_slamview_plan_matches_oracle():
