@@ -98,6 +98,12 @@ struct ssb_sim {
     int *d_small = nullptr, *d_big = nullptr, *d_dec = nullptr, *d_pes = nullptr, *d_cleanup = nullptr, *d_gate = nullptr;
     int* d_lin_rows = nullptr;
     float* d_lin_ab = nullptr;
+    // dense blocks of the row program (rows sharing one column list), found at finalize
+    int *d_dense_items = nullptr, *d_dense_desc = nullptr, *d_dense_cols = nullptr, *d_dense_rows = nullptr;
+    float* d_dense_T = nullptr;
+    struct LinSeg { int csr_row0 = 0, n_csr = 0, item0 = 0, n_items = 0; };
+    std::vector<LinSeg> lin_segs;            // one per level + the end-of-step segment
+    long long n_dense_rows = 0, n_dense_blocks = 0;
     float* d_ntypes = nullptr;
     double* d_s64 = nullptr;
     std::vector<int> h_stages, h_small, h_big, h_dec, h_cleanup, h_pes;
@@ -284,12 +290,15 @@ int build_scan_tiles(const float* S32, int G, int dpad, CleanupDev* cd) {
 void launch_scan_tc(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const CleanupDev& cd, int n_groups) {
     dim3 grid(cd.n_chunks, (n_groups + 3) / 4);
     const size_t smem = (size_t)6 * SSB_TC_ROWS * cd.kp * sizeof(float);
-    const int n_cand = cd.n_chunks * SSB_TOPK;
+    const int n_cand = cd.n_chunks * SSB_TOPK * 2;
     if (csr)
-        k_cleanup_scan_tc<true><<<grid, 128, smem, st>>>(c, desc, cd.stc, cd.cx, cd.pval, cd.pidx, cd.kp, cd.n_tiles, n_groups, n_cand);
+        k_cleanup_scan_tc<true><<<grid, 256, smem, st>>>(c, desc, cd.stc, cd.cx, cd.pval, cd.pidx, cd.kp, cd.n_tiles, n_groups, n_cand);
     else
-        k_cleanup_scan_tc<false><<<grid, 128, smem, st>>>(c, desc, cd.stc, cd.cx, cd.pval, cd.pidx, cd.kp, cd.n_tiles, n_groups, n_cand);
+        k_cleanup_scan_tc<false><<<grid, 256, smem, st>>>(c, desc, cd.stc, cd.cx, cd.pval, cd.pidx, cd.kp, cd.n_tiles, n_groups, n_cand);
 }
+
+// candidates per trial left by the scan (the tensor-core scan keeps two lists per chunk)
+int scan_n_cand(const CleanupDev& cd) { return cd.n_chunks * SSB_TOPK * (cd.tc ? 2 : 1); }
 
 // relative near-tie band of the fp64 re-score: fp32 FFMA bound, or the 3xTF32 bound (3 * 2^-22 + accumulation)
 float scan_eps_floor(const CleanupDev& cd) { return cd.tc ? 1.6e-5f : 0.f; }
@@ -442,6 +451,109 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
     k_pes<<<grid, 128, 0, st>>>(s->ctx, s->d_pes, max_chunks, i_rel);
 }
 
+// One k_lin launch = the dense items of a segment (x ceil(G/4) trial-group quads) + its CSR rows (x G groups).
+void launch_lin(ssb_sim* s, cudaStream_t st, int seg, int i_rel) {
+    const ssb_sim::LinSeg& L = s->lin_segs[seg];
+    const int G = s->n_groups;
+    const long long blocks = (long long)L.n_items * ((G + 3) / 4) + (long long)((L.n_csr + 3) / 4) * G;
+    if (blocks <= 0) return;
+    k_lin<<<(unsigned)blocks, 128, 0, st>>>(s->ctx, s->d_lin_rows + (size_t)L.csr_row0 * 5, s->d_lin_ab + (size_t)L.csr_row0 * 2,
+                                            L.n_csr, i_rel, s->d_dense_items + (size_t)L.item0 * 4, L.n_items, s->d_dense_desc,
+                                            s->d_dense_T, s->d_dense_cols, s->d_dense_rows);
+}
+
+// Split the row program of every launch segment into dense blocks and CSR rows.  Rows (of one view) with an
+// identical column list and at least SSB_DENSE_MIN_K entries form a block when there are >= SSB_DENSE_MIN_R of them.
+#define SSB_DENSE_MIN_K 16
+#define SSB_DENSE_MIN_R 8
+int build_lin_program(ssb_sim* s) {
+    const std::vector<int> rows3 = host_ints(s, "lin_rows"), ptr = host_ints(s, "csr_ptr");
+    const std::vector<int> e0 = host_ints(s, "csr_ent0"), e1 = host_ints(s, "csr_ent1");   // (row, coefficient bits) pairs
+    const float* ab = s->arrays.count("lin_ab") ? reinterpret_cast<const float*>(s->arrays["lin_ab"].bytes.data()) : nullptr;
+    const size_t n_rows = rows3.size() / 3;
+    if ((size_t)(s->lin0 + s->n_lin) != n_rows) return fail(-1, "ssb_finalize: lin_rows segments do not add up");
+    std::vector<int> rows5, items, ddesc, dcols, drows;
+    std::vector<float> ab2, dT;
+    s->lin_segs.assign(s->n_levels + 1, ssb_sim::LinSeg());
+    for (int seg = 0; seg <= s->n_levels; ++seg) {
+        const int r0 = seg < s->n_levels ? s->h_stages[seg * 12 + 10] : s->lin0;
+        const int nr = seg < s->n_levels ? s->h_stages[seg * 12 + 11] : s->n_lin;
+        ssb_sim::LinSeg& L = s->lin_segs[seg];
+        L.csr_row0 = (int)(rows5.size() / 5);
+        L.item0 = (int)(items.size() / 4);
+        // group candidate rows by (view, column list)
+        std::map<std::vector<int>, std::vector<int>> groups;
+        for (int r = r0; r < r0 + nr; ++r) {
+            const int src = rows3[r * 3], kind = rows3[r * 3 + 1];
+            if (kind == 2) continue;
+            if (src < 0 || (size_t)src + 1 >= ptr.size()) return fail(-1, "ssb_finalize: lin_rows CSR row out of range");
+            const int lo = ptr[src], hi = ptr[src + 1];
+            if (hi - lo < SSB_DENSE_MIN_K) continue;
+            std::vector<int> key;
+            key.reserve(hi - lo + 1);
+            key.push_back(kind == 4 ? 1 : 0);
+            for (int p = lo; p < hi; ++p) key.push_back(e0[(size_t)p * 2]);
+            groups[key].push_back(r);
+        }
+        std::vector<char> is_dense(nr, 0);
+        for (auto& kv : groups) {
+            const std::vector<int>& members = kv.second;
+            if ((int)members.size() < SSB_DENSE_MIN_R) continue;
+            const int K = (int)kv.first.size() - 1;
+            const int kpad = (K + SSB_DENSE_SLAB - 1) / SSB_DENSE_SLAB * SSB_DENSE_SLAB;
+            const int R = (int)members.size();
+            const int block = (int)(ddesc.size() / 8);
+            const int t_off = (int)dT.size(), cols_off = (int)dcols.size(), rows_off = (int)(drows.size() / 4);
+            const int lo0 = ptr[rows3[members[0] * 3]];
+            for (int par = 0; par < 2; ++par)
+                for (int k = 0; k < kpad; ++k) dcols.push_back(k < K ? (par ? e1 : e0)[(size_t)(lo0 + k) * 2] : 0);
+            for (int m : members) {
+                const int lo = ptr[rows3[m * 3]];
+                for (int k = 0; k < kpad; ++k) {
+                    float v = 0.f;
+                    if (k < K) memcpy(&v, &e0[(size_t)(lo + k) * 2 + 1], 4);
+                    dT.push_back(v);
+                }
+                int abits = 0, bbits = 0;
+                if (ab) {
+                    memcpy(&abits, &ab[(size_t)m * 2], 4);
+                    memcpy(&bbits, &ab[(size_t)m * 2 + 1], 4);
+                }
+                drows.insert(drows.end(), {rows3[m * 3 + 1], rows3[m * 3 + 2], abits, bbits});
+                is_dense[m - r0] = 1;
+            }
+            ddesc.insert(ddesc.end(), {R, kpad, t_off, cols_off, rows_off, 0, 0, 0});
+            for (int row0 = 0; row0 < R; row0 += SSB_DENSE_RCH)
+                items.insert(items.end(), {block, row0, std::min(SSB_DENSE_RCH, R - row0), 0});
+            s->n_dense_rows += R;
+            s->n_dense_blocks++;
+        }
+        for (int r = r0; r < r0 + nr; ++r) {
+            if (is_dense[r - r0]) continue;
+            const int src = rows3[r * 3], kind = rows3[r * 3 + 1];
+            rows5.insert(rows5.end(), {src, kind, rows3[r * 3 + 2], kind == 2 ? 0 : ptr[src], kind == 2 ? 0 : ptr[src + 1]});
+            ab2.push_back(ab ? ab[(size_t)r * 2] : 0.f);
+            ab2.push_back(ab ? ab[(size_t)r * 2 + 1] : 1.f);
+        }
+        L.n_csr = (int)(rows5.size() / 5) - L.csr_row0;
+        L.n_items = (int)(items.size() / 4) - L.item0;
+    }
+    auto up_i = [&](std::vector<int>& v, int** dst) {
+        v.resize(v.size() + 8, 0);
+        if (cudaMalloc((void**)dst, v.size() * sizeof(int)) != cudaSuccess) return 1;
+        return cudaMemcpy(*dst, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ? 1 : 0;
+    };
+    auto up_f = [&](std::vector<float>& v, float** dst) {
+        v.resize(v.size() + 8, 0.f);
+        if (cudaMalloc((void**)dst, v.size() * sizeof(float)) != cudaSuccess) return 1;
+        return cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ? 1 : 0;
+    };
+    if (up_i(rows5, &s->d_lin_rows) || up_f(ab2, &s->d_lin_ab) || up_i(items, &s->d_dense_items) || up_i(ddesc, &s->d_dense_desc) ||
+        up_i(dcols, &s->d_dense_cols) || up_i(drows, &s->d_dense_rows) || up_f(dT, &s->d_dense_T))
+        return fail(-2, "ssb_finalize: row program upload failed");
+    return 0;
+}
+
 // One simulator step = this launch sequence; `i_rel` is the step's offset from the device-side step
 // counter dyn[0], which ssb_run_steps advances once per call (or once per replayed graph).
 //
@@ -468,8 +580,7 @@ int one_step(ssb_sim* s, int i_rel) {
         const LevelInfo& li = s->levels[lvl];
         if (st[11] > 0) {   // materialise this level's sink rows (ensemble / node inputs, PES errors)
             LaunchTimer t(s, K_LIN);
-            dim3 grid((st[11] + 3) / 4, G);
-            k_lin<<<grid, 128, 0, A>>>(c, s->d_lin_rows + st[10] * 3, s->d_lin_ab + st[10] * 2, st[11], i_rel);
+            launch_lin(s, A, lvl, i_rel);
         }
         const bool pes_here = !pes_done && lvl == s->pes_level;
         const bool useB = li.n_voja > 0 || pes_here;
@@ -502,7 +613,7 @@ int one_step(ssb_sim* s, int i_rel) {
             }
             {
                 LaunchTimer t(s, K_PICK);
-                k_cleanup_pick<<<G, 256, 0, C>>>(d[1], d[2], cd.n_chunks * SSB_TOPK, cd.cx, cd.pval, cd.pidx, cd.s64,
+                k_cleanup_pick<<<G, 256, 0, C>>>(d[1], d[2], scan_n_cand(cd), cd.cx, cd.pval, cd.pidx, cd.s64,
                                                  s->d_W + d[3], s->vec, (int)s->nv, d[5], cd.idx, nullptr, 0, 0,
                                                  scan_eps_floor(cd));
             }
@@ -542,8 +653,7 @@ int one_step(ssb_sim* s, int i_rel) {
     if (!pes_done) launch_pes(s, A, i_rel);
     if (s->n_lin > 0) {
         LaunchTimer t(s, K_LIN);
-        dim3 grid((s->n_lin + 3) / 4, G);
-        k_lin<<<grid, 128, 0, A>>>(c, s->d_lin_rows + s->lin0 * 3, s->d_lin_ab + s->lin0 * 2, s->n_lin, i_rel);
+        launch_lin(s, A, s->n_levels, i_rel);
     }
     return 0;
 }
@@ -669,11 +779,8 @@ int ssb_finalize(ssb_sim* s) {
     s->n_pes = (int)(cnt / 13);
     if (upload_array(s, "cleanup", &s->d_cleanup)) return -2;
     if (upload_array(s, "gate", &s->d_gate)) return -2;
-    if (upload_array(s, "lin_rows", &s->d_lin_rows, &cnt)) return -2;
     s->lin0 = (int)iscalar(s, "lin0");
     s->n_lin = (int)iscalar(s, "n_lin");
-    if ((size_t)(s->lin0 + s->n_lin) * 3 != cnt) return fail(-1, "ssb_finalize: lin_rows segments do not add up");
-    if (upload_array(s, "lin_ab", &s->d_lin_ab)) return -2;
     if (upload_array(s, "ntypes", &s->d_ntypes)) return -2;
     if (upload_array(s, "cleanup_s64", &s->d_s64)) return -2;
     s->h_stages = host_ints(s, "stages");
@@ -683,6 +790,7 @@ int ssb_finalize(ssb_sim* s) {
     s->h_cleanup = host_ints(s, "cleanup");
     s->h_pes = host_ints(s, "pes");
     if ((int)s->h_stages.size() != s->n_levels * 12) return fail(-1, "ssb_finalize: stages array has wrong size");
+    if (int rc = build_lin_program(s)) return rc;
     s->levels.assign(s->n_levels, LevelInfo());
     for (int lvl = 0; lvl < s->n_levels; ++lvl) {
         const int* st = &s->h_stages[lvl * 12];
@@ -740,8 +848,8 @@ int ssb_finalize(ssb_sim* s) {
         CleanupDev& cd = s->cleanups[i];
         scan_geometry(d[0], d[2], s->n_groups, &cd);
         if (alloc_rows(&cd.cx, d[2], B)) return -2;
-        if (alloc_rows(&cd.pval, cd.n_chunks * SSB_TOPK, B)) return -2;
-        if (alloc_rows(reinterpret_cast<float**>(&cd.pidx), cd.n_chunks * SSB_TOPK, B)) return -2;
+        if (alloc_rows(&cd.pval, scan_n_cand(cd), B)) return -2;
+        if (alloc_rows(reinterpret_cast<float**>(&cd.pidx), scan_n_cand(cd), B)) return -2;
         cd.idx = s->cidx + (size_t)i * B;
         const size_t need = (size_t)d[0] * d[1];
         if (s64_off + need <= s64_total) {
@@ -949,7 +1057,7 @@ void ssb_destroy(ssb_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
-                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
                     s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1081,8 +1189,8 @@ int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* q
     SSB_CUDA(cudaMalloc((void**)&dS64, (size_t)G * d * sizeof(double)));
     SSB_CUDA(cudaMalloc((void**)&dq, (size_t)n_q * d * sizeof(double)));
     SSB_CUDA(cudaMalloc((void**)&cx, (size_t)dpad * B * sizeof(float)));
-    SSB_CUDA(cudaMalloc((void**)&pval, (size_t)cd.n_chunks * SSB_TOPK * B * sizeof(float)));
-    SSB_CUDA(cudaMalloc((void**)&pidx, (size_t)cd.n_chunks * SSB_TOPK * B * sizeof(int)));
+    SSB_CUDA(cudaMalloc((void**)&pval, (size_t)scan_n_cand(cd) * B * sizeof(float)));
+    SSB_CUDA(cudaMalloc((void**)&pidx, (size_t)scan_n_cand(cd) * B * sizeof(int)));
     SSB_CUDA(cudaMalloc((void**)&didx, (size_t)B * sizeof(int)));
     SSB_CUDA(cudaMemcpy(dS32, s32.data(), s32.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (cd.tc && build_scan_tiles(s32.data(), G, dpad, &cd)) return -2;
@@ -1104,7 +1212,7 @@ int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* q
         k_decode_prep<<<(B + 127) / 128, 128>>>(dq, cx, n_q, B, d, dpad, q0);
         dispatch_scan(nullptr, false, dpad, B / 32, c, ddesc, dS32, cd, 0);
         // near-ties are re-scored against the float64 grid with the float64 query
-        k_cleanup_pick<<<B / 32, 256>>>(d, dpad, cd.n_chunks * SSB_TOPK, cx, pval, pidx, dS64, dS32, nullptr, 0, 0, didx, dq,
+        k_cleanup_pick<<<B / 32, 256>>>(d, dpad, scan_n_cand(cd), cx, pval, pidx, dS64, dS32, nullptr, 0, 0, didx, dq,
                                         q0, n_q, scan_eps_floor(cd));
         SSB_CUDA(cudaGetLastError());
         SSB_CUDA(cudaMemcpy(idx_out + q0, didx, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));

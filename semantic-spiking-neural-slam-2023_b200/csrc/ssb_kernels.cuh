@@ -117,7 +117,7 @@ __device__ __forceinline__ float ssb_row(const int* __restrict__ ptr, const int2
 struct SsbNeuron {
     int type;                 // 0 LIF, 1 LIFRate, 2 RectifiedLinear
     bool fast;                // LIF with dt/tau_rc <= 1/16: polynomial expm1 / log1p, exact to fp32
-    float tau_rc, tau_ref, amp_dt, amp, dt, neg_inv_tau, c0;
+    float tau_rc, tau_ref, amp_dt, amp, dt, inv_dt, neg_dt_over_tau, c0;
 };
 
 __device__ __forceinline__ SsbNeuron ssb_neuron(const SsbCtx& c, int tid) {
@@ -130,7 +130,8 @@ __device__ __forceinline__ SsbNeuron ssb_neuron(const SsbCtx& c, int tid) {
     n.fast = p[5] != 0.f;
     n.dt = c.dt;
     n.amp_dt = p[4] / c.dt;
-    n.neg_inv_tau = (n.type == 0) ? -1.0f / p[1] : 0.f;
+    n.inv_dt = 1.0f / c.dt;
+    n.neg_dt_over_tau = (n.type == 0) ? -c.dt / p[1] : 0.f;
     n.c0 = p[2] + c.dt;       // tau_ref + dt
     return n;
 }
@@ -157,19 +158,22 @@ __device__ __forceinline__ float ssb_log1p_neg_small(float z) {
 }
 
 // nengo LIF.step on the packed state (App. A.4), branch-free.  Returns the output (0 or amplitude/dt).
-//   r = max(-s, 0) is the refractory time, v = max(s, 0) the voltage (one of them is always 0).
+//   m = min(s, 0) is minus the remaining refractory time, v = max(s, 0) the voltage (one of them is 0).
+//   nengo: refractory_time -= dt; delta = clip(dt - refractory_time, 0, dt)  =>  delta/dt = clip(2 + m/dt, 0, 1);
+//   the neuron stays refractory (state m + dt) exactly when that clip gives 0, i.e. refractory_time - dt >= dt.
 template <bool FAST>
 __device__ __forceinline__ float ssb_lif_packed(const SsbNeuron& n, float J, float& s) {
-    const float rp = fmaxf(-s, 0.f) - n.dt;                // refractory_time after "-= dt"
+    const float m = fminf(s, 0.f);
     float v = fmaxf(s, 0.f);
-    const float delta = fminf(fmaxf(n.dt - rp, 0.f), n.dt);
-    const float em1 = FAST ? ssb_expm1_small(delta * n.neg_inv_tau) : expm1f(delta * n.neg_inv_tau);
+    const float dn = __saturatef(fmaf(m, n.inv_dt, 2.f));  // delta / dt
+    const float x = dn * n.neg_dt_over_tau;                // -delta / tau_rc
+    const float em1 = FAST ? ssb_expm1_small(x) : expm1f(x);
     v = fmaf(v - J, em1, v);                               // v -= (J - v) * expm1(-delta / tau_rc)
     const bool spiked = v > 1.f;
     const float z = __fdividef(v - 1.f, J - 1.f);          // used only when spiked (then J > v > 1)
     const float lp = FAST ? ssb_log1p_neg_small(z) : log1pf(-z);
     const float r_new = fmaf(n.tau_rc, lp, n.c0);          // tau_ref + dt + tau_rc * log1p(-z) > 0
-    const float keep = (rp >= n.dt) ? -rp : fmaxf(v, 0.f);
+    const float keep = (dn > 0.f) ? fmaxf(v, 0.f) : m + n.dt;
     s = spiked ? -r_new : keep;
     return spiked ? n.amp_dt : 0.f;
 }
@@ -1103,9 +1107,12 @@ __device__ __forceinline__ void ssb_tc_fence_before() { asm volatile("tcgen05.fe
 __device__ __forceinline__ void ssb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // Stc: [n_tiles][2 (hi, lo)][KP/4][16][8][4] floats.  dynamic smem: (2 + 2*2) * 128 * KP floats.
+// 256 threads: warps w and w + 4 own the same TMEM lane quadrant (the 32 trials of group 4*blockIdx.y + w % 4)
+// and drain the two halves of every tile's columns, each into its own top-4 list (candidate slot
+// (2 * chunk + half) * 4 + i), so two warps per scheduler hide the insert latency.
 // desc: G d dpad s_off in_row0 out_vec
 template <bool CSR_INPUT>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__ Stc, float* __restrict__ cx,
                   float* __restrict__ pval, int* __restrict__ pidx, int KP, int n_tiles, int n_groups, int n_cand) {
     extern __shared__ __align__(1024) float sm[];
@@ -1113,7 +1120,8 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
     __shared__ uint32_t tmem_slot;
     const int G = d[0], dims = d[1], dpad = d[2], in_row0 = d[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int group = blockIdx.y * 4 + warp;
+    const int quad = warp & 3, half = warp >> 2;
+    const int group = blockIdx.y * 4 + quad;
     const bool live = group < n_groups;
     const int g = live ? group : 0;
     const int chunk = blockIdx.x, n_chunks = gridDim.x;
@@ -1140,14 +1148,14 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
     }
     {   // A operand: this thread's trial is row r of the tile; four K columns per 16-byte store.
         // Loads are issued 32 at a time (8 chunks of 4 columns) before anything consumes them.
-        const int r = threadIdx.x;
+        const int r = quad * 32 + lane;
         const float* vg = ssb_grp(c.vec, c.nv, g, lane);
         float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
         float* a_hi = sA + (r >> 3) * 32 + (r & 7) * 4;
         float* a_lo = a_hi + part_floats;
         const float* src = CSR_INPUT ? vg + (size_t)in_row0 * 32 : cxg;
         const bool copy_q = CSR_INPUT && live && blockIdx.x == 0;
-        for (int k0 = 0; k0 < KP; k0 += 32) {
+        for (int k0 = half * 32; k0 < KP; k0 += 64) {   // the two warps of a quadrant alternate 32-column blocks
             float x[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
@@ -1206,18 +1214,16 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
     // per-trial top-4 in registers, sorted by (value desc, index asc); scores arrive in ascending index order
     float tv0 = -INFINITY, tv1 = -INFINITY, tv2 = -INFINITY, tv3 = -INFINITY;
     int tg0 = 0x7fffffff, tg1 = 0x7fffffff, tg2 = 0x7fffffff, tg3 = 0x7fffffff;
-    auto push = [&](float val, int gi) {
-        if (val > tv3) {
-            const bool b0 = val > tv0, b1 = val > tv1, b2 = val > tv2;
-            tv3 = b2 ? tv2 : val;
-            tg3 = b2 ? tg2 : gi;
-            tv2 = b1 ? tv1 : (b2 ? val : tv2);
-            tg2 = b1 ? tg1 : (b2 ? gi : tg2);
-            tv1 = b0 ? tv0 : (b1 ? val : tv1);
-            tg1 = b0 ? tg0 : (b1 ? gi : tg1);
-            tv0 = b0 ? val : tv0;
-            tg0 = b0 ? gi : tg0;
-        }
+    auto push = [&](float val, int gi) {   // branch-free sorted insert (a strict > keeps the earlier index on ties)
+        const bool b0 = val > tv0, b1 = val > tv1, b2 = val > tv2, b3 = val > tv3;
+        tv3 = b2 ? tv2 : (b3 ? val : tv3);
+        tg3 = b2 ? tg2 : (b3 ? gi : tg3);
+        tv2 = b1 ? tv1 : (b2 ? val : tv2);
+        tg2 = b1 ? tg1 : (b2 ? gi : tg2);
+        tv1 = b0 ? tv0 : (b1 ? val : tv1);
+        tg1 = b0 ? tg0 : (b1 ? gi : tg1);
+        tv0 = b0 ? val : tv0;
+        tg0 = b0 ? gi : tg0;
     };
     if (threadIdx.x == 0 && my_tiles > 0) issue_mma(0);
     __syncwarp();
@@ -1234,9 +1240,9 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
         }
         __syncwarp();
         const int row0 = (chunk + i * n_chunks) * SSB_TC_ROWS;
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)s * SSB_TC_ROWS;
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * SSB_TC_ROWS;
 #pragma unroll 1
-        for (int b = 0; b < SSB_TC_ROWS / 32; ++b) {
+        for (int b = half * (SSB_TC_ROWS / 64); b < (half + 1) * (SSB_TC_ROWS / 64); ++b) {
             float v[32];
             ssb_tmem_ld32(taddr + b * 32, v);
             const int gg0 = row0 + b * 32;
@@ -1260,8 +1266,8 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
         const int tg[4] = {tg0, tg1, tg2, tg3};
 #pragma unroll
         for (int i = 0; i < SSB_TOPK; ++i) {
-            pv[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = tv[i];
-            pi[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = tg[i];
+            pv[(size_t)((blockIdx.x * 2 + half) * SSB_TOPK + i) * 32] = tv[i];
+            pi[(size_t)((blockIdx.x * 2 + half) * SSB_TOPK + i) * 32] = tg[i];
         }
     }
     __syncthreads();
@@ -1432,43 +1438,132 @@ __global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ 
 // the ping-pong buffer = nengo's update-after-read), probe samples, PES activity traces.
 // The same kernel materialises the sink rows of a dependency level into vec scratch before the level's
 // consumers run (kinds 3 / 4), so that no consumer evaluates CSR rows itself.
-// rows: [csr_row | act_row, kind, dst]; kind 0 filter, 1 probe, 2 activity trace, 3 / 4 materialise
-__global__ void __launch_bounds__(128) k_lin(SsbCtx c, const int* __restrict__ rows, const float* __restrict__ ab, int n_rows,
-                                              int i_rel) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = blockIdx.x * 4 + warp;
-#ifdef SSB_DEBUG
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
-        printf("k_lin: vec %p probe %p afilt %p act %p ent0 %p ent1 %p ptr %p rows %p ab %p dyn %p n_rows %d nv %d\n", c.vec,
-               c.probe, c.afilt, c.act, c.ent0, c.ent1, c.csr_ptr, rows, ab, c.dyn, n_rows, c.nv);
-#endif
-    if (r >= n_rows) return;
-    const int g = blockIdx.y;
-    const SsbStep s = ssb_step(c, i_rel);
-    float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    const int src = rows[r * 3], kind = rows[r * 3 + 1], dst = rows[r * 3 + 2];
-#ifdef SSB_DEBUG
-    if (lane == 0 && g == 0 && r < 4)
-        printf("k_lin r %d src %d kind %d dst %d lo %d hi %d step %lld\n", r, src, kind, dst, c.csr_ptr[src], c.csr_ptr[src + 1],
-               s.step);
-#endif
-    const float a = ab[r * 2], b = ab[r * 2 + 1];
+// kind 0 filter, 1 probe, 2 activity trace, 3 / 4 materialise (4: on the values the previous step read).
+//
+// Two CTA populations in one launch:
+//  * dense items (blockIdx.x < n_items * ceil(G/4)): rows that share one column list (the circular-convolution
+//    DFT matrices, to_Fourier / to_SSP, decoder-to-filter fans) form a dense block T[R][Kpad] found by the host.
+//    A CTA owns 8 rows of a block for 4 trial groups (one per warp): per 32-column slab the warp gathers its
+//    group's 32 source rows once into registers and the 8 x 32 coefficient slab is broadcast from shared memory,
+//    so a source row is fetched once per 8 sink rows instead of once per entry;
+//  * CSR rows (the rest): one warp per (row, group), entries as warp-uniform 8-byte loads.
+// Both accumulate in ascending column order with one accumulator per row (bit-identical results).
+#define SSB_DENSE_RCH 8
+#define SSB_DENSE_SLAB 32
+
+// dense desc: R Kpad t_off cols_off rows_off - - -   | item: block row0 nr -   | dense rows: kind dst a_bits b_bits
+__device__ __forceinline__ void ssb_lin_store(const SsbCtx& c, const SsbStep& s, float* vg, int g, int lane, int kind, int dst,
+                                              float a, float b, float u) {
     if (kind == 0) {
-        const float u = ssb_row(c.csr_ptr, s.ent_old, src, vg);
         const float y = vg[(size_t)(1 + dst + s.par_old) * 32];
         vg[(size_t)(1 + dst + s.par_new) * 32] = fmaf(b, u, a * y);
-    } else if (kind >= 3) {   // materialise a sink row for the consumers of this level (4: previous step's view)
-        vg[(size_t)dst * 32] = ssb_row(c.csr_ptr, kind == 3 ? s.ent_old : s.ent_new, src, vg);
-    } else if (kind == 1) {
-        const float u = ssb_row(c.csr_ptr, s.ent_old, src, vg);
+    } else if (kind >= 3) {
+        vg[(size_t)dst * 32] = u;
+    } else {
         float* pg = c.probe + (((size_t)g * c.probe_cap + (size_t)(s.step - c.dyn[2])) * c.n_probe + dst) * 32 + lane;
         __stcs(pg, u);
-    } else {
+    }
+}
+
+__global__ void __launch_bounds__(128) k_lin(SsbCtx c, const int* __restrict__ rows, const float* __restrict__ ab, int n_rows,
+                                              int i_rel, const int* __restrict__ items, int n_items,
+                                              const int* __restrict__ ddesc, const float* __restrict__ dT,
+                                              const int* __restrict__ dcols, const int* __restrict__ drows) {
+    __shared__ __align__(16) float s_t[2][SSB_DENSE_RCH][SSB_DENSE_SLAB];
+    __shared__ int s_col[2][SSB_DENSE_SLAB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const SsbStep s = ssb_step(c, i_rel);
+    const int gq_n = (c.G + 3) >> 2;
+    const int n_dense_ctas = n_items * gq_n;
+    if ((int)blockIdx.x < n_dense_ctas) {
+        const int item = blockIdx.x / gq_n, gq = blockIdx.x - item * gq_n;
+        const int* it = items + item * 4;
+        const int* d = ddesc + it[0] * 8;
+        const int row0 = it[1], nr = it[2];
+        const int kpad = d[1];
+        const float* __restrict__ T = dT + d[2] + (size_t)row0 * kpad;
+        const int* __restrict__ dr = drows + (size_t)(d[4] + row0) * 4;
+        const bool prev_view = dr[0] == 4;   // a block never mixes views
+        const int* __restrict__ cols = dcols + d[3] + ((s.odd ^ (prev_view ? 1 : 0)) ? kpad : 0);
+        const int g = gq * 4 + warp;
+        const bool live = g < c.G;
+        float* vg = ssb_grp(c.vec, c.nv, live ? g : 0, lane);
+        float acc[SSB_DENSE_RCH];
+#pragma unroll
+        for (int r = 0; r < SSB_DENSE_RCH; ++r) acc[r] = 0.f;
+        // slab 0 -> buffer 0
+        const int tr = threadIdx.x >> 3, tq = threadIdx.x & 7;          // thread -> (row, float4) of the slab, threads 0..63
+        float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+        int pc = 0;
+        if (threadIdx.x < 64 && tr < nr) pt = __ldg(reinterpret_cast<const float4*>(T + (size_t)tr * kpad) + tq);
+        if (threadIdx.x >= 96) pc = __ldg(cols + (threadIdx.x - 96));
+        if (threadIdx.x < 64) *reinterpret_cast<float4*>(&s_t[0][tr][tq * 4]) = pt;
+        if (threadIdx.x >= 96) s_col[0][threadIdx.x - 96] = pc;
+        __syncthreads();
+        const int n_slabs = kpad / SSB_DENSE_SLAB;
+        for (int sl = 0; sl < n_slabs; ++sl) {
+            const int bsel = sl & 1;
+            if (sl + 1 < n_slabs) {          // prefetch the next slab into registers
+                const int k0 = (sl + 1) * SSB_DENSE_SLAB;
+                if (threadIdx.x < 64) {
+                    pt = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (tr < nr) pt = __ldg(reinterpret_cast<const float4*>(T + (size_t)tr * kpad + k0) + tq);
+                }
+                if (threadIdx.x >= 96) pc = __ldg(cols + k0 + (threadIdx.x - 96));
+            }
+            float x[SSB_DENSE_SLAB];
+#pragma unroll
+            for (int e = 0; e < SSB_DENSE_SLAB; ++e) x[e] = ssb_ld_src(vg + (size_t)s_col[bsel][e] * 32);
+#pragma unroll
+            for (int r = 0; r < SSB_DENSE_RCH; ++r) {
+#pragma unroll
+                for (int q = 0; q < SSB_DENSE_SLAB / 4; ++q) {
+                    const float4 t = *reinterpret_cast<const float4*>(&s_t[bsel][r][q * 4]);
+                    acc[r] = fmaf(t.x, x[4 * q + 0], acc[r]);
+                    acc[r] = fmaf(t.y, x[4 * q + 1], acc[r]);
+                    acc[r] = fmaf(t.z, x[4 * q + 2], acc[r]);
+                    acc[r] = fmaf(t.w, x[4 * q + 3], acc[r]);
+                }
+            }
+            if (sl + 1 < n_slabs) {
+                if (threadIdx.x < 64) *reinterpret_cast<float4*>(&s_t[bsel ^ 1][tr][tq * 4]) = pt;
+                if (threadIdx.x >= 96) s_col[bsel ^ 1][threadIdx.x - 96] = pc;
+            }
+            __syncthreads();
+        }
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < SSB_DENSE_RCH; ++r) {
+                if (r < nr)
+                    ssb_lin_store(c, s, vg, g, lane, dr[r * 4], dr[r * 4 + 1], __int_as_float(dr[r * 4 + 2]),
+                                  __int_as_float(dr[r * 4 + 3]), acc[r]);
+            }
+        }
+        return;
+    }
+    // ---- CSR rows: flat index -> (row block, group)
+    const int cb = blockIdx.x - n_dense_ctas;
+    const int rblk = cb / c.G, g = cb - rblk * c.G;
+    const int r = rblk * 4 + warp;
+    if (r >= n_rows) return;
+    float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    const int* rp = rows + (size_t)r * 5;
+    const int src = rp[0], kind = rp[1], dst = rp[2];
+    const float a = ab[r * 2], b = ab[r * 2 + 1];
+    if (kind == 2) {
         float* fg = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane);
         const float y = fg[((size_t)s.odd * c.n_afilt + dst) * 32];
         const float u = ssb_grp(c.act, c.n_act, g, lane)[(size_t)src * 32];
         fg[((size_t)(1 - s.odd) * c.n_afilt + dst) * 32] = fmaf(b, u, a * y);
+        return;
     }
+    const int2* __restrict__ ent = kind == 4 ? s.ent_new : s.ent_old;
+    const int lo = rp[3], hi = rp[4];
+    float u = 0.f;
+    int p = lo;
+    for (; p + 32 <= hi; p += 32) u = ssb_row_batch<32>(ent + p, vg, u);
+    for (; p < hi; p += 8) u = ssb_row_batch<8>(ent + p, vg, u);
+    ssb_lin_store(c, s, vg, g, lane, kind, dst, a, b, u);
 }
 
 __global__ void k_advance(long long* dyn, int n) { dyn[0] += n; }
