@@ -101,7 +101,8 @@ struct ssb_sim {
     // dense blocks of the row program (rows sharing one column list), found at finalize
     int *d_dense_items = nullptr, *d_dense_desc = nullptr, *d_dense_cols = nullptr, *d_dense_rows = nullptr;
     float* d_dense_T = nullptr;
-    struct LinSeg { int csr_row0 = 0, n_csr = 0, item0 = 0, n_items = 0; };
+    struct LinSeg { int csr_row0 = 0, n_csr = 0, item0 = 0, n_items = 0, rec0 = 0, n_recs = 0; };
+    int* d_lin_recs = nullptr;
     std::vector<LinSeg> lin_segs;            // one per level + the end-of-step segment
     long long n_dense_rows = 0, n_dense_blocks = 0;
     float* d_ntypes = nullptr;
@@ -451,15 +452,26 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
     k_pes<<<grid, 128, 0, st>>>(s->ctx, s->d_pes, max_chunks, i_rel);
 }
 
-// One k_lin launch = the dense items of a segment (x ceil(G/4) trial-group quads) + its CSR rows (x G groups).
+// One k_lin launch = the dense items of a segment + its packed records + its remaining CSR rows, each x G groups.
 void launch_lin(ssb_sim* s, cudaStream_t st, int seg, int i_rel) {
     const ssb_sim::LinSeg& L = s->lin_segs[seg];
     const int G = s->n_groups;
-    const long long blocks = (long long)L.n_items * ((G + 3) / 4) + (long long)((L.n_csr + 3) / 4) * G;
+    const int rec_per_cta = 4 * SSB_REC_PER_WARP;
+    const long long blocks = ((long long)L.n_items + (L.n_recs + rec_per_cta - 1) / rec_per_cta + (L.n_csr + 3) / 4) * G;
     if (blocks <= 0) return;
-    k_lin<<<(unsigned)blocks, 128, 0, st>>>(s->ctx, s->d_lin_rows + (size_t)L.csr_row0 * 5, s->d_lin_ab + (size_t)L.csr_row0 * 2,
-                                            L.n_csr, i_rel, s->d_dense_items + (size_t)L.item0 * 4, L.n_items, s->d_dense_desc,
-                                            s->d_dense_T, s->d_dense_cols, s->d_dense_rows);
+    SsbLinArgs a;
+    a.rows = s->d_lin_rows + (size_t)L.csr_row0 * 5;
+    a.ab = s->d_lin_ab + (size_t)L.csr_row0 * 2;
+    a.n_rows = L.n_csr;
+    a.items = s->d_dense_items + (size_t)L.item0 * 4;
+    a.n_items = L.n_items;
+    a.ddesc = s->d_dense_desc;
+    a.dT = s->d_dense_T;
+    a.dcols = s->d_dense_cols;
+    a.drows = s->d_dense_rows;
+    a.recs = s->d_lin_recs + (size_t)L.rec0 * 32;
+    a.n_recs = L.n_recs;
+    k_lin<<<(unsigned)blocks, 128, 0, st>>>(s->ctx, a, i_rel);
 }
 
 // Split the row program of every launch segment into dense blocks and CSR rows.  Rows (of one view) with an
@@ -472,7 +484,7 @@ int build_lin_program(ssb_sim* s) {
     const float* ab = s->arrays.count("lin_ab") ? reinterpret_cast<const float*>(s->arrays["lin_ab"].bytes.data()) : nullptr;
     const size_t n_rows = rows3.size() / 3;
     if ((size_t)(s->lin0 + s->n_lin) != n_rows) return fail(-1, "ssb_finalize: lin_rows segments do not add up");
-    std::vector<int> rows5, items, ddesc, dcols, drows;
+    std::vector<int> rows5, items, ddesc, dcols, drows, recs;
     std::vector<float> ab2, dT;
     s->lin_segs.assign(s->n_levels + 1, ssb_sim::LinSeg());
     for (int seg = 0; seg <= s->n_levels; ++seg) {
@@ -528,13 +540,32 @@ int build_lin_program(ssb_sim* s) {
             s->n_dense_rows += R;
             s->n_dense_blocks++;
         }
+        L.rec0 = (int)(recs.size() / 32);
         for (int r = r0; r < r0 + nr; ++r) {
             if (is_dense[r - r0]) continue;
             const int src = rows3[r * 3], kind = rows3[r * 3 + 1];
-            rows5.insert(rows5.end(), {src, kind, rows3[r * 3 + 2], kind == 2 ? 0 : ptr[src], kind == 2 ? 0 : ptr[src + 1]});
-            ab2.push_back(ab ? ab[(size_t)r * 2] : 0.f);
-            ab2.push_back(ab ? ab[(size_t)r * 2 + 1] : 1.f);
+            const int lo = kind == 2 ? 0 : ptr[src], hi = kind == 2 ? 0 : ptr[src + 1];
+            const float fa = ab ? ab[(size_t)r * 2] : 0.f, fb = ab ? ab[(size_t)r * 2 + 1] : 1.f;
+            if (hi - lo <= 8) {              // one 128-byte record
+                int w[32] = {0};
+                w[0] = kind;
+                w[1] = rows3[r * 3 + 2];
+                memcpy(&w[2], &fa, 4);
+                memcpy(&w[3], &fb, 4);
+                for (int e = 0; e < hi - lo; ++e) {
+                    w[4 + e] = e0[(size_t)(lo + e) * 2];
+                    w[12 + e] = e1[(size_t)(lo + e) * 2];
+                    w[20 + e] = e0[(size_t)(lo + e) * 2 + 1];
+                }
+                w[28] = src;
+                recs.insert(recs.end(), w, w + 32);
+                continue;
+            }
+            rows5.insert(rows5.end(), {src, kind, rows3[r * 3 + 2], lo, hi});
+            ab2.push_back(fa);
+            ab2.push_back(fb);
         }
+        L.n_recs = (int)(recs.size() / 32) - L.rec0;
         L.n_csr = (int)(rows5.size() / 5) - L.csr_row0;
         L.n_items = (int)(items.size() / 4) - L.item0;
     }
@@ -549,7 +580,7 @@ int build_lin_program(ssb_sim* s) {
         return cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ? 1 : 0;
     };
     if (up_i(rows5, &s->d_lin_rows) || up_f(ab2, &s->d_lin_ab) || up_i(items, &s->d_dense_items) || up_i(ddesc, &s->d_dense_desc) ||
-        up_i(dcols, &s->d_dense_cols) || up_i(drows, &s->d_dense_rows) || up_f(dT, &s->d_dense_T))
+        up_i(dcols, &s->d_dense_cols) || up_i(drows, &s->d_dense_rows) || up_f(dT, &s->d_dense_T) || up_i(recs, &s->d_lin_recs))
         return fail(-2, "ssb_finalize: row program upload failed");
     return 0;
 }
@@ -1057,7 +1088,7 @@ void ssb_destroy(ssb_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
-                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
                     s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);
