@@ -463,7 +463,7 @@ void launch_lin(ssb_sim* s, cudaStream_t st, int seg, int i_rel) {
     a.rows = s->d_lin_rows + (size_t)L.csr_row0 * 5;
     a.ab = s->d_lin_ab + (size_t)L.csr_row0 * 2;
     a.n_rows = L.n_csr;
-    a.items = s->d_dense_items + (size_t)L.item0 * 4;
+    a.items = s->d_dense_items + (size_t)L.item0 * 8;
     a.n_items = L.n_items;
     a.ddesc = s->d_dense_desc;
     a.dT = s->d_dense_T;
@@ -492,7 +492,7 @@ int build_lin_program(ssb_sim* s) {
         const int nr = seg < s->n_levels ? s->h_stages[seg * 12 + 11] : s->n_lin;
         ssb_sim::LinSeg& L = s->lin_segs[seg];
         L.csr_row0 = (int)(rows5.size() / 5);
-        L.item0 = (int)(items.size() / 4);
+        L.item0 = (int)(items.size() / 8);
         // group candidate rows by (view, column list)
         std::map<std::vector<int>, std::vector<int>> groups;
         for (int r = r0; r < r0 + nr; ++r) {
@@ -535,8 +535,10 @@ int build_lin_program(ssb_sim* s) {
                 is_dense[m - r0] = 1;
             }
             ddesc.insert(ddesc.end(), {R, kpad, t_off, cols_off, rows_off, 0, 0, 0});
+            (void)block;
             for (int row0 = 0; row0 < R; row0 += SSB_DENSE_RCH)
-                items.insert(items.end(), {block, row0, std::min(SSB_DENSE_RCH, R - row0), 0});
+                items.insert(items.end(), {t_off + row0 * kpad, cols_off, kpad, rows_off + row0, std::min(SSB_DENSE_RCH, R - row0),
+                                           kv.first[0], 0, 0});
             s->n_dense_rows += R;
             s->n_dense_blocks++;
         }
@@ -567,7 +569,7 @@ int build_lin_program(ssb_sim* s) {
         }
         L.n_recs = (int)(recs.size() / 32) - L.rec0;
         L.n_csr = (int)(rows5.size() / 5) - L.csr_row0;
-        L.n_items = (int)(items.size() / 4) - L.item0;
+        L.n_items = (int)(items.size() / 8) - L.item0;
     }
     auto up_i = [&](std::vector<int>& v, int** dst) {
         v.resize(v.size() + 8, 0);
@@ -672,7 +674,7 @@ int one_step(ssb_sim* s, int i_rel) {
                 const int* d = &s->h_dec[(st[4] + i) * 9];
                 max_chunks = std::max(max_chunks, d[6]);
                 const size_t per = (d[0] + d[6] - 1) / d[6];
-                smem = std::max(smem, (per * d[2] + per * 32 + 56 * 32) * sizeof(float));
+                smem = std::max(smem, (per * d[2] + per * 32 + 2 * 56 * 32) * sizeof(float));
             }
             dim3 grid(max_chunks, G, st[5]);
             k_decode<<<grid, 128, smem, D>>>(c, s->d_dec, st[4]);

@@ -684,17 +684,19 @@ __device__ __forceinline__ void ssb_splitk_finish(const SsbCtx& c, float (*red)[
 }
 
 // Static decoders of wide ensembles: out[j] = sum_n Wd[n][j] * act[n].  CTA = (decoder, trial group,
-// neuron chunk).  The chunk's weight rows [cnt][jpad] and activity rows [cnt][32] are contiguous and are
-// staged in shared memory by two TMA bulk copies; each warp keeps a 56-wide accumulator tile in registers
-// and walks every fourth neuron of the chunk with broadcast float4 weight reads; a neuron whose activity
-// is zero in all 32 trials is skipped (spiking activity is sparse).  Warps are folded into one shared
-// tile in warp order, chunks by the split-K semaphore (fixed summation order).
+// neuron chunk).  The chunk's weight rows [cnt][jpad] and activity rows [cnt][32] are contiguous; they are
+// fetched in three stages by TMA bulk copies that are all issued up front, so the warps start on the first
+// third while the rest is still in flight.  Each warp keeps a 56-wide accumulator tile in registers and
+// walks every fourth neuron with broadcast float4 weight reads; a neuron whose activity is zero in all 32
+// trials is skipped (spiking activity is sparse).  Warps are folded pairwise through shared memory in a
+// fixed order, (w0 + w2) + (w1 + w3); chunks by the split-K semaphore (fixed summation order).
 // desc: n size_out jpad act0 w_off out_vec n_chunks part_off counter0
-// dynamic smem: per*jpad (weights) + per*32 (activities) + 56*32 (fold tile) floats, per = ceil(n / n_chunks)
+// dynamic smem: per*jpad (weights) + per*32 (activities) + 2*56*32 (fold tiles) floats, per = ceil(n / n_chunks)
 #define SSB_DEC_NJ 56
+#define SSB_DEC_STAGES 3
 __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict__ desc, int item0) {
     extern __shared__ __align__(128) float sm[];
-    __shared__ unsigned long long bar;
+    __shared__ unsigned long long bar[SSB_DEC_STAGES];
     __shared__ int flag;
     const int* d = desc + (item0 + blockIdx.z) * 9;
     const int n = d[0], size_out = d[1], jpad = d[2], act0 = d[3], w_off = d[4], out_vec = d[5], n_chunks = d[6];
@@ -707,17 +709,22 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
     const int g = blockIdx.y;
     float* s_w = sm;                                   // [per][jpad]
     float* s_a = s_w + (size_t)per * jpad;             // [per][32]
-    float* fold = s_a + (size_t)per * 32;              // [56][32]
+    float* fold = s_a + (size_t)per * 32;              // [2][56][32]
+    const int st_n = ((cnt + SSB_DEC_STAGES - 1) / SSB_DEC_STAGES + 3) & ~3;   // neurons per stage (multiple of 4)
     if (threadIdx.x == 0) {
-        ssb_mbar_init(&bar, 1);
+        for (int q = 0; q < SSB_DEC_STAGES; ++q) ssb_mbar_init(&bar[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t bw = (uint32_t)cnt * jpad * 4, ba = (uint32_t)cnt * 128;
-        ssb_mbar_expect_tx(&bar, bw + ba);
-        ssb_bulk_g2s(s_w, c.W + w_off + (size_t)i_lo * jpad, bw, &bar);
-        ssb_bulk_g2s(s_a, c.act + ((size_t)g * c.n_act + act0 + i_lo) * 32, ba, &bar);
+        for (int q = 0; q < SSB_DEC_STAGES; ++q) {
+            const int q0 = min(cnt, q * st_n), qn = min(cnt, (q + 1) * st_n) - q0;
+            const uint32_t bw = (uint32_t)qn * jpad * 4, ba = (uint32_t)qn * 128;
+            ssb_mbar_expect_tx(&bar[q], bw + ba);
+            if (qn > 0) {
+                ssb_bulk_g2s(s_w + (size_t)q0 * jpad, c.W + w_off + (size_t)(i_lo + q0) * jpad, bw, &bar[q]);
+                ssb_bulk_g2s(s_a + (size_t)q0 * 32, c.act + ((size_t)g * c.n_act + act0 + i_lo + q0) * 32, ba, &bar[q]);
+            }
+        }
     }
     __syncthreads();
-    ssb_mbar_wait(&bar, 0);
     float* vg = ssb_grp(c.vec, c.nv, g, lane);
     float* pg = ssb_grp(c.part, c.n_part, g, lane);
     for (int jb = 0; jb < jpad; jb += SSB_DEC_NJ) {
@@ -725,38 +732,52 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
         float acc[SSB_DEC_NJ];
 #pragma unroll
         for (int j = 0; j < SSB_DEC_NJ; ++j) acc[j] = 0.f;
-        for (int i = warp; i < cnt; i += 4) {
-            const float a = s_a[i * 32 + lane];
-            if (__any_sync(0xffffffffu, a != 0.f)) {
-                const float4* w4 = reinterpret_cast<const float4*>(s_w + (size_t)i * jpad + jb);
+        for (int q = 0; q < SSB_DEC_STAGES; ++q) {
+            if (jb == 0) ssb_mbar_wait(&bar[q], 0);
+            const int q1 = min(cnt, (q + 1) * st_n);
+            for (int i = q * st_n + warp; i < q1; i += 4) {
+                const float a = s_a[i * 32 + lane];
+                if (__any_sync(0xffffffffu, a != 0.f)) {
+                    const float4* w4 = reinterpret_cast<const float4*>(s_w + (size_t)i * jpad + jb);
 #pragma unroll
-                for (int q = 0; q < SSB_DEC_NJ / 4; ++q) {
-                    if (q < nq) {
-                        const float4 w = w4[q];
-                        acc[4 * q + 0] = fmaf(w.x, a, acc[4 * q + 0]);
-                        acc[4 * q + 1] = fmaf(w.y, a, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(w.z, a, acc[4 * q + 2]);
-                        acc[4 * q + 3] = fmaf(w.w, a, acc[4 * q + 3]);
-                    }
-                }
-            }
-        }
-        // fold the four warps in warp order: ((w0 + w1) + w2) + w3
-        for (int w = 0; w < 4; ++w) {
-            if (warp == w) {
-#pragma unroll
-                for (int j = 0; j < SSB_DEC_NJ; ++j) {
-                    if (j < 4 * nq) {
-                        const float t = (w == 0) ? acc[j] : fold[j * 32 + lane] + acc[j];
-                        if (w < 3) fold[j * 32 + lane] = t;
-                        else if (jb + j < size_out) {
-                            if (n_chunks == 1) vg[(size_t)(out_vec + jb + j) * 32] = t;
-                            else pg[(size_t)(part_off + chunk * size_out + jb + j) * 32] = t;
+                    for (int k = 0; k < SSB_DEC_NJ / 4; ++k) {
+                        if (k < nq) {
+                            const float4 w = w4[k];
+                            acc[4 * k + 0] = fmaf(w.x, a, acc[4 * k + 0]);
+                            acc[4 * k + 1] = fmaf(w.y, a, acc[4 * k + 1]);
+                            acc[4 * k + 2] = fmaf(w.z, a, acc[4 * k + 2]);
+                            acc[4 * k + 3] = fmaf(w.w, a, acc[4 * k + 3]);
                         }
                     }
                 }
             }
-            __syncthreads();
+        }
+        // pairwise fold: w2 -> tile 0, w3 -> tile 1; w0 += tile 0, w1 += tile 1; w1 -> tile 0; w0 += tile 0
+        __syncthreads();                                      // fold tiles free (previous pass consumed)
+        if (warp >= 2) {
+#pragma unroll
+            for (int j = 0; j < SSB_DEC_NJ; ++j) fold[((warp - 2) * SSB_DEC_NJ + j) * 32 + lane] = acc[j];
+        }
+        __syncthreads();
+        if (warp < 2) {
+#pragma unroll
+            for (int j = 0; j < SSB_DEC_NJ; ++j) acc[j] += fold[(warp * SSB_DEC_NJ + j) * 32 + lane];
+        }
+        __syncthreads();
+        if (warp == 1) {
+#pragma unroll
+            for (int j = 0; j < SSB_DEC_NJ; ++j) fold[j * 32 + lane] = acc[j];
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int j = 0; j < SSB_DEC_NJ; ++j) {
+                if (j < 4 * nq && jb + j < size_out) {
+                    const float t = acc[j] + fold[j * 32 + lane];
+                    if (n_chunks == 1) vg[(size_t)(out_vec + jb + j) * 32] = t;
+                    else pg[(size_t)(part_off + chunk * size_out + jb + j) * 32] = t;
+                }
+            }
         }
     }
     if (n_chunks == 1) return;
@@ -1457,7 +1478,7 @@ __global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ 
 #define SSB_DENSE_SLAB 32
 #define SSB_REC_PER_WARP 2
 
-// dense desc: R Kpad t_off cols_off rows_off - - -   | item: block row0 nr -   | dense rows: kind dst a_bits b_bits
+// dense rows: kind dst a_bits b_bits
 __device__ __forceinline__ void ssb_lin_store(const SsbCtx& c, const SsbStep& s, float* vg, int g, int lane, int kind, int dst,
                                               float a, float b, float u) {
     if (kind == 0) {
@@ -1485,7 +1506,7 @@ struct SsbLinArgs {
     int n_recs;
 };
 
-__global__ void __launch_bounds__(128) k_lin(SsbCtx c, SsbLinArgs L, int i_rel) {
+__global__ void __launch_bounds__(128, 8) k_lin(SsbCtx c, SsbLinArgs L, int i_rel) {
     __shared__ __align__(16) float s_t[4][SSB_DENSE_RCH][SSB_DENSE_SLAB];
     __shared__ float s_red[4][SSB_DENSE_RCH][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1493,14 +1514,13 @@ __global__ void __launch_bounds__(128) k_lin(SsbCtx c, SsbLinArgs L, int i_rel) 
     const int n_dense_ctas = L.n_items * c.G;
     if ((int)blockIdx.x < n_dense_ctas) {
         const int item = blockIdx.x / c.G, g = blockIdx.x - item * c.G;
-        const int* it = L.items + item * 4;
-        const int* d = L.ddesc + it[0] * 8;
-        const int row0 = it[1], nr = it[2];
-        const int kpad = d[1];
-        const float* __restrict__ T = L.dT + d[2] + (size_t)row0 * kpad;
-        const int* __restrict__ dr = L.drows + (size_t)(d[4] + row0) * 4;
-        const bool prev_view = dr[0] == 4;   // a block never mixes views
-        const int* __restrict__ cols = L.dcols + d[3] + ((s.odd ^ (prev_view ? 1 : 0)) ? kpad : 0);
+        // item: t_off (of its first row) | cols_off | kpad | rows_off (of its first row) | nr | previous-step view | - | -
+        const int4 it = __ldg(reinterpret_cast<const int4*>(L.items + (size_t)item * 8));
+        const int2 it2 = __ldg(reinterpret_cast<const int2*>(L.items + (size_t)item * 8 + 4));
+        const int kpad = it.z, nr = it2.x;
+        const float* __restrict__ T = L.dT + it.x;
+        const int* __restrict__ dr = L.drows + (size_t)it.w * 4;
+        const int* __restrict__ cols = L.dcols + it.y + ((s.odd ^ it2.y) ? kpad : 0);
         float* vg = ssb_grp(c.vec, c.nv, g, lane);
         float acc[SSB_DENSE_RCH];
 #pragma unroll

@@ -43,14 +43,14 @@ PES_CTAS_PER_SM = 4         # k_pes: 116 registers x 128 threads
 DEC_CTAS_PER_SM = 5         # k_decode: 96 registers x 128 threads (before its shared-memory limit)
 
 
-def _best_chunks(n, units, slots_of, k_min, k_max):
+def _best_chunks(n, units, slots_of, k_min, k_max, fixed=8):
     """Split a neuron range into k chunks so that the launch (units * k CTAs) wastes the least time on
     partial waves: minimise ceil(CTAs / resident slots) * neurons per chunk."""
     best, best_cost = k_min, None
     for k in range(k_min, k_max + 1):
         per = -(-n // k)
         waves = -(-(units * k) // max(1, slots_of(per)))
-        cost = waves * (per + 8)            # + a fixed per-CTA cost (prologue, split-K epilogue)
+        cost = waves * (per + fixed)        # + a fixed per-CTA cost (prologue, fold, split-K epilogue)
         if best_cost is None or cost < best_cost:
             best, best_cost = k, cost
     return best
@@ -186,9 +186,9 @@ class _Lowerer:
                     k_max = int(max(need, min(max(1, ens.n_neurons // 32), MAX_DEC_CHUNKS)))
 
                     def slots(per, jpad=jpad):
-                        smem = per * (jpad * 4 + 128) + 56 * 32 * 4 + 1024
+                        smem = per * (jpad * 4 + 128) + 2 * 56 * 32 * 4 + 1024
                         return N_SM * max(1, min(DEC_CTAS_PER_SM, SMEM_PER_SM // smem))
-                    self.dec_chunks[c] = _best_chunks(ens.n_neurons, max(1, n_static) * self.n_groups, slots, need, k_max)
+                    self.dec_chunks[c] = _best_chunks(ens.n_neurons, max(1, n_static) * self.n_groups, slots, need, k_max, fixed=24)
 
     @staticmethod
     def _out_size(c):
