@@ -1,0 +1,30 @@
+"""Throughput probe only (no oracle): B trials of BASELINE configs[1]; prints us/step for a few repetitions."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as g
+g.build()
+from sspslam_b200 import scenarios, lowering
+from sspslam_b200.simulator import Simulator
+
+B = int(os.environ.get("B", "1024"))
+steps = int(os.environ.get("STEPS", "64"))
+reps = int(os.environ.get("REPS", "4"))
+sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=8)
+sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, chunk_steps=steps)
+bytes_ts = lowering.algorithmic_bytes_per_trial_step(sim.plan.stats)
+sim.run_steps(steps)
+out = []
+for rep in range(reps):
+    sim.run_steps(steps)
+    ms = sim.last_run_ms()
+    out.append(ms / steps * 1e3)
+tps = B / (min(out) * 1e-6)
+print(f"[perf {os.environ.get('TAG','')}] us/step " + " ".join(f"{x:.1f}" for x in out) +
+      f" -> best {tps/1e6:.3f} M trial-steps/s ({tps*bytes_ts/1e9/6535.4:.3f} of HBM model)")
+if os.environ.get("KERNELS"):
+    sim.set_profiling(True)
+    sim.run_steps(steps)
+    for k, (ms, cnt) in sim.kernel_times().items():
+        if cnt:
+            print(f"[perf]   {k:13s} {ms/cnt*1e3:8.1f} us/launch x {cnt//steps}/step")
+sim.close()

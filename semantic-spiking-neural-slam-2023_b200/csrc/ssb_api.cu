@@ -121,6 +121,7 @@ struct ssb_sim {
     int pes_level = -1;
     bool pes_needs_static = false;
     std::vector<LevelInfo> levels;
+    size_t pes_pad_smem = 0, voja_pad_smem = 0;   // experiment knobs: extra dynamic smem lowers residency
     std::map<int, int> wide_chunk_cache;   // launch geometry of the wide-ensemble kernels, decided once
     long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
     std::vector<size_t> s64_offsets;
@@ -385,7 +386,7 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
     } else {
         int nwarps = 4;
         auto smem_of = [&](int nw) {
-            return (size_t)(max_dpad * 32 + max_jn * 32 + nw * 2 * max_dims * 32) * sizeof(float);
+            return (size_t)(max_dpad * 32 + max_jn * 32 + nw * 2 * max_dims * 32) * sizeof(float) + s->voja_pad_smem;
         };
         while (nwarps > 1 && smem_of(nwarps) > 200 * 1024) nwarps >>= 1;
         // one wave: every resident CTA slot gets one contiguous neuron range of a trial group
@@ -416,6 +417,7 @@ void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int i
 void wide_smem_optin() {
     const int lim = 200 * 1024;
     cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_pes, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -449,7 +451,7 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
         max_chunks = std::max(max_chunks, s->h_pes[i * 13 + 10]);
     }
     dim3 grid((max_out + 7) / 8, s->n_groups, s->n_pes * max_chunks);
-    k_pes<<<grid, 128, 0, st>>>(s->ctx, s->d_pes, max_chunks, i_rel);
+    k_pes<<<grid, 128, s->pes_pad_smem, st>>>(s->ctx, s->d_pes, max_chunks, i_rel);
 }
 
 // One k_lin launch = the dense items of a segment + its packed records + its remaining CSR rows, each x G groups.
@@ -674,9 +676,9 @@ int one_step(ssb_sim* s, int i_rel) {
                 const int* d = &s->h_dec[(st[4] + i) * 9];
                 max_chunks = std::max(max_chunks, d[6]);
                 const size_t per = (d[0] + d[6] - 1) / d[6];
-                smem = std::max(smem, (per * d[2] + per * 32 + 2 * 56 * 32) * sizeof(float));
+                smem = std::max(smem, (per * d[2] + 4 * per * 32) * sizeof(float));
             }
-            dim3 grid(max_chunks, G, st[5]);
+            dim3 grid(max_chunks, (G + 3) / 4, st[5]);
             k_decode<<<grid, 128, smem, D>>>(c, s->d_dec, st[4]);
         }
         if (useC) stream_dep(s, C, A);
@@ -757,6 +759,8 @@ int ssb_create(int device, int n_trials, ssb_sim** out) {
         SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[2], cudaStreamNonBlocking, pr_hi));
     }
     if (const char* e = getenv("SSB_SERIAL")) s->parallel = e[0] != '1';
+    if (const char* e = getenv("SSB_PES_PAD")) s->pes_pad_smem = (size_t)atoi(e) * 1024;
+    if (const char* e = getenv("SSB_VOJA_PAD")) s->voja_pad_smem = (size_t)atoi(e) * 1024;
     SSB_CUDA(cudaEventCreate(&s->ev_run0));
     SSB_CUDA(cudaEventCreate(&s->ev_run1));
     *out = s;

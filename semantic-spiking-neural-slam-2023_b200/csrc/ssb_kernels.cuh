@@ -677,125 +677,127 @@ __device__ __forceinline__ void ssb_splitk_finish(const SsbCtx& c, float (*red)[
     for (int j = warp; j < 8; j += 4) {
         if (j0 + j < size_out) {
             float t = 0.f;
-            for (int ck = 0; ck < n_chunks; ++ck) t += __ldcg(pg + (size_t)(part_off + ck * size_out + j0 + j) * 32);
+            for (int ck0 = 0; ck0 < n_chunks; ck0 += 8) {     // 8 independent loads in flight, added in chunk order
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    v[q] = ck0 + q < n_chunks ? __ldcg(pg + (size_t)(part_off + (ck0 + q) * size_out + j0 + j) * 32) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t += v[q];
+            }
             vg[(size_t)(out_vec + j0 + j) * 32] = t;
         }
     }
 }
 
-// Static decoders of wide ensembles: out[j] = sum_n Wd[n][j] * act[n].  CTA = (decoder, trial group,
-// neuron chunk).  The chunk's weight rows [cnt][jpad] and activity rows [cnt][32] are contiguous; they are
-// fetched in three stages by TMA bulk copies that are all issued up front, so the warps start on the first
-// third while the rest is still in flight.  Each warp keeps a 56-wide accumulator tile in registers and
-// walks every fourth neuron with broadcast float4 weight reads; a neuron whose activity is zero in all 32
-// trials is skipped (spiking activity is sparse).  Warps are folded pairwise through shared memory in a
-// fixed order, (w0 + w2) + (w1 + w3); chunks by the split-K semaphore (fixed summation order).
+// Static decoders of wide ensembles: out[j] = sum_n Wd[n][j] * act[n].  CTA = (decoder, quad of trial
+// groups, neuron chunk); each WARP owns one trial group and the whole 56-wide output tile for the chunk, so
+// there is no cross-warp reduction: the four warps share the chunk's weight rows [cnt][jpad] (one TMA bulk
+// copy, broadcast float4 reads) and each fetches its own group's activity rows [cnt][32] (one bulk copy per
+// warp, own mbarrier).  A neuron whose activity is zero in all 32 trials of the group is skipped (spiking
+// activity is sparse).  Chunks are combined by the split-K semaphore in chunk order (fixed summation order).
 // desc: n size_out jpad act0 w_off out_vec n_chunks part_off counter0
-// dynamic smem: per*jpad (weights) + per*32 (activities) + 2*56*32 (fold tiles) floats, per = ceil(n / n_chunks)
+// dynamic smem: per*jpad (weights) + 4*per*32 (activities) floats, per = ceil(n / n_chunks)
 #define SSB_DEC_NJ 56
-#define SSB_DEC_STAGES 3
 __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict__ desc, int item0) {
     extern __shared__ __align__(128) float sm[];
-    __shared__ unsigned long long bar[SSB_DEC_STAGES];
-    __shared__ int flag;
+    __shared__ unsigned long long bar_w, bar_a[4];
     const int* d = desc + (item0 + blockIdx.z) * 9;
     const int n = d[0], size_out = d[1], jpad = d[2], act0 = d[3], w_off = d[4], out_vec = d[5], n_chunks = d[6];
-    const int part_off = d[7], counter = d[8] * c.G + blockIdx.y;
+    const int part_off = d[7];
     const int chunk = blockIdx.x;
     if (chunk >= n_chunks) return;
     const int per = (n + n_chunks - 1) / n_chunks;
     const int i_lo = chunk * per, cnt = min(n, i_lo + per) - i_lo;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.y;
-    float* s_w = sm;                                   // [per][jpad]
-    float* s_a = s_w + (size_t)per * jpad;             // [per][32]
-    float* fold = s_a + (size_t)per * 32;              // [2][56][32]
-    const int st_n = ((cnt + SSB_DEC_STAGES - 1) / SSB_DEC_STAGES + 3) & ~3;   // neurons per stage (multiple of 4)
+    const int g = blockIdx.y * 4 + warp;
+    const bool live = g < c.G;
+    float* s_w = sm;                                                   // [per][jpad]
+    float* s_a = s_w + (size_t)per * jpad + (size_t)warp * per * 32;   // [per][32] of this warp's group
     if (threadIdx.x == 0) {
-        for (int q = 0; q < SSB_DEC_STAGES; ++q) ssb_mbar_init(&bar[q], 1);
+        ssb_mbar_init(&bar_w, 1);
+        for (int q = 0; q < 4; ++q) ssb_mbar_init(&bar_a[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int q = 0; q < SSB_DEC_STAGES; ++q) {
-            const int q0 = min(cnt, q * st_n), qn = min(cnt, (q + 1) * st_n) - q0;
-            const uint32_t bw = (uint32_t)qn * jpad * 4, ba = (uint32_t)qn * 128;
-            ssb_mbar_expect_tx(&bar[q], bw + ba);
-            if (qn > 0) {
-                ssb_bulk_g2s(s_w + (size_t)q0 * jpad, c.W + w_off + (size_t)(i_lo + q0) * jpad, bw, &bar[q]);
-                ssb_bulk_g2s(s_a + (size_t)q0 * 32, c.act + ((size_t)g * c.n_act + act0 + i_lo + q0) * 32, ba, &bar[q]);
-            }
-        }
+        ssb_mbar_expect_tx(&bar_w, (uint32_t)cnt * jpad * 4);
+        ssb_bulk_g2s(s_w, c.W + w_off + (size_t)i_lo * jpad, (uint32_t)cnt * jpad * 4, &bar_w);
     }
     __syncthreads();
+    if (!live) return;
+    if (lane == 0) {
+        ssb_mbar_expect_tx(&bar_a[warp], (uint32_t)cnt * 128);
+        ssb_bulk_g2s(s_a, c.act + ((size_t)g * c.n_act + act0 + i_lo) * 32, (uint32_t)cnt * 128, &bar_a[warp]);
+    }
     float* vg = ssb_grp(c.vec, c.nv, g, lane);
     float* pg = ssb_grp(c.part, c.n_part, g, lane);
+    ssb_mbar_wait(&bar_a[warp], 0);
+    ssb_mbar_wait(&bar_w, 0);
     for (int jb = 0; jb < jpad; jb += SSB_DEC_NJ) {
         const int nq = min(SSB_DEC_NJ, jpad - jb) >> 2;      // float4 columns of this pass (jpad is a multiple of 8)
         float acc[SSB_DEC_NJ];
 #pragma unroll
         for (int j = 0; j < SSB_DEC_NJ; ++j) acc[j] = 0.f;
-        for (int q = 0; q < SSB_DEC_STAGES; ++q) {
-            if (jb == 0) ssb_mbar_wait(&bar[q], 0);
-            const int q1 = min(cnt, (q + 1) * st_n);
-            for (int i = q * st_n + warp; i < q1; i += 4) {
-                const float a = s_a[i * 32 + lane];
-                if (__any_sync(0xffffffffu, a != 0.f)) {
-                    const float4* w4 = reinterpret_cast<const float4*>(s_w + (size_t)i * jpad + jb);
+        for (int i = 0; i < cnt; ++i) {
+            const float a = s_a[i * 32 + lane];
+            if (__any_sync(0xffffffffu, a != 0.f)) {
+                const float4* w4 = reinterpret_cast<const float4*>(s_w + (size_t)i * jpad + jb);
 #pragma unroll
-                    for (int k = 0; k < SSB_DEC_NJ / 4; ++k) {
-                        if (k < nq) {
-                            const float4 w = w4[k];
-                            acc[4 * k + 0] = fmaf(w.x, a, acc[4 * k + 0]);
-                            acc[4 * k + 1] = fmaf(w.y, a, acc[4 * k + 1]);
-                            acc[4 * k + 2] = fmaf(w.z, a, acc[4 * k + 2]);
-                            acc[4 * k + 3] = fmaf(w.w, a, acc[4 * k + 3]);
-                        }
+                for (int k = 0; k < SSB_DEC_NJ / 4; ++k) {
+                    if (k < nq) {
+                        const float4 w = w4[k];
+                        acc[4 * k + 0] = fmaf(w.x, a, acc[4 * k + 0]);
+                        acc[4 * k + 1] = fmaf(w.y, a, acc[4 * k + 1]);
+                        acc[4 * k + 2] = fmaf(w.z, a, acc[4 * k + 2]);
+                        acc[4 * k + 3] = fmaf(w.w, a, acc[4 * k + 3]);
                     }
                 }
             }
         }
-        // pairwise fold: w2 -> tile 0, w3 -> tile 1; w0 += tile 0, w1 += tile 1; w1 -> tile 0; w0 += tile 0
-        __syncthreads();                                      // fold tiles free (previous pass consumed)
-        if (warp >= 2) {
 #pragma unroll
-            for (int j = 0; j < SSB_DEC_NJ; ++j) fold[((warp - 2) * SSB_DEC_NJ + j) * 32 + lane] = acc[j];
-        }
-        __syncthreads();
-        if (warp < 2) {
-#pragma unroll
-            for (int j = 0; j < SSB_DEC_NJ; ++j) acc[j] += fold[(warp * SSB_DEC_NJ + j) * 32 + lane];
-        }
-        __syncthreads();
-        if (warp == 1) {
-#pragma unroll
-            for (int j = 0; j < SSB_DEC_NJ; ++j) fold[j * 32 + lane] = acc[j];
-        }
-        __syncthreads();
-        if (warp == 0) {
-#pragma unroll
-            for (int j = 0; j < SSB_DEC_NJ; ++j) {
-                if (j < 4 * nq && jb + j < size_out) {
-                    const float t = acc[j] + fold[j * 32 + lane];
-                    if (n_chunks == 1) vg[(size_t)(out_vec + jb + j) * 32] = t;
-                    else pg[(size_t)(part_off + chunk * size_out + jb + j) * 32] = t;
-                }
+        for (int j = 0; j < SSB_DEC_NJ; ++j) {
+            if (j < 4 * nq && jb + j < size_out) {
+                if (n_chunks == 1) vg[(size_t)(out_vec + jb + j) * 32] = acc[j];
+                else pg[(size_t)(part_off + chunk * size_out + jb + j) * 32] = acc[j];
             }
         }
     }
     if (n_chunks == 1) return;
+    // split-K: one arrival counter per (decoder, trial group); the warp that arrives last adds the partials
     __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int old = atomicAdd(c.counters + counter, 1);
-        const int last = old == n_chunks - 1;
-        if (last) c.counters[counter] = 0;
-        flag = last;
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+        int* cnt_p = c.counters + d[8] * c.G + g;
+        const int old = atomicAdd(cnt_p, 1);
+        last = old == n_chunks - 1;
+        if (last) *cnt_p = 0;
     }
-    __syncthreads();
-    if (!flag) return;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
     __threadfence();
-    for (int j = warp; j < size_out; j += 4) {
-        float t = 0.f;
-        for (int ck = 0; ck < n_chunks; ++ck) t += __ldcg(pg + (size_t)(part_off + ck * size_out + j) * 32);
-        vg[(size_t)(out_vec + j) * 32] = t;
+    // 8 outputs x 8 chunks = 64 independent loads in flight; the additions stay in chunk order
+    for (int j = 0; j < size_out; j += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = 0.f;
+        for (int ck0 = 0; ck0 < n_chunks; ck0 += 8) {
+            float v[8][8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool ok = ck0 + q < n_chunks && j + u < size_out;
+                    v[q][u] = ok ? __ldcg(pg + (size_t)(part_off + (ck0 + q) * size_out + j + u) * 32) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] += v[q][u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (j + u < size_out) vg[(size_t)(out_vec + j + u) * 32] = t[u];
     }
 }
 

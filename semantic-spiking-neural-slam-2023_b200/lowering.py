@@ -43,14 +43,15 @@ PES_CTAS_PER_SM = 4         # k_pes: 116 registers x 128 threads
 DEC_CTAS_PER_SM = 5         # k_decode: 96 registers x 128 threads (before its shared-memory limit)
 
 
-def _best_chunks(n, units, slots_of, k_min, k_max, fixed=8):
+def _best_chunks(n, units, slots_of, k_min, k_max, fixed=8, per_chunk=0.0):
     """Split a neuron range into k chunks so that the launch (units * k CTAs) wastes the least time on
-    partial waves: minimise ceil(CTAs / resident slots) * neurons per chunk."""
+    partial waves: minimise ceil(CTAs / resident slots) * neurons per chunk (+ the split-K reduce, which
+    grows with the number of partial sums)."""
     best, best_cost = k_min, None
     for k in range(k_min, k_max + 1):
         per = -(-n // k)
         waves = -(-(units * k) // max(1, slots_of(per)))
-        cost = waves * (per + fixed)        # + a fixed per-CTA cost (prologue, fold, split-K epilogue)
+        cost = waves * (per + fixed) + per_chunk * k   # + a fixed per-CTA cost (prologue, split-K epilogue)
         if best_cost is None or cost < best_cost:
             best, best_cost = k, cost
     return best
@@ -181,14 +182,16 @@ class _Lowerer:
                                                       lambda per: N_SM * PES_CTAS_PER_SM, 1, k_max)
                 else:                  # k_decode: CTA = (decoder, trial group, neuron chunk), all outputs at once
                     jpad = -(-self._out_size(c) // DEC_TILE) * DEC_TILE
-                    per_max = max(1, DEC_SMEM_BYTES // (jpad * 4 + 128))   # weight + activity tile of a chunk
+                    per_max = max(1, DEC_SMEM_BYTES // (jpad * 4 + 4 * 128))   # weight tile + 4 activity tiles of a chunk
                     need = -(-ens.n_neurons // per_max)
                     k_max = int(max(need, min(max(1, ens.n_neurons // 32), MAX_DEC_CHUNKS)))
 
-                    def slots(per, jpad=jpad):
-                        smem = per * (jpad * 4 + 128) + 2 * 56 * 32 * 4 + 1024
+                    def slots(per, jpad=jpad):      # CTA = 4 trial groups: shared weight tile + 4 activity tiles
+                        smem = per * (jpad * 4 + 4 * 128) + 1024
                         return N_SM * max(1, min(DEC_CTAS_PER_SM, SMEM_PER_SM // smem))
-                    self.dec_chunks[c] = _best_chunks(ens.n_neurons, max(1, n_static) * self.n_groups, slots, need, k_max, fixed=24)
+                    quads = -(-self.n_groups // 4)
+                    self.dec_chunks[c] = _best_chunks(ens.n_neurons, max(1, n_static) * quads, slots, need, k_max, fixed=12,
+                                                      per_chunk=3.0)
 
     @staticmethod
     def _out_size(c):
