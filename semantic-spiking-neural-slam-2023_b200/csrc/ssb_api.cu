@@ -121,6 +121,9 @@ struct ssb_sim {
     int pes_level = -1;
     bool pes_needs_static = false;
     std::vector<LevelInfo> levels;
+    float* d_dec_wt = nullptr;              // static decoders pre-tiled for k_decode_tc (3xTF32 hi | lo)
+    int* d_dec_wt_off = nullptr;
+    std::vector<char> dec_tc_level;         // per level: every decoder of the level can use the tensor-core kernel
     size_t pes_pad_smem = 0, voja_pad_smem = 0;   // experiment knobs: extra dynamic smem lowers residency
     std::map<int, int> wide_chunk_cache;   // launch geometry of the wide-ensemble kernels, decided once
     long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
@@ -454,6 +457,57 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
     k_pes<<<grid, 128, s->pes_pad_smem, st>>>(s->ctx, s->d_pes, max_chunks, i_rel);
 }
 
+// SSB_DECODE=ffma forces the FFMA decoder kernel (measured comparison); default is tcgen05 when the output fits 64 columns.
+bool decode_tc_allowed() {
+    const char* e = getenv("SSB_DECODE");
+    return !(e && std::string(e) == "ffma");
+}
+
+// Static decoders [n][jpad] -> per 64-neuron stage: Wd^T as 64 x 64 K-major operand tiles (hi | lo) in UMMA core-matrix order.
+int build_decode_tiles(ssb_sim* s) {
+    const int n_dec = (int)(s->h_dec.size() / 9);
+    s->dec_tc_level.assign(s->n_levels, 0);
+    if (n_dec == 0 || !decode_tc_allowed()) return 0;
+    const float* hW = reinterpret_cast<const float*>(s->arrays["weights"].bytes.data());
+    std::vector<float> wt;
+    std::vector<int> off(n_dec + 8, -1);
+    const int part = SSB_DTC_N * SSB_DTC_KS;
+    for (int i = 0; i < n_dec; ++i) {
+        const int* d = &s->h_dec[i * 9];
+        const int n = d[0], jpad = d[2], w_off = d[4];
+        if (jpad > SSB_DTC_N) continue;
+        const int n_stages = (n + SSB_DTC_KS - 1) / SSB_DTC_KS;
+        off[i] = (int)wt.size();
+        wt.resize(wt.size() + (size_t)n_stages * 2 * part, 0.f);
+        float* base = &wt[off[i]];
+        for (int k = 0; k < n; ++k) {
+            const int st = k / SSB_DTC_KS, kk = k % SSB_DTC_KS;
+            float* hi = base + (size_t)st * 2 * part;
+            float* lo = hi + part;
+            for (int j = 0; j < jpad; ++j) {
+                const float x = hW[(size_t)w_off + (size_t)k * jpad + j];
+                const float h = ssb_tf32_round(x);
+                const size_t o = ((size_t)(kk / 4) * 8 + j / 8) * 32 + (j % 8) * 4 + kk % 4;
+                hi[o] = h;
+                lo[o] = ssb_tf32_round(x - h);
+            }
+        }
+    }
+    for (int lvl = 0; lvl < s->n_levels; ++lvl) {
+        const int* st = &s->h_stages[lvl * 12];
+        bool all = st[5] > 0;
+        for (int i = 0; i < st[5]; ++i) all = all && off[st[4] + i] >= 0;
+        s->dec_tc_level[lvl] = all ? 1 : 0;
+    }
+    wt.resize(wt.size() + 8, 0.f);
+    SSB_CUDA(cudaMalloc((void**)&s->d_dec_wt, wt.size() * sizeof(float)));
+    SSB_CUDA(cudaMemcpy(s->d_dec_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SSB_CUDA(cudaMalloc((void**)&s->d_dec_wt_off, off.size() * sizeof(int)));
+    SSB_CUDA(cudaMemcpy(s->d_dec_wt_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SSB_CUDA(cudaFuncSetAttribute(k_decode_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return 0;
+}
+
 // One k_lin launch = the dense items of a segment + its packed records + its remaining CSR rows, each x G groups.
 void launch_lin(ssb_sim* s, cudaStream_t st, int seg, int i_rel) {
     const ssb_sim::LinSeg& L = s->lin_segs[seg];
@@ -679,7 +733,11 @@ int one_step(ssb_sim* s, int i_rel) {
                 smem = std::max(smem, (per * d[2] + 4 * per * 32) * sizeof(float));
             }
             dim3 grid(max_chunks, (G + 3) / 4, st[5]);
-            k_decode<<<grid, 128, smem, D>>>(c, s->d_dec, st[4]);
+            if (s->dec_tc_level[lvl])
+                k_decode_tc<<<grid, 256, (size_t)(4 * 128 * SSB_DTC_KS + 4 * SSB_DTC_N * SSB_DTC_KS) * sizeof(float), D>>>(
+                    c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off);
+            else
+                k_decode<<<grid, 128, smem, D>>>(c, s->d_dec, st[4]);
         }
         if (useC) stream_dep(s, C, A);
         if (useD) stream_dep(s, D, A);
@@ -828,6 +886,7 @@ int ssb_finalize(ssb_sim* s) {
     s->h_pes = host_ints(s, "pes");
     if ((int)s->h_stages.size() != s->n_levels * 12) return fail(-1, "ssb_finalize: stages array has wrong size");
     if (int rc = build_lin_program(s)) return rc;
+    if (int rc = build_decode_tiles(s)) return rc;
     s->levels.assign(s->n_levels, LevelInfo());
     for (int lvl = 0; lvl < s->n_levels; ++lvl) {
         const int* st = &s->h_stages[lvl * 12];
@@ -1094,7 +1153,7 @@ void ssb_destroy(ssb_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
-                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
                     s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -233,6 +233,71 @@ __device__ __forceinline__ void ssb_bulk_wait0() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void ssb_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // --------------------------------------------------------------------------------------
+// tcgen05 / TMEM helpers shared by the tensor-core kernels (grid scan, static decoders).
+#define SSB_TC_ROWS 128
+
+__host__ __device__ __forceinline__ float ssb_tf32_round(float x) {   // round-to-nearest-even to a 10-bit mantissa
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(x);
+#else
+    uint32_t u;
+    memcpy(&u, &x, 4);
+#endif
+    u += 0xfffu + ((u >> 13) & 1u);
+    u &= 0xffffe000u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+#endif
+}
+
+__device__ __forceinline__ uint64_t ssb_umma_desc(const void* smem_ptr) {
+    const uint32_t a = ssb_smem(smem_ptr);
+    return (uint64_t)((a >> 4) & 0x3fffu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void ssb_umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void ssb_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    // the registers are valid only after wait::ld; tying them to the wait keeps every use behind it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void ssb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ssb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// --------------------------------------------------------------------------------------
 // Start of a step: the input-table rows of this step become ordinary vec rows, so every CSR entry
 // addresses one arena.  grid (ceil(nt/4), G) x 128
 __global__ void __launch_bounds__(128) k_begin(SsbCtx c, int i_rel) {
@@ -801,6 +866,194 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
     }
 }
 
+// Tensor-core static decoders (tcgen05 + TMEM): out[trial][j] = sum_k act[k][trial] * Wd[k][j] is a dense GEMM
+// whose weights are shared by every trial.  CTA = (decoder, block of 128 trials = 4 trial groups, K chunk);
+//   A = activities (128 trials x 64 neurons per stage, K-major), gathered by the CTA's 256 threads from the
+//       group-tiled act arena (coalesced 128-byte rows) and split on the fly into TF32 hi + lo,
+//   B = Wd^T (64 output rows x 64 neurons per stage, K-major) pre-split into hi / lo and pre-tiled by the host in
+//       UMMA core-matrix order, one TMA bulk copy per stage,
+//   D = 128 lanes x 64 fp32 columns in TMEM, accumulated over the chunk's stages with the 3xTF32 scheme
+//       (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi).  Building stage s+1 overlaps the MMAs of stage s (two buffers).
+// The epilogue reads D with tcgen05.ld (lane = trial) and writes the output rows (or split-K partial sums,
+// combined in chunk order by the last CTA to arrive, as in the FFMA kernel).
+// Wt: [n_stages][hi|lo][k/4][8 row groups][8][4] floats (64 rows x 64 columns per part).
+#define SSB_DTC_KS 64          // neurons per stage
+#define SSB_DTC_N 64           // padded output width
+__device__ __forceinline__ uint64_t ssb_umma_desc_lbo(const void* smem_ptr, uint32_t lbo_bytes) {
+    const uint32_t a = ssb_smem(smem_ptr);
+    return (uint64_t)((a >> 4) & 0x3fffu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __restrict__ Wt_all, const int* __restrict__ wt_off) {
+    extern __shared__ __align__(1024) float sm[];
+    __shared__ unsigned long long full[2], done[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int s_last[4];
+    const int* d = desc + (item0 + blockIdx.z) * 9;
+    const int n = d[0], size_out = d[1], act0 = d[3], out_vec = d[5], n_chunks = d[6], part_off = d[7];
+    const float* __restrict__ Wt = Wt_all + wt_off[item0 + blockIdx.z];
+    const int chunk = blockIdx.x;
+    if (chunk >= n_chunks) return;
+    const int n_stages = (n + SSB_DTC_KS - 1) / SSB_DTC_KS;
+    const int spc = (n_stages + n_chunks - 1) / n_chunks;
+    const int s_lo = chunk * spc, s_hi = min(n_stages, s_lo + spc);
+    const int my = max(0, s_hi - s_lo);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int quad = warp & 3, half = warp >> 2;
+    const int group = blockIdx.y * 4 + quad;
+    const bool live = group < c.G;
+    const int g = live ? group : 0;
+    constexpr int A_PART = 128 * SSB_DTC_KS;            // floats of one A part (hi or lo)
+    constexpr int B_PART = SSB_DTC_N * SSB_DTC_KS;
+    float* sA = sm;                                     // [2 buffers][hi|lo][A_PART]
+    float* sB = sm + 4 * A_PART;                        // [2 buffers][hi|lo][B_PART]
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (threadIdx.x == 0) {
+        ssb_mbar_init(&full[0], 1);
+        ssb_mbar_init(&full[1], 1);
+        ssb_mbar_init(&done[0], 1);
+        ssb_mbar_init(&done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 2 && i < my; ++i) {
+            ssb_mbar_expect_tx(&full[i], 2u * B_PART * 4u);
+            ssb_bulk_g2s(sB + (size_t)i * 2 * B_PART, Wt + (size_t)(s_lo + i) * 2 * B_PART, 2u * B_PART * 4u, &full[i]);
+        }
+    }
+    ssb_tc_fence_before();
+    __syncthreads();
+    ssb_tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    // D fp32, A/B tf32, both K-major, N = 64, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SSB_DTC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int r = quad * 32 + lane;                     // this thread's trial row; `half` picks its 32 of the 64 columns
+    const float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
+    for (int i = 0; i < my; ++i) {
+        const int b = i & 1;
+        if (i >= 2) {                                   // buffer b was read by the MMAs of stage i - 2
+            ssb_mbar_wait(&done[b], (uint32_t)((i - 2) >> 1) & 1u);
+            ssb_tc_fence_after();
+            if (threadIdx.x == 0) {
+                ssb_mbar_expect_tx(&full[b], 2u * B_PART * 4u);
+                ssb_bulk_g2s(sB + (size_t)b * 2 * B_PART, Wt + (size_t)(s_lo + i) * 2 * B_PART, 2u * B_PART * 4u, &full[b]);
+            }
+        }
+        {   // A stage: 32 activity rows per thread, all loads issued before they are consumed
+            const int k0 = (s_lo + i) * SSB_DTC_KS + half * 32;
+            float x[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = (live && k0 + e < n) ? ag[(size_t)(k0 + e) * 32] : 0.f;
+            float* a_hi = sA + (size_t)b * 2 * A_PART + (r >> 3) * 32 + (r & 7) * 4 + (size_t)(half * 8) * 16 * 32;
+            float* a_lo = a_hi + A_PART;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 hi, lo;
+                hi.x = ssb_tf32_round(x[4 * q + 0]);
+                hi.y = ssb_tf32_round(x[4 * q + 1]);
+                hi.z = ssb_tf32_round(x[4 * q + 2]);
+                hi.w = ssb_tf32_round(x[4 * q + 3]);
+                lo.x = ssb_tf32_round(x[4 * q + 0] - hi.x);
+                lo.y = ssb_tf32_round(x[4 * q + 1] - hi.y);
+                lo.z = ssb_tf32_round(x[4 * q + 2] - hi.z);
+                lo.w = ssb_tf32_round(x[4 * q + 3] - hi.w);
+                *reinterpret_cast<float4*>(a_hi + (size_t)q * 16 * 32) = hi;
+                *reinterpret_cast<float4*>(a_lo + (size_t)q * 16 * 32) = lo;
+            }
+        }
+        ssb_fence_async();
+        ssb_tc_fence_before();
+        __syncthreads();
+        ssb_tc_fence_after();
+        if (threadIdx.x == 0) {
+            ssb_mbar_wait(&full[b], (uint32_t)(i >> 1) & 1u);
+            ssb_tc_fence_after();
+            const float* ah = sA + (size_t)b * 2 * A_PART;
+            const float* bh = sB + (size_t)b * 2 * B_PART;
+#pragma unroll 1
+            for (int j = 0; j < SSB_DTC_KS / 8; ++j) {
+                const size_t oa = (size_t)j * 2 * 16 * 32, ob = (size_t)j * 2 * 8 * 32;   // two 16-byte K chunks per MMA
+                const uint64_t dah = ssb_umma_desc_lbo(ah + oa, 2048), dal = ssb_umma_desc_lbo(ah + A_PART + oa, 2048);
+                const uint64_t dbh = ssb_umma_desc_lbo(bh + ob, 1024), dbl = ssb_umma_desc_lbo(bh + B_PART + ob, 1024);
+                ssb_umma_tf32(tmem, dal, dbh, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                ssb_umma_tf32(tmem, dah, dbl, idesc, 1);
+                ssb_umma_tf32(tmem, dah, dbh, idesc, 1);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ssb_smem(&done[b]))
+                         : "memory");
+        }
+        __syncwarp();
+    }
+    float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    float* pg = ssb_grp(c.part, c.n_part, g, lane);
+    if (my > 0) {
+        // the commit of the last stage covers every earlier MMA
+        ssb_mbar_wait(&done[(my - 1) & 1], (uint32_t)((my - 1) >> 1) & 1u);
+        ssb_tc_fence_after();
+        float v[32];
+        ssb_tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 32, v);
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int jo = half * 32 + j;
+                if (jo < size_out) {
+                    if (n_chunks == 1) vg[(size_t)(out_vec + jo) * 32] = v[j];
+                    else pg[(size_t)(part_off + chunk * size_out + jo) * 32] = v[j];
+                }
+            }
+        }
+    } else if (live && n_chunks > 1) {                  // an empty trailing chunk still owns its partial slot
+        for (int j = half * 32; j < min(size_out, half * 32 + 32); ++j) pg[(size_t)(part_off + chunk * size_out + j) * 32] = 0.f;
+    }
+    ssb_tc_fence_before();
+    __threadfence();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+    if (n_chunks == 1) return;
+    // split-K: one arrival counter per (decoder, trial group); the CTA that arrives last adds the partials in chunk order
+    if (half == 0) {
+        if (lane == 0) {
+            int last = 0;
+            if (live) {
+                int* cnt_p = c.counters + d[8] * c.G + group;
+                const int old = atomicAdd(cnt_p, 1);
+                last = old == n_chunks - 1;
+                if (last) *cnt_p = 0;
+            }
+            s_last[quad] = last;
+        }
+    }
+    __syncthreads();
+    if (!s_last[quad]) return;
+    __threadfence();
+    for (int j = half * 32; j < min(size_out, half * 32 + 32); j += 8) {   // the two warps of a group split the outputs
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = 0.f;
+        for (int ck0 = 0; ck0 < n_chunks; ck0 += 4) {
+            float w[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool ok = ck0 + q < n_chunks && j + u < size_out;
+                    w[q][u] = ok ? __ldcg(pg + (size_t)(part_off + (ck0 + q) * size_out + j + u) * 32) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] += w[q][u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (j + u < size_out) vg[(size_t)(out_vec + j + u) * 32] = t[u];
+    }
+}
+
 // --------------------------------------------------------------------------------------
 // PES-learned decoders (per trial): one streaming pass that applies the pending rank-1 delta,
 // decodes with the updated weights and writes them back:
@@ -1066,68 +1319,6 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
 // Shared-memory operand layout (UMMA "interleave" / no-swizzle, K-major): 8 rows x 16 bytes core matrices,
 //   float offset(row r, column k) = ((k / 4) * 16 + r / 8) * 32 + (r % 8) * 4 + k % 4
 // => stride between 8-row groups SBO = 128 B, stride between 16-byte K chunks LBO = 2048 B.
-#define SSB_TC_ROWS 128
-
-__host__ __device__ __forceinline__ float ssb_tf32_round(float x) {   // round-to-nearest-even to a 10-bit mantissa
-#ifdef __CUDA_ARCH__
-    uint32_t u = __float_as_uint(x);
-#else
-    uint32_t u;
-    memcpy(&u, &x, 4);
-#endif
-    u += 0xfffu + ((u >> 13) & 1u);
-    u &= 0xffffe000u;
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(u);
-#else
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
-#endif
-}
-
-__device__ __forceinline__ uint64_t ssb_umma_desc(const void* smem_ptr) {
-    const uint32_t a = ssb_smem(smem_ptr);
-    return (uint64_t)((a >> 4) & 0x3fffu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void ssb_umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                              uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void ssb_tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    // the registers are valid only after wait::ld; tying them to the wait keeps every use behind it
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void ssb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void ssb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // Stc: [n_tiles][2 (hi, lo)][KP/4][16][8][4] floats.  dynamic smem: (2 + 2*2) * 128 * KP floats.
 // 256 threads: warps w and w + 4 own the same TMEM lane quadrant (the 32 trials of group 4*blockIdx.y + w % 4)

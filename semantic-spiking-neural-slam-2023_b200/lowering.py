@@ -24,6 +24,7 @@ The per-trial arena uses ``[row][trial]`` layout everywhere (trial is the coales
 from __future__ import annotations
 
 import dataclasses
+import os
 import numpy as np
 import scipy.sparse as sp
 
@@ -41,6 +42,8 @@ DEC_SMEM_BYTES = 96 * 1024  # shared-memory budget of a k_decode chunk (weights 
 SMEM_PER_SM = 227 * 1024
 PES_CTAS_PER_SM = 4         # k_pes: 116 registers x 128 threads
 DEC_CTAS_PER_SM = 5         # k_decode: 96 registers x 128 threads (before its shared-memory limit)
+DEC_TC_WIDTH = 64           # k_decode_tc: padded output width / neurons per stage of the tensor-core decoder
+DEC_TC_STAGE = 64
 
 
 def _best_chunks(n, units, slots_of, k_min, k_max, fixed=8, per_chunk=0.0):
@@ -180,8 +183,15 @@ class _Lowerer:
                     k_max = int(max(1, min(ens.n_neurons // 32, MAX_DEC_CHUNKS)))
                     self.dec_chunks[c] = _best_chunks(ens.n_neurons, jtiles * self.n_groups,
                                                       lambda per: N_SM * PES_CTAS_PER_SM, 1, k_max)
-                else:                  # k_decode: CTA = (decoder, trial group, neuron chunk), all outputs at once
+                else:                  # static decoders
                     jpad = -(-self._out_size(c) // DEC_TILE) * DEC_TILE
+                    quads = -(-self.n_groups // 4)
+                    if jpad <= DEC_TC_WIDTH and os.environ.get("SSB_DECODE") != "ffma":
+                        # k_decode_tc: CTA = (decoder, 128 trials, K chunk of 64-neuron stages), one CTA per SM
+                        n_stages = -(-ens.n_neurons // DEC_TC_STAGE)
+                        self.dec_chunks[c] = int(max(1, min(n_stages, N_SM // max(1, n_static * quads))))
+                        continue
+                    # k_decode (FFMA): CTA = (decoder, quad of trial groups, neuron chunk), all outputs at once
                     per_max = max(1, DEC_SMEM_BYTES // (jpad * 4 + 4 * 128))   # weight tile + 4 activity tiles of a chunk
                     need = -(-ens.n_neurons // per_max)
                     k_max = int(max(need, min(max(1, ens.n_neurons // 32), MAX_DEC_CHUNKS)))
