@@ -121,6 +121,9 @@ struct ssb_sim {
     int pes_level = -1;
     bool pes_needs_static = false;
     std::vector<LevelInfo> levels;
+    float* d_enc_t = nullptr;               // static wide encoders pre-tiled for k_wide_static_tc (3xTF32 hi | lo)
+    int* d_enc_t_off = nullptr;
+    std::vector<int> enc_t_off;             // host copy: -1 = not eligible
     float* d_dec_wt = nullptr;              // static decoders pre-tiled for k_decode_tc (3xTF32 hi | lo)
     int* d_dec_wt_off = nullptr;
     std::vector<char> dec_tc_level;         // per level: every decoder of the level can use the tensor-core kernel
@@ -411,7 +414,10 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
     }
 }
 
+bool launch_wide_tc(ssb_sim* s, cudaStream_t st, const int* stage, bool dry);
+
 void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int i_rel, bool dry = false) {
+    if (!voja && launch_wide_tc(s, st, stage, dry)) return;
     launch_wide_class<56>(s, st, stage, voja, 0, i_rel, dry);
     launch_wide_class<100>(s, st, stage, voja, 1, i_rel, dry);
     launch_wide_class<0>(s, st, stage, voja, 2, i_rel, dry);
@@ -455,6 +461,86 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
     }
     dim3 grid((max_out + 7) / 8, s->n_groups, s->n_pes * max_chunks);
     k_pes<<<grid, 128, s->pes_pad_smem, st>>>(s->ctx, s->d_pes, max_chunks, i_rel);
+}
+
+// SSB_ENCODE=tc selects the tensor-core wide-ensemble kernel.  Measured on B200 (BASELINE configs[1], 1024 trials):
+// k_wide_static (FFMA, 20 warps/SM) 33 us vs k_wide_static_tc 55 us per step: the GEMM is only 40 % of that kernel's
+// instructions and the 8-warp TMEM epilogue cannot hide the LIF dependency chains, so FFMA stays the default.
+bool encode_tc_allowed() {
+    const char* e = getenv("SSB_ENCODE");
+    return e && std::string(e) == "tc";
+}
+
+// Static wide-ensemble encoders [n][dpad] -> 64-neuron K-major operand tiles (hi | lo) in UMMA core-matrix order.
+int build_encode_tiles(ssb_sim* s) {
+    const int n_big = (int)(s->h_big.size() / 16);
+    s->enc_t_off.assign(n_big + 8, -1);
+    if (n_big == 0 || !encode_tc_allowed()) return 0;
+    const float* hW = reinterpret_cast<const float*>(s->arrays["weights"].bytes.data());
+    std::vector<float> et;
+    for (int i = 0; i < n_big; ++i) {
+        const int* d = &s->h_big[i * 16];
+        const int n = d[0], dpad = d[2], enc_off = d[5];
+        const int kp = (dpad + 7) / 8 * 8;
+        if ((d[9] & 1) || kp > 104 || d[11] > 4) continue;     // Voja ensembles keep per-trial encoders
+        const int n_tiles = (n + SSB_ETC_N - 1) / SSB_ETC_N, part = SSB_ETC_N * kp;
+        s->enc_t_off[i] = (int)et.size();
+        et.resize(et.size() + (size_t)n_tiles * 2 * part, 0.f);
+        float* base = &et[s->enc_t_off[i]];
+        for (int nn = 0; nn < n; ++nn) {
+            float* hi = base + (size_t)(nn / SSB_ETC_N) * 2 * part;
+            float* lo = hi + part;
+            const int r = nn % SSB_ETC_N;
+            for (int k = 0; k < dpad; ++k) {
+                const float x = hW[(size_t)enc_off + (size_t)nn * dpad + k];
+                const float h = ssb_tf32_round(x);
+                const size_t o = ((size_t)(k / 4) * 8 + r / 8) * 32 + (r % 8) * 4 + k % 4;
+                hi[o] = h;
+                lo[o] = ssb_tf32_round(x - h);
+            }
+        }
+    }
+    et.resize(et.size() + 8, 0.f);
+    SSB_CUDA(cudaMalloc((void**)&s->d_enc_t, et.size() * sizeof(float)));
+    SSB_CUDA(cudaMemcpy(s->d_enc_t, et.data(), et.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SSB_CUDA(cudaMalloc((void**)&s->d_enc_t_off, s->enc_t_off.size() * sizeof(int)));
+    SSB_CUDA(cudaMemcpy(s->d_enc_t_off, s->enc_t_off.data(), s->enc_t_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SSB_CUDA(cudaFuncSetAttribute(k_wide_static_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    return 0;
+}
+
+// Static wide ensembles of a level on the tensor-core kernel: one launch per operand width.  Returns false if
+// some ensemble of the level is not eligible (the caller then uses the FFMA kernels for the whole level).
+bool launch_wide_tc(ssb_sim* s, cudaStream_t st, const int* stage, bool dry) {
+    if (!s->d_enc_t) return false;
+    std::map<int, SsbItemList> by_kp;
+    std::map<int, int> max_n;
+    for (int i = 0; i < stage[3]; ++i) {
+        const int idx = stage[2] + i;
+        const int* d = &s->h_big[idx * 16];
+        if (d[9] & 1) continue;
+        if (s->enc_t_off[idx] < 0) return false;
+        const int kp = (d[2] + 7) / 8 * 8;
+        SsbItemList& L = by_kp[kp];
+        if (by_kp.count(kp) == 1 && max_n.count(kp) == 0) L.n = 0;
+        if (L.n >= 15) return false;
+        L.idx[L.n++] = idx;
+        max_n[kp] = std::max(max_n[kp], d[0]);
+    }
+    if (dry) return true;
+    for (auto& kv : by_kp) {
+        const int kp = kv.first;
+        const SsbItemList& L = kv.second;
+        const int quads = (s->n_groups + 3) / 4;
+        const int n_tiles = (max_n[kp] + SSB_ETC_N - 1) / SSB_ETC_N;
+        const size_t smem = (size_t)(2 * 128 + 4 * SSB_ETC_N) * kp * sizeof(float);
+        const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+        const int chunks_wanted = std::max(1, 148 * per_sm / std::max(1, quads * L.n));
+        const int tpc = std::max(1, (n_tiles + chunks_wanted - 1) / chunks_wanted);
+        dim3 grid((n_tiles + tpc - 1) / tpc, quads, L.n);
+        k_wide_static_tc<<<grid, 256, smem, st>>>(s->ctx, s->d_big, L, s->d_enc_t, s->d_enc_t_off, kp, tpc);
+    }
+    return true;
 }
 
 // SSB_DECODE=ffma forces the FFMA decoder kernel (measured comparison); default is tcgen05 when the output fits 64 columns.
@@ -887,6 +973,7 @@ int ssb_finalize(ssb_sim* s) {
     if ((int)s->h_stages.size() != s->n_levels * 12) return fail(-1, "ssb_finalize: stages array has wrong size");
     if (int rc = build_lin_program(s)) return rc;
     if (int rc = build_decode_tiles(s)) return rc;
+    if (int rc = build_encode_tiles(s)) return rc;
     s->levels.assign(s->n_levels, LevelInfo());
     for (int lvl = 0; lvl < s->n_levels; ++lvl) {
         const int* st = &s->h_stages[lvl * 12];
@@ -1153,7 +1240,7 @@ void ssb_destroy(ssb_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
-                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_enc_t, s->d_enc_t_off, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
                     s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);

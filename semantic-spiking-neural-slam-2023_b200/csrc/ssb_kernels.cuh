@@ -259,6 +259,12 @@ __device__ __forceinline__ uint64_t ssb_umma_desc(const void* smem_ptr) {
     return (uint64_t)((a >> 4) & 0x3fffu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
 }
 
+// same, with the stride between 16-byte K chunks given (= 128 B x row groups of the tile)
+__device__ __forceinline__ uint64_t ssb_umma_desc_lbo(const void* smem_ptr, uint32_t lbo_bytes) {
+    const uint32_t a = ssb_smem(smem_ptr);
+    return (uint64_t)((a >> 4) & 0x3fffu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
 __device__ __forceinline__ void ssb_umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate) {
     asm volatile(
@@ -579,6 +585,161 @@ __global__ void __launch_bounds__(128) k_wide_static(SsbCtx c, const int* __rest
     }
 }
 
+// Tensor-core variant of k_wide_static (tcgen05 + TMEM): the input currents of a static wide ensemble are the
+// GEMM J[trial][neuron] = X[trial][k] . E[neuron][k] with encoders shared by every trial.  CTA = (ensemble, block
+// of 128 trials, chunk of 64-neuron tiles).  A = X (128 x KP, K-major, 3xTF32 hi | lo) is built once from the
+// materialised input rows; B = encoder tiles (64 x KP, hi | lo, pre-tiled by the host) arrive by TMA in a
+// two-stage ring; D (128 lanes x 64 columns) is double-buffered in TMEM so the MMAs of tile i+1 overlap the
+// neuron epilogue of tile i: tcgen05.ld (lane = trial), + bias (+ direct neuron currents), LIF update on the
+// packed state rows (coalesced 128-byte loads / stores per neuron), activities to the act arena.
+// Et: [n_tiles][hi|lo][k/4][8 row groups][8][4] floats.  dynamic smem: (2*128 + 4*64) * KP floats.
+#define SSB_ETC_N 64
+__global__ void __launch_bounds__(256, 1)
+k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, const float* __restrict__ Et_all,
+                 const int* __restrict__ et_off, int KP, int tiles_per_chunk) {
+    extern __shared__ __align__(1024) float sm[];
+    __shared__ unsigned long long full[2], done[2];
+    __shared__ uint32_t tmem_slot;
+    const int item = items.idx[blockIdx.z];
+    const int* d = desc + item * 16;
+    const int n = d[0], dims = d[1], state0 = d[3], act0 = d[4], bias_off = d[6], in_row0 = d[7];
+    const int jn_row0 = d[10], jn_m = d[11], jn_w = d[12];
+    const float* __restrict__ Et = Et_all + et_off[item];
+    const int n_tiles = (n + SSB_ETC_N - 1) / SSB_ETC_N;
+    const int t_lo = blockIdx.x * tiles_per_chunk;
+    if (t_lo >= n_tiles) return;
+    const int my_tiles = min(n_tiles, t_lo + tiles_per_chunk) - t_lo;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int quad = warp & 3, half = warp >> 2;
+    const int group = blockIdx.y * 4 + quad;
+    const bool live = group < c.G;
+    const int g = live ? group : 0;
+    const SsbNeuron nt = ssb_neuron(c, d[8]);
+    const bool stateful = nt.type == 0;
+    const int a_part = 128 * KP, b_part = SSB_ETC_N * KP;
+    const uint32_t tile_bytes = 2u * b_part * 4u;
+    float* sA = sm;                                         // [hi|lo][a_part]
+    float* sB = sm + 2 * a_part;                            // [2 stages][hi|lo][b_part]
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (threadIdx.x == 0) {
+        ssb_mbar_init(&full[0], 1);
+        ssb_mbar_init(&full[1], 1);
+        ssb_mbar_init(&done[0], 1);
+        ssb_mbar_init(&done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 2 && i < my_tiles; ++i) {
+            ssb_mbar_expect_tx(&full[i], tile_bytes);
+            ssb_bulk_g2s(sB + (size_t)i * 2 * b_part, Et + (size_t)(t_lo + i) * 2 * b_part, tile_bytes, &full[i]);
+        }
+    }
+    float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    {   // A operand: this thread's trial is row r; the two warps of a quadrant alternate 32-column blocks
+        const int r = quad * 32 + lane;
+        float* a_hi = sA + (r >> 3) * 32 + (r & 7) * 4;
+        float* a_lo = a_hi + a_part;
+        const float* src = vg + (size_t)in_row0 * 32;
+        for (int k0 = half * 32; k0 < KP; k0 += 64) {
+            float x[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = (live && k0 + e < dims) ? src[(size_t)(k0 + e) * 32] : 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = k0 + 4 * q;
+                if (k < KP) {
+                    float4 hi, lo;
+                    hi.x = ssb_tf32_round(x[4 * q + 0]);
+                    hi.y = ssb_tf32_round(x[4 * q + 1]);
+                    hi.z = ssb_tf32_round(x[4 * q + 2]);
+                    hi.w = ssb_tf32_round(x[4 * q + 3]);
+                    lo.x = ssb_tf32_round(x[4 * q + 0] - hi.x);
+                    lo.y = ssb_tf32_round(x[4 * q + 1] - hi.y);
+                    lo.z = ssb_tf32_round(x[4 * q + 2] - hi.z);
+                    lo.w = ssb_tf32_round(x[4 * q + 3] - hi.w);
+                    *reinterpret_cast<float4*>(a_hi + (size_t)(k >> 2) * 16 * 32) = hi;
+                    *reinterpret_cast<float4*>(a_lo + (size_t)(k >> 2) * 16 * 32) = lo;
+                }
+            }
+        }
+    }
+    ssb_fence_async();
+    ssb_tc_fence_before();
+    __syncthreads();
+    ssb_tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SSB_ETC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto issue_mma = [&](int i) {
+        const int s = i & 1;
+        ssb_mbar_wait(&full[s], (uint32_t)(i >> 1) & 1u);
+        ssb_tc_fence_after();
+        const float* b_hi = sB + (size_t)s * 2 * b_part;
+        const uint32_t dst = tmem + (uint32_t)s * SSB_ETC_N;
+#pragma unroll 1
+        for (int j = 0; j < KP / 8; ++j) {
+            const size_t oa = (size_t)j * 2 * 16 * 32, ob = (size_t)j * 2 * 8 * 32;
+            const uint64_t ah = ssb_umma_desc_lbo(sA + oa, 2048), al = ssb_umma_desc_lbo(sA + a_part + oa, 2048);
+            const uint64_t bh = ssb_umma_desc_lbo(b_hi + ob, 1024), bl = ssb_umma_desc_lbo(b_hi + b_part + ob, 1024);
+            ssb_umma_tf32(dst, al, bh, idesc, j > 0);
+            ssb_umma_tf32(dst, ah, bl, idesc, 1);
+            ssb_umma_tf32(dst, ah, bh, idesc, 1);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ssb_smem(&done[s]))
+                     : "memory");
+    };
+    float u_jn[4];                                          // direct neuron currents (inhibition): a few inputs per trial
+#pragma unroll
+    for (int m = 0; m < 4; ++m) u_jn[m] = (m < jn_m) ? vg[(size_t)(jn_row0 + m) * 32] : 0.f;
+    float* sg = ssb_grp(c.st, c.nn, g, lane) + (size_t)state0 * 32;
+    float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
+    if (threadIdx.x == 0) issue_mma(0);
+    __syncwarp();
+    for (int i = 0; i < my_tiles; ++i) {
+        const int s = i & 1;
+        if (threadIdx.x == 0 && i + 1 < my_tiles) issue_mma(i + 1);
+        __syncwarp();
+        const int nn0 = (t_lo + i) * SSB_ETC_N + half * 32;     // first neuron of this thread's 32 columns
+        float sv[32];
+        if (stateful) {                                         // state rows in flight while the MMAs finish
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sv[j] = (live && nn0 + j < n) ? __ldcs(sg + (size_t)(nn0 + j) * 32) : 0.f;
+        }
+        ssb_mbar_wait(&done[s], (uint32_t)(i >> 1) & 1u);
+        ssb_tc_fence_after();
+        if (threadIdx.x == 0 && i + 2 < my_tiles) {
+            ssb_mbar_expect_tx(&full[s], tile_bytes);
+            ssb_bulk_g2s(sB + (size_t)s * 2 * b_part, Et + (size_t)(t_lo + i + 2) * 2 * b_part, tile_bytes, &full[s]);
+        }
+        __syncwarp();
+        float v[32];
+        ssb_tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * SSB_ETC_N + (uint32_t)half * 32, v);
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int nn = nn0 + j;
+                if (nn < n) {
+                    float J = v[j] + __ldg(c.W + bias_off + nn);
+                    for (int m = 0; m < jn_m && m < 4; ++m) J = fmaf(__ldg(c.W + jn_w + nn * jn_m + m), u_jn[m], J);
+                    float out;
+                    if (stateful) {
+                        float st = sv[j];
+                        out = nt.fast ? ssb_lif_packed<true>(nt, J, st) : ssb_lif_packed<false>(nt, J, st);
+                        __stcs(sg + (size_t)nn * 32, st);
+                    } else {
+                        out = ssb_rate(nt, J);
+                    }
+                    ag[(size_t)nn * 32] = out;
+                }
+            }
+        }
+        ssb_tc_fence_before();
+        __syncthreads();
+        ssb_tc_fence_after();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
 // Voja-learned ensemble (associative-memory keys): the scaled encoders are per trial, the `dims` rows
 // of one neuron are `dims` consecutive 128-byte lines.  Each warp streams its neurons' encoder tiles
 // through a double-buffered shared-memory stage with TMA bulk copies; lanes that spiked update their
@@ -879,11 +1040,6 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
 // Wt: [n_stages][hi|lo][k/4][8 row groups][8][4] floats (64 rows x 64 columns per part).
 #define SSB_DTC_KS 64          // neurons per stage
 #define SSB_DTC_N 64           // padded output width
-__device__ __forceinline__ uint64_t ssb_umma_desc_lbo(const void* smem_ptr, uint32_t lbo_bytes) {
-    const uint32_t a = ssb_smem(smem_ptr);
-    return (uint64_t)((a >> 4) & 0x3fffu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
-}
-
 __global__ void __launch_bounds__(256, 1)
 k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __restrict__ Wt_all, const int* __restrict__ wt_off) {
     extern __shared__ __align__(1024) float sm[];
