@@ -195,7 +195,10 @@ def load_traffic(kind):
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(path):
         with open(path) as f:
-            return json.load(f).get(kind)
+            entry = json.load(f).get(kind)
+        if isinstance(entry, dict):
+            return entry.get("dram_bytes_per_launch")
+        return entry
     return None
 
 

@@ -178,6 +178,35 @@ def test_generic_width_network_matches_oracle():
     assert _rel(got[1], _oracle(sc, sim, 1, 120).data[sc.probe]) < 1e-4
 
 
+@pytest.mark.parametrize("env", [{"SSB_SCAN": "ffma"}, {"SSB_DECODE": "ffma"}, {"SSB_ENCODE": "tc"},
+                                 {"SSB_SCAN": "ffma", "SSB_DECODE": "ffma", "SSB_SERIAL": "1"}])
+def test_alternate_kernel_paths_match_oracle(env, monkeypatch):
+    """Every shared-weight GEMM has an FFMA and a tcgen05 (3xTF32) kernel; whichever is selected, the
+    trajectory stays within the rate-mode tolerance and the clean-up index is the float64 argmax."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n_steps = 120
+    sc = scenarios.make_slam(n_trials=5, n_steps=n_steps, ssp_dim=55, pi_n_neurons=80, mem_n_neurons=160,
+                             circonv_n_neurons=24, n_landmarks=12, T=20.0, neuron_type="lifrate")
+    slam = sc.extra["slam"]
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=5, trial_inputs=sc.trial_inputs) as sim:
+        sim.run_steps(n_steps)
+        idx = sim.cleanup_indices()[0].copy()
+    got = sim.data[sc.probe]
+    for trial in (0, 4):
+        ref = _oracle(sc, sim, trial, n_steps)
+        assert _rel(got[trial], ref.data[sc.probe]) < 1e-4
+        x = ref.signals[slam.gridcells, "in"].a
+        assert idx[trial] == ssp_ref.cleanup_index(slam.sample_ssps, x)
+
+
+def test_ssp_decode_ffma_scan_is_bit_exact_too(golden, monkeypatch):
+    monkeypatch.setenv("SSB_SCAN", "ffma")
+    sp = HexagonalSSPSpace(2, ssp_dim=55, domain_bounds=BOUNDS2, length_scale=0.2)
+    ssps, _ = sp.get_sample_pts_and_ssps(100, "grid")
+    assert np.array_equal(cabi.ssp_decode_argmax(ssps, golden["dec55_in"]), golden["dec55_idx"])
+
+
 # ------------------------------------------------------------------------------- simulator surface
 def test_simulator_surface_run_trange_reset_unbatched():
     sc = scenarios.make_pathint(n_trials=1, n_steps=120, ssp_dim=19, pi_n_neurons=50, neuron_type="lif")
