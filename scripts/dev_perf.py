@@ -9,7 +9,17 @@ from sspslam_b200.simulator import Simulator
 B = int(os.environ.get("B", "1024"))
 steps = int(os.environ.get("STEPS", "64"))
 reps = int(os.environ.get("REPS", "4"))
-sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=8)
+cfg = os.environ.get("CONFIG", "slam55")
+if cfg == "pathint97":      # BASELINE configs[0]
+    sc = scenarios.make_pathint(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=97, pi_n_neurons=500, neuron_type="lif")
+elif cfg == "slamview97":   # BASELINE configs[3] sizes
+    sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=97, pi_n_neurons=800, mem_n_neurons=970,
+                             circonv_n_neurons=100, n_landmarks=100, T=200.0, length_scale=0.3, view=True, distinct_tables=8)
+elif cfg == "slam55gif":    # BASELINE configs[2] sizes (run_slam_map_gif.py defaults)
+    sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=55, pi_n_neurons=800, mem_n_neurons=1000,
+                             circonv_n_neurons=100, n_landmarks=50, T=200.0, length_scale=0.1, distinct_tables=8)
+else:
+    sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=8)
 sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, chunk_steps=steps)
 bytes_ts = lowering.algorithmic_bytes_per_trial_step(sim.plan.stats)
 sim.run_steps(steps)
@@ -19,7 +29,7 @@ for rep in range(reps):
     ms = sim.last_run_ms()
     out.append(ms / steps * 1e3)
 tps = B / (min(out) * 1e-6)
-print(f"[perf {os.environ.get('TAG','')}] us/step " + " ".join(f"{x:.1f}" for x in out) +
+print(f"[perf {cfg} {os.environ.get('TAG','')}] neurons {sim.plan.stats['n_neurons']} bytes/trial-step {bytes_ts} us/step " + " ".join(f"{x:.1f}" for x in out) +
       f" -> best {tps/1e6:.3f} M trial-steps/s ({tps*bytes_ts/1e9/6535.4:.3f} of HBM model)")
 if os.environ.get("KERNELS"):
     sim.set_profiling(True)

@@ -392,7 +392,7 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
     } else {
         int nwarps = 4;
         auto smem_of = [&](int nw) {
-            return (size_t)(max_dpad * 32 + max_jn * 32 + nw * 2 * max_dims * 32) * sizeof(float) + s->voja_pad_smem;
+            return (size_t)(max_dpad * 32 + max_jn * 32 + nw * SSB_VOJA_NB * max_dims * 32) * sizeof(float) + s->voja_pad_smem;
         };
         while (nwarps > 1 && smem_of(nwarps) > 200 * 1024) nwarps >>= 1;
         // one wave: every resident CTA slot gets one contiguous neuron range of a trial group

@@ -746,11 +746,12 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
 // column in place and the tile is written back only if some lane spiked (post_synapse=None => the
 // delta is row-sparse).  SimVoja: delta = alpha*L*(scale*outer(post, x) - post[:,None]*E), visible
 // to the next step.
+#define SSB_VOJA_NB 3         // encoder tiles in flight per warp
 template <int DP>
 __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restrict__ desc, SsbItemList items, int chunk,
                                                     int i_rel) {
     extern __shared__ __align__(128) float sm[];
-    __shared__ unsigned long long wbar[4][2];
+    __shared__ unsigned long long wbar[4][SSB_VOJA_NB];
     const int* d = desc + items.idx[blockIdx.z] * 16;
     const int n = d[0], dims = d[1], dpad = d[2], state0 = d[3], act0 = d[4], enc_off = d[5], bias_off = d[6];
     const int in_row0 = d[7], jn_row0 = d[10], jn_m = d[11], jn_w = d[12], voja_row = d[13], scale_off = d[14];
@@ -763,16 +764,15 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
     const bool stateful = nt.type == 0;
     float* xs = sm;                                        // [dpad][32]
     float* us = xs + (size_t)dpad * 32;                    // [jn_m][32]
-    float* ebuf = us + (size_t)jn_m * 32 + (size_t)warp * 2 * dims * 32;   // [2][dims][32] per warp
+    float* ebuf = us + (size_t)jn_m * 32 + (size_t)warp * SSB_VOJA_NB * dims * 32;   // [NB][dims][32] per warp
     const int per = (chunk + nwarps - 1) / nwarps;
     const int i_lo = warp * per, i_hi = min(cnt, i_lo + per);
     float* eg = c.lenc + ((size_t)g * c.n_lenc + enc_off + (size_t)(n0 + i_lo) * dims) * 32;   // tile of neuron i_lo
     const uint32_t tile_bytes = (uint32_t)dims * 128;
     if (lane == 0) {
-        ssb_mbar_init(&wbar[warp][0], 1);
-        ssb_mbar_init(&wbar[warp][1], 1);
+        for (int t = 0; t < SSB_VOJA_NB; ++t) ssb_mbar_init(&wbar[warp][t], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int t = 0; t < 2 && i_lo + t < i_hi; ++t) {
+        for (int t = 0; t < SSB_VOJA_NB && i_lo + t < i_hi; ++t) {
             ssb_mbar_expect_tx(&wbar[warp][t], tile_bytes);
             ssb_bulk_g2s(ebuf + (size_t)t * dims * 32, eg + (size_t)t * dims * 32, tile_bytes, &wbar[warp][t]);
         }
@@ -791,13 +791,13 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
     float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)(act0 + n0) * 32;
     uint32_t phases = 0;
     for (int i = i_lo; i < i_hi; ++i) {
-        const int t = i - i_lo, b = t & 1;
+        const int t = i - i_lo, b = t % SSB_VOJA_NB;
         float* E = ebuf + (size_t)b * dims * 32 + lane;
         float sv = 0.f;
         if (stateful) sv = __ldcs(sp + (size_t)i * 32);
         float J = __ldg(c.W + bias_off + n0 + i);
         for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + (n0 + i) * jn_m + m), us[m * 32 + lane], J);
-        ssb_mbar_wait(&wbar[warp][b], (phases >> b) & 1u);
+        ssb_mbar_wait(&wbar[warp][b], (phases >> b) & 1u);   // phases: one parity bit per buffer
         phases ^= 1u << b;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (DP > 0) {
@@ -846,20 +846,19 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
             }
         }
         const bool dirty = __any_sync(0xffffffffu, fired);
-        if (dirty) {
-            ssb_fence_async();
-            __syncwarp();
-            if (lane == 0) {
-                ssb_bulk_s2g(eg + (size_t)t * dims * 32, ebuf + (size_t)b * dims * 32, tile_bytes);
-                ssb_bulk_commit();
-            }
-        }
-        if (i + 2 < i_hi) {
-            if (dirty && lane == 0) ssb_bulk_wait_read0();
-            __syncwarp();
-            if (lane == 0) {
-                ssb_mbar_expect_tx(&wbar[warp][b], tile_bytes);
-                ssb_bulk_g2s(ebuf + (size_t)b * dims * 32, eg + (size_t)(t + 2) * dims * 32, tile_bytes, &wbar[warp][b]);
+        if (dirty) ssb_fence_async();
+        __syncwarp();
+        if (lane == 0) {
+            // one bulk group per tile (empty when the tile is clean) keeps the group count in step with the tiles:
+            // before buffer b_prev = (t - 1) % NB is refilled, only the group of tile t may still be reading
+            if (dirty) ssb_bulk_s2g(eg + (size_t)t * dims * 32, ebuf + (size_t)b * dims * 32, tile_bytes);
+            ssb_bulk_commit();
+            if (t >= 1 && i + SSB_VOJA_NB - 1 < i_hi) {
+                const int bp = (t - 1) % SSB_VOJA_NB;
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                ssb_mbar_expect_tx(&wbar[warp][bp], tile_bytes);
+                ssb_bulk_g2s(ebuf + (size_t)bp * dims * 32, eg + (size_t)(t - 1 + SSB_VOJA_NB) * dims * 32, tile_bytes,
+                             &wbar[warp][bp]);
             }
         }
     }

@@ -270,3 +270,32 @@ def test_full_size_config2_properties():
     real = sc.real_ssp[:, :300]
     cos = np.sum(out[:, -1] * real[:, -1], axis=1) / (np.linalg.norm(out[:, -1], axis=1) * np.linalg.norm(real[:, -1], axis=1))
     assert np.mean(cos) > 0.6
+
+
+def test_full_size_config1_pathint_d97_rate_mode_matches_oracle():
+    """BASELINE configs[0]: run_pathint.py defaults (d = 97, 49 VCOs x 500): generic-width kernels at full size."""
+    n_steps = 150
+    sc = scenarios.make_pathint(n_trials=32, n_steps=n_steps, ssp_dim=97, pi_n_neurons=500, neuron_type="lifrate")
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=32, trial_inputs=sc.trial_inputs) as sim:
+        assert sim.plan.stats["n_neurons"] == 24500
+        sim.run_steps(n_steps)
+    got = sim.data[sc.probe]
+    assert got.shape == (32, n_steps, 97) and np.all(np.isfinite(got))
+    for trial in (0, 31):
+        assert _rel(got[trial], _oracle(sc, sim, trial, n_steps).data[sc.probe]) < 1e-4
+
+
+def test_full_size_config4_slamview_d97_rate_mode_matches_oracle():
+    """BASELINE configs[3] sizes: SLAMViewNetwork, d = 97, pi 800, mem 970, 100 landmarks, PES + Voja per trial."""
+    n_steps = 100
+    sc = scenarios.make_slam(n_trials=32, n_steps=n_steps, ssp_dim=97, pi_n_neurons=800, mem_n_neurons=970,
+                             circonv_n_neurons=100, n_landmarks=100, T=20.0, length_scale=0.3, neuron_type="lifrate",
+                             view=True, distinct_tables=4)
+    slam = sc.extra["slam"]
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=32, trial_inputs=sc.trial_inputs) as sim:
+        assert sim.plan.stats["n_neurons"] == 42110
+        sim.run_steps(n_steps)
+        dec = sim.learned_decoders(slam.assomemory.conn_out)
+    got = sim.data[sc.probe]
+    assert np.all(np.isfinite(got)) and np.all(np.isfinite(dec))
+    assert _rel(got[1], _oracle(sc, sim, 1, n_steps).data[sc.probe]) < 1e-4
