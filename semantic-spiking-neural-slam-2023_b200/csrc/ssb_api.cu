@@ -42,16 +42,23 @@ struct CleanupDev {
     // tensor-core scan (k_cleanup_scan_tc): pre-tiled 3xTF32 grid, K padded to a multiple of 8
     bool tc = false;
     float* stc = nullptr;
-    int kp = 0, n_tiles = 0;
+    int kp = 0, n_tiles = 0, tr = 128;
 };
+
+// grid rows per tensor-core tile: 128, or 64 when the operand tiles of 128 rows do not fit in shared memory; 0 = no fit
+int scan_tc_rows(int dpad) {
+    const int kp = (dpad + 7) / 8 * 8;
+    for (int tr : {128, 64})
+        if ((size_t)(2 * 128 + 4 * tr) * kp * sizeof(float) <= 216 * 1024) return tr;
+    return 0;
+}
 
 // SSB_SCAN=ffma forces the FFMA scan (the measured comparison in DESIGN.md); default is the tcgen05 scan
 // whenever its operand tiles fit in shared memory.
 bool scan_tc_allowed(int dpad) {
     const char* e = getenv("SSB_SCAN");
     if (e && std::string(e) == "ffma") return false;
-    const int kp = (dpad + 7) / 8 * 8;
-    return (size_t)6 * SSB_TC_ROWS * kp * sizeof(float) <= 216 * 1024;
+    return scan_tc_rows(dpad) > 0;
 }
 
 // Grid-scan geometry: a CTA scans rows_per_chunk grid rows in shared-memory tiles of tile_rows rows for 4 trial
@@ -62,9 +69,10 @@ void scan_geometry(int G, int dpad, int n_groups, CleanupDev* cd) {
     if (scan_tc_allowed(dpad)) {   // one CTA per SM: trial blocks x grid chunks ~ 148
         cd->tc = true;
         cd->kp = (dpad + 7) / 8 * 8;
-        cd->n_tiles = (G + SSB_TC_ROWS - 1) / SSB_TC_ROWS;
+        cd->tr = scan_tc_rows(dpad);
+        cd->n_tiles = (G + cd->tr - 1) / cd->tr;
         cd->n_chunks = std::max(1, std::min(std::min(cd->n_tiles, SSB_SCAN_MAX_CHUNKS), 148 / std::max(1, group_ctas)));
-        cd->rows_per_chunk = cd->tile_rows = SSB_TC_ROWS;
+        cd->rows_per_chunk = cd->tile_rows = cd->tr;
         return;
     }
     int want = std::max(1, (148 * 8 + group_ctas - 1) / group_ctas);
@@ -126,6 +134,7 @@ struct ssb_sim {
     std::vector<int> enc_t_off;             // host copy: -1 = not eligible
     float* d_dec_wt = nullptr;              // static decoders pre-tiled for k_decode_tc (3xTF32 hi | lo)
     int* d_dec_wt_off = nullptr;
+    int dec_tc_n = 64;                      // operand tile width of k_decode_tc (64 or 128 output columns)
     std::vector<char> dec_tc_level;         // per level: every decoder of the level can use the tensor-core kernel
     size_t pes_pad_smem = 0, voja_pad_smem = 0;   // experiment knobs: extra dynamic smem lowers residency
     std::map<int, int> wide_chunk_cache;   // launch geometry of the wide-ensemble kernels, decided once
@@ -276,16 +285,16 @@ int collect_profile(ssb_sim* s) {
 
 // Grid rows -> 3xTF32 operand tiles in UMMA core-matrix order: [tile][hi|lo][k/4][row/8][row%8][k%4].
 int build_scan_tiles(const float* S32, int G, int dpad, CleanupDev* cd) {
-    const int kp = cd->kp, part = SSB_TC_ROWS * kp;
+    const int kp = cd->kp, tr = cd->tr, part = tr * kp;
     std::vector<float> t((size_t)cd->n_tiles * 2 * part, 0.f);
     for (int g = 0; g < G; ++g) {
-        const int tile = g / SSB_TC_ROWS, r = g % SSB_TC_ROWS;
+        const int tile = g / tr, r = g % tr;
         float* hi = &t[(size_t)tile * 2 * part];
         float* lo = hi + part;
         for (int k = 0; k < dpad; ++k) {
             const float x = S32[(size_t)g * dpad + k];
             const float h = ssb_tf32_round(x);
-            const size_t off = ((size_t)(k / 4) * 16 + r / 8) * 32 + (r % 8) * 4 + k % 4;
+            const size_t off = ((size_t)(k / 4) * (tr / 8) + r / 8) * 32 + (r % 8) * 4 + k % 4;
             hi[off] = h;
             lo[off] = ssb_tf32_round(x - h);
         }
@@ -297,12 +306,18 @@ int build_scan_tiles(const float* S32, int G, int dpad, CleanupDev* cd) {
 
 void launch_scan_tc(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const CleanupDev& cd, int n_groups) {
     dim3 grid(cd.n_chunks, (n_groups + 3) / 4);
-    const size_t smem = (size_t)6 * SSB_TC_ROWS * cd.kp * sizeof(float);
+    const size_t smem = (size_t)(2 * 128 + 4 * cd.tr) * cd.kp * sizeof(float);
     const int n_cand = cd.n_chunks * SSB_TOPK * 2;
-    if (csr)
-        k_cleanup_scan_tc<true><<<grid, 256, smem, st>>>(c, desc, cd.stc, cd.cx, cd.pval, cd.pidx, cd.kp, cd.n_tiles, n_groups, n_cand);
-    else
-        k_cleanup_scan_tc<false><<<grid, 256, smem, st>>>(c, desc, cd.stc, cd.cx, cd.pval, cd.pidx, cd.kp, cd.n_tiles, n_groups, n_cand);
+#define SSB_SCAN_TC(CSR, TR) \
+    k_cleanup_scan_tc<CSR, TR><<<grid, 256, smem, st>>>(c, desc, cd.stc, cd.cx, cd.pval, cd.pidx, cd.kp, cd.n_tiles, n_groups, n_cand)
+    if (cd.tr == 128) {
+        if (csr) SSB_SCAN_TC(true, 128);
+        else SSB_SCAN_TC(false, 128);
+    } else {
+        if (csr) SSB_SCAN_TC(true, 64);
+        else SSB_SCAN_TC(false, 64);
+    }
+#undef SSB_SCAN_TC
 }
 
 // candidates per trial left by the scan (the tensor-core scan keeps two lists per chunk)
@@ -338,8 +353,10 @@ void scan_smem_optin() {
     const int lim = 200 * 1024;
     cudaFuncSetAttribute(k_cleanup_scan<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_cleanup_scan<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_cleanup_scan_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_cleanup_scan_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_cleanup_scan_tc<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_cleanup_scan_tc<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_cleanup_scan_tc<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_cleanup_scan_tc<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 
 // Wide ensembles of one level: one launch per (kernel flavour, width class); the items of a launch are
@@ -549,48 +566,49 @@ bool decode_tc_allowed() {
     return !(e && std::string(e) == "ffma");
 }
 
-// Static decoders [n][jpad] -> per 64-neuron stage: Wd^T as 64 x 64 K-major operand tiles (hi | lo) in UMMA core-matrix order.
+// Static decoders [n][jpad] -> per K stage: Wd^T as N x KS K-major operand tiles (hi | lo) in UMMA core-matrix order.
+// (N, KS) = (64, 64) when every decoder of the plan fits 64 columns, else (128, 32) up to 128 columns.
 int build_decode_tiles(ssb_sim* s) {
     const int n_dec = (int)(s->h_dec.size() / 9);
     s->dec_tc_level.assign(s->n_levels, 0);
     if (n_dec == 0 || !decode_tc_allowed()) return 0;
+    int max_jpad = 0;
+    for (int i = 0; i < n_dec; ++i) max_jpad = std::max(max_jpad, s->h_dec[i * 9 + 2]);
+    if (max_jpad > 128) return 0;
+    const int N = max_jpad <= 64 ? 64 : 128, KS = max_jpad <= 64 ? 64 : 32;
+    s->dec_tc_n = N;
     const float* hW = reinterpret_cast<const float*>(s->arrays["weights"].bytes.data());
     std::vector<float> wt;
     std::vector<int> off(n_dec + 8, -1);
-    const int part = SSB_DTC_N * SSB_DTC_KS;
+    const int part = N * KS;
     for (int i = 0; i < n_dec; ++i) {
         const int* d = &s->h_dec[i * 9];
         const int n = d[0], jpad = d[2], w_off = d[4];
-        if (jpad > SSB_DTC_N) continue;
-        const int n_stages = (n + SSB_DTC_KS - 1) / SSB_DTC_KS;
+        const int n_stages = (n + KS - 1) / KS;
         off[i] = (int)wt.size();
         wt.resize(wt.size() + (size_t)n_stages * 2 * part, 0.f);
         float* base = &wt[off[i]];
         for (int k = 0; k < n; ++k) {
-            const int st = k / SSB_DTC_KS, kk = k % SSB_DTC_KS;
+            const int st = k / KS, kk = k % KS;
             float* hi = base + (size_t)st * 2 * part;
             float* lo = hi + part;
             for (int j = 0; j < jpad; ++j) {
                 const float x = hW[(size_t)w_off + (size_t)k * jpad + j];
                 const float h = ssb_tf32_round(x);
-                const size_t o = ((size_t)(kk / 4) * 8 + j / 8) * 32 + (j % 8) * 4 + kk % 4;
+                const size_t o = ((size_t)(kk / 4) * (N / 8) + j / 8) * 32 + (j % 8) * 4 + kk % 4;
                 hi[o] = h;
                 lo[o] = ssb_tf32_round(x - h);
             }
         }
     }
-    for (int lvl = 0; lvl < s->n_levels; ++lvl) {
-        const int* st = &s->h_stages[lvl * 12];
-        bool all = st[5] > 0;
-        for (int i = 0; i < st[5]; ++i) all = all && off[st[4] + i] >= 0;
-        s->dec_tc_level[lvl] = all ? 1 : 0;
-    }
+    for (int lvl = 0; lvl < s->n_levels; ++lvl) s->dec_tc_level[lvl] = s->h_stages[lvl * 12 + 5] > 0 ? 1 : 0;
     wt.resize(wt.size() + 8, 0.f);
     SSB_CUDA(cudaMalloc((void**)&s->d_dec_wt, wt.size() * sizeof(float)));
     SSB_CUDA(cudaMemcpy(s->d_dec_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
     SSB_CUDA(cudaMalloc((void**)&s->d_dec_wt_off, off.size() * sizeof(int)));
     SSB_CUDA(cudaMemcpy(s->d_dec_wt_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
-    SSB_CUDA(cudaFuncSetAttribute(k_decode_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SSB_CUDA(cudaFuncSetAttribute(k_decode_tc<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SSB_CUDA(cudaFuncSetAttribute(k_decode_tc<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return 0;
 }
 
@@ -819,8 +837,11 @@ int one_step(ssb_sim* s, int i_rel) {
                 smem = std::max(smem, (per * d[2] + 4 * per * 32) * sizeof(float));
             }
             dim3 grid(max_chunks, (G + 3) / 4, st[5]);
-            if (s->dec_tc_level[lvl])
-                k_decode_tc<<<grid, 256, (size_t)(4 * 128 * SSB_DTC_KS + 4 * SSB_DTC_N * SSB_DTC_KS) * sizeof(float), D>>>(
+            if (s->dec_tc_level[lvl] && s->dec_tc_n == 64)
+                k_decode_tc<64, 64><<<grid, 256, (size_t)(4 * 128 * 64 + 4 * 64 * 64) * sizeof(float), D>>>(
+                    c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off);
+            else if (s->dec_tc_level[lvl])
+                k_decode_tc<128, 32><<<grid, 256, (size_t)(4 * 128 * 32 + 4 * 128 * 32) * sizeof(float), D>>>(
                     c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off);
             else
                 k_decode<<<grid, 128, smem, D>>>(c, s->d_dec, st[4]);

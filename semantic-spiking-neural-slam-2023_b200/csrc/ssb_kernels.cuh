@@ -1037,8 +1037,8 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
 // The epilogue reads D with tcgen05.ld (lane = trial) and writes the output rows (or split-K partial sums,
 // combined in chunk order by the last CTA to arrive, as in the FFMA kernel).
 // Wt: [n_stages][hi|lo][k/4][8 row groups][8][4] floats (64 rows x 64 columns per part).
-#define SSB_DTC_KS 64          // neurons per stage
-#define SSB_DTC_N 64           // padded output width
+// Instantiated for <N = 64 outputs, KS = 64 neurons per stage> and <N = 128, KS = 32> (wider decoders, e.g. d = 97).
+template <int SSB_DTC_N, int SSB_DTC_KS>
 __global__ void __launch_bounds__(256, 1)
 k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __restrict__ Wt_all, const int* __restrict__ wt_off) {
     extern __shared__ __align__(1024) float sm[];
@@ -1064,7 +1064,7 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
     float* sA = sm;                                     // [2 buffers][hi|lo][A_PART]
     float* sB = sm + 4 * A_PART;                        // [2 buffers][hi|lo][B_PART]
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(64));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(SSB_DTC_N));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (threadIdx.x == 0) {
@@ -1084,7 +1084,8 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
     const uint32_t tmem = tmem_slot;
     // D fp32, A/B tf32, both K-major, N = 64, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SSB_DTC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int r = quad * 32 + lane;                     // this thread's trial row; `half` picks its 32 of the 64 columns
+    const int r = quad * 32 + lane;                     // this thread's trial row; `half` picks its half of the stage's columns
+    constexpr int HK = SSB_DTC_KS / 2;                  // activity rows per thread and stage
     const float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
     for (int i = 0; i < my; ++i) {
         const int b = i & 1;
@@ -1096,15 +1097,15 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
                 ssb_bulk_g2s(sB + (size_t)b * 2 * B_PART, Wt + (size_t)(s_lo + i) * 2 * B_PART, 2u * B_PART * 4u, &full[b]);
             }
         }
-        {   // A stage: 32 activity rows per thread, all loads issued before they are consumed
-            const int k0 = (s_lo + i) * SSB_DTC_KS + half * 32;
-            float x[32];
+        {   // A stage: HK activity rows per thread, all loads issued before they are consumed
+            const int k0 = (s_lo + i) * SSB_DTC_KS + half * HK;
+            float x[HK];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) x[e] = (live && k0 + e < n) ? ag[(size_t)(k0 + e) * 32] : 0.f;
-            float* a_hi = sA + (size_t)b * 2 * A_PART + (r >> 3) * 32 + (r & 7) * 4 + (size_t)(half * 8) * 16 * 32;
+            for (int e = 0; e < HK; ++e) x[e] = (live && k0 + e < n) ? ag[(size_t)(k0 + e) * 32] : 0.f;
+            float* a_hi = sA + (size_t)b * 2 * A_PART + (r >> 3) * 32 + (r & 7) * 4 + (size_t)(half * (HK / 4)) * 16 * 32;
             float* a_lo = a_hi + A_PART;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < HK / 4; ++q) {
                 float4 hi, lo;
                 hi.x = ssb_tf32_round(x[4 * q + 0]);
                 hi.y = ssb_tf32_round(x[4 * q + 1]);
@@ -1129,9 +1130,10 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
             const float* bh = sB + (size_t)b * 2 * B_PART;
 #pragma unroll 1
             for (int j = 0; j < SSB_DTC_KS / 8; ++j) {
-                const size_t oa = (size_t)j * 2 * 16 * 32, ob = (size_t)j * 2 * 8 * 32;   // two 16-byte K chunks per MMA
+                const size_t oa = (size_t)j * 2 * 16 * 32, ob = (size_t)j * 2 * (SSB_DTC_N / 8) * 32;   // two 16-byte K chunks per MMA
                 const uint64_t dah = ssb_umma_desc_lbo(ah + oa, 2048), dal = ssb_umma_desc_lbo(ah + A_PART + oa, 2048);
-                const uint64_t dbh = ssb_umma_desc_lbo(bh + ob, 1024), dbl = ssb_umma_desc_lbo(bh + B_PART + ob, 1024);
+                const uint64_t dbh = ssb_umma_desc_lbo(bh + ob, (SSB_DTC_N / 8) * 128);
+                const uint64_t dbl = ssb_umma_desc_lbo(bh + B_PART + ob, (SSB_DTC_N / 8) * 128);
                 ssb_umma_tf32(tmem, dal, dbh, idesc, (i > 0 || j > 0) ? 1u : 0u);
                 ssb_umma_tf32(tmem, dah, dbl, idesc, 1);
                 ssb_umma_tf32(tmem, dah, dbh, idesc, 1);
@@ -1147,25 +1149,30 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
         // the commit of the last stage covers every earlier MMA
         ssb_mbar_wait(&done[(my - 1) & 1], (uint32_t)((my - 1) >> 1) & 1u);
         ssb_tc_fence_after();
-        float v[32];
-        ssb_tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 32, v);
-        if (live) {
+#pragma unroll 1
+        for (int cb = 0; cb < SSB_DTC_N / 64; ++cb) {       // this warp's half of the columns, 32 at a time
+            const int c0 = half * (SSB_DTC_N / 2) + cb * 32;
+            float v[32];
+            ssb_tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+            if (live) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int jo = half * 32 + j;
-                if (jo < size_out) {
-                    if (n_chunks == 1) vg[(size_t)(out_vec + jo) * 32] = v[j];
-                    else pg[(size_t)(part_off + chunk * size_out + jo) * 32] = v[j];
+                for (int j = 0; j < 32; ++j) {
+                    const int jo = c0 + j;
+                    if (jo < size_out) {
+                        if (n_chunks == 1) vg[(size_t)(out_vec + jo) * 32] = v[j];
+                        else pg[(size_t)(part_off + chunk * size_out + jo) * 32] = v[j];
+                    }
                 }
             }
         }
     } else if (live && n_chunks > 1) {                  // an empty trailing chunk still owns its partial slot
-        for (int j = half * 32; j < min(size_out, half * 32 + 32); ++j) pg[(size_t)(part_off + chunk * size_out + j) * 32] = 0.f;
+        for (int j = half * (SSB_DTC_N / 2); j < min(size_out, (half + 1) * (SSB_DTC_N / 2)); ++j)
+            pg[(size_t)(part_off + chunk * size_out + j) * 32] = 0.f;
     }
     ssb_tc_fence_before();
     __threadfence();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(SSB_DTC_N));
     if (n_chunks == 1) return;
     // split-K: one arrival counter per (decoder, trial group); the CTA that arrives last adds the partials in chunk order
     if (half == 0) {
@@ -1183,7 +1190,7 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
     __syncthreads();
     if (!s_last[quad]) return;
     __threadfence();
-    for (int j = half * 32; j < min(size_out, half * 32 + 32); j += 8) {   // the two warps of a group split the outputs
+    for (int j = half * (SSB_DTC_N / 2); j < min(size_out, (half + 1) * (SSB_DTC_N / 2)); j += 8) {   // the two warps of a group split the outputs
         float t[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) t[u] = 0.f;
@@ -1475,12 +1482,13 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
 //   float offset(row r, column k) = ((k / 4) * 16 + r / 8) * 32 + (r % 8) * 4 + k % 4
 // => stride between 8-row groups SBO = 128 B, stride between 16-byte K chunks LBO = 2048 B.
 
-// Stc: [n_tiles][2 (hi, lo)][KP/4][16][8][4] floats.  dynamic smem: (2 + 2*2) * 128 * KP floats.
+// Stc: [n_tiles][2 (hi, lo)][KP/4][TR/8][8][4] floats, TR = 128 grid rows per tile (64 when 128 does not fit in
+// shared memory, e.g. d = 97).  dynamic smem: (2 * 128 + 4 * TR) * KP floats.
 // 256 threads: warps w and w + 4 own the same TMEM lane quadrant (the 32 trials of group 4*blockIdx.y + w % 4)
 // and drain the two halves of every tile's columns, each into its own top-4 list (candidate slot
 // (2 * chunk + half) * 4 + i), so two warps per scheduler hide the insert latency.
 // desc: G d dpad s_off in_row0 out_vec
-template <bool CSR_INPUT>
+template <bool CSR_INPUT, int TR>
 __global__ void __launch_bounds__(256, 1)
 k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__ Stc, float* __restrict__ cx,
                   float* __restrict__ pval, int* __restrict__ pidx, int KP, int n_tiles, int n_groups, int n_cand) {
@@ -1495,12 +1503,13 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
     const int g = live ? group : 0;
     const int chunk = blockIdx.x, n_chunks = gridDim.x;
     const int my_tiles = chunk < n_tiles ? (n_tiles - chunk + n_chunks - 1) / n_chunks : 0;
-    const int part_floats = SSB_TC_ROWS * KP;               // one operand part (hi or lo)
-    const uint32_t tile_bytes = 2u * part_floats * 4u;      // hi + lo
+    const int part_floats = 128 * KP;                       // one part (hi or lo) of the A operand (128 trials)
+    const int b_part = TR * KP;                             // one part of a grid tile (TR rows)
+    const uint32_t tile_bytes = 2u * b_part * 4u;           // hi + lo
     float* sA = sm;                                         // [2][part]
     float* sB = sm + 2 * part_floats;                       // [2 stages][2][part]
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(2 * TR));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (threadIdx.x == 0) {
@@ -1511,8 +1520,7 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int i = 0; i < 2 && i < my_tiles; ++i) {
             ssb_mbar_expect_tx(&full[i], tile_bytes);
-            ssb_bulk_g2s(sB + (size_t)i * 2 * part_floats, Stc + (size_t)(chunk + i * n_chunks) * 2 * part_floats, tile_bytes,
-                         &full[i]);
+            ssb_bulk_g2s(sB + (size_t)i * 2 * b_part, Stc + (size_t)(chunk + i * n_chunks) * 2 * b_part, tile_bytes, &full[i]);
         }
     }
     {   // A operand: this thread's trial is row r of the tile; four K columns per 16-byte store.
@@ -1561,18 +1569,19 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
     ssb_tc_fence_after();
     const uint32_t tmem = tmem_slot;
     // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SSB_TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     auto issue_mma = [&](int i) {   // one thread: wait for the tile, queue its 3 * KP/8 MMAs, commit
         const int s = i & 1;
         ssb_mbar_wait(&full[s], (uint32_t)(i >> 1) & 1u);
         ssb_tc_fence_after();
-        const float* b_hi = sB + (size_t)s * 2 * part_floats;
-        const float* b_lo = b_hi + part_floats;
-        const uint32_t dst = tmem + (uint32_t)s * SSB_TC_ROWS;
+        const float* b_hi = sB + (size_t)s * 2 * b_part;
+        const float* b_lo = b_hi + b_part;
+        const uint32_t dst = tmem + (uint32_t)s * TR;
         for (int j = 0; j < KP / 8; ++j) {
             const size_t off = (size_t)j * 2 * 16 * 32;     // two 16-byte K chunks per MMA
+            const size_t ob = (size_t)j * 2 * (TR / 8) * 32;
             const uint64_t ah = ssb_umma_desc(sA + off), al = ssb_umma_desc(sA + part_floats + off);
-            const uint64_t bh = ssb_umma_desc(b_hi + off), bl = ssb_umma_desc(b_lo + off);
+            const uint64_t bh = ssb_umma_desc_lbo(b_hi + ob, (TR / 8) * 128), bl = ssb_umma_desc_lbo(b_lo + ob, (TR / 8) * 128);
             ssb_umma_tf32(dst, al, bh, idesc, j > 0);
             ssb_umma_tf32(dst, ah, bl, idesc, 1);
             ssb_umma_tf32(dst, ah, bh, idesc, 1);
@@ -1604,14 +1613,14 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
         ssb_tc_fence_after();
         if (threadIdx.x == 0 && i + 2 < my_tiles) {           // the MMAs of tile i have consumed stage s
             ssb_mbar_expect_tx(&full[s], tile_bytes);
-            ssb_bulk_g2s(sB + (size_t)s * 2 * part_floats, Stc + (size_t)(chunk + (i + 2) * n_chunks) * 2 * part_floats,
-                         tile_bytes, &full[s]);
+            ssb_bulk_g2s(sB + (size_t)s * 2 * b_part, Stc + (size_t)(chunk + (i + 2) * n_chunks) * 2 * b_part, tile_bytes,
+                         &full[s]);
         }
         __syncwarp();
-        const int row0 = (chunk + i * n_chunks) * SSB_TC_ROWS;
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * SSB_TC_ROWS;
+        const int row0 = (chunk + i * n_chunks) * TR;
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * TR;
 #pragma unroll 1
-        for (int b = half * (SSB_TC_ROWS / 64); b < (half + 1) * (SSB_TC_ROWS / 64); ++b) {
+        for (int b = half * (TR / 64); b < (half + 1) * (TR / 64); ++b) {
             float v[32];
             ssb_tmem_ld32(taddr + b * 32, v);
             const int gg0 = row0 + b * 32;
@@ -1640,7 +1649,7 @@ k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__
         }
     }
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * TR));
 }
 
 // CTA = one trial group x 8 warps: warps split the candidate list, merge through shared memory, then

@@ -174,6 +174,8 @@ class _Lowerer:
             self.is_small[ens] = small
         n_static = sum(1 for e in self.ensembles if not self.is_small[e]
                        for c in self.ens_dec_conns[e] if c not in pes_conns)
+        max_jpad = max([-(-self._out_size(c) // DEC_TILE) * DEC_TILE for e in self.ensembles if not self.is_small[e]
+                        for c in self.ens_dec_conns[e] if c not in pes_conns] + [0])
         for ens in self.ensembles:
             for c in self.ens_dec_conns[ens]:
                 if self.is_small[ens]:
@@ -186,9 +188,9 @@ class _Lowerer:
                 else:                  # static decoders
                     jpad = -(-self._out_size(c) // DEC_TILE) * DEC_TILE
                     quads = -(-self.n_groups // 4)
-                    if jpad <= DEC_TC_WIDTH and os.environ.get("SSB_DECODE") != "ffma":
-                        # k_decode_tc: CTA = (decoder, 128 trials, K chunk of 64-neuron stages), one CTA per SM
-                        n_stages = -(-ens.n_neurons // DEC_TC_STAGE)
+                    if max_jpad <= 2 * DEC_TC_WIDTH and os.environ.get("SSB_DECODE") != "ffma":
+                        # k_decode_tc: CTA = (decoder, 128 trials, K chunk of 64- (or 32-) neuron stages), one CTA per SM
+                        n_stages = -(-ens.n_neurons // (DEC_TC_STAGE if max_jpad <= DEC_TC_WIDTH else DEC_TC_STAGE // 2))
                         self.dec_chunks[c] = int(max(1, min(n_stages, N_SM // max(1, n_static * quads))))
                         continue
                     # k_decode (FFMA): CTA = (decoder, quad of trial groups, neuron chunk), all outputs at once
