@@ -57,6 +57,14 @@ int ssb_rebase_tables(ssb_sim* s, long long step0);
 
 /* Replaces: sim.run_steps(n) / sim.run(T) (run_slam.py:232-233).  Asynchronous. */
 int ssb_run_steps(ssb_sim* s, int n_steps);
+/* ssb_set_tables + ssb_run_steps + ssb_read_probes in one call, software-pipelined over 16-step sub-chunks: tables of
+ * the next sub-chunk are copied host->device and probe rows of the previous one device->host while the current one
+ * computes.  Both host buffers should be page-locked (ssb_host_alloc).  host_tables [n_steps][nt][n_trials_padded] for
+ * the steps following ssb_n_steps(); host_probes [n_steps][n_probe][n_trials_padded] (may be NULL).  Asynchronous:
+ * the host buffers belong to the library until ssb_io_wait() returns.
+ * Replaces: sim.run_steps(n) + sim.data[probe] with host-resident inputs (run_slam.py:232-233,250). */
+int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* host_probes);
+int ssb_io_wait(ssb_sim* s);
 /* Replaces: sim.data[probe] for node/ensemble probes: host [n_steps][n_probe][n_trials_padded]. */
 int ssb_read_probes(ssb_sim* s, float* host, long long step0, int n_steps);
 long long ssb_n_steps(ssb_sim* s);

@@ -124,6 +124,8 @@ struct ssb_sim {
     // capture these become parallel branches of the step graph)
     bool parallel = true;
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t io_h2d = nullptr, io_d2h = nullptr;   // copy streams of ssb_run_steps_io (one per DMA direction)
+    std::vector<cudaEvent_t> io_events;
     std::vector<cudaEvent_t> dep_pool;
     size_t dep_used = 0;
     int pes_level = -1;
@@ -222,15 +224,17 @@ int arena(ssb_sim* s, const char* name, ArenaRef* out) {
 
 // Host rows are [n_rows][B] (trial contiguous); device arenas are tiled [G][arena_rows][32].
 // One strided 2-D copy per trial group moves n_rows lines of 128 bytes.
-int copy_rows(ssb_sim* s, float* dev_base, long long arena_rows, size_t row0, size_t n_rows, float* host, bool to_device) {
+int copy_rows(ssb_sim* s, float* dev_base, long long arena_rows, size_t row0, size_t n_rows, float* host, bool to_device,
+              cudaStream_t st = nullptr) {
     const size_t B = s->B;
+    if (!st) st = s->stream;
     for (int g = 0; g < s->n_groups; ++g) {
         float* d = dev_base + ((size_t)g * arena_rows + row0) * 32;
         float* h = host + (size_t)g * 32;
         if (to_device)
-            SSB_CUDA(cudaMemcpy2DAsync(d, 128, h, B * sizeof(float), 128, n_rows, cudaMemcpyHostToDevice, s->stream));
+            SSB_CUDA(cudaMemcpy2DAsync(d, 128, h, B * sizeof(float), 128, n_rows, cudaMemcpyHostToDevice, st));
         else
-            SSB_CUDA(cudaMemcpy2DAsync(h, B * sizeof(float), d, 128, 128, n_rows, cudaMemcpyDeviceToHost, s->stream));
+            SSB_CUDA(cudaMemcpy2DAsync(h, B * sizeof(float), d, 128, 128, n_rows, cudaMemcpyDeviceToHost, st));
     }
     return 0;
 }
@@ -1203,6 +1207,86 @@ int ssb_run_steps(ssb_sim* s, int n_steps) {
     return 0;
 }
 
+// ssb_set_tables + ssb_run_steps + ssb_read_probes as one software pipeline over 16-step sub-chunks: the input tables of
+// sub-chunk j+1 are copied (H2D stream) while sub-chunk j computes, and the probe rows of sub-chunk j go back to the
+// host (D2H stream) while sub-chunk j+1 computes.  Asynchronous: ssb_io_wait() returns once steps and copies are done.
+int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* host_probes) {
+    if (!s || !s->finalized) return fail(-1, "ssb_run_steps_io: bad handle");
+    if (n_steps <= 0) return 0;
+    if (n_steps > s->chunk_cap) return fail(-1, "ssb_run_steps_io: n_steps exceeds chunk_cap");
+    if (s->nt > 0 && !host_tables) return fail(-1, "ssb_run_steps_io: null table buffer");
+    SSB_CUDA(cudaSetDevice(s->device));
+    if (!s->io_h2d) {
+        SSB_CUDA(cudaStreamCreateWithFlags(&s->io_h2d, cudaStreamNonBlocking));
+        SSB_CUDA(cudaStreamCreateWithFlags(&s->io_d2h, cudaStreamNonBlocking));
+    }
+    const int sub = 16;
+    const int n_sub = (n_steps + sub - 1) / sub;
+    while ((int)s->io_events.size() < 2 * n_sub + 1) {
+        cudaEvent_t e;
+        SSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->io_events.push_back(e);
+    }
+    const bool graphs = s->use_graph && !s->profiling;
+    if (graphs && n_steps >= sub && !s->step_graph) {
+        if (build_graph(s, sub)) return -2;
+    }
+    s->tab_step0 = s->steps_done;
+    s->tab_steps = n_steps;
+    s->probe_step0 = s->steps_done;
+    if (push_dyn(s)) return -2;
+    SSB_CUDA(cudaEventRecord(s->ev_run0, s->stream));
+    // the copy streams start after everything already queued on the compute stream (previous readers of the arenas)
+    SSB_CUDA(cudaEventRecord(s->io_events[2 * n_sub], s->stream));
+    SSB_CUDA(cudaStreamWaitEvent(s->io_h2d, s->io_events[2 * n_sub], 0));
+    for (int j = 0; j < n_sub; ++j) {
+        const int j0 = j * sub, jn = std::min(sub, n_steps - j0);
+        if (s->nt > 0) {
+            if (copy_rows(s, s->tab, (long long)s->chunk_cap * s->nt, (size_t)j0 * s->nt, (size_t)jn * s->nt,
+                          const_cast<float*>(host_tables) + (size_t)j0 * s->nt * s->B, true, s->io_h2d))
+                return -2;
+            SSB_CUDA(cudaEventRecord(s->io_events[2 * j], s->io_h2d));
+        }
+    }
+    for (int j = 0; j < n_sub; ++j) {
+        const int j0 = j * sub, jn = std::min(sub, n_steps - j0);
+        if (s->nt > 0) SSB_CUDA(cudaStreamWaitEvent(s->stream, s->io_events[2 * j], 0));
+        if (graphs && s->step_graph && jn == s->graph_steps) {
+            SSB_CUDA(cudaGraphLaunch(s->step_graph, s->stream));
+            for (int k = 0; k < K_NKINDS; ++k) {
+                s->kind_launches[k] += s->kind_per_graph[k];
+                s->total_launches += s->kind_per_graph[k];
+            }
+        } else {
+            s->dep_used = 0;
+            for (int r = 0; r < jn; ++r)
+                if (one_step(s, r)) return -2;
+            advance(s, jn);
+        }
+        if (host_probes && s->n_probe > 0) {
+            SSB_CUDA(cudaEventRecord(s->io_events[2 * j + 1], s->stream));
+            SSB_CUDA(cudaStreamWaitEvent(s->io_d2h, s->io_events[2 * j + 1], 0));
+            if (copy_rows(s, s->probe, (long long)s->chunk_cap * s->n_probe, (size_t)j0 * s->n_probe, (size_t)jn * s->n_probe,
+                          host_probes + (size_t)j0 * s->n_probe * s->B, false, s->io_d2h))
+                return -2;
+        }
+    }
+    SSB_CUDA(cudaEventRecord(s->ev_run1, s->stream));
+    s->run_timed = true;
+    s->steps_done += n_steps;
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ssb_io_wait(ssb_sim* s) {
+    if (!s || !s->finalized) return fail(-1, "ssb_io_wait: bad handle");
+    SSB_CUDA(cudaSetDevice(s->device));
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->io_d2h) SSB_CUDA(cudaStreamSynchronize(s->io_d2h));
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int ssb_read_probes(ssb_sim* s, float* host, long long step0, int n_steps) {
     if (!s || !s->finalized || !host) return fail(-1, "ssb_read_probes: bad arguments");
     if (step0 < s->probe_step0 || step0 + n_steps > s->steps_done || n_steps < 0)
@@ -1273,6 +1357,9 @@ void ssb_destroy(ssb_sim* s) {
     }
     if (s->step_graph) cudaGraphExecDestroy(s->step_graph);
     for (auto e : s->dep_pool) cudaEventDestroy(e);
+    for (auto e : s->io_events) cudaEventDestroy(e);
+    if (s->io_h2d) cudaStreamDestroy(s->io_h2d);
+    if (s->io_d2h) cudaStreamDestroy(s->io_d2h);
     for (auto a : s->aux)
         if (a) cudaStreamDestroy(a);
     for (auto e : s->ev_pool) cudaEventDestroy(e);

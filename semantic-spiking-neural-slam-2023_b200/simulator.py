@@ -81,7 +81,10 @@ class Simulator:
         self._nt = int(self.plan.scalars["nt"])
         self._np = int(self.plan.scalars["n_probe"])
         self._tab_buf = cabi.PinnedBuffer(max(1, self.chunk_steps * self._nt * self.B))
-        self._probe_buf = cabi.PinnedBuffer(max(1, self.chunk_steps * self._np * self.B))
+        # two page-locked probe buffers: the host-side copy-out of chunk k overlaps the device work of chunk k + 1
+        self._probe_bufs = [cabi.PinnedBuffer(max(1, self.chunk_steps * self._np * self.B)) for _ in range(2)]
+        self._probe_cur = 0
+        self._probe_pending = None   # (buffer index, n_steps) whose rows have not been copied out yet
         self._probe_infos = {info.probe: info for info in self.plan.probes}
         self._n_steps = 0
         self._init_state()
@@ -141,8 +144,10 @@ class Simulator:
                 self._lib.ssb_sync(self._h)
                 self._lib.ssb_destroy(self._h)
                 self._h = None
+            self._flush_probes()
             self._tab_buf.free()
-            self._probe_buf.free()
+            for b in self._probe_bufs:
+                b.free()
             if getattr(self, "_staged", None) is not None:
                 self._staged.free()
 
@@ -180,6 +185,7 @@ class Simulator:
     def reset(self, seed=None):
         self._check_open()
         cabi.check(self._lib.ssb_reset(self._h), "ssb_reset")
+        self._probe_pending = None
         self._n_steps = 0
         self._init_state()
 
@@ -257,19 +263,35 @@ class Simulator:
             if src is None:
                 self._fill_tables(self._n_steps, n)
                 src = self._tab_buf.ptr
-            cabi.check(lib.ssb_set_tables(self._h, src, self._n_steps, n), "ssb_set_tables")
-            cabi.check(lib.ssb_run_steps(self._h, n), "ssb_run_steps")
+            # one pipelined call: tables host -> device, steps, probe rows device -> host (16-step sub-chunks overlap)
+            pbuf = self._probe_bufs[self._probe_cur]
+            if self._probe_pending is not None and self._probe_pending[0] == self._probe_cur:
+                self._flush_probes()
+            rc = lib.ssb_run_steps_io(self._h, src, n, pbuf.ptr if self._np else None)
+            cabi.check(rc, "ssb_run_steps_io")
             if self._np:
-                cabi.check(lib.ssb_read_probes(self._h, self._probe_buf.ptr, self._n_steps, n), "ssb_read_probes")
-                chunk = self._probe_buf.array[:n * self._np * self.B].reshape(n, self._np, self.B)
-                self._probe_rows.append(chunk[:, :, :self.n_trials].copy())
-            else:
-                cabi.check(lib.ssb_sync(self._h), "ssb_sync")
+                self._flush_probes()                       # the previous chunk (other buffer), while the device works
+            cabi.check(lib.ssb_io_wait(self._h), "ssb_io_wait")
+            if self._np:
+                self._probe_pending = (self._probe_cur, n)
+                self._probe_cur ^= 1
             self._n_steps += n
             done += n
             for info in self.plan.probes:
                 if info.kind != "rows" and self._n_steps % info.period == 0:
                     self._snap[info.probe].append(self._snapshot(info))
+
+    def _flush_probes(self):
+        """Copy the rows of the last finished chunk out of its page-locked buffer."""
+        if self._probe_pending is None:
+            return
+        idx, n = self._probe_pending
+        self._probe_pending = None
+        buf = self._probe_bufs[idx]
+        if buf.array is None:
+            return
+        chunk = buf.array[:n * self._np * self.B].reshape(n, self._np, self.B)
+        self._probe_rows.append(chunk[:, :, :self.n_trials].copy())
 
     def _snapshot(self, info):
         if info.kind == "weights":
@@ -283,6 +305,7 @@ class Simulator:
     def _probe_array(self, probe):
         info = self._probe_infos[probe]
         if info.kind == "rows":
+            self._flush_probes()
             if self._probe_rows:
                 allrows = np.concatenate(self._probe_rows, axis=0) if len(self._probe_rows) > 1 else self._probe_rows[0]
                 self._probe_rows = [allrows]
