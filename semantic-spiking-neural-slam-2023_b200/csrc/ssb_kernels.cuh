@@ -1235,17 +1235,32 @@ __device__ __forceinline__ void ssb_pes_body(const float* __restrict__ ap, const
 #pragma unroll
     for (int j = 0; j < 8; ++j) rowp[j] = dp + (size_t)((FULL || j < jn) ? j : 0) * n * 32;
     constexpr int U = 4;
+    // activities / traces of the NEXT batch are requested before this batch's weights, so the two dependent
+    // memory rounds of a batch (a, f -> vote -> weights) overlap across iterations
+    float an[U], fn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int ii = i_lo + warp + 4 * u;
+        an[u] = 0.f;
+        fn[u] = 0.f;
+        if (ii < i_hi) {
+            an[u] = ap[(size_t)ii * 32];
+            fn[u] = fp[(size_t)ii * 32];
+        }
+    }
     for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
         float a[U], f[U], w[U][8];
         bool on[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int ii = i + 4 * u;
-            a[u] = 0.f;
-            f[u] = 0.f;
+            a[u] = an[u];
+            f[u] = fn[u];
+            const int ii = i + 4 * U + 4 * u;
+            an[u] = 0.f;
+            fn[u] = 0.f;
             if (ii < i_hi) {
-                a[u] = ap[(size_t)ii * 32];
-                f[u] = fp[(size_t)ii * 32];
+                an[u] = ap[(size_t)ii * 32];
+                fn[u] = fp[(size_t)ii * 32];
             }
         }
 #pragma unroll
