@@ -1848,7 +1848,7 @@ __global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ 
 //               20..27 coefficients | 28 src (kind 2) | 29..31 unused
 #define SSB_DENSE_RCH 8
 #define SSB_DENSE_SLAB 32
-#define SSB_REC_PER_WARP 2
+#define SSB_REC_PER_WARP 4
 
 // dense rows: kind dst a_bits b_bits
 __device__ __forceinline__ void ssb_lin_store(const SsbCtx& c, const SsbStep& s, float* vg, int g, int lane, int kind, int dst,
@@ -1894,6 +1894,11 @@ __global__ void __launch_bounds__(128, 8) k_lin(SsbCtx c, SsbLinArgs L, int i_re
         const int* __restrict__ dr = L.drows + (size_t)it.w * 4;
         const int* __restrict__ cols = L.dcols + it.y + ((s.odd ^ it2.y) ? kpad : 0);
         float* vg = ssb_grp(c.vec, c.nv, g, lane);
+        // this warp's output rows (r = warp, warp + 4): descriptors requested now, used after the reduction
+        int4 rd[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            rd[q] = (warp + 4 * q < nr) ? __ldg(reinterpret_cast<const int4*>(dr) + warp + 4 * q) : make_int4(3, 0, 0, 0);
         float acc[SSB_DENSE_RCH];
 #pragma unroll
         for (int r = 0; r < SSB_DENSE_RCH; ++r) acc[r] = 0.f;
@@ -1927,10 +1932,13 @@ __global__ void __launch_bounds__(128, 8) k_lin(SsbCtx c, SsbLinArgs L, int i_re
 #pragma unroll
         for (int r = 0; r < SSB_DENSE_RCH; ++r) s_red[warp][r][lane] = acc[r];
         __syncthreads();
-        for (int r = warp; r < nr; r += 4) {                            // fixed order: ((w0 + w1) + w2) + w3
-            const float u = ((s_red[0][r][lane] + s_red[1][r][lane]) + s_red[2][r][lane]) + s_red[3][r][lane];
-            ssb_lin_store(c, s, vg, g, lane, dr[r * 4], dr[r * 4 + 1], __int_as_float(dr[r * 4 + 2]),
-                          __int_as_float(dr[r * 4 + 3]), u);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {                                   // fixed order: ((w0 + w1) + w2) + w3
+            const int r = warp + 4 * q;
+            if (r < nr) {
+                const float u = ((s_red[0][r][lane] + s_red[1][r][lane]) + s_red[2][r][lane]) + s_red[3][r][lane];
+                ssb_lin_store(c, s, vg, g, lane, rd[q].x, rd[q].y, __int_as_float(rd[q].z), __int_as_float(rd[q].w), u);
+            }
         }
         return;
     }
