@@ -8,6 +8,7 @@ Public surface (mirrors what the reference drivers touch):
   device encode / grid-decode.
 * ``networks`` — from-scratch declarations of the reference topologies (used where the
   reference checkout is not present, e.g. on the GPU box).
+* ``results`` — the drivers' post-processing and ``.npz`` schema (``run_slam.py:236-293``, ``run_pathint.py:168-203``).
 * ``nengo_shim`` — nengo-compatible declaration layer (``install()`` registers it as
   ``nengo`` when the real package is missing).
 """
@@ -30,7 +31,8 @@ def __getattr__(name):
         import importlib
         mod, attr = _LAZY[name]
         return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
-    if name in ("networks", "sspspace", "builder", "lowering", "simulator", "inputs", "cabi", "refload"):
+    if name in ("networks", "sspspace", "builder", "lowering", "simulator", "inputs", "cabi", "refload", "results",
+                "scenarios", "sharding"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -299,3 +299,48 @@ def test_full_size_config4_slamview_d97_rate_mode_matches_oracle():
     got = sim.data[sc.probe]
     assert np.all(np.isfinite(got)) and np.all(np.isfinite(dec))
     assert _rel(got[1], _oracle(sc, sim, 1, n_steps).data[sc.probe]) < 1e-4
+
+
+def test_spiking_error_distribution_matches_oracle():
+    """Spiking runs are chaotic (fp32 vs fp64), so they are compared as a distribution over trials: the mean
+    similarity to the true SSP and the mean decoded position error over the last 200 steps must agree with the
+    oracle's within 0.02 / 0.03 (BASELINE north_star: 'reproduce the reference's RMSE distribution')."""
+    from sspslam_b200 import results
+    n_trials, n_steps = 8, 400
+    sc = scenarios.make_pathint(n_trials=n_trials, n_steps=n_steps, ssp_dim=55, pi_n_neurons=100, neuron_type="lif")
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=n_trials, trial_inputs=sc.trial_inputs) as sim:
+        sim.run_steps(n_steps)
+    sp = HexagonalSSPSpace(2, ssp_dim=55, domain_bounds=BOUNDS2, length_scale=0.2, rng=np.random.default_rng(0))
+
+    class _Ref:                                      # the oracle behind the same results.* interface
+        def __init__(self, ref):
+            self.data, self._n = ref.data, n_steps
+        def trange(self):
+            return sc.dt * np.arange(1, self._n + 1)
+
+    gpu_sims, gpu_err, ref_sims, ref_err = [], [], [], []
+    for trial in range(n_trials):
+        r = results.pathint_results(sim, sc.probe, sp, sc.paths[trial], sc.real_ssp[trial], trial=trial)
+        o = results.pathint_results(_Ref(_oracle(sc, sim, trial, n_steps)), sc.probe, sp, sc.paths[trial], sc.real_ssp[trial])
+        gpu_sims.append(np.mean(r["pi_sims"][-200:])); gpu_err.append(np.mean(r["pi_error"][-200:]))
+        ref_sims.append(np.mean(o["pi_sims"][-200:])); ref_err.append(np.mean(o["pi_error"][-200:]))
+    assert np.mean(ref_sims) > 0.5                                   # the network does integrate the path
+    assert abs(np.mean(gpu_sims) - np.mean(ref_sims)) < 0.02
+    assert abs(np.mean(gpu_err) - np.mean(ref_err)) < 0.03
+    assert np.max(np.abs(np.array(gpu_sims) - np.array(ref_sims))) < 0.06
+
+
+def test_slam_results_with_landmark_estimates():
+    """run_slam.py:236-293 on a finished batched run: decoded path, error, similarity, landmark recall."""
+    from sspslam_b200 import results
+    n_steps = 160
+    sc = scenarios.make_slam(n_trials=2, n_steps=n_steps, ssp_dim=55, pi_n_neurons=60, mem_n_neurons=128,
+                             circonv_n_neurons=20, n_landmarks=10, T=20.0, neuron_type="lif", weights_probe=True)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=2, trial_inputs=sc.trial_inputs) as sim:
+        sim.run_steps(n_steps)
+    sp = HexagonalSSPSpace(2, ssp_dim=55, domain_bounds=BOUNDS2, length_scale=0.2, rng=np.random.default_rng(0))
+    res = results.slam_results(sim, sc.probe, sp, sc.paths[1], sc.real_ssp[1], trial=1, slam=sc.extra["slam"],
+                               weights_probe=sc.extra["weights_probe"], lm_vectors=sc.extra["lm_space"].vectors)
+    assert res["slam_path"].shape == (n_steps, 2) and res["slam_error"].shape == (n_steps,)
+    assert res["landmark_ssps_est"].shape == (10, 55) and res["landmark_loc_est"].shape == (10, 2)
+    assert np.all(np.isfinite(res["slam_sims"])) and np.all(np.isfinite(res["landmark_ssps_est"]))
