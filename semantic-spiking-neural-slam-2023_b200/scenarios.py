@@ -69,12 +69,12 @@ def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0,
 def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neurons=970, circonv_n_neurons=100,
               n_landmarks=50, view_rad=0.2, T=200.0, limit=0.1, seed=0, dt=0.001, length_scale=0.2,
               shift_rate=0.2, update_thres=0.2, neuron_type="lif", weights_probe=False, view=False,
-              distinct_tables=None):
+              distinct_tables=None, domain_dim=2, grid_points_per_dim=100):
     """``run_slam.py`` (or ``run_slamview.py`` when ``view``) workload, batched over trials.
 
     ``distinct_tables``: synthesise only that many distinct trials' tables and tile them
     over the batch (bench warm-up economy); state/voltages still differ per trial."""
-    space = make_space(2, ssp_dim, length_scale)
+    space = make_space(domain_dim, ssp_dim, length_scale)
     d = space.ssp_dim
     lm_space = SPSpace(n_landmarks, d, seed=seed)
     n_distinct = n_trials if distinct_tables is None else min(n_trials, distinct_tables)
@@ -82,11 +82,12 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
     scale = None
     for i in range(n_distinct):
         s_i = seed + 1000 * i
-        path = inputs.random_path(T, dt, limit, s_i, 2)[:max(n_steps + 2, 4)]
+        path = inputs.random_path(T, dt, limit, s_i, domain_dim)[:max(n_steps + 2, 4)]
         vels = inputs.velocities(path, dt)
         if scale is None:
-            scale = inputs.velocity_scale(space.phase_matrix, inputs.velocities(inputs.random_path(T, dt, limit, seed, 2), dt))
-        obj_locs = 1.8 * (inputs.rd_sampling(n_landmarks, 2, seed=s_i) - 0.5)
+            scale = inputs.velocity_scale(space.phase_matrix,
+                                          inputs.velocities(inputs.random_path(T, dt, limit, seed, domain_dim), dt))
+        obj_locs = 1.8 * (inputs.rd_sampling(n_landmarks, domain_dim, seed=s_i) - 0.5)
         vec_to_lm = obj_locs[None, :, :] - path[:, None, :]
         real = space.encode_host(path)
         if view:
@@ -118,7 +119,7 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
             slam = networks.SLAMViewNetwork(space, lm_space, view_rad, n_landmarks, pi_n_neurons, mem_n_neurons,
                                             circonv_n_neurons, tau_pi=0.05, update_thres=update_thres,
                                             vel_scaling_factor=scale, shift_rate=0.02, voja_learning_rate=5e-4,
-                                            pes_learning_rate=1e-3)
+                                            pes_learning_rate=1e-3, grid_points_per_dim=grid_points_per_dim)
             nengo.Connection(lm_id, slam.view_input, synapse=None)
             table_nodes = {"vel": vel_in, "init": init, "lm_sp": lm_id, "nolm": is_lm}
         else:
@@ -126,7 +127,8 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
             slam = networks.SLAMNetwork(space, lm_space, view_rad, n_landmarks, pi_n_neurons, mem_n_neurons,
                                         circonv_n_neurons, tau_pi=0.05, update_thres=update_thres,
                                         vel_scaling_factor=scale, shift_rate=shift_rate, voja_learning_rate=1e-4,
-                                        pes_learning_rate=5e-3, intercept=0.1, seed=seed)
+                                        pes_learning_rate=5e-3, intercept=0.1, seed=seed,
+                                        grid_points_per_dim=grid_points_per_dim)
             nengo.Connection(lm_vec, slam.landmark_vec_ssp, synapse=None)
             nengo.Connection(lm_id, slam.landmark_id_input, synapse=None)
             table_nodes = {"vel": vel_in, "init": init, "lm_sp": lm_id, "nolm": is_lm, "lmvec_ssp": lm_vec}

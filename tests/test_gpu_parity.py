@@ -344,3 +344,20 @@ def test_slam_results_with_landmark_estimates():
     assert res["slam_path"].shape == (n_steps, 2) and res["slam_error"].shape == (n_steps,)
     assert res["landmark_ssps_est"].shape == (10, 55) and res["landmark_loc_est"].shape == (10, 2)
     assert np.all(np.isfinite(res["slam_sims"])) and np.all(np.isfinite(res["landmark_ssps_est"]))
+
+
+def test_slam_3d_domain_matches_oracle():
+    """BASELINE configs[4] topology (3-D domain, HexagonalSSPSpace with random rotations) at reduced size."""
+    n_steps = 120
+    sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=60, mem_n_neurons=128,
+                             circonv_n_neurons=20, n_landmarks=8, T=20.0, neuron_type="lifrate", view_rad=0.6,
+                             domain_dim=3, grid_points_per_dim=14)
+    slam = sc.extra["slam"]
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        sim.run_steps(n_steps)
+        idx = sim.cleanup_indices()[0].copy()
+    got = sim.data[sc.probe]
+    for trial in (0, 2):
+        ref = _oracle(sc, sim, trial, n_steps)
+        assert _rel(got[trial], ref.data[sc.probe]) < 1e-4
+        assert idx[trial] == ssp_ref.cleanup_index(slam.sample_ssps, ref.signals[slam.gridcells, "in"].a)

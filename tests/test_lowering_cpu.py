@@ -94,3 +94,15 @@ def test_traffic_model_config2_sizes():
                  n_table_words=168, n_probe_words=55)
     b = lowering.algorithmic_bytes_per_trial_step(stats)
     assert 1.50e6 < b < 1.53e6
+
+
+def test_slam_3d_plan_matches_oracle():
+    """BASELINE configs[4] topology at toy size: 3-D domain (3-D velocity into the 3-D VCOs, 12^3 grid)."""
+    sc = scenarios.make_slam(n_trials=1, n_steps=50, ssp_dim=55, pi_n_neurons=30, mem_n_neurons=64, circonv_n_neurons=16,
+                             n_landmarks=6, T=20.0, neuron_type="lifrate", view_rad=0.6, domain_dim=3,
+                             grid_points_per_dim=12)
+    assert sc.ssp_space.domain_dim == 3
+    plan, *_ = _compare(sc, 50)
+    assert int(plan.arrays["cleanup"][0][0]) == 12 ** 3
+    assert {int(r[1]) for r in plan.arrays["ens_small"]} == {1, 3}    # VCOs stay (Re, Im, frequency) in any domain
+    assert sc.trial_inputs[[n for n in sc.trial_inputs if n.label == "vel_input"][0]].shape[2] == 3
