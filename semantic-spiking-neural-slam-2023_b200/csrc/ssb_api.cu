@@ -138,6 +138,8 @@ struct ssb_sim {
     int* d_dec_wt_off = nullptr;
     int dec_tc_n = 64;                      // operand tile width of k_decode_tc (64 or 128 output columns)
     std::vector<char> dec_tc_level;         // per level: every decoder of the level can use the tensor-core kernel
+    SsbPesDefer pes_h = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};   // deferred PES history (K = 0: off)
+    int* d_pes_hdesc = nullptr;
     size_t pes_pad_smem = 0, voja_pad_smem = 0;   // experiment knobs: extra dynamic smem lowers residency
     std::map<int, int> wide_chunk_cache;   // launch geometry of the wide-ensemble kernels, decided once
     long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
@@ -473,8 +475,75 @@ void stream_dep(ssb_sim* s, cudaStream_t from, cudaStream_t to) {
     cudaStreamWaitEvent(to, e, 0);
 }
 
+// Deferred PES: history arenas + per-decoder rows.  SSB_PES_DEFER=0 keeps the every-step read-modify-write kernel;
+// SSB_PES_DEFER=4|8 sets the window (default 8).
+int setup_pes_defer(ssb_sim* s) {
+    int K = 8;
+    if (const char* e = getenv("SSB_PES_DEFER")) K = atoi(e);
+    if (s->n_pes == 0 || (K != 4 && K != 8)) return 0;
+    std::vector<int> hd;
+    int rows_e = 0, rows_f = 0, rows_p = 0;
+    for (int i = 0; i < s->n_pes; ++i) {
+        const int* d = &s->h_pes[i * 13];
+        hd.insert(hd.end(), {rows_e, rows_f, rows_p, i});
+        rows_e += K * d[1];
+        rows_f += K * d[0];
+        rows_p += d[10] * (d[1] + K);
+    }
+    SsbPesDefer& h = s->pes_h;
+    h.rows_e = rows_e;
+    h.rows_f = rows_f;
+    h.rows_p = rows_p;
+    if (alloc_rows(&h.hist_e, rows_e, s->B) || alloc_rows(&h.hist_f, rows_f, s->B) || alloc_rows(&h.part, rows_p, s->B)) return -2;
+    SSB_CUDA(cudaMalloc((void**)&h.counters, (size_t)s->n_pes * s->n_groups * sizeof(int)));
+    SSB_CUDA(cudaMemset(h.counters, 0, (size_t)s->n_pes * s->n_groups * sizeof(int)));
+    hd.resize(hd.size() + 8, 0);
+    SSB_CUDA(cudaMalloc((void**)&s->d_pes_hdesc, hd.size() * sizeof(int)));
+    SSB_CUDA(cudaMemcpy(s->d_pes_hdesc, hd.data(), hd.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h.K = K;
+    return 0;
+}
+
+void pes_grid(ssb_sim* s, dim3* grid, int* max_chunks) {
+    int max_out = 0;
+    *max_chunks = 1;
+    for (int i = 0; i < s->n_pes; ++i) {
+        max_out = std::max(max_out, s->h_pes[i * 13 + 1]);
+        *max_chunks = std::max(*max_chunks, s->h_pes[i * 13 + 10]);
+    }
+    *grid = dim3((max_out + 7) / 8, s->n_groups, s->n_pes * *max_chunks);
+}
+
+void launch_pes_fold(ssb_sim* s, cudaStream_t st, int i_rel, int force) {
+    dim3 grid;
+    int max_chunks;
+    pes_grid(s, &grid, &max_chunks);
+    if (s->pes_h.K == 4) k_pes_fold<4><<<grid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel, force);
+    else k_pes_fold<8><<<grid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel, force);
+    k_pes_clear<<<dim3((s->pes_h.rows_e + 3) / 4, s->n_groups), 128, 0, st>>>(s->ctx, s->pes_h, i_rel, force);
+}
+
+// Fold the pending history into the decoders (before any host read / write of the ldec arena).
+int pes_flush(ssb_sim* s) {
+    if (s->pes_h.K == 0 || !s->finalized) return 0;
+    launch_pes_fold(s, s->stream, 0, 1);
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
 void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
     LaunchTimer t(s, K_PES);
+    if (s->pes_h.K > 0) {
+        dim3 grid;
+        int max_chunks, max_rows = 0;
+        pes_grid(s, &grid, &max_chunks);
+        for (int i = 0; i < s->n_pes; ++i) max_rows = std::max(max_rows, s->h_pes[i * 13] + s->h_pes[i * 13 + 1]);
+        k_pes_hist<<<dim3((max_rows + 3) / 4, s->n_groups, s->n_pes), 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, i_rel);
+        if (s->pes_h.K == 4) k_pes_defer<4><<<grid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks);
+        else k_pes_defer<8><<<grid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks);
+        launch_pes_fold(s, st, i_rel, 0);
+        return;
+    }
     int max_out = 0, max_chunks = 1;
     for (int i = 0; i < s->n_pes; ++i) {
         max_out = std::max(max_out, s->h_pes[i * 13 + 1]);
@@ -997,6 +1066,7 @@ int ssb_finalize(ssb_sim* s) {
     s->h_pes = host_ints(s, "pes");
     if ((int)s->h_stages.size() != s->n_levels * 12) return fail(-1, "ssb_finalize: stages array has wrong size");
     if (int rc = build_lin_program(s)) return rc;
+    if (int rc = setup_pes_defer(s)) return rc;
     if (int rc = build_decode_tiles(s)) return rc;
     if (int rc = build_encode_tiles(s)) return rc;
     s->levels.assign(s->n_levels, LevelInfo());
@@ -1121,6 +1191,7 @@ int ssb_upload(ssb_sim* s, const char* name, size_t row0, size_t n_rows, const f
     if (arena(s, name, &a)) return -3;
     if ((long long)(row0 + n_rows) > a.rows) return fail(-1, "ssb_upload: rows out of range");
     SSB_CUDA(cudaSetDevice(s->device));
+    if (a.ptr == s->ldec && pes_flush(s)) return -2;
     if (a.tiled) {
         if (copy_rows(s, a.ptr, std::max(1LL, a.rows), row0, n_rows, const_cast<float*>(host), true)) return -2;
     } else {
@@ -1136,6 +1207,7 @@ int ssb_download(ssb_sim* s, const char* name, size_t row0, size_t n_rows, float
     if (arena(s, name, &a)) return -3;
     if ((long long)(row0 + n_rows) > a.rows) return fail(-1, "ssb_download: rows out of range");
     SSB_CUDA(cudaSetDevice(s->device));
+    if (a.ptr == s->ldec && pes_flush(s)) return -2;
     if (a.tiled) {
         if (copy_rows(s, a.ptr, std::max(1LL, a.rows), row0, n_rows, host, false)) return -2;
     } else {
@@ -1325,6 +1397,11 @@ int ssb_reset(ssb_sim* s) {
     SSB_CUDA(zero(s->lenc, s->n_lenc));
     SSB_CUDA(zero(s->ldec, s->n_ldec));
     SSB_CUDA(zero(s->afilt, 2 * s->n_afilt));
+    if (s->pes_h.K > 0) {
+        SSB_CUDA(zero(s->pes_h.hist_e, s->pes_h.rows_e));
+        SSB_CUDA(zero(s->pes_h.hist_f, s->pes_h.rows_f));
+        SSB_CUDA(cudaMemsetAsync(s->pes_h.counters, 0, (size_t)s->n_pes * s->n_groups * sizeof(int), s->stream));
+    }
     SSB_CUDA(cudaMemsetAsync(s->counters, 0, (size_t)std::max(1LL, s->n_counters) * sizeof(int), s->stream));
     {
         std::vector<float> ones(32, 1.0f);
@@ -1345,7 +1422,8 @@ void ssb_destroy(ssb_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
-                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_enc_t, s->d_enc_t_off, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_enc_t, s->d_enc_t_off, s->pes_h.hist_e, s->pes_h.hist_f, s->pes_h.part,
+                    s->pes_h.counters, s->d_pes_hdesc, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
                     s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -1326,6 +1326,240 @@ __global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ d
 }
 
 // --------------------------------------------------------------------------------------
+// Deferred PES (default).  SimPES changes the decoders by one rank-1 term per step, D(t) = D(t-1) + ae(t) (x) f(t),
+// and the only per-step consumer is out(t) = D(t) . a(t) with a sparse spike vector a.  Instead of rewriting D every
+// step, the last K terms are kept as a history (ae_s: size_out rows, f_s: n rows per slot, slot = step mod K) and
+//     out(t) = D_base . a(t) + sum_s ae_s * (f_s . a(t)),
+// which reads D_base only where some trial of the group spiked and writes nothing; every K-th step (and before any
+// read-back of the decoders) the K terms are folded into D_base in one streaming pass.  Same arithmetic up to fp32
+// summation order; HBM traffic drops from 8 B to ~(active fraction * 4 + 8 / K) B per learned weight and step.
+//   k_pes_hist   appends this step's term (ae from the materialised error rows, f = the trace the previous step read)
+//   k_pes_defer  the sparse decode; CTA = (8-row tile, trial group, neuron chunk); tile-0 CTAs also accumulate the K
+//                history dot products; the last CTA of a (decoder, group) adds partials in a fixed order and applies
+//                the history correction
+//   k_pes_fold   D_base += sum_s ae_s (x) f_s (runs when slot == K - 1, or when the host asks), then k_pes_clear zeroes
+//                the ae rows, so an empty history always contributes exactly 0
+// desc as k_pes; hdesc per decoder: e_row0 f_row0 part_row0 counter0 (rows of the hist_e / hist_f / pes_part arenas)
+#define SSB_PES_KMAX 16
+struct SsbPesDefer {
+    float* hist_e;            // [G][rows_e][32]
+    float* hist_f;            // [G][rows_f][32]
+    float* part;              // [G][rows_p][32]
+    int* counters;
+    int rows_e, rows_f, rows_p, K;
+};
+
+__global__ void __launch_bounds__(128) k_pes_hist(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
+                                                    const int* __restrict__ hdesc, int i_rel) {
+    const int item = blockIdx.z;
+    const int* d = desc + item * 13;
+    const int* hd = hdesc + item * 4;
+    const int n = d[0], size_out = d[1], a_off = d[3], err_vec = d[5];
+    const float alpha = __int_as_float(d[7]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.y;
+    const SsbStep s = ssb_step(c, i_rel);
+    const int slot = (int)(s.step % h.K);
+    const int r = blockIdx.x * 4 + warp;
+    float* he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
+    if (r < size_out) {
+        const float e = ssb_grp(c.vec, c.nv, g, lane)[(size_t)(err_vec + r) * 32];
+        he[(size_t)(slot * size_out + r) * 32] = s.step > 0 ? alpha * e : 0.f;
+    } else if (r < size_out + n) {
+        const int i = r - size_out;
+        const int prev_buf = 1 - s.odd;      // afilt half that still holds what the previous step read
+        const float f = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane)[((size_t)prev_buf * c.n_afilt + a_off + i) * 32];
+        ssb_grp(h.hist_f, h.rows_f, g, lane)[(size_t)(hd[1] + slot * n + i) * 32] = f;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
+                                                     const int* __restrict__ hdesc, int max_chunks) {
+    __shared__ float red[4][8 + SSB_PES_KMAX][32];
+    __shared__ int flag;
+    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
+    const int* d = desc + item * 13;
+    const int* hd = hdesc + item * 4;
+    const int n = d[0], size_out = d[1], d_off = d[2], act0 = d[4], out_vec = d[6], n_chunks = d[10];
+    const int j0 = blockIdx.x * 8;
+    if (j0 >= size_out || chunk >= n_chunks) return;
+    const int n_jt = (size_out + 7) >> 3;
+    const int per = (n + n_chunks - 1) / n_chunks;
+    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.y;
+    const int jn = min(8, size_out - j0);
+    const bool dots = blockIdx.x == 0;        // tile-0 CTAs also carry the history dot products of their chunk
+    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
+    const float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
+    const float* __restrict__ hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
+    float acc[8], dacc[K];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int q = 0; q < K; ++q) dacc[q] = 0.f;
+    constexpr int U = 4;
+    float an[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int ii = i_lo + warp + 4 * u;
+        an[u] = ii < i_hi ? ap[(size_t)ii * 32] : 0.f;
+    }
+    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
+        float a[U], w[U][8];
+        bool on[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a[u] = an[u];
+            const int ii = i + 4 * U + 4 * u;
+            an[u] = ii < i_hi ? ap[(size_t)ii * 32] : 0.f;
+            on[u] = __any_sync(0xffffffffu, a[u] != 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (on[u]) {
+                const size_t off = (size_t)(i + 4 * u) * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[u][j] = (j < jn) ? __ldcs(dp + (size_t)j * n * 32 + off) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (on[u]) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[u][j], a[u], acc[j]);
+                if (dots) {
+                    const size_t off = (size_t)(i + 4 * u) * 32;
+                    float fv[K];
+#pragma unroll
+                    for (int q = 0; q < K; ++q) fv[q] = hf[(size_t)q * n * 32 + off];
+#pragma unroll
+                    for (int q = 0; q < K; ++q) dacc[q] = fmaf(fv[q], a[u], dacc[q]);
+                }
+            }
+        }
+    }
+    // CTA partial: ((w0 + w1) + (w2 + w3)) per row, parked in the partial arena [chunk][size_out + K]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
+    if (dots) {
+#pragma unroll
+        for (int q = 0; q < K; ++q) red[warp][8 + q][lane] = dacc[q];
+    }
+    __syncthreads();
+    const int prow = size_out + K;
+    float* pg = ssb_grp(h.part, h.rows_p, g, lane) + (size_t)hd[2] * 32;
+    for (int j = warp; j < 8 + (dots ? K : 0); j += 4) {
+        const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
+        if (j < 8) {
+            if (j < jn) pg[(size_t)(chunk * prow + j0 + j) * 32] = t;
+        } else {
+            pg[(size_t)(chunk * prow + size_out + (j - 8)) * 32] = t;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* cnt_p = h.counters + hd[3] * c.G + g;
+        const int old = atomicAdd(cnt_p, 1);
+        const int last = old == n_jt * n_chunks - 1;
+        if (last) *cnt_p = 0;
+        flag = last;
+    }
+    __syncthreads();
+    if (!flag) return;
+    __threadfence();
+    // the last CTA of this (decoder, group): history dot products, then every output row
+    float dsum[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) dsum[q] = 0.f;
+    for (int ck = 0; ck < n_chunks; ++ck) {              // K independent loads per chunk, added in chunk order
+        float v[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) v[q] = __ldcg(pg + (size_t)(ck * prow + size_out + q) * 32);
+#pragma unroll
+        for (int q = 0; q < K; ++q) dsum[q] += v[q];
+    }
+    const float* __restrict__ he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
+    float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    for (int jb = warp * 8; jb < size_out; jb += 32) {   // each warp takes 8 consecutive output rows at a time
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = 0.f;
+        for (int ck = 0; ck < n_chunks; ++ck) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (jb + u < size_out) ? __ldcg(pg + (size_t)(ck * prow + jb + u) * 32) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] += v[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (jb + u < size_out) {
+                float e[K];
+#pragma unroll
+                for (int q = 0; q < K; ++q) e[q] = he[(size_t)(q * size_out + jb + u) * 32];
+                float r = t[u];
+#pragma unroll
+                for (int q = 0; q < K; ++q) r = fmaf(e[q], dsum[q], r);
+                vg[(size_t)(out_vec + jb + u) * 32] = r;
+            }
+        }
+    }
+}
+
+// force != 0: fold whatever is pending (host read-back); otherwise only on the last slot of a window
+template <int K>
+__global__ void __launch_bounds__(128) k_pes_fold(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
+                                                    const int* __restrict__ hdesc, int max_chunks, int i_rel, int force) {
+    const SsbStep s = ssb_step(c, i_rel);
+    if (!force && (int)(s.step % K) != K - 1) return;
+    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
+    const int* d = desc + item * 13;
+    const int* hd = hdesc + item * 4;
+    const int n = d[0], size_out = d[1], d_off = d[2], n_chunks = d[10];
+    const int j0 = blockIdx.x * 8;
+    if (j0 >= size_out || chunk >= n_chunks) return;
+    const int per = (n + n_chunks - 1) / n_chunks;
+    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.y;
+    const int jn = min(8, size_out - j0);
+    float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
+    const float* __restrict__ hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
+    const float* __restrict__ he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
+    float ae[K][8];
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ae[q][j] = (j < jn) ? he[(size_t)(q * size_out + j0 + j) * 32] : 0.f;
+    for (int i = i_lo + warp; i < i_hi; i += 4) {
+        const size_t off = (size_t)i * 32;
+        float fv[K], w[8];
+#pragma unroll
+        for (int q = 0; q < K; ++q) fv[q] = hf[(size_t)q * n * 32 + off];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = (j < jn) ? __ldcs(dp + (size_t)j * n * 32 + off) : 0.f;
+#pragma unroll
+        for (int q = 0; q < K; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = fmaf(ae[q][j], fv[q], w[j]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < jn) __stcs(dp + (size_t)j * n * 32 + off, w[j]);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pes_clear(SsbCtx c, SsbPesDefer h, int i_rel, int force) {
+    const SsbStep s = ssb_step(c, i_rel);
+    if (!force && (int)(s.step % h.K) != h.K - 1) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * 4 + warp;
+    if (r < h.rows_e) ssb_grp(h.hist_e, h.rows_e, blockIdx.y, lane)[(size_t)r * 32] = 0.f;
+}
+
+// --------------------------------------------------------------------------------------
 // Grid clean-up / decode: argmax_g S[g].x with first-maximum-wins.  Scan in fp32 keeping the
 // top-4 candidates per (grid chunk, trial); the pick kernel re-scores near-ties in fp64 so
 // that the chosen index equals the float64 NumPy argmax on the same input.
