@@ -118,6 +118,7 @@ struct ssb_sim {
     std::vector<int> h_stages, h_small, h_big, h_dec, h_cleanup, h_pes;
     cudaGraphExec_t step_graph = nullptr;   // graph_steps consecutive steps (the step counter lives on the device)
     int graph_steps = 0;
+    int graph_phase = 0;                    // steps_done mod (PES window) the graph was captured at
     bool use_graph = true;
     bool debug_sync = false, debug_failed = false;
     // independent kernels of one dependency level run on side streams (fork/join with events; under
@@ -153,6 +154,7 @@ struct ssb_sim {
     float *vec = nullptr, *tab = nullptr, *st = nullptr, *act = nullptr, *lenc = nullptr, *ldec = nullptr;
     float *afilt = nullptr, *probe = nullptr, *part = nullptr;
     int* counters = nullptr;
+    int* aflag = nullptr;
     long long* dyn = nullptr;
     std::vector<CleanupDev> cleanups;
     int* cidx = nullptr;  // [n_cleanup][B] (trial-major, not tiled)
@@ -538,10 +540,13 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
         int max_chunks, max_rows = 0;
         pes_grid(s, &grid, &max_chunks);
         for (int i = 0; i < s->n_pes; ++i) max_rows = std::max(max_rows, s->h_pes[i * 13] + s->h_pes[i * 13 + 1]);
+        dim3 dgrid(grid.x + 1, grid.y, grid.z);          // + one tile of history rows per (group, chunk)
+        if (s->pes_h.K == 4) k_pes_defer<4><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel);
+        else k_pes_defer<8><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel);
         k_pes_hist<<<dim3((max_rows + 3) / 4, s->n_groups, s->n_pes), 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, i_rel);
-        if (s->pes_h.K == 4) k_pes_defer<4><<<grid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks);
-        else k_pes_defer<8><<<grid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks);
-        launch_pes_fold(s, st, i_rel, 0);
+        // the host mirrors the step counter, so the fold is launched only after the last slot of a window
+        // (a captured graph bakes this in; it is replayed only from steps with the same phase, see ssb_run_steps)
+        if ((int)((s->steps_done + i_rel) % s->pes_h.K) == s->pes_h.K - 1) launch_pes_fold(s, st, i_rel, 1);
         return;
     }
     int max_out = 0, max_chunks = 1;
@@ -946,6 +951,7 @@ int build_graph(ssb_sim* s, int n) {
     memcpy(saved, s->kind_launches, sizeof(saved));
     const long long saved_total = s->total_launches;
     s->dep_used = 0;
+    s->graph_phase = s->pes_h.K > 0 ? (int)(s->steps_done % s->pes_h.K) : 0;
     SSB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < n; ++i) one_step(s, i);
     advance(s, n);
@@ -1168,6 +1174,9 @@ int ssb_finalize(ssb_sim* s) {
     c.tab = s->tab;
     c.st = s->st;
     c.act = s->act;
+    SSB_CUDA(cudaMalloc((void**)&s->aflag, (size_t)std::max(1LL, s->n_act) * s->n_groups * sizeof(int)));
+    SSB_CUDA(cudaMemset(s->aflag, 0, (size_t)std::max(1LL, s->n_act) * s->n_groups * sizeof(int)));
+    c.aflag = s->aflag;
     c.lenc = s->lenc;
     c.ldec = s->ldec;
     c.afilt = s->afilt;
@@ -1254,7 +1263,8 @@ int ssb_run_steps(ssb_sim* s, int n_steps) {
         if (n_steps >= gs && !s->step_graph) {
             if (build_graph(s, gs)) return -2;
         }
-        if (s->step_graph) {
+        const bool phase_ok = s->pes_h.K == 0 || (int)(s->steps_done % s->pes_h.K) == s->graph_phase;
+        if (s->step_graph && phase_ok) {
             int replays = 0;
             for (; i + s->graph_steps <= n_steps; i += s->graph_steps, ++replays)
                 SSB_CUDA(cudaGraphLaunch(s->step_graph, s->stream));
@@ -1323,7 +1333,8 @@ int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* h
     for (int j = 0; j < n_sub; ++j) {
         const int j0 = j * sub, jn = std::min(sub, n_steps - j0);
         if (s->nt > 0) SSB_CUDA(cudaStreamWaitEvent(s->stream, s->io_events[2 * j], 0));
-        if (graphs && s->step_graph && jn == s->graph_steps) {
+        const bool phase_ok = s->pes_h.K == 0 || (int)(s->steps_done % s->pes_h.K) == s->graph_phase;
+        if (graphs && s->step_graph && jn == s->graph_steps && phase_ok) {
             SSB_CUDA(cudaGraphLaunch(s->step_graph, s->stream));
             for (int k = 0; k < K_NKINDS; ++k) {
                 s->kind_launches[k] += s->kind_per_graph[k];
@@ -1423,7 +1434,7 @@ void ssb_destroy(ssb_sim* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
                     s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_enc_t, s->d_enc_t_off, s->pes_h.hist_e, s->pes_h.hist_f, s->pes_h.part,
-                    s->pes_h.counters, s->d_pes_hdesc, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->pes_h.counters, s->d_pes_hdesc, s->aflag, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
                     s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);

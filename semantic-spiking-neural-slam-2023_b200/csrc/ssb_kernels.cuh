@@ -34,6 +34,7 @@ struct SsbCtx {
     const float* tab;         // [G][tab_cap][nt][32]
     float* st;                // [G][nn][32]   packed LIF state
     float* act;               // [G][n_act][32]
+    int* aflag;               // [G][n_act]: some trial of the group has a non-zero activity (sparse consumers skip on it)
     float* lenc;              // [G][n_lenc][32]
     float* ldec;              // [G][n_ldec][32]
     float* afilt;             // [G][2*n_afilt][32]
@@ -573,6 +574,8 @@ __global__ void __launch_bounds__(128) k_wide_static(SsbCtx c, const int* __rest
             out = ssb_rate(nt, J);
         }
         ag[(size_t)i * 32] = out;
+        const bool any_on = __any_sync(0xffffffffu, out != 0.f);
+        if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + n0 + i] = any_on;
     }
     if (stateful && i_hi > i_lo) {
         ssb_fence_async();
@@ -730,6 +733,8 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
                         out = ssb_rate(nt, J);
                     }
                     ag[(size_t)nn * 32] = out;
+                    const bool any_on = __any_sync(0xffffffffu, out != 0.f);     // nn < n is warp-uniform
+                    if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + nn] = any_on;
                 }
             }
         }
@@ -828,6 +833,10 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
         }
         ag[(size_t)i * 32] = out;
         const bool fired = out != 0.f;
+        {
+            const bool any_on = __any_sync(0xffffffffu, fired);
+            if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + n0 + i] = any_on;
+        }
         if (fired) {
             const float sc = __ldg(c.W + scale_off + n0 + i);
             if (DP > 0) {
@@ -1333,7 +1342,8 @@ __global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ d
 // which reads D_base only where some trial of the group spiked and writes nothing; every K-th step (and before any
 // read-back of the decoders) the K terms are folded into D_base in one streaming pass.  Same arithmetic up to fp32
 // summation order; HBM traffic drops from 8 B to ~(active fraction * 4 + 8 / K) B per learned weight and step.
-//   k_pes_hist   appends this step's term (ae from the materialised error rows, f = the trace the previous step read)
+//   k_pes_hist   appends this step's term (ae from the materialised error rows, f = the trace the previous step read);
+//                it runs AFTER the decode of its own step, which reads that term at its source
 //   k_pes_defer  the sparse decode; CTA = (8-row tile, trial group, neuron chunk); tile-0 CTAs also accumulate the K
 //                history dot products; the last CTA of a (decoder, group) adds partials in a fixed order and applies
 //                the history correction
@@ -1375,67 +1385,75 @@ __global__ void __launch_bounds__(128) k_pes_hist(SsbCtx c, SsbPesDefer h, const
 
 template <int K>
 __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
-                                                     const int* __restrict__ hdesc, int max_chunks) {
-    __shared__ float red[4][8 + SSB_PES_KMAX][32];
+                                                     const int* __restrict__ hdesc, int max_chunks, int i_rel) {
+    __shared__ float red[4][8][32];
     __shared__ int flag;
     const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
     const int* d = desc + item * 13;
     const int* hd = hdesc + item * 4;
-    const int n = d[0], size_out = d[1], d_off = d[2], act0 = d[4], out_vec = d[6], n_chunks = d[10];
-    const int j0 = blockIdx.x * 8;
-    if (j0 >= size_out || chunk >= n_chunks) return;
+    const int n = d[0], size_out = d[1], d_off = d[2], a_off = d[3], act0 = d[4], err_vec = d[5], out_vec = d[6];
+    const int n_chunks = d[10];
     const int n_jt = (size_out + 7) >> 3;
+    // blockIdx.x < n_jt: an 8-row tile of D_base; blockIdx.x == n_jt: the K history rows (f_s . a), same loop
+    const bool dots = (int)blockIdx.x == n_jt;
+    const int j0 = blockIdx.x * 8;
+    if ((int)blockIdx.x > n_jt || chunk >= n_chunks) return;
     const int per = (n + n_chunks - 1) / n_chunks;
     const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.y;
-    const int jn = min(8, size_out - j0);
-    const bool dots = blockIdx.x == 0;        // tile-0 CTAs also carry the history dot products of their chunk
+    const int jn = dots ? K : min(8, size_out - j0);
+    const SsbStep s = ssb_step(c, i_rel);
+    const int slot = (int)(s.step % K);       // this step's term is not in the history yet: it is read at its source
     const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
-    const float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
-    const float* __restrict__ hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
-    float acc[8], dacc[K];
+    const int* __restrict__ fl = c.aflag + (size_t)g * c.n_act + act0;
+    const float* rowp[8];
+    {
+        const float* dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
+        const float* hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
+        const float* fcur = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)(1 - s.odd) * c.n_afilt + a_off) * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (dots) rowp[j] = (j == slot) ? fcur : hf + (size_t)(j < K ? j : 0) * n * 32;
+            else rowp[j] = dp + (size_t)(j < jn ? j : 0) * n * 32;
+        }
+    }
+    float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int q = 0; q < K; ++q) dacc[q] = 0.f;
+    // each warp owns a contiguous quarter of the chunk and walks only the neurons flagged active by their producer:
+    // 32 flags per coalesced load -> ballot -> up to U active neurons per batch with all their loads in flight
+    const int qn = (i_hi - i_lo + 3) >> 2;
+    const int w_lo = i_lo + warp * qn, w_hi = min(i_hi, w_lo + qn);
     constexpr int U = 4;
-    float an[U];
+    for (int base = w_lo; base < w_hi; base += 32) {
+        unsigned m = __ballot_sync(0xffffffffu, base + lane < w_hi && __ldg(fl + base + lane) != 0);
+        while (m) {
+            int idx[U];
+            float a[U], w[U][8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int ii = i_lo + warp + 4 * u;
-        an[u] = ii < i_hi ? ap[(size_t)ii * 32] : 0.f;
-    }
-    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
-        float a[U], w[U][8];
-        bool on[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            a[u] = an[u];
-            const int ii = i + 4 * U + 4 * u;
-            an[u] = ii < i_hi ? ap[(size_t)ii * 32] : 0.f;
-            on[u] = __any_sync(0xffffffffu, a[u] != 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (on[u]) {
-                const size_t off = (size_t)(i + 4 * u) * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) w[u][j] = (j < jn) ? __ldcs(dp + (size_t)j * n * 32 + off) : 0.f;
+            for (int u = 0; u < U; ++u) {
+                idx[u] = -1;
+                if (m) {
+                    idx[u] = base + __ffs(m) - 1;
+                    m &= m - 1;
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (on[u]) {
+            for (int u = 0; u < U; ++u) {
+                a[u] = 0.f;
+                if (idx[u] >= 0) {
+                    const size_t off = (size_t)idx[u] * 32;
+                    a[u] = ap[off];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[u][j], a[u], acc[j]);
-                if (dots) {
-                    const size_t off = (size_t)(i + 4 * u) * 32;
-                    float fv[K];
+                    for (int j = 0; j < 8; ++j) w[u][j] = (j < jn) ? __ldcs(rowp[j] + off) : 0.f;
+                }
+            }
 #pragma unroll
-                    for (int q = 0; q < K; ++q) fv[q] = hf[(size_t)q * n * 32 + off];
+            for (int u = 0; u < U; ++u) {
+                if (idx[u] >= 0) {
 #pragma unroll
-                    for (int q = 0; q < K; ++q) dacc[q] = fmaf(fv[q], a[u], dacc[q]);
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[u][j], a[u], acc[j]);
                 }
             }
         }
@@ -1443,27 +1461,19 @@ __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
     // CTA partial: ((w0 + w1) + (w2 + w3)) per row, parked in the partial arena [chunk][size_out + K]
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
-    if (dots) {
-#pragma unroll
-        for (int q = 0; q < K; ++q) red[warp][8 + q][lane] = dacc[q];
-    }
     __syncthreads();
     const int prow = size_out + K;
     float* pg = ssb_grp(h.part, h.rows_p, g, lane) + (size_t)hd[2] * 32;
-    for (int j = warp; j < 8 + (dots ? K : 0); j += 4) {
+    for (int j = warp; j < jn; j += 4) {
         const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
-        if (j < 8) {
-            if (j < jn) pg[(size_t)(chunk * prow + j0 + j) * 32] = t;
-        } else {
-            pg[(size_t)(chunk * prow + size_out + (j - 8)) * 32] = t;
-        }
+        pg[(size_t)(chunk * prow + (dots ? size_out : j0) + j) * 32] = t;
     }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         int* cnt_p = h.counters + hd[3] * c.G + g;
         const int old = atomicAdd(cnt_p, 1);
-        const int last = old == n_jt * n_chunks - 1;
+        const int last = old == (n_jt + 1) * n_chunks - 1;
         if (last) *cnt_p = 0;
         flag = last;
     }
@@ -1483,6 +1493,7 @@ __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
     }
     const float* __restrict__ he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
     float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    const float alpha = s.step > 0 ? __int_as_float(d[7]) : 0.f;
     for (int jb = warp * 8; jb < size_out; jb += 32) {   // each warp takes 8 consecutive output rows at a time
         float t[8];
 #pragma unroll
@@ -1499,7 +1510,8 @@ __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
             if (jb + u < size_out) {
                 float e[K];
 #pragma unroll
-                for (int q = 0; q < K; ++q) e[q] = he[(size_t)(q * size_out + jb + u) * 32];
+                for (int q = 0; q < K; ++q)
+                    e[q] = (q == slot) ? alpha * vg[(size_t)(err_vec + jb + u) * 32] : he[(size_t)(q * size_out + jb + u) * 32];
                 float r = t[u];
 #pragma unroll
                 for (int q = 0; q < K; ++q) r = fmaf(e[q], dsum[q], r);
@@ -1509,12 +1521,10 @@ __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
     }
 }
 
-// force != 0: fold whatever is pending (host read-back); otherwise only on the last slot of a window
+// launched by the host after the step whose slot is K - 1, and before any read-back of the decoders
 template <int K>
 __global__ void __launch_bounds__(128) k_pes_fold(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
                                                     const int* __restrict__ hdesc, int max_chunks, int i_rel, int force) {
-    const SsbStep s = ssb_step(c, i_rel);
-    if (!force && (int)(s.step % K) != K - 1) return;
     const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
     const int* d = desc + item * 13;
     const int* hd = hdesc + item * 4;
@@ -1552,8 +1562,6 @@ __global__ void __launch_bounds__(128) k_pes_fold(SsbCtx c, SsbPesDefer h, const
 }
 
 __global__ void __launch_bounds__(128) k_pes_clear(SsbCtx c, SsbPesDefer h, int i_rel, int force) {
-    const SsbStep s = ssb_step(c, i_rel);
-    if (!force && (int)(s.step % h.K) != h.K - 1) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x * 4 + warp;
     if (r < h.rows_e) ssb_grp(h.hist_e, h.rows_e, blockIdx.y, lane)[(size_t)r * 32] = 0.f;
