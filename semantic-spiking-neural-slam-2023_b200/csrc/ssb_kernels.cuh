@@ -1544,20 +1544,32 @@ __global__ void __launch_bounds__(128) k_pes_fold(SsbCtx c, SsbPesDefer h, const
     for (int q = 0; q < K; ++q)
 #pragma unroll
         for (int j = 0; j < 8; ++j) ae[q][j] = (j < jn) ? he[(size_t)(q * size_out + j0 + j) * 32] : 0.f;
-    for (int i = i_lo + warp; i < i_hi; i += 4) {
-        const size_t off = (size_t)i * 32;
-        float fv[K], w[8];
+    constexpr int U = 2;                     // two neurons per iteration: 2 * (K + 8) loads in flight per warp
+    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
+        float fv[U][K], w[U][8];
 #pragma unroll
-        for (int q = 0; q < K; ++q) fv[q] = hf[(size_t)q * n * 32 + off];
+        for (int u = 0; u < U; ++u) {
+            const int ii = i + 4 * u;
+            const size_t off = (size_t)(ii < i_hi ? ii : i) * 32;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = (j < jn) ? __ldcs(dp + (size_t)j * n * 32 + off) : 0.f;
+            for (int q = 0; q < K; ++q) fv[u][q] = hf[(size_t)q * n * 32 + off];
 #pragma unroll
-        for (int q = 0; q < K; ++q)
+            for (int j = 0; j < 8; ++j) w[u][j] = (j < jn) ? __ldcs(dp + (size_t)j * n * 32 + off) : 0.f;
+        }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = fmaf(ae[q][j], fv[q], w[j]);
+        for (int u = 0; u < U; ++u) {
+            const int ii = i + 4 * u;
+            if (ii < i_hi) {
+                const size_t off = (size_t)ii * 32;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < jn) __stcs(dp + (size_t)j * n * 32 + off, w[j]);
+                for (int q = 0; q < K; ++q)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[u][j] = fmaf(ae[q][j], fv[u][q], w[u][j]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < jn) __stcs(dp + (size_t)j * n * 32 + off, w[u][j]);
+            }
+        }
     }
 }
 
