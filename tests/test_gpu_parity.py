@@ -361,3 +361,24 @@ def test_slam_3d_domain_matches_oracle():
         ref = _oracle(sc, sim, trial, n_steps)
         assert _rel(got[trial], ref.data[sc.probe]) < 1e-4
         assert idx[trial] == ssp_ref.cleanup_index(slam.sample_ssps, ref.signals[slam.gridcells, "in"].a)
+
+
+def test_deferred_pes_read_back_in_the_middle_of_a_window():
+    """The PES history (window of 8 steps) is folded into the decoders before any read-back; reading at steps that
+    are not multiples of the window, then continuing, must still follow the oracle's learned weights."""
+    sc = scenarios.make_slam(n_trials=2, n_steps=64, ssp_dim=55, pi_n_neurons=60, mem_n_neurons=128,
+                             circonv_n_neurons=20, n_landmarks=8, T=20.0, neuron_type="lifrate", view_rad=0.8)
+    conn = sc.extra["slam"].assomemory.conn_out
+    sim = _Simulator()(sc.network, dt=sc.dt, n_trials=2, trial_inputs=sc.trial_inputs)
+    ref = RefSimulator(sc.network, dt=sc.dt, model=sim.model, trial_seed=sim.trial_seeds[1],
+                       node_tables={node: arr[1] for node, arr in sc.trial_inputs.items()})
+    seen_learning = False
+    for n in (13, 16, 3, 21):                       # cumulative 13, 29, 32, 53
+        sim.run_steps(n)
+        ref.run_steps(n)
+        got, want = sim.learned_decoders(conn)[1], ref.learned_weights(conn)
+        seen_learning = seen_learning or np.max(np.abs(want)) > 0
+        assert np.max(np.abs(got - want)) < 1e-4 * np.max(np.abs(want)) + 1e-9
+    assert seen_learning
+    assert _rel(sim.data[sc.probe][1], ref.data[sc.probe]) < 1e-4
+    sim.close()
