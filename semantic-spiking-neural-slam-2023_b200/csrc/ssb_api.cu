@@ -26,7 +26,7 @@ int fail(int code, const std::string& msg) {
             return fail(-2, std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
     } while (0)
 
-enum Kind { K_SMALL = 0, K_WIDE, K_DEC, K_PES, K_SCAN, K_PICK, K_GATE, K_LIN, K_ADV, K_BEGIN, K_VOJA, K_NKINDS };
+enum Kind { K_SMALL = 0, K_WIDE, K_DEC, K_PES, K_SCAN, K_PICK, K_GATE, K_LIN, K_ADV, K_BEGIN, K_VOJA, K_EXTRA, K_NKINDS };   // K_EXTRA: further kernels of a multi-kernel scope
 
 struct HostArray {
     std::vector<unsigned char> bytes;
@@ -546,7 +546,13 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
         k_pes_hist<<<dim3((max_rows + 3) / 4, s->n_groups, s->n_pes), 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, i_rel);
         // the host mirrors the step counter, so the fold is launched only after the last slot of a window
         // (a captured graph bakes this in; it is replayed only from steps with the same phase, see ssb_run_steps)
-        if ((int)((s->steps_done + i_rel) % s->pes_h.K) == s->pes_h.K - 1) launch_pes_fold(s, st, i_rel, 1);
+        int extra = 1;                                   // k_pes_hist
+        if ((int)((s->steps_done + i_rel) % s->pes_h.K) == s->pes_h.K - 1) {
+            launch_pes_fold(s, st, i_rel, 1);
+            extra += 2;                                  // k_pes_fold + k_pes_clear
+        }
+        s->kind_launches[K_EXTRA] += extra;
+        s->total_launches += extra;
         return;
     }
     int max_out = 0, max_chunks = 1;
