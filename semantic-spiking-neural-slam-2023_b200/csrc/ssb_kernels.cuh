@@ -102,17 +102,6 @@ __device__ __forceinline__ float ssb_row_batch(const int2* __restrict__ ent, con
     return acc;
 }
 
-__device__ __forceinline__ float ssb_row(const int* __restrict__ ptr, const int2* __restrict__ ent, int row,
-                                         const float* vg) {
-    const int lo = __ldg(ptr + row), hi = __ldg(ptr + row + 1);
-    float acc = 0.f;
-    int p = lo;
-    // long rows (dense DFT / product transforms): 32 independent source loads in flight
-    for (; p + 32 <= hi; p += 32) acc = ssb_row_batch<32>(ent + p, vg, acc);
-    for (; p < hi; p += 8) acc = ssb_row_batch<8>(ent + p, vg, acc);
-    return acc;
-}
-
 // --------------------------------------------------------------------------------------
 // Neuron models.
 struct SsbNeuron {
