@@ -337,16 +337,20 @@ float scan_eps_floor(const CleanupDev& cd) { return cd.tc ? 1.6e-5f : 0.f; }
 template <int DP>
 void launch_scan(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const float* S, const CleanupDev& cd,
                  int dpad, int n_groups, int i_rel) {
-    dim3 grid(cd.n_chunks, (n_groups + 3) / 4);
+    int nw = 4;                                          // warps (= trial groups) per CTA
     size_t smem = (size_t)cd.tile_rows * dpad * sizeof(float);
-    if (DP == 0) smem += (size_t)4 * dpad * 32 * sizeof(float);
+    if (DP == 0) {
+        while (nw > 1 && smem + (size_t)nw * dpad * 32 * sizeof(float) > 200 * 1024) nw >>= 1;
+        smem += (size_t)nw * dpad * 32 * sizeof(float);
+    }
+    dim3 grid(cd.n_chunks, (n_groups + nw - 1) / nw);
     const int n_cand = cd.n_chunks * SSB_TOPK;
     if (csr)
-        k_cleanup_scan<DP, true><<<grid, 128, smem, st>>>(c, desc, S, cd.cx, cd.pval, cd.pidx, cd.rows_per_chunk,
-                                                           cd.tile_rows, n_groups, n_cand, i_rel);
+        k_cleanup_scan<DP, true><<<grid, 32 * nw, smem, st>>>(c, desc, S, cd.cx, cd.pval, cd.pidx, cd.rows_per_chunk,
+                                                              cd.tile_rows, n_groups, n_cand, i_rel);
     else
-        k_cleanup_scan<DP, false><<<grid, 128, smem, st>>>(c, desc, S, cd.cx, cd.pval, cd.pidx, cd.rows_per_chunk,
-                                                            cd.tile_rows, n_groups, n_cand, i_rel);
+        k_cleanup_scan<DP, false><<<grid, 32 * nw, smem, st>>>(c, desc, S, cd.cx, cd.pval, cd.pidx, cd.rows_per_chunk,
+                                                               cd.tile_rows, n_groups, n_cand, i_rel);
 }
 
 void dispatch_scan(cudaStream_t st, bool csr, int dpad, int n_groups, const SsbCtx& c, const int* desc, const float* S,
@@ -415,10 +419,12 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
         dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
         k_wide_static<DP><<<grid, 128, smem_of(chunk), st>>>(s->ctx, s->d_big, items, chunk, i_rel);
     } else {
-        int nwarps = 4;
+        int nwarps = 4, nb = SSB_VOJA_NB;
         auto smem_of = [&](int nw) {
-            return (size_t)(max_dpad * 32 + max_jn * 32 + nw * SSB_VOJA_NB * max_dims * 32) * sizeof(float) + s->voja_pad_smem;
+            return (size_t)(max_dpad * 32 + max_jn * 32 + nw * nb * max_dims * 32) * sizeof(float) + s->voja_pad_smem;
         };
+        // very wide ensembles (d = 649: 83 KB per encoder tile): fewer tiles in flight, then fewer warps
+        while (nb > 1 && smem_of(1) > 200 * 1024) --nb;
         while (nwarps > 1 && smem_of(nwarps) > 200 * 1024) nwarps >>= 1;
         // one wave: every resident CTA slot gets one contiguous neuron range of a trial group
         const int key = (1 << 30) | (DP << 20) | (max_n << 6) | (units & 63);
@@ -435,7 +441,7 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
         }
         if (dry) return;
         dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
-        k_wide_voja<DP><<<grid, 32 * nwarps, smem_of(nwarps), st>>>(s->ctx, s->d_big, items, chunk, i_rel);
+        k_wide_voja<DP><<<grid, 32 * nwarps, smem_of(nwarps), st>>>(s->ctx, s->d_big, items, chunk, i_rel, nb);
     }
 }
 

@@ -740,10 +740,10 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
 // column in place and the tile is written back only if some lane spiked (post_synapse=None => the
 // delta is row-sparse).  SimVoja: delta = alpha*L*(scale*outer(post, x) - post[:,None]*E), visible
 // to the next step.
-#define SSB_VOJA_NB 3         // encoder tiles in flight per warp
+#define SSB_VOJA_NB 3         // encoder tiles in flight per warp (fewer when a tile is too large: very wide ensembles)
 template <int DP>
 __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restrict__ desc, SsbItemList items, int chunk,
-                                                    int i_rel) {
+                                                    int i_rel, int nb) {
     extern __shared__ __align__(128) float sm[];
     __shared__ unsigned long long wbar[4][SSB_VOJA_NB];
     const int* d = desc + items.idx[blockIdx.z] * 16;
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
     const bool stateful = nt.type == 0;
     float* xs = sm;                                        // [dpad][32]
     float* us = xs + (size_t)dpad * 32;                    // [jn_m][32]
-    float* ebuf = us + (size_t)jn_m * 32 + (size_t)warp * SSB_VOJA_NB * dims * 32;   // [NB][dims][32] per warp
+    float* ebuf = us + (size_t)jn_m * 32 + (size_t)warp * nb * dims * 32;   // [nb][dims][32] per warp
     const int per = (chunk + nwarps - 1) / nwarps;
     const int i_lo = warp * per, i_hi = min(cnt, i_lo + per);
     float* eg = c.lenc + ((size_t)g * c.n_lenc + enc_off + (size_t)(n0 + i_lo) * dims) * 32;   // tile of neuron i_lo
@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
     if (lane == 0) {
         for (int t = 0; t < SSB_VOJA_NB; ++t) ssb_mbar_init(&wbar[warp][t], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int t = 0; t < SSB_VOJA_NB && i_lo + t < i_hi; ++t) {
+        for (int t = 0; t < nb && i_lo + t < i_hi; ++t) {
             ssb_mbar_expect_tx(&wbar[warp][t], tile_bytes);
             ssb_bulk_g2s(ebuf + (size_t)t * dims * 32, eg + (size_t)t * dims * 32, tile_bytes, &wbar[warp][t]);
         }
@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
     float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)(act0 + n0) * 32;
     uint32_t phases = 0;
     for (int i = i_lo; i < i_hi; ++i) {
-        const int t = i - i_lo, b = t % SSB_VOJA_NB;
+        const int t = i - i_lo, b = t % nb;
         float* E = ebuf + (size_t)b * dims * 32 + lane;
         float sv = 0.f;
         if (stateful) sv = __ldcs(sp + (size_t)i * 32);
@@ -851,12 +851,17 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
             // before buffer b_prev = (t - 1) % NB is refilled, only the group of tile t may still be reading
             if (dirty) ssb_bulk_s2g(eg + (size_t)t * dims * 32, ebuf + (size_t)b * dims * 32, tile_bytes);
             ssb_bulk_commit();
-            if (t >= 1 && i + SSB_VOJA_NB - 1 < i_hi) {
-                const int bp = (t - 1) % SSB_VOJA_NB;
+            if (nb == 1) {                                   // single buffer: refill after this tile's own store has read it
+                if (i + 1 < i_hi) {
+                    ssb_bulk_wait_read0();
+                    ssb_mbar_expect_tx(&wbar[warp][0], tile_bytes);
+                    ssb_bulk_g2s(ebuf, eg + (size_t)(t + 1) * dims * 32, tile_bytes, &wbar[warp][0]);
+                }
+            } else if (t >= 1 && i + nb - 1 < i_hi) {
+                const int bp = (t - 1) % nb;
                 asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 ssb_mbar_expect_tx(&wbar[warp][bp], tile_bytes);
-                ssb_bulk_g2s(ebuf + (size_t)bp * dims * 32, eg + (size_t)(t - 1 + SSB_VOJA_NB) * dims * 32, tile_bytes,
-                             &wbar[warp][bp]);
+                ssb_bulk_g2s(ebuf + (size_t)bp * dims * 32, eg + (size_t)(t - 1 + nb) * dims * 32, tile_bytes, &wbar[warp][bp]);
             }
         }
     }
@@ -1617,13 +1622,13 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
     extern __shared__ float sm[];
     const int G = d[0], dims = d[1], dpad = d[2], in_row0 = d[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int group = blockIdx.y * 4 + warp;
+    const int group = blockIdx.y * (blockDim.x >> 5) + warp;   // 4 warps per CTA; fewer for very wide queries (x staging)
     const bool live = group < n_groups;
     const int g = live ? group : 0;
     const int g_lo = blockIdx.x * rows_per_chunk;
     const int g_hi = min(G, g_lo + rows_per_chunk);
     float* tile = sm;                              // [tile_rows][dpad]
-    float* xs = sm + (size_t)tile_rows * dpad;     // [4][dpad][32] (generic width only)
+    float* xs = sm + (size_t)tile_rows * dpad;     // [warps][dpad][32] (generic width only)
     float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
     float x[DP > 0 ? DP : 1];
     if (CSR_INPUT) {   // query = materialised vec rows of this step
