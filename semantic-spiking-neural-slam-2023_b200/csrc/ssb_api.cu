@@ -337,12 +337,8 @@ float scan_eps_floor(const CleanupDev& cd) { return cd.tc ? 1.6e-5f : 0.f; }
 template <int DP>
 void launch_scan(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const float* S, const CleanupDev& cd,
                  int dpad, int n_groups, int i_rel) {
-    int nw = 4;                                          // warps (= trial groups) per CTA
-    size_t smem = (size_t)cd.tile_rows * dpad * sizeof(float);
-    if (DP == 0) {
-        while (nw > 1 && smem + (size_t)nw * dpad * 32 * sizeof(float) > 200 * 1024) nw >>= 1;
-        smem += (size_t)nw * dpad * 32 * sizeof(float);
-    }
+    const int nw = 4;                                    // warps (= trial groups) per CTA
+    const size_t smem = (size_t)cd.tile_rows * dpad * sizeof(float);
     dim3 grid(cd.n_chunks, (n_groups + nw - 1) / nw);
     const int n_cand = cd.n_chunks * SSB_TOPK;
     if (csr)

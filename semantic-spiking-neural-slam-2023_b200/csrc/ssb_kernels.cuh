@@ -1613,7 +1613,7 @@ __device__ __forceinline__ void ssb_top_push(SsbTop& t, float val, int g) {
 
 // desc: G d dpad s_off in_row0 out_vec ; scratch: cx[G][dpad][32], pval/pidx[G][n_cand][32]
 // A CTA owns grid rows [blockIdx.x*rows_per_chunk, +rows_per_chunk) and walks them in shared-memory
-// tiles of tile_rows rows.  dynamic smem: tile_rows*dpad (S tile) + 4*dpad*32 (x staging, generic width only)
+// tiles of tile_rows rows.  dynamic smem: tile_rows*dpad (S tile)
 template <int DP, bool CSR_INPUT>
 __global__ void __launch_bounds__(128)
 k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S, float* __restrict__ cx,
@@ -1622,13 +1622,12 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
     extern __shared__ float sm[];
     const int G = d[0], dims = d[1], dpad = d[2], in_row0 = d[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int group = blockIdx.y * (blockDim.x >> 5) + warp;   // 4 warps per CTA; fewer for very wide queries (x staging)
+    const int group = blockIdx.y * 4 + warp;
     const bool live = group < n_groups;
     const int g = live ? group : 0;
     const int g_lo = blockIdx.x * rows_per_chunk;
     const int g_hi = min(G, g_lo + rows_per_chunk);
     float* tile = sm;                              // [tile_rows][dpad]
-    float* xs = sm + (size_t)tile_rows * dpad;     // [warps][dpad][32] (generic width only)
     float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
     float x[DP > 0 ? DP : 1];
     if (CSR_INPUT) {   // query = materialised vec rows of this step
@@ -1639,21 +1638,17 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
                 x[k] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
                 if (blockIdx.x == 0 && live) cxg[(size_t)k * 32] = x[k];
             }
-        } else {
-            for (int k = 0; k < dpad; ++k) {
-                const float xv = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
-                xs[(warp * dpad + k) * 32 + lane] = xv;
-                if (blockIdx.x == 0 && live) cxg[(size_t)k * 32] = xv;
-            }
+        } else if (blockIdx.x == 0 && live) {      // generic width: the query is re-read per tile; keep the copy for the pick
+            for (int k = 0; k < dpad; ++k) cxg[(size_t)k * 32] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
         }
     } else {
         if (DP > 0) {
 #pragma unroll
             for (int k = 0; k < DP; ++k) x[k] = (k < dims) ? cxg[(size_t)k * 32] : 0.f;
-        } else {
-            for (int k = 0; k < dpad; ++k) xs[(warp * dpad + k) * 32 + lane] = (k < dims) ? cxg[(size_t)k * 32] : 0.f;
         }
     }
+    // generic width: source of the query columns (materialised vec rows, or the prepared stand-alone query)
+    const float* xsrc = CSR_INPUT ? ssb_grp(c.vec, c.nv, g, lane) + (size_t)in_row0 * 32 : cxg;
     SsbTop top;
     ssb_top_init(top);
     for (int g0 = g_lo; g0 < g_hi; g0 += tile_rows) {
@@ -1702,19 +1697,37 @@ k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S,
                 ssb_top_push(top, (a0 + a1) + (a2 + a3), gg);
             }
         } else {
-            const float* xw = xs + (size_t)warp * dpad * 32 + lane;
-            for (int gg = g0; gg < g1; ++gg) {
-                const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(gg - g0) * dpad);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                for (int k4 = 0; k4 < (dpad >> 2); ++k4) {
-                    const float4 e = s4[k4];
-                    const float* xk = xw + (k4 * 4) * 32;
-                    a0 = fmaf(e.x, xk[0], a0);
-                    a1 = fmaf(e.y, xk[32], a1);
-                    a2 = fmaf(e.z, xk[64], a2);
-                    a3 = fmaf(e.w, xk[96], a3);
+            // generic width (any d, e.g. 649): the query is streamed in 32-column register chunks while the partial
+            // scores of up to 16 tile rows stay in registers: 8 broadcast float4 grid reads per 32 FFMAs
+            for (int gg0 = g0; gg0 < g1; gg0 += 16) {
+                const int nr = min(16, g1 - gg0);
+                float acc[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+                for (int k0 = 0; k0 < dpad; k0 += 32) {
+                    float xk[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) xk[e] = (k0 + e < dims) ? xsrc[(size_t)(k0 + e) * 32] : 0.f;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        if (r < nr) {
+                            const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(gg0 - g0 + r) * dpad + k0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                if (k0 + 4 * q < dpad) {
+                                    const float4 e = s4[q];
+                                    acc[r] = fmaf(e.x, xk[4 * q + 0], acc[r]);
+                                    acc[r] = fmaf(e.y, xk[4 * q + 1], acc[r]);
+                                    acc[r] = fmaf(e.z, xk[4 * q + 2], acc[r]);
+                                    acc[r] = fmaf(e.w, xk[4 * q + 3], acc[r]);
+                                }
+                            }
+                        }
+                    }
                 }
-                ssb_top_push(top, (a0 + a1) + (a2 + a3), gg);
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    if (r < nr) ssb_top_push(top, acc[r], gg0 + r);
             }
         }
     }

@@ -80,7 +80,10 @@ def test_ssp_decode_ties_first_maximum_wins():
     assert np.array_equal(cabi.ssp_decode_argmax(ssps, qs), ssp_ref.decode_indices(ssps, qs))
 
 
-def test_ssp_decode_generic_width_3d():
+@pytest.mark.parametrize("scan", ["tc", "ffma"])
+def test_ssp_decode_generic_width_3d(scan, monkeypatch):
+    if scan == "ffma":
+        monkeypatch.setenv("SSB_SCAN", "ffma")             # the register-chunked generic-width FFMA scan (what d = 649 uses)
     sp = HexagonalSSPSpace(3, ssp_dim=55, domain_bounds=np.tile([-1.0, 1.0], (3, 1)), length_scale=0.3,
                            rng=np.random.default_rng(0), backend="host")       # d = 33 -> generic-width kernels
     ssps, pts = sp.get_sample_pts_and_ssps(12, "grid")
