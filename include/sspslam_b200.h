@@ -65,6 +65,20 @@ int ssb_run_steps(ssb_sim* s, int n_steps);
  * Replaces: sim.run_steps(n) + sim.data[probe] with host-resident inputs (run_slam.py:232-233,250). */
 int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* host_probes);
 int ssb_io_wait(ssb_sim* s);
+/* On-device input synthesis.  Replaces the input tables, i.e. the reference's per-step Python input
+ * closures (sspslam/networks/slam.py:442-497 get_slam_input_functions2; experiments/run_slam.py:164-169;
+ * run_pathint.py:134-136), by a kernel that evaluates them from per-trial paths and landmarks:
+ *   cfg     = {domain_dim, ssp_dim, n_landmarks, path_len, vel_col, init_col, lmvec_col, lmsp_col, nolm_col}
+ *             (column = first input-table row of that signal, -1 = absent),
+ *   fparams = {view_rad, none_in_view_value},
+ *   phases  [ssp_dim][domain_dim] = phase_matrix / length_scale, lm_sp [n_landmarks][ssp_dim] (float64, shared),
+ *   path_rows / vel_rows [path_len*domain_dim][n_trials_padded], lm_rows [n_landmarks*domain_dim][n_trials_padded]
+ *             (float32, per trial; vel = velocities already multiplied by vel_scaling_factor).
+ * Call after ssb_finalize.  ssb_synth_steps then supplies, per chunk, the float-fragile step indices the closures use
+ * (idx [n_steps][3] = int((t-dt)/dt), min(floor(t/dt), path_len-2), t < init_time) instead of table rows. */
+int ssb_synth_setup(ssb_sim* s, const int* cfg, const float* fparams, const double* phases, const double* lm_sp,
+                    const float* path_rows, const float* vel_rows, const float* lm_rows);
+int ssb_synth_steps(ssb_sim* s, const int* idx, long long step0, int n_steps);
 /* Replaces: sim.data[probe] for node/ensemble probes: host [n_steps][n_probe][n_trials_padded]. */
 int ssb_read_probes(ssb_sim* s, float* host, long long step0, int n_steps);
 long long ssb_n_steps(ssb_sim* s);

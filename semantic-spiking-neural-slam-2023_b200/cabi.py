@@ -44,6 +44,8 @@ def load():
         "ssb_run_steps": (I, [P, I]),
         "ssb_run_steps_io": (I, [P, P, I, P]),
         "ssb_io_wait": (I, [P]),
+        "ssb_synth_setup": (I, [P, P, P, P, P, P, P, P]),
+        "ssb_synth_steps": (I, [P, P, LL, I]),
         "ssb_read_probes": (I, [P, P, LL, I]),
         "ssb_n_steps": (LL, [P]),
         "ssb_n_trials_padded": (I, [P]),
@@ -71,7 +73,7 @@ def load():
 
 
 EXPORTS = ("ssb_create", "ssb_set_array", "ssb_set_scalar", "ssb_finalize", "ssb_upload", "ssb_download",
-           "ssb_set_tables", "ssb_rebase_tables", "ssb_run_steps", "ssb_run_steps_io", "ssb_io_wait", "ssb_read_probes", "ssb_n_steps",
+           "ssb_set_tables", "ssb_rebase_tables", "ssb_run_steps", "ssb_run_steps_io", "ssb_io_wait", "ssb_synth_setup", "ssb_synth_steps", "ssb_read_probes", "ssb_n_steps",
            "ssb_n_trials_padded", "ssb_sync", "ssb_reset", "ssb_destroy", "ssb_set_profiling", "ssb_last_run_ms",
            "ssb_kernel_times", "ssb_total_launches", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_ssp_encode", "ssb_ssp_decode_argmax", "ssb_host_alloc",
            "ssb_host_free", "ssb_last_error", "ssb_version")

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <map>
 #include <string>
 #include <vector>
@@ -139,6 +140,14 @@ struct ssb_sim {
     int* d_dec_wt_off = nullptr;
     int dec_tc_n = 64;                      // operand tile width of k_decode_tc (64 or 128 output columns)
     std::vector<char> dec_tc_level;         // per level: every decoder of the level can use the tensor-core kernel
+    // on-device input synthesis (ssb_synth_setup): replaces k_begin and the input tables
+    bool synth_on = false;
+    SsbSynth synth;
+    float *syn_path = nullptr, *syn_vel = nullptr, *syn_lm = nullptr, *syn_phases = nullptr, *syn_lmsp = nullptr;
+    float *syn_cos = nullptr, *syn_sin = nullptr;
+    int* syn_idx = nullptr;
+    long long syn_step0 = 0;
+    int syn_steps = 0;
     SsbPesDefer pes_h = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};   // deferred PES history (K = 0: off)
     int* d_pes_hdesc = nullptr;
     size_t pes_pad_smem = 0, voja_pad_smem = 0;   // experiment knobs: extra dynamic smem lowers residency
@@ -848,7 +857,10 @@ int one_step(ssb_sim* s, int i_rel) {
     const int G = s->n_groups;
     const bool par = s->parallel && !s->profiling && !s->debug_sync;
     cudaStream_t A = s->stream, B = par ? s->aux[0] : A, C = par ? s->aux[1] : A, D = par ? s->aux[2] : A;
-    if (s->nt > 0) {
+    if (s->synth_on) {
+        LaunchTimer t(s, K_BEGIN);
+        k_synth<<<G, 256, (size_t)2 * s->synth.d * 32 * sizeof(float), A>>>(c, s->synth, i_rel);
+    } else if (s->nt > 0) {
         LaunchTimer t(s, K_BEGIN);
         dim3 grid(((int)s->nt + 3) / 4, G);
         k_begin<<<grid, 128, 0, A>>>(c, i_rel);
@@ -977,7 +989,7 @@ int build_graph(ssb_sim* s, int n) {
 }
 
 int push_dyn(ssb_sim* s) {
-    long long h[3] = {s->steps_done, s->tab_step0, s->probe_step0};
+    long long h[4] = {s->steps_done, s->tab_step0, s->probe_step0, s->syn_step0};
     SSB_CUDA(cudaMemcpyAsync(s->dyn, h, sizeof(h), cudaMemcpyHostToDevice, s->stream));
     return 0;
 }
@@ -1259,7 +1271,10 @@ int ssb_run_steps(ssb_sim* s, int n_steps) {
     if (!s || !s->finalized) return fail(-1, "ssb_run_steps: bad handle");
     if (n_steps <= 0) return 0;
     if (n_steps > s->chunk_cap) return fail(-1, "ssb_run_steps: n_steps exceeds chunk_cap (probe buffer)");
-    if (s->nt > 0 && (s->steps_done < s->tab_step0 || s->steps_done + n_steps > s->tab_step0 + s->tab_steps))
+    if (s->synth_on) {
+        if (s->steps_done < s->syn_step0 || s->steps_done + n_steps > s->syn_step0 + s->syn_steps)
+            return fail(-4, "ssb_run_steps: resident step indices (ssb_synth_steps) do not cover the requested steps");
+    } else if (s->nt > 0 && (s->steps_done < s->tab_step0 || s->steps_done + n_steps > s->tab_step0 + s->tab_steps))
         return fail(-4, "ssb_run_steps: resident input tables do not cover the requested steps");
     SSB_CUDA(cudaSetDevice(s->device));
     s->probe_step0 = s->steps_done;
@@ -1304,7 +1319,10 @@ int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* h
     if (!s || !s->finalized) return fail(-1, "ssb_run_steps_io: bad handle");
     if (n_steps <= 0) return 0;
     if (n_steps > s->chunk_cap) return fail(-1, "ssb_run_steps_io: n_steps exceeds chunk_cap");
-    if (s->nt > 0 && !host_tables) return fail(-1, "ssb_run_steps_io: null table buffer");
+    const bool copy_tables = s->nt > 0 && !s->synth_on;
+    if (copy_tables && !host_tables) return fail(-1, "ssb_run_steps_io: null table buffer");
+    if (s->synth_on && (s->steps_done < s->syn_step0 || s->steps_done + n_steps > s->syn_step0 + s->syn_steps))
+        return fail(-4, "ssb_run_steps_io: resident step indices (ssb_synth_steps) do not cover the requested steps");
     SSB_CUDA(cudaSetDevice(s->device));
     if (!s->io_h2d) {
         SSB_CUDA(cudaStreamCreateWithFlags(&s->io_h2d, cudaStreamNonBlocking));
@@ -1331,7 +1349,7 @@ int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* h
     SSB_CUDA(cudaStreamWaitEvent(s->io_h2d, s->io_events[2 * n_sub], 0));
     for (int j = 0; j < n_sub; ++j) {
         const int j0 = j * sub, jn = std::min(sub, n_steps - j0);
-        if (s->nt > 0) {
+        if (copy_tables) {
             if (copy_rows(s, s->tab, (long long)s->chunk_cap * s->nt, (size_t)j0 * s->nt, (size_t)jn * s->nt,
                           const_cast<float*>(host_tables) + (size_t)j0 * s->nt * s->B, true, s->io_h2d))
                 return -2;
@@ -1340,7 +1358,7 @@ int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* h
     }
     for (int j = 0; j < n_sub; ++j) {
         const int j0 = j * sub, jn = std::min(sub, n_steps - j0);
-        if (s->nt > 0) SSB_CUDA(cudaStreamWaitEvent(s->stream, s->io_events[2 * j], 0));
+        if (copy_tables) SSB_CUDA(cudaStreamWaitEvent(s->stream, s->io_events[2 * j], 0));
         const bool phase_ok = s->pes_h.K == 0 || (int)(s->steps_done % s->pes_h.K) == s->graph_phase;
         if (graphs && s->step_graph && jn == s->graph_steps && phase_ok) {
             SSB_CUDA(cudaGraphLaunch(s->step_graph, s->stream));
@@ -1375,6 +1393,96 @@ int ssb_io_wait(ssb_sim* s) {
     SSB_CUDA(cudaStreamSynchronize(s->stream));
     if (s->io_d2h) SSB_CUDA(cudaStreamSynchronize(s->io_d2h));
     SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ssb_synth_setup(ssb_sim* s, const int* cfg, const float* fparams, const double* phases, const double* lm_sp,
+                    const float* path_rows, const float* vel_rows, const float* lm_rows) {
+    if (!s || !s->finalized || !cfg || !fparams || !phases || !path_rows || !vel_rows)
+        return fail(-1, "ssb_synth_setup: bad arguments");
+    if (s->synth_on) return fail(-1, "ssb_synth_setup: already configured");
+    SSB_CUDA(cudaSetDevice(s->device));
+    SsbSynth& y = s->synth;
+    memset(&y, 0, sizeof(y));
+    y.dim = cfg[0];
+    y.d = cfg[1];
+    y.n_lm = cfg[2];
+    y.T = cfg[3];
+    y.vel_col = cfg[4];
+    y.init_col = cfg[5];
+    y.lmvec_col = cfg[6];
+    y.lmsp_col = cfg[7];
+    y.nolm_col = cfg[8];
+    y.view_rad = fparams[0];
+    y.none_value = fparams[1];
+    if (y.dim < 1 || y.dim > 3 || y.d < 1 || y.T < 2 || y.n_lm < 0) return fail(-1, "ssb_synth_setup: bad sizes");
+    if (y.n_lm > 0 && (!lm_sp || !lm_rows)) return fail(-1, "ssb_synth_setup: landmark arrays missing");
+    const int cols[5] = {y.vel_col, y.init_col, y.lmvec_col, y.lmsp_col, y.nolm_col};
+    const int widths[5] = {y.dim, y.d, y.d, y.d, 1};
+    for (int i = 0; i < 5; ++i)
+        if (cols[i] >= 0 && cols[i] + widths[i] > s->nt) return fail(-1, "ssb_synth_setup: input column outside the table rows");
+    if ((size_t)2 * y.d * 32 * sizeof(float) > 200 * 1024) return fail(-1, "ssb_synth_setup: ssp_dim too large");
+    const size_t B = s->B;
+    auto rows_up = [&](float** dst, const float* host, long long rows) {
+        if (alloc_rows(dst, rows, (int)B)) return 1;
+        if (rows > 0 && copy_rows(s, *dst, rows, 0, (size_t)rows, const_cast<float*>(host), true)) return 1;
+        return 0;
+    };
+    if (rows_up(&s->syn_path, path_rows, (long long)y.T * y.dim) || rows_up(&s->syn_vel, vel_rows, (long long)y.T * y.dim)) return -2;
+    if (y.n_lm > 0 && rows_up(&s->syn_lm, lm_rows, (long long)y.n_lm * y.dim)) return -2;
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<float> ph((size_t)y.d * y.dim), sp((size_t)std::max(1, y.n_lm) * y.d, 0.f), ct((size_t)y.d * y.d), st((size_t)y.d * y.d);
+    for (size_t i = 0; i < ph.size(); ++i) ph[i] = (float)phases[i];
+    for (size_t i = 0; i < (size_t)y.n_lm * y.d; ++i) sp[i] = (float)lm_sp[i];
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k = 0; k < y.d; ++k)
+        for (int m = 0; m < y.d; ++m) {
+            const double ang = two_pi * (double)(((long long)k * m) % y.d) / (double)y.d;
+            ct[(size_t)k * y.d + m] = (float)cos(ang);
+            st[(size_t)k * y.d + m] = (float)sin(ang);
+        }
+    auto up = [&](float** dst, const std::vector<float>& v) {
+        if (cudaMalloc((void**)dst, v.size() * sizeof(float)) != cudaSuccess) return 1;
+        return cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ? 1 : 0;
+    };
+    if (up(&s->syn_phases, ph) || up(&s->syn_lmsp, sp) || up(&s->syn_cos, ct) || up(&s->syn_sin, st))
+        return fail(-2, "ssb_synth_setup: upload failed");
+    SSB_CUDA(cudaMalloc((void**)&s->syn_idx, (size_t)s->chunk_cap * 4 * sizeof(int)));
+    SSB_CUDA(cudaMemset(s->syn_idx, 0, (size_t)s->chunk_cap * 4 * sizeof(int)));
+    SSB_CUDA(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    y.path = s->syn_path;
+    y.vel = s->syn_vel;
+    y.lm = s->syn_lm;
+    y.phases = s->syn_phases;
+    y.lm_sp = s->syn_lmsp;
+    y.cosT = s->syn_cos;
+    y.sinT = s->syn_sin;
+    y.idx = s->syn_idx;
+    s->synth_on = true;
+    if (s->step_graph) {                     // a graph captured with k_begin is stale now
+        cudaGraphExecDestroy(s->step_graph);
+        s->step_graph = nullptr;
+    }
+    return 0;
+}
+
+int ssb_synth_steps(ssb_sim* s, const int* idx, long long step0, int n_steps) {
+    if (!s || !s->finalized || !s->synth_on || !idx) return fail(-1, "ssb_synth_steps: bad arguments");
+    if (n_steps < 0 || n_steps > s->chunk_cap) return fail(-1, "ssb_synth_steps: n_steps exceeds chunk_cap");
+    SSB_CUDA(cudaSetDevice(s->device));
+    std::vector<int> h((size_t)n_steps * 4, 0);
+    for (int i = 0; i < n_steps; ++i) {
+        const int ip = idx[i * 3], ic = idx[i * 3 + 1];
+        if (ip < 0 || ip >= s->synth.T || ic < 0 || ic >= s->synth.T) return fail(-1, "ssb_synth_steps: path index out of range");
+        h[(size_t)i * 4] = ip;
+        h[(size_t)i * 4 + 1] = ic;
+        h[(size_t)i * 4 + 2] = idx[i * 3 + 2];
+    }
+    // the stream is idle between calls of the synchronous run entry points; a plain ordered copy is enough
+    SSB_CUDA(cudaStreamSynchronize(s->stream));
+    SSB_CUDA(cudaMemcpy(s->syn_idx, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+    s->syn_step0 = step0;
+    s->syn_steps = n_steps;
     return 0;
 }
 
@@ -1442,7 +1550,8 @@ void ssb_destroy(ssb_sim* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
                     s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_enc_t, s->d_enc_t_off, s->pes_h.hist_e, s->pes_h.hist_f, s->pes_h.part,
-                    s->pes_h.counters, s->d_pes_hdesc, s->aflag, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->pes_h.counters, s->d_pes_hdesc, s->aflag, s->syn_path, s->syn_vel, s->syn_lm, s->syn_phases, s->syn_lmsp,
+                    s->syn_cos, s->syn_sin, s->syn_idx, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
                     s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);

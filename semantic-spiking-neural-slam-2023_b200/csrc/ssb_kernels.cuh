@@ -46,7 +46,8 @@ struct SsbCtx {
     const int2* ent0;         // CSR entries (vec row, coefficient bits) resolved for even steps
     const int2* ent1;         //   ... and for odd steps (filter columns point at the other half)
     const float* ntypes;      // [n][8] = type, tau_rc, tau_ref, min_voltage, amplitude, fast_math, -, -
-    const long long* dyn;     // [0] completed steps, [1] first step of resident tables, [2] first step of probe buffer
+    const long long* dyn;     // [0] completed steps, [1] first step of resident tables, [2] first step of probe buffer,
+                              // [3] first step of the resident synthesis indices
 };
 
 struct SsbStep {
@@ -303,6 +304,120 @@ __global__ void __launch_bounds__(128) k_begin(SsbCtx c, int i_rel) {
     const long long s_loc = c.dyn[0] + i_rel - c.dyn[1];
     const float* src = c.tab + (((size_t)g * c.tab_cap + (size_t)s_loc) * c.nt + row) * 32 + lane;
     ssb_grp(c.vec, c.nv, g, lane)[(size_t)(c.tab_row0 + row) * 32] = __ldcs(src);
+}
+
+// --------------------------------------------------------------------------------------
+// On-device input synthesis: what the reference's per-step Python closures compute
+// (sspslam/networks/slam.py:442-497 get_slam_input_functions2, experiments/run_slam.py:164-169,
+// run_pathint.py:134-136), from per-trial paths / landmarks instead of 168-float-per-step host tables:
+//   vel      = vels_scaled[i_prev]
+//   init     = encode(path[i_prev]) while t < init_time, else 0
+//   lm_sp    = sum of the landmark SPs within view_rad of path[i_prev]
+//   lmvec    = sum_l in view encode(landmark_l - path[i_cur]) = IDFT(sum_l exp(i A v_l)): the complex exponentials
+//              are summed first, so one inverse-DFT mat-vec per trial serves any number of landmarks
+//   nolm     = 0 if some landmark is in view, else none_in_view_value
+// The float-fragile step indices (int((t-dt)/dt), floor(t/dt)) stay on the host: 12 bytes per step instead of a table row.
+// CTA = one trial group, 8 warps; warps split the frequency index k (phase 1) and the output index m (phase 2).
+struct SsbSynth {
+    const float* path;        // [G][T*dim][32]
+    const float* vel;         // [G][T*dim][32]
+    const float* lm;          // [G][n_lm*dim][32]
+    const float* phases;      // [d][dim]   A / length_scale
+    const float* lm_sp;       // [n_lm][d]
+    const float* cosT;        // [d][d]     cos(2 pi k m / d)
+    const float* sinT;
+    const int* idx;           // [steps][4] i_prev, i_cur, init flag, -
+    int T, dim, d, n_lm;
+    int vel_col, init_col, lmvec_col, lmsp_col, nolm_col;
+    float view_rad, none_value;
+};
+
+__device__ __forceinline__ void ssb_synth_idft(const SsbSynth& y, const float* sC, const float* sS, float* out_row0, int lane,
+                                               int warp) {
+    const float inv_d = 1.f / (float)y.d;
+    for (int m = warp; m < y.d; m += 8) {
+        float acc = 0.f;
+        for (int k = 0; k < y.d; ++k) {
+            const float ct = __ldg(y.cosT + (size_t)k * y.d + m), st = __ldg(y.sinT + (size_t)k * y.d + m);
+            acc = fmaf(sC[k * 32 + lane], ct, acc);
+            acc = fmaf(-sS[k * 32 + lane], st, acc);
+        }
+        out_row0[(size_t)m * 32] = acc * inv_d;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_synth(SsbCtx c, SsbSynth y, int i_rel) {
+    extern __shared__ float sm[];
+    float* sC = sm;                               // [d][32]
+    float* sS = sm + (size_t)y.d * 32;            // [d][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x;
+    const long long s_loc = c.dyn[0] + i_rel - c.dyn[3];   // dyn[3]: first step of the resident index block (not baked into graphs)
+    const int* ix = y.idx + s_loc * 4;
+    const int ip = ix[0], ic = ix[1], init = ix[2];
+    float* tabv = ssb_grp(c.vec, c.nv, g, lane) + (size_t)c.tab_row0 * 32;
+    const float* pg = y.path + ((size_t)g * y.T * y.dim) * 32 + lane;
+    float pp[3] = {0.f, 0.f, 0.f}, pc[3] = {0.f, 0.f, 0.f};
+    for (int a = 0; a < y.dim; ++a) {
+        pp[a] = pg[(size_t)(ip * y.dim + a) * 32];
+        pc[a] = pg[(size_t)(ic * y.dim + a) * 32];
+    }
+    if (warp == 0 && y.vel_col >= 0) {
+        const float* vp = y.vel + ((size_t)g * y.T * y.dim) * 32 + lane;
+        for (int a = 0; a < y.dim; ++a) tabv[(size_t)(y.vel_col + a) * 32] = vp[(size_t)(ip * y.dim + a) * 32];
+    }
+    for (int k = warp; k < y.d; k += 8) {
+        sC[k * 32 + lane] = 0.f;
+        sS[k * 32 + lane] = 0.f;
+        if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] = 0.f;
+    }
+    bool any_view = false;
+    const float* lg = y.lm + ((size_t)g * y.n_lm * y.dim) * 32 + lane;
+    for (int l = 0; l < y.n_lm; ++l) {
+        float v[3] = {0.f, 0.f, 0.f}, d2 = 0.f;
+        for (int a = 0; a < y.dim; ++a) {
+            const float q = lg[(size_t)(l * y.dim + a) * 32];
+            const float dv = q - pp[a];
+            d2 = fmaf(dv, dv, d2);
+            v[a] = q - pc[a];
+        }
+        const bool in = sqrtf(d2) <= y.view_rad;
+        any_view = any_view || in;
+        if (!__any_sync(0xffffffffu, in)) continue;
+        for (int k = warp; k < y.d; k += 8) {     // each (k, lane) is owned by one thread: plain read-modify-write
+            float th = 0.f;
+            for (int a = 0; a < y.dim; ++a) th = fmaf(__ldg(y.phases + k * y.dim + a), v[a], th);
+            float sn, cs;
+            sincosf(th, &sn, &cs);
+            if (in) {
+                if (y.lmvec_col >= 0) {
+                    sC[k * 32 + lane] += cs;
+                    sS[k * 32 + lane] += sn;
+                }
+                if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] += __ldg(y.lm_sp + (size_t)l * y.d + k);
+            }
+        }
+    }
+    if (warp == 0 && y.nolm_col >= 0) tabv[(size_t)y.nolm_col * 32] = any_view ? 0.f : y.none_value;
+    __syncthreads();
+    if (y.lmvec_col >= 0) ssb_synth_idft(y, sC, sS, tabv + (size_t)y.lmvec_col * 32, lane, warp);
+    if (y.init_col >= 0) {
+        if (init) {                               // the first init_time seconds only
+            __syncthreads();
+            for (int k = warp; k < y.d; k += 8) {
+                float th = 0.f;
+                for (int a = 0; a < y.dim; ++a) th = fmaf(__ldg(y.phases + k * y.dim + a), pp[a], th);
+                float sn, cs;
+                sincosf(th, &sn, &cs);
+                sC[k * 32 + lane] = cs;
+                sS[k * 32 + lane] = sn;
+            }
+            __syncthreads();
+            ssb_synth_idft(y, sC, sS, tabv + (size_t)y.init_col * 32, lane, warp);
+        } else {
+            for (int m = warp; m < y.d; m += 8) tabv[(size_t)(y.init_col + m) * 32] = 0.f;
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------------

@@ -39,7 +39,7 @@ def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0,
     """``run_pathint.py`` workload; trial i uses path seed ``seed + 1000*i``."""
     space = make_space(2, ssp_dim)
     d = space.ssp_dim
-    paths, ssps, tabs = [], [], []
+    paths, ssps, tabs, full_paths, full_vels = [], [], [], [], []
     scale = None
     for i in range(n_trials):
         path = inputs.random_path(T, dt, limit, seed + 1000 * i, 2)
@@ -50,6 +50,8 @@ def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0,
         tabs.append(inputs.pathint_tables(real, vels * scale, n_steps, dt))
         paths.append(path[:n_steps])
         ssps.append(real[:n_steps])
+        full_paths.append(path)
+        full_vels.append(vels * scale)
     vel0, init0 = tabs[0]["vel"], tabs[0]["init"]
     model = nengo.Network(seed=seed)
     model.config[nengo.Ensemble].neuron_type = _neuron_type(neuron_type)
@@ -62,8 +64,10 @@ def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0,
         nengo.Connection(init, pi.input, synapse=None)
         probe = nengo.Probe(pi.output, synapse=0.05)
     trial_inputs = {vel_in: np.stack([t["vel"] for t in tabs]), init: np.stack([t["init"] for t in tabs])}
+    synth = dict(nodes={"vel": vel_in, "init": init}, ssp_space=space, path=np.stack(full_paths),
+                 vels_scaled=np.stack(full_vels))
     return Scenario(model, probe, trial_inputs, space, np.stack(paths), np.stack(ssps),
-                    dict(pathint=pi, vel_scale=scale), dt)
+                    dict(pathint=pi, vel_scale=scale, input_synthesis=synth), dt)
 
 
 def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neurons=970, circonv_n_neurons=100,
@@ -78,7 +82,7 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
     d = space.ssp_dim
     lm_space = SPSpace(n_landmarks, d, seed=seed)
     n_distinct = n_trials if distinct_tables is None else min(n_trials, distinct_tables)
-    paths, ssps, tabs = [], [], []
+    paths, ssps, tabs, syn_paths, syn_vels, syn_lms = [], [], [], [], [], []
     scale = None
     for i in range(n_distinct):
         s_i = seed + 1000 * i
@@ -101,6 +105,9 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
         tabs.append(tb)
         paths.append(path[:n_steps])
         ssps.append(real[:n_steps])
+        syn_paths.append(path)
+        syn_vels.append(vels * scale)
+        syn_lms.append(obj_locs)
     t0 = tabs[0]
 
     def tab_fn(name):
@@ -146,5 +153,9 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
         trial_inputs[node] = np.tile(stacked, (reps, 1, 1))[:n_trials]
     paths = np.tile(np.stack(paths), (reps, 1, 1))[:n_trials]
     ssps = np.tile(np.stack(ssps), (reps, 1, 1))[:n_trials]
+    tile = lambda lst: np.tile(np.stack(lst), (reps, 1, 1))[:n_trials]
+    synth = dict(nodes={k: table_nodes.get(k) for k in ("vel", "init", "lmvec_ssp", "lm_sp", "nolm")}, ssp_space=space,
+                 path=tile(syn_paths), vels_scaled=tile(syn_vels), landmarks=tile(syn_lms), lm_vectors=lm_space.vectors,
+                 view_rad=view_rad, none_in_view_value=1.0 if view else 10.0)
     return Scenario(model, probe, trial_inputs, space, paths, ssps,
-                    dict(slam=slam, vel_scale=scale, weights_probe=wprobe, lm_space=lm_space), dt)
+                    dict(slam=slam, vel_scale=scale, weights_probe=wprobe, lm_space=lm_space, input_synthesis=synth), dt)

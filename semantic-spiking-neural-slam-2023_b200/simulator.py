@@ -44,7 +44,8 @@ class _SimData:
 
 class Simulator:
     def __init__(self, network, dt=0.001, seed=None, model: BuiltModel | None = None, progress_bar=True,
-                 optimize=True, n_trials=None, trial_inputs=None, trial_seeds=None, device=0, chunk_steps=256):
+                 optimize=True, n_trials=None, trial_inputs=None, trial_seeds=None, device=0, chunk_steps=256,
+                 input_synthesis=None):
         self.network = network
         self.dt = float(dt)
         self.closed = False
@@ -87,7 +88,56 @@ class Simulator:
         self._probe_pending = None   # (buffer index, n_steps) whose rows have not been copied out yet
         self._probe_infos = {info.probe: info for info in self.plan.probes}
         self._n_steps = 0
+        self._synth = None
+        if input_synthesis is not None:
+            self._setup_input_synthesis(input_synthesis)
         self._init_state()
+
+    # ------------------------------------------------------------------ on-device input synthesis
+    def _setup_input_synthesis(self, spec):
+        """Evaluate the drivers' input closures on the device (``ssb_synth_setup``) instead of
+        feeding per-step tables.  ``spec``: ``nodes`` {'vel','init','lmvec_ssp','lm_sp','nolm' -> Node}, ``ssp_space``,
+        per-trial ``path`` / ``vels_scaled`` ``[n_trials, T, dim]``, ``landmarks`` ``[n_trials, n_lm, dim]``,
+        ``lm_vectors`` ``[n_lm, d]``, ``view_rad``, ``none_in_view_value``, ``init_time`` — the arguments of
+        ``get_slam_input_functions2`` (``slam.py:442-497``) / the ``run_pathint.py:134-136`` lambdas."""
+        import ctypes as C
+        space = spec["ssp_space"]
+        path = np.asarray(spec["path"], dtype=np.float64)
+        vels = np.asarray(spec["vels_scaled"], dtype=np.float64)
+        if path.ndim != 3 or path.shape[0] != self.n_trials or vels.shape != path.shape:
+            raise ValueError("input_synthesis: path / vels_scaled must be [n_trials, T, dim]")
+        T, dim = path.shape[1], path.shape[2]
+        d = space.ssp_dim
+        col_of = {node: col0 for node, col0, size in self.plan.tables}
+        nodes = spec["nodes"]
+        missing = [n for n in col_of if n not in nodes.values()]
+        if missing:
+            raise ValueError(f"input_synthesis: table nodes without a synthesised signal: {missing}")
+        cols = [col_of[nodes[k]] if nodes.get(k) is not None else -1 for k in ("vel", "init", "lmvec_ssp", "lm_sp", "nolm")]
+        lms = spec.get("landmarks")
+        n_lm = 0 if lms is None else np.asarray(lms).shape[1]
+
+        def rows(a):                                      # [n_trials, R] -> float32 [R, B]
+            out = np.zeros((a.shape[1], self.B), dtype=np.float32)
+            out[:, :self.n_trials] = a.T
+            return np.ascontiguousarray(out)
+        path_rows, vel_rows = rows(path.reshape(self.n_trials, T * dim)), rows(vels.reshape(self.n_trials, T * dim))
+        lm_rows = rows(np.asarray(lms, dtype=np.float64).reshape(self.n_trials, n_lm * dim)) if n_lm else None
+        lm_sp = np.ascontiguousarray(spec["lm_vectors"], dtype=np.float64) if n_lm else None
+        phases = np.ascontiguousarray(space._scaled_phases(), dtype=np.float64)            # [d, dim] = A / length_scale
+        cfg = np.asarray([dim, d, n_lm, T] + cols, dtype=np.int32)
+        fpar = np.asarray([spec.get("view_rad", 0.0), spec.get("none_in_view_value", 10.0)], dtype=np.float32)
+        ptr = lambda a: cabi._ptr(a) if a is not None else None
+        cabi.check(self._lib.ssb_synth_setup(self._h, ptr(cfg), ptr(fpar), ptr(phases), ptr(lm_sp), ptr(path_rows),
+                                             ptr(vel_rows), ptr(lm_rows)), "ssb_synth_setup")
+        self._synth = dict(T=T, init_time=float(spec.get("init_time", 0.05)))
+
+    def _synth_steps(self, step0, n):
+        from . import inputs
+        t, i_prev, i_cur = inputs.step_indices(n, self.dt, self._synth["T"], step0)
+        idx = np.ascontiguousarray(np.stack([i_prev, i_cur, (t < self._synth["init_time"]).astype(np.int64)], axis=1),
+                                   dtype=np.int32)
+        cabi.check(self._lib.ssb_synth_steps(self._h, cabi._ptr(idx), int(step0), int(n)), "ssb_synth_steps")
 
     # ------------------------------------------------------------------ state
     def _rows(self, per_trial):
@@ -259,10 +309,14 @@ class Simulator:
             for p in periods:  # stop exactly on snapshot steps of weight / encoder probes
                 to_next = p - (self._n_steps % p)
                 n = min(n, to_next)
-            src = self._staged_ptr(self._n_steps, n)
-            if src is None:
-                self._fill_tables(self._n_steps, n)
-                src = self._tab_buf.ptr
+            if self._synth is not None:                    # inputs are evaluated on the device: 12 bytes per step
+                self._synth_steps(self._n_steps, n)
+                src = None
+            else:
+                src = self._staged_ptr(self._n_steps, n)
+                if src is None:
+                    self._fill_tables(self._n_steps, n)
+                    src = self._tab_buf.ptr
             # one pipelined call: tables host -> device, steps, probe rows device -> host (16-step sub-chunks overlap)
             pbuf = self._probe_bufs[self._probe_cur]
             if self._probe_pending is not None and self._probe_pending[0] == self._probe_cur:

@@ -385,3 +385,31 @@ def test_deferred_pes_read_back_in_the_middle_of_a_window():
     assert seen_learning
     assert _rel(sim.data[sc.probe][1], ref.data[sc.probe]) < 1e-4
     sim.close()
+
+
+@pytest.mark.parametrize("kind", ["pathint", "slam", "slamview"])
+def test_on_device_input_synthesis_matches_tables_and_oracle(kind):
+    """the input closures (slam.py:442-497, run_pathint.py:134-136) evaluated by k_synth from the
+    per-trial path / landmarks must drive the network like the host tables the oracle reads (fp32 sincos / IDFT
+    instead of the float64 FFT: inside the rate-mode tolerance)."""
+    n_steps = 130                                      # covers the t < 0.05 s init window and landmarks in view
+    if kind == "pathint":
+        sc = scenarios.make_pathint(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=100, neuron_type="lifrate")
+    else:
+        sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=80, mem_n_neurons=160,
+                                 circonv_n_neurons=24, n_landmarks=12, T=20.0, neuron_type="lifrate", view_rad=0.5,
+                                 view=(kind == "slamview"))
+    S = _Simulator()
+    with S(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as a:
+        a.run_steps(n_steps)
+    with S(sc.network, dt=sc.dt, n_trials=3, input_synthesis=sc.extra["input_synthesis"], model=a.model,
+           chunk_steps=48) as b:                       # 48-step chunks: indices re-uploaded per chunk, graph + direct steps
+        b.run_steps(n_steps)
+    got_tab, got_syn = a.data[sc.probe], b.data[sc.probe]
+    assert np.max(np.abs(got_tab)) > 0.1
+    assert _rel(got_syn, got_tab) < 1e-4
+    for trial in (0, 2):
+        assert _rel(got_syn[trial], _oracle(sc, a, trial, n_steps).data[sc.probe]) < 1e-4
+    if kind != "pathint":                              # some landmark was in view, so the synthesised sums were exercised
+        nolm = [n for n in sc.trial_inputs if n.label == "lm_in_view_input"][0]
+        assert np.any(sc.trial_inputs[nolm][:, :n_steps] == 0.0)
