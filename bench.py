@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--ref-chunk", type=int, default=40, help="timesteps per bench step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-steps", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-synth", action="store_true", help="skip the on-device input-synthesis e2e leg")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -292,6 +293,27 @@ def run_b200(args):
                 "kernel_shares": {k: round(ms / tot_ms, 4) for k, (ms, c) in kt.items() if c}}
     step_gbs = bytes_ts * B * chunk * K / (value_ms * 1e-3) / 1e9
 
+    # ---------------- e2e with on-device input synthesis: the host sends 12 bytes per timestep
+    e2e_synth = None
+    if not args.no_synth:
+        sim2 = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_seeds=trial_seeds, device=local, chunk_steps=chunk,
+                         model=sim.model, input_synthesis=sc.extra["input_synthesis"])
+        for _ in range(W):
+            sim2.run_steps(chunk)
+        sim2.sync()
+        barrier()
+        sim2.mark(2)
+        for _ in range(K):
+            sim2.run_steps(chunk)
+        sim2.mark(3)
+        sim2.sync()
+        barrier()
+        syn_ms = max_over_ranks(sim2.mark_elapsed_ms(2, 3))
+        e2e_synth = {"value": world * B * chunk * K / (syn_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": chunk * 12,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": syn_ms / K,
+                     "inputs": "k_synth evaluates the input closures on the device from per-trial paths / landmarks"}
+        sim2.close()
+
     # ---------------- error statistics: one small collective at the very end
     probe = sim.data[sc.probe]                                  # [B, samples, d] of the e2e + profile phases
     n_have = probe.shape[1]
@@ -315,6 +337,7 @@ def run_b200(args):
                        "parallelism": f"trials sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": tsteps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
+            "e2e_synth": e2e_synth,
             "gpu_launches": int(launches),
             "clocks": {k: clock_info[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "roofline": roofline,

@@ -20,7 +20,10 @@ elif cfg == "slam55gif":    # BASELINE configs[2] sizes (run_slam_map_gif.py def
                              circonv_n_neurons=100, n_landmarks=50, T=200.0, length_scale=0.1, distinct_tables=8)
 else:
     sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=8)
-sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, chunk_steps=steps)
+if os.environ.get("SYNTH"):      # on-device input synthesis instead of tables
+    sim = Simulator(sc.network, dt=sc.dt, n_trials=B, input_synthesis=sc.extra["input_synthesis"], chunk_steps=steps)
+else:
+    sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, chunk_steps=steps)
 bytes_ts = lowering.algorithmic_bytes_per_trial_step(sim.plan.stats)
 sim.run_steps(steps)
 out = []

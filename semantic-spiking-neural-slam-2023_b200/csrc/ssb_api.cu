@@ -852,18 +852,37 @@ int build_lin_program(ssb_sim* s) {
 //   D  static wide ensembles -> static decoders
 // A level's successor waits for C and D only: nothing inside a step reads what k_pes writes (its outputs
 // reach consumers through Lowpass filters, i.e. the final k_lin), so B joins A just before that launch.
-int one_step(ssb_sim* s, int i_rel) {
+// The step's input rows (parity copy of step dyn[0] + i_rel): copied from the resident tables or synthesised.
+void launch_inputs(ssb_sim* s, cudaStream_t st, int i_rel) {
+    const SsbCtx& c = s->ctx;
+    const int G = s->n_groups;
+    if (s->synth_on) {
+        LaunchTimer t(s, K_BEGIN);
+        const int d = s->synth.d;
+        const size_t small_smem = (size_t)(2 * d * 32 + s->synth.n_lm * d + s->synth.n_lm * s->synth.dim * 32) * sizeof(float) +
+                                  (size_t)s->synth.n_lm * 32 + 32;
+        if (d <= 128 && s->synth.n_lm < 255 && small_smem <= 200 * 1024) k_synth<true><<<G, 256, small_smem, st>>>(c, s->synth, i_rel);
+        else k_synth<false><<<G, 256, (size_t)2 * d * 32 * sizeof(float), st>>>(c, s->synth, i_rel);
+    } else if (s->nt > 0) {
+        LaunchTimer t(s, K_BEGIN);
+        dim3 grid(((int)s->nt + 3) / 4, G);
+        k_begin<<<grid, 128, 0, st>>>(c, i_rel);
+    }
+}
+
+// `have_inputs`: the previous step of this launch sequence already produced this step's input rows;
+// `prefetch_next`: produce the next step's input rows on stream C while this step runs (they go to the other parity copy).
+int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next = false) {
     const SsbCtx& c = s->ctx;
     const int G = s->n_groups;
     const bool par = s->parallel && !s->profiling && !s->debug_sync;
     cudaStream_t A = s->stream, B = par ? s->aux[0] : A, C = par ? s->aux[1] : A, D = par ? s->aux[2] : A;
-    if (s->synth_on) {
-        LaunchTimer t(s, K_BEGIN);
-        k_synth<<<G, 256, (size_t)2 * s->synth.d * 32 * sizeof(float), A>>>(c, s->synth, i_rel);
-    } else if (s->nt > 0) {
-        LaunchTimer t(s, K_BEGIN);
-        dim3 grid(((int)s->nt + 3) / 4, G);
-        k_begin<<<grid, 128, 0, A>>>(c, i_rel);
+    const bool any_inputs = s->synth_on || s->nt > 0;
+    if (any_inputs && !(have_inputs && par)) launch_inputs(s, A, i_rel);
+    const bool prefetch = any_inputs && prefetch_next && par;
+    if (prefetch) {                 // everything of the previous step is behind A here, so the other copy is free
+        stream_dep(s, A, C);
+        launch_inputs(s, C, i_rel + 1);
     }
     bool pes_done = s->n_pes == 0, b_used = false;
     for (int lvl = 0; lvl < s->n_levels; ++lvl) {
@@ -947,6 +966,7 @@ int one_step(ssb_sim* s, int i_rel) {
         if (useC) stream_dep(s, C, A);
         if (useD) stream_dep(s, D, A);
     }
+    if (prefetch) stream_dep(s, C, A);
     if (b_used) stream_dep(s, B, A);
     if (!pes_done) launch_pes(s, A, i_rel);
     if (s->n_lin > 0) {
@@ -973,7 +993,7 @@ int build_graph(ssb_sim* s, int n) {
     s->dep_used = 0;
     s->graph_phase = s->pes_h.K > 0 ? (int)(s->steps_done % s->pes_h.K) : 0;
     SSB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-    for (int i = 0; i < n; ++i) one_step(s, i);
+    for (int i = 0; i < n; ++i) one_step(s, i, i > 0, i + 1 < n);
     advance(s, n);
     cudaError_t e = cudaStreamEndCapture(s->stream, &g);
     for (int k = 0; k < K_NKINDS; ++k) s->kind_per_graph[k] = s->kind_launches[k] - saved[k];
@@ -1301,7 +1321,7 @@ int ssb_run_steps(ssb_sim* s, int n_steps) {
         const int rest = n_steps - i;
         s->dep_used = 0;
         for (int r = 0; r < rest; ++r) {
-            if (one_step(s, r)) return -2;
+            if (one_step(s, r, r > 0, r + 1 < rest)) return -2;
         }
         advance(s, rest);
     }
@@ -1369,7 +1389,7 @@ int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* h
         } else {
             s->dep_used = 0;
             for (int r = 0; r < jn; ++r)
-                if (one_step(s, r)) return -2;
+                if (one_step(s, r, r > 0, r + 1 < jn)) return -2;
             advance(s, jn);
         }
         if (host_probes && s->n_probe > 0) {
@@ -1449,7 +1469,8 @@ int ssb_synth_setup(ssb_sim* s, const int* cfg, const float* fparams, const doub
         return fail(-2, "ssb_synth_setup: upload failed");
     SSB_CUDA(cudaMalloc((void**)&s->syn_idx, (size_t)s->chunk_cap * 4 * sizeof(int)));
     SSB_CUDA(cudaMemset(s->syn_idx, 0, (size_t)s->chunk_cap * 4 * sizeof(int)));
-    SSB_CUDA(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SSB_CUDA(cudaFuncSetAttribute(k_synth<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SSB_CUDA(cudaFuncSetAttribute(k_synth<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     y.path = s->syn_path;
     y.vel = s->syn_vel;
     y.lm = s->syn_lm;

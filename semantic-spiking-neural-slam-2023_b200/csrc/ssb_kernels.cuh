@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(128) k_begin(SsbCtx c, int i_rel) {
     if (row >= c.nt) return;
     const long long s_loc = c.dyn[0] + i_rel - c.dyn[1];
     const float* src = c.tab + (((size_t)g * c.tab_cap + (size_t)s_loc) * c.nt + row) * 32 + lane;
-    ssb_grp(c.vec, c.nv, g, lane)[(size_t)(c.tab_row0 + row) * 32] = __ldcs(src);
+    const int par = (int)((c.dyn[0] + i_rel) & 1) ? c.nt : 0;      // the input rows are double-buffered by step parity
+    ssb_grp(c.vec, c.nv, g, lane)[(size_t)(c.tab_row0 + par + row) * 32] = __ldcs(src);
 }
 
 // --------------------------------------------------------------------------------------
@@ -332,30 +333,64 @@ struct SsbSynth {
     float view_rad, none_value;
 };
 
+// inverse DFT of the summed exponentials: out[m] = (1/d) sum_k (C_k cos(2 pi k m / d) - S_k sin(2 pi k m / d)).
+// RECUR: the twiddles of one output m are generated by the rotation recurrence from (cos, sin)(2 pi m / d) (row k = 1 of
+// the tables; error grows like d * 2^-24, used for d <= 128); otherwise they are read from the global tables.
+template <bool RECUR>
 __device__ __forceinline__ void ssb_synth_idft(const SsbSynth& y, const float* sC, const float* sS, float* out_row0, int lane,
                                                int warp) {
     const float inv_d = 1.f / (float)y.d;
     for (int m = warp; m < y.d; m += 8) {
-        float acc = 0.f;
-        for (int k = 0; k < y.d; ++k) {
-            const float ct = __ldg(y.cosT + (size_t)k * y.d + m), st = __ldg(y.sinT + (size_t)k * y.d + m);
-            acc = fmaf(sC[k * 32 + lane], ct, acc);
-            acc = fmaf(-sS[k * 32 + lane], st, acc);
+        float a0 = 0.f, a1 = 0.f;
+        if (RECUR) {
+            const float cm = __ldg(y.cosT + y.d + m), sm_ = __ldg(y.sinT + y.d + m);   // k = 1
+            float ck = 1.f, sk = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < y.d; ++k) {
+                a0 = fmaf(sC[k * 32 + lane], ck, a0);
+                a1 = fmaf(sS[k * 32 + lane], sk, a1);
+                const float cn = fmaf(ck, cm, -sk * sm_);
+                sk = fmaf(sk, cm, ck * sm_);
+                ck = cn;
+            }
+        } else {
+#pragma unroll 8
+            for (int k = 0; k < y.d; ++k) {
+                a0 = fmaf(sC[k * 32 + lane], __ldg(y.cosT + (size_t)k * y.d + m), a0);
+                a1 = fmaf(sS[k * 32 + lane], __ldg(y.sinT + (size_t)k * y.d + m), a1);
+            }
         }
-        out_row0[(size_t)m * 32] = acc * inv_d;
+        out_row0[(size_t)m * 32] = (a0 - a1) * inv_d;
     }
 }
 
+// dynamic smem: 2*d*32 floats (C, S per trial); SMALL (d <= 128) adds n_lm*d (SPs) + n_lm*dim*32 (coordinates) floats
+// + n_lm*32 bytes (per-trial list of the landmarks in view)
+template <bool SMALL>
 __global__ void __launch_bounds__(256) k_synth(SsbCtx c, SsbSynth y, int i_rel) {
     extern __shared__ float sm[];
     float* sC = sm;                               // [d][32]
     float* sS = sm + (size_t)y.d * 32;            // [d][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
+    const float* lg = y.lm + ((size_t)g * y.n_lm * y.dim) * 32 + lane;   // landmark coordinates of this trial: row * 32
+    const float* lsp = y.lm_sp;
+    unsigned char* s_list = nullptr;
+    if (SMALL) {   // stage the landmark SPs and this group's landmark coordinates once per CTA (one load round)
+        float* s_sp = sS + (size_t)y.d * 32;                             // [n_lm][d]
+        float* s_lm = s_sp + (size_t)y.n_lm * y.d;                       // [n_lm*dim][32]
+        s_list = reinterpret_cast<unsigned char*>(s_lm + (size_t)y.n_lm * y.dim * 32);   // [n_lm][32]
+#pragma unroll 16
+        for (int i = threadIdx.x; i < y.n_lm * y.d; i += 256) s_sp[i] = __ldg(y.lm_sp + i);
+#pragma unroll 16
+        for (int r = warp; r < y.n_lm * y.dim; r += 8) s_lm[r * 32 + lane] = lg[(size_t)r * 32];
+        lsp = s_sp;
+        lg = s_lm + lane;
+    }
     const long long s_loc = c.dyn[0] + i_rel - c.dyn[3];   // dyn[3]: first step of the resident index block (not baked into graphs)
     const int* ix = y.idx + s_loc * 4;
     const int ip = ix[0], ic = ix[1], init = ix[2];
-    float* tabv = ssb_grp(c.vec, c.nv, g, lane) + (size_t)c.tab_row0 * 32;
+    float* tabv = ssb_grp(c.vec, c.nv, g, lane) + (size_t)(c.tab_row0 + (((c.dyn[0] + i_rel) & 1) ? c.nt : 0)) * 32;
     const float* pg = y.path + ((size_t)g * y.T * y.dim) * 32 + lane;
     float pp[3] = {0.f, 0.f, 0.f}, pc[3] = {0.f, 0.f, 0.f};
     for (int a = 0; a < y.dim; ++a) {
@@ -366,41 +401,100 @@ __global__ void __launch_bounds__(256) k_synth(SsbCtx c, SsbSynth y, int i_rel) 
         const float* vp = y.vel + ((size_t)g * y.T * y.dim) * 32 + lane;
         for (int a = 0; a < y.dim; ++a) tabv[(size_t)(y.vel_col + a) * 32] = vp[(size_t)(ip * y.dim + a) * 32];
     }
-    for (int k = warp; k < y.d; k += 8) {
-        sC[k * 32 + lane] = 0.f;
-        sS[k * 32 + lane] = 0.f;
-        if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] = 0.f;
-    }
+    if (SMALL) __syncthreads();
     bool any_view = false;
-    const float* lg = y.lm + ((size_t)g * y.n_lm * y.dim) * 32 + lane;
-    for (int l = 0; l < y.n_lm; ++l) {
-        float v[3] = {0.f, 0.f, 0.f}, d2 = 0.f;
-        for (int a = 0; a < y.dim; ++a) {
-            const float q = lg[(size_t)(l * y.dim + a) * 32];
-            const float dv = q - pp[a];
-            d2 = fmaf(dv, dv, d2);
-            v[a] = q - pc[a];
-        }
-        const bool in = sqrtf(d2) <= y.view_rad;
-        any_view = any_view || in;
-        if (!__any_sync(0xffffffffu, in)) continue;
-        for (int k = warp; k < y.d; k += 8) {     // each (k, lane) is owned by one thread: plain read-modify-write
-            float th = 0.f;
-            for (int a = 0; a < y.dim; ++a) th = fmaf(__ldg(y.phases + k * y.dim + a), v[a], th);
-            float sn, cs;
-            sincosf(th, &sn, &cs);
-            if (in) {
-                if (y.lmvec_col >= 0) {
-                    sC[k * 32 + lane] += cs;
-                    sS[k * 32 + lane] += sn;
+    if (SMALL) {
+        // every trial lists its own landmarks in view (warp 0), so phase 1 loops over the longest list (a few entries)
+        // instead of over every landmark some trial of the group can see
+        int cnt = 0;
+        if (warp == 0) {
+            for (int l = 0; l < y.n_lm; ++l) {
+                float d2 = 0.f;
+                for (int a = 0; a < y.dim; ++a) {
+                    const float dv = lg[(size_t)(l * y.dim + a) * 32] - pp[a];
+                    d2 = fmaf(dv, dv, d2);
                 }
-                if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] += __ldg(y.lm_sp + (size_t)l * y.d + k);
+                if (sqrtf(d2) <= y.view_rad) s_list[(cnt++) * 32 + lane] = (unsigned char)l;
+            }
+            if (cnt < y.n_lm) s_list[cnt * 32 + lane] = 255;     // terminator
+            if (y.nolm_col >= 0) tabv[(size_t)y.nolm_col * 32] = cnt > 0 ? 0.f : y.none_value;
+        }
+        __syncthreads();
+        // phase 1: this thread owns the frequencies k = warp + 8 j of its trial
+        constexpr int KS = 16;
+        float rC[KS], rS[KS], rL[KS], ph[KS][3];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            rC[j] = rS[j] = rL[j] = 0.f;
+            const int k = warp + 8 * j;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) ph[j][a] = (k < y.d && a < y.dim) ? __ldg(y.phases + k * y.dim + a) : 0.f;
+        }
+        bool alive = true;
+        for (int q = 0; q < y.n_lm; ++q) {
+            const int l = s_list[q * 32 + lane];
+            alive = alive && l != 255;                           // entries after a trial's terminator are not initialised
+            const bool on = alive;
+            if (!__any_sync(0xffffffffu, on)) break;             // nobody has a q-th entry
+            const int ls = on ? l : 0;
+            float v[3] = {0.f, 0.f, 0.f};
+            for (int a = 0; a < y.dim; ++a) v[a] = lg[(size_t)(ls * y.dim + a) * 32] - pc[a];
+            const float w = on ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                const int k = warp + 8 * j;
+                if (k < y.d) {
+                    const float th = fmaf(ph[j][0], v[0], fmaf(ph[j][1], v[1], ph[j][2] * v[2]));
+                    float sn, cs;
+                    sincosf(th, &sn, &cs);
+                    rC[j] = fmaf(w, cs, rC[j]);
+                    rS[j] = fmaf(w, sn, rS[j]);
+                    if (y.lmsp_col >= 0) rL[j] = fmaf(w, lsp[(size_t)ls * y.d + k], rL[j]);
+                }
             }
         }
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            const int k = warp + 8 * j;
+            if (k < y.d) {
+                sC[k * 32 + lane] = rC[j];
+                sS[k * 32 + lane] = rS[j];
+                if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] = rL[j];
+            }
+        }
+    } else {
+        for (int k = warp; k < y.d; k += 8) {
+            sC[k * 32 + lane] = 0.f;
+            sS[k * 32 + lane] = 0.f;
+            if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] = 0.f;
+        }
+        for (int l = 0; l < y.n_lm; ++l) {
+            float v[3] = {0.f, 0.f, 0.f}, d2 = 0.f;
+            for (int a = 0; a < y.dim; ++a) {
+                const float q = lg[(size_t)(l * y.dim + a) * 32];
+                const float dv = q - pp[a];
+                d2 = fmaf(dv, dv, d2);
+                v[a] = q - pc[a];
+            }
+            const bool in = sqrtf(d2) <= y.view_rad;
+            any_view = any_view || in;
+            if (!__any_sync(0xffffffffu, in)) continue;
+            for (int k = warp; k < y.d; k += 8) {     // each (k, lane) is owned by one thread: plain read-modify-write
+                float th = 0.f;
+                for (int a = 0; a < y.dim; ++a) th = fmaf(__ldg(y.phases + k * y.dim + a), v[a], th);
+                float sn, cs;
+                sincosf(th, &sn, &cs);
+                if (in) {
+                    sC[k * 32 + lane] += cs;
+                    sS[k * 32 + lane] += sn;
+                    if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] += __ldg(y.lm_sp + (size_t)l * y.d + k);
+                }
+            }
+        }
+        if (warp == 0 && y.nolm_col >= 0) tabv[(size_t)y.nolm_col * 32] = any_view ? 0.f : y.none_value;
     }
-    if (warp == 0 && y.nolm_col >= 0) tabv[(size_t)y.nolm_col * 32] = any_view ? 0.f : y.none_value;
     __syncthreads();
-    if (y.lmvec_col >= 0) ssb_synth_idft(y, sC, sS, tabv + (size_t)y.lmvec_col * 32, lane, warp);
+    if (y.lmvec_col >= 0) ssb_synth_idft<SMALL>(y, sC, sS, tabv + (size_t)y.lmvec_col * 32, lane, warp);
     if (y.init_col >= 0) {
         if (init) {                               // the first init_time seconds only
             __syncthreads();
@@ -413,7 +507,7 @@ __global__ void __launch_bounds__(256) k_synth(SsbCtx c, SsbSynth y, int i_rel) 
                 sS[k * 32 + lane] = sn;
             }
             __syncthreads();
-            ssb_synth_idft(y, sC, sS, tabv + (size_t)y.init_col * 32, lane, warp);
+            ssb_synth_idft<SMALL>(y, sC, sS, tabv + (size_t)y.init_col * 32, lane, warp);
         } else {
             for (int m = warp; m < y.d; m += 8) tabv[(size_t)(y.init_col + m) * 32] = 0.f;
         }

@@ -405,7 +405,8 @@ class _Lowerer:
         dev_col = np.zeros(self.ncol, dtype=np.int64)
         next_filt, next_tab = 1, 0
         tab_row0 = 1 + 2 * NF
-        next_scratch = tab_row0 + NT
+        next_scratch = tab_row0 + 2 * NT      # two copies of the input rows (step parity), so step t+1's inputs can be
+                                             # written while step t still reads its own
         for c in range(1, self.ncol):
             k = self.col_kind[c]
             if k == "filt":
@@ -697,8 +698,8 @@ class _Lowerer:
             stages.append(entry + list(level_rows[lvl]))
         plan.arrays.update({
             "csr_ptr": np.asarray(csr_ptr, dtype=np.int32),
-            "csr_ent0": self._entries(csr_idx, csr_val, 0, NF),
-            "csr_ent1": self._entries(csr_idx, csr_val, NF, NF),
+            "csr_ent0": self._entries(csr_idx, csr_val, 0, NF, tab_row0, NT),
+            "csr_ent1": self._entries(csr_idx, csr_val, NF, NF, tab_row0, NT),
             # 8 floats of slack: bulk copies of bias / current weights round their length up to 16 bytes
             "weights": np.concatenate(W + [np.zeros(8, dtype=np.float32)]),
             "ens_small": arr(cat["small"], 9),
@@ -738,10 +739,13 @@ class _Lowerer:
         return plan
 
     @staticmethod
-    def _entries(idx, val, par, nf):
+    def _entries(idx, val, par, nf, tab_row0=0, nt=0):
         """CSR entries as (vec row, float32 coefficient bits) pairs with the filter columns resolved to
-        the half that is read on steps of this parity (``par`` = 0 for even steps, ``nf`` for odd ones)."""
+        the half that is read on steps of this parity (``par`` = 0 for even steps, ``nf`` for odd ones);
+        input-table rows likewise point at the copy written for steps of this parity."""
         rows = np.asarray(idx, dtype=np.int64)
+        if par and nt:
+            rows = np.where((rows >= tab_row0) & (rows < tab_row0 + nt), rows + nt, rows)
         rows = np.where((rows >= 1) & (rows <= nf), rows + par, rows)
         ent = np.empty((len(rows), 2), dtype=np.int32)
         ent[:, 0] = rows

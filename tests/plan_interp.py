@@ -95,7 +95,8 @@ class PlanInterpreter:
         s = self.step
         par_old, par_new = (self.nf, 0) if s & 1 else (0, self.nf)
         if self.nt:
-            self.vec[self.tab_row0:self.tab_row0 + self.nt] = self.tables[s]      # k_begin
+            r0 = self.tab_row0 + (self.nt if s & 1 else 0)                       # k_begin: the copy of this step's parity
+            self.vec[r0:r0 + self.nt] = self.tables[s]
         for st in a["stages"]:
             for src, kind, dst in a["lin_rows"][st[10]:st[10] + st[11]]:     # materialise this level's sink rows
                 assert kind in (3, 4)
