@@ -255,7 +255,7 @@ class SLAMNetwork(Network):
                  clean_up_method="grid", gc_n_neurons=0, encoders=None, voja=True, seed=0,
                  landmark_sps=None, intercept=None, grid_points_per_dim=100):
         super().__init__()
-        if clean_up_method != "grid" or gc_n_neurons > 0:
+        if clean_up_method != "grid":
             raise NotImplementedError("only the grid clean-up node is on the hot path (SURVEY.md §8f-4)")
         d, n_dom = ssp_space.ssp_dim, ssp_space.domain_dim
         rng = np.random.RandomState(seed=seed)
@@ -294,9 +294,18 @@ class SLAMNetwork(Network):
             self.landmark_ssp_ens = CircularConvolution(circonv_n_neurons, dimensions=d, label="landmark_circonv")
             Connection(self.ovc_ens, self.landmark_ssp_ens.input_b, synapse=None)
 
-            self.gridcells = Node(self.clean_up_fun, size_in=d)
-            Connection(self.pathintegrator.output, self.gridcells, synapse=tau)
-            Connection(self.gridcells, self.landmark_ssp_ens.input_a, synapse=None)
+            if gc_n_neurons <= 0:
+                self.gridcells = Node(self.clean_up_fun, size_in=d)
+                Connection(self.pathintegrator.output, self.gridcells, synapse=tau)
+                Connection(self.gridcells, self.landmark_ssp_ens.input_a, synapse=None)
+            else:   # slam.py:274-281: the cleaned-up SSP is represented by a grid-cell ensemble
+                gc_encoders = ssp_space.sample_grid_encoders(gc_n_neurons)
+                self.cleanup = Node(self.clean_up_fun, size_in=d)
+                self.gridcells = Ensemble(gc_n_neurons, d, encoders=gc_encoders,
+                                          intercepts=nengo.dists.CosineSimilarity(d + 2))
+                Connection(self.pathintegrator.output, self.cleanup, synapse=tau)
+                Connection(self.cleanup, self.gridcells, synapse=None)
+                Connection(self.gridcells, self.landmark_ssp_ens.input_a, synapse=tau)
 
             self.assomemory = AssociativeMemory(mem_n_neurons, d, d, intercept,
                                                 voja_learning_rate=voja_learning_rate,

@@ -73,7 +73,8 @@ def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0,
 def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neurons=970, circonv_n_neurons=100,
               n_landmarks=50, view_rad=0.2, T=200.0, limit=0.1, seed=0, dt=0.001, length_scale=0.2,
               shift_rate=0.2, update_thres=0.2, neuron_type="lif", weights_probe=False, view=False,
-              distinct_tables=None, domain_dim=2, grid_points_per_dim=100):
+              distinct_tables=None, domain_dim=2, grid_points_per_dim=100, gc_n_neurons=0, approx_vel=False,
+              vel_n_neurons=500):
     """``run_slam.py`` (or ``run_slamview.py`` when ``view``) workload, batched over trials.
 
     ``distinct_tables``: synthesise only that many distinct trials' tables and tile them
@@ -135,12 +136,17 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
                                         circonv_n_neurons, tau_pi=0.05, update_thres=update_thres,
                                         vel_scaling_factor=scale, shift_rate=shift_rate, voja_learning_rate=1e-4,
                                         pes_learning_rate=5e-3, intercept=0.1, seed=seed,
-                                        grid_points_per_dim=grid_points_per_dim)
+                                        grid_points_per_dim=grid_points_per_dim, gc_n_neurons=gc_n_neurons)
             nengo.Connection(lm_vec, slam.landmark_vec_ssp, synapse=None)
             nengo.Connection(lm_id, slam.landmark_id_input, synapse=None)
             table_nodes = {"vel": vel_in, "init": init, "lm_sp": lm_id, "nolm": is_lm, "lmvec_ssp": lm_vec}
         nengo.Connection(is_lm, slam.no_landmark_in_view, synapse=None)
-        nengo.Connection(vel_in, slam.velocity_input, synapse=None)
+        if approx_vel:   # run_slam.py:154-160: the velocity passes through a spiking ensemble (vel_syn = 0.01)
+            vel_ens = nengo.Ensemble(vel_n_neurons, domain_dim)
+            nengo.Connection(vel_in, vel_ens, synapse=None)
+            nengo.Connection(vel_ens, slam.velocity_input, synapse=0.01)
+        else:
+            nengo.Connection(vel_in, slam.velocity_input, synapse=None)
         nengo.Connection(init, slam.pathintegrator.input, synapse=None)
         probe = nengo.Probe(slam.pathintegrator.output, synapse=0.05)
         wprobe = None

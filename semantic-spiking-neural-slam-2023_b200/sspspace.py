@@ -171,11 +171,38 @@ class SSPSpace:
             counts = [int(samples_per_dim)] * self.domain_dim
         elif method == "length-scale":
             counts = [2 * int(np.ceil((hi - lo) / self.length_scale[i, 0])) for i, (lo, hi) in enumerate(bounds)]
+        elif method == "sobol":   # sspspace.py:469-474: scrambled Sobol points from the space's own generator
+            from scipy.stats import qmc
+            sampler = qmc.Sobol(d=self.domain_dim, seed=self.rng)
+            u = sampler.random(int(np.prod(samples_per_dim)))
+            return qmc.scale(u, np.asarray(bounds)[:, 0], np.asarray(bounds)[:, 1])
         else:
             raise NotImplementedError(f"sampling method {method!r} is outside the hot path")
         axes = [np.linspace(bounds[i, 0], bounds[i, 1], counts[i]) for i in range(self.domain_dim)]
         mesh = np.meshgrid(*axes)  # 'xy' indexing, like the reference (:460-464)
         return np.stack([m.reshape(-1) for m in mesh], axis=1)
+
+    def sample_grid_encoders(self, n_neurons, method="sobol"):
+        """Grid-cell encoders (``sspspace.py:733-762``): each neuron is the SSP of a sample point restricted to ONE
+        simplex sub-lattice of the phase matrix (its ``n + 1`` frequencies, conjugate-completed, DC = 1), normalised."""
+        d, n, A = self.ssp_dim, self.domain_dim, self.phase_matrix
+        k = (d - 1) // 2
+        N = ((d - 2) // 2) // (n + 1) if d % 2 == 0 else ((d - 1) // 2) // (n + 1)
+        num_pts = int(np.ceil(n_neurons ** (1 / n))) if method == "grid" else n_neurons
+        pts = self.get_sample_points(num_pts, method=method)[:n_neurons, :]
+        per = int(np.floor(n_neurons / N))
+        sorts = np.concatenate([np.repeat(np.arange(0, N), per), self.rng.integers(0, N, size=n_neurons - N * per)])
+        enc = np.zeros((n_neurons, d))
+        for i in range(n_neurons):
+            lo, hi = 1 + sorts[i] * (n + 1), n + 2 + sorts[i] * (n + 1)
+            res = np.zeros(d, dtype=complex)
+            res[lo:hi] = np.exp(1.j * A[lo:hi] @ pts[i, :])
+            res[(k + 1):] = np.conjugate(np.flip(res[1:(k + 1)]))
+            res[0] = 1
+            if d % 2 == 0:
+                res[d // 2] = 1
+            enc[i, :] = np.fft.ifft(res).real
+        return enc / np.linalg.norm(enc, axis=-1, keepdims=True)
 
     def get_sample_ssps(self, num_points, **kwargs):
         return self.encode_host(self.get_sample_points(num_points, **kwargs))

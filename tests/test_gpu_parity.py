@@ -413,3 +413,17 @@ def test_on_device_input_synthesis_matches_tables_and_oracle(kind):
     if kind != "pathint":                              # some landmark was in view, so the synthesised sums were exercised
         nolm = [n for n in sc.trial_inputs if n.label == "lm_in_view_input"][0]
         assert np.any(sc.trial_inputs[nolm][:, :n_steps] == 0.0)
+
+
+def test_grid_cell_ensemble_and_approx_velocity_variants_match_oracle():
+    """gc_n_neurons > 0 (slam.py:274-281) and --approx-vel (run_slam.py:154-160) on the same kernels."""
+    n_steps = 120
+    sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=80, mem_n_neurons=160,
+                             circonv_n_neurons=24, n_landmarks=12, T=20.0, neuron_type="lifrate", view_rad=0.5,
+                             gc_n_neurons=200, approx_vel=True, vel_n_neurons=100)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        assert sim.plan.stats["n_big"] == 5
+        sim.run_steps(n_steps)
+    got = sim.data[sc.probe]
+    for trial in (0, 2):
+        assert _rel(got[trial], _oracle(sc, sim, trial, n_steps).data[sc.probe]) < 1e-4

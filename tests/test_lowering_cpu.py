@@ -106,3 +106,16 @@ def test_slam_3d_plan_matches_oracle():
     assert int(plan.arrays["cleanup"][0][0]) == 12 ** 3
     assert {int(r[1]) for r in plan.arrays["ens_small"]} == {1, 3}    # VCOs stay (Re, Im, frequency) in any domain
     assert sc.trial_inputs[[n for n in sc.trial_inputs if n.label == "vel_input"][0]].shape[2] == 3
+
+
+def test_slam_grid_cell_ensemble_and_approx_velocity_plan_matches_oracle():
+    """SURVEY.md §8f-4 topologies on the same kernels: clean-up -> grid-cell ensemble (wide, custom encoders,
+    CosineSimilarity intercepts) -> circular convolution, and the velocity routed through a spiking ensemble."""
+    sc = scenarios.make_slam(n_trials=1, n_steps=60, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=64, circonv_n_neurons=16,
+                             n_landmarks=6, T=20.0, neuron_type="lifrate", view_rad=0.6, gc_n_neurons=40, approx_vel=True,
+                             vel_n_neurons=50)
+    slam = sc.extra["slam"]
+    assert slam.gridcells.n_neurons == 40
+    plan, *_ = _compare(sc, 60)
+    assert plan.stats["n_big"] == 5                      # OVC, memory, recall, error + the grid-cell ensemble
+    assert plan.stats["n_levels"] >= 2                   # clean-up node -> grid cells in the same step

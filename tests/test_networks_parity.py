@@ -86,6 +86,28 @@ def test_slam_network_matches_reference():
     assert (gate.d, gate.shift_rate, gate.update_thres) == (space.ssp_dim, 0.2, 0.2)
 
 
+def test_slam_network_with_grid_cell_ensemble_matches_reference():
+    """gc_n_neurons > 0 (slam.py:274-281, sample_grid_encoders sspspace.py:733-762, CosineSimilarity)."""
+    ref = _ref()
+    lm_seed = 2
+    nets = []
+    for mod, space_cls, sp_cls in ((networks, HexagonalSSPSpace, SPSpace), (ref.networks, ref.HexagonalSSPSpace, ref.SPSpace)):
+        kw = dict(backend="host") if space_cls is HexagonalSSPSpace else {}
+        sp = space_cls(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2, rng=np.random.default_rng(5), **kw)
+        l = sp_cls(6, sp.ssp_dim, seed=lm_seed)
+        np.random.seed(9)
+        with nengo.Network(seed=4) as net:
+            slam = mod.SLAMNetwork(sp, l, 0.2, 6, 30, 64, 16, tau_pi=0.05, update_thres=0.2, vel_scaling_factor=0.7,
+                                   shift_rate=0.2, voja_learning_rate=1e-4, pes_learning_rate=5e-3, intercept=0.1,
+                                   gc_n_neurons=48)
+            nengo.Probe(slam.pathintegrator.output, synapse=0.05)
+        nets.append((net, slam))
+    (na, sa), (nb, sb) = nets
+    _assert_same_model(na, nb)
+    assert sa.gridcells.n_neurons == 48 and sa.gridcells.dimensions == sa.sample_ssps.shape[1]
+    np.testing.assert_allclose(np.asarray(sa.gridcells.encoders), np.asarray(sb.gridcells.encoders), atol=1e-14)
+
+
 def test_slamview_network_matches_reference():
     ref = _ref()
     space = HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.3, backend="host")
