@@ -169,6 +169,67 @@ __device__ __forceinline__ float ssb_lif_packed(const SsbNeuron& n, float J, flo
     return spiked ? n.amp_dt : 0.f;
 }
 
+// Two neurons per lane with sm_100's packed fp32 instructions (FFMA2 / FADD2 / FMUL2: one issue slot for two
+// operations).  k_ens_small is issue-bound, and two thirds of the LIF update are fma / add / mul chains.
+__device__ __forceinline__ float2 ssb_fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return r;
+}
+__device__ __forceinline__ float2 ssb_mul2(float2 a, float2 b) {
+    float2 r;
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return r;
+}
+__device__ __forceinline__ float2 ssb_add2(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.ftz.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return r;
+}
+__device__ __forceinline__ float2 ssb_splat(float x) { return make_float2(x, x); }
+
+// ssb_lif_packed<true> for two neurons at once (same arithmetic, element-wise): s0/s1 states, J0/J1 currents.
+__device__ __forceinline__ float2 ssb_lif_pair(const SsbNeuron& n, float2 J, float2& s) {
+    const float2 m = make_float2(fminf(s.x, 0.f), fminf(s.y, 0.f));
+    float2 v = make_float2(fmaxf(s.x, 0.f), fmaxf(s.y, 0.f));
+    float2 dn = ssb_fma2(m, ssb_splat(n.inv_dt), ssb_splat(2.f));
+    dn = make_float2(__saturatef(dn.x), __saturatef(dn.y));
+    const float2 x = ssb_mul2(dn, ssb_splat(n.neg_dt_over_tau));
+    float2 p = ssb_fma2(ssb_splat(1.f / 120.f), x, ssb_splat(1.f / 24.f));     // expm1(x), degree-5 Taylor
+    p = ssb_fma2(p, x, ssb_splat(1.f / 6.f));
+    p = ssb_fma2(p, x, ssb_splat(0.5f));
+    p = ssb_fma2(p, x, ssb_splat(1.f));
+    const float2 em1 = ssb_mul2(p, x);
+    const float2 vmj = ssb_fma2(J, ssb_splat(-1.f), v);                        // v - J
+    v = ssb_fma2(vmj, em1, v);
+    const bool sp0 = v.x > 1.f, sp1 = v.y > 1.f;
+    const float2 vm1 = ssb_add2(v, ssb_splat(-1.f)), jm1 = ssb_add2(J, ssb_splat(-1.f));
+    float2 rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc.x) : "f"(jm1.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc.y) : "f"(jm1.y));
+    const float2 z = ssb_mul2(vm1, rc);
+    float2 q = ssb_fma2(ssb_splat(-1.f / 6.f), z, ssb_splat(-0.2f));            // log1p(-z), 6 terms
+    q = ssb_fma2(q, z, ssb_splat(-0.25f));
+    q = ssb_fma2(q, z, ssb_splat(-1.f / 3.f));
+    q = ssb_fma2(q, z, ssb_splat(-0.5f));
+    q = ssb_fma2(q, z, ssb_splat(-1.f));
+    const float2 lp = ssb_mul2(q, z);
+    const float2 r_new = ssb_fma2(ssb_splat(n.tau_rc), lp, ssb_splat(n.c0));
+    const float2 mdt = ssb_add2(m, ssb_splat(n.dt));
+    const float keep0 = (dn.x > 0.f) ? fmaxf(v.x, 0.f) : mdt.x;
+    const float keep1 = (dn.y > 0.f) ? fmaxf(v.y, 0.f) : mdt.y;
+    s.x = sp0 ? -r_new.x : keep0;
+    s.y = sp1 ? -r_new.y : keep1;
+    return make_float2(sp0 ? n.amp_dt : 0.f, sp1 ? n.amp_dt : 0.f);
+}
+
 __device__ __forceinline__ float ssb_rate(const SsbNeuron& n, float J) {
     if (n.type == 1) {
         const float j = J - 1.f;
@@ -563,8 +624,36 @@ __device__ __forceinline__ void ssb_small_range(const SsbCtx& c, const int* __re
         phases ^= 1u << b;
         float* ss = sm.st[warp][b] + lane;
         const float4* ww = reinterpret_cast<const float4*>(sm.w[warp][b]);
+        int k = 0;
+        if (MODE == 0) {       // fast-LIF ensembles: two neurons per iteration on the packed fp32 pipe
+#pragma unroll 2
+            for (; k + 2 <= cnt; k += 2) {
+                float wa[4 * S4], wb[4 * S4];
+#pragma unroll
+                for (int q = 0; q < S4; ++q) {
+                    const float4 t = ww[k * S4 + q], u = ww[(k + 1) * S4 + q];
+                    wa[4 * q + 0] = t.x;
+                    wa[4 * q + 1] = t.y;
+                    wa[4 * q + 2] = t.z;
+                    wa[4 * q + 3] = t.w;
+                    wb[4 * q + 0] = u.x;
+                    wb[4 * q + 1] = u.y;
+                    wb[4 * q + 2] = u.z;
+                    wb[4 * q + 3] = u.w;
+                }
+                float2 J = make_float2(wa[0], wb[0]);
+#pragma unroll
+                for (int kk = 0; kk < DIMS; ++kk) J = ssb_fma2(make_float2(wa[1 + kk], wb[1 + kk]), ssb_splat(x[kk]), J);
+                float2 sv = make_float2(ss[k * 32], ss[(k + 1) * 32]);
+                const float2 out = ssb_lif_pair(nt, J, sv);
+                ss[k * 32] = sv.x;
+                ss[(k + 1) * 32] = sv.y;
+#pragma unroll
+                for (int j = 0; j < NCOL; ++j) acc[j] = fmaf(wb[1 + DIMS + j], out.y, fmaf(wa[1 + DIMS + j], out.x, acc[j]));
+            }
+        }
 #pragma unroll 4
-        for (int k = 0; k < cnt; ++k) {
+        for (; k < cnt; ++k) {
             float wl[4 * S4];
 #pragma unroll
             for (int q = 0; q < S4; ++q) {
@@ -644,7 +733,7 @@ __device__ __forceinline__ void ssb_small_dispatch(const SsbCtx& c, const int* _
 }
 
 // desc: n, dims, nout, state0, w_off, in_vec, out_vec, ntype, stride
-__global__ void __launch_bounds__(128) k_ens_small(SsbCtx c, const int* __restrict__ desc, int n_items, int n_split) {
+__global__ void __launch_bounds__(128, 6) k_ens_small(SsbCtx c, const int* __restrict__ desc, int n_items, int n_split) {
     __shared__ SsbSmallSmem sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
