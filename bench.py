@@ -288,6 +288,9 @@ def run_b200(args):
                 # the SURVEY 8d model charges 16 B per neuron state and a write of every learned weight; the kernels
                 # keep a one-word state and write back only what changed, so the DRAM bytes ncu measured are lower:
                 "achieved_traffic": None if traffic is None else traffic / (dom_ms / max(dom_cnt, 1) * 1e-3) / 1e9,
+                "note": "achieved = SURVEY 8d algorithmic bytes / CUDA-event time; the model charges 16 B per neuron state "
+                        "(the kernels keep a one-word state: 8 B) and a write of every learned weight per step (only changed "
+                        "tiles are written), so it can exceed the copy peak; achieved_traffic = ncu DRAM bytes / the same time",
                 "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_us": dom_ms / max(dom_cnt, 1) * 1e3,
                 "share_of_step": dom_ms / tot_ms,
                 "kernel_shares": {k: round(ms / tot_ms, 4) for k, (ms, c) in kt.items() if c}}
