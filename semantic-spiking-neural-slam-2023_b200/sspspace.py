@@ -183,26 +183,29 @@ class SSPSpace:
         return np.stack([m.reshape(-1) for m in mesh], axis=1)
 
     def sample_grid_encoders(self, n_neurons, method="sobol"):
-        """Grid-cell encoders (``sspspace.py:733-762``): each neuron is the SSP of a sample point restricted to ONE
-        simplex sub-lattice of the phase matrix (its ``n + 1`` frequencies, conjugate-completed, DC = 1), normalised."""
-        d, n, A = self.ssp_dim, self.domain_dim, self.phase_matrix
-        k = (d - 1) // 2
-        N = ((d - 2) // 2) // (n + 1) if d % 2 == 0 else ((d - 1) // 2) // (n + 1)
-        num_pts = int(np.ceil(n_neurons ** (1 / n))) if method == "grid" else n_neurons
-        pts = self.get_sample_points(num_pts, method=method)[:n_neurons, :]
-        per = int(np.floor(n_neurons / N))
-        sorts = np.concatenate([np.repeat(np.arange(0, N), per), self.rng.integers(0, N, size=n_neurons - N * per)])
-        enc = np.zeros((n_neurons, d))
-        for i in range(n_neurons):
-            lo, hi = 1 + sorts[i] * (n + 1), n + 2 + sorts[i] * (n + 1)
-            res = np.zeros(d, dtype=complex)
-            res[lo:hi] = np.exp(1.j * A[lo:hi] @ pts[i, :])
-            res[(k + 1):] = np.conjugate(np.flip(res[1:(k + 1)]))
-            res[0] = 1
-            if d % 2 == 0:
-                res[d // 2] = 1
-            enc[i, :] = np.fft.ifft(res).real
-        return enc / np.linalg.norm(enc, axis=-1, keepdims=True)
+        """Grid-cell encoders (behaviour of ``sspspace.py:733-762``): neuron ``i`` is the SSP of sample point ``p_i`` with
+        every frequency switched off except ONE simplex sub-lattice ``g_i`` of the phase matrix (its ``n + 1`` rows) and
+        the DC (and Nyquist) term; rows are normalised.  Sub-lattices are dealt out in equal blocks, the remainder at
+        random from the space's generator (drawn after the sample points, as the reference does)."""
+        d, n = self.ssp_dim, self.domain_dim
+        half = (d - 1) // 2
+        n_lattices = ((d - 2) // 2 if d % 2 == 0 else half) // (n + 1)
+        n_pts = int(np.ceil(n_neurons ** (1.0 / n))) if method == "grid" else n_neurons
+        points = self.get_sample_points(n_pts, method=method)[:n_neurons]
+        block = n_neurons // n_lattices
+        lattice = np.concatenate([np.repeat(np.arange(n_lattices), block),
+                                  self.rng.integers(0, n_lattices, size=n_neurons - n_lattices * block)])
+        # spectrum[i, k]: exp(i A_k . p_i) on the rows of lattice g_i, conjugate-mirrored, 1 at DC / Nyquist
+        rows = 1 + lattice[:, None] * (n + 1) + np.arange(n + 1)[None, :]            # [n_neurons, n + 1]
+        phase = np.einsum("ijk,ik->ij", self.phase_matrix[rows], points)
+        spectrum = np.zeros((n_neurons, d), dtype=complex)
+        np.put_along_axis(spectrum, rows, np.exp(1j * phase), axis=1)
+        spectrum[:, half + 1:] = np.conj(spectrum[:, half:0:-1]) if d % 2 else np.conj(spectrum[:, 1:half + 1][:, ::-1])
+        spectrum[:, 0] = 1.0
+        if d % 2 == 0:
+            spectrum[:, d // 2] = 1.0
+        enc = np.fft.ifft(spectrum, axis=1).real
+        return enc / np.linalg.norm(enc, axis=1, keepdims=True)
 
     def get_sample_ssps(self, num_points, **kwargs):
         return self.encode_host(self.get_sample_points(num_points, **kwargs))
