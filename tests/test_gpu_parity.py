@@ -182,7 +182,8 @@ def test_generic_width_network_matches_oracle():
 
 
 @pytest.mark.parametrize("env", [{"SSB_SCAN": "ffma"}, {"SSB_DECODE": "ffma"}, {"SSB_ENCODE": "tc"},
-                                 {"SSB_SCAN": "ffma", "SSB_DECODE": "ffma", "SSB_SERIAL": "1"}])
+                                 {"SSB_SCAN": "ffma", "SSB_DECODE": "ffma", "SSB_SERIAL": "1"},
+                                 {"SSB_PES_DEFER": "0"}, {"SSB_PES_DEFER": "4"}])
 def test_alternate_kernel_paths_match_oracle(env, monkeypatch):
     """Every shared-weight GEMM has an FFMA and a tcgen05 (3xTF32) kernel; whichever is selected, the
     trajectory stays within the rate-mode tolerance and the clean-up index is the float64 argmax."""
