@@ -12,7 +12,10 @@ One bench *step* = ``--chunk`` simulator timesteps of the whole batch (one ``run
   timestep already resident in HBM, probes written to the device probe buffer.
 * ``e2e``    — the same work through ``Simulator.run_steps`` with HOST buffers: per step the
   tables are copied from page-locked host memory and the probe block is read back to the host.
-* ``roofline`` — dominant kernel kind: algorithmic bytes (SURVEY.md §8d model) / CUDA-event time.
+* ``e2e_synth`` — the same, with the input closures evaluated on the device (``Simulator(input_synthesis=...)``,
+  SURVEY.md §8f-2): the host sends 12 bytes per timestep instead of table rows.
+* ``roofline`` — dominant kernel kind: algorithmic bytes (SURVEY.md §8d model) / CUDA-event time; ``traffic`` /
+  ``achieved_traffic`` are the DRAM bytes ncu measured for that kernel (``profiles/ncu_traffic.json``).
 * ``cpu_baseline`` — the operator-level NumPy port of the nengo reference simulator
   (``oracle/nengo_ref_sim.py``) on the same built network, one trial, one host core.
 

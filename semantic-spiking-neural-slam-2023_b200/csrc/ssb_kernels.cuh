@@ -615,7 +615,7 @@ __device__ __forceinline__ void ssb_small_range(const SsbCtx& c, const int* __re
     };
     if (n_chunks > 0) issue(0);
     if (n_chunks > 1) issue(1);
-    float x[DIMS];                       // the materialised input vector (written by k_rows of this level)
+    float x[DIMS];                       // the materialised input vector (written by k_lin for this level)
 #pragma unroll
     for (int k = 0; k < DIMS; ++k) x[k] = vg[(size_t)(in_vec + k) * 32];
     for (int ck = 0; ck < n_chunks; ++ck) {
@@ -1034,7 +1034,7 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
 
 // Voja-learned ensemble (associative-memory keys): the scaled encoders are per trial, the `dims` rows
 // of one neuron are `dims` consecutive 128-byte lines.  Each warp streams its neurons' encoder tiles
-// through a double-buffered shared-memory stage with TMA bulk copies; lanes that spiked update their
+// through a ring of shared-memory tiles (three in flight) with TMA bulk copies; lanes that spiked update their
 // column in place and the tile is written back only if some lane spiked (post_synapse=None => the
 // delta is row-sparse).  SimVoja: delta = alpha*L*(scale*outer(post, x) - post[:,None]*E), visible
 // to the next step.
@@ -1614,7 +1614,7 @@ __global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ d
     for (int j = 0; j < 8; ++j) {
         acc[j] = 0.f;
         float e = 0.f;
-        if (j < jn) e = vg[(size_t)(err_vec + j0 + j) * 32];   // error of the previous step, materialised by k_rows
+        if (j < jn) e = vg[(size_t)(err_vec + j0 + j) * 32];   // error of the previous step, materialised by k_lin
         ae[j] = s.step > 0 ? alpha * e : 0.f;
     }
     const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;

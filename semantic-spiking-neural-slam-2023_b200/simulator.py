@@ -11,6 +11,9 @@ Batching extension (not in the reference, which has no batch axis):
 runs B independent trials that share the static weights; learned PES/Voja matrices and
 all state are per trial.  ``sim.data[probe]`` then has a leading trial axis.
 
+``input_synthesis=dict(...)`` (optional) evaluates the drivers' per-step input closures on the device from
+per-trial paths / landmarks (``slam.py:442-497``) instead of ``trial_inputs`` tables.
+
 Everything that is stepped runs in the CUDA library behind ``include/sspslam_b200.h``;
 if the library or a GPU is missing, construction raises.
 """
