@@ -185,6 +185,8 @@ class _Lowerer:
                     k_max = int(max(1, min(ens.n_neurons // 32, MAX_DEC_CHUNKS)))
                     self.dec_chunks[c] = _best_chunks(ens.n_neurons, jtiles * self.n_groups,
                                                       lambda per: N_SM * PES_CTAS_PER_SM, 1, k_max)
+                    if os.environ.get("SSB_PES_CHUNKS"):          # tuning knob (scripts/dev_perf.py sweeps)
+                        self.dec_chunks[c] = int(max(1, min(int(os.environ["SSB_PES_CHUNKS"]), k_max)))
                 else:                  # static decoders
                     jpad = -(-self._out_size(c) // DEC_TILE) * DEC_TILE
                     quads = -(-self.n_groups // 4)
