@@ -801,6 +801,7 @@ int build_lin_program(ssb_sim* s) {
         for (int r = r0; r < r0 + nr; ++r) {
             if (is_dense[r - r0]) continue;
             const int src = rows3[r * 3], kind = rows3[r * 3 + 1];
+            if (kind == 2 && s->pes_h.K > 0) continue;      // deferred PES: k_pes_hist updates the activity traces
             const int lo = kind == 2 ? 0 : ptr[src], hi = kind == 2 ? 0 : ptr[src + 1];
             const float fa = ab ? ab[(size_t)r * 2] : 0.f, fb = ab ? ab[(size_t)r * 2 + 1] : 1.f;
             if (hi - lo <= 8) {              // one 128-byte record
@@ -1111,8 +1112,8 @@ int ssb_finalize(ssb_sim* s) {
     s->h_cleanup = host_ints(s, "cleanup");
     s->h_pes = host_ints(s, "pes");
     if ((int)s->h_stages.size() != s->n_levels * 12) return fail(-1, "ssb_finalize: stages array has wrong size");
+    if (int rc = setup_pes_defer(s)) return rc;        // decides whether k_pes_hist owns the PES activity traces
     if (int rc = build_lin_program(s)) return rc;
-    if (int rc = setup_pes_defer(s)) return rc;
     if (int rc = build_decode_tiles(s)) return rc;
     if (int rc = build_encode_tiles(s)) return rc;
     s->levels.assign(s->n_levels, LevelInfo());

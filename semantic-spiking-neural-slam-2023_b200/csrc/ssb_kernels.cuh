@@ -1670,8 +1670,14 @@ __global__ void __launch_bounds__(128) k_pes_hist(SsbCtx c, SsbPesDefer h, const
     } else if (r < size_out + n) {
         const int i = r - size_out;
         const int prev_buf = 1 - s.odd;      // afilt half that still holds what the previous step read
-        const float f = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane)[((size_t)prev_buf * c.n_afilt + a_off + i) * 32];
+        float* fg = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane);
+        const float f = fg[((size_t)prev_buf * c.n_afilt + a_off + i) * 32];
         ssb_grp(h.hist_f, h.rows_f, g, lane)[(size_t)(hd[1] + slot * n + i) * 32] = f;
+        // this kernel is the last reader of that half in the step, so it also performs the trace update the row
+        // program would do (kind 2): new trace = decay * trace + (1 - decay) * activity, written over the old half
+        const float y = fg[((size_t)s.odd * c.n_afilt + a_off + i) * 32];
+        const float u = ssb_grp(c.act, c.n_act, g, lane)[(size_t)(d[4] + i) * 32];
+        fg[((size_t)prev_buf * c.n_afilt + a_off + i) * 32] = fmaf(__int_as_float(d[9]), u, __int_as_float(d[8]) * y);
     }
 }
 
