@@ -576,8 +576,11 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
 }
 
 // SSB_ENCODE=tc selects the tensor-core wide-ensemble kernel.  Measured on B200 (BASELINE configs[1], 1024 trials):
-// k_wide_static (FFMA, 20 warps/SM) 33 us vs k_wide_static_tc 55 us per step: the GEMM is only 40 % of that kernel's
-// instructions and the 8-warp TMEM epilogue cannot hide the LIF dependency chains, so FFMA stays the default.
+// k_wide_static (FFMA, 20 warps/SM) 36.5 us; k_wide_static_tc 55 us with 8 warps and per-neuron bias loads, 45.7 us
+// with bias / direct-current weights staged in shared memory, 27.4 us with 16 warps x 16 TMEM columns.  Both kernels
+// are issue-bound (LIF update + addressing ~50 instructions per neuron and trial group; the dot product adds 56 FFMA),
+// but the tcgen05 kernel holds a whole SM (114 KB smem, 512 threads) while the FFMA one shares SMs with the other
+// dependency streams: the step changes by ~1 us (284.8 vs 286.0), inside run-to-run noise, so FFMA stays the default.
 bool encode_tc_allowed() {
     const char* e = getenv("SSB_ENCODE");
     return e && std::string(e) == "tc";
@@ -617,7 +620,8 @@ int build_encode_tiles(ssb_sim* s) {
     SSB_CUDA(cudaMemcpy(s->d_enc_t, et.data(), et.size() * sizeof(float), cudaMemcpyHostToDevice));
     SSB_CUDA(cudaMalloc((void**)&s->d_enc_t_off, s->enc_t_off.size() * sizeof(int)));
     SSB_CUDA(cudaMemcpy(s->d_enc_t_off, s->enc_t_off.data(), s->enc_t_off.size() * sizeof(int), cudaMemcpyHostToDevice));
-    SSB_CUDA(cudaFuncSetAttribute(k_wide_static_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SSB_CUDA(cudaFuncSetAttribute(k_wide_static_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SSB_CUDA(cudaFuncSetAttribute(k_wide_static_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     return 0;
 }
 
@@ -632,7 +636,8 @@ bool launch_wide_tc(ssb_sim* s, cudaStream_t st, const int* stage, bool dry) {
         const int* d = &s->h_big[idx * 16];
         if (d[9] & 1) continue;
         if (s->enc_t_off[idx] < 0) return false;
-        const int kp = (d[2] + 7) / 8 * 8;
+        const float* nt = reinterpret_cast<const float*>(s->arrays["ntypes"].bytes.data()) + (size_t)d[8] * 8;
+        const int kp = ((d[2] + 7) / 8 * 8) * 2 + (nt[5] != 0.f ? 1 : 0);       // launch class: operand width, LIF variant
         SsbItemList& L = by_kp[kp];
         if (by_kp.count(kp) == 1 && max_n.count(kp) == 0) L.n = 0;
         if (L.n >= 15) return false;
@@ -641,16 +646,18 @@ bool launch_wide_tc(ssb_sim* s, cudaStream_t st, const int* stage, bool dry) {
     }
     if (dry) return true;
     for (auto& kv : by_kp) {
-        const int kp = kv.first;
+        const int kp = kv.first >> 1;
+        const bool fast = kv.first & 1;
         const SsbItemList& L = kv.second;
         const int quads = (s->n_groups + 3) / 4;
-        const int n_tiles = (max_n[kp] + SSB_ETC_N - 1) / SSB_ETC_N;
+        const int n_tiles = (max_n[kv.first] + SSB_ETC_N - 1) / SSB_ETC_N;
         const size_t smem = (size_t)(2 * 128 + 4 * SSB_ETC_N) * kp * sizeof(float);
         const int per_sm = smem <= 110 * 1024 ? 2 : 1;
         const int chunks_wanted = std::max(1, 148 * per_sm / std::max(1, quads * L.n));
         const int tpc = std::max(1, (n_tiles + chunks_wanted - 1) / chunks_wanted);
         dim3 grid((n_tiles + tpc - 1) / tpc, quads, L.n);
-        k_wide_static_tc<<<grid, 256, smem, st>>>(s->ctx, s->d_big, L, s->d_enc_t, s->d_enc_t_off, kp, tpc);
+        if (fast) k_wide_static_tc<true><<<grid, 512, smem, st>>>(s->ctx, s->d_big, L, s->d_enc_t, s->d_enc_t_off, kp, tpc);
+        else k_wide_static_tc<false><<<grid, 512, smem, st>>>(s->ctx, s->d_big, L, s->d_enc_t, s->d_enc_t_off, kp, tpc);
     }
     return true;
 }

@@ -352,6 +352,23 @@ __device__ __forceinline__ void ssb_tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void ssb_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void ssb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ssb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -884,12 +901,14 @@ __global__ void __launch_bounds__(128) k_wide_static(SsbCtx c, const int* __rest
 // packed state rows (coalesced 128-byte loads / stores per neuron), activities to the act arena.
 // Et: [n_tiles][hi|lo][k/4][8 row groups][8][4] floats.  dynamic smem: (2*128 + 4*64) * KP floats.
 #define SSB_ETC_N 64
-__global__ void __launch_bounds__(256, 1)
+template <bool FAST>
+__global__ void __launch_bounds__(512, 1)
 k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, const float* __restrict__ Et_all,
                  const int* __restrict__ et_off, int KP, int tiles_per_chunk) {
     extern __shared__ __align__(1024) float sm[];
     __shared__ unsigned long long full[2], done[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_bias[2][SSB_ETC_N], s_jnw[2][4 * SSB_ETC_N];   // per-tile bias / direct-current weights, double-buffered
     const int item = items.idx[blockIdx.z];
     const int* d = desc + item * 16;
     const int n = d[0], dims = d[1], state0 = d[3], act0 = d[4], bias_off = d[6], in_row0 = d[7];
@@ -900,7 +919,7 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
     if (t_lo >= n_tiles) return;
     const int my_tiles = min(n_tiles, t_lo + tiles_per_chunk) - t_lo;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, part = warp >> 2;        // 16 warps: TMEM quadrant, 16-column slice of the tile
     const int group = blockIdx.y * 4 + quad;
     const bool live = group < c.G;
     const int g = live ? group : 0;
@@ -926,12 +945,12 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
         }
     }
     float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    {   // A operand: this thread's trial is row r; the two warps of a quadrant alternate 32-column blocks
+    {   // A operand: this thread's trial is row r; the four warps of a quadrant alternate 32-column blocks
         const int r = quad * 32 + lane;
         float* a_hi = sA + (r >> 3) * 32 + (r & 7) * 4;
         float* a_lo = a_hi + a_part;
         const float* src = vg + (size_t)in_row0 * 32;
-        for (int k0 = half * 32; k0 < KP; k0 += 64) {
+        for (int k0 = part * 32; k0 < KP; k0 += 128) {
             float x[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) x[e] = (live && k0 + e < dims) ? src[(size_t)(k0 + e) * 32] : 0.f;
@@ -954,6 +973,19 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
             }
         }
     }
+    const int jm = min(jn_m, 4);
+    auto stage_consts = [&](int i) {                        // tile i's bias / jn weights -> smem stage i & 1
+        const int s = i & 1, base = (t_lo + i) * SSB_ETC_N;
+        if (threadIdx.x < SSB_ETC_N) {
+            const int nn = base + threadIdx.x;
+            s_bias[s][threadIdx.x] = nn < n ? __ldg(c.W + bias_off + nn) : 0.f;
+        }
+        if (threadIdx.x < jm * SSB_ETC_N) {
+            const int e = base * jn_m + threadIdx.x;         // jm == jn_m whenever this path is taken (host guarantees jn_m <= 4)
+            s_jnw[s][threadIdx.x] = e < n * jn_m ? __ldg(c.W + jn_w + e) : 0.f;
+        }
+    };
+    stage_consts(0);
     ssb_fence_async();
     ssb_tc_fence_before();
     __syncthreads();
@@ -989,11 +1021,15 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
         const int s = i & 1;
         if (threadIdx.x == 0 && i + 1 < my_tiles) issue_mma(i + 1);
         __syncwarp();
-        const int nn0 = (t_lo + i) * SSB_ETC_N + half * 32;     // first neuron of this thread's 32 columns
-        float sv[32];
+        if (i + 1 < my_tiles) stage_consts(i + 1);
+        const int nn0 = (t_lo + i) * SSB_ETC_N + part * 16;     // first neuron of this thread's 16 columns
+        const int nvalid = live ? min(16, max(0, n - nn0)) : 0;
+        float* sgt = sg + (size_t)nn0 * 32;
+        float* agt = ag + (size_t)nn0 * 32;
+        float sv[16];
         if (stateful) {                                         // state rows in flight while the MMAs finish
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sv[j] = (live && nn0 + j < n) ? __ldcs(sg + (size_t)(nn0 + j) * 32) : 0.f;
+            for (int j = 0; j < 16; ++j) sv[j] = j < nvalid ? __ldcs(sgt + j * 32) : 0.f;
         }
         ssb_mbar_wait(&done[s], (uint32_t)(i >> 1) & 1u);
         ssb_tc_fence_after();
@@ -1002,27 +1038,46 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
             ssb_bulk_g2s(sB + (size_t)s * 2 * b_part, Et + (size_t)(t_lo + i + 2) * 2 * b_part, tile_bytes, &full[s]);
         }
         __syncwarp();
-        float v[32];
-        ssb_tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * SSB_ETC_N + (uint32_t)half * 32, v);
-        if (live) {
+        float v[16];
+        ssb_tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * SSB_ETC_N + (uint32_t)part * 16, v);
+        int* fl = c.aflag + (size_t)g * c.n_act + act0 + nn0;
+        auto neuron = [&](int j) {
+            float J = v[j] + s_bias[s][part * 16 + j];
+            for (int m = 0; m < jm; ++m) J = fmaf(s_jnw[s][(part * 16 + j) * jm + m], u_jn[m], J);
+            float out;
+            if (stateful) {
+                float st = sv[j];
+                out = ssb_lif_packed<FAST>(nt, J, st);
+                __stcs(sgt + j * 32, st);
+            } else {
+                out = ssb_rate(nt, J);
+            }
+            agt[j * 32] = out;
+            const bool any_on = __any_sync(0xffffffffu, out != 0.f);
+            if (lane == 0) fl[j] = any_on;
+        };
+        if (nvalid == 16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int nn = nn0 + j;
-                if (nn < n) {
-                    float J = v[j] + __ldg(c.W + bias_off + nn);
-                    for (int m = 0; m < jn_m && m < 4; ++m) J = fmaf(__ldg(c.W + jn_w + nn * jn_m + m), u_jn[m], J);
-                    float out;
-                    if (stateful) {
-                        float st = sv[j];
-                        out = nt.fast ? ssb_lif_packed<true>(nt, J, st) : ssb_lif_packed<false>(nt, J, st);
-                        __stcs(sg + (size_t)nn * 32, st);
-                    } else {
-                        out = ssb_rate(nt, J);
-                    }
-                    ag[(size_t)nn * 32] = out;
-                    const bool any_on = __any_sync(0xffffffffu, out != 0.f);     // nn < n is warp-uniform
-                    if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + nn] = any_on;
+            for (int j = 0; j < 16; ++j) neuron(j);
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < nvalid; ++j) {
+                float vj = 0.f, svj = 0.f;                      // ragged last tile: select without dynamic register indexing
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if (q == j) { vj = v[q]; svj = sv[q]; }
+                float J = vj + s_bias[s][part * 16 + j];
+                for (int m = 0; m < jm; ++m) J = fmaf(s_jnw[s][(part * 16 + j) * jm + m], u_jn[m], J);
+                float out;
+                if (stateful) {
+                    out = ssb_lif_packed<FAST>(nt, J, svj);
+                    __stcs(sgt + j * 32, svj);
+                } else {
+                    out = ssb_rate(nt, J);
                 }
+                agt[j * 32] = out;
+                const bool any_on = __any_sync(0xffffffffu, out != 0.f);
+                if (lane == 0) fl[j] = any_on;
             }
         }
         ssb_tc_fence_before();
