@@ -759,7 +759,7 @@ int build_lin_program(ssb_sim* s) {
         std::map<std::vector<int>, std::vector<int>> groups;
         for (int r = r0; r < r0 + nr; ++r) {
             const int src = rows3[r * 3], kind = rows3[r * 3 + 1];
-            if (kind == 2) continue;
+            if (kind == 2 || kind == 5) continue;            // activity rows (trace / neuron probe) read the act arena
             if (src < 0 || (size_t)src + 1 >= ptr.size()) return fail(-1, "ssb_finalize: lin_rows CSR row out of range");
             const int lo = ptr[src], hi = ptr[src + 1];
             if (hi - lo < SSB_DENSE_MIN_K) continue;
@@ -809,9 +809,10 @@ int build_lin_program(ssb_sim* s) {
             if (is_dense[r - r0]) continue;
             const int src = rows3[r * 3], kind = rows3[r * 3 + 1];
             if (kind == 2 && s->pes_h.K > 0) continue;      // deferred PES: k_pes_hist updates the activity traces
-            const int lo = kind == 2 ? 0 : ptr[src], hi = kind == 2 ? 0 : ptr[src + 1];
+            const bool from_act = kind == 2 || kind == 5;
+            const int lo = from_act ? 0 : ptr[src], hi = from_act ? 0 : ptr[src + 1];
             const float fa = ab ? ab[(size_t)r * 2] : 0.f, fb = ab ? ab[(size_t)r * 2 + 1] : 1.f;
-            if (hi - lo <= 8) {              // one 128-byte record
+            if (hi - lo <= 8 && kind != 5) {              // one 128-byte record
                 int w[32] = {0};
                 w[0] = kind;
                 w[1] = rows3[r * 3 + 2];

@@ -2451,7 +2451,8 @@ __global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ 
 // the ping-pong buffer = nengo's update-after-read), probe samples, PES activity traces.
 // The same kernel materialises the sink rows of a dependency level into vec scratch before the level's
 // consumers run (kinds 3 / 4), so that no consumer evaluates CSR rows itself.
-// kind 0 filter, 1 probe, 2 activity trace, 3 / 4 materialise (4: on the values the previous step read).
+// kind 0 filter, 1 probe, 2 activity trace, 3 / 4 materialise (4: on the values the previous step read),
+// 5 neuron-output probe (activity row -> probe block; CSR population only).
 //
 // Three CTA populations in one launch (the host sorts every segment's rows into them at finalize):
 //  * dense items: rows that share one column list (the circular-convolution DFT matrices, to_Fourier / to_SSP,
@@ -2629,6 +2630,10 @@ __global__ void __launch_bounds__(128, 8) k_lin(SsbCtx c, SsbLinArgs L, int i_re
         const float y = fg[((size_t)s.odd * c.n_afilt + dst) * 32];
         const float u = ssb_grp(c.act, c.n_act, g, lane)[(size_t)src * 32];
         fg[((size_t)(1 - s.odd) * c.n_afilt + dst) * 32] = fmaf(b, u, a * y);
+        return;
+    }
+    if (kind == 5) {                                          // neuron-output probe: this step's activity row, unfiltered
+        ssb_lin_store(c, s, vg, g, lane, 1, dst, a, b, ssb_grp(c.act, c.n_act, g, lane)[(size_t)src * 32]);
         return;
     }
     const int2* __restrict__ ent = kind == 4 ? s.ent_new : s.ent_old;

@@ -164,13 +164,15 @@ class _Lowerer:
         pes_conns = {c for c in self.conns
                      if c.learning_rule is not None and isinstance(c.learning_rule.learning_rule_type, ns.PES)}
         jn_posts = {c.post_obj.ensemble for c in self.conns if isinstance(c.post_obj, ns.Neurons)}
+        # ensembles whose neuron outputs are probed keep their activities in the act arena (wide path)
+        neuron_probed = {p.obj.ensemble for p in self.probes if isinstance(p.obj, ns.Neurons)}
         self.is_small, self.dec_chunks = {}, {}
         for ens in self.ensembles:
             outs = self.ens_dec_conns[ens]
             nout = sum(self._out_size(c) for c in outs)
             has_pes = any(c in pes_conns for c in outs)
             small = (ens.dimensions <= SMALL_MAX_DIMS and nout <= SMALL_MAX_OUT and ens not in voja_posts
-                     and ens not in jn_posts and not has_pes)
+                     and ens not in jn_posts and not has_pes and ens not in neuron_probed)
             self.is_small[ens] = small
         n_static = sum(1 for e in self.ensembles if not self.is_small[e]
                        for c in self.ens_dec_conns[e] if c not in pes_conns)
@@ -651,7 +653,20 @@ class _Lowerer:
         for probe in self.probes:
             period = 1 if probe.sample_every is None else int(round(probe.sample_every / dt))
             obj = probe.obj
-            if isinstance(obj, (ns.Node, ns.Ensemble)):
+            if isinstance(obj, ns.Neurons):
+                # neuron-output probes (run_pathint_gif.py:157-159: ``ea_ensembles[k].neurons[:500]``, synapse=None):
+                # the step's activity rows are copied to the probe block by the row program (kind 5)
+                if probe.synapse is not None:
+                    raise NotImplementedError("filtered probes on ens.neurons are outside the hot path")
+                if obj.ensemble not in plan.ens_act:
+                    raise NotImplementedError(f"probe {probe!r}: the ensemble is not simulated on the device")
+                sel = _idx(probe.slice, obj.size_out)
+                info = ProbeInfo(probe, "rows", n_probe_rows, len(sel), period)
+                for i, k in enumerate(sel):
+                    lin_rows.append([plan.ens_act[obj.ensemble] + int(k), 5, n_probe_rows + i])
+                    lin_ab.append([0.0, 1.0])
+                n_probe_rows += len(sel)
+            elif isinstance(obj, (ns.Node, ns.Ensemble)):
                 if probe in self.filt_col:
                     mat = self._eye(self.filt_col[probe], probe.size_in)
                 else:

@@ -168,6 +168,8 @@ class PlanInterpreter:
                 new_f[1 + dst + par_new] = cb * self.rows(src, 1)[0] + ca * self.vec[1 + dst + par_old]
             elif kind == 1:
                 probe[dst] = self.rows(src, 1)[0]
+            elif kind == 5:
+                probe[dst] = self.act[src]
             else:
                 ob = s & 1
                 self.afilt[1 - ob, dst] = cb * self.act[src] + ca * self.afilt[ob, dst]

@@ -428,3 +428,36 @@ def test_grid_cell_ensemble_and_approx_velocity_variants_match_oracle():
     got = sim.data[sc.probe]
     for trial in (0, 2):
         assert _rel(got[trial], _oracle(sc, sim, trial, n_steps).data[sc.probe]) < 1e-4
+
+
+@pytest.mark.parametrize("neuron_type", ["lifrate", "lif"])
+def test_neuron_output_and_sliced_vco_probes_match_oracle(neuron_type):
+    """the probes of run_pathint_gif.py:156-159 — a sliced, filtered VCO output probe and neuron-output
+    probes (``ea_ensembles[k].neurons[:m]``, synapse=None, sample_every) served by the row program from the act arena."""
+    from sspslam_b200 import nengo_shim as nengo
+    n_steps = 120
+    sc = scenarios.make_pathint(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=200, neuron_type=neuron_type)
+    pi = sc.extra["pathint"]
+    with sc.network:
+        vco_p = nengo.Probe(pi.oscillators.output[3:12], synapse=0.05)
+        n1 = nengo.Probe(pi.oscillators.ea_ensembles[1].neurons[:150], synapse=None, sample_every=4 * sc.dt)
+        n2 = nengo.Probe(pi.oscillators.ea_ensembles[2].neurons, synapse=None)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        assert sim.plan.stats["n_big"] == 2
+        sim.run_steps(n_steps)
+    assert sim.data[n1].shape == (3, n_steps // 4, 150) and sim.data[n2].shape == (3, n_steps, 200)
+    assert sim.trange(sample_every=4 * sc.dt).shape == (n_steps // 4,)
+    for trial in (0, 2):
+        ref = _oracle(sc, sim, trial, n_steps)
+        if neuron_type == "lifrate":
+            for p in (sc.probe, vco_p, n1, n2):
+                assert np.max(np.abs(ref.data[p])) > 0
+                assert _rel(sim.data[p][trial], ref.data[p]) < 1e-4
+        else:
+            assert _rel(sim.data[sc.probe][trial], ref.data[sc.probe]) < 2e-3
+            for p in (n1, n2):          # spikes: amplitude / dt or 0; a float32 voltage may cross one step early / late
+                got, want = sim.data[p][trial], ref.data[p]
+                assert np.allclose(got[got != 0], 1.0 / sc.dt, rtol=1e-6)     # float32 amplitude / dt
+                assert want.sum() > 0
+                assert abs(got.sum() - want.sum()) <= 0.02 * want.sum()
+                assert np.mean((got != 0) != (want != 0)) < 2e-3

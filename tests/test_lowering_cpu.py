@@ -119,3 +119,27 @@ def test_slam_grid_cell_ensemble_and_approx_velocity_plan_matches_oracle():
     plan, *_ = _compare(sc, 60)
     assert plan.stats["n_big"] == 5                      # OVC, memory, recall, error + the grid-cell ensemble
     assert plan.stats["n_levels"] >= 2                   # clean-up node -> grid cells in the same step
+
+
+def test_neuron_slice_and_vco_probes_match_oracle():
+    """run_pathint_gif.py:156-159: a sliced output probe and neuron-output probes with sample_every."""
+    from sspslam_b200 import nengo_shim as nengo
+    sc = scenarios.make_pathint(n_trials=1, n_steps=60, ssp_dim=19, pi_n_neurons=40, neuron_type="lif")
+    pi = sc.extra["pathint"]
+    with sc.network:
+        vco_p = nengo.Probe(pi.oscillators.output[3:12], synapse=0.05)
+        n1 = nengo.Probe(pi.oscillators.ea_ensembles[1].neurons[:25], synapse=None, sample_every=5 * sc.dt)
+        n2 = nengo.Probe(pi.oscillators.ea_ensembles[2].neurons, synapse=None)
+    plan, model, ref, it = _compare(sc, 60)
+    assert plan.stats["n_big"] == 2                      # the two probed VCO populations keep activity rows
+    for probe in (vco_p, n1, n2):
+        info = [i for i in plan.probes if i.probe is probe][0]
+        got, want = it.probe_data(info), ref.data[probe]
+        assert got.shape == want.shape
+        if probe is vco_p:
+            assert np.max(np.abs(got - want)) <= 2e-5 * np.max(np.abs(want))
+        else:
+            assert np.max(np.abs(want)) > 0              # some neuron spiked
+            assert np.array_equal(got != 0, want != 0)   # same spikes, step for step
+            assert np.allclose(got, want, rtol=1e-6)
+    assert ref.data[n1].shape == (12, 25)
