@@ -185,7 +185,7 @@ class SimLowpass(Op):
 
     def __init__(self, tau, dt, inp, out):
         self.inp, self.out = inp, out
-        a = np.exp(-dt / tau)
+        a = np.exp(-dt / tau) if tau > 0 else 0.0     # Lowpass(0): no state, the update-after-read delay remains
         self.a = out.a.dtype.type(a)
         self.b = out.a.dtype.type(1.0 - a)
         self.reads = (inp,)

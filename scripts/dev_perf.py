@@ -18,6 +18,8 @@ elif cfg == "slamview97":   # BASELINE configs[3] sizes
 elif cfg == "slam55gif":    # BASELINE configs[2] sizes (run_slam_map_gif.py defaults)
     sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=55, pi_n_neurons=800, mem_n_neurons=1000,
                              circonv_n_neurons=100, n_landmarks=50, T=200.0, length_scale=0.1, distinct_tables=8)
+elif cfg == "slam55loihi":  # run_slam.py --backend loihi-sim sizes: SLAMLoihiNetwork, d=55, pi 500, mem 970, circonv 100, dot-product 50
+    sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=8, loihi=True, dotprod_n_neurons=50)
 else:
     sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=8)
 if os.environ.get("SYNTH"):      # on-device input synthesis instead of tables

@@ -36,6 +36,7 @@ class BuiltConnection:
     solver_info: dict | None
     transform: np.ndarray | None
     weights: np.ndarray | float | None  # folded ``transform @ decoders`` (size_out x n) for decoded conns
+    decoders: np.ndarray | None = None  # unfolded decoders (size_mid x n)
 
 
 class BuiltModel:
@@ -205,7 +206,7 @@ def _build_connection(model, conn, cache):
             raise NotImplementedError("per-connection eval_points are outside the hot path")
         decoders = cache.solve(pre, conn.solver, _targets(conn, eval_points)).T  # size_mid x n
         weights = fold_transform(conn.transform, decoders)
-        model.params[conn] = BuiltConnection(eval_points, {}, conn.transform, weights)
+        model.params[conn] = BuiltConnection(eval_points, {}, conn.transform, weights, decoders)
     elif isinstance(pre, ns.Neurons):
         raise NotImplementedError("connections *from* ens.neurons are outside the hot path")
     else:

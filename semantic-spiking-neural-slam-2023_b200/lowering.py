@@ -62,6 +62,10 @@ def _best_chunks(n, units, slots_of, k_min, k_max, fixed=8, per_chunk=0.0):
 NT_LIF, NT_LIFRATE, NT_RELU = 0, 1, 2
 
 
+def _ens_to_neurons(c):
+    return isinstance(c.pre_obj, ns.Ensemble) and isinstance(c.post_obj, ns.Neurons)
+
+
 def _idx(key, size):
     return np.atleast_1d(np.arange(size)[key])
 
@@ -211,7 +215,11 @@ class _Lowerer:
 
     @staticmethod
     def _out_size(c):
-        return c.size_out if isinstance(c, ns.Connection) else c.size_in
+        if isinstance(c, ns.Connection):
+            # ensemble -> neurons (slam_loihi.py:266): decode size_mid values, the (n x size_mid) transform is applied
+            # as direct neuron currents after the synapse (linear, so equal to filtering the n folded currents)
+            return c.size_mid if _ens_to_neurons(c) else c.size_out
+        return c.size_in
 
     def _dec_expr(self, c):
         """Decoded value of connection/probe ``c`` (split-K partial sums are reduced inside the launch)."""
@@ -236,9 +244,9 @@ class _Lowerer:
                 self.tab_col[node] = alloc("tab", node, node.size_out)
         for conn in self.conns:
             if conn.synapse is not None:
-                if isinstance(conn.post_obj, ns.Neurons) or isinstance(conn.pre_obj, ns.Neurons):
+                if isinstance(conn.pre_obj, ns.Neurons) or (isinstance(conn.post_obj, ns.Neurons) and not _ens_to_neurons(conn)):
                     raise NotImplementedError("filtered neuron-to-neuron connections are outside the hot path")
-                self.filt_col[conn] = alloc("filt", conn, conn.size_out)
+                self.filt_col[conn] = alloc("filt", conn, self._out_size(conn))
         for probe in self.probes:
             if isinstance(probe.obj, (ns.Node, ns.Ensemble)) and probe.synapse is not None:
                 self.filt_col[probe] = alloc("filt", probe, probe.size_in)
@@ -316,7 +324,12 @@ class _Lowerer:
                 if conn.transform is None or np.ndim(conn.transform) != 2 or conn.post_slice != slice(None):
                     raise NotImplementedError("neuron-direct connections need a full (n x m) transform")
                 pre = conn.pre_obj
-                u = self.expr_out(pre)[_idx(conn.pre_slice, pre.size_out)]
+                if _ens_to_neurons(conn):
+                    if conn.synapse is None:
+                        raise NotImplementedError("unfiltered ensemble -> neurons connections are outside the hot path")
+                    u = self._eye(self.filt_col[conn], conn.size_mid)
+                else:
+                    u = self.expr_out(pre)[_idx(conn.pre_slice, pre.size_out)]
                 G = self.model.params[ens].gain[:, None] * np.asarray(conn.transform, dtype=np.float64)
                 jn.append((u.tocsr(), G))
             if jn:
@@ -427,7 +440,7 @@ class _Lowerer:
         for node, c0 in self.tab_col.items():
             plan.tables.append((node, int(dev_col[c0] - tab_row0), node.size_out))
         for key, c0 in self.filt_col.items():
-            size = key.size_out if isinstance(key, ns.Connection) else key.size_in
+            size = self._out_size(key)
             plan.filters[key] = (int(dev_col[c0] - 1), size)
 
         # ---- CSR program
@@ -524,7 +537,7 @@ class _Lowerer:
             n, dims = ens.n_neurons, ens.dimensions
             lvl = ens_level[ens]
             outs = self.ens_dec_conns[ens]
-            nout = sum((c.size_out if isinstance(c, ns.Connection) else c.size_in) for c in outs)
+            nout = sum(self._out_size(c) for c in outs)
             is_small = self.is_small[ens]
             state0 = nn
             nn += n
@@ -578,7 +591,7 @@ class _Lowerer:
                                   jn_row0, jn_m, jn_w, voja_row, scale_off,
                                   int(np.float32(voja_alpha).view(np.int32))])
             for c in outs:
-                size_out = c.size_out if isinstance(c, ns.Connection) else c.size_in
+                size_out = self._out_size(c)
                 out_vec = int(dev_col[self.dec_col[c]])
                 if isinstance(c, ns.Connection) and c in pes_rule:
                     rin, lrt = pes_rule[c]
@@ -637,7 +650,7 @@ class _Lowerer:
         for key, mat in filt_in.items():
             f0, size = plan.filters[key]
             tau = key.synapse.tau
-            a64 = np.exp(-dt / tau)
+            a64 = np.exp(-dt / tau) if tau > 0 else 0.0     # Lowpass(0) (slam_loihi.py:233): a pure one-step delay
             a, b = np.float32(a64), np.float32(1.0 - a64)
             r0 = add_rows(mat)
             if mat.shape[0] != size:
@@ -771,6 +784,8 @@ class _Lowerer:
 
     def _dec_weights(self, c):
         if isinstance(c, ns.Connection):
+            if _ens_to_neurons(c):
+                return np.asarray(self.model.params[c].decoders, dtype=np.float64)
             return np.asarray(self.model.params[c].weights, dtype=np.float64)
         return np.asarray(self.model.probe_conns[c], dtype=np.float64)
 

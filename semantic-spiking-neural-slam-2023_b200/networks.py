@@ -10,6 +10,7 @@ creation-order dependent, SURVEY.md App. A.2 — the creation order) of:
 * ``AssociativeMemory``    <- ``sspslam/networks/associativememory.py:12-54``
 * ``SLAMNetwork``          <- ``sspslam/networks/slam.py:182-307``
 * ``SLAMViewNetwork``      <- ``sspslam/networks/slam_view.py:181-276``
+* ``SLAMLoihiNetwork``     <- ``sspslam/networks/slam_loihi.py:190-293`` (all-neural gating)
 
 ``tests/test_networks_parity.py`` checks (in the authoring container, where the
 reference is mounted) that a model built from these declarations is *identical* —
@@ -27,7 +28,7 @@ from .nengo_shim.params import Default
 from .nodeops import Identity, GridCleanup, GatedCorrection
 
 __all__ = ["PathIntegration", "Product", "CircularConvolution", "AssociativeMemory", "SLAMNetwork",
-           "SLAMViewNetwork", "get_to_Fourier", "get_from_Fourier", "transform_in", "transform_out",
+           "SLAMViewNetwork", "SLAMLoihiNetwork", "get_to_Fourier", "get_from_Fourier", "transform_in", "transform_out",
            "dft_half", "circconv", "oscillator_feedback"]
 
 
@@ -367,3 +368,89 @@ class SLAMViewNetwork(Network):
 
             Connection(self.assomemory.recall, self.update_state[:d], function=lambda x: make_unitary(x), synapse=tau)
             Connection(self.pathintegrator.output, self.update_state[d:-1], synapse=tau)
+
+
+class SLAMLoihiNetwork(Network):
+    """SLAM without Python node functions (``slam_loihi.py:190-293``): fixed landmark encoders instead of Voja, a
+    neural correction population, and the update gate computed by neurons — ``|a + b|^2 - |a - b|^2`` from two arrays of
+    squaring populations feeds a threshold population that inhibits the correction neurons.  Input nodes may be passed
+    in (the driver's table nodes, ``run_slam.py:171-176``) or are created as pass-through nodes."""
+
+    def __init__(self, ssp_space, lm_space, view_rad, n_landmarks, pi_n_neurons, mem_n_neurons, circonv_n_neurons,
+                 dotprod_n_neurons, velocity_input=None, landmark_vecssp_input=None, landmark_sp_input=None,
+                 no_landmark_in_view=None, tau=0.01, tau_pi=0.05, update_thres=0.2, vel_scaling_factor=1.0,
+                 rad_scaling_factor=1, shift_rate=0.1, pes_learning_rate=1e-2, encoders=None, solver=Default,
+                 pi_solver_weights=False, seed=0):
+        super().__init__()
+        d, n_dom = ssp_space.ssp_dim, ssp_space.domain_dim
+        landmark_sps = lm_space.vectors
+        rng = np.random.RandomState(seed=seed)
+        if encoders is None:
+            encoders = landmark_sps[rng.randint(n_landmarks, size=mem_n_neurons), :]
+        intercept = _default_intercept(landmark_sps, n_landmarks)
+
+        def given(node, size, label):
+            return Node(size_in=size, label=label) if node is None else node
+
+        with self:
+            self.velocity_input = given(velocity_input, n_dom, "vel_input")
+            self.landmark_vecssp_input = given(landmark_vecssp_input, d, "lm_vecssp_input")
+            self.landmark_sp_input = given(landmark_sp_input, d, "lm_sp_input")
+            self.no_landmark_in_view = given(no_landmark_in_view, 1, "lm_in_view_input")
+
+            self.pathintegrator = PathIntegration(ssp_space, pi_n_neurons, tau_pi, max_radius=rad_scaling_factor,
+                                                  scaling_factor=vel_scaling_factor, stable=True, with_gcs=False,
+                                                  solver_weights=pi_solver_weights, label="pathint")
+            Connection(self.velocity_input, self.pathintegrator.velocity_input, synapse=None)
+            self.output = self.pathintegrator.output
+
+            # landmark location = own position (*) displacement
+            self.landmark_ssp_ens = CircularConvolution(circonv_n_neurons, dimensions=d, solver=solver,
+                                                        label="landmark_circonv")
+            Connection(self.pathintegrator.output, self.landmark_ssp_ens.input_a, synapse=tau)
+            Connection(self.landmark_vecssp_input, self.landmark_ssp_ens.input_b, synapse=0)
+
+            # environment map: landmark SP -> landmark location SSP, PES-learned
+            mem = self.assomemory = nengo.Network(seed=seed)
+            mem.memory = Ensemble(mem_n_neurons, d, intercepts=[intercept] * mem_n_neurons, encoders=encoders,
+                                  radius=1, label="memory")
+            mem.recall = Ensemble(mem_n_neurons, d, label="memory_recall")
+            Connection(self.landmark_sp_input, mem.memory, synapse=None, label="map_conn_in")
+            mem.conn_out = Connection(mem.memory, mem.recall, learning_rule_type=nengo.PES(pes_learning_rate),
+                                      label="map_conn_pes", function=lambda x: np.zeros(d))
+            mem_error = Ensemble(mem_n_neurons, d, label="memory_pes_error")
+            Connection(self.no_landmark_in_view, mem_error.neurons, transform=[[-2.5]] * mem_n_neurons, synapse=None)
+            Connection(self.landmark_ssp_ens.output, mem_error, transform=-1, synapse=tau)
+            Connection(mem.recall, mem_error, synapse=tau)
+            Connection(mem_error, mem.conn_out.learning_rule, synapse=tau)
+
+            # position from the map: recalled location (*) inverse displacement
+            self.position_estimate = CircularConvolution(circonv_n_neurons, d, input_magnitude=1, invert_a=True,
+                                                         solver=solver, label="newpos_circonv")
+            Connection(self.landmark_vecssp_input, self.position_estimate.input_a, synapse=None)
+            Connection(mem.recall, self.position_estimate.input_b, synapse=tau)
+
+            # correction population, fed back through a long synapse
+            self.correction = Ensemble(mem_n_neurons, d, label="correction_ens")
+            Connection(self.position_estimate.output, self.correction, synapse=tau, transform=1)
+            Connection(self.pathintegrator.output, self.correction, synapse=tau, transform=-1)
+            Connection(self.correction, self.pathintegrator.input, synapse=0.1, transform=shift_rate)
+
+            # gate: the correction is inhibited unless <estimate, state> exceeds the threshold
+            bias = Node(1, label="threshold_bias")
+            self.threshold = Ensemble(circonv_n_neurons, 1, intercepts=nengo.dists.Choice([update_thres]),
+                                      encoders=np.ones((circonv_n_neurons, 1)), label="threshold")
+            Connection(bias, self.threshold, synapse=None)
+            Connection(self.no_landmark_in_view, self.threshold, synapse=None)
+            Connection(self.threshold, self.correction.neurons, transform=[[-5]] * mem_n_neurons, synapse=0.05)
+            half = max(1, dotprod_n_neurons // 2)
+            squares = [EnsembleArray(half, n_ensembles=d, ens_dimensions=1, radius=np.sqrt(2), label=f"dotprod_sq{k}")
+                       for k in (1, 2)]
+            tr = 1.0 / np.sqrt(2.0)
+            for arr, sign in zip(squares, (1.0, -1.0)):
+                Connection(self.position_estimate.output, arr.input, transform=tr, synapse=tau)
+                Connection(self.pathintegrator.output, arr.input, transform=sign * tr, synapse=tau)
+            for i in range(d):
+                Connection(squares[0].ea_ensembles[i], self.threshold, function=lambda x: -0.5 * x ** 2, synapse=tau)
+                Connection(squares[1].ea_ensembles[i], self.threshold, function=lambda x: 0.5 * x ** 2, synapse=tau)
+

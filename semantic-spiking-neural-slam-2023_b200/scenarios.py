@@ -74,11 +74,12 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
               n_landmarks=50, view_rad=0.2, T=200.0, limit=0.1, seed=0, dt=0.001, length_scale=0.2,
               shift_rate=0.2, update_thres=0.2, neuron_type="lif", weights_probe=False, view=False,
               distinct_tables=None, domain_dim=2, grid_points_per_dim=100, gc_n_neurons=0, approx_vel=False,
-              vel_n_neurons=500):
+              vel_n_neurons=500, loihi=False, dotprod_n_neurons=50):
     """``run_slam.py`` (or ``run_slamview.py`` when ``view``) workload, batched over trials.
 
     ``distinct_tables``: synthesise only that many distinct trials' tables and tile them
-    over the batch (bench warm-up economy); state/voltages still differ per trial."""
+    over the batch (bench warm-up economy); state/voltages still differ per trial.
+    ``loihi``: the all-neural ``SLAMLoihiNetwork`` with the driver's arguments of ``run_slam.py:171-176``."""
     space = make_space(domain_dim, ssp_dim, length_scale)
     d = space.ssp_dim
     lm_space = SPSpace(n_landmarks, d, seed=seed)
@@ -123,7 +124,14 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
         init = nengo.Node(tab_fn("init"), label="init_state")
         lm_id = nengo.Node(tab_fn("lm_sp"), label="lm_sp_input")
         is_lm = nengo.Node(tab_fn("nolm"), label="lm_in_view_input")
-        if view:
+        if loihi:
+            lm_vec = nengo.Node(tab_fn("lmvec_ssp"), label="lm_vecssp_input")
+            slam = networks.SLAMLoihiNetwork(space, lm_space, view_rad, n_landmarks, pi_n_neurons, mem_n_neurons,
+                                             circonv_n_neurons, dotprod_n_neurons, vel_in, lm_vec, lm_id, is_lm,
+                                             tau_pi=0.05, update_thres=update_thres, vel_scaling_factor=scale,
+                                             shift_rate=0.1, pes_learning_rate=1e-3, encoders=None, seed=seed)
+            table_nodes = {"vel": vel_in, "init": init, "lm_sp": lm_id, "nolm": is_lm, "lmvec_ssp": lm_vec}
+        elif view:
             slam = networks.SLAMViewNetwork(space, lm_space, view_rad, n_landmarks, pi_n_neurons, mem_n_neurons,
                                             circonv_n_neurons, tau_pi=0.05, update_thres=update_thres,
                                             vel_scaling_factor=scale, shift_rate=0.02, voja_learning_rate=5e-4,
@@ -140,8 +148,11 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
             nengo.Connection(lm_vec, slam.landmark_vec_ssp, synapse=None)
             nengo.Connection(lm_id, slam.landmark_id_input, synapse=None)
             table_nodes = {"vel": vel_in, "init": init, "lm_sp": lm_id, "nolm": is_lm, "lmvec_ssp": lm_vec}
-        nengo.Connection(is_lm, slam.no_landmark_in_view, synapse=None)
-        if approx_vel:   # run_slam.py:154-160: the velocity passes through a spiking ensemble (vel_syn = 0.01)
+        if not loihi:
+            nengo.Connection(is_lm, slam.no_landmark_in_view, synapse=None)
+        if loihi:
+            pass                     # the driver's nodes are the network's inputs
+        elif approx_vel:   # run_slam.py:154-160: the velocity passes through a spiking ensemble (vel_syn = 0.01)
             vel_ens = nengo.Ensemble(vel_n_neurons, domain_dim)
             nengo.Connection(vel_in, vel_ens, synapse=None)
             nengo.Connection(vel_ens, slam.velocity_input, synapse=0.01)

@@ -461,3 +461,20 @@ def test_neuron_output_and_sliced_vco_probes_match_oracle(neuron_type):
                 assert want.sum() > 0
                 assert abs(got.sum() - want.sum()) <= 0.02 * want.sum()
                 assert np.mean((got != 0) != (want != 0)) < 2e-3
+
+
+def test_slam_loihi_variant_matches_oracle():
+    """SLAMLoihiNetwork (slam_loihi.py:190-293) on the same kernels — no node functions, the update gate is
+    a threshold population that inhibits the correction neurons through a filtered ensemble -> neurons connection."""
+    n_steps = 150
+    sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=80, mem_n_neurons=160,
+                             circonv_n_neurons=24, n_landmarks=12, T=20.0, neuron_type="lifrate", view_rad=0.5,
+                             loihi=True, dotprod_n_neurons=20)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        assert sim.plan.stats["n_big"] == 4
+        sim.run_steps(n_steps)
+    got = sim.data[sc.probe]
+    for trial in (0, 2):
+        want = _oracle(sc, sim, trial, n_steps).data[sc.probe]
+        assert np.max(np.abs(want)) > 0.1
+        assert _rel(got[trial], want) < 1e-4

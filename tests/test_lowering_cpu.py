@@ -143,3 +143,13 @@ def test_neuron_slice_and_vco_probes_match_oracle():
             assert np.array_equal(got != 0, want != 0)   # same spikes, step for step
             assert np.allclose(got, want, rtol=1e-6)
     assert ref.data[n1].shape == (12, 25)
+
+
+def test_slam_loihi_plan_matches_oracle():
+    """SLAMLoihiNetwork (slam_loihi.py) — neural gate, Lowpass(0) input, four wide populations."""
+    sc = scenarios.make_slam(n_trials=1, n_steps=60, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=48, circonv_n_neurons=12,
+                             n_landmarks=6, T=20.0, neuron_type="lifrate", view_rad=0.5, grid_points_per_dim=12,
+                             loihi=True, dotprod_n_neurons=16)
+    plan, *_ = _compare(sc, 60)
+    assert plan.stats["n_big"] == 4          # memory, recall, PES error, correction
+    assert not plan.arrays["cleanup"].size and not plan.arrays["gate"].size     # no node functions: the gate is neural

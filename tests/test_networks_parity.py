@@ -146,3 +146,25 @@ def test_reference_network_steps_identically_in_the_oracle():
         out.append(sim.data[p])
     np.testing.assert_allclose(out[0], out[1], rtol=0, atol=1e-9)
     assert np.max(np.abs(out[0])) > 0.05
+
+
+def test_slam_loihi_network_matches_reference():
+    """the all-neural variant (slam_loihi.py:190-293) — same census, seeds, encoders, decoders."""
+    ref = _ref()
+    space = HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2, backend="host")
+    rspace = ref.HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2)
+    lm, rlm = SPSpace(6, space.ssp_dim, seed=2), ref.SPSpace(6, rspace.ssp_dim, seed=2)
+    nets = []
+    for mod, sp, l in ((networks, space, lm), (ref.networks, rspace, rlm)):
+        with nengo.Network(seed=4) as net:
+            slam = mod.SLAMLoihiNetwork(sp, l, 0.2, 6, 30, 64, 16, 20, tau_pi=0.05, update_thres=0.2,
+                                        vel_scaling_factor=0.7, shift_rate=0.1, pes_learning_rate=1e-3, seed=3)
+            nengo.Probe(slam.pathintegrator.output, synapse=0.05)
+        nets.append((net, slam))
+    (na, sa), (nb, sb) = nets
+    _assert_same_model(na, nb)
+    assert [e.label for e in na.all_ensembles] == [e.label for e in nb.all_ensembles]
+    from sspslam_b200 import nodeops
+    owners = [nb] + nb.all_networks     # no clean-up / gate node functions in this variant, only the PI pass-through
+    assert [nodeops.recognize(n, owners).kind for n in nb.all_nodes if callable(n.output) and n.size_in > 0] == ["identity"]
+    np.testing.assert_allclose(np.asarray(sa.assomemory.memory.encoders), np.asarray(sb.assomemory.memory.encoders))
