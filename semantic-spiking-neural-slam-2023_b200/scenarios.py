@@ -74,12 +74,14 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
               n_landmarks=50, view_rad=0.2, T=200.0, limit=0.1, seed=0, dt=0.001, length_scale=0.2,
               shift_rate=0.2, update_thres=0.2, neuron_type="lif", weights_probe=False, view=False,
               distinct_tables=None, domain_dim=2, grid_points_per_dim=100, gc_n_neurons=0, approx_vel=False,
-              vel_n_neurons=500, loihi=False, dotprod_n_neurons=50):
+              vel_n_neurons=500, loihi=False, dotprod_n_neurons=50, inverse_memory=False):
     """``run_slam.py`` (or ``run_slamview.py`` when ``view``) workload, batched over trials.
 
     ``distinct_tables``: synthesise only that many distinct trials' tables and tile them
     over the batch (bench warm-up economy); state/voltages still differ per trial.
-    ``loihi``: the all-neural ``SLAMLoihiNetwork`` with the driver's arguments of ``run_slam.py:171-176``."""
+    ``loihi``: the all-neural ``SLAMLoihiNetwork`` with the driver's arguments of ``run_slam.py:171-176``.
+    ``inverse_memory``: the topology of ``experiments/slam_map_new.py:207-263`` — a second, uncorrected path integrator and
+    a second Voja + PES memory mapping landmark locations back to landmark SPs, with that script's probes."""
     space = make_space(domain_dim, ssp_dim, length_scale)
     d = space.ssp_dim
     lm_space = SPSpace(n_landmarks, d, seed=seed)
@@ -160,6 +162,29 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
             nengo.Connection(vel_in, slam.velocity_input, synapse=None)
         nengo.Connection(init, slam.pathintegrator.input, synapse=None)
         probe = nengo.Probe(slam.pathintegrator.output, synapse=0.05)
+        more = {}
+        if inverse_memory:
+            pi2 = networks.PathIntegration(space, pi_n_neurons, 0.05, scaling_factor=scale, stable=True,
+                                           solver_weights=False)
+            nengo.Connection(vel_in, pi2.velocity_input, synapse=None)
+            nengo.Connection(init, pi2.input, synapse=None)
+            inv = networks.AssociativeMemory(mem_n_neurons, d, d, 0.1, voja_learning_rate=5e-4, pes_learning_rate=1e-2,
+                                             voja=True, encoders=space.sample_grid_encoders(mem_n_neurons), radius=1.3)
+            nengo.Connection(slam.landmark_ssp_ens.output, inv.key_input, synapse=0.05)
+            nengo.Connection(lm_id, inv.value_input, synapse=None)
+            nengo.Connection(is_lm, inv.learning, synapse=None)
+            every = n_steps * dt
+            more = dict(pathintegrator2=pi2, invassomemory=inv,
+                        ssp_pi_p=nengo.Probe(pi2.output, synapse=0.05),
+                        newpos_p=nengo.Probe(slam.position_estimate.output, synapse=0.05),
+                        objssp_p=nengo.Probe(slam.landmark_ssp_ens.output, synapse=0.05),
+                        recall_p=nengo.Probe(slam.assomemory.recall, synapse=0.05),
+                        isitem_p=nengo.Probe(is_lm, synapse=None),
+                        mem_weights=nengo.Probe(slam.assomemory.conn_out, "weights", sample_every=every / 2),
+                        meminv_weights=nengo.Probe(inv.conn_out, "weights", sample_every=every),
+                        mem_encoders=nengo.Probe(slam.assomemory.conn_in.learning_rule, "scaled_encoders",
+                                                 sample_every=every / 2),
+                        meminv_encoders=nengo.Probe(inv.conn_in.learning_rule, "scaled_encoders", sample_every=every))
         wprobe = None
         if weights_probe:
             wprobe = nengo.Probe(slam.assomemory.conn_out, "weights", sample_every=n_steps * dt)
@@ -175,4 +200,5 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
                  path=tile(syn_paths), vels_scaled=tile(syn_vels), landmarks=tile(syn_lms), lm_vectors=lm_space.vectors,
                  view_rad=view_rad, none_in_view_value=1.0 if view else 10.0)
     return Scenario(model, probe, trial_inputs, space, paths, ssps,
-                    dict(slam=slam, vel_scale=scale, weights_probe=wprobe, lm_space=lm_space, input_synthesis=synth), dt)
+                    dict(slam=slam, vel_scale=scale, weights_probe=wprobe, lm_space=lm_space, input_synthesis=synth,
+                         **more), dt)

@@ -478,3 +478,26 @@ def test_slam_loihi_variant_matches_oracle():
         want = _oracle(sc, sim, trial, n_steps).data[sc.probe]
         assert np.max(np.abs(want)) > 0.1
         assert _rel(got[trial], want) < 1e-4
+
+
+def test_inverse_memory_topology_matches_oracle():
+    """experiments/slam_map_new.py:207-263 — a second path integrator and a second Voja + PES memory on the
+    same kernels (two PES rules, two Voja rules), with that script's decoded / node / weights / scaled_encoders probes."""
+    n_steps = 128
+    sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=80, mem_n_neurons=160,
+                             circonv_n_neurons=24, n_landmarks=12, T=20.0, neuron_type="lifrate", view_rad=0.5,
+                             inverse_memory=True)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        assert len(sim.plan.arrays["pes"]) == 2
+        sim.run_steps(n_steps)
+    x = sc.extra
+    assert sim.data[x["mem_weights"]].shape == (3, 2, 55, 160) and sim.data[x["meminv_encoders"]].shape == (3, 1, 160, 55)
+    for trial in (0, 2):
+        ref = _oracle(sc, sim, trial, n_steps)
+        for name in ("ssp_pi_p", "newpos_p", "objssp_p", "recall_p", "isitem_p"):
+            assert _rel(sim.data[x[name]][trial], ref.data[x[name]]) < 1e-4, name
+        assert _rel(sim.data[sc.probe][trial], ref.data[sc.probe]) < 1e-4
+        for name in ("mem_weights", "meminv_weights", "mem_encoders", "meminv_encoders"):
+            want = ref.data[x[name]]
+            assert np.max(np.abs(want)) > 0
+            assert _rel(sim.data[x[name]][trial], want) < 1e-4, name

@@ -153,3 +153,23 @@ def test_slam_loihi_plan_matches_oracle():
     plan, *_ = _compare(sc, 60)
     assert plan.stats["n_big"] == 4          # memory, recall, PES error, correction
     assert not plan.arrays["cleanup"].size and not plan.arrays["gate"].size     # no node functions: the gate is neural
+
+
+def test_inverse_memory_topology_plan_matches_oracle():
+    """experiments/slam_map_new.py:207-263 — two path integrators, two Voja + PES memories, and that
+    script's probes (decoded ensemble output, node, weights, scaled_encoders)."""
+    n = 60
+    sc = scenarios.make_slam(n_trials=1, n_steps=n, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=48, circonv_n_neurons=12,
+                             n_landmarks=6, T=20.0, neuron_type="lifrate", view_rad=0.5, grid_points_per_dim=12,
+                             inverse_memory=True)
+    plan, model, ref, it = _compare(sc, n)
+    d = sc.ssp_space.ssp_dim
+    assert len(plan.arrays["pes"]) == 2 and plan.stats["n_learned"] == 2 * (48 * d + 48 * d)
+    for name in ("ssp_pi_p", "newpos_p", "objssp_p", "recall_p", "isitem_p"):
+        probe = sc.extra[name]
+        info = [i for i in plan.probes if i.probe is probe][0]
+        got, want = it.probe_data(info), ref.data[probe]
+        assert got.shape == want.shape
+        assert np.max(np.abs(got - want)) <= 2e-5 * max(1e-3, np.max(np.abs(want)))
+    kinds = sorted(i.kind for i in plan.probes)
+    assert kinds.count("weights") == 2 and kinds.count("scaled_encoders") == 2
