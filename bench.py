@@ -67,19 +67,37 @@ def slam_scenario(n_trials, n_steps, seed, distinct):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """nvidia-smi sampling loop.  It is started BEFORE the warm-up steps (process start-up on an 8-GPU box takes longer
+    than a short timed region) and waits for its first sample; the timed regions are registered with ``window`` and only
+    samples whose timestamp falls inside one are used (all samples under load if the regions were shorter than a period)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.windows = []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < 5.0 and os.path.getsize(self.tmp.name) == 0:
+            time.sleep(0.02)
+
+    def window(self, t_start, t_end):
+        self.windows.append((t_start, t_end))
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -92,25 +110,28 @@ class ClockSampler:
             self.proc.kill()
         self.tmp.flush()
         self.tmp.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.tmp.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                sm, mx = float(parts[0]), float(parts[1])
             except ValueError:
                 continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+            stamp = self._stamp(parts[7]) if len(parts) > 7 else None
+            rows.append((stamp, sm, mx, {n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")}))
         self.tmp.close()
         os.unlink(self.tmp.name)
-        if sm:
+        inside = [r for r in rows if r[0] is not None and any(a - 0.05 <= r[0] <= b + 0.05 for a, b in self.windows)]
+        use = inside or rows          # regions shorter than one sampling period: every sample was taken under load
+        if use:
+            sm = [r[1] for r in use]
             busy = [x for x in sm if x > 0.5 * max(sm)] or sm
-            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            reasons = set().union(*[r[3] for r in use])
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(r[2] for r in use)), reasons=sorted(reasons),
+                       samples=len(use), samples_in_timed_regions=len(inside))
         return out
 
 
@@ -246,16 +267,18 @@ def run_b200(args):
 
     # ---------------- value: every table of the phase is resident in HBM before the timed region
     sim.load_tables(0, n_phase)
+    clocks = ClockSampler(local)
     for _ in range(W):
         sim.run_resident(chunk)
     barrier()
-    clocks = ClockSampler(local)
     launches0 = sim.total_launches()
+    t_wall = time.time()
     sim.mark(0)
     for _ in range(K):
         sim.run_resident(chunk)
     sim.mark(1)
     barrier()
+    clocks.window(t_wall, time.time())
     value_ms = max_over_ranks(sim.mark_elapsed_ms(0, 1))
     launches = sim.total_launches() - launches0
 
@@ -265,11 +288,13 @@ def run_b200(args):
     for _ in range(W):
         sim.run_steps(chunk)
     barrier()
+    t_wall = time.time()
     sim.mark(2)
     for _ in range(K):
         sim.run_steps(chunk)
     sim.mark(3)
     barrier()
+    clocks.window(t_wall, time.time())
     e2e_ms = max_over_ranks(sim.mark_elapsed_ms(2, 3))
     clock_info = clocks.stop()
 
