@@ -82,3 +82,16 @@ def slam_tables(encode, lm_vectors, vels_scaled, vec_to_landmarks, view_rad, n_s
     if real_ssp is not None:
         out["init"] = np.where((t < init_time)[:, None], real_ssp[i_prev], 0.0)
     return out
+
+
+def sparsity_to_x_intercept(d, p):
+    """Intercept at which a neuron with a unit encoder in ``d`` dimensions is active for a fraction ``p`` of the points of
+    the unit sphere (``sspslam/utils/utils.py:5-10``): the cap with relative area p has cos(angle) = sqrt(1 - I^-1), with
+    I the regularised incomplete beta function of ((d-1)/2, 1/2)."""
+    from scipy.special import betaincinv
+    flip = p > 0.5
+    if flip:
+        p = 1.0 - p
+    x = np.sqrt(1.0 - betaincinv((d - 1) / 2.0, 0.5, 2.0 * p))
+    return -x if flip else x
+

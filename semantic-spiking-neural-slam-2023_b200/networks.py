@@ -134,8 +134,6 @@ class PathIntegration(Network):
                  max_radius=1, with_gcs=False, n_gcs=1000, solver_weights=False, label="pathint",
                  **ens_kwargs):
         super().__init__(label=label)
-        if with_gcs:
-            raise NotImplementedError("with_gcs output population is outside the hot path (SURVEY.md §8f-4)")
         d, n_dom = ssp_space.ssp_dim, ssp_space.domain_dim
         n_osc = (d + 1) // 2
         if callable(stable):
@@ -148,7 +146,13 @@ class PathIntegration(Network):
         with self:
             self.velocity_input = Node(size_in=n_dom, label=label + "_vel_input")
             self.input = Node(size_in=d, label=label + "_input")
-            self.output = Node(size_in=d, label=label + "_output")
+            if with_gcs:    # pathintegration.py:150-154: the SSP is represented by a grid-cell population
+                from .inputs import sparsity_to_x_intercept
+                self.output = Ensemble(n_gcs, d, encoders=ssp_space.sample_grid_encoders(n_gcs),
+                                       intercepts=nengo.dists.Choice([sparsity_to_x_intercept(d, 0.1)]),
+                                       label=label + "_output")
+            else:
+                self.output = Node(size_in=d, label=label + "_output")
             self.oscillators = EnsembleArray(n_neurons, n_osc, ens_dimensions=3, radius=np.sqrt(2),
                                              label=label + "_vco", **ens_kwargs)
             self.oscillators.output.output = Identity()

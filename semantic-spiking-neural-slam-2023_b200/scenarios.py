@@ -35,7 +35,7 @@ def make_space(domain_dim=2, ssp_dim=55, length_scale=0.2, radius=1.0, backend="
 
 
 def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0, limit=0.1, seed=0,
-                 neuron_type="lif", dt=0.001, tau=0.05):
+                 neuron_type="lif", dt=0.001, tau=0.05, with_gcs=False, n_gcs=1000):
     """``run_pathint.py`` workload; trial i uses path seed ``seed + 1000*i``."""
     space = make_space(2, ssp_dim)
     d = space.ssp_dim
@@ -59,7 +59,7 @@ def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0,
         vel_in = nengo.Node(lambda t: vel0[int(round(t / dt)) - 1], label="vel_input")
         init = nengo.Node(lambda t: init0[int(round(t / dt)) - 1], label="init_state")
         pi = networks.PathIntegration(space, pi_n_neurons, tau, scaling_factor=scale, stable=True,
-                                      solver_weights=False)
+                                      solver_weights=False, with_gcs=with_gcs, n_gcs=n_gcs)
         nengo.Connection(vel_in, pi.velocity_input, synapse=None)
         nengo.Connection(init, pi.input, synapse=None)
         probe = nengo.Probe(pi.output, synapse=0.05)

@@ -501,3 +501,19 @@ def test_inverse_memory_topology_matches_oracle():
             want = ref.data[x[name]]
             assert np.max(np.abs(want)) > 0
             assert _rel(sim.data[x[name]][trial], want) < 1e-4, name
+
+
+def test_pathintegration_with_grid_cell_output_matches_oracle():
+    """pathintegration.py:150-154 (``with_gcs=True``): the VCO array drives a grid-cell output population whose decoded,
+    filtered output is probed."""
+    n_steps = 200
+    sc = scenarios.make_pathint(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=200, neuron_type="lifrate",
+                                with_gcs=True, n_gcs=400)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        assert sim.plan.stats["n_big"] == 1
+        sim.run_steps(n_steps)
+    got = sim.data[sc.probe]
+    for trial in (0, 2):
+        want = _oracle(sc, sim, trial, n_steps).data[sc.probe]
+        assert np.max(np.abs(want)) > 0.05
+        assert _rel(got[trial], want) < 1e-4

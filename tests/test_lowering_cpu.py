@@ -173,3 +173,11 @@ def test_inverse_memory_topology_plan_matches_oracle():
         assert np.max(np.abs(got - want)) <= 2e-5 * max(1e-3, np.max(np.abs(want)))
     kinds = sorted(i.kind for i in plan.probes)
     assert kinds.count("weights") == 2 and kinds.count("scaled_encoders") == 2
+
+
+def test_pathint_with_grid_cell_output_plan_matches_oracle():
+    """pathintegration.py:150-154 (``with_gcs=True``): the probed output is a decoded grid-cell population."""
+    sc = scenarios.make_pathint(n_trials=1, n_steps=80, ssp_dim=19, pi_n_neurons=40, neuron_type="lifrate",
+                                with_gcs=True, n_gcs=64)
+    plan, *_ = _compare(sc, 80)
+    assert plan.stats["n_big"] == 1

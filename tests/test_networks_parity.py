@@ -168,3 +168,25 @@ def test_slam_loihi_network_matches_reference():
     owners = [nb] + nb.all_networks     # no clean-up / gate node functions in this variant, only the PI pass-through
     assert [nodeops.recognize(n, owners).kind for n in nb.all_nodes if callable(n.output) and n.size_in > 0] == ["identity"]
     np.testing.assert_allclose(np.asarray(sa.assomemory.memory.encoders), np.asarray(sb.assomemory.memory.encoders))
+
+
+def test_pathintegration_with_grid_cell_output_matches_reference():
+    """pathintegration.py:150-154: ``with_gcs=True`` — the output node becomes a grid-cell population whose intercept comes
+    from ``sparsity_to_x_intercept`` (sspslam/utils/utils.py:5-10)."""
+    ref = _ref()
+    from sspslam_b200.inputs import sparsity_to_x_intercept
+    for d, p in ((7, 0.1), (55, 0.1), (19, 0.7)):
+        assert sparsity_to_x_intercept(d, p) == pytest.approx(ref.utils.sparsity_to_x_intercept(d, p), abs=1e-15)
+    nets = []
+    for mod, space_cls in ((networks, HexagonalSSPSpace), (ref.networks, ref.HexagonalSSPSpace)):
+        kw = dict(backend="host") if space_cls is HexagonalSSPSpace else {}
+        sp = space_cls(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2, rng=np.random.default_rng(5), **kw)
+        with nengo.Network(seed=4) as net:
+            pi = mod.PathIntegration(sp, 40, 0.05, scaling_factor=0.7, stable=True, solver_weights=False,
+                                     with_gcs=True, n_gcs=64)
+            nengo.Probe(pi.output, synapse=0.05)
+        nets.append((net, pi))
+    (na, pa), (nb, pb) = nets
+    _assert_same_model(na, nb)
+    assert pa.output.n_neurons == 64
+    np.testing.assert_allclose(np.asarray(pa.output.encoders), np.asarray(pb.output.encoders), atol=1e-14)
