@@ -74,7 +74,7 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
               n_landmarks=50, view_rad=0.2, T=200.0, limit=0.1, seed=0, dt=0.001, length_scale=0.2,
               shift_rate=0.2, update_thres=0.2, neuron_type="lif", weights_probe=False, view=False,
               distinct_tables=None, domain_dim=2, grid_points_per_dim=100, gc_n_neurons=0, approx_vel=False,
-              vel_n_neurons=500, loihi=False, dotprod_n_neurons=50, inverse_memory=False):
+              vel_n_neurons=500, loihi=False, dotprod_n_neurons=50, inverse_memory=False, voja=True):
     """``run_slam.py`` (or ``run_slamview.py`` when ``view``) workload, batched over trials.
 
     ``distinct_tables``: synthesise only that many distinct trials' tables and tile them
@@ -146,7 +146,7 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
                                         circonv_n_neurons, tau_pi=0.05, update_thres=update_thres,
                                         vel_scaling_factor=scale, shift_rate=shift_rate, voja_learning_rate=1e-4,
                                         pes_learning_rate=5e-3, intercept=0.1, seed=seed,
-                                        grid_points_per_dim=grid_points_per_dim, gc_n_neurons=gc_n_neurons)
+                                        grid_points_per_dim=grid_points_per_dim, gc_n_neurons=gc_n_neurons, voja=voja)
             nengo.Connection(lm_vec, slam.landmark_vec_ssp, synapse=None)
             nengo.Connection(lm_id, slam.landmark_id_input, synapse=None)
             table_nodes = {"vel": vel_in, "init": init, "lm_sp": lm_id, "nolm": is_lm, "lmvec_ssp": lm_vec}

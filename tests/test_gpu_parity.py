@@ -517,3 +517,16 @@ def test_pathintegration_with_grid_cell_output_matches_oracle():
         want = _oracle(sc, sim, trial, n_steps).data[sc.probe]
         assert np.max(np.abs(want)) > 0.05
         assert _rel(got[trial], want) < 1e-4
+
+
+def test_slam_without_voja_matches_oracle():
+    """run_slam.py --no-voja: fixed landmark encoders (slam.py:196-198); only the PES decoders are learned."""
+    n_steps = 120
+    sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=80, mem_n_neurons=160,
+                             circonv_n_neurons=24, n_landmarks=12, T=20.0, neuron_type="lifrate", view_rad=0.5, voja=False)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        assert sim.plan.stats["n_learned"] == 160 * 55
+        sim.run_steps(n_steps)
+    got = sim.data[sc.probe]
+    for trial in (0, 2):
+        assert _rel(got[trial], _oracle(sc, sim, trial, n_steps).data[sc.probe]) < 1e-4

@@ -181,3 +181,12 @@ def test_pathint_with_grid_cell_output_plan_matches_oracle():
                                 with_gcs=True, n_gcs=64)
     plan, *_ = _compare(sc, 80)
     assert plan.stats["n_big"] == 1
+
+
+def test_slam_without_voja_plan_matches_oracle():
+    """run_slam.py --no-voja (slam.py:196-198): fixed landmark encoders, the memory becomes a static wide ensemble."""
+    sc = scenarios.make_slam(n_trials=1, n_steps=60, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=48, circonv_n_neurons=12,
+                             n_landmarks=6, T=20.0, neuron_type="lifrate", view_rad=0.5, grid_points_per_dim=12, voja=False)
+    plan, *_ = _compare(sc, 60)
+    d = sc.ssp_space.ssp_dim
+    assert plan.stats["n_learned"] == 48 * d          # only the PES decoders are per trial

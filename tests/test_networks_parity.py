@@ -190,3 +190,23 @@ def test_pathintegration_with_grid_cell_output_matches_reference():
     _assert_same_model(na, nb)
     assert pa.output.n_neurons == 64
     np.testing.assert_allclose(np.asarray(pa.output.encoders), np.asarray(pb.output.encoders), atol=1e-14)
+
+
+def test_slam_network_without_voja_matches_reference():
+    """run_slam.py --no-voja: the memory encoders are landmark SPs drawn with RandomState(seed) (slam.py:196-198)."""
+    ref = _ref()
+    space = HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2, backend="host")
+    rspace = ref.HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2)
+    lm, rlm = SPSpace(6, space.ssp_dim, seed=2), ref.SPSpace(6, rspace.ssp_dim, seed=2)
+    nets = []
+    for mod, sp, l in ((networks, space, lm), (ref.networks, rspace, rlm)):
+        np.random.seed(9)
+        with nengo.Network(seed=4) as net:
+            slam = mod.SLAMNetwork(sp, l, 0.2, 6, 30, 64, 16, tau_pi=0.05, update_thres=0.2, vel_scaling_factor=0.7,
+                                   shift_rate=0.2, pes_learning_rate=5e-3, intercept=0.1, voja=False, seed=5)
+            nengo.Probe(slam.pathintegrator.output, synapse=0.05)
+        nets.append((net, slam))
+    (na, sa), (nb, sb) = nets
+    _assert_same_model(na, nb)
+    assert not [c for c in na.all_connections if c.learning_rule is not None
+                and isinstance(c.learning_rule.learning_rule_type, nengo.Voja)]
