@@ -95,3 +95,127 @@ def sparsity_to_x_intercept(d, p):
     x = np.sqrt(1.0 - betaincinv((d - 1) / 2.0, 0.5, 2.0 * p))
     return -x if flip else x
 
+
+class _SlamInputs:
+    """Per-path lookups behind the node callables of ``get_slam_input_functions`` / ``get_slam_input_functions2``.
+
+    The in-view masks and nearest-landmark ids of the whole path are computed once (vectorised); the callables only
+    index them with the reference's two time -> row rules: ``int((t-dt)/dt)`` for the velocity, the in-view set, the
+    landmark SP and the displacement vector, and ``min(floor(t/dt), pathlen-2)`` for the displacement that is SSP-encoded
+    (slam.py:393,408,434 / :452,457,485)."""
+
+    def __init__(self, ssp_space, lm_space, velocity_data, vec_to_landmarks_data, view_rad, dt, superpose):
+        self.space, self.dt, self.superpose = ssp_space, dt, superpose
+        self.vec = np.asarray(vec_to_landmarks_data, dtype=np.float64)
+        self.pathlen, _, self.domain_dim = self.vec.shape
+        self.d = ssp_space.ssp_dim
+        self.lm = np.asarray(lm_space.vectors, dtype=np.float64)
+        self.scale = velocity_scale(ssp_space.phase_matrix, velocity_data)
+        self.vels_scaled = np.asarray(velocity_data) * self.scale
+        dists = np.linalg.norm(self.vec, axis=2)
+        self.in_view = dists <= view_rad
+        self.any_view = self.in_view.any(axis=1)
+        self.nearest = np.argmin(dists, axis=1)
+        self.encode = getattr(ssp_space, "encode_host", ssp_space.encode)
+
+    def prev(self, t):
+        return int((t - self.dt) / self.dt)
+
+    def cur(self, t):
+        return int(np.minimum(np.floor(t / self.dt), self.pathlen - 2))
+
+    def ids(self, t):
+        i = self.prev(t)
+        if not self.any_view[i]:
+            return None if self.superpose else -1
+        return np.where(self.in_view[i])[0] if self.superpose else self.nearest[i]
+
+    def _members(self, t):
+        i = self.prev(t)
+        if not self.any_view[i]:
+            return np.zeros(0, dtype=int)
+        return np.where(self.in_view[i])[0] if self.superpose else self.nearest[i:i + 1]
+
+    def velocity(self, t):
+        return self.vels_scaled[self.prev(t)]
+
+    def vec_to(self, t):
+        return self.vec[self.prev(t), self._members(t)].sum(axis=0) if self.any_view[self.prev(t)] else np.zeros(self.domain_dim)
+
+    def sp(self, t):
+        m = self._members(t)
+        return self.lm[m].sum(axis=0) if len(m) else np.zeros(self.d)
+
+    def vec_ssp(self, t):
+        m = self._members(t)
+        if not len(m):
+            return np.zeros(self.d)
+        return np.asarray(self.encode(self.vec[self.cur(t), m])).reshape(len(m), -1).sum(axis=0)
+
+    def none_in_view(self, t):
+        return 0 if self.any_view[self.prev(t)] else 10
+
+    def functions(self):
+        return (self.velocity, self.scale, self.none_in_view, self.ids, self.sp, self.vec_to, self.vec_ssp)
+
+
+def get_slam_input_functions(ssp_space, lm_space, velocity_data, vec_to_landmarks_data, view_rad, dt=0.001):
+    """Node callables for recorded data, nearest in-view landmark only (``sspslam/networks/slam.py:312-440``).  Returns
+    ``(velocity_func, vel_scaling_factor, is_landmark_in_view, landmark_id_func, landmark_sp_func, landmark_vec_func,
+    landmark_vecssp_func)`` — ``is_landmark_in_view`` is 10 when NO landmark is in view, as in the reference."""
+    return _SlamInputs(ssp_space, lm_space, velocity_data, vec_to_landmarks_data, view_rad, dt, False).functions()
+
+
+def get_slam_input_functions2(ssp_space, lm_space, velocity_data, vec_to_landmarks_data, view_rad, dt=0.001):
+    """Same, with every in-view landmark superposed (``slam.py:442-497``; what ``run_slam.py:139-141`` uses).
+    ``slam_tables`` is the batched table form of the same arithmetic."""
+    return _SlamInputs(ssp_space, lm_space, velocity_data, vec_to_landmarks_data, view_rad, dt, True).functions()
+
+
+def slamview_tables(ssp_space, lm_vectors, vels_scaled, vec_to_landmarks, view_rad, n_steps, dt=0.001, step0=0):
+    """Batched table form of ``get_slamview_input_functions`` (``slam_view.py:352-403``): the local view is the normalised
+    sum over in-view landmarks of ``SP_l (*) encode(displacement_l)``.  Note the index rules are the opposite of the SLAM
+    variant: velocity and the in-view set (strict ``<``) use ``min(floor(t/dt), pathlen-2)``, the displacement
+    ``int((t-dt)/dt)``; the none-in-view flag is 1, not 10."""
+    vec = np.asarray(vec_to_landmarks, dtype=np.float64)
+    _, i_prev, i_cur = step_indices(n_steps, dt, vec.shape[0], step0)
+    d = lm_vectors.shape[1]
+    in_view = np.linalg.norm(vec[i_cur], axis=2) < view_rad
+    steps, ids = np.nonzero(in_view)
+    view = np.zeros((n_steps, d))
+    if len(steps):
+        encode = getattr(ssp_space, "encode_host", ssp_space.encode)
+        ssps = np.asarray(encode(vec[i_prev[steps], ids])).reshape(len(steps), d)
+        bound = np.fft.ifft(np.fft.fft(np.asarray(lm_vectors)[ids], axis=1) * np.fft.fft(ssps, axis=1), axis=1).real
+        np.add.at(view, steps, bound)
+    norm = np.linalg.norm(view, axis=1, keepdims=True)
+    view = np.where(norm > 1e-8, view / np.maximum(norm, 1e-300), view)
+    return {"vel": np.asarray(vels_scaled)[i_cur], "view": view,
+            "nolm": np.where(in_view.any(axis=1), 0.0, 1.0)[:, None]}
+
+
+def get_slamview_input_functions(ssp_space, lm_space, velocity_data, vec_to_landmarks_data, view_rad, dt=0.001):
+    """Node callables of the local-view variant (``sspslam/networks/slam_view.py:281-404``): returns
+    ``(velocity_func, vel_scaling_factor, is_landmark_in_view, landmark_func)``."""
+    vec = np.asarray(vec_to_landmarks_data, dtype=np.float64)
+    pathlen, d = vec.shape[0], ssp_space.ssp_dim
+    lm = np.asarray(lm_space.vectors, dtype=np.float64)
+    scale = velocity_scale(ssp_space.phase_matrix, velocity_data)
+    vels_scaled = np.asarray(velocity_data) * scale
+    in_view = np.linalg.norm(vec, axis=2) < view_rad
+    encode = getattr(ssp_space, "encode_host", ssp_space.encode)
+
+    def cur(t):
+        return int(np.minimum(np.floor(t / dt), pathlen - 2))
+
+    def landmark_func(t):
+        ids = np.where(in_view[cur(t)])[0]
+        out = np.zeros(d)
+        if len(ids):
+            ssps = np.asarray(encode(vec[int((t - dt) / dt), ids])).reshape(len(ids), d)
+            out = np.fft.ifft(np.fft.fft(lm[ids], axis=1) * np.fft.fft(ssps, axis=1), axis=1).real.sum(axis=0)
+        norm = np.linalg.norm(out)
+        return out / norm if norm > 1e-8 else out
+
+    return (lambda t: vels_scaled[cur(t)]), scale, (lambda t: 0 if in_view[cur(t)].any() else 1), landmark_func
+

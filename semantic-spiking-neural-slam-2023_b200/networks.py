@@ -26,9 +26,12 @@ from .nengo_shim import Network, Node, Ensemble, Connection
 from .nengo_shim.networks import EnsembleArray
 from .nengo_shim.params import Default
 from .nodeops import Identity, GridCleanup, GatedCorrection
+from .inputs import (get_slam_input_functions, get_slam_input_functions2,      # re-exported like sspslam.networks does
+                     get_slamview_input_functions)
 
 __all__ = ["PathIntegration", "Product", "CircularConvolution", "AssociativeMemory", "SLAMNetwork",
-           "SLAMViewNetwork", "SLAMLoihiNetwork", "get_to_Fourier", "get_from_Fourier", "transform_in", "transform_out",
+           "SLAMViewNetwork", "SLAMLoihiNetwork", "get_slam_input_functions", "get_slam_input_functions2", "get_slamview_input_functions",
+           "get_to_Fourier", "get_from_Fourier", "transform_in", "transform_out",
            "dft_half", "circconv", "oscillator_feedback"]
 
 

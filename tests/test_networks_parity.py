@@ -210,3 +210,58 @@ def test_slam_network_without_voja_matches_reference():
     _assert_same_model(na, nb)
     assert not [c for c in na.all_connections if c.learning_rule is not None
                 and isinstance(c.learning_rule.learning_rule_type, nengo.Voja)]
+
+
+@pytest.mark.parametrize("name", ["get_slam_input_functions", "get_slam_input_functions2"])
+def test_slam_input_function_closures_match_reference(name):
+    """The node callables handed to nengo.Node by the drivers (run_slam.py:139-141,164-169), at step times and between."""
+    ref = _ref()
+    dt = 0.001
+    space = HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2, backend="host")
+    rspace = ref.HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2)
+    lm, rlm = SPSpace(8, space.ssp_dim, seed=2), ref.SPSpace(8, rspace.ssp_dim, seed=2)
+    path = inputs.random_path(20.0, dt, 0.3, 3, 2)[:2000]
+    vels = inputs.velocities(path, dt)
+    obj = 1.8 * (inputs.rd_sampling(8, 2, seed=3) - 0.5)
+    vec_to = obj[None, :, :] - path[:, None, :]
+    mine = getattr(networks, name)(space, lm, vels, vec_to, 0.45, dt)
+    theirs = getattr(ref.networks.slam, name)(rspace, rlm, vels, vec_to, 0.45, dt)
+    assert mine[1] == pytest.approx(theirs[1], rel=1e-15)
+    seen = set()
+    times = np.concatenate([dt * np.arange(1, 1500, 7), np.random.default_rng(0).uniform(dt, 1.9, 100)])
+    for t in times:
+        for k in (0, 2, 4, 5, 6):
+            np.testing.assert_allclose(np.asarray(mine[k](t), dtype=float), np.asarray(theirs[k](t), dtype=float),
+                                       rtol=0, atol=1e-12)
+        a, b = mine[3](t), theirs[3](t)
+        assert (a is None and b is None) or np.array_equal(a, b)
+        seen.add(0 if mine[2](t) else (1 if np.size(a) == 1 else 2))
+    assert seen >= {0, 1} and (name.endswith("functions") or 2 in seen)    # none / one / several landmarks in view
+
+
+def test_slamview_input_functions_and_tables_match_reference():
+    """slam_view.py:281-404: the local-view closures, and their batched table form, against the reference closures."""
+    ref = _ref()
+    dt = 0.001
+    space = HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2, backend="host")
+    rspace = ref.HexagonalSSPSpace(2, ssp_dim=19, domain_bounds=BOUNDS2, length_scale=0.2)
+    lm, rlm = SPSpace(8, space.ssp_dim, seed=2), ref.SPSpace(8, rspace.ssp_dim, seed=2)
+    path = inputs.random_path(20.0, dt, 0.3, 3, 2)[:2000]
+    vels = inputs.velocities(path, dt)
+    obj = 1.8 * (inputs.rd_sampling(8, 2, seed=3) - 0.5)
+    vec_to = obj[None, :, :] - path[:, None, :]
+    mine = networks.get_slamview_input_functions(space, lm, vels, vec_to, 0.45, dt)
+    theirs = ref.networks.slam_view.get_slamview_input_functions(rspace, rlm, vels, vec_to, 0.45, dt)
+    assert mine[1] == pytest.approx(theirs[1], rel=1e-15)
+    n = 1500
+    tb = inputs.slamview_tables(space, lm.vectors, vels * mine[1], vec_to, 0.45, n, dt)
+    flags = set()
+    for k in range(1, n + 1, 3):
+        t = k * dt
+        for i in (0, 2, 3):
+            np.testing.assert_allclose(np.asarray(mine[i](t), dtype=float), np.asarray(theirs[i](t), dtype=float), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(tb["vel"][k - 1], theirs[0](t), rtol=0, atol=1e-15)
+        np.testing.assert_allclose(tb["view"][k - 1], theirs[3](t), rtol=0, atol=1e-12)
+        assert tb["nolm"][k - 1, 0] == theirs[2](t)
+        flags.add(theirs[2](t))
+    assert flags == {0, 1}
