@@ -799,6 +799,26 @@ struct SsbItemList {
 
 __device__ __forceinline__ int ssb_r4(int x) { return (x + 3) & ~3; }
 
+// Input rows of a wide ensemble -> shared memory [dpad][32].  Each warp takes every nwarps-th row, eight rows per batch
+// so that the (L2-resident) loads of a batch are in flight together instead of one dependent load per store.
+__device__ __forceinline__ void ssb_stage_rows(float* xs, const float* vg, int row0, int dims, int dpad, int warp,
+                                               int nwarps, int lane) {
+    for (int k0 = warp; k0 < dpad; k0 += nwarps * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * nwarps;
+            v[u] = (k < dims) ? vg[(size_t)(row0 + k) * 32] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * nwarps;
+            if (k < dpad) xs[k * 32 + lane] = v[u];
+        }
+    }
+}
+
+
 template <int DP>
 __global__ void __launch_bounds__(128) k_wide_static(SsbCtx c, const int* __restrict__ desc, SsbItemList items, int chunk,
                                                       int i_rel) {
@@ -833,7 +853,7 @@ __global__ void __launch_bounds__(128) k_wide_static(SsbCtx c, const int* __rest
         if (stateful) ssb_bulk_g2s(s_st, stg, b_st, &bar);
     }
     const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    for (int k = warp; k < dpad; k += 4) xs[k * 32 + lane] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
+    ssb_stage_rows(xs, vg, in_row0, dims, dpad, warp, 4, lane);
     for (int m = warp; m < jn_m; m += 4) us[m * 32 + lane] = vg[(size_t)(jn_row0 + m) * 32];
     __syncthreads();                 // xs / us complete, barrier initialised for every thread
     ssb_mbar_wait(&bar, 0);
@@ -1125,24 +1145,35 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
         }
     }
     const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    for (int k = warp; k < dpad; k += nwarps) xs[k * 32 + lane] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
+    float x[DP > 0 ? DP : 1];
+    if (DP > 0) {       // the input rows go straight to registers: DP independent L2 loads per lane, no shared-memory hop
+#pragma unroll
+        for (int k = 0; k < DP; ++k) x[k] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
+    } else {
+        ssb_stage_rows(xs, vg, in_row0, dims, dpad, warp, nwarps, lane);
+    }
     for (int m = warp; m < jn_m; m += nwarps) us[m * 32 + lane] = vg[(size_t)(jn_row0 + m) * 32];
     const float aL = __int_as_float(d[15]) * vg[(size_t)voja_row * 32];
     __syncthreads();
-    float x[DP > 0 ? DP : 1];
-    if (DP > 0) {
-#pragma unroll
-        for (int k = 0; k < DP; ++k) x[k] = xs[k * 32 + lane];
-    }
     float* sp = ssb_grp(c.st, c.nn, g, lane) + (size_t)(state0 + n0) * 32;
     float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)(act0 + n0) * 32;
     uint32_t phases = 0;
+    // the state row (HBM) and the bias of neuron i + 1 are requested while neuron i is computed: eight warps per SM do
+    // not hide one memory round trip per neuron
+    float sv_next = 0.f, bias_next = 0.f;
+    if (i_lo < i_hi) {
+        if (stateful) sv_next = __ldcs(sp + (size_t)i_lo * 32);
+        bias_next = __ldg(c.W + bias_off + n0 + i_lo);
+    }
     for (int i = i_lo; i < i_hi; ++i) {
         const int t = i - i_lo, b = t % nb;
         float* E = ebuf + (size_t)b * dims * 32 + lane;
-        float sv = 0.f;
-        if (stateful) sv = __ldcs(sp + (size_t)i * 32);
-        float J = __ldg(c.W + bias_off + n0 + i);
+        float sv = sv_next;
+        float J = bias_next;
+        if (i + 1 < i_hi) {
+            if (stateful) sv_next = __ldcs(sp + (size_t)(i + 1) * 32);
+            bias_next = __ldg(c.W + bias_off + n0 + i + 1);
+        }
         for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + (n0 + i) * jn_m + m), us[m * 32 + lane], J);
         ssb_mbar_wait(&wbar[warp][b], (phases >> b) & 1u);   // phases: one parity bit per buffer
         phases ^= 1u << b;
