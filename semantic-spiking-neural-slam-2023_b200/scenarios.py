@@ -74,14 +74,17 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
               n_landmarks=50, view_rad=0.2, T=200.0, limit=0.1, seed=0, dt=0.001, length_scale=0.2,
               shift_rate=0.2, update_thres=0.2, neuron_type="lif", weights_probe=False, view=False,
               distinct_tables=None, domain_dim=2, grid_points_per_dim=100, gc_n_neurons=0, approx_vel=False,
-              vel_n_neurons=500, loihi=False, dotprod_n_neurons=50, inverse_memory=False, voja=True):
+              vel_n_neurons=500, loihi=False, dotprod_n_neurons=50, inverse_memory=False, voja=True, view_bound=False):
     """``run_slam.py`` (or ``run_slamview.py`` when ``view``) workload, batched over trials.
 
     ``distinct_tables``: synthesise only that many distinct trials' tables and tile them
     over the batch (bench warm-up economy); state/voltages still differ per trial.
     ``loihi``: the all-neural ``SLAMLoihiNetwork`` with the driver's arguments of ``run_slam.py:171-176``.
     ``inverse_memory``: the topology of ``experiments/slam_map_new.py:207-263`` — a second, uncorrected path integrator and
-    a second Voja + PES memory mapping landmark locations back to landmark SPs, with that script's probes."""
+    a second Voja + PES memory mapping landmark locations back to landmark SPs, with that script's probes.
+    ``view_bound`` (with ``view``): feed the local view of ``run_slamview.py:103,123-130`` — the normalised sum of
+    ``SP_l (*) encode(displacement_l)`` with that driver's index rules (``inputs.slamview_tables``) — instead of the SP sum;
+    tables only (the on-device input synthesis evaluates the SP-sum form)."""
     space = make_space(domain_dim, ssp_dim, length_scale)
     d = space.ssp_dim
     lm_space = SPSpace(n_landmarks, d, seed=seed)
@@ -98,9 +101,13 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
         obj_locs = 1.8 * (inputs.rd_sampling(n_landmarks, domain_dim, seed=s_i) - 0.5)
         vec_to_lm = obj_locs[None, :, :] - path[:, None, :]
         real = space.encode_host(path)
-        if view:
-            # run_slamview.py feeds a local-view vector; here: superposed landmark SPs bound with
-            # their displacement SSPs would need the driver's view code — use the SP sum (key) directly
+        if view and view_bound:
+            vt = inputs.slamview_tables(space, lm_space.vectors, vels * scale, vec_to_lm, view_rad, n_steps, dt)
+            tb = inputs.slam_tables(space.encode_host, lm_space.vectors, vels * scale, vec_to_lm, view_rad, n_steps, dt,
+                                    real_ssp=real, none_in_view_value=1.0)
+            tb.update(vel=vt["vel"], lm_sp=vt["view"], nolm=vt["nolm"])
+        elif view:
+            # default: the superposed landmark SPs as the view key (what the on-device input synthesis evaluates)
             tb = inputs.slam_tables(space.encode_host, lm_space.vectors, vels * scale, vec_to_lm, view_rad, n_steps, dt,
                                     real_ssp=real, none_in_view_value=1.0)
         else:
@@ -199,6 +206,8 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
     synth = dict(nodes={k: table_nodes.get(k) for k in ("vel", "init", "lmvec_ssp", "lm_sp", "nolm")}, ssp_space=space,
                  path=tile(syn_paths), vels_scaled=tile(syn_vels), landmarks=tile(syn_lms), lm_vectors=lm_space.vectors,
                  view_rad=view_rad, none_in_view_value=1.0 if view else 10.0)
+    if view and view_bound:
+        synth = None
     return Scenario(model, probe, trial_inputs, space, paths, ssps,
                     dict(slam=slam, vel_scale=scale, weights_probe=wprobe, lm_space=lm_space, input_synthesis=synth,
                          **more), dt)

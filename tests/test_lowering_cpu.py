@@ -190,3 +190,15 @@ def test_slam_without_voja_plan_matches_oracle():
     plan, *_ = _compare(sc, 60)
     d = sc.ssp_space.ssp_dim
     assert plan.stats["n_learned"] == 48 * d          # only the PES decoders are per trial
+
+
+def test_slamview_with_the_drivers_bound_view_input_matches_oracle():
+    """run_slamview.py:103,123-130: the view vector is the normalised sum of SP (*) SSP(displacement) (slam_view.py:384-394)."""
+    sc = scenarios.make_slam(n_trials=1, n_steps=60, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=64,
+                             circonv_n_neurons=16, n_landmarks=6, T=20.0, neuron_type="lifrate", view=True, view_rad=0.6,
+                             view_bound=True)
+    view = [arr for node, arr in sc.trial_inputs.items() if node.label == "lm_sp_input"][0][0]
+    norms = np.linalg.norm(view, axis=1)
+    assert np.all((np.abs(norms - 1.0) < 1e-9) | (norms == 0)) and norms.max() > 0     # unit view vectors when in view
+    assert sc.extra["input_synthesis"] is None
+    _compare(sc, 60)
