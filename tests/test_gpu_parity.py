@@ -530,3 +530,16 @@ def test_slam_without_voja_matches_oracle():
     got = sim.data[sc.probe]
     for trial in (0, 2):
         assert _rel(got[trial], _oracle(sc, sim, trial, n_steps).data[sc.probe]) < 1e-4
+
+
+def test_slamview_with_bound_view_input_matches_oracle():
+    """run_slamview.py:103,123-130 inputs (normalised sum of SP (*) SSP(displacement), slam_view.py:384-394) as tables."""
+    n_steps = 120
+    sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=55, pi_n_neurons=80, mem_n_neurons=160,
+                             circonv_n_neurons=24, n_landmarks=12, T=20.0, neuron_type="lifrate", view=True, view_rad=0.6,
+                             view_bound=True)
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        sim.run_steps(n_steps)
+    got = sim.data[sc.probe]
+    for trial in (0, 2):
+        assert _rel(got[trial], _oracle(sc, sim, trial, n_steps).data[sc.probe]) < 1e-4
