@@ -14,10 +14,17 @@ One bench *step* = ``--chunk`` simulator timesteps of the whole batch (one ``run
   tables are copied from page-locked host memory and the probe block is read back to the host.
 * ``e2e_synth`` — the same, with the input closures evaluated on the device (``Simulator(input_synthesis=...)``,
   SURVEY.md §8f-2): the host sends 12 bytes per timestep instead of table rows.
+* ``sustained`` — the same (on-device inputs) for >= 10 s of device time in ``--sustained-chunk``-timestep calls, with its
+  own clock samples: the number to expect from a 200 s reference-length run.
 * ``roofline`` — dominant kernel kind: algorithmic bytes (SURVEY.md §8d model) / CUDA-event time; ``traffic`` /
-  ``achieved_traffic`` are the DRAM bytes ncu measured for that kernel (``profiles/ncu_traffic.json``).
+  ``achieved_traffic`` / ``frac_dram`` are the DRAM bytes ncu measured for that kernel (``profiles/ncu_traffic.json``);
+  ``step_roofline`` is the same pair for the whole step (``frac`` = algorithmic model, ``frac_dram`` = measured DRAM bytes).
 * ``cpu_baseline`` — the operator-level NumPy port of the nengo reference simulator
-  (``oracle/nengo_ref_sim.py``) on the same built network, one trial, one host core.
+  (``oracle/nengo_ref_sim.py``) on the same built network, one trial, one host core (BLAS pinned to one thread, and
+  unpinned under ``blas_unpinned``).
+
+Every trial of the batch is distinct: trial ``i`` (global id over all ranks) has its own path (seed ``1000 i``), landmark
+set and start voltages; the static weights are shared by the whole job (one network seed).  ``config.distinct_trials``.
 
 ``--impl reference`` times that CPU port on all host cores (one independent trial per process).
 Multi-GPU: one process per GPU (torchrun), trials sharded, no data-path collective; one NCCL
@@ -54,15 +61,20 @@ def parse():
     ap.add_argument("--cpu-baseline-steps", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-synth", action="store_true", help="skip the on-device input-synthesis e2e leg")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct trials per GPU (0 = every trial; <trials tiles them)")
+    ap.add_argument("--sustained-steps", type=int, default=49152,
+                    help="simulator timesteps of the sustained leg (0 = skip; the default is >= 10 s at 1024 trials)")
+    ap.add_argument("--sustained-chunk", type=int, default=2048)
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
 
-def slam_scenario(n_trials, n_steps, seed, distinct):
+def slam_scenario(n_trials, n_steps, seed, distinct, table_steps=None, trial0=0, workers=None):
     from sspslam_b200 import scenarios
     return scenarios.make_slam(n_trials=n_trials, n_steps=n_steps, ssp_dim=55, pi_n_neurons=500, mem_n_neurons=970,
                                circonv_n_neurons=100, n_landmarks=50, T=200.0, seed=seed, neuron_type="lif",
-                               distinct_tables=distinct)
+                               distinct_tables=distinct, table_steps=table_steps, trial0=trial0, workers=workers,
+                               table_dtype=np.float32)
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -143,15 +155,27 @@ def _oracle_for_trial(sc, model, trial):
 
 
 def cpu_baseline_single(sc, model, n_steps, warm=40):
-    """One trial of the CPU port on one core (BLAS threads as NumPy finds them; ops are tiny)."""
-    ref = _oracle_for_trial(sc, model, 0)
-    ref.run_steps(warm)
-    t0 = time.perf_counter()
-    ref.run_steps(n_steps)
-    dt = time.perf_counter() - t0
-    return {"value": n_steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+    """One trial of the CPU port on one core: BLAS pinned to one thread (the headline row; the operators are tiny) and
+    BLAS threads as NumPy finds them (BASELINE.md §4 asks for both)."""
+    def timed(n):
+        ref = _oracle_for_trial(sc, model, 0)
+        ref.run_steps(warm)
+        t0 = time.perf_counter()
+        ref.run_steps(n)
+        return n / (time.perf_counter() - t0)
+    unpinned = timed(max(1, n_steps // 2))
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            pinned = timed(n_steps)
+    except Exception:
+        pinned = timed(n_steps)
+    return {"value": pinned, "unit": UNIT, "cores": 1, "kind": "port",
+            "blas_unpinned": {"value": unpinned, "threads_available": len(os.sched_getaffinity(0))},
+            "host_cpu_count": os.cpu_count(),
             "sample": f"1 trial x {n_steps} timesteps of the same built network after {warm} warm-up steps "
-                      f"(oracle/nengo_ref_sim.py, float64, unmerged operators)"}
+                      f"(oracle/nengo_ref_sim.py, float64, unmerged operators: ~5 500 NumPy calls per timestep, so it is "
+                      f"several times slower than nengo's merged-operator reference simulator would be)"}
 
 
 def _ref_worker(args):
@@ -180,7 +204,7 @@ def run_reference(args):
     from sspslam_b200.builder import build_model
     cores = len(os.sched_getaffinity(0))
     n_steps = (args.warmup + args.steps) * args.ref_chunk
-    sc = slam_scenario(cores, n_steps + 2, args.seed, distinct=cores)
+    sc = slam_scenario(cores, n_steps + 2, args.seed, distinct=cores, workers=1)
     model = build_model(sc.network, dt=sc.dt)
     ctx = mp.get_context("fork")
     barrier, q = ctx.Barrier(cores), ctx.Queue()
@@ -199,7 +223,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "timesteps_per_step": args.ref_chunk, "trials": cores},
+            "config": {"workload": WORKLOAD, "timesteps_per_step": args.ref_chunk, "trials": cores, "distinct_trials": cores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -227,6 +251,17 @@ def load_traffic(kind):
     return None
 
 
+def load_step_traffic():
+    """DRAM bytes of one whole simulator timestep (all kernels) from the committed ncu capture, and the batch it was taken at."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            entry = json.load(f).get("_step")
+        if isinstance(entry, dict):
+            return entry.get("dram_bytes_per_timestep"), entry.get("trials")
+    return None, None
+
+
 def run_b200(args):
     import torch
     import __graft_entry__ as entry
@@ -247,8 +282,13 @@ def run_b200(args):
     B, chunk, K, W = args.trials, args.chunk, args.steps, args.warmup
     n_phase = (W + K) * chunk
     total_steps = 2 * n_phase + chunk
-    # trial ids are global: rank r owns [r*B, (r+1)*B); static weights are shared (one network seed)
-    sc = slam_scenario(B, total_steps + 2, args.seed + 8000 * rank, distinct=8)
+    # trial ids are global: rank r owns [r*B, (r+1)*B) — its own paths, landmark sets and start voltages; the static
+    # weights are shared by the whole job (one network seed on every rank)
+    distinct = B if args.distinct <= 0 else min(B, args.distinct)
+    n_sust = 0 if args.no_synth else max(0, args.sustained_steps)
+    cores = len(os.sched_getaffinity(0))
+    sc = slam_scenario(B, total_steps + 2 + n_sust, args.seed, distinct=distinct, table_steps=total_steps + 2,
+                       trial0=rank * B, workers=max(1, cores // max(1, min(world, 8))))
     trial_seeds = sharding.trial_seeds(world * B, rank, world)
     sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, trial_seeds=trial_seeds,
                     device=local, chunk_steps=n_phase)
@@ -313,6 +353,7 @@ def run_b200(args):
     traffic = load_traffic(dom)
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac_dram": None if traffic is None else traffic / (dom_ms / max(dom_cnt, 1) * 1e-3) / 1e9 / peak,
                 # the SURVEY 8d model charges 16 B per neuron state and a write of every learned weight; the kernels
                 # keep a one-word state and write back only what changed, so the DRAM bytes ncu measured are lower:
                 "achieved_traffic": None if traffic is None else traffic / (dom_ms / max(dom_cnt, 1) * 1e-3) / 1e9,
@@ -323,12 +364,17 @@ def run_b200(args):
                 "share_of_step": dom_ms / tot_ms,
                 "kernel_shares": {k: round(ms / tot_ms, 4) for k, (ms, c) in kt.items() if c}}
     step_gbs = bytes_ts * B * chunk * K / (value_ms * 1e-3) / 1e9
+    step_traffic, traffic_trials = load_step_traffic()
+    step_dram_gbs = None
+    if step_traffic is not None and traffic_trials:
+        step_dram_gbs = step_traffic * (B / traffic_trials) * chunk * K / (value_ms * 1e-3) / 1e9
 
     # ---------------- e2e with on-device input synthesis: the host sends 12 bytes per timestep
-    e2e_synth = None
+    e2e_synth = sustained = None
     if not args.no_synth:
-        sim2 = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_seeds=trial_seeds, device=local, chunk_steps=chunk,
-                         model=sim.model, input_synthesis=sc.extra["input_synthesis"])
+        sim2 = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_seeds=trial_seeds, device=local,
+                         chunk_steps=max(chunk, args.sustained_chunk if n_sust else chunk),
+                         model=sim.model, input_synthesis=sc.extra["input_synthesis"], keep_probe_history=False)
         for _ in range(W):
             sim2.run_steps(chunk)
         sim2.sync()
@@ -343,6 +389,27 @@ def run_b200(args):
         e2e_synth = {"value": world * B * chunk * K / (syn_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": chunk * 12,
                      "d2h_bytes_per_step": d2h, "ms_per_step": syn_ms / K,
                      "inputs": "k_synth evaluates the input closures on the device from per-trial paths / landmarks"}
+        # ------------ sustained: >= 10 s of device time through the same public call, its own clock samples
+        if n_sust:
+            sc_chunk = args.sustained_chunk
+            n_calls = max(1, min(n_sust, sc.extra["input_synthesis"]["path"].shape[1] - 2 - sim2.n_steps) // sc_chunk)
+            clocks2 = ClockSampler(local)
+            barrier()
+            t_wall = time.time()
+            sim2.mark(0)
+            for _ in range(n_calls):
+                sim2.run_steps(sc_chunk)
+            sim2.mark(1)
+            sim2.sync()
+            barrier()
+            clocks2.window(t_wall, time.time())
+            sus_ms = max_over_ranks(sim2.mark_elapsed_ms(0, 1))
+            ci2 = clocks2.stop()
+            sustained = {"value": world * B * sc_chunk * n_calls / (sus_ms * 1e-3), "unit": UNIT, "seconds": sus_ms * 1e-3,
+                         "timesteps": sc_chunk * n_calls, "timesteps_per_call": sc_chunk,
+                         "h2d_bytes_per_call": sc_chunk * 12, "d2h_bytes_per_call": sc_chunk * int(sim2.plan.scalars["n_probe"]) * sim2.B * 4,
+                         "clocks": {k: ci2.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
+                         "path": "Simulator.run_steps with on-device input synthesis, probe block read back to the host every call"}
         sim2.close()
 
     # ---------------- error statistics: one small collective at the very end
@@ -362,6 +429,10 @@ def run_b200(args):
             "ms_per_step": value_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "trials_per_gpu": B, "timesteps_per_step": chunk, "weights": "shared",
+                       "distinct_trials": world * distinct,
+                       "trial_diversity": "every trial has its own band-limited random path (seed 1000*i), its own 50 R_d "
+                                          "landmarks and its own start voltages; static weights shared (one network seed)"
+                                          if distinct == B else f"{distinct} distinct input sets per GPU tiled over {B} trials",
                        "neurons_per_trial": stats["n_neurons"], "learned_per_trial": stats["n_learned"],
                        "algorithmic_bytes_per_trial_timestep": bytes_ts,
                        "l2": f"per-step working set {bytes_ts * B / 1e6:.0f} MB streams through HBM (> 126 MB L2)",
@@ -369,10 +440,15 @@ def run_b200(args):
             "e2e": {"value": tsteps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
             "e2e_synth": e2e_synth,
+            "sustained": sustained,
             "gpu_launches": int(launches),
             "clocks": {k: clock_info[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "roofline": roofline,
-            "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
+            "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                              "achieved_dram": step_dram_gbs, "frac_dram": None if step_dram_gbs is None else step_dram_gbs / peak,
+                              "note": "frac = SURVEY 8d algorithmic bytes / time / peak; frac_dram = DRAM bytes ncu measured "
+                                      "for one whole timestep (profiles/ncu_traffic.json '_step') / time / peak: the kernels "
+                                      "move fewer bytes than the model charges, so the step is issue / latency-bound"},
             "final_cosine_similarity": {"mean": float(np.mean(gathered)), "min": float(np.min(gathered)),
                                         "n_trials": int(gathered.size)},
         }

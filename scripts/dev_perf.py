@@ -10,18 +10,20 @@ B = int(os.environ.get("B", "1024"))
 steps = int(os.environ.get("STEPS", "64"))
 reps = int(os.environ.get("REPS", "4"))
 cfg = os.environ.get("CONFIG", "slam55")
+import numpy as np
+DISTINCT = int(os.environ.get("DISTINCT", str(B)))
 if cfg == "pathint97":      # BASELINE configs[0]
     sc = scenarios.make_pathint(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=97, pi_n_neurons=500, neuron_type="lif")
 elif cfg == "slamview97":   # BASELINE configs[3] sizes
     sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=97, pi_n_neurons=800, mem_n_neurons=970,
-                             circonv_n_neurons=100, n_landmarks=100, T=200.0, length_scale=0.3, view=True, distinct_tables=8)
+                             circonv_n_neurons=100, n_landmarks=100, T=200.0, length_scale=0.3, view=True, distinct_tables=DISTINCT, table_dtype=np.float32)
 elif cfg == "slam55gif":    # BASELINE configs[2] sizes (run_slam_map_gif.py defaults)
     sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=55, pi_n_neurons=800, mem_n_neurons=1000,
-                             circonv_n_neurons=100, n_landmarks=50, T=200.0, length_scale=0.1, distinct_tables=8)
+                             circonv_n_neurons=100, n_landmarks=50, T=200.0, length_scale=0.1, distinct_tables=DISTINCT, table_dtype=np.float32)
 elif cfg == "slam55loihi":  # run_slam.py --backend loihi-sim sizes: SLAMLoihiNetwork, d=55, pi 500, mem 970, circonv 100, dot-product 50
-    sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=8, loihi=True, dotprod_n_neurons=50)
+    sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=DISTINCT, table_dtype=np.float32, loihi=True, dotprod_n_neurons=50)
 else:
-    sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=8)
+    sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=DISTINCT, table_dtype=np.float32)
 if os.environ.get("SYNTH"):      # on-device input synthesis instead of tables
     sim = Simulator(sc.network, dt=sc.dt, n_trials=B, input_synthesis=sc.extra["input_synthesis"], chunk_steps=steps)
 else:

@@ -8,7 +8,9 @@ from sspslam_b200.simulator import Simulator
 
 B = int(os.environ.get("B", "1024"))
 steps = int(os.environ.get("STEPS", "6"))
-sc = scenarios.make_slam(n_trials=B, n_steps=steps + 4, T=200.0, distinct_tables=4)
+import numpy as np
+DISTINCT = int(os.environ.get("DISTINCT", str(B)))
+sc = scenarios.make_slam(n_trials=B, n_steps=steps + 4, T=200.0, distinct_tables=DISTINCT, table_dtype=np.float32)
 sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, chunk_steps=steps)
 sim.run_steps(steps)      # fewer than 16 steps: direct launches, no graph replay
 sim.sync()

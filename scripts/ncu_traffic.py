@@ -21,6 +21,19 @@ for r in rows[2:]:
     a["time_us"] += float(r[it])
 res = {k: {"dram_bytes_per_launch": v["dram_bytes"] / v["launches"], "launches_captured": v["launches"],
            "ncu_time_us_per_launch": v["time_us"] / v["launches"]} for k, v in acc.items()}
+# whole-timestep DRAM bytes: every kernel of the capture / number of timesteps captured (k_gate runs once per step; the
+# deferred-PES fold runs every 8th step, so captures should span a multiple of 8 steps or carry the fold's share)
+all_acc = {}
+for r in rows[2:]:
+    name = r[ik].split("(")[0].split("<")[0]
+    a = all_acc.setdefault(name, [0, 0.0])
+    a[0] += 1
+    a[1] += float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+import os
+n_steps = int(os.environ.get("CAPTURED_STEPS", "0")) or max(1, all_acc.get("k_gate", [1])[0])
+res["_step"] = {"dram_bytes_per_timestep": sum(v[1] for v in all_acc.values()) / n_steps, "timesteps_captured": n_steps,
+                "trials": int(os.environ.get("B", "1024")),
+                "by_kernel": {k: {"launches": v[0], "dram_bytes": v[1]} for k, v in sorted(all_acc.items())}}
 res["_source"] = rep.split("/")[-1]
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps(res, indent=1))

@@ -6,7 +6,8 @@ lambdas (``experiments/run_slam.py:164-169``, ``run_pathint.py:134-136``) are ev
 by nengo once per step at ``t = n*dt``.  Their index expressions are float-fragile
 (``int((t-dt)/dt)`` is ``n-1`` for only ~80 % of ``n``; K7) so the tables here reproduce
 the *same expressions* element-wise in float64 rather than "fixing" them.
-``tests/test_inputs_golden.py`` checks the tables against the unmodified closures.
+``tests/test_transforms_inputs_golden.py`` / ``tests/test_networks_parity.py`` check the tables against the unmodified
+closures.
 """
 from __future__ import annotations
 
@@ -27,6 +28,28 @@ def random_path(T, dt=0.001, limit=0.1, seed=0, domain_dim=2, radius=1.0):
     """Band-limited white-noise path rescaled to +-0.9*radius per axis (run_slam.py:95-112)."""
     cols = [WhiteSignal(T, high=limit, seed=seed + i).run(T, dt=dt) for i in range(domain_dim)]
     path = np.hstack(cols)
+    lo, hi = path.min(axis=0), path.max(axis=0)
+    return (1.8 * radius) * (path - lo) / (hi - lo) - 0.9 * radius
+
+
+def stretch_trajectory(traj, original_dt=0.02, new_dt=0.001):
+    """Linear re-sampling of a recorded path to the simulation step (``run_slam.py:80-89``): ``int(n*original_dt/new_dt)``
+    points on the same time span, per axis."""
+    traj = np.asarray(traj, dtype=np.float64)
+    n = traj.shape[0]
+    total = n * original_dt
+    t_old, t_new = np.linspace(0, total, n), np.linspace(0, total, int(total / new_dt))
+    return np.stack([np.interp(t_new, t_old, traj[:, k]) for k in range(traj.shape[1])], axis=1)
+
+
+def load_path(path_data, data_dt=0.001, dt=0.001, radius=1.0):
+    """The ``--path-data`` branch of the drivers (``run_slam.py:100-112``): the first 99 999 rows of the recorded path
+    (a ``.npy`` file name or an array ``[n, domain_dim]``), re-sampled when ``data_dt != dt``, then every axis min-max
+    rescaled to +-0.9*radius.  The simulated time is ``len(result) * dt``."""
+    raw = np.load(path_data) if isinstance(path_data, (str, bytes)) or hasattr(path_data, "__fspath__") else path_data
+    path = np.array(raw, dtype=np.float64)[:99999, :]
+    if data_dt != dt:
+        path = stretch_trajectory(path, original_dt=data_dt, new_dt=dt)
     lo, hi = path.min(axis=0), path.max(axis=0)
     return (1.8 * radius) * (path - lo) / (hi - lo) - 0.9 * radius
 

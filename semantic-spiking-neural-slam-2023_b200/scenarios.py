@@ -70,11 +70,63 @@ def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0,
                     dict(pathint=pi, vel_scale=scale, input_synthesis=synth), dt)
 
 
+class _TrialJob:
+    """Inputs of one trial (path, scaled velocities, landmark set, tables for the first ``table_steps`` steps); a
+    picklable callable so that a batch of distinct trials can be synthesised by a process pool."""
+
+    def __init__(self, space, lm_vectors, scale, recorded, T, dt, limit, seed, domain_dim, n_landmarks, view_rad,
+                 n_steps, table_steps, view, view_bound, table_dtype, trial0):
+        self.__dict__.update(locals())
+
+    def __call__(self, i):
+        s_i = self.seed + 1000 * (self.trial0 + i)
+        n_keep = max(self.n_steps + 2, 4)
+        if self.recorded is not None:
+            path = self.recorded[:n_keep]
+        else:
+            path = inputs.random_path(self.T, self.dt, self.limit, s_i, self.domain_dim)[:n_keep]
+        vels = inputs.velocities(path, self.dt) * self.scale
+        obj_locs = 1.8 * (inputs.rd_sampling(self.n_landmarks, self.domain_dim, seed=s_i) - 0.5)
+        n_tab = self.table_steps
+        head = path[:max(n_tab + 2, 4)]            # the table index rules only look at rows < n_tab + 2
+        vec_to_lm = obj_locs[None, :, :] - head[:, None, :]
+        space, lmv, dt = self.space, self.lm_vectors, self.dt
+        real = space.encode_host(head)
+        kw = dict(real_ssp=real)     # (the ``pathlen - 2`` clip of the index rule never bites for steps <= n_tab)
+        if self.view and self.view_bound:
+            vt = inputs.slamview_tables(space, lmv, vels[:len(head)], vec_to_lm, self.view_rad, n_tab, dt)
+            tb = inputs.slam_tables(space.encode_host, lmv, vels[:len(head)], vec_to_lm, self.view_rad, n_tab, dt,
+                                    none_in_view_value=1.0, **kw)
+            tb.update(vel=vt["vel"], lm_sp=vt["view"], nolm=vt["nolm"])
+        elif self.view:
+            # default: the superposed landmark SPs as the view key (what the on-device input synthesis evaluates)
+            tb = inputs.slam_tables(space.encode_host, lmv, vels[:len(head)], vec_to_lm, self.view_rad, n_tab, dt,
+                                    none_in_view_value=1.0, **kw)
+        else:
+            tb = inputs.slam_tables(space.encode_host, lmv, vels[:len(head)], vec_to_lm, self.view_rad, n_tab, dt, **kw)
+        tb = {k: np.asarray(v, dtype=self.table_dtype) for k, v in tb.items()}
+        return tb, path, real[:n_tab].astype(self.table_dtype), vels, obj_locs
+
+
+def _map_trials(job, n, workers=None):
+    """Evaluate ``job(i)`` for i < n, on a fork pool when there are enough trials to pay for it."""
+    import os
+    if workers is None:
+        workers = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = int(max(1, min(workers, n // 8)))
+    if workers <= 1:
+        return [job(i) for i in range(n)]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(job, range(n), chunksize=max(1, n // (4 * workers)))
+
+
 def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neurons=970, circonv_n_neurons=100,
               n_landmarks=50, view_rad=0.2, T=200.0, limit=0.1, seed=0, dt=0.001, length_scale=0.2,
               shift_rate=0.2, update_thres=0.2, neuron_type="lif", weights_probe=False, view=False,
               distinct_tables=None, domain_dim=2, grid_points_per_dim=100, gc_n_neurons=0, approx_vel=False,
-              vel_n_neurons=500, loihi=False, dotprod_n_neurons=50, inverse_memory=False, voja=True, view_bound=False):
+              vel_n_neurons=500, loihi=False, dotprod_n_neurons=50, inverse_memory=False, voja=True, view_bound=False,
+              table_steps=None, path_data=None, data_dt=0.001, workers=None, table_dtype=np.float64, trial0=0):
     """``run_slam.py`` (or ``run_slamview.py`` when ``view``) workload, batched over trials.
 
     ``distinct_tables``: synthesise only that many distinct trials' tables and tile them
@@ -84,41 +136,39 @@ def make_slam(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, mem_n_neur
     a second Voja + PES memory mapping landmark locations back to landmark SPs, with that script's probes.
     ``view_bound`` (with ``view``): feed the local view of ``run_slamview.py:103,123-130`` — the normalised sum of
     ``SP_l (*) encode(displacement_l)`` with that driver's index rules (``inputs.slamview_tables``) — instead of the SP sum;
-    tables only (the on-device input synthesis evaluates the SP-sum form)."""
+    tables only (the on-device input synthesis evaluates the SP-sum form).
+    ``table_steps``: build host tables / ``real_ssp`` for the first ``table_steps`` steps only, while the per-trial paths
+    handed to the on-device input synthesis cover ``n_steps`` (long sustained runs need no host tables).
+    ``path_data`` / ``data_dt``: a recorded path (array or ``.npy`` file) with the ``--path-data`` rules of
+    ``run_slam.py:100-112`` (``inputs.load_path``); every trial then walks the same path and trial ``i`` differs in its
+    landmark set (``Rd_sampling(seed + 1000 i)``) and start state — BASELINE configs[2] / [3].
+    ``trial0``: global id of the first trial (sharded runs: rank r passes ``r * n_trials``; trial ``i`` uses path / landmark
+    seed ``seed + 1000 * (trial0 + i)`` while the network seed — the shared static weights — stays ``seed``).
+    ``table_dtype``: dtype of the host tables (the device arena is float32; large batches pass ``np.float32``).
+    ``workers``: processes used to synthesise the distinct trials (default: the host cores this process may use)."""
+    recorded = None
+    if path_data is not None:
+        recorded = inputs.load_path(path_data, data_dt, dt)
+        domain_dim = recorded.shape[1]
     space = make_space(domain_dim, ssp_dim, length_scale)
     d = space.ssp_dim
     lm_space = SPSpace(n_landmarks, d, seed=seed)
     n_distinct = n_trials if distinct_tables is None else min(n_trials, distinct_tables)
-    paths, ssps, tabs, syn_paths, syn_vels, syn_lms = [], [], [], [], [], []
-    scale = None
-    for i in range(n_distinct):
-        s_i = seed + 1000 * i
-        path = inputs.random_path(T, dt, limit, s_i, domain_dim)[:max(n_steps + 2, 4)]
-        vels = inputs.velocities(path, dt)
-        if scale is None:
-            scale = inputs.velocity_scale(space.phase_matrix,
-                                          inputs.velocities(inputs.random_path(T, dt, limit, seed, domain_dim), dt))
-        obj_locs = 1.8 * (inputs.rd_sampling(n_landmarks, domain_dim, seed=s_i) - 0.5)
-        vec_to_lm = obj_locs[None, :, :] - path[:, None, :]
-        real = space.encode_host(path)
-        if view and view_bound:
-            vt = inputs.slamview_tables(space, lm_space.vectors, vels * scale, vec_to_lm, view_rad, n_steps, dt)
-            tb = inputs.slam_tables(space.encode_host, lm_space.vectors, vels * scale, vec_to_lm, view_rad, n_steps, dt,
-                                    real_ssp=real, none_in_view_value=1.0)
-            tb.update(vel=vt["vel"], lm_sp=vt["view"], nolm=vt["nolm"])
-        elif view:
-            # default: the superposed landmark SPs as the view key (what the on-device input synthesis evaluates)
-            tb = inputs.slam_tables(space.encode_host, lm_space.vectors, vels * scale, vec_to_lm, view_rad, n_steps, dt,
-                                    real_ssp=real, none_in_view_value=1.0)
-        else:
-            tb = inputs.slam_tables(space.encode_host, lm_space.vectors, vels * scale, vec_to_lm, view_rad, n_steps, dt,
-                                    real_ssp=real)
-        tabs.append(tb)
-        paths.append(path[:n_steps])
-        ssps.append(real[:n_steps])
-        syn_paths.append(path)
-        syn_vels.append(vels * scale)
-        syn_lms.append(obj_locs)
+    table_steps = n_steps if table_steps is None else min(int(table_steps), n_steps)
+    if recorded is not None:
+        scale = inputs.velocity_scale(space.phase_matrix, inputs.velocities(recorded, dt))
+    else:
+        scale = inputs.velocity_scale(space.phase_matrix,
+                                      inputs.velocities(inputs.random_path(T, dt, limit, seed, domain_dim), dt))
+    job = _TrialJob(space, lm_space.vectors, scale, recorded, T, dt, limit, seed, domain_dim, n_landmarks, view_rad,
+                    n_steps, table_steps, view, view_bound, table_dtype, trial0)
+    results = _map_trials(job, n_distinct, workers)
+    tabs = [r[0] for r in results]
+    paths = [r[1][:table_steps] for r in results]
+    ssps = [r[2] for r in results]
+    syn_paths = [r[1] for r in results]
+    syn_vels = [r[3] for r in results]
+    syn_lms = [r[4] for r in results]
     t0 = tabs[0]
 
     def tab_fn(name):

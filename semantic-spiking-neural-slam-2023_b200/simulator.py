@@ -48,7 +48,7 @@ class _SimData:
 class Simulator:
     def __init__(self, network, dt=0.001, seed=None, model: BuiltModel | None = None, progress_bar=True,
                  optimize=True, n_trials=None, trial_inputs=None, trial_seeds=None, device=0, chunk_steps=256,
-                 input_synthesis=None):
+                 input_synthesis=None, keep_probe_history=True):
         self.network = network
         self.dt = float(dt)
         self.closed = False
@@ -84,7 +84,8 @@ class Simulator:
         self.B = int(self._lib.ssb_n_trials_padded(self._h))
         self._nt = int(self.plan.scalars["nt"])
         self._np = int(self.plan.scalars["n_probe"])
-        self._tab_buf = cabi.PinnedBuffer(max(1, self.chunk_steps * self._nt * self.B))
+        self._tab_buf_ = None        # page-locked table staging of one chunk, allocated on first use
+        self.keep_probe_history = bool(keep_probe_history)
         # two page-locked probe buffers: the host-side copy-out of chunk k overlaps the device work of chunk k + 1
         self._probe_bufs = [cabi.PinnedBuffer(max(1, self.chunk_steps * self._np * self.B)) for _ in range(2)]
         self._probe_cur = 0
@@ -95,6 +96,12 @@ class Simulator:
         if input_synthesis is not None:
             self._setup_input_synthesis(input_synthesis)
         self._init_state()
+
+    @property
+    def _tab_buf(self):
+        if self._tab_buf_ is None:
+            self._tab_buf_ = cabi.PinnedBuffer(max(1, self.chunk_steps * self._nt * self.B))
+        return self._tab_buf_
 
     # ------------------------------------------------------------------ on-device input synthesis
     def _setup_input_synthesis(self, spec):
@@ -177,7 +184,9 @@ class Simulator:
             self._upload("lenc", row0, self._rows(m.params[ens].scaled_encoders.reshape(-1)))
         for conn, (row0, size_out, n) in plan.learned_dec.items():
             self._upload("ldec", row0, self._rows(np.asarray(m.params[conn].weights).reshape(-1)))
-        self._probe_rows = []      # list of [steps, n_probe, n_trials] float32 chunks
+        # per "rows" probe: list of [samples, size, n_trials] float32 chunks, already decimated by the probe's period
+        self._probe_rows = {info.probe: [] for info in plan.probes if info.kind == "rows"}
+        self._probe_steps_flushed = 0
         self._snap = {info.probe: [] for info in plan.probes if info.kind != "rows"}
         self._table_cache = {}
 
@@ -198,7 +207,8 @@ class Simulator:
                 self._lib.ssb_destroy(self._h)
                 self._h = None
             self._flush_probes()
-            self._tab_buf.free()
+            if self._tab_buf_ is not None:
+                self._tab_buf_.free()
             for b in self._probe_bufs:
                 b.free()
             if getattr(self, "_staged", None) is not None:
@@ -236,7 +246,11 @@ class Simulator:
         self.run_steps(1)
 
     def reset(self, seed=None):
+        """Back to step 0 with the same built model, start voltages and ``trial_seeds`` (nengo's ``reset(seed)`` would
+        rebuild the model with another seed; that is refused rather than ignored)."""
         self._check_open()
+        if seed is not None:
+            raise NotImplementedError("reset(seed=...) would rebuild the model; construct a new Simulator instead")
         cabi.check(self._lib.ssb_reset(self._h), "ssb_reset")
         self._probe_pending = None
         self._n_steps = 0
@@ -271,6 +285,8 @@ class Simulator:
         if self._nt == 0:
             return
         n_steps = int(n_steps)
+        if getattr(self, "_staged", None) is not None:
+            self._staged.free()
         self._staged = cabi.PinnedBuffer(n_steps * self._nt * self.B)
         self._staged_step0 = int(step0)
         self._staged_steps = n_steps
@@ -348,7 +364,16 @@ class Simulator:
         if buf.array is None:
             return
         chunk = buf.array[:n * self._np * self.B].reshape(n, self._np, self.B)
-        self._probe_rows.append(chunk[:, :, :self.n_trials].copy())
+        step0 = self._probe_steps_flushed                  # steps already copied out: this chunk holds step0+1 ..
+        for probe, rows in self._probe_rows.items():
+            info = self._probe_infos[probe]
+            first = (-(step0 + 1)) % info.period            # offset of the first step with (step % period) == 0
+            part = chunk[first::info.period, info.row0:info.row0 + info.size, :self.n_trials]
+            if not self.keep_probe_history:
+                rows.clear()
+            if part.shape[0]:
+                rows.append(part.copy())
+        self._probe_steps_flushed += n
 
     def _snapshot(self, info):
         if info.kind == "weights":
@@ -363,14 +388,12 @@ class Simulator:
         info = self._probe_infos[probe]
         if info.kind == "rows":
             self._flush_probes()
-            if self._probe_rows:
-                allrows = np.concatenate(self._probe_rows, axis=0) if len(self._probe_rows) > 1 else self._probe_rows[0]
-                self._probe_rows = [allrows]
-                data = allrows[:, info.row0:info.row0 + info.size, :]
+            rows = self._probe_rows[probe]
+            if rows:
+                data = np.concatenate(rows, axis=0) if len(rows) > 1 else rows[0]
+                self._probe_rows[probe] = [data]
             else:
                 data = np.zeros((0, info.size, self.n_trials), dtype=np.float32)
-            if info.period > 1:
-                data = data[info.period - 1::info.period]
             data = np.transpose(data, (2, 0, 1)).astype(np.float64)   # [trial, sample, size]
         else:
             snaps = self._snap[probe]
