@@ -36,7 +36,7 @@ from __future__ import annotations
 import numpy as np
 
 from sspslam_b200 import nengo_shim as ns
-from sspslam_b200.builder import build_model, BuiltModel
+from oracle.nengo_ref_build import build as ref_build
 
 
 # ----------------------------------------------------------------------------- signals
@@ -262,11 +262,13 @@ def _toposort(ops):
 class RefSimulator:
     """``nengo.Simulator``-shaped reference stepper (single trial, CPU, NumPy)."""
 
-    def __init__(self, network, dt=0.001, model: BuiltModel | None = None, dtype=np.float64,
-                 trial_seed=None, node_tables=None):
+    def __init__(self, network, dt=0.001, model=None, dtype=np.float64, trial_seed=None, node_tables=None):
+        """``model=None``: the network is built by the oracle's OWN builder (``oracle/nengo_ref_build.py``).  The parity
+        tests pass the product's built model instead so that both sides step the same numbers (the two builders are
+        compared with each other in ``tests/test_oracle_build.py``)."""
         self.network = network
         self.dt = float(dt)
-        self.model = model if model is not None else build_model(network, dt)
+        self.model = model if model is not None else ref_build(network, dt)
         self.dtype = np.dtype(dtype)
         self.trial_seed = trial_seed
         self.node_tables = node_tables or {}  # node -> array [n_steps, size_out] replacing its callable

@@ -12,8 +12,8 @@ from __future__ import annotations
 import dataclasses
 import numpy as np
 
-from . import nengo_shim as ns
-from .nengo_shim import dists as nd
+from . import compat
+from .nengo_shim.exceptions import BuildError
 from .nengo_shim.utils.numpy import maxint
 
 _TYPE_ORDER = ("connections", "ensembles", "networks", "nodes", "probes")  # App. A.2
@@ -56,7 +56,7 @@ class BuiltModel:
         ``trial_seed`` is this backend's batching extension: a counter-based hash of
         (ensemble seed, trial seed, neuron index), so a trial's start state does not depend
         on which other trials share the batch (and thousands of trials cost no RNG set-up)."""
-        if not isinstance(ens.neuron_type, ns.LIF):
+        if compat.neuron_kind(ens.neuron_type) != "lif":
             return np.zeros(ens.n_neurons)
         if trial_seed is None:
             return np.random.RandomState(self.seeds[ens] + 1).uniform(0.0, 1.0, size=ens.n_neurons)
@@ -66,7 +66,7 @@ class BuiltModel:
         """[n_trials, n_neurons] start voltages; entries of ``trial_seeds`` may be ``None``."""
         n = ens.n_neurons
         out = np.zeros((len(trial_seeds), n))
-        if not isinstance(ens.neuron_type, ns.LIF):
+        if compat.neuron_kind(ens.neuron_type) != "lif":
             return out
         ints = np.array([-1 if s is None else int(s) for s in trial_seeds], dtype=np.int64)
         hashed = ints >= 0
@@ -106,32 +106,32 @@ def n_eval_points_default(n_neurons, dimensions):
 def _build_ensemble(model, ens):
     rng = np.random.RandomState(model.seeds[ens])
     # draw order: eval points -> encoders -> max_rates -> intercepts (App. A.3)
-    if isinstance(ens.eval_points, nd.Distribution):
+    if compat.is_distribution(ens.eval_points):
         n_pts = ens.n_eval_points or n_eval_points_default(ens.n_neurons, ens.dimensions)
         eval_points = ens.eval_points.sample(n_pts, ens.dimensions, rng=rng)
     else:
         eval_points = np.array(ens.eval_points, dtype=np.float64)
     eval_points = eval_points * ens.radius
 
-    if isinstance(ens.encoders, nd.Distribution):
+    if compat.is_distribution(ens.encoders):
         encoders = np.asarray(ens.encoders.sample(ens.n_neurons, ens.dimensions, rng=rng), dtype=np.float64)
     else:
         encoders = np.array(ens.encoders, dtype=np.float64)
     if ens.normalize_encoders:
         encoders = encoders / np.linalg.norm(encoders, axis=1, keepdims=True)
     if not np.all(np.isfinite(encoders)):
-        raise ns.exceptions.BuildError(f"non-finite encoders in {ens!r}")
+        raise BuildError(f"non-finite encoders in {ens!r}")
 
     if ens.gain is not None and ens.bias is not None:
         gain = np.array(ens.gain, dtype=np.float64)
         bias = np.array(ens.bias, dtype=np.float64)
         max_rates = intercepts = None
     else:
-        max_rates = nd.get_samples(ens.max_rates, ens.n_neurons, rng=rng)
-        intercepts = nd.get_samples(ens.intercepts, ens.n_neurons, rng=rng)
+        max_rates = compat.get_samples(ens.max_rates, ens.n_neurons, rng=rng)
+        intercepts = compat.get_samples(ens.intercepts, ens.n_neurons, rng=rng)
         gain, bias = ens.neuron_type.gain_bias(max_rates, intercepts)
     if not (np.all(np.isfinite(gain)) and np.all(np.isfinite(bias))):
-        raise ns.exceptions.BuildError(f"non-finite gain/bias in {ens!r}")
+        raise BuildError(f"non-finite gain/bias in {ens!r}")
 
     scaled = encoders * (gain / ens.radius)[:, None]
     model.params[ens] = BuiltEnsemble(eval_points, encoders, intercepts, max_rates, scaled, gain, bias)
@@ -153,18 +153,18 @@ class _DecoderCache:
             x = p.eval_points @ (p.encoders.T / ens.radius)
             self._acts[ens] = ens.neuron_type.rates(x, p.gain, p.bias)
             if np.count_nonzero(self._acts[ens]) == 0:
-                raise ns.exceptions.BuildError(f"all tuning curves of {ens!r} are zero")
+                raise BuildError(f"all tuning curves of {ens!r} are zero")
         return self._acts[ens]
 
     def solve(self, ens, solver, targets):
         A = self.activities(ens)
-        if not isinstance(solver, ns.solvers.LstsqL2):
+        if not compat.is_lstsq_l2(solver):
             X, _ = solver(A, targets)
             return X
-        key = (ens, solver.reg)
+        key = (ens, float(solver.reg))
         if key not in self._factor:
-            self._factor[key] = solver.gram(A)
-        return solver.solve(A, targets, self._factor[key])
+            self._factor[key] = compat.lstsq_l2_factor(A, float(solver.reg))
+        return compat.lstsq_l2_solve(A, targets, self._factor[key])
 
 
 def _targets(conn, eval_points):
@@ -195,29 +195,30 @@ def fold_transform(transform, mat):
 
 def _build_connection(model, conn, cache):
     pre = conn.pre_obj
-    if isinstance(pre, ns.Ensemble):
+    transform = compat.transform_of(conn)
+    if compat.is_ensemble(pre):
         if conn.solver.weights:
             raise NotImplementedError("weight solvers (solver.weights=True) are outside the hot path")
-        if isinstance(pre.neuron_type, ns.Direct):
+        if compat.neuron_kind(pre.neuron_type) == "direct":
             raise NotImplementedError("Direct-mode ensembles are not supported")
         eval_points = model.params[pre].eval_points if conn.eval_points is None \
             else np.array(conn.eval_points, dtype=np.float64)
         if conn.eval_points is not None:
             raise NotImplementedError("per-connection eval_points are outside the hot path")
         decoders = cache.solve(pre, conn.solver, _targets(conn, eval_points)).T  # size_mid x n
-        weights = fold_transform(conn.transform, decoders)
-        model.params[conn] = BuiltConnection(eval_points, {}, conn.transform, weights, decoders)
-    elif isinstance(pre, ns.Neurons):
+        weights = fold_transform(transform, decoders)
+        model.params[conn] = BuiltConnection(eval_points, {}, transform, weights, decoders)
+    elif compat.is_neurons(pre):
         raise NotImplementedError("connections *from* ens.neurons are outside the hot path")
     else:
         if conn.function is not None:
             raise NotImplementedError("functions on Node->X connections are outside the hot path")
-        model.params[conn] = BuiltConnection(None, None, conn.transform, conn.transform)
+        model.params[conn] = BuiltConnection(None, None, transform, transform)
 
 
 def _build_probe(model, probe, cache):
     obj = probe.obj
-    if isinstance(obj, ns.Ensemble) and probe.attr == "decoded_output":
+    if compat.is_ensemble(obj) and probe.attr == "decoded_output":
         dec = cache.solve(obj, probe.solver, model.params[obj].eval_points).T
         model.probe_conns[probe] = dec[np.arange(obj.dimensions)[probe.slice]]
     model.params[probe] = None

@@ -28,7 +28,7 @@ import os
 import numpy as np
 import scipy.sparse as sp
 
-from . import nengo_shim as ns
+from . import compat
 from . import nodeops
 from .builder import BuiltModel
 
@@ -63,7 +63,7 @@ NT_LIF, NT_LIFRATE, NT_RELU = 0, 1, 2
 
 
 def _ens_to_neurons(c):
-    return isinstance(c.pre_obj, ns.Ensemble) and isinstance(c.post_obj, ns.Neurons)
+    return compat.is_ensemble(c.pre_obj) and compat.is_neurons(c.post_obj)
 
 
 def _idx(key, size):
@@ -158,18 +158,18 @@ class _Lowerer:
         (split-K: partial sums are parked in a scratch arena and added up by the last CTA to arrive)."""
         self.ens_dec_conns = {e: [] for e in self.ensembles}
         for conn in self.conns:
-            if isinstance(conn.pre_obj, ns.Ensemble):
+            if compat.is_ensemble(conn.pre_obj):
                 self.ens_dec_conns[conn.pre_obj].append(conn)
         for probe in self.probes:
-            if isinstance(probe.obj, ns.Ensemble) and probe.attr == "decoded_output":
+            if compat.is_ensemble(probe.obj) and probe.attr == "decoded_output":
                 self.ens_dec_conns[probe.obj].append(probe)
         voja_posts = {c.post_obj for c in self.conns
-                      if c.learning_rule is not None and isinstance(c.learning_rule.learning_rule_type, ns.Voja)}
+                      if c.learning_rule is not None and compat.rule_kind(c.learning_rule.learning_rule_type) == "voja"}
         pes_conns = {c for c in self.conns
-                     if c.learning_rule is not None and isinstance(c.learning_rule.learning_rule_type, ns.PES)}
-        jn_posts = {c.post_obj.ensemble for c in self.conns if isinstance(c.post_obj, ns.Neurons)}
+                     if c.learning_rule is not None and compat.rule_kind(c.learning_rule.learning_rule_type) == "pes"}
+        jn_posts = {c.post_obj.ensemble for c in self.conns if compat.is_neurons(c.post_obj)}
         # ensembles whose neuron outputs are probed keep their activities in the act arena (wide path)
-        neuron_probed = {p.obj.ensemble for p in self.probes if isinstance(p.obj, ns.Neurons)}
+        neuron_probed = {p.obj.ensemble for p in self.probes if compat.is_neurons(p.obj)}
         self.is_small, self.dec_chunks = {}, {}
         for ens in self.ensembles:
             outs = self.ens_dec_conns[ens]
@@ -215,7 +215,7 @@ class _Lowerer:
 
     @staticmethod
     def _out_size(c):
-        if isinstance(c, ns.Connection):
+        if compat.is_connection(c):
             # ensemble -> neurons (slam_loihi.py:266): decode size_mid values, the (n x size_mid) transform is applied
             # as direct neuron currents after the synapse (linear, so equal to filtering the n folded currents)
             return c.size_mid if _ens_to_neurons(c) else c.size_out
@@ -244,11 +244,11 @@ class _Lowerer:
                 self.tab_col[node] = alloc("tab", node, node.size_out)
         for conn in self.conns:
             if conn.synapse is not None:
-                if isinstance(conn.pre_obj, ns.Neurons) or (isinstance(conn.post_obj, ns.Neurons) and not _ens_to_neurons(conn)):
+                if compat.is_neurons(conn.pre_obj) or (compat.is_neurons(conn.post_obj) and not _ens_to_neurons(conn)):
                     raise NotImplementedError("filtered neuron-to-neuron connections are outside the hot path")
                 self.filt_col[conn] = alloc("filt", conn, self._out_size(conn))
         for probe in self.probes:
-            if isinstance(probe.obj, (ns.Node, ns.Ensemble)) and probe.synapse is not None:
+            if compat.kind(probe.obj) in ("node", "ensemble") and probe.synapse is not None:
                 self.filt_col[probe] = alloc("filt", probe, probe.size_in)
         # decoded outputs, grouped per ensemble so that small ensembles own one contiguous slot
         for ens in self.ensembles:
@@ -297,14 +297,14 @@ class _Lowerer:
 
     def weighted(self, conn):
         pre = conn.pre_obj
-        if isinstance(pre, ns.Ensemble):
+        if compat.is_ensemble(pre):
             return self._dec_expr(conn)
-        if isinstance(pre, ns.Neurons):
+        if compat.is_neurons(pre):
             raise NotImplementedError("connections from ens.neurons are outside the hot path")
         src = self.expr_out(pre)
         rows = _idx(conn.pre_slice, pre.size_out)
         src = src[rows]
-        return _apply_transform(conn.transform, src).tocsr()
+        return _apply_transform(compat.transform_of(conn), src).tocsr()
 
     # ------------------------------------------------------------------ main
     def lower(self, chunk_cap):
@@ -321,7 +321,8 @@ class _Lowerer:
             ens_in[ens] = self.expr_in(ens)
             jn = []
             for conn in self.incoming.get(ens.neurons, []):
-                if conn.transform is None or np.ndim(conn.transform) != 2 or conn.post_slice != slice(None):
+                tr = compat.transform_of(conn)
+                if tr is None or np.ndim(tr) != 2 or conn.post_slice != slice(None):
                     raise NotImplementedError("neuron-direct connections need a full (n x m) transform")
                 pre = conn.pre_obj
                 if _ens_to_neurons(conn):
@@ -330,7 +331,7 @@ class _Lowerer:
                     u = self._eye(self.filt_col[conn], conn.size_mid)
                 else:
                     u = self.expr_out(pre)[_idx(conn.pre_slice, pre.size_out)]
-                G = self.model.params[ens].gain[:, None] * np.asarray(conn.transform, dtype=np.float64)
+                G = self.model.params[ens].gain[:, None] * tr
                 jn.append((u.tocsr(), G))
             if jn:
                 ens_jn[ens] = (sp.vstack([u for u, _ in jn]).tocsr(), np.hstack([G for _, G in jn]))
@@ -340,19 +341,19 @@ class _Lowerer:
                 continue
             lrt = rule.learning_rule_type
             rin = self.expr_in(rule)
-            if isinstance(lrt, ns.Voja):
+            if compat.rule_kind(lrt) == "voja":
                 if lrt.post_synapse is not None:
                     raise NotImplementedError("Voja with a post_synapse is outside the hot path")
                 one = sp.csr_matrix(([1.0], ([0], [0])), shape=(1, self.ncol))
                 voja_rule[conn.post_obj] = (conn, (one + rin).tocsr(), lrt)
-            elif isinstance(lrt, ns.PES):
+            elif compat.rule_kind(lrt) == "pes":
                 pes_rule[conn] = (rin, lrt)
             else:
                 raise NotImplementedError(type(lrt).__name__)
         fn_in = {n: self.expr_in(n) for n in self.nodes if self.node_kind[n] == "fn"}
         filt_in = {}
         for key in self.filt_col:
-            if isinstance(key, ns.Connection):
+            if compat.is_connection(key):
                 filt_in[key] = self.weighted(key)
             else:  # probe with synapse
                 filt_in[key] = self._probe_expr(key)
@@ -367,7 +368,7 @@ class _Lowerer:
         unresolved = np.zeros(self.ncol, dtype=bool)
         for c, col0 in self.dec_col.items():
             size = dec_width[c]
-            if not (isinstance(c, ns.Connection) and c in pes_rule):
+            if not (compat.is_connection(c) and c in pes_rule):
                 unresolved[col0:col0 + size] = True
         for n, col0 in self.fn_col.items():
             unresolved[col0:col0 + n.size_out] = True
@@ -393,7 +394,7 @@ class _Lowerer:
                     raise NotImplementedError("a PES-learned connection feeds an ensemble without a synapse")
                 ens_level[ens] = lvl
                 for c in self.ens_dec_conns[ens]:
-                    if isinstance(c, ns.Connection) and c in pes_rule:
+                    if compat.is_connection(c) and c in pes_rule:
                         continue
                     size = dec_width[c]
                     col_level[self.dec_col[c]:self.dec_col[c] + size] = lvl + 1
@@ -495,15 +496,15 @@ class _Lowerer:
         ntypes, ntype_ids = [], {}
 
         def ntype_id(nt):
-            if isinstance(nt, ns.LIF):
+            if compat.neuron_kind(nt) == "lif":
                 if nt.min_voltage != 0:
                     raise NotImplementedError("the packed one-word LIF state needs min_voltage == 0 (nengo's default)")
                 # polynomial expm1 / log1p are exact to fp32 for dt / tau_rc <= 1/16 (SSB kernels header)
                 fast = 1.0 if dt / nt.tau_rc <= 0.0625 else 0.0
                 key = (NT_LIF, nt.tau_rc, nt.tau_ref, nt.min_voltage, nt.amplitude, fast, 0.0, 0.0)
-            elif isinstance(nt, ns.LIFRate):
+            elif compat.neuron_kind(nt) == "lifrate":
                 key = (NT_LIFRATE, nt.tau_rc, nt.tau_ref, 0.0, nt.amplitude, 0.0, 0.0, 0.0)
-            elif isinstance(nt, ns.RectifiedLinear):
+            elif compat.neuron_kind(nt) == "relu":
                 key = (NT_RELU, 0.0, 0.0, 0.0, nt.amplitude, 0.0, 0.0, 0.0)
             else:
                 raise NotImplementedError(f"neuron type {type(nt).__name__} is not supported by the B200 backend")
@@ -593,7 +594,7 @@ class _Lowerer:
             for c in outs:
                 size_out = self._out_size(c)
                 out_vec = int(dev_col[self.dec_col[c]])
-                if isinstance(c, ns.Connection) and c in pes_rule:
+                if compat.is_connection(c) and c in pes_rule:
                     rin, lrt = pes_rule[c]
                     d_off = n_ldec
                     n_ldec += size_out * n
@@ -610,7 +611,7 @@ class _Lowerer:
                     if lrt.pre_synapse is None:
                         decay = 0.0
                     else:
-                        decay = float(np.exp(-dt / lrt.pre_synapse.tau))
+                        decay = float(np.exp(-dt / compat.synapse_tau(lrt.pre_synapse)))
                     pes_trace.append((act0, a_off, n, np.float32(decay), np.float32(1.0 - decay)))
                     pes_level = max(pes_level, lvl)
                     pes_desc.append([n, size_out, d_off, a_off, act0, err_row0, out_vec,
@@ -649,7 +650,7 @@ class _Lowerer:
         lin_rows, lin_ab = [], []
         for key, mat in filt_in.items():
             f0, size = plan.filters[key]
-            tau = key.synapse.tau
+            tau = compat.synapse_tau(key.synapse)
             a64 = np.exp(-dt / tau) if tau > 0 else 0.0     # Lowpass(0) (slam_loihi.py:233): a pure one-step delay
             a, b = np.float32(a64), np.float32(1.0 - a64)
             r0 = add_rows(mat)
@@ -666,7 +667,7 @@ class _Lowerer:
         for probe in self.probes:
             period = 1 if probe.sample_every is None else int(round(probe.sample_every / dt))
             obj = probe.obj
-            if isinstance(obj, ns.Neurons):
+            if compat.is_neurons(obj):
                 # neuron-output probes (run_pathint_gif.py:157-159: ``ea_ensembles[k].neurons[:500]``, synapse=None):
                 # the step's activity rows are copied to the probe block by the row program (kind 5)
                 if probe.synapse is not None:
@@ -679,7 +680,7 @@ class _Lowerer:
                     lin_rows.append([plan.ens_act[obj.ensemble] + int(k), 5, n_probe_rows + i])
                     lin_ab.append([0.0, 1.0])
                 n_probe_rows += len(sel)
-            elif isinstance(obj, (ns.Node, ns.Ensemble)):
+            elif compat.kind(obj) in ("node", "ensemble"):
                 if probe in self.filt_col:
                     mat = self._eye(self.filt_col[probe], probe.size_in)
                 else:
@@ -690,11 +691,11 @@ class _Lowerer:
                     lin_rows.append([r0 + i, 1, n_probe_rows + i])
                     lin_ab.append([0.0, 1.0])
                 n_probe_rows += probe.size_in
-            elif isinstance(obj, ns.Connection) and probe.attr == "weights":
+            elif compat.is_connection(obj) and probe.attr == "weights":
                 if obj not in plan.learned_dec:
                     raise NotImplementedError("'weights' probes are supported on PES-learned connections")
                 info = ProbeInfo(probe, "weights", period=period, conn=obj)
-            elif isinstance(obj, ns.LearningRule) and probe.attr == "scaled_encoders":
+            elif compat.is_learning_rule(obj) and probe.attr == "scaled_encoders":
                 info = ProbeInfo(probe, "scaled_encoders", period=period, ens=obj.connection.post_obj)
             else:
                 raise NotImplementedError(f"probe {probe!r} is outside the hot path")
@@ -783,7 +784,7 @@ class _Lowerer:
         return ent
 
     def _dec_weights(self, c):
-        if isinstance(c, ns.Connection):
+        if compat.is_connection(c):
             if _ens_to_neurons(c):
                 return np.asarray(self.model.params[c].decoders, dtype=np.float64)
             return np.asarray(self.model.params[c].weights, dtype=np.float64)
@@ -791,7 +792,7 @@ class _Lowerer:
 
     def _probe_expr(self, probe):
         obj = probe.obj
-        if isinstance(obj, ns.Ensemble):
+        if compat.is_ensemble(obj):
             return self._dec_expr(probe)
         return self.expr_out(obj)[_idx(probe.slice, obj.size_out)].tocsr()
 
