@@ -96,6 +96,10 @@ int ssb_last_run_ms(ssb_sim* s, float* ms);
  *        10 ens_voja */
 int ssb_kernel_times(ssb_sim* s, float* ms_per_kind, long long* launches_per_kind, int n_kinds);
 long long ssb_total_launches(ssb_sim* s);
+/* Timeline of the launches since ssb_set_profiling(s, 2) ("timeline" profiling: per-launch CUDA events recorded on the
+ * dependency streams the launches really use, so concurrency between the streams is preserved): start / end in ms since
+ * that call and the kernel kind of every launch, in host launch order.  *n_out = launches available. */
+int ssb_timeline(ssb_sim* s, float* start_ms, float* end_ms, int* kinds, int max_n, int* n_out);
 /* CUDA-event marks on the library stream (4 slots) and the device time between two of them:
  * brackets a timed region that spans several ssb_run_steps / table / probe calls. */
 int ssb_mark(ssb_sim* s, int slot);

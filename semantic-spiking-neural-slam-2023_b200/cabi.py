@@ -56,6 +56,7 @@ def load():
         "ssb_last_run_ms": (I, [P, C.POINTER(C.c_float)]),
         "ssb_kernel_times": (I, [P, P, P, I]),
         "ssb_total_launches": (LL, [P]),
+        "ssb_timeline": (I, [P, P, P, P, I, C.POINTER(I)]),
         "ssb_mark": (I, [P, I]),
         "ssb_mark_elapsed_ms": (I, [P, I, I, C.POINTER(C.c_float)]),
         "ssb_ssp_encode": (I, [I, P, P, P, LL, I, I]),
@@ -75,7 +76,7 @@ def load():
 EXPORTS = ("ssb_create", "ssb_set_array", "ssb_set_scalar", "ssb_finalize", "ssb_upload", "ssb_download",
            "ssb_set_tables", "ssb_rebase_tables", "ssb_run_steps", "ssb_run_steps_io", "ssb_io_wait", "ssb_synth_setup", "ssb_synth_steps", "ssb_read_probes", "ssb_n_steps",
            "ssb_n_trials_padded", "ssb_sync", "ssb_reset", "ssb_destroy", "ssb_set_profiling", "ssb_last_run_ms",
-           "ssb_kernel_times", "ssb_total_launches", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_ssp_encode", "ssb_ssp_decode_argmax", "ssb_host_alloc",
+           "ssb_kernel_times", "ssb_total_launches", "ssb_timeline", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_ssp_encode", "ssb_ssp_decode_argmax", "ssb_host_alloc",
            "ssb_host_free", "ssb_last_error", "ssb_version")
 
 

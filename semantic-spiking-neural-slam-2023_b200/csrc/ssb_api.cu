@@ -172,6 +172,10 @@ struct ssb_sim {
     int tab_steps = 0;
     // timing
     bool profiling = false;
+    bool timeline = false;                  // profiling with the dependency streams kept (per-launch start / end times)
+    cudaEvent_t ev_timeline0 = nullptr;
+    std::vector<float> tl_start, tl_end;
+    std::vector<int> tl_kind;
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
     cudaEvent_t ev_mark[4] = {nullptr, nullptr, nullptr, nullptr};
     bool run_timed = false;
@@ -267,16 +271,18 @@ struct LaunchTimer {
     ssb_sim* s;
     cudaEvent_t* ev = nullptr;
     int kind;
-    LaunchTimer(ssb_sim* s_, int kind_) : s(s_), kind(kind_) {
+    cudaStream_t st;
+    // `st_`: the stream the launch goes to (timeline mode keeps the dependency streams, so the event pair must sit on it)
+    LaunchTimer(ssb_sim* s_, int kind_, cudaStream_t st_ = nullptr) : s(s_), kind(kind_), st(st_ ? st_ : s_->stream) {
         s->kind_launches[kind]++;
         s->total_launches++;
         if (s->profiling) {
             ev = next_events(s, kind);
-            cudaEventRecord(ev[0], s->stream);
+            cudaEventRecord(ev[0], st);
         }
     }
     ~LaunchTimer() {
-        if (ev) cudaEventRecord(ev[1], s->stream);
+        if (ev) cudaEventRecord(ev[1], st);
         if (s->debug_sync && !s->debug_failed) {   // SSB_DEBUG_SYNC=1: find the launch that faults
             cudaError_t e = cudaStreamSynchronize(s->stream);
             if (e != cudaSuccess) {
@@ -291,10 +297,24 @@ struct LaunchTimer {
 int collect_profile(ssb_sim* s) {
     if (s->ev_used.empty()) return 0;
     SSB_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->timeline) {
+        SSB_CUDA(cudaDeviceSynchronize());
+        s->tl_start.clear();
+        s->tl_end.clear();
+        s->tl_kind.clear();
+    }
     for (auto& u : s->ev_used) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, s->ev_pool[u.second], s->ev_pool[u.second + 1]);
         s->kind_ms[u.first] += ms;
+        if (s->timeline && s->ev_timeline0) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, s->ev_timeline0, s->ev_pool[u.second]);
+            cudaEventElapsedTime(&b, s->ev_timeline0, s->ev_pool[u.second + 1]);
+            s->tl_start.push_back(a);
+            s->tl_end.push_back(b);
+            s->tl_kind.push_back(u.first);
+        }
     }
     s->ev_used.clear();
     return 0;
@@ -545,7 +565,7 @@ int pes_flush(ssb_sim* s) {
 }
 
 void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
-    LaunchTimer t(s, K_PES);
+    LaunchTimer t(s, K_PES, st);
     if (s->pes_h.K > 0) {
         dim3 grid;
         int max_chunks, max_rows = 0;
@@ -866,14 +886,14 @@ void launch_inputs(ssb_sim* s, cudaStream_t st, int i_rel) {
     const SsbCtx& c = s->ctx;
     const int G = s->n_groups;
     if (s->synth_on) {
-        LaunchTimer t(s, K_BEGIN);
+        LaunchTimer t(s, K_BEGIN, st);
         const int d = s->synth.d;
         const size_t small_smem = (size_t)(2 * d * 32 + s->synth.n_lm * d + s->synth.n_lm * s->synth.dim * 32) * sizeof(float) +
                                   (size_t)s->synth.n_lm * 32 + 32;
         if (d <= 128 && s->synth.n_lm < 255 && small_smem <= 200 * 1024) k_synth<true><<<G, 256, small_smem, st>>>(c, s->synth, i_rel);
         else k_synth<false><<<G, 256, (size_t)2 * d * 32 * sizeof(float), st>>>(c, s->synth, i_rel);
     } else if (s->nt > 0) {
-        LaunchTimer t(s, K_BEGIN);
+        LaunchTimer t(s, K_BEGIN, st);
         dim3 grid(((int)s->nt + 3) / 4, G);
         k_begin<<<grid, 128, 0, st>>>(c, i_rel);
     }
@@ -884,7 +904,7 @@ void launch_inputs(ssb_sim* s, cudaStream_t st, int i_rel) {
 int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next = false) {
     const SsbCtx& c = s->ctx;
     const int G = s->n_groups;
-    const bool par = s->parallel && !s->profiling && !s->debug_sync;
+    const bool par = s->parallel && (!s->profiling || s->timeline) && !s->debug_sync;
     cudaStream_t A = s->stream, B = par ? s->aux[0] : A, C = par ? s->aux[1] : A, D = par ? s->aux[2] : A;
     const bool any_inputs = s->synth_on || s->nt > 0;
     if (any_inputs && !(have_inputs && par)) launch_inputs(s, A, i_rel);
@@ -898,7 +918,7 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
         const int* st = &s->h_stages[lvl * 12];
         const LevelInfo& li = s->levels[lvl];
         if (st[11] > 0) {   // materialise this level's sink rows (ensemble / node inputs, PES errors)
-            LaunchTimer t(s, K_LIN);
+            LaunchTimer t(s, K_LIN, A);
             launch_lin(s, A, lvl, i_rel);
         }
         const bool pes_here = !pes_done && lvl == s->pes_level;
@@ -910,11 +930,11 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
         if (useD) stream_dep(s, A, D);
         b_used = b_used || useB;
         if (li.n_voja > 0) {
-            LaunchTimer t(s, K_VOJA);
+            LaunchTimer t(s, K_VOJA, B);
             launch_wide(s, B, st, true, i_rel);
         }
         if (li.n_static > 0) {
-            LaunchTimer t(s, K_WIDE);
+            LaunchTimer t(s, K_WIDE, D);
             launch_wide(s, D, st, false, i_rel);
         }
         if (pes_here) {   // every PES pre-ensemble has produced its activities
@@ -927,23 +947,23 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
             const int* d = &s->h_cleanup[ci * 6];
             const CleanupDev& cd = s->cleanups[ci];
             {
-                LaunchTimer t(s, K_SCAN);
+                LaunchTimer t(s, K_SCAN, C);
                 dispatch_scan(C, true, d[2], G, c, s->d_cleanup + ci * 6, s->d_W + d[3], cd, i_rel);
             }
             {
-                LaunchTimer t(s, K_PICK);
+                LaunchTimer t(s, K_PICK, C);
                 k_cleanup_pick<<<G, 256, 0, C>>>(d[1], d[2], scan_n_cand(cd), cd.cx, cd.pval, cd.pidx, cd.s64,
                                                  s->d_W + d[3], s->vec, (int)s->nv, d[5], cd.idx, nullptr, 0, 0,
                                                  scan_eps_floor(cd));
             }
         }
         if (st[9] > 0) {
-            LaunchTimer t(s, K_GATE);
+            LaunchTimer t(s, K_GATE, C);
             dim3 grid(G, st[9]);
             k_gate<<<grid, 256, 0, C>>>(c, s->d_gate, st[8], i_rel);
         }
         if (st[1] > 0) {
-            LaunchTimer t(s, K_SMALL);
+            LaunchTimer t(s, K_SMALL, A);
             // items are sorted by neuron count (descending): the leading ones get a whole CTA per trial group
             int n_split = 0;
             while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
@@ -953,7 +973,7 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
         }
         if (st[5] > 0) {
             if (li.dec_needs_voja) stream_dep(s, B, D);   // recorded after the Voja kernel (and k_pes, if any)
-            LaunchTimer t(s, K_DEC);
+            LaunchTimer t(s, K_DEC, D);
             int max_chunks = 1;
             size_t smem = 0;
             for (int i = 0; i < st[5]; ++i) {
@@ -979,7 +999,7 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
     if (b_used) stream_dep(s, B, A);
     if (!pes_done) launch_pes(s, A, i_rel);
     if (s->n_lin > 0) {
-        LaunchTimer t(s, K_LIN);
+        LaunchTimer t(s, K_LIN, A);
         launch_lin(s, A, s->n_levels, i_rel);
     }
     return 0;
@@ -1601,6 +1621,7 @@ void ssb_destroy(ssb_sim* s) {
     for (auto e : s->ev_pool) cudaEventDestroy(e);
     for (auto e : s->ev_mark)
         if (e) cudaEventDestroy(e);
+    if (s->ev_timeline0) cudaEventDestroy(s->ev_timeline0);
     if (s->ev_run0) cudaEventDestroy(s->ev_run0);
     if (s->ev_run1) cudaEventDestroy(s->ev_run1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -1611,6 +1632,13 @@ int ssb_set_profiling(ssb_sim* s, int on) {
     if (!s) return fail(-1, "ssb_set_profiling: null handle");
     if (collect_profile(s)) return -2;
     s->profiling = on != 0;
+    s->timeline = on == 2;
+    if (s->timeline) {
+        SSB_CUDA(cudaSetDevice(s->device));
+        if (!s->ev_timeline0) SSB_CUDA(cudaEventCreate(&s->ev_timeline0));
+        SSB_CUDA(cudaStreamSynchronize(s->stream));
+        SSB_CUDA(cudaEventRecord(s->ev_timeline0, s->stream));
+    }
     for (int k = 0; k < K_NKINDS; ++k) {
         s->kind_ms[k] = 0.f;
         s->kind_launches[k] = 0;
@@ -1638,6 +1666,19 @@ int ssb_kernel_times(ssb_sim* s, float* ms_per_kind, long long* launches_per_kin
 }
 
 long long ssb_total_launches(ssb_sim* s) { return s ? s->total_launches : -1; }
+
+int ssb_timeline(ssb_sim* s, float* start_ms, float* end_ms, int* kinds, int max_n, int* n_out) {
+    if (!s || !n_out) return fail(-1, "ssb_timeline: bad arguments");
+    if (collect_profile(s)) return -2;
+    const int n = (int)s->tl_kind.size();
+    *n_out = n;
+    for (int i = 0; i < n && i < max_n; ++i) {
+        if (start_ms) start_ms[i] = s->tl_start[i];
+        if (end_ms) end_ms[i] = s->tl_end[i];
+        if (kinds) kinds[i] = s->tl_kind[i];
+    }
+    return 0;
+}
 
 int ssb_mark(ssb_sim* s, int slot) {
     if (!s || slot < 0 || slot >= 4) return fail(-1, "ssb_mark: bad arguments");

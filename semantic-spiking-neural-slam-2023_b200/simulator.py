@@ -440,8 +440,20 @@ class Simulator:
         half = nf if (self._n_steps & 1) else 0   # values the *next* step will read
         return self._download("vec", 1 + half + f0, size)[:, :self.n_trials].T
 
-    def set_profiling(self, on=True):
-        cabi.check(self._lib.ssb_set_profiling(self._h, int(bool(on))), "ssb_set_profiling")
+    def set_profiling(self, on=True, timeline=False):
+        """Per-launch CUDA events.  Plain profiling serialises the launches on one stream (solo kernel times);
+        ``timeline=True`` keeps the dependency streams, so ``timeline()`` shows what really overlaps."""
+        cabi.check(self._lib.ssb_set_profiling(self._h, 2 if (on and timeline) else int(bool(on))), "ssb_set_profiling")
+
+    def timeline(self):
+        """[(kind, start_us, end_us)] of every launch since ``set_profiling(True, timeline=True)``, in launch order."""
+        import ctypes as C
+        n = C.c_int()
+        cabi.check(self._lib.ssb_timeline(self._h, None, None, None, 0, C.byref(n)), "ssb_timeline")
+        a, b, k = (C.c_float * n.value)(), (C.c_float * n.value)(), (C.c_int * n.value)()
+        cabi.check(self._lib.ssb_timeline(self._h, a, b, k, n.value, C.byref(n)), "ssb_timeline")
+        names = cabi.KERNEL_KINDS
+        return [(names[k[i]] if k[i] < len(names) else str(k[i]), a[i] * 1e3, b[i] * 1e3) for i in range(n.value)]
 
     def kernel_times(self):
         import ctypes as C
