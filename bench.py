@@ -45,6 +45,24 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = "run_slam d=55 pi_n_neurons=500 mem=970 circonv=100 landmarks=50 LIF PES+Voja (BASELINE configs[1])"
+FIXTURE_PATH = os.path.join(ROOT, "tests", "golden", "twoRooms_path_ds20.npy")
+# --workload: the default is the configuration BASELINE.json's metric is quoted on; the others are the remaining
+# BASELINE configs at their full network sizes (parity-tested in tests/, offered here for measurement)
+WORKLOADS = {
+    "cfg2": (WORKLOAD, dict(ssp_dim=55, pi_n_neurons=500, mem_n_neurons=970, circonv_n_neurons=100, n_landmarks=50, T=200.0)),
+    "cfg3": ("SLAMNetwork d=55 pi=800 mem=1000 circonv=100 length_scale=0.1 on the recorded twoRooms path (down-sampled "
+             "fixture, run_slam.py --path-data rules), one landmark set per trial (BASELINE configs[2])",
+             dict(ssp_dim=55, pi_n_neurons=800, mem_n_neurons=1000, circonv_n_neurons=100, n_landmarks=50, length_scale=0.1,
+                  path_data=FIXTURE_PATH, data_dt=0.02)),
+    "cfg4": ("SLAMViewNetwork d=97 pi=800 mem=970 landmarks=100 length_scale=0.3 PES+Voja on the recorded twoRooms path "
+             "(BASELINE configs[3])",
+             dict(ssp_dim=97, pi_n_neurons=800, mem_n_neurons=970, circonv_n_neurons=100, n_landmarks=100, length_scale=0.3,
+                  view=True, path_data=FIXTURE_PATH, data_dt=0.02)),
+    "cfg5": ("3-D SSP-SLAM HexagonalSSPSpace n_rotates=9 n_scales=9 (d=649), pi=500 mem=970 circonv=100, clean-up grid 30^3 "
+             "(BASELINE configs[4]; 512 trials per GPU)",
+             dict(ssp_dim=649, pi_n_neurons=500, mem_n_neurons=970, circonv_n_neurons=100, n_landmarks=50, T=200.0,
+                  domain_dim=3, grid_points_per_dim=30, view_rad=0.6)),
+}
 METRIC = "trial-timesteps/sec (SSP-SLAM)"
 UNIT = "trial-timesteps/s"
 
@@ -66,15 +84,18 @@ def parse():
                     help="simulator timesteps of the sustained leg (0 = skip; the default is >= 10 s at 1024 trials)")
     ap.add_argument("--sustained-chunk", type=int, default=2048)
     ap.add_argument("--seed", type=int, default=0)
-    return ap.parse_args()
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.workload == "cfg5" and args.trials == 1024:
+        args.trials = 512
+    return args
 
 
-def slam_scenario(n_trials, n_steps, seed, distinct, table_steps=None, trial0=0, workers=None):
+def slam_scenario(n_trials, n_steps, seed, distinct, table_steps=None, trial0=0, workers=None, workload="cfg2"):
     from sspslam_b200 import scenarios
-    return scenarios.make_slam(n_trials=n_trials, n_steps=n_steps, ssp_dim=55, pi_n_neurons=500, mem_n_neurons=970,
-                               circonv_n_neurons=100, n_landmarks=50, T=200.0, seed=seed, neuron_type="lif",
+    return scenarios.make_slam(n_trials=n_trials, n_steps=n_steps, seed=seed, neuron_type="lif",
                                distinct_tables=distinct, table_steps=table_steps, trial0=trial0, workers=workers,
-                               table_dtype=np.float32)
+                               table_dtype=np.float32, **WORKLOADS[workload][1])
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -204,7 +225,7 @@ def run_reference(args):
     from sspslam_b200.builder import build_model
     cores = len(os.sched_getaffinity(0))
     n_steps = (args.warmup + args.steps) * args.ref_chunk
-    sc = slam_scenario(cores, n_steps + 2, args.seed, distinct=cores, workers=1)
+    sc = slam_scenario(cores, n_steps + 2, args.seed, distinct=cores, workers=1, workload=args.workload)
     model = build_model(sc.network, dt=sc.dt)
     ctx = mp.get_context("fork")
     barrier, q = ctx.Barrier(cores), ctx.Queue()
@@ -223,7 +244,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "timesteps_per_step": args.ref_chunk, "trials": cores, "distinct_trials": cores},
+            "config": {"workload": WORKLOADS[args.workload][0], "timesteps_per_step": args.ref_chunk, "trials": cores, "distinct_trials": cores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -288,7 +309,7 @@ def run_b200(args):
     n_sust = 0 if args.no_synth else max(0, args.sustained_steps)
     cores = len(os.sched_getaffinity(0))
     sc = slam_scenario(B, total_steps + 2 + n_sust, args.seed, distinct=distinct, table_steps=total_steps + 2,
-                       trial0=rank * B, workers=max(1, cores // max(1, min(world, 8))))
+                       trial0=rank * B, workers=max(1, cores // max(1, min(world, 8))), workload=args.workload)
     trial_seeds = sharding.trial_seeds(world * B, rank, world)
     sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, trial_seeds=trial_seeds,
                     device=local, chunk_steps=n_phase)
@@ -428,7 +449,7 @@ def run_b200(args):
             "metric": METRIC, "value": tsteps / (value_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": value_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "trials_per_gpu": B, "timesteps_per_step": chunk, "weights": "shared",
+            "config": {"workload": WORKLOADS[args.workload][0], "trials_per_gpu": B, "timesteps_per_step": chunk, "weights": "shared",
                        "distinct_trials": world * distinct,
                        "trial_diversity": "every trial has its own band-limited random path (seed 1000*i), its own 50 R_d "
                                           "landmarks and its own start voltages; static weights shared (one network seed)"

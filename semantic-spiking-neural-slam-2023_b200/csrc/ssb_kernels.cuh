@@ -1,2726 +1,20 @@
-// sm_100a kernels of the SSP-SLAM step engine (device side).
-//
-// Layout rule: every per-trial arena is tiled by trial group, arena[g][row][32]: a warp's 32
-// lanes are the 32 trials of one group, a row is one 128-byte line, and consecutive rows of one
-// group are contiguous, so each warp streams a sequential address range (DRAM-page friendly) and
-// whole neuron ranges can be moved by 1-D TMA bulk copies.  Everything indexed by neuron /
-// weight is warp-uniform (broadcast from shared memory or L1/L2).  Static weights are shared by
-// all trials; learned matrices (Voja encoders, PES decoders) are per-trial rows of the same form.
-//
-// LIF state is ONE word per neuron: s >= 0 is the membrane voltage of a neuron that is not
-// refractory, s < 0 is minus the remaining refractory time (the voltage is exactly 0 then).  With
-// nengo's default min_voltage = 0 this is equivalent to the (voltage, refractory_time) pair: the
-// refractory time only matters while it is >= dt, and the voltage is pinned to 0 exactly then.
-//
-// Semantics restate nengo's operators, executed in dependency
-// levels instead of one operator at a time; the CPU checker is oracle/nengo_ref_sim.py.
+// sm_100a kernels of the SSP-SLAM step engine (device side), split by kernel family:
+//   ssb_common.cuh     context, step helpers, neuron models, TMA / mbarrier and tcgen05 / TMEM helpers (layout rules are there)
+//   ssb_inputs.cuh     k_begin, k_synth
+//   ssb_ens_small.cuh  k_ens_small
+//   ssb_ens_wide.cuh   k_wide_static, k_wide_static_tc, k_wide_voja
+//   ssb_decode.cuh     k_decode, k_decode_tc
+//   ssb_pes.cuh        k_pes, k_pes_hist, k_pes_defer, k_pes_fold, k_pes_clear
+//   ssb_cleanup.cuh    k_cleanup_scan, k_cleanup_scan_tc, k_cleanup_pick, k_gate
+//   ssb_lin.cuh        k_lin, k_advance
+//   ssb_ssp.cuh        k_ssp_encode, k_decode_prep
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
-
-#define SSB_TOPK 4
-#define SSB_SCAN_MAX_CHUNKS 512
-#define SSB_SM_CH 16          // neurons per TMA-staged chunk of the narrow-ensemble kernel
-#define SSB_SM_WMAX 16        // max packed weight stride (floats) of a narrow ensemble
-
-struct SsbCtx {
-    int G;                    // trial groups (32 trials each)
-    int nv, nf, nt, tab_row0, nn, n_act, n_lenc, n_ldec, n_afilt, n_probe, n_part;
-    int tab_cap, probe_cap;
-    float dt;
-    float* vec;               // [G][nv][32]   0: ones | 1..nf: filters A | nf+1..2nf: filters B | tables | scratch
-    const float* tab;         // [G][tab_cap][nt][32]
-    float* st;                // [G][nn][32]   packed LIF state
-    float* act;               // [G][n_act][32]
-    int* aflag;               // [G][n_act]: some trial of the group has a non-zero activity (sparse consumers skip on it)
-    float* lenc;              // [G][n_lenc][32]
-    float* ldec;              // [G][n_ldec][32]
-    float* afilt;             // [G][2*n_afilt][32]
-    float* probe;             // [G][probe_cap][n_probe][32]
-    float* part;              // [G][n_part][32] split-K partial sums of decode / PES launches
-    int* counters;            // split-K arrival counters, self-resetting
-    const float* W;           // shared static weights
-    const int* csr_ptr;
-    const int2* ent0;         // CSR entries (vec row, coefficient bits) resolved for even steps
-    const int2* ent1;         //   ... and for odd steps (filter columns point at the other half)
-    const float* ntypes;      // [n][8] = type, tau_rc, tau_ref, min_voltage, amplitude, fast_math, -, -
-    const long long* dyn;     // [0] completed steps, [1] first step of resident tables, [2] first step of probe buffer,
-                              // [3] first step of the resident synthesis indices
-};
-
-struct SsbStep {
-    long long step;
-    int odd;
-    const int2* ent_old;      // rows evaluated on the values this step reads (old filter states)
-    const int2* ent_new;      // ... on the half the previous step read (PES error of step-1)
-    int par_old, par_new;     // row offset of the filter half read / written this step
-};
-
-__device__ __forceinline__ SsbStep ssb_step(const SsbCtx& c, int i_rel) {
-    SsbStep s;
-    s.step = c.dyn[0] + i_rel;
-    s.odd = (int)(s.step & 1);
-    s.ent_old = s.odd ? c.ent1 : c.ent0;
-    s.ent_new = s.odd ? c.ent0 : c.ent1;
-    s.par_old = s.odd ? c.nf : 0;
-    s.par_new = s.odd ? 0 : c.nf;
-    return s;
-}
-
-// Group base pointers (lane already added): element of row r is p[r * 32].
-__device__ __forceinline__ float* ssb_grp(float* base, int rows, int g, int lane) {
-    return base + ((size_t)g * rows) * 32 + lane;
-}
-
-// One sink row: sparse linear combination of vec rows for the 32 trials of a group.  Entries are
-// warp-uniform 8-byte loads; the host pads every row to a multiple of 8 entries with (row 0,
-// coefficient 0), so the loop has no tail and the 8 per-trial source loads of a batch are independent.
-// `asm volatile` loads keep program order, so the compiler cannot re-serialise a batch to save registers:
-// all entry loads of a batch are issued, then all source loads, then the multiply-adds.
-__device__ __forceinline__ int2 ssb_ld_ent(const int2* p) {
-    int2 v;
-    asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ssb_ld_src(const float* p) {
-    float v;
-    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
-template <int NB>
-__device__ __forceinline__ float ssb_row_batch(const int2* __restrict__ ent, const float* vg, float acc) {
-    int2 e[NB];
-    float x[NB];
-#pragma unroll
-    for (int u = 0; u < NB; ++u) e[u] = ssb_ld_ent(ent + u);
-#pragma unroll
-    for (int u = 0; u < NB; ++u) x[u] = ssb_ld_src(vg + (size_t)e[u].x * 32);
-#pragma unroll
-    for (int u = 0; u < NB; ++u) acc = fmaf(__int_as_float(e[u].y), x[u], acc);
-    return acc;
-}
-
-// --------------------------------------------------------------------------------------
-// Neuron models.
-struct SsbNeuron {
-    int type;                 // 0 LIF, 1 LIFRate, 2 RectifiedLinear
-    bool fast;                // LIF with dt/tau_rc <= 1/16: polynomial expm1 / log1p, exact to fp32
-    float tau_rc, tau_ref, amp_dt, amp, dt, inv_dt, neg_dt_over_tau, c0;
-};
-
-__device__ __forceinline__ SsbNeuron ssb_neuron(const SsbCtx& c, int tid) {
-    const float* p = c.ntypes + tid * 8;
-    SsbNeuron n;
-    n.type = (int)p[0];
-    n.tau_rc = p[1];
-    n.tau_ref = p[2];
-    n.amp = p[4];
-    n.fast = p[5] != 0.f;
-    n.dt = c.dt;
-    n.amp_dt = p[4] / c.dt;
-    n.inv_dt = 1.0f / c.dt;
-    n.neg_dt_over_tau = (n.type == 0) ? -c.dt / p[1] : 0.f;
-    n.c0 = p[2] + c.dt;       // tau_ref + dt
-    return n;
-}
-
-// expm1(x) for -1/16 <= x <= 0 (x = -delta/tau_rc with delta <= dt): degree-5 Taylor, rel. error < 2e-9.
-__device__ __forceinline__ float ssb_expm1_small(float x) {
-    float p = 1.f / 120.f;
-    p = fmaf(p, x, 1.f / 24.f);
-    p = fmaf(p, x, 1.f / 6.f);
-    p = fmaf(p, x, 0.5f);
-    p = fmaf(p, x, 1.f);
-    return p * x;
-}
-
-// log1p(-z) for 0 <= z <= 1/16 (z = overshoot / (J - 1) <= 1 - exp(-dt/tau_rc)): 6 terms, rel. error < 1e-8.
-__device__ __forceinline__ float ssb_log1p_neg_small(float z) {
-    float p = -1.f / 6.f;
-    p = fmaf(p, z, -0.2f);
-    p = fmaf(p, z, -0.25f);
-    p = fmaf(p, z, -1.f / 3.f);
-    p = fmaf(p, z, -0.5f);
-    p = fmaf(p, z, -1.f);
-    return p * z;
-}
-
-// nengo LIF.step on the packed state (App. A.4), branch-free.  Returns the output (0 or amplitude/dt).
-//   m = min(s, 0) is minus the remaining refractory time, v = max(s, 0) the voltage (one of them is 0).
-//   nengo: refractory_time -= dt; delta = clip(dt - refractory_time, 0, dt)  =>  delta/dt = clip(2 + m/dt, 0, 1);
-//   the neuron stays refractory (state m + dt) exactly when that clip gives 0, i.e. refractory_time - dt >= dt.
-template <bool FAST>
-__device__ __forceinline__ float ssb_lif_packed(const SsbNeuron& n, float J, float& s) {
-    const float m = fminf(s, 0.f);
-    float v = fmaxf(s, 0.f);
-    const float dn = __saturatef(fmaf(m, n.inv_dt, 2.f));  // delta / dt
-    const float x = dn * n.neg_dt_over_tau;                // -delta / tau_rc
-    const float em1 = FAST ? ssb_expm1_small(x) : expm1f(x);
-    v = fmaf(v - J, em1, v);                               // v -= (J - v) * expm1(-delta / tau_rc)
-    const bool spiked = v > 1.f;
-    const float z = __fdividef(v - 1.f, J - 1.f);          // used only when spiked (then J > v > 1)
-    const float lp = FAST ? ssb_log1p_neg_small(z) : log1pf(-z);
-    const float r_new = fmaf(n.tau_rc, lp, n.c0);          // tau_ref + dt + tau_rc * log1p(-z) > 0
-    const float keep = (dn > 0.f) ? fmaxf(v, 0.f) : m + n.dt;
-    s = spiked ? -r_new : keep;
-    return spiked ? n.amp_dt : 0.f;
-}
-
-// Two neurons per lane with sm_100's packed fp32 instructions (FFMA2 / FADD2 / FMUL2: one issue slot for two
-// operations).  k_ens_small is issue-bound, and two thirds of the LIF update are fma / add / mul chains.
-__device__ __forceinline__ float2 ssb_fma2(float2 a, float2 b, float2 c) {
-    float2 r;
-    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;"
-        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
-          "l"(*reinterpret_cast<unsigned long long*>(&c)));
-    return r;
-}
-__device__ __forceinline__ float2 ssb_mul2(float2 a, float2 b) {
-    float2 r;
-    asm("mul.rn.ftz.f32x2 %0, %1, %2;"
-        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return r;
-}
-__device__ __forceinline__ float2 ssb_add2(float2 a, float2 b) {
-    float2 r;
-    asm("add.rn.ftz.f32x2 %0, %1, %2;"
-        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-    return r;
-}
-__device__ __forceinline__ float2 ssb_splat(float x) { return make_float2(x, x); }
-
-// ssb_lif_packed<true> for two neurons at once (same arithmetic, element-wise): s0/s1 states, J0/J1 currents.
-__device__ __forceinline__ float2 ssb_lif_pair(const SsbNeuron& n, float2 J, float2& s) {
-    const float2 m = make_float2(fminf(s.x, 0.f), fminf(s.y, 0.f));
-    float2 v = make_float2(fmaxf(s.x, 0.f), fmaxf(s.y, 0.f));
-    float2 dn = ssb_fma2(m, ssb_splat(n.inv_dt), ssb_splat(2.f));
-    dn = make_float2(__saturatef(dn.x), __saturatef(dn.y));
-    const float2 x = ssb_mul2(dn, ssb_splat(n.neg_dt_over_tau));
-    float2 p = ssb_fma2(ssb_splat(1.f / 120.f), x, ssb_splat(1.f / 24.f));     // expm1(x), degree-5 Taylor
-    p = ssb_fma2(p, x, ssb_splat(1.f / 6.f));
-    p = ssb_fma2(p, x, ssb_splat(0.5f));
-    p = ssb_fma2(p, x, ssb_splat(1.f));
-    const float2 em1 = ssb_mul2(p, x);
-    const float2 vmj = ssb_fma2(J, ssb_splat(-1.f), v);                        // v - J
-    v = ssb_fma2(vmj, em1, v);
-    const bool sp0 = v.x > 1.f, sp1 = v.y > 1.f;
-    const float2 vm1 = ssb_add2(v, ssb_splat(-1.f)), jm1 = ssb_add2(J, ssb_splat(-1.f));
-    float2 rc;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc.x) : "f"(jm1.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc.y) : "f"(jm1.y));
-    const float2 z = ssb_mul2(vm1, rc);
-    float2 q = ssb_fma2(ssb_splat(-1.f / 6.f), z, ssb_splat(-0.2f));            // log1p(-z), 6 terms
-    q = ssb_fma2(q, z, ssb_splat(-0.25f));
-    q = ssb_fma2(q, z, ssb_splat(-1.f / 3.f));
-    q = ssb_fma2(q, z, ssb_splat(-0.5f));
-    q = ssb_fma2(q, z, ssb_splat(-1.f));
-    const float2 lp = ssb_mul2(q, z);
-    const float2 r_new = ssb_fma2(ssb_splat(n.tau_rc), lp, ssb_splat(n.c0));
-    const float2 mdt = ssb_add2(m, ssb_splat(n.dt));
-    const float keep0 = (dn.x > 0.f) ? fmaxf(v.x, 0.f) : mdt.x;
-    const float keep1 = (dn.y > 0.f) ? fmaxf(v.y, 0.f) : mdt.y;
-    s.x = sp0 ? -r_new.x : keep0;
-    s.y = sp1 ? -r_new.y : keep1;
-    return make_float2(sp0 ? n.amp_dt : 0.f, sp1 ? n.amp_dt : 0.f);
-}
-
-__device__ __forceinline__ float ssb_rate(const SsbNeuron& n, float J) {
-    if (n.type == 1) {
-        const float j = J - 1.f;
-        return j > 0.f ? n.amp / (n.tau_ref + n.tau_rc * log1pf(1.f / j)) : 0.f;
-    }
-    return n.amp * fmaxf(J, 0.f);
-}
-
-// MODE 0: LIF with polynomial transcendental functions; MODE 1: anything else (uniform run-time switch).
-template <int MODE>
-__device__ __forceinline__ float ssb_neuron_apply(const SsbNeuron& n, float J, float& s) {
-    if (MODE == 0) return ssb_lif_packed<true>(n, J, s);
-    if (n.type == 0) return ssb_lif_packed<false>(n, J, s);
-    return ssb_rate(n, J);
-}
-
-// --------------------------------------------------------------------------------------
-// TMA 1-D bulk copies + mbarriers (one elected lane issues; the warp waits on the barrier).
-__device__ __forceinline__ uint32_t ssb_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void ssb_mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ssb_smem(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void ssb_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ssb_smem(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ssb_mbar_wait(unsigned long long* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(ssb_smem(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void ssb_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     ssb_smem(dst)),
-                 "l"(src), "r"(bytes), "r"(ssb_smem(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void ssb_bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ssb_smem(src)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void ssb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void ssb_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void ssb_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void ssb_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// --------------------------------------------------------------------------------------
-// tcgen05 / TMEM helpers shared by the tensor-core kernels (grid scan, static decoders).
-#define SSB_TC_ROWS 128
-
-__host__ __device__ __forceinline__ float ssb_tf32_round(float x) {   // round-to-nearest-even to a 10-bit mantissa
-#ifdef __CUDA_ARCH__
-    uint32_t u = __float_as_uint(x);
-#else
-    uint32_t u;
-    memcpy(&u, &x, 4);
-#endif
-    u += 0xfffu + ((u >> 13) & 1u);
-    u &= 0xffffe000u;
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(u);
-#else
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
-#endif
-}
-
-__device__ __forceinline__ uint64_t ssb_umma_desc(const void* smem_ptr) {
-    const uint32_t a = ssb_smem(smem_ptr);
-    return (uint64_t)((a >> 4) & 0x3fffu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
-}
-
-// same, with the stride between 16-byte K chunks given (= 128 B x row groups of the tile)
-__device__ __forceinline__ uint64_t ssb_umma_desc_lbo(const void* smem_ptr, uint32_t lbo_bytes) {
-    const uint32_t a = ssb_smem(smem_ptr);
-    return (uint64_t)((a >> 4) & 0x3fffu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void ssb_umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                              uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void ssb_tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    // the registers are valid only after wait::ld; tying them to the wait keeps every use behind it
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void ssb_tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void ssb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void ssb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// --------------------------------------------------------------------------------------
-// Start of a step: the input-table rows of this step become ordinary vec rows, so every CSR entry
-// addresses one arena.  grid (ceil(nt/4), G) x 128
-__global__ void __launch_bounds__(128) k_begin(SsbCtx c, int i_rel) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = blockIdx.x * 4 + warp, g = blockIdx.y;
-    if (row >= c.nt) return;
-    const long long s_loc = c.dyn[0] + i_rel - c.dyn[1];
-    const float* src = c.tab + (((size_t)g * c.tab_cap + (size_t)s_loc) * c.nt + row) * 32 + lane;
-    const int par = (int)((c.dyn[0] + i_rel) & 1) ? c.nt : 0;      // the input rows are double-buffered by step parity
-    ssb_grp(c.vec, c.nv, g, lane)[(size_t)(c.tab_row0 + par + row) * 32] = __ldcs(src);
-}
-
-// --------------------------------------------------------------------------------------
-// On-device input synthesis: what the reference's per-step Python closures compute
-// (sspslam/networks/slam.py:442-497 get_slam_input_functions2, experiments/run_slam.py:164-169,
-// run_pathint.py:134-136), from per-trial paths / landmarks instead of 168-float-per-step host tables:
-//   vel      = vels_scaled[i_prev]
-//   init     = encode(path[i_prev]) while t < init_time, else 0
-//   lm_sp    = sum of the landmark SPs within view_rad of path[i_prev]
-//   lmvec    = sum_l in view encode(landmark_l - path[i_cur]) = IDFT(sum_l exp(i A v_l)): the complex exponentials
-//              are summed first, so one inverse-DFT mat-vec per trial serves any number of landmarks
-//   nolm     = 0 if some landmark is in view, else none_in_view_value
-// The float-fragile step indices (int((t-dt)/dt), floor(t/dt)) stay on the host: 12 bytes per step instead of a table row.
-// CTA = one trial group, 8 warps; warps split the frequency index k (phase 1) and the output index m (phase 2).
-struct SsbSynth {
-    const float* path;        // [G][T*dim][32]
-    const float* vel;         // [G][T*dim][32]
-    const float* lm;          // [G][n_lm*dim][32]
-    const float* phases;      // [d][dim]   A / length_scale
-    const float* lm_sp;       // [n_lm][d]
-    const float* cosT;        // [d][d]     cos(2 pi k m / d)
-    const float* sinT;
-    const int* idx;           // [steps][4] i_prev, i_cur, init flag, -
-    int T, dim, d, n_lm;
-    int vel_col, init_col, lmvec_col, lmsp_col, nolm_col;
-    float view_rad, none_value;
-};
-
-// inverse DFT of the summed exponentials: out[m] = (1/d) sum_k (C_k cos(2 pi k m / d) - S_k sin(2 pi k m / d)).
-// RECUR: the twiddles of one output m are generated by the rotation recurrence from (cos, sin)(2 pi m / d) (row k = 1 of
-// the tables; error grows like d * 2^-24, used for d <= 128); otherwise they are read from the global tables.
-template <bool RECUR>
-__device__ __forceinline__ void ssb_synth_idft(const SsbSynth& y, const float* sC, const float* sS, float* out_row0, int lane,
-                                               int warp) {
-    const float inv_d = 1.f / (float)y.d;
-    for (int m = warp; m < y.d; m += 8) {
-        float a0 = 0.f, a1 = 0.f;
-        if (RECUR) {
-            const float cm = __ldg(y.cosT + y.d + m), sm_ = __ldg(y.sinT + y.d + m);   // k = 1
-            float ck = 1.f, sk = 0.f;
-#pragma unroll 4
-            for (int k = 0; k < y.d; ++k) {
-                a0 = fmaf(sC[k * 32 + lane], ck, a0);
-                a1 = fmaf(sS[k * 32 + lane], sk, a1);
-                const float cn = fmaf(ck, cm, -sk * sm_);
-                sk = fmaf(sk, cm, ck * sm_);
-                ck = cn;
-            }
-        } else {
-#pragma unroll 8
-            for (int k = 0; k < y.d; ++k) {
-                a0 = fmaf(sC[k * 32 + lane], __ldg(y.cosT + (size_t)k * y.d + m), a0);
-                a1 = fmaf(sS[k * 32 + lane], __ldg(y.sinT + (size_t)k * y.d + m), a1);
-            }
-        }
-        out_row0[(size_t)m * 32] = (a0 - a1) * inv_d;
-    }
-}
-
-// dynamic smem: 2*d*32 floats (C, S per trial); SMALL (d <= 128) adds n_lm*d (SPs) + n_lm*dim*32 (coordinates) floats
-// + n_lm*32 bytes (per-trial list of the landmarks in view)
-template <bool SMALL>
-__global__ void __launch_bounds__(256) k_synth(SsbCtx c, SsbSynth y, int i_rel) {
-    extern __shared__ float sm[];
-    float* sC = sm;                               // [d][32]
-    float* sS = sm + (size_t)y.d * 32;            // [d][32]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.x;
-    const float* lg = y.lm + ((size_t)g * y.n_lm * y.dim) * 32 + lane;   // landmark coordinates of this trial: row * 32
-    const float* lsp = y.lm_sp;
-    unsigned char* s_list = nullptr;
-    if (SMALL) {   // stage the landmark SPs and this group's landmark coordinates once per CTA (one load round)
-        float* s_sp = sS + (size_t)y.d * 32;                             // [n_lm][d]
-        float* s_lm = s_sp + (size_t)y.n_lm * y.d;                       // [n_lm*dim][32]
-        s_list = reinterpret_cast<unsigned char*>(s_lm + (size_t)y.n_lm * y.dim * 32);   // [n_lm][32]
-#pragma unroll 16
-        for (int i = threadIdx.x; i < y.n_lm * y.d; i += 256) s_sp[i] = __ldg(y.lm_sp + i);
-#pragma unroll 16
-        for (int r = warp; r < y.n_lm * y.dim; r += 8) s_lm[r * 32 + lane] = lg[(size_t)r * 32];
-        lsp = s_sp;
-        lg = s_lm + lane;
-    }
-    const long long s_loc = c.dyn[0] + i_rel - c.dyn[3];   // dyn[3]: first step of the resident index block (not baked into graphs)
-    const int* ix = y.idx + s_loc * 4;
-    const int ip = ix[0], ic = ix[1], init = ix[2];
-    float* tabv = ssb_grp(c.vec, c.nv, g, lane) + (size_t)(c.tab_row0 + (((c.dyn[0] + i_rel) & 1) ? c.nt : 0)) * 32;
-    const float* pg = y.path + ((size_t)g * y.T * y.dim) * 32 + lane;
-    float pp[3] = {0.f, 0.f, 0.f}, pc[3] = {0.f, 0.f, 0.f};
-    for (int a = 0; a < y.dim; ++a) {
-        pp[a] = pg[(size_t)(ip * y.dim + a) * 32];
-        pc[a] = pg[(size_t)(ic * y.dim + a) * 32];
-    }
-    if (warp == 0 && y.vel_col >= 0) {
-        const float* vp = y.vel + ((size_t)g * y.T * y.dim) * 32 + lane;
-        for (int a = 0; a < y.dim; ++a) tabv[(size_t)(y.vel_col + a) * 32] = vp[(size_t)(ip * y.dim + a) * 32];
-    }
-    if (SMALL) __syncthreads();
-    bool any_view = false;
-    if (SMALL) {
-        // every trial lists its own landmarks in view (warp 0), so phase 1 loops over the longest list (a few entries)
-        // instead of over every landmark some trial of the group can see
-        int cnt = 0;
-        if (warp == 0) {
-            for (int l = 0; l < y.n_lm; ++l) {
-                float d2 = 0.f;
-                for (int a = 0; a < y.dim; ++a) {
-                    const float dv = lg[(size_t)(l * y.dim + a) * 32] - pp[a];
-                    d2 = fmaf(dv, dv, d2);
-                }
-                if (sqrtf(d2) <= y.view_rad) s_list[(cnt++) * 32 + lane] = (unsigned char)l;
-            }
-            if (cnt < y.n_lm) s_list[cnt * 32 + lane] = 255;     // terminator
-            if (y.nolm_col >= 0) tabv[(size_t)y.nolm_col * 32] = cnt > 0 ? 0.f : y.none_value;
-        }
-        __syncthreads();
-        // phase 1: this thread owns the frequencies k = warp + 8 j of its trial
-        constexpr int KS = 16;
-        float rC[KS], rS[KS], rL[KS], ph[KS][3];
-#pragma unroll
-        for (int j = 0; j < KS; ++j) {
-            rC[j] = rS[j] = rL[j] = 0.f;
-            const int k = warp + 8 * j;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) ph[j][a] = (k < y.d && a < y.dim) ? __ldg(y.phases + k * y.dim + a) : 0.f;
-        }
-        bool alive = true;
-        for (int q = 0; q < y.n_lm; ++q) {
-            const int l = s_list[q * 32 + lane];
-            alive = alive && l != 255;                           // entries after a trial's terminator are not initialised
-            const bool on = alive;
-            if (!__any_sync(0xffffffffu, on)) break;             // nobody has a q-th entry
-            const int ls = on ? l : 0;
-            float v[3] = {0.f, 0.f, 0.f};
-            for (int a = 0; a < y.dim; ++a) v[a] = lg[(size_t)(ls * y.dim + a) * 32] - pc[a];
-            const float w = on ? 1.f : 0.f;
-#pragma unroll
-            for (int j = 0; j < KS; ++j) {
-                const int k = warp + 8 * j;
-                if (k < y.d) {
-                    const float th = fmaf(ph[j][0], v[0], fmaf(ph[j][1], v[1], ph[j][2] * v[2]));
-                    float sn, cs;
-                    sincosf(th, &sn, &cs);
-                    rC[j] = fmaf(w, cs, rC[j]);
-                    rS[j] = fmaf(w, sn, rS[j]);
-                    if (y.lmsp_col >= 0) rL[j] = fmaf(w, lsp[(size_t)ls * y.d + k], rL[j]);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < KS; ++j) {
-            const int k = warp + 8 * j;
-            if (k < y.d) {
-                sC[k * 32 + lane] = rC[j];
-                sS[k * 32 + lane] = rS[j];
-                if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] = rL[j];
-            }
-        }
-    } else {
-        for (int k = warp; k < y.d; k += 8) {
-            sC[k * 32 + lane] = 0.f;
-            sS[k * 32 + lane] = 0.f;
-            if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] = 0.f;
-        }
-        for (int l = 0; l < y.n_lm; ++l) {
-            float v[3] = {0.f, 0.f, 0.f}, d2 = 0.f;
-            for (int a = 0; a < y.dim; ++a) {
-                const float q = lg[(size_t)(l * y.dim + a) * 32];
-                const float dv = q - pp[a];
-                d2 = fmaf(dv, dv, d2);
-                v[a] = q - pc[a];
-            }
-            const bool in = sqrtf(d2) <= y.view_rad;
-            any_view = any_view || in;
-            if (!__any_sync(0xffffffffu, in)) continue;
-            for (int k = warp; k < y.d; k += 8) {     // each (k, lane) is owned by one thread: plain read-modify-write
-                float th = 0.f;
-                for (int a = 0; a < y.dim; ++a) th = fmaf(__ldg(y.phases + k * y.dim + a), v[a], th);
-                float sn, cs;
-                sincosf(th, &sn, &cs);
-                if (in) {
-                    sC[k * 32 + lane] += cs;
-                    sS[k * 32 + lane] += sn;
-                    if (y.lmsp_col >= 0) tabv[(size_t)(y.lmsp_col + k) * 32] += __ldg(y.lm_sp + (size_t)l * y.d + k);
-                }
-            }
-        }
-        if (warp == 0 && y.nolm_col >= 0) tabv[(size_t)y.nolm_col * 32] = any_view ? 0.f : y.none_value;
-    }
-    __syncthreads();
-    if (y.lmvec_col >= 0) ssb_synth_idft<SMALL>(y, sC, sS, tabv + (size_t)y.lmvec_col * 32, lane, warp);
-    if (y.init_col >= 0) {
-        if (init) {                               // the first init_time seconds only
-            __syncthreads();
-            for (int k = warp; k < y.d; k += 8) {
-                float th = 0.f;
-                for (int a = 0; a < y.dim; ++a) th = fmaf(__ldg(y.phases + k * y.dim + a), pp[a], th);
-                float sn, cs;
-                sincosf(th, &sn, &cs);
-                sC[k * 32 + lane] = cs;
-                sS[k * 32 + lane] = sn;
-            }
-            __syncthreads();
-            ssb_synth_idft<SMALL>(y, sC, sS, tabv + (size_t)y.init_col * 32, lane, warp);
-        } else {
-            for (int m = warp; m < y.d; m += 8) tabv[(size_t)(y.init_col + m) * 32] = 0.f;
-        }
-    }
-}
-
-// --------------------------------------------------------------------------------------
-// Narrow ensembles (VCO 3-D x 500, product squares 1-D x 50): fused encode -> neuron -> decode.
-// Each warp walks a contiguous neuron range of one (ensemble, trial group) in chunks of SSB_SM_CH
-// neurons.  A chunk's packed weights [bias, enc[DIMS], dec[nout]] and its 128-byte state rows are
-// staged in shared memory by TMA bulk copies (double-buffered per warp, mbarrier completion); the
-// updated state goes back with a bulk store.  Input vector and decoded sums live in registers.
-//   blocks [0, n_split*G)  "split":  a CTA of 4 warps owns one (ensemble, group); the neuron range is
-//                                    quartered and the partial decodes are reduced in shared memory;
-//   remaining blocks       "packed": each warp owns one (ensemble, group) of a small ensemble.
-// desc: n, dims, nout, state0, w_off, in_row0, out_vec, ntype, stride
-struct __align__(128) SsbSmallSmem {
-    float st[4][2][SSB_SM_CH * 32];
-    float w[4][2][SSB_SM_CH * SSB_SM_WMAX];
-    float red[4][8][32];
-    unsigned long long bar[4][2];
-};
-
-template <int DIMS, int S4, int MODE>
-__device__ __forceinline__ void ssb_small_range(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt,
-                                                const float* vg, int g, int i_begin, int i_end, float (&acc)[8],
-                                                SsbSmallSmem& sm) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int state0 = d[3], w_off = d[4], in_vec = d[5];
-    const bool stateful = nt.type == 0;
-    constexpr int NCOL = (4 * S4 - 1 - DIMS) < 8 ? (4 * S4 - 1 - DIMS) : 8;   // decoder columns present (zero padded)
-    const float* wsrc = c.W + w_off;
-    float* sg = c.st + ((size_t)g * c.nn + state0) * 32;
-    const int n_chunks = (i_end - i_begin + SSB_SM_CH - 1) / SSB_SM_CH;
-    uint32_t phases = 0;
-    auto issue = [&](int ck) {
-        if (lane == 0) {
-            const int b = ck & 1, i0 = i_begin + ck * SSB_SM_CH, cnt = min(SSB_SM_CH, i_end - i0);
-            const uint32_t bw = (uint32_t)cnt * S4 * 16, bs = stateful ? (uint32_t)cnt * 128 : 0u;
-            ssb_mbar_expect_tx(&sm.bar[warp][b], bw + bs);
-            ssb_bulk_g2s(sm.w[warp][b], wsrc + (size_t)i0 * 4 * S4, bw, &sm.bar[warp][b]);
-            if (stateful) ssb_bulk_g2s(sm.st[warp][b], sg + (size_t)i0 * 32, bs, &sm.bar[warp][b]);
-        }
-    };
-    if (n_chunks > 0) issue(0);
-    if (n_chunks > 1) issue(1);
-    float x[DIMS];                       // the materialised input vector (written by k_lin for this level)
-#pragma unroll
-    for (int k = 0; k < DIMS; ++k) x[k] = vg[(size_t)(in_vec + k) * 32];
-    for (int ck = 0; ck < n_chunks; ++ck) {
-        const int b = ck & 1, i0 = i_begin + ck * SSB_SM_CH, cnt = min(SSB_SM_CH, i_end - i0);
-        ssb_mbar_wait(&sm.bar[warp][b], (phases >> b) & 1u);
-        phases ^= 1u << b;
-        float* ss = sm.st[warp][b] + lane;
-        const float4* ww = reinterpret_cast<const float4*>(sm.w[warp][b]);
-        int k = 0;
-        if (MODE == 0) {       // fast-LIF ensembles: two neurons per iteration on the packed fp32 pipe
-#pragma unroll 2
-            for (; k + 2 <= cnt; k += 2) {
-                float wa[4 * S4], wb[4 * S4];
-#pragma unroll
-                for (int q = 0; q < S4; ++q) {
-                    const float4 t = ww[k * S4 + q], u = ww[(k + 1) * S4 + q];
-                    wa[4 * q + 0] = t.x;
-                    wa[4 * q + 1] = t.y;
-                    wa[4 * q + 2] = t.z;
-                    wa[4 * q + 3] = t.w;
-                    wb[4 * q + 0] = u.x;
-                    wb[4 * q + 1] = u.y;
-                    wb[4 * q + 2] = u.z;
-                    wb[4 * q + 3] = u.w;
-                }
-                float2 J = make_float2(wa[0], wb[0]);
-#pragma unroll
-                for (int kk = 0; kk < DIMS; ++kk) J = ssb_fma2(make_float2(wa[1 + kk], wb[1 + kk]), ssb_splat(x[kk]), J);
-                float2 sv = make_float2(ss[k * 32], ss[(k + 1) * 32]);
-                const float2 out = ssb_lif_pair(nt, J, sv);
-                ss[k * 32] = sv.x;
-                ss[(k + 1) * 32] = sv.y;
-#pragma unroll
-                for (int j = 0; j < NCOL; ++j) acc[j] = fmaf(wb[1 + DIMS + j], out.y, fmaf(wa[1 + DIMS + j], out.x, acc[j]));
-            }
-        }
-#pragma unroll 4
-        for (; k < cnt; ++k) {
-            float wl[4 * S4];
-#pragma unroll
-            for (int q = 0; q < S4; ++q) {
-                const float4 t = ww[k * S4 + q];
-                wl[4 * q + 0] = t.x;
-                wl[4 * q + 1] = t.y;
-                wl[4 * q + 2] = t.z;
-                wl[4 * q + 3] = t.w;
-            }
-            float J = wl[0];
-#pragma unroll
-            for (int kk = 0; kk < DIMS; ++kk) J = fmaf(wl[1 + kk], x[kk], J);
-            float sv = 0.f;
-            if (MODE == 0 || stateful) sv = ss[k * 32];
-            const float out = ssb_neuron_apply<MODE>(nt, J, sv);
-            if (MODE == 0 || stateful) ss[k * 32] = sv;
-#pragma unroll
-            for (int j = 0; j < NCOL; ++j) acc[j] = fmaf(wl[1 + DIMS + j], out, acc[j]);
-        }
-        if (stateful) {
-            ssb_fence_async();     // generic-proxy writes of this chunk -> visible to the bulk store
-            __syncwarp();
-            if (lane == 0) {
-                ssb_bulk_s2g(sg + (size_t)i0 * 32, sm.st[warp][b], (uint32_t)cnt * 128);
-                ssb_bulk_commit();
-            }
-        }
-        if (ck + 2 < n_chunks) {
-            if (stateful && lane == 0) ssb_bulk_wait_read0();   // the store has drained this buffer
-            __syncwarp();
-            issue(ck + 2);
-        }
-    }
-}
-
-template <int DIMS, int S4, int MODE>
-__device__ __forceinline__ void ssb_small_item(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt, int g,
-                                               bool split, SsbSmallSmem& sm) {
-    const int n = d[0], nout = d[2], out_vec = d[6];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (split) {
-        const int q = (n + 3) >> 2;
-        ssb_small_range<DIMS, S4, MODE>(c, d, nt, vg, g, min(n, warp * q), min(n, (warp + 1) * q), acc, sm);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sm.red[warp][j][lane] = acc[j];
-        __syncthreads();
-        for (int j = warp; j < nout; j += 4) {
-            const float t = (sm.red[0][j][lane] + sm.red[1][j][lane]) + (sm.red[2][j][lane] + sm.red[3][j][lane]);
-            vg[(size_t)(out_vec + j) * 32] = t;
-        }
-    } else {
-        ssb_small_range<DIMS, S4, MODE>(c, d, nt, vg, g, 0, n, acc, sm);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < nout) vg[(size_t)(out_vec + j) * 32] = acc[j];
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ void ssb_small_dispatch(const SsbCtx& c, const int* __restrict__ d, const SsbNeuron& nt, int g,
-                                                   bool split, SsbSmallSmem& sm) {
-    const int key = d[1] * 8 + (d[8] >> 2);
-    switch (key) {
-#define SSB_CASE(D, S) \
-    case (D) * 8 + (S): ssb_small_item<D, S, MODE>(c, d, nt, g, split, sm); break;
-        SSB_CASE(1, 1) SSB_CASE(1, 2) SSB_CASE(1, 3)
-        SSB_CASE(2, 1) SSB_CASE(2, 2) SSB_CASE(2, 3)
-        SSB_CASE(3, 1) SSB_CASE(3, 2) SSB_CASE(3, 3)
-        SSB_CASE(4, 2) SSB_CASE(4, 3) SSB_CASE(4, 4)
-#undef SSB_CASE
-        default: break;  // excluded by the host-side lowering (dims <= 4, dims + nout <= 11)
-    }
-}
-
-// desc: n, dims, nout, state0, w_off, in_vec, out_vec, ntype, stride
-__global__ void __launch_bounds__(128, 6) k_ens_small(SsbCtx c, const int* __restrict__ desc, int n_items, int n_split) {
-    __shared__ SsbSmallSmem sm;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-        ssb_mbar_init(&sm.bar[warp][0], 1);
-        ssb_mbar_init(&sm.bar[warp][1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int G = c.G;
-    const int split_blocks = n_split * G;
-    int item, g;
-    bool split, live = true;
-    if ((int)blockIdx.x < split_blocks) {
-        split = true;
-        item = blockIdx.x / G;
-        g = blockIdx.x - item * G;
-    } else {
-        split = false;
-        const int w = (blockIdx.x - split_blocks) * 4 + warp;
-        live = w < (n_items - n_split) * G;
-        item = live ? n_split + w / G : 0;
-        g = live ? w % G : 0;
-    }
-    if (live) {
-        const int* d = desc + item * 9;
-        const SsbNeuron nt = ssb_neuron(c, d[7]);
-        if (nt.type == 0 && nt.fast) ssb_small_dispatch<0>(c, d, nt, g, split, sm);
-        else ssb_small_dispatch<1>(c, d, nt, g, split, sm);
-    }
-    if (lane == 0) ssb_bulk_wait0();   // bulk stores complete before the CTA's shared memory is released
-}
-
-// --------------------------------------------------------------------------------------
-// Wide ensembles (OVC / memory / recall / error: 970 x 55).  A CTA owns (ensemble, trial group,
-// chunk of neurons).  Everything the chunk needs is contiguous in memory and is staged in shared
-// memory by TMA bulk copies issued by one thread while all warps evaluate the input vector:
-// static encoders [chunk][dpad], bias, direct-current weights, the chunk's 128-byte state rows.
-// The input vector is copied to registers (templated widths), each warp walks its quarter of the
-// chunk with broadcast float4 encoder reads, and the updated state goes back with a bulk store.
-// Output activities go to act[n] for the decode / PES kernels.
-// desc: n dims dpad state0 act0 enc_off bias_off in_row0 ntype flags jn_row0 jn_m jn_w voja_row scale_off alpha_bits
-struct SsbItemList {
-    int n;
-    int idx[15];
-};
-
-__device__ __forceinline__ int ssb_r4(int x) { return (x + 3) & ~3; }
-
-// Input rows of a wide ensemble -> shared memory [dpad][32].  Each warp takes every nwarps-th row, eight rows per batch
-// so that the (L2-resident) loads of a batch are in flight together instead of one dependent load per store.
-__device__ __forceinline__ void ssb_stage_rows(float* xs, const float* vg, int row0, int dims, int dpad, int warp,
-                                               int nwarps, int lane) {
-    for (int k0 = warp; k0 < dpad; k0 += nwarps * 8) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = k0 + u * nwarps;
-            v[u] = (k < dims) ? vg[(size_t)(row0 + k) * 32] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = k0 + u * nwarps;
-            if (k < dpad) xs[k * 32 + lane] = v[u];
-        }
-    }
-}
-
-
-template <int DP>
-__global__ void __launch_bounds__(128) k_wide_static(SsbCtx c, const int* __restrict__ desc, SsbItemList items, int chunk,
-                                                      int i_rel) {
-    extern __shared__ __align__(128) float sm[];
-    __shared__ unsigned long long bar;
-    const int* d = desc + items.idx[blockIdx.z] * 16;
-    const int n = d[0], dims = d[1], dpad = d[2], state0 = d[3], act0 = d[4], enc_off = d[5], bias_off = d[6];
-    const int in_row0 = d[7], jn_row0 = d[10], jn_m = d[11], jn_w = d[12];
-    const int n0 = blockIdx.x * chunk;
-    if (n0 >= n) return;
-    const int cnt = min(chunk, n - n0);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.y;
-    const SsbNeuron nt = ssb_neuron(c, d[8]);
-    const bool stateful = nt.type == 0;
-    float* s_enc = sm;                                  // [chunk][dpad]
-    float* s_bias = s_enc + (size_t)chunk * dpad;       // [chunk]
-    float* s_jn = s_bias + chunk;                       // [chunk][jn_m]
-    float* s_st = s_jn + (size_t)chunk * jn_m;          // [chunk][32]
-    float* xs = s_st + (size_t)chunk * 32;              // [dpad][32]
-    float* us = xs + (size_t)dpad * 32;                 // [jn_m][32]
-    float* stg = c.st + ((size_t)g * c.nn + state0 + n0) * 32;
-    if (threadIdx.x == 0) {
-        ssb_mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t b_enc = (uint32_t)cnt * dpad * 4, b_bias = (uint32_t)ssb_r4(cnt) * 4;
-        const uint32_t b_jn = jn_m ? (uint32_t)ssb_r4(cnt * jn_m) * 4 : 0u, b_st = stateful ? (uint32_t)cnt * 128 : 0u;
-        ssb_mbar_expect_tx(&bar, b_enc + b_bias + b_jn + b_st);
-        ssb_bulk_g2s(s_enc, c.W + enc_off + (size_t)n0 * dpad, b_enc, &bar);
-        ssb_bulk_g2s(s_bias, c.W + bias_off + n0, b_bias, &bar);
-        if (jn_m) ssb_bulk_g2s(s_jn, c.W + jn_w + (size_t)n0 * jn_m, b_jn, &bar);
-        if (stateful) ssb_bulk_g2s(s_st, stg, b_st, &bar);
-    }
-    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    ssb_stage_rows(xs, vg, in_row0, dims, dpad, warp, 4, lane);
-    for (int m = warp; m < jn_m; m += 4) us[m * 32 + lane] = vg[(size_t)(jn_row0 + m) * 32];
-    __syncthreads();                 // xs / us complete, barrier initialised for every thread
-    ssb_mbar_wait(&bar, 0);
-    float x[DP > 0 ? DP : 1];
-    if (DP > 0) {
-#pragma unroll
-        for (int k = 0; k < DP; ++k) x[k] = xs[k * 32 + lane];
-    }
-    const int per = chunk >> 2;
-    const int i_lo = warp * per, i_hi = min(cnt, i_lo + per);
-    float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)(act0 + n0) * 32;
-    for (int i = i_lo; i < i_hi; ++i) {
-        const float4* e4 = reinterpret_cast<const float4*>(s_enc + (size_t)i * dpad);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (DP > 0) {
-#pragma unroll
-            for (int k4 = 0; k4 < DP / 4; ++k4) {
-                const float4 e = e4[k4];
-                a0 = fmaf(e.x, x[4 * k4 + 0], a0);
-                a1 = fmaf(e.y, x[4 * k4 + 1], a1);
-                a2 = fmaf(e.z, x[4 * k4 + 2], a2);
-                a3 = fmaf(e.w, x[4 * k4 + 3], a3);
-            }
-        } else {
-            for (int k4 = 0; k4 < (dpad >> 2); ++k4) {
-                const float4 e = e4[k4];
-                const float* xk = xs + (k4 * 4) * 32 + lane;
-                a0 = fmaf(e.x, xk[0], a0);
-                a1 = fmaf(e.y, xk[32], a1);
-                a2 = fmaf(e.z, xk[64], a2);
-                a3 = fmaf(e.w, xk[96], a3);
-            }
-        }
-        float J = s_bias[i] + ((a0 + a1) + (a2 + a3));
-        for (int m = 0; m < jn_m; ++m) J = fmaf(s_jn[i * jn_m + m], us[m * 32 + lane], J);
-        float out;
-        if (stateful) {
-            float sv = s_st[i * 32 + lane];
-            out = nt.fast ? ssb_lif_packed<true>(nt, J, sv) : ssb_lif_packed<false>(nt, J, sv);
-            s_st[i * 32 + lane] = sv;
-        } else {
-            out = ssb_rate(nt, J);
-        }
-        ag[(size_t)i * 32] = out;
-        const bool any_on = __any_sync(0xffffffffu, out != 0.f);
-        if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + n0 + i] = any_on;
-    }
-    if (stateful && i_hi > i_lo) {
-        ssb_fence_async();
-        __syncwarp();
-        if (lane == 0) {
-            ssb_bulk_s2g(stg + (size_t)i_lo * 32, s_st + (size_t)i_lo * 32, (uint32_t)(i_hi - i_lo) * 128);
-            ssb_bulk_commit();
-            ssb_bulk_wait0();
-        }
-    }
-}
-
-// Tensor-core variant of k_wide_static (tcgen05 + TMEM): the input currents of a static wide ensemble are the
-// GEMM J[trial][neuron] = X[trial][k] . E[neuron][k] with encoders shared by every trial.  CTA = (ensemble, block
-// of 128 trials, chunk of 64-neuron tiles).  A = X (128 x KP, K-major, 3xTF32 hi | lo) is built once from the
-// materialised input rows; B = encoder tiles (64 x KP, hi | lo, pre-tiled by the host) arrive by TMA in a
-// two-stage ring; D (128 lanes x 64 columns) is double-buffered in TMEM so the MMAs of tile i+1 overlap the
-// neuron epilogue of tile i: tcgen05.ld (lane = trial), + bias (+ direct neuron currents), LIF update on the
-// packed state rows (coalesced 128-byte loads / stores per neuron), activities to the act arena.
-// Et: [n_tiles][hi|lo][k/4][8 row groups][8][4] floats.  dynamic smem: (2*128 + 4*64) * KP floats.
-#define SSB_ETC_N 64
-template <bool FAST>
-__global__ void __launch_bounds__(512, 1)
-k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, const float* __restrict__ Et_all,
-                 const int* __restrict__ et_off, int KP, int tiles_per_chunk) {
-    extern __shared__ __align__(1024) float sm[];
-    __shared__ unsigned long long full[2], done[2];
-    __shared__ uint32_t tmem_slot;
-    __shared__ float s_bias[2][SSB_ETC_N], s_jnw[2][4 * SSB_ETC_N];   // per-tile bias / direct-current weights, double-buffered
-    const int item = items.idx[blockIdx.z];
-    const int* d = desc + item * 16;
-    const int n = d[0], dims = d[1], state0 = d[3], act0 = d[4], bias_off = d[6], in_row0 = d[7];
-    const int jn_row0 = d[10], jn_m = d[11], jn_w = d[12];
-    const float* __restrict__ Et = Et_all + et_off[item];
-    const int n_tiles = (n + SSB_ETC_N - 1) / SSB_ETC_N;
-    const int t_lo = blockIdx.x * tiles_per_chunk;
-    if (t_lo >= n_tiles) return;
-    const int my_tiles = min(n_tiles, t_lo + tiles_per_chunk) - t_lo;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int quad = warp & 3, part = warp >> 2;        // 16 warps: TMEM quadrant, 16-column slice of the tile
-    const int group = blockIdx.y * 4 + quad;
-    const bool live = group < c.G;
-    const int g = live ? group : 0;
-    const SsbNeuron nt = ssb_neuron(c, d[8]);
-    const bool stateful = nt.type == 0;
-    const int a_part = 128 * KP, b_part = SSB_ETC_N * KP;
-    const uint32_t tile_bytes = 2u * b_part * 4u;
-    float* sA = sm;                                         // [hi|lo][a_part]
-    float* sB = sm + 2 * a_part;                            // [2 stages][hi|lo][b_part]
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(128));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (threadIdx.x == 0) {
-        ssb_mbar_init(&full[0], 1);
-        ssb_mbar_init(&full[1], 1);
-        ssb_mbar_init(&done[0], 1);
-        ssb_mbar_init(&done[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < 2 && i < my_tiles; ++i) {
-            ssb_mbar_expect_tx(&full[i], tile_bytes);
-            ssb_bulk_g2s(sB + (size_t)i * 2 * b_part, Et + (size_t)(t_lo + i) * 2 * b_part, tile_bytes, &full[i]);
-        }
-    }
-    float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    {   // A operand: this thread's trial is row r; the four warps of a quadrant alternate 32-column blocks
-        const int r = quad * 32 + lane;
-        float* a_hi = sA + (r >> 3) * 32 + (r & 7) * 4;
-        float* a_lo = a_hi + a_part;
-        const float* src = vg + (size_t)in_row0 * 32;
-        for (int k0 = part * 32; k0 < KP; k0 += 128) {
-            float x[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) x[e] = (live && k0 + e < dims) ? src[(size_t)(k0 + e) * 32] : 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k = k0 + 4 * q;
-                if (k < KP) {
-                    float4 hi, lo;
-                    hi.x = ssb_tf32_round(x[4 * q + 0]);
-                    hi.y = ssb_tf32_round(x[4 * q + 1]);
-                    hi.z = ssb_tf32_round(x[4 * q + 2]);
-                    hi.w = ssb_tf32_round(x[4 * q + 3]);
-                    lo.x = ssb_tf32_round(x[4 * q + 0] - hi.x);
-                    lo.y = ssb_tf32_round(x[4 * q + 1] - hi.y);
-                    lo.z = ssb_tf32_round(x[4 * q + 2] - hi.z);
-                    lo.w = ssb_tf32_round(x[4 * q + 3] - hi.w);
-                    *reinterpret_cast<float4*>(a_hi + (size_t)(k >> 2) * 16 * 32) = hi;
-                    *reinterpret_cast<float4*>(a_lo + (size_t)(k >> 2) * 16 * 32) = lo;
-                }
-            }
-        }
-    }
-    const int jm = min(jn_m, 4);
-    auto stage_consts = [&](int i) {                        // tile i's bias / jn weights -> smem stage i & 1
-        const int s = i & 1, base = (t_lo + i) * SSB_ETC_N;
-        if (threadIdx.x < SSB_ETC_N) {
-            const int nn = base + threadIdx.x;
-            s_bias[s][threadIdx.x] = nn < n ? __ldg(c.W + bias_off + nn) : 0.f;
-        }
-        if (threadIdx.x < jm * SSB_ETC_N) {
-            const int e = base * jn_m + threadIdx.x;         // jm == jn_m whenever this path is taken (host guarantees jn_m <= 4)
-            s_jnw[s][threadIdx.x] = e < n * jn_m ? __ldg(c.W + jn_w + e) : 0.f;
-        }
-    };
-    stage_consts(0);
-    ssb_fence_async();
-    ssb_tc_fence_before();
-    __syncthreads();
-    ssb_tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SSB_ETC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    auto issue_mma = [&](int i) {
-        const int s = i & 1;
-        ssb_mbar_wait(&full[s], (uint32_t)(i >> 1) & 1u);
-        ssb_tc_fence_after();
-        const float* b_hi = sB + (size_t)s * 2 * b_part;
-        const uint32_t dst = tmem + (uint32_t)s * SSB_ETC_N;
-#pragma unroll 1
-        for (int j = 0; j < KP / 8; ++j) {
-            const size_t oa = (size_t)j * 2 * 16 * 32, ob = (size_t)j * 2 * 8 * 32;
-            const uint64_t ah = ssb_umma_desc_lbo(sA + oa, 2048), al = ssb_umma_desc_lbo(sA + a_part + oa, 2048);
-            const uint64_t bh = ssb_umma_desc_lbo(b_hi + ob, 1024), bl = ssb_umma_desc_lbo(b_hi + b_part + ob, 1024);
-            ssb_umma_tf32(dst, al, bh, idesc, j > 0);
-            ssb_umma_tf32(dst, ah, bl, idesc, 1);
-            ssb_umma_tf32(dst, ah, bh, idesc, 1);
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ssb_smem(&done[s]))
-                     : "memory");
-    };
-    float u_jn[4];                                          // direct neuron currents (inhibition): a few inputs per trial
-#pragma unroll
-    for (int m = 0; m < 4; ++m) u_jn[m] = (m < jn_m) ? vg[(size_t)(jn_row0 + m) * 32] : 0.f;
-    float* sg = ssb_grp(c.st, c.nn, g, lane) + (size_t)state0 * 32;
-    float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
-    if (threadIdx.x == 0) issue_mma(0);
-    __syncwarp();
-    for (int i = 0; i < my_tiles; ++i) {
-        const int s = i & 1;
-        if (threadIdx.x == 0 && i + 1 < my_tiles) issue_mma(i + 1);
-        __syncwarp();
-        if (i + 1 < my_tiles) stage_consts(i + 1);
-        const int nn0 = (t_lo + i) * SSB_ETC_N + part * 16;     // first neuron of this thread's 16 columns
-        const int nvalid = live ? min(16, max(0, n - nn0)) : 0;
-        float* sgt = sg + (size_t)nn0 * 32;
-        float* agt = ag + (size_t)nn0 * 32;
-        float sv[16];
-        if (stateful) {                                         // state rows in flight while the MMAs finish
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sv[j] = j < nvalid ? __ldcs(sgt + j * 32) : 0.f;
-        }
-        ssb_mbar_wait(&done[s], (uint32_t)(i >> 1) & 1u);
-        ssb_tc_fence_after();
-        if (threadIdx.x == 0 && i + 2 < my_tiles) {
-            ssb_mbar_expect_tx(&full[s], tile_bytes);
-            ssb_bulk_g2s(sB + (size_t)s * 2 * b_part, Et + (size_t)(t_lo + i + 2) * 2 * b_part, tile_bytes, &full[s]);
-        }
-        __syncwarp();
-        float v[16];
-        ssb_tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * SSB_ETC_N + (uint32_t)part * 16, v);
-        int* fl = c.aflag + (size_t)g * c.n_act + act0 + nn0;
-        auto neuron = [&](int j) {
-            float J = v[j] + s_bias[s][part * 16 + j];
-            for (int m = 0; m < jm; ++m) J = fmaf(s_jnw[s][(part * 16 + j) * jm + m], u_jn[m], J);
-            float out;
-            if (stateful) {
-                float st = sv[j];
-                out = ssb_lif_packed<FAST>(nt, J, st);
-                __stcs(sgt + j * 32, st);
-            } else {
-                out = ssb_rate(nt, J);
-            }
-            agt[j * 32] = out;
-            const bool any_on = __any_sync(0xffffffffu, out != 0.f);
-            if (lane == 0) fl[j] = any_on;
-        };
-        if (nvalid == 16) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) neuron(j);
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < nvalid; ++j) {
-                float vj = 0.f, svj = 0.f;                      // ragged last tile: select without dynamic register indexing
-#pragma unroll
-                for (int q = 0; q < 16; ++q)
-                    if (q == j) { vj = v[q]; svj = sv[q]; }
-                float J = vj + s_bias[s][part * 16 + j];
-                for (int m = 0; m < jm; ++m) J = fmaf(s_jnw[s][(part * 16 + j) * jm + m], u_jn[m], J);
-                float out;
-                if (stateful) {
-                    out = ssb_lif_packed<FAST>(nt, J, svj);
-                    __stcs(sgt + j * 32, svj);
-                } else {
-                    out = ssb_rate(nt, J);
-                }
-                agt[j * 32] = out;
-                const bool any_on = __any_sync(0xffffffffu, out != 0.f);
-                if (lane == 0) fl[j] = any_on;
-            }
-        }
-        ssb_tc_fence_before();
-        __syncthreads();
-        ssb_tc_fence_after();
-    }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
-}
-
-// Voja-learned ensemble (associative-memory keys): the scaled encoders are per trial, the `dims` rows
-// of one neuron are `dims` consecutive 128-byte lines.  Each warp streams its neurons' encoder tiles
-// through a ring of shared-memory tiles (three in flight) with TMA bulk copies; lanes that spiked update their
-// column in place and the tile is written back only if some lane spiked (post_synapse=None => the
-// delta is row-sparse).  SimVoja: delta = alpha*L*(scale*outer(post, x) - post[:,None]*E), visible
-// to the next step.
-#define SSB_VOJA_NB 3         // encoder tiles in flight per warp (fewer when a tile is too large: very wide ensembles)
-template <int DP>
-__global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restrict__ desc, SsbItemList items, int chunk,
-                                                    int i_rel, int nb) {
-    extern __shared__ __align__(128) float sm[];
-    __shared__ unsigned long long wbar[4][SSB_VOJA_NB];
-    const int* d = desc + items.idx[blockIdx.z] * 16;
-    const int n = d[0], dims = d[1], dpad = d[2], state0 = d[3], act0 = d[4], enc_off = d[5], bias_off = d[6];
-    const int in_row0 = d[7], jn_row0 = d[10], jn_m = d[11], jn_w = d[12], voja_row = d[13], scale_off = d[14];
-    const int n0 = blockIdx.x * chunk;
-    if (n0 >= n) return;
-    const int cnt = min(chunk, n - n0);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int g = blockIdx.y;
-    const SsbNeuron nt = ssb_neuron(c, d[8]);
-    const bool stateful = nt.type == 0;
-    float* xs = sm;                                        // [dpad][32]
-    float* us = xs + (size_t)dpad * 32;                    // [jn_m][32]
-    float* ebuf = us + (size_t)jn_m * 32 + (size_t)warp * nb * dims * 32;   // [nb][dims][32] per warp
-    const int per = (chunk + nwarps - 1) / nwarps;
-    const int i_lo = warp * per, i_hi = min(cnt, i_lo + per);
-    float* eg = c.lenc + ((size_t)g * c.n_lenc + enc_off + (size_t)(n0 + i_lo) * dims) * 32;   // tile of neuron i_lo
-    const uint32_t tile_bytes = (uint32_t)dims * 128;
-    if (lane == 0) {
-        for (int t = 0; t < SSB_VOJA_NB; ++t) ssb_mbar_init(&wbar[warp][t], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int t = 0; t < nb && i_lo + t < i_hi; ++t) {
-            ssb_mbar_expect_tx(&wbar[warp][t], tile_bytes);
-            ssb_bulk_g2s(ebuf + (size_t)t * dims * 32, eg + (size_t)t * dims * 32, tile_bytes, &wbar[warp][t]);
-        }
-    }
-    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    float x[DP > 0 ? DP : 1];
-    if (DP > 0) {       // the input rows go straight to registers: DP independent L2 loads per lane, no shared-memory hop
-#pragma unroll
-        for (int k = 0; k < DP; ++k) x[k] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
-    } else {
-        ssb_stage_rows(xs, vg, in_row0, dims, dpad, warp, nwarps, lane);
-    }
-    for (int m = warp; m < jn_m; m += nwarps) us[m * 32 + lane] = vg[(size_t)(jn_row0 + m) * 32];
-    const float aL = __int_as_float(d[15]) * vg[(size_t)voja_row * 32];
-    __syncthreads();
-    float* sp = ssb_grp(c.st, c.nn, g, lane) + (size_t)(state0 + n0) * 32;
-    float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)(act0 + n0) * 32;
-    uint32_t phases = 0;
-    // the state row (HBM) and the bias of neuron i + 1 are requested while neuron i is computed: eight warps per SM do
-    // not hide one memory round trip per neuron
-    float sv_next = 0.f, bias_next = 0.f;
-    if (i_lo < i_hi) {
-        if (stateful) sv_next = __ldcs(sp + (size_t)i_lo * 32);
-        bias_next = __ldg(c.W + bias_off + n0 + i_lo);
-    }
-    for (int i = i_lo; i < i_hi; ++i) {
-        const int t = i - i_lo, b = t % nb;
-        float* E = ebuf + (size_t)b * dims * 32 + lane;
-        float sv = sv_next;
-        float J = bias_next;
-        if (i + 1 < i_hi) {
-            if (stateful) sv_next = __ldcs(sp + (size_t)(i + 1) * 32);
-            bias_next = __ldg(c.W + bias_off + n0 + i + 1);
-        }
-        for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + (n0 + i) * jn_m + m), us[m * 32 + lane], J);
-        ssb_mbar_wait(&wbar[warp][b], (phases >> b) & 1u);   // phases: one parity bit per buffer
-        phases ^= 1u << b;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (DP > 0) {
-#pragma unroll
-            for (int k = 0; k < DP; k += 4) {
-                a0 = fmaf(k + 0 < dims ? E[(k + 0) * 32] : 0.f, x[k + 0], a0);
-                a1 = fmaf(k + 1 < dims ? E[(k + 1) * 32] : 0.f, x[k + 1], a1);
-                a2 = fmaf(k + 2 < dims ? E[(k + 2) * 32] : 0.f, x[k + 2], a2);
-                a3 = fmaf(k + 3 < dims ? E[(k + 3) * 32] : 0.f, x[k + 3], a3);
-            }
-        } else {
-            int k = 0;
-            for (; k + 4 <= dims; k += 4) {
-                a0 = fmaf(E[k * 32], xs[k * 32 + lane], a0);
-                a1 = fmaf(E[(k + 1) * 32], xs[(k + 1) * 32 + lane], a1);
-                a2 = fmaf(E[(k + 2) * 32], xs[(k + 2) * 32 + lane], a2);
-                a3 = fmaf(E[(k + 3) * 32], xs[(k + 3) * 32 + lane], a3);
-            }
-            for (; k < dims; ++k) a0 = fmaf(E[k * 32], xs[k * 32 + lane], a0);
-        }
-        J += (a0 + a1) + (a2 + a3);
-        float out;
-        if (stateful) {
-            out = nt.fast ? ssb_lif_packed<true>(nt, J, sv) : ssb_lif_packed<false>(nt, J, sv);
-            __stcs(sp + (size_t)i * 32, sv);
-        } else {
-            out = ssb_rate(nt, J);
-        }
-        ag[(size_t)i * 32] = out;
-        const bool fired = out != 0.f;
-        {
-            const bool any_on = __any_sync(0xffffffffu, fired);
-            if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + n0 + i] = any_on;
-        }
-        if (fired) {
-            const float sc = __ldg(c.W + scale_off + n0 + i);
-            if (DP > 0) {
-#pragma unroll
-                for (int k = 0; k < DP; ++k) {
-                    if (k < dims) {
-                        const float e = E[k * 32];
-                        E[k * 32] = e + aL * (sc * (out * x[k]) - out * e);
-                    }
-                }
-            } else {
-                for (int k = 0; k < dims; ++k) {
-                    const float e = E[k * 32];
-                    E[k * 32] = e + aL * (sc * (out * xs[k * 32 + lane]) - out * e);
-                }
-            }
-        }
-        const bool dirty = __any_sync(0xffffffffu, fired);
-        if (dirty) ssb_fence_async();
-        __syncwarp();
-        if (lane == 0) {
-            // one bulk group per tile (empty when the tile is clean) keeps the group count in step with the tiles:
-            // before buffer b_prev = (t - 1) % NB is refilled, only the group of tile t may still be reading
-            if (dirty) ssb_bulk_s2g(eg + (size_t)t * dims * 32, ebuf + (size_t)b * dims * 32, tile_bytes);
-            ssb_bulk_commit();
-            if (nb == 1) {                                   // single buffer: refill after this tile's own store has read it
-                if (i + 1 < i_hi) {
-                    ssb_bulk_wait_read0();
-                    ssb_mbar_expect_tx(&wbar[warp][0], tile_bytes);
-                    ssb_bulk_g2s(ebuf, eg + (size_t)(t + 1) * dims * 32, tile_bytes, &wbar[warp][0]);
-                }
-            } else if (t >= 1 && i + nb - 1 < i_hi) {
-                const int bp = (t - 1) % nb;
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                ssb_mbar_expect_tx(&wbar[warp][bp], tile_bytes);
-                ssb_bulk_g2s(ebuf + (size_t)bp * dims * 32, eg + (size_t)(t - 1 + nb) * dims * 32, tile_bytes, &wbar[warp][bp]);
-            }
-        }
-    }
-    if (lane == 0) ssb_bulk_wait0();
-}
-
-// --------------------------------------------------------------------------------------
-// Split-K epilogue shared by the decode and PES kernels.  The neuron range of one (decoder,
-// 8-row tile, trial group) is split over n_chunks CTAs; each CTA reduces its 4 warps in shared
-// memory and, if it is not alone, parks its partial sums in the `part` arena.  The CTA that
-// arrives last (atomic counter, self-resetting) adds the partials in chunk order — a fixed order,
-// so the result does not depend on scheduling — and writes the single output slot.
-__device__ __forceinline__ void ssb_splitk_finish(const SsbCtx& c, float (*red)[8][32], int* flag, const float (&acc)[8],
-                                                  int g, int j0, int size_out, int out_vec, int n_chunks, int chunk,
-                                                  int part_off, int counter) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
-    __syncthreads();
-    float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    float* pg = ssb_grp(c.part, c.n_part, g, lane);
-    for (int j = warp; j < 8; j += 4) {
-        if (j0 + j < size_out) {
-            const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
-            if (n_chunks == 1) vg[(size_t)(out_vec + j0 + j) * 32] = t;
-            else pg[(size_t)(part_off + chunk * size_out + j0 + j) * 32] = t;
-        }
-    }
-    if (n_chunks == 1) return;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int old = atomicAdd(c.counters + counter, 1);
-        const int last = old == n_chunks - 1;
-        if (last) c.counters[counter] = 0;
-        *flag = last;
-    }
-    __syncthreads();
-    if (!*flag) return;
-    __threadfence();
-    for (int j = warp; j < 8; j += 4) {
-        if (j0 + j < size_out) {
-            float t = 0.f;
-            for (int ck0 = 0; ck0 < n_chunks; ck0 += 8) {     // 8 independent loads in flight, added in chunk order
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    v[q] = ck0 + q < n_chunks ? __ldcg(pg + (size_t)(part_off + (ck0 + q) * size_out + j0 + j) * 32) : 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) t += v[q];
-            }
-            vg[(size_t)(out_vec + j0 + j) * 32] = t;
-        }
-    }
-}
-
-// Static decoders of wide ensembles: out[j] = sum_n Wd[n][j] * act[n].  CTA = (decoder, quad of trial
-// groups, neuron chunk); each WARP owns one trial group and the whole 56-wide output tile for the chunk, so
-// there is no cross-warp reduction: the four warps share the chunk's weight rows [cnt][jpad] (one TMA bulk
-// copy, broadcast float4 reads) and each fetches its own group's activity rows [cnt][32] (one bulk copy per
-// warp, own mbarrier).  A neuron whose activity is zero in all 32 trials of the group is skipped (spiking
-// activity is sparse).  Chunks are combined by the split-K semaphore in chunk order (fixed summation order).
-// desc: n size_out jpad act0 w_off out_vec n_chunks part_off counter0
-// dynamic smem: per*jpad (weights) + 4*per*32 (activities) floats, per = ceil(n / n_chunks)
-#define SSB_DEC_NJ 56
-__global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict__ desc, int item0) {
-    extern __shared__ __align__(128) float sm[];
-    __shared__ unsigned long long bar_w, bar_a[4];
-    const int* d = desc + (item0 + blockIdx.z) * 9;
-    const int n = d[0], size_out = d[1], jpad = d[2], act0 = d[3], w_off = d[4], out_vec = d[5], n_chunks = d[6];
-    const int part_off = d[7];
-    const int chunk = blockIdx.x;
-    if (chunk >= n_chunks) return;
-    const int per = (n + n_chunks - 1) / n_chunks;
-    const int i_lo = chunk * per, cnt = min(n, i_lo + per) - i_lo;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.y * 4 + warp;
-    const bool live = g < c.G;
-    float* s_w = sm;                                                   // [per][jpad]
-    float* s_a = s_w + (size_t)per * jpad + (size_t)warp * per * 32;   // [per][32] of this warp's group
-    if (threadIdx.x == 0) {
-        ssb_mbar_init(&bar_w, 1);
-        for (int q = 0; q < 4; ++q) ssb_mbar_init(&bar_a[q], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        ssb_mbar_expect_tx(&bar_w, (uint32_t)cnt * jpad * 4);
-        ssb_bulk_g2s(s_w, c.W + w_off + (size_t)i_lo * jpad, (uint32_t)cnt * jpad * 4, &bar_w);
-    }
-    __syncthreads();
-    if (!live) return;
-    if (lane == 0) {
-        ssb_mbar_expect_tx(&bar_a[warp], (uint32_t)cnt * 128);
-        ssb_bulk_g2s(s_a, c.act + ((size_t)g * c.n_act + act0 + i_lo) * 32, (uint32_t)cnt * 128, &bar_a[warp]);
-    }
-    float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    float* pg = ssb_grp(c.part, c.n_part, g, lane);
-    ssb_mbar_wait(&bar_a[warp], 0);
-    ssb_mbar_wait(&bar_w, 0);
-    for (int jb = 0; jb < jpad; jb += SSB_DEC_NJ) {
-        const int nq = min(SSB_DEC_NJ, jpad - jb) >> 2;      // float4 columns of this pass (jpad is a multiple of 8)
-        float acc[SSB_DEC_NJ];
-#pragma unroll
-        for (int j = 0; j < SSB_DEC_NJ; ++j) acc[j] = 0.f;
-        for (int i = 0; i < cnt; ++i) {
-            const float a = s_a[i * 32 + lane];
-            if (__any_sync(0xffffffffu, a != 0.f)) {
-                const float4* w4 = reinterpret_cast<const float4*>(s_w + (size_t)i * jpad + jb);
-#pragma unroll
-                for (int k = 0; k < SSB_DEC_NJ / 4; ++k) {
-                    if (k < nq) {
-                        const float4 w = w4[k];
-                        acc[4 * k + 0] = fmaf(w.x, a, acc[4 * k + 0]);
-                        acc[4 * k + 1] = fmaf(w.y, a, acc[4 * k + 1]);
-                        acc[4 * k + 2] = fmaf(w.z, a, acc[4 * k + 2]);
-                        acc[4 * k + 3] = fmaf(w.w, a, acc[4 * k + 3]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < SSB_DEC_NJ; ++j) {
-            if (j < 4 * nq && jb + j < size_out) {
-                if (n_chunks == 1) vg[(size_t)(out_vec + jb + j) * 32] = acc[j];
-                else pg[(size_t)(part_off + chunk * size_out + jb + j) * 32] = acc[j];
-            }
-        }
-    }
-    if (n_chunks == 1) return;
-    // split-K: one arrival counter per (decoder, trial group); the warp that arrives last adds the partials
-    __threadfence();
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) {
-        int* cnt_p = c.counters + d[8] * c.G + g;
-        const int old = atomicAdd(cnt_p, 1);
-        last = old == n_chunks - 1;
-        if (last) *cnt_p = 0;
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    __threadfence();
-    // 8 outputs x 8 chunks = 64 independent loads in flight; the additions stay in chunk order
-    for (int j = 0; j < size_out; j += 8) {
-        float t[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = 0.f;
-        for (int ck0 = 0; ck0 < n_chunks; ck0 += 8) {
-            float v[8][8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const bool ok = ck0 + q < n_chunks && j + u < size_out;
-                    v[q][u] = ok ? __ldcg(pg + (size_t)(part_off + (ck0 + q) * size_out + j + u) * 32) : 0.f;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] += v[q][u];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (j + u < size_out) vg[(size_t)(out_vec + j + u) * 32] = t[u];
-    }
-}
-
-// Tensor-core static decoders (tcgen05 + TMEM): out[trial][j] = sum_k act[k][trial] * Wd[k][j] is a dense GEMM
-// whose weights are shared by every trial.  CTA = (decoder, block of 128 trials = 4 trial groups, K chunk);
-//   A = activities (128 trials x 64 neurons per stage, K-major), gathered by the CTA's 256 threads from the
-//       group-tiled act arena (coalesced 128-byte rows) and split on the fly into TF32 hi + lo,
-//   B = Wd^T (64 output rows x 64 neurons per stage, K-major) pre-split into hi / lo and pre-tiled by the host in
-//       UMMA core-matrix order, one TMA bulk copy per stage,
-//   D = 128 lanes x 64 fp32 columns in TMEM, accumulated over the chunk's stages with the 3xTF32 scheme
-//       (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi).  Building stage s+1 overlaps the MMAs of stage s (two buffers).
-// The epilogue reads D with tcgen05.ld (lane = trial) and writes the output rows (or split-K partial sums,
-// combined in chunk order by the last CTA to arrive, as in the FFMA kernel).
-// Wt: [n_stages][hi|lo][k/4][8 row groups][8][4] floats (64 rows x 64 columns per part).
-// Instantiated for <N = 64 outputs, KS = 64 neurons per stage> and <N = 128, KS = 32> (wider decoders, e.g. d = 97).
-template <int SSB_DTC_N, int SSB_DTC_KS>
-__global__ void __launch_bounds__(256, 1)
-k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __restrict__ Wt_all, const int* __restrict__ wt_off) {
-    extern __shared__ __align__(1024) float sm[];
-    __shared__ unsigned long long full[2], done[2];
-    __shared__ uint32_t tmem_slot;
-    __shared__ int s_last[4];
-    const int* d = desc + (item0 + blockIdx.z) * 9;
-    const int n = d[0], size_out = d[1], act0 = d[3], out_vec = d[5], n_chunks = d[6], part_off = d[7];
-    const float* __restrict__ Wt = Wt_all + wt_off[item0 + blockIdx.z];
-    const int chunk = blockIdx.x;
-    if (chunk >= n_chunks) return;
-    const int n_stages = (n + SSB_DTC_KS - 1) / SSB_DTC_KS;
-    const int spc = (n_stages + n_chunks - 1) / n_chunks;
-    const int s_lo = chunk * spc, s_hi = min(n_stages, s_lo + spc);
-    const int my = max(0, s_hi - s_lo);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int quad = warp & 3, half = warp >> 2;
-    const int group = blockIdx.y * 4 + quad;
-    const bool live = group < c.G;
-    const int g = live ? group : 0;
-    constexpr int A_PART = 128 * SSB_DTC_KS;            // floats of one A part (hi or lo)
-    constexpr int B_PART = SSB_DTC_N * SSB_DTC_KS;
-    float* sA = sm;                                     // [2 buffers][hi|lo][A_PART]
-    float* sB = sm + 4 * A_PART;                        // [2 buffers][hi|lo][B_PART]
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(SSB_DTC_N));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (threadIdx.x == 0) {
-        ssb_mbar_init(&full[0], 1);
-        ssb_mbar_init(&full[1], 1);
-        ssb_mbar_init(&done[0], 1);
-        ssb_mbar_init(&done[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < 2 && i < my; ++i) {
-            ssb_mbar_expect_tx(&full[i], 2u * B_PART * 4u);
-            ssb_bulk_g2s(sB + (size_t)i * 2 * B_PART, Wt + (size_t)(s_lo + i) * 2 * B_PART, 2u * B_PART * 4u, &full[i]);
-        }
-    }
-    ssb_tc_fence_before();
-    __syncthreads();
-    ssb_tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    // D fp32, A/B tf32, both K-major, N = 64, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SSB_DTC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int r = quad * 32 + lane;                     // this thread's trial row; `half` picks its half of the stage's columns
-    constexpr int HK = SSB_DTC_KS / 2;                  // activity rows per thread and stage
-    const float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
-    for (int i = 0; i < my; ++i) {
-        const int b = i & 1;
-        if (i >= 2) {                                   // buffer b was read by the MMAs of stage i - 2
-            ssb_mbar_wait(&done[b], (uint32_t)((i - 2) >> 1) & 1u);
-            ssb_tc_fence_after();
-            if (threadIdx.x == 0) {
-                ssb_mbar_expect_tx(&full[b], 2u * B_PART * 4u);
-                ssb_bulk_g2s(sB + (size_t)b * 2 * B_PART, Wt + (size_t)(s_lo + i) * 2 * B_PART, 2u * B_PART * 4u, &full[b]);
-            }
-        }
-        {   // A stage: HK activity rows per thread, all loads issued before they are consumed
-            const int k0 = (s_lo + i) * SSB_DTC_KS + half * HK;
-            float x[HK];
-#pragma unroll
-            for (int e = 0; e < HK; ++e) x[e] = (live && k0 + e < n) ? ag[(size_t)(k0 + e) * 32] : 0.f;
-            float* a_hi = sA + (size_t)b * 2 * A_PART + (r >> 3) * 32 + (r & 7) * 4 + (size_t)(half * (HK / 4)) * 16 * 32;
-            float* a_lo = a_hi + A_PART;
-#pragma unroll
-            for (int q = 0; q < HK / 4; ++q) {
-                float4 hi, lo;
-                hi.x = ssb_tf32_round(x[4 * q + 0]);
-                hi.y = ssb_tf32_round(x[4 * q + 1]);
-                hi.z = ssb_tf32_round(x[4 * q + 2]);
-                hi.w = ssb_tf32_round(x[4 * q + 3]);
-                lo.x = ssb_tf32_round(x[4 * q + 0] - hi.x);
-                lo.y = ssb_tf32_round(x[4 * q + 1] - hi.y);
-                lo.z = ssb_tf32_round(x[4 * q + 2] - hi.z);
-                lo.w = ssb_tf32_round(x[4 * q + 3] - hi.w);
-                *reinterpret_cast<float4*>(a_hi + (size_t)q * 16 * 32) = hi;
-                *reinterpret_cast<float4*>(a_lo + (size_t)q * 16 * 32) = lo;
-            }
-        }
-        ssb_fence_async();
-        ssb_tc_fence_before();
-        __syncthreads();
-        ssb_tc_fence_after();
-        if (threadIdx.x == 0) {
-            ssb_mbar_wait(&full[b], (uint32_t)(i >> 1) & 1u);
-            ssb_tc_fence_after();
-            const float* ah = sA + (size_t)b * 2 * A_PART;
-            const float* bh = sB + (size_t)b * 2 * B_PART;
-#pragma unroll 1
-            for (int j = 0; j < SSB_DTC_KS / 8; ++j) {
-                const size_t oa = (size_t)j * 2 * 16 * 32, ob = (size_t)j * 2 * (SSB_DTC_N / 8) * 32;   // two 16-byte K chunks per MMA
-                const uint64_t dah = ssb_umma_desc_lbo(ah + oa, 2048), dal = ssb_umma_desc_lbo(ah + A_PART + oa, 2048);
-                const uint64_t dbh = ssb_umma_desc_lbo(bh + ob, (SSB_DTC_N / 8) * 128);
-                const uint64_t dbl = ssb_umma_desc_lbo(bh + B_PART + ob, (SSB_DTC_N / 8) * 128);
-                ssb_umma_tf32(tmem, dal, dbh, idesc, (i > 0 || j > 0) ? 1u : 0u);
-                ssb_umma_tf32(tmem, dah, dbl, idesc, 1);
-                ssb_umma_tf32(tmem, dah, dbh, idesc, 1);
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ssb_smem(&done[b]))
-                         : "memory");
-        }
-        __syncwarp();
-    }
-    float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    float* pg = ssb_grp(c.part, c.n_part, g, lane);
-    if (my > 0) {
-        // the commit of the last stage covers every earlier MMA
-        ssb_mbar_wait(&done[(my - 1) & 1], (uint32_t)((my - 1) >> 1) & 1u);
-        ssb_tc_fence_after();
-#pragma unroll 1
-        for (int cb = 0; cb < SSB_DTC_N / 64; ++cb) {       // this warp's half of the columns, 32 at a time
-            const int c0 = half * (SSB_DTC_N / 2) + cb * 32;
-            float v[32];
-            ssb_tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int jo = c0 + j;
-                    if (jo < size_out) {
-                        if (n_chunks == 1) vg[(size_t)(out_vec + jo) * 32] = v[j];
-                        else pg[(size_t)(part_off + chunk * size_out + jo) * 32] = v[j];
-                    }
-                }
-            }
-        }
-    } else if (live && n_chunks > 1) {                  // an empty trailing chunk still owns its partial slot
-        for (int j = half * (SSB_DTC_N / 2); j < min(size_out, (half + 1) * (SSB_DTC_N / 2)); ++j)
-            pg[(size_t)(part_off + chunk * size_out + j) * 32] = 0.f;
-    }
-    ssb_tc_fence_before();
-    __threadfence();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(SSB_DTC_N));
-    if (n_chunks == 1) return;
-    // split-K: one arrival counter per (decoder, trial group); the CTA that arrives last adds the partials in chunk order
-    if (half == 0) {
-        if (lane == 0) {
-            int last = 0;
-            if (live) {
-                int* cnt_p = c.counters + d[8] * c.G + group;
-                const int old = atomicAdd(cnt_p, 1);
-                last = old == n_chunks - 1;
-                if (last) *cnt_p = 0;
-            }
-            s_last[quad] = last;
-        }
-    }
-    __syncthreads();
-    if (!s_last[quad]) return;
-    __threadfence();
-    for (int j = half * (SSB_DTC_N / 2); j < min(size_out, (half + 1) * (SSB_DTC_N / 2)); j += 8) {   // the two warps of a group split the outputs
-        float t[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = 0.f;
-        for (int ck0 = 0; ck0 < n_chunks; ck0 += 4) {
-            float w[4][8];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const bool ok = ck0 + q < n_chunks && j + u < size_out;
-                    w[q][u] = ok ? __ldcg(pg + (size_t)(part_off + (ck0 + q) * size_out + j + u) * 32) : 0.f;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] += w[q][u];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (j + u < size_out) vg[(size_t)(out_vec + j + u) * 32] = t[u];
-    }
-}
-
-// --------------------------------------------------------------------------------------
-// PES-learned decoders (per trial): one streaming pass that applies the pending rank-1 delta,
-// decodes with the updated weights and writes them back:
-//   D <- D + outer(alpha*err_prev, a_prev)     (nengo: Copy(delta->weights, inc) at step start)
-//   out = D . act                               (DotInc)
-// err_prev / a_prev are the values the previous step read (the error rows are materialised from the
-// not-yet-overwritten filter half, the trace comes from the other half of its ping-pong buffer), which
-// is exactly SimPES' delta of the previous step.  For a fixed output row the weights of consecutive
-// neurons are consecutive 128-byte lines.  A neuron whose trace and activity are zero in all 32 trials
-// changes nothing and contributes nothing: its weights are neither read nor written (exact).
-// desc: n size_out d_off a_off act0 err_vec out_vec alpha_bits decay_bits onemdecay_bits n_chunks part_off counter0
-template <bool FULL>
-__device__ __forceinline__ void ssb_pes_body(const float* __restrict__ ap, const float* __restrict__ fp, float* __restrict__ dp,
-                                             int n, int jn, int i_lo, int i_hi, const float (&ae)[8], float (&acc)[8]) {
-    const int warp = threadIdx.x >> 5;
-    float* rowp[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rowp[j] = dp + (size_t)((FULL || j < jn) ? j : 0) * n * 32;
-    constexpr int U = 4;
-    // activities / traces of the NEXT batch are requested before this batch's weights, so the two dependent
-    // memory rounds of a batch (a, f -> vote -> weights) overlap across iterations
-    float an[U], fn[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int ii = i_lo + warp + 4 * u;
-        an[u] = 0.f;
-        fn[u] = 0.f;
-        if (ii < i_hi) {
-            an[u] = ap[(size_t)ii * 32];
-            fn[u] = fp[(size_t)ii * 32];
-        }
-    }
-    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
-        float a[U], f[U], w[U][8];
-        bool on[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            a[u] = an[u];
-            f[u] = fn[u];
-            const int ii = i + 4 * U + 4 * u;
-            an[u] = 0.f;
-            fn[u] = 0.f;
-            if (ii < i_hi) {
-                an[u] = ap[(size_t)ii * 32];
-                fn[u] = fp[(size_t)ii * 32];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            on[u] = __any_sync(0xffffffffu, a[u] != 0.f || f[u] != 0.f);
-            if (on[u]) {
-                const size_t off = (size_t)(i + 4 * u) * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (FULL || j < jn) w[u][j] = __ldcs(rowp[j] + off);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (on[u]) {
-                const size_t off = (size_t)(i + 4 * u) * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (FULL || j < jn) {
-                        const float wn = fmaf(ae[j], f[u], w[u][j]);
-                        acc[j] = fmaf(wn, a[u], acc[j]);
-                        __stcs(rowp[j] + off, wn);
-                    }
-                }
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ desc, int max_chunks, int i_rel) {
-    __shared__ float red[4][8][32];
-    __shared__ int flag;
-    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
-    const int* d = desc + item * 13;
-    const int n = d[0], size_out = d[1], d_off = d[2], a_off = d[3], act0 = d[4], err_vec = d[5], out_vec = d[6];
-    const int n_chunks = d[10];
-    const float alpha = __int_as_float(d[7]);
-    const int j0 = blockIdx.x * 8;
-    if (j0 >= size_out || chunk >= n_chunks) return;
-    const int per = (n + n_chunks - 1) / n_chunks;
-    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.y;
-    const SsbStep s = ssb_step(c, i_rel);
-    const int prev_buf = 1 - s.odd;  // afilt half that still holds what the previous step read
-    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    const int jn = min(8, size_out - j0);
-    float ae[8], acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        acc[j] = 0.f;
-        float e = 0.f;
-        if (j < jn) e = vg[(size_t)(err_vec + j0 + j) * 32];   // error of the previous step, materialised by k_lin
-        ae[j] = s.step > 0 ? alpha * e : 0.f;
-    }
-    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
-    const float* __restrict__ fp = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)prev_buf * c.n_afilt + a_off) * 32;
-    float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
-    if (jn == 8) ssb_pes_body<true>(ap, fp, dp, n, jn, i_lo, i_hi, ae, acc);
-    else ssb_pes_body<false>(ap, fp, dp, n, jn, i_lo, i_hi, ae, acc);
-    ssb_splitk_finish(c, red, &flag, acc, g, j0, size_out, out_vec, n_chunks, chunk, d[11],
-                      (d[12] + (int)blockIdx.x) * c.G + g);
-}
-
-// --------------------------------------------------------------------------------------
-// Deferred PES (default).  SimPES changes the decoders by one rank-1 term per step, D(t) = D(t-1) + ae(t) (x) f(t),
-// and the only per-step consumer is out(t) = D(t) . a(t) with a sparse spike vector a.  Instead of rewriting D every
-// step, the last K terms are kept as a history (ae_s: size_out rows, f_s: n rows per slot, slot = step mod K) and
-//     out(t) = D_base . a(t) + sum_s ae_s * (f_s . a(t)),
-// which reads D_base only where some trial of the group spiked and writes nothing; every K-th step (and before any
-// read-back of the decoders) the K terms are folded into D_base in one streaming pass.  Same arithmetic up to fp32
-// summation order; HBM traffic drops from 8 B to ~(active fraction * 4 + 8 / K) B per learned weight and step.
-//   k_pes_hist   appends this step's term (ae from the materialised error rows, f = the trace the previous step read);
-//                it runs AFTER the decode of its own step, which reads that term at its source
-//   k_pes_defer  the sparse decode; CTA = (8-row tile, trial group, neuron chunk); tile-0 CTAs also accumulate the K
-//                history dot products; the last CTA of a (decoder, group) adds partials in a fixed order and applies
-//                the history correction
-//   k_pes_fold   D_base += sum_s ae_s (x) f_s (runs when slot == K - 1, or when the host asks), then k_pes_clear zeroes
-//                the ae rows, so an empty history always contributes exactly 0
-// desc as k_pes; hdesc per decoder: e_row0 f_row0 part_row0 counter0 (rows of the hist_e / hist_f / pes_part arenas)
-#define SSB_PES_KMAX 16
-struct SsbPesDefer {
-    float* hist_e;            // [G][rows_e][32]
-    float* hist_f;            // [G][rows_f][32]
-    float* part;              // [G][rows_p][32]
-    int* counters;
-    int rows_e, rows_f, rows_p, K;
-};
-
-__global__ void __launch_bounds__(128) k_pes_hist(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
-                                                    const int* __restrict__ hdesc, int i_rel) {
-    const int item = blockIdx.z;
-    const int* d = desc + item * 13;
-    const int* hd = hdesc + item * 4;
-    const int n = d[0], size_out = d[1], a_off = d[3], err_vec = d[5];
-    const float alpha = __int_as_float(d[7]);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.y;
-    const SsbStep s = ssb_step(c, i_rel);
-    const int slot = (int)(s.step % h.K);
-    const int r = blockIdx.x * 4 + warp;
-    float* he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
-    if (r < size_out) {
-        const float e = ssb_grp(c.vec, c.nv, g, lane)[(size_t)(err_vec + r) * 32];
-        he[(size_t)(slot * size_out + r) * 32] = s.step > 0 ? alpha * e : 0.f;
-    } else if (r < size_out + n) {
-        const int i = r - size_out;
-        const int prev_buf = 1 - s.odd;      // afilt half that still holds what the previous step read
-        float* fg = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane);
-        const float f = fg[((size_t)prev_buf * c.n_afilt + a_off + i) * 32];
-        ssb_grp(h.hist_f, h.rows_f, g, lane)[(size_t)(hd[1] + slot * n + i) * 32] = f;
-        // this kernel is the last reader of that half in the step, so it also performs the trace update the row
-        // program would do (kind 2): new trace = decay * trace + (1 - decay) * activity, written over the old half
-        const float y = fg[((size_t)s.odd * c.n_afilt + a_off + i) * 32];
-        const float u = ssb_grp(c.act, c.n_act, g, lane)[(size_t)(d[4] + i) * 32];
-        fg[((size_t)prev_buf * c.n_afilt + a_off + i) * 32] = fmaf(__int_as_float(d[9]), u, __int_as_float(d[8]) * y);
-    }
-}
-
-template <int K>
-__global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
-                                                     const int* __restrict__ hdesc, int max_chunks, int i_rel) {
-    __shared__ float red[4][8][32];
-    __shared__ int flag;
-    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
-    const int* d = desc + item * 13;
-    const int* hd = hdesc + item * 4;
-    const int n = d[0], size_out = d[1], d_off = d[2], a_off = d[3], act0 = d[4], err_vec = d[5], out_vec = d[6];
-    const int n_chunks = d[10];
-    const int n_jt = (size_out + 7) >> 3;
-    // blockIdx.x < n_jt: an 8-row tile of D_base; blockIdx.x == n_jt: the K history rows (f_s . a), same loop
-    const bool dots = (int)blockIdx.x == n_jt;
-    const int j0 = blockIdx.x * 8;
-    if ((int)blockIdx.x > n_jt || chunk >= n_chunks) return;
-    const int per = (n + n_chunks - 1) / n_chunks;
-    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.y;
-    const int jn = dots ? K : min(8, size_out - j0);
-    const SsbStep s = ssb_step(c, i_rel);
-    const int slot = (int)(s.step % K);       // this step's term is not in the history yet: it is read at its source
-    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
-    const int* __restrict__ fl = c.aflag + (size_t)g * c.n_act + act0;
-    const float* rowp[8];
-    {
-        const float* dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
-        const float* hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
-        const float* fcur = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)(1 - s.odd) * c.n_afilt + a_off) * 32;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (dots) rowp[j] = (j == slot) ? fcur : hf + (size_t)(j < K ? j : 0) * n * 32;
-            else rowp[j] = dp + (size_t)(j < jn ? j : 0) * n * 32;
-        }
-    }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // each warp owns a contiguous quarter of the chunk and walks only the neurons flagged active by their producer:
-    // 32 flags per coalesced load -> ballot -> up to U active neurons per batch with all their loads in flight
-    const int qn = (i_hi - i_lo + 3) >> 2;
-    const int w_lo = i_lo + warp * qn, w_hi = min(i_hi, w_lo + qn);
-    constexpr int U = 4;
-    for (int base = w_lo; base < w_hi; base += 32) {
-        unsigned m = __ballot_sync(0xffffffffu, base + lane < w_hi && __ldg(fl + base + lane) != 0);
-        while (m) {
-            int idx[U];
-            float a[U], w[U][8];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                idx[u] = -1;
-                if (m) {
-                    idx[u] = base + __ffs(m) - 1;
-                    m &= m - 1;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                a[u] = 0.f;
-                if (idx[u] >= 0) {
-                    const size_t off = (size_t)idx[u] * 32;
-                    a[u] = ap[off];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) w[u][j] = (j < jn) ? __ldcs(rowp[j] + off) : 0.f;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (idx[u] >= 0) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[u][j], a[u], acc[j]);
-                }
-            }
-        }
-    }
-    // CTA partial: ((w0 + w1) + (w2 + w3)) per row, parked in the partial arena [chunk][size_out + K]
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
-    __syncthreads();
-    const int prow = size_out + K;
-    float* pg = ssb_grp(h.part, h.rows_p, g, lane) + (size_t)hd[2] * 32;
-    for (int j = warp; j < jn; j += 4) {
-        const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
-        pg[(size_t)(chunk * prow + (dots ? size_out : j0) + j) * 32] = t;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int* cnt_p = h.counters + hd[3] * c.G + g;
-        const int old = atomicAdd(cnt_p, 1);
-        const int last = old == (n_jt + 1) * n_chunks - 1;
-        if (last) *cnt_p = 0;
-        flag = last;
-    }
-    __syncthreads();
-    if (!flag) return;
-    __threadfence();
-    // the last CTA of this (decoder, group): history dot products, then every output row
-    float dsum[K];
-#pragma unroll
-    for (int q = 0; q < K; ++q) dsum[q] = 0.f;
-    for (int ck = 0; ck < n_chunks; ++ck) {              // K independent loads per chunk, added in chunk order
-        float v[K];
-#pragma unroll
-        for (int q = 0; q < K; ++q) v[q] = __ldcg(pg + (size_t)(ck * prow + size_out + q) * 32);
-#pragma unroll
-        for (int q = 0; q < K; ++q) dsum[q] += v[q];
-    }
-    const float* __restrict__ he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
-    float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    const float alpha = s.step > 0 ? __int_as_float(d[7]) : 0.f;
-    for (int jb = warp * 8; jb < size_out; jb += 32) {   // each warp takes 8 consecutive output rows at a time
-        float t[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = 0.f;
-        for (int ck = 0; ck < n_chunks; ++ck) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = (jb + u < size_out) ? __ldcg(pg + (size_t)(ck * prow + jb + u) * 32) : 0.f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] += v[u];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (jb + u < size_out) {
-                float e[K];
-#pragma unroll
-                for (int q = 0; q < K; ++q)
-                    e[q] = (q == slot) ? alpha * vg[(size_t)(err_vec + jb + u) * 32] : he[(size_t)(q * size_out + jb + u) * 32];
-                float r = t[u];
-#pragma unroll
-                for (int q = 0; q < K; ++q) r = fmaf(e[q], dsum[q], r);
-                vg[(size_t)(out_vec + jb + u) * 32] = r;
-            }
-        }
-    }
-}
-
-// launched by the host after the step whose slot is K - 1, and before any read-back of the decoders
-template <int K>
-__global__ void __launch_bounds__(128) k_pes_fold(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
-                                                    const int* __restrict__ hdesc, int max_chunks, int i_rel, int force) {
-    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
-    const int* d = desc + item * 13;
-    const int* hd = hdesc + item * 4;
-    const int n = d[0], size_out = d[1], d_off = d[2], n_chunks = d[10];
-    const int j0 = blockIdx.x * 8;
-    if (j0 >= size_out || chunk >= n_chunks) return;
-    const int per = (n + n_chunks - 1) / n_chunks;
-    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.y;
-    const int jn = min(8, size_out - j0);
-    float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
-    const float* __restrict__ hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
-    const float* __restrict__ he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
-    float ae[K][8];
-#pragma unroll
-    for (int q = 0; q < K; ++q)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ae[q][j] = (j < jn) ? he[(size_t)(q * size_out + j0 + j) * 32] : 0.f;
-    constexpr int U = 2;                     // two neurons per iteration: 2 * (K + 8) loads in flight per warp
-    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
-        float fv[U][K], w[U][8];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int ii = i + 4 * u;
-            const size_t off = (size_t)(ii < i_hi ? ii : i) * 32;
-#pragma unroll
-            for (int q = 0; q < K; ++q) fv[u][q] = hf[(size_t)q * n * 32 + off];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[u][j] = (j < jn) ? __ldcs(dp + (size_t)j * n * 32 + off) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int ii = i + 4 * u;
-            if (ii < i_hi) {
-                const size_t off = (size_t)ii * 32;
-#pragma unroll
-                for (int q = 0; q < K; ++q)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) w[u][j] = fmaf(ae[q][j], fv[u][q], w[u][j]);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j < jn) __stcs(dp + (size_t)j * n * 32 + off, w[u][j]);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128) k_pes_clear(SsbCtx c, SsbPesDefer h, int i_rel, int force) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = blockIdx.x * 4 + warp;
-    if (r < h.rows_e) ssb_grp(h.hist_e, h.rows_e, blockIdx.y, lane)[(size_t)r * 32] = 0.f;
-}
-
-// --------------------------------------------------------------------------------------
-// Grid clean-up / decode: argmax_g S[g].x with first-maximum-wins.  Scan in fp32 keeping the
-// top-4 candidates per (grid chunk, trial); the pick kernel re-scores near-ties in fp64 so
-// that the chosen index equals the float64 NumPy argmax on the same input.
-// A CTA = 4 warps = 4 different trial groups scanning the SAME grid chunk: the chunk of S is
-// staged in shared memory tiles and read back as warp-uniform (broadcast) float4s, the query
-// vector sits in registers; two grid rows are scored per iteration.
-struct SsbTop {
-    float v[SSB_TOPK];
-    int g[SSB_TOPK];
-};
-
-__device__ __forceinline__ void ssb_top_init(SsbTop& t) {
-#pragma unroll
-    for (int i = 0; i < SSB_TOPK; ++i) {
-        t.v[i] = -INFINITY;
-        t.g[i] = 0x7fffffff;
-    }
-}
-
-// keep sorted by (value desc, index asc); candidates arrive in ascending g
-__device__ __forceinline__ void ssb_top_push(SsbTop& t, float val, int g) {
-    if (val > t.v[SSB_TOPK - 1]) {
-#pragma unroll
-        for (int i = SSB_TOPK - 1; i >= 0; --i) {
-            const bool shift = (i > 0) && (val > t.v[i - 1]);
-            if (shift) {
-                t.v[i] = t.v[i - 1];
-                t.g[i] = t.g[i - 1];
-            } else {
-                t.v[i] = val;
-                t.g[i] = g;
-                break;
-            }
-        }
-    }
-}
-
-// desc: G d dpad s_off in_row0 out_vec ; scratch: cx[G][dpad][32], pval/pidx[G][n_cand][32]
-// A CTA owns grid rows [blockIdx.x*rows_per_chunk, +rows_per_chunk) and walks them in shared-memory
-// tiles of tile_rows rows.  dynamic smem: tile_rows*dpad (S tile)
-template <int DP, bool CSR_INPUT>
-__global__ void __launch_bounds__(128)
-k_cleanup_scan(SsbCtx c, const int* __restrict__ d, const float* __restrict__ S, float* __restrict__ cx,
-               float* __restrict__ pval, int* __restrict__ pidx, int rows_per_chunk, int tile_rows, int n_groups,
-               int n_cand, int i_rel) {
-    extern __shared__ float sm[];
-    const int G = d[0], dims = d[1], dpad = d[2], in_row0 = d[4];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int group = blockIdx.y * 4 + warp;
-    const bool live = group < n_groups;
-    const int g = live ? group : 0;
-    const int g_lo = blockIdx.x * rows_per_chunk;
-    const int g_hi = min(G, g_lo + rows_per_chunk);
-    float* tile = sm;                              // [tile_rows][dpad]
-    float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
-    float x[DP > 0 ? DP : 1];
-    if (CSR_INPUT) {   // query = materialised vec rows of this step
-        const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-        if (DP > 0) {
-#pragma unroll
-            for (int k = 0; k < DP; ++k) {
-                x[k] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
-                if (blockIdx.x == 0 && live) cxg[(size_t)k * 32] = x[k];
-            }
-        } else if (blockIdx.x == 0 && live) {      // generic width: the query is re-read per tile; keep the copy for the pick
-            for (int k = 0; k < dpad; ++k) cxg[(size_t)k * 32] = (k < dims) ? vg[(size_t)(in_row0 + k) * 32] : 0.f;
-        }
-    } else {
-        if (DP > 0) {
-#pragma unroll
-            for (int k = 0; k < DP; ++k) x[k] = (k < dims) ? cxg[(size_t)k * 32] : 0.f;
-        }
-    }
-    // generic width: source of the query columns (materialised vec rows, or the prepared stand-alone query)
-    const float* xsrc = CSR_INPUT ? ssb_grp(c.vec, c.nv, g, lane) + (size_t)in_row0 * 32 : cxg;
-    SsbTop top;
-    ssb_top_init(top);
-    for (int g0 = g_lo; g0 < g_hi; g0 += tile_rows) {
-        const int g1 = min(g_hi, g0 + tile_rows);
-        __syncthreads();   // previous tile fully consumed (and xs visible on the first pass)
-        {   // stage the grid tile (coalesced float4)
-            const float4* __restrict__ src = reinterpret_cast<const float4*>(S + (size_t)g0 * dpad);
-            float4* dst = reinterpret_cast<float4*>(tile);
-            const int n4 = (g1 - g0) * (dpad >> 2);
-            for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
-        }
-        __syncthreads();
-        if (!live) continue;
-        if (DP > 0) {
-            int gg = g0;
-            for (; gg + 2 <= g1; gg += 2) {
-                const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(gg - g0) * DP);
-                const float4* t4 = s4 + DP / 4;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-#pragma unroll
-                for (int k4 = 0; k4 < DP / 4; ++k4) {
-                    const float4 e = s4[k4], f = t4[k4];
-                    a0 = fmaf(e.x, x[4 * k4 + 0], a0);
-                    a1 = fmaf(e.y, x[4 * k4 + 1], a1);
-                    a2 = fmaf(e.z, x[4 * k4 + 2], a2);
-                    a3 = fmaf(e.w, x[4 * k4 + 3], a3);
-                    b0 = fmaf(f.x, x[4 * k4 + 0], b0);
-                    b1 = fmaf(f.y, x[4 * k4 + 1], b1);
-                    b2 = fmaf(f.z, x[4 * k4 + 2], b2);
-                    b3 = fmaf(f.w, x[4 * k4 + 3], b3);
-                }
-                ssb_top_push(top, (a0 + a1) + (a2 + a3), gg);
-                ssb_top_push(top, (b0 + b1) + (b2 + b3), gg + 1);
-            }
-            for (; gg < g1; ++gg) {
-                const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(gg - g0) * DP);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                for (int k4 = 0; k4 < DP / 4; ++k4) {
-                    const float4 e = s4[k4];
-                    a0 = fmaf(e.x, x[4 * k4 + 0], a0);
-                    a1 = fmaf(e.y, x[4 * k4 + 1], a1);
-                    a2 = fmaf(e.z, x[4 * k4 + 2], a2);
-                    a3 = fmaf(e.w, x[4 * k4 + 3], a3);
-                }
-                ssb_top_push(top, (a0 + a1) + (a2 + a3), gg);
-            }
-        } else {
-            // generic width (any d, e.g. 649): the query is streamed in 32-column register chunks while the partial
-            // scores of up to 16 tile rows stay in registers: 8 broadcast float4 grid reads per 32 FFMAs
-            for (int gg0 = g0; gg0 < g1; gg0 += 16) {
-                const int nr = min(16, g1 - gg0);
-                float acc[16];
-#pragma unroll
-                for (int r = 0; r < 16; ++r) acc[r] = 0.f;
-                for (int k0 = 0; k0 < dpad; k0 += 32) {
-                    float xk[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) xk[e] = (k0 + e < dims) ? xsrc[(size_t)(k0 + e) * 32] : 0.f;
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        if (r < nr) {
-                            const float4* s4 = reinterpret_cast<const float4*>(tile + (size_t)(gg0 - g0 + r) * dpad + k0);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                if (k0 + 4 * q < dpad) {
-                                    const float4 e = s4[q];
-                                    acc[r] = fmaf(e.x, xk[4 * q + 0], acc[r]);
-                                    acc[r] = fmaf(e.y, xk[4 * q + 1], acc[r]);
-                                    acc[r] = fmaf(e.z, xk[4 * q + 2], acc[r]);
-                                    acc[r] = fmaf(e.w, xk[4 * q + 3], acc[r]);
-                                }
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 16; ++r)
-                    if (r < nr) ssb_top_push(top, acc[r], gg0 + r);
-            }
-        }
-    }
-    if (!live) return;
-    float* pv = pval + ((size_t)g * n_cand) * 32 + lane;
-    int* pi = pidx + ((size_t)g * n_cand) * 32 + lane;
-#pragma unroll
-    for (int i = 0; i < SSB_TOPK; ++i) {
-        pv[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = top.v[i];
-        pi[(size_t)(blockIdx.x * SSB_TOPK + i) * 32] = top.g[i];
-    }
-}
-
-// --------------------------------------------------------------------------------------
-// Tensor-core grid scan (tcgen05 + TMEM).  The similarity scores of a trial block against the sample
-// grid are a real GEMM with weights shared by every trial: D[trial][grid row] = X[trial][k] . S[grid row][k].
-// One CTA owns 128 trials (4 trial groups = the 128 TMEM lanes) and every n_chunks-th tile of 128 grid rows.
-//   A = X  (128 x KP, K-major)  built once per CTA in shared memory from the materialised vec rows,
-//   B = S  (128 x KP, K-major)  pre-tiled on the host in the UMMA core-matrix order, fetched by one TMA bulk
-//                               copy per tile into a two-stage ring,
-//   D      (128 lanes x 128 columns fp32) double-buffered in TMEM: the MMAs of tile i+1 run while the four
-//                               warps drain tile i with tcgen05.ld and keep a per-trial top-4.
-// fp32 accuracy comes from the 3xTF32 split: x = x_hi + x_lo with both parts exactly representable in
-// TF32, D = X_lo.S_hi + X_hi.S_lo + X_hi.S_hi (the dropped lo.lo term is < 2^-22 relative).  Near-ties are
-// still re-scored in fp64 by k_cleanup_pick, so the chosen index equals the float64 argmax.
-//
-// Shared-memory operand layout (UMMA "interleave" / no-swizzle, K-major): 8 rows x 16 bytes core matrices,
-//   float offset(row r, column k) = ((k / 4) * 16 + r / 8) * 32 + (r % 8) * 4 + k % 4
-// => stride between 8-row groups SBO = 128 B, stride between 16-byte K chunks LBO = 2048 B.
-
-// Stc: [n_tiles][2 (hi, lo)][KP/4][TR/8][8][4] floats, TR = 128 grid rows per tile (64 when 128 does not fit in
-// shared memory, e.g. d = 97).  dynamic smem: (2 * 128 + 4 * TR) * KP floats.
-// 256 threads: warps w and w + 4 own the same TMEM lane quadrant (the 32 trials of group 4*blockIdx.y + w % 4)
-// and drain the two halves of every tile's columns, each into its own top-4 list (candidate slot
-// (2 * chunk + half) * 4 + i), so two warps per scheduler hide the insert latency.
-// desc: G d dpad s_off in_row0 out_vec
-template <bool CSR_INPUT, int TR>
-__global__ void __launch_bounds__(256, 1)
-k_cleanup_scan_tc(SsbCtx c, const int* __restrict__ d, const float* __restrict__ Stc, float* __restrict__ cx,
-                  float* __restrict__ pval, int* __restrict__ pidx, int KP, int n_tiles, int n_groups, int n_cand) {
-    extern __shared__ __align__(1024) float sm[];
-    __shared__ unsigned long long full[2], done[2];
-    __shared__ uint32_t tmem_slot;
-    const int G = d[0], dims = d[1], dpad = d[2], in_row0 = d[4];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int quad = warp & 3, half = warp >> 2;
-    const int group = blockIdx.y * 4 + quad;
-    const bool live = group < n_groups;
-    const int g = live ? group : 0;
-    const int chunk = blockIdx.x, n_chunks = gridDim.x;
-    const int my_tiles = chunk < n_tiles ? (n_tiles - chunk + n_chunks - 1) / n_chunks : 0;
-    const int part_floats = 128 * KP;                       // one part (hi or lo) of the A operand (128 trials)
-    const int b_part = TR * KP;                             // one part of a grid tile (TR rows)
-    const uint32_t tile_bytes = 2u * b_part * 4u;           // hi + lo
-    float* sA = sm;                                         // [2][part]
-    float* sB = sm + 2 * part_floats;                       // [2 stages][2][part]
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(2 * TR));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (threadIdx.x == 0) {
-        ssb_mbar_init(&full[0], 1);
-        ssb_mbar_init(&full[1], 1);
-        ssb_mbar_init(&done[0], 1);
-        ssb_mbar_init(&done[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < 2 && i < my_tiles; ++i) {
-            ssb_mbar_expect_tx(&full[i], tile_bytes);
-            ssb_bulk_g2s(sB + (size_t)i * 2 * b_part, Stc + (size_t)(chunk + i * n_chunks) * 2 * b_part, tile_bytes, &full[i]);
-        }
-    }
-    {   // A operand: this thread's trial is row r of the tile; four K columns per 16-byte store.
-        // Loads are issued 32 at a time (8 chunks of 4 columns) before anything consumes them.
-        const int r = quad * 32 + lane;
-        const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-        float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
-        float* a_hi = sA + (r >> 3) * 32 + (r & 7) * 4;
-        float* a_lo = a_hi + part_floats;
-        const float* src = CSR_INPUT ? vg + (size_t)in_row0 * 32 : cxg;
-        const bool copy_q = CSR_INPUT && live && blockIdx.x == 0;
-        for (int k0 = half * 32; k0 < KP; k0 += 64) {   // the two warps of a quadrant alternate 32-column blocks
-            float x[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int k = k0 + e;
-                x[e] = (live && k < dims) ? src[(size_t)k * 32] : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k = k0 + 4 * q;
-                if (k < KP) {
-                    float4 hi, lo;
-                    hi.x = ssb_tf32_round(x[4 * q + 0]);
-                    hi.y = ssb_tf32_round(x[4 * q + 1]);
-                    hi.z = ssb_tf32_round(x[4 * q + 2]);
-                    hi.w = ssb_tf32_round(x[4 * q + 3]);
-                    lo.x = ssb_tf32_round(x[4 * q + 0] - hi.x);
-                    lo.y = ssb_tf32_round(x[4 * q + 1] - hi.y);
-                    lo.z = ssb_tf32_round(x[4 * q + 2] - hi.z);
-                    lo.w = ssb_tf32_round(x[4 * q + 3] - hi.w);
-                    *reinterpret_cast<float4*>(a_hi + (size_t)(k >> 2) * 16 * 32) = hi;
-                    *reinterpret_cast<float4*>(a_lo + (size_t)(k >> 2) * 16 * 32) = lo;
-                }
-            }
-            if (copy_q) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    if (k0 + e < dpad) cxg[(size_t)(k0 + e) * 32] = x[e];
-            }
-        }
-    }
-    ssb_fence_async();            // generic-proxy stores of A -> visible to the tensor core (async proxy)
-    ssb_tc_fence_before();
-    __syncthreads();
-    ssb_tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    auto issue_mma = [&](int i) {   // one thread: wait for the tile, queue its 3 * KP/8 MMAs, commit
-        const int s = i & 1;
-        ssb_mbar_wait(&full[s], (uint32_t)(i >> 1) & 1u);
-        ssb_tc_fence_after();
-        const float* b_hi = sB + (size_t)s * 2 * b_part;
-        const float* b_lo = b_hi + b_part;
-        const uint32_t dst = tmem + (uint32_t)s * TR;
-        for (int j = 0; j < KP / 8; ++j) {
-            const size_t off = (size_t)j * 2 * 16 * 32;     // two 16-byte K chunks per MMA
-            const size_t ob = (size_t)j * 2 * (TR / 8) * 32;
-            const uint64_t ah = ssb_umma_desc(sA + off), al = ssb_umma_desc(sA + part_floats + off);
-            const uint64_t bh = ssb_umma_desc_lbo(b_hi + ob, (TR / 8) * 128), bl = ssb_umma_desc_lbo(b_lo + ob, (TR / 8) * 128);
-            ssb_umma_tf32(dst, al, bh, idesc, j > 0);
-            ssb_umma_tf32(dst, ah, bl, idesc, 1);
-            ssb_umma_tf32(dst, ah, bh, idesc, 1);
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ssb_smem(&done[s]))
-                     : "memory");
-    };
-    // per-trial top-4 in registers, sorted by (value desc, index asc); scores arrive in ascending index order
-    float tv0 = -INFINITY, tv1 = -INFINITY, tv2 = -INFINITY, tv3 = -INFINITY;
-    int tg0 = 0x7fffffff, tg1 = 0x7fffffff, tg2 = 0x7fffffff, tg3 = 0x7fffffff;
-    auto push = [&](float val, int gi) {   // branch-free sorted insert (a strict > keeps the earlier index on ties)
-        const bool b0 = val > tv0, b1 = val > tv1, b2 = val > tv2, b3 = val > tv3;
-        tv3 = b2 ? tv2 : (b3 ? val : tv3);
-        tg3 = b2 ? tg2 : (b3 ? gi : tg3);
-        tv2 = b1 ? tv1 : (b2 ? val : tv2);
-        tg2 = b1 ? tg1 : (b2 ? gi : tg2);
-        tv1 = b0 ? tv0 : (b1 ? val : tv1);
-        tg1 = b0 ? tg0 : (b1 ? gi : tg1);
-        tv0 = b0 ? val : tv0;
-        tg0 = b0 ? gi : tg0;
-    };
-    if (threadIdx.x == 0 && my_tiles > 0) issue_mma(0);
-    __syncwarp();
-    for (int i = 0; i < my_tiles; ++i) {
-        const int s = i & 1;
-        if (threadIdx.x == 0 && i + 1 < my_tiles) issue_mma(i + 1);
-        __syncwarp();
-        ssb_mbar_wait(&done[s], (uint32_t)(i >> 1) & 1u);
-        ssb_tc_fence_after();
-        if (threadIdx.x == 0 && i + 2 < my_tiles) {           // the MMAs of tile i have consumed stage s
-            ssb_mbar_expect_tx(&full[s], tile_bytes);
-            ssb_bulk_g2s(sB + (size_t)s * 2 * b_part, Stc + (size_t)(chunk + (i + 2) * n_chunks) * 2 * b_part, tile_bytes,
-                         &full[s]);
-        }
-        __syncwarp();
-        const int row0 = (chunk + i * n_chunks) * TR;
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)s * TR;
-#pragma unroll 1
-        for (int b = half * (TR / 64); b < (half + 1) * (TR / 64); ++b) {
-            float v[32];
-            ssb_tmem_ld32(taddr + b * 32, v);
-            const int gg0 = row0 + b * 32;
-            if (gg0 + 32 <= G) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) push(v[j], gg0 + j);
-            } else {                                   // last tile: rows beyond the grid are padding
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (gg0 + j < G) push(v[j], gg0 + j);
-            }
-        }
-        ssb_tc_fence_before();
-        __syncthreads();           // every warp has drained TMEM buffer s before tile i+2 is accumulated into it
-        ssb_tc_fence_after();
-    }
-    if (live) {
-        float* pv = pval + ((size_t)g * n_cand) * 32 + lane;
-        int* pi = pidx + ((size_t)g * n_cand) * 32 + lane;
-        const float tv[4] = {tv0, tv1, tv2, tv3};
-        const int tg[4] = {tg0, tg1, tg2, tg3};
-#pragma unroll
-        for (int i = 0; i < SSB_TOPK; ++i) {
-            pv[(size_t)((blockIdx.x * 2 + half) * SSB_TOPK + i) * 32] = tv[i];
-            pi[(size_t)((blockIdx.x * 2 + half) * SSB_TOPK + i) * 32] = tg[i];
-        }
-    }
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * TR));
-}
-
-// CTA = one trial group x 8 warps: warps split the candidate list, merge through shared memory, then
-// candidates within eps of the fp32 maximum are re-scored in fp64 (S64 is the float64 grid) and
-// the winning index / grid row are written.  out_base (may be null) is a group-tiled arena.
-__global__ void __launch_bounds__(256)
-k_cleanup_pick(int dims, int dpad, int ncand, const float* __restrict__ cx, const float* __restrict__ pval,
-               const int* __restrict__ pidx, const double* __restrict__ S64, const float* __restrict__ S32,
-               float* __restrict__ out_base, int out_rows_per_group, int out_row0, int* __restrict__ out_idx,
-               const double* __restrict__ q64, long long q0, long long n_q, float eps_floor_rel) {
-    __shared__ float sv[8][32];
-    __shared__ int sg[8][32];
-    __shared__ float sn[8][32];
-    __shared__ int sc[8][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.x;
-    const int trial = g * 32 + lane;
-    const float* pv = pval + ((size_t)g * ncand) * 32 + lane;
-    const int* pi = pidx + ((size_t)g * ncand) * 32 + lane;
-    const float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
-    float best = -INFINITY;
-    int best_g = 0x7fffffff;
-    for (int i0 = warp; i0 < ncand; i0 += 64) {   // 8 independent candidate loads in flight per thread
-        float v[8];
-        int gi[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + 8 * u;
-            v[u] = (i < ncand) ? pv[(size_t)i * 32] : -INFINITY;
-            gi[u] = (i < ncand) ? pi[(size_t)i * 32] : 0x7fffffff;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (v[u] > best || (v[u] == best && gi[u] < best_g)) {
-                best = v[u];
-                best_g = gi[u];
-            }
-        }
-    }
-    float xn = 0.f;
-    for (int k = warp; k < dims; k += 8) {
-        const float xv = cxg[(size_t)k * 32];
-        xn = fmaf(xv, xv, xn);
-    }
-    sv[warp][lane] = best;
-    sg[warp][lane] = best_g;
-    sn[warp][lane] = xn;
-    __syncthreads();
-    best = sv[0][lane];
-    best_g = sg[0][lane];
-    xn = sn[0][lane];
-    for (int w = 1; w < 8; ++w) {
-        const float v = sv[w][lane];
-        const int gi = sg[w][lane];
-        if (v > best || (v == best && gi < best_g)) {
-            best = v;
-            best_g = gi;
-        }
-        xn += sn[w][lane];
-    }
-    // fp32 dot-product error bound: ~dims * 2^-24 * |S_g||x| with |S_g| = 1
-    // (the 3xTF32 tensor-core scan passes its own relative floor: dropped lo.lo terms + fp32 accumulation)
-    const float eps = fmaxf(4.0f * (float)dims * 5.97e-8f, eps_floor_rel) * sqrtf(xn) + 1e-30f;
-    int n_close = 0;
-    for (int i0 = warp; i0 < ncand; i0 += 64) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (i0 + 8 * u < ncand) ? pv[(size_t)(i0 + 8 * u) * 32] : -INFINITY;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) n_close += v[u] >= best - eps;
-    }
-    sc[warp][lane] = n_close;
-    __syncthreads();
-    n_close = 0;
-    for (int w = 0; w < 8; ++w) n_close += sc[w][lane];
-    // Near-ties (rare): lanes with more than one candidate inside the fp32 error band re-score those
-    // candidates in fp64.  Every warp re-walks only its own slice of the candidate list, so a tie costs one
-    // more pass instead of a serial scan; the per-warp winners are merged in (value desc, index asc) order.
-    __shared__ double sd[8][32];
-    const bool multi = n_close > 1 && S64 != nullptr;
-    double dbest = -1e300;
-    int dg = 0x7fffffff;
-    if (__any_sync(0xffffffffu, multi)) {
-        for (int i = warp; i < ncand; i += 8) {
-            const float v = pv[(size_t)i * 32];
-            const int gi = pi[(size_t)i * 32];
-            if (multi && v >= best - eps && gi != 0x7fffffff) {
-                const double* sgp = S64 + (size_t)gi * dims;
-                double acc = 0.0;
-                // argmax is invariant to the positive normalisation, so the raw float64 query can be used
-                if (q64 != nullptr && q0 + trial < n_q) {
-                    const double* qr = q64 + (size_t)(q0 + trial) * dims;
-                    for (int k = 0; k < dims; ++k) acc += sgp[k] * qr[k];
-                } else {
-                    for (int k = 0; k < dims; ++k) acc += sgp[k] * (double)cxg[(size_t)k * 32];
-                }
-                if (acc > dbest || (acc == dbest && gi < dg)) {
-                    dbest = acc;
-                    dg = gi;
-                }
-            }
-        }
-    }
-    __syncthreads();          // sg is re-used for the merge
-    sd[warp][lane] = dbest;
-    sg[warp][lane] = dg;
-    __syncthreads();
-    if (multi) {
-        dbest = sd[0][lane];
-        dg = sg[0][lane];
-        for (int w = 1; w < 8; ++w) {
-            const double v = sd[w][lane];
-            const int gi = sg[w][lane];
-            if (v > dbest || (v == dbest && gi < dg)) {
-                dbest = v;
-                dg = gi;
-            }
-        }
-        best_g = dg;
-    }
-    if (out_idx && warp == 0) out_idx[trial] = best_g;
-    if (out_base) {
-        const float* sgp = S32 + (size_t)best_g * dpad;
-        float* og = out_base + ((size_t)g * out_rows_per_group + out_row0) * 32 + lane;
-        for (int k = warp; k < dims; k += 8) og[(size_t)k * 32] = sgp[k];
-    }
-}
-
-// --------------------------------------------------------------------------------------
-// Gated correction node (slam.py:233-237): x = [p ; q ; flag].  CTA = one trial group x 8 warps;
-// warps split the dimensions, the dot product is reduced through shared memory.
-// desc: d in_row0 out_vec rate_bits thres_bits atol_bits
-__global__ void __launch_bounds__(256) k_gate(SsbCtx c, const int* __restrict__ desc, int item0, int i_rel) {
-    __shared__ float part[8][32];
-    const int* d = desc + (item0 + blockIdx.y) * 6;
-    const int dims = d[0], in_row0 = d[1], out_vec = d[2];
-    const float rate = __int_as_float(d[3]), thres = __int_as_float(d[4]), atol = __int_as_float(d[5]);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.x;
-    float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    // pass 1: p - q goes to the output slot, p.q is reduced over the 8 warps
-    float dot = 0.f;
-    for (int k = warp; k < dims; k += 8) {
-        const float p = vg[(size_t)(in_row0 + k) * 32];
-        const float q = vg[(size_t)(in_row0 + dims + k) * 32];
-        dot = fmaf(p, q, dot);
-        vg[(size_t)(out_vec + k) * 32] = p - q;
-    }
-    part[warp][lane] = dot;
-    __syncthreads();
-    dot = 0.f;
-    for (int w = 0; w < 8; ++w) dot += part[w][lane];
-    const float flag = vg[(size_t)(in_row0 + 2 * dims) * 32];
-    const bool open = (fabsf(flag) <= atol) && (dot > thres);
-    // pass 2: each thread rescales the values it wrote itself
-    for (int k = warp; k < dims; k += 8) {
-        float* o = vg + (size_t)(out_vec + k) * 32;
-        *o = open ? rate * *o : 0.f;
-    }
-}
-
-// --------------------------------------------------------------------------------------
-// End-of-step rows: Lowpass updates (y_new = a*y_old + b*u, written to the other half of
-// the ping-pong buffer = nengo's update-after-read), probe samples, PES activity traces.
-// The same kernel materialises the sink rows of a dependency level into vec scratch before the level's
-// consumers run (kinds 3 / 4), so that no consumer evaluates CSR rows itself.
-// kind 0 filter, 1 probe, 2 activity trace, 3 / 4 materialise (4: on the values the previous step read),
-// 5 neuron-output probe (activity row -> probe block; CSR population only).
-//
-// Three CTA populations in one launch (the host sorts every segment's rows into them at finalize):
-//  * dense items: rows that share one column list (the circular-convolution DFT matrices, to_Fourier / to_SSP,
-//    decoder-to-filter fans) form a dense block T[R][Kpad].  A CTA owns 8 rows of a block for ONE trial group;
-//    its four warps split the 32-column slabs (split-K), each warp gathers its slab's 32 source rows once into
-//    registers and reads the 8 x 32 coefficient slab as shared-memory broadcasts; the four partial sums are
-//    added in warp order.  A source row is fetched once per 8 sink rows instead of once per entry, and the
-//    whole item is two dependent memory rounds (coefficients + column list, then the gathers);
-//  * records: rows with at most 8 entries (most Lowpass inputs) and the PES activity traces are packed by the
-//    host into one 128-byte record each: the warp reads it with one coalesced load and distributes the words
-//    with shuffles, so a row is two dependent rounds (record, then gathers) and two rows per warp are in flight;
-//  * CSR rows (the rest): one warp per (row, group), entries as warp-uniform 8-byte loads.
-// record words: 0 kind | 1 dst | 2 a | 3 b | 4..11 columns on even steps | 12..19 columns on odd steps |
-//               20..27 coefficients | 28 src (kind 2) | 29..31 unused
-#define SSB_DENSE_RCH 8
-#define SSB_DENSE_SLAB 32
-#define SSB_REC_PER_WARP 4
-
-// dense rows: kind dst a_bits b_bits
-__device__ __forceinline__ void ssb_lin_store(const SsbCtx& c, const SsbStep& s, float* vg, int g, int lane, int kind, int dst,
-                                              float a, float b, float u) {
-    if (kind == 0) {
-        const float y = vg[(size_t)(1 + dst + s.par_old) * 32];
-        vg[(size_t)(1 + dst + s.par_new) * 32] = fmaf(b, u, a * y);
-    } else if (kind >= 3) {
-        vg[(size_t)dst * 32] = u;
-    } else {
-        float* pg = c.probe + (((size_t)g * c.probe_cap + (size_t)(s.step - c.dyn[2])) * c.n_probe + dst) * 32 + lane;
-        __stcs(pg, u);
-    }
-}
-
-struct SsbLinArgs {
-    const int* rows;          // CSR rows [src kind dst lo hi]
-    const float* ab;
-    int n_rows;
-    const int* items;         // dense items
-    int n_items;
-    const int* ddesc;
-    const float* dT;
-    const int* dcols;
-    const int* drows;
-    const int* recs;          // packed records, 32 words each
-    int n_recs;
-};
-
-__global__ void __launch_bounds__(128, 8) k_lin(SsbCtx c, SsbLinArgs L, int i_rel) {
-    __shared__ __align__(16) float s_t[4][SSB_DENSE_RCH][SSB_DENSE_SLAB];
-    __shared__ float s_red[4][SSB_DENSE_RCH][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const SsbStep s = ssb_step(c, i_rel);
-    const int n_dense_ctas = L.n_items * c.G;
-    if ((int)blockIdx.x < n_dense_ctas) {
-        const int item = blockIdx.x / c.G, g = blockIdx.x - item * c.G;
-        // item: t_off (of its first row) | cols_off | kpad | rows_off (of its first row) | nr | previous-step view | - | -
-        const int4 it = __ldg(reinterpret_cast<const int4*>(L.items + (size_t)item * 8));
-        const int2 it2 = __ldg(reinterpret_cast<const int2*>(L.items + (size_t)item * 8 + 4));
-        const int kpad = it.z, nr = it2.x;
-        const float* __restrict__ T = L.dT + it.x;
-        const int* __restrict__ dr = L.drows + (size_t)it.w * 4;
-        const int* __restrict__ cols = L.dcols + it.y + ((s.odd ^ it2.y) ? kpad : 0);
-        float* vg = ssb_grp(c.vec, c.nv, g, lane);
-        // this warp's output rows (r = warp, warp + 4): descriptors requested now, used after the reduction
-        int4 rd[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-            rd[q] = (warp + 4 * q < nr) ? __ldg(reinterpret_cast<const int4*>(dr) + warp + 4 * q) : make_int4(3, 0, 0, 0);
-        float acc[SSB_DENSE_RCH];
-#pragma unroll
-        for (int r = 0; r < SSB_DENSE_RCH; ++r) acc[r] = 0.f;
-        const int n_slabs = kpad / SSB_DENSE_SLAB;
-        const int tr0 = lane >> 3, tq = lane & 7;                       // lane -> rows tr0, tr0 + 4, float4 tq of the slab
-        for (int sl = warp; sl < n_slabs; sl += 4) {
-            const int k0 = sl * SSB_DENSE_SLAB;
-            const int col = __ldg(cols + k0 + lane);
-            float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-            if (tr0 < nr) t0 = __ldg(reinterpret_cast<const float4*>(T + (size_t)tr0 * kpad + k0) + tq);
-            if (tr0 + 4 < nr) t1 = __ldg(reinterpret_cast<const float4*>(T + (size_t)(tr0 + 4) * kpad + k0) + tq);
-            float x[SSB_DENSE_SLAB];
-#pragma unroll
-            for (int e = 0; e < SSB_DENSE_SLAB; ++e) x[e] = ssb_ld_src(vg + (size_t)__shfl_sync(0xffffffffu, col, e) * 32);
-            __syncwarp();                                               // previous slab's broadcasts are done
-            *reinterpret_cast<float4*>(&s_t[warp][tr0][tq * 4]) = t0;
-            *reinterpret_cast<float4*>(&s_t[warp][tr0 + 4][tq * 4]) = t1;
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < SSB_DENSE_RCH; ++r) {
-#pragma unroll
-                for (int q = 0; q < SSB_DENSE_SLAB / 4; ++q) {
-                    const float4 t = *reinterpret_cast<const float4*>(&s_t[warp][r][q * 4]);
-                    acc[r] = fmaf(t.x, x[4 * q + 0], acc[r]);
-                    acc[r] = fmaf(t.y, x[4 * q + 1], acc[r]);
-                    acc[r] = fmaf(t.z, x[4 * q + 2], acc[r]);
-                    acc[r] = fmaf(t.w, x[4 * q + 3], acc[r]);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < SSB_DENSE_RCH; ++r) s_red[warp][r][lane] = acc[r];
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {                                   // fixed order: ((w0 + w1) + w2) + w3
-            const int r = warp + 4 * q;
-            if (r < nr) {
-                const float u = ((s_red[0][r][lane] + s_red[1][r][lane]) + s_red[2][r][lane]) + s_red[3][r][lane];
-                ssb_lin_store(c, s, vg, g, lane, rd[q].x, rd[q].y, __int_as_float(rd[q].z), __int_as_float(rd[q].w), u);
-            }
-        }
-        return;
-    }
-    const int rec_per_cta = 4 * SSB_REC_PER_WARP;
-    const int n_rec_ctas = ((L.n_recs + rec_per_cta - 1) / rec_per_cta) * c.G;
-    if ((int)blockIdx.x < n_dense_ctas + n_rec_ctas) {
-        const int cb = blockIdx.x - n_dense_ctas;
-        const int rblk = cb / c.G, g = cb - rblk * c.G;
-        const int r0 = (rblk * 4 + warp) * SSB_REC_PER_WARP;
-        float* vg = ssb_grp(c.vec, c.nv, g, lane);
-        int w[SSB_REC_PER_WARP];
-#pragma unroll
-        for (int q = 0; q < SSB_REC_PER_WARP; ++q) w[q] = (r0 + q < L.n_recs) ? __ldg(L.recs + (size_t)(r0 + q) * 32 + lane) : 0;
-        float x[SSB_REC_PER_WARP][8], y[SSB_REC_PER_WARP];
-        int kind[SSB_REC_PER_WARP], dst[SSB_REC_PER_WARP];
-        const int cbase = 4 + (s.odd ? 8 : 0);
-#pragma unroll
-        for (int q = 0; q < SSB_REC_PER_WARP; ++q) {
-            kind[q] = __shfl_sync(0xffffffffu, w[q], 0);
-            dst[q] = __shfl_sync(0xffffffffu, w[q], 1);
-            y[q] = 0.f;
-            if (r0 + q >= L.n_recs) {
-                kind[q] = -1;
-                continue;
-            }
-            if (kind[q] == 2) {
-                const int src = __shfl_sync(0xffffffffu, w[q], 28);
-                x[q][0] = ssb_grp(c.act, c.n_act, g, lane)[(size_t)src * 32];
-                y[q] = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane)[((size_t)s.odd * c.n_afilt + dst[q]) * 32];
-            } else {
-                const int cb4 = kind[q] == 4 ? 4 + (s.odd ? 0 : 8) : cbase;   // kind 4 reads the previous step's view
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[q][e] = ssb_ld_src(vg + (size_t)__shfl_sync(0xffffffffu, w[q], cb4 + e) * 32);
-                if (kind[q] == 0) y[q] = vg[(size_t)(1 + dst[q] + s.par_old) * 32];
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < SSB_REC_PER_WARP; ++q) {
-            if (kind[q] < 0) continue;
-            const float a = __int_as_float(__shfl_sync(0xffffffffu, w[q], 2)), b = __int_as_float(__shfl_sync(0xffffffffu, w[q], 3));
-            if (kind[q] == 2) {
-                ssb_grp(c.afilt, 2 * c.n_afilt, g, lane)[((size_t)(1 - s.odd) * c.n_afilt + dst[q]) * 32] = fmaf(b, x[q][0], a * y[q]);
-                continue;
-            }
-            float u = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) u = fmaf(__int_as_float(__shfl_sync(0xffffffffu, w[q], 20 + e)), x[q][e], u);
-            if (kind[q] == 0) vg[(size_t)(1 + dst[q] + s.par_new) * 32] = fmaf(b, u, a * y[q]);
-            else if (kind[q] >= 3) vg[(size_t)dst[q] * 32] = u;
-            else {
-                float* pg = c.probe + (((size_t)g * c.probe_cap + (size_t)(s.step - c.dyn[2])) * c.n_probe + dst[q]) * 32 + lane;
-                __stcs(pg, u);
-            }
-        }
-        return;
-    }
-    // ---- CSR rows: flat index -> (row block, group)
-    const int cb = blockIdx.x - n_dense_ctas - n_rec_ctas;
-    const int rblk = cb / c.G, g = cb - rblk * c.G;
-    const int r = rblk * 4 + warp;
-    if (r >= L.n_rows) return;
-    float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    const int* rp = L.rows + (size_t)r * 5;
-    const int src = rp[0], kind = rp[1], dst = rp[2];
-    const float a = L.ab[r * 2], b = L.ab[r * 2 + 1];
-    if (kind == 2) {
-        float* fg = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane);
-        const float y = fg[((size_t)s.odd * c.n_afilt + dst) * 32];
-        const float u = ssb_grp(c.act, c.n_act, g, lane)[(size_t)src * 32];
-        fg[((size_t)(1 - s.odd) * c.n_afilt + dst) * 32] = fmaf(b, u, a * y);
-        return;
-    }
-    if (kind == 5) {                                          // neuron-output probe: this step's activity row, unfiltered
-        ssb_lin_store(c, s, vg, g, lane, 1, dst, a, b, ssb_grp(c.act, c.n_act, g, lane)[(size_t)src * 32]);
-        return;
-    }
-    const int2* __restrict__ ent = kind == 4 ? s.ent_new : s.ent_old;
-    const int lo = rp[3], hi = rp[4];
-    float u = 0.f;
-    int p = lo;
-    for (; p + 32 <= hi; p += 32) u = ssb_row_batch<32>(ent + p, vg, u);
-    for (; p < hi; p += 8) u = ssb_row_batch<8>(ent + p, vg, u);
-    ssb_lin_store(c, s, vg, g, lane, kind, dst, a, b, u);
-}
-
-__global__ void k_advance(long long* dyn, int n) { dyn[0] += n; }
-
-// --------------------------------------------------------------------------------------
-// Stand-alone SSP encode: out[p][m] = (1/d) * sum_k cos(theta_k + 2 pi k m / d), theta = A_scaled x.
-__global__ void k_ssp_encode(const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ out,
-                             long long n_points, int n, int d) {
-    extern __shared__ double cs[];  // [2][d]
-    const long long p = blockIdx.x;
-    if (p >= n_points) return;
-    for (int k = threadIdx.x; k < d; k += blockDim.x) {
-        double th = 0.0;
-        for (int j = 0; j < n; ++j) th += A[(size_t)k * n + j] * x[(size_t)p * n + j];
-        double sn, cn;
-        sincos(th, &sn, &cn);
-        cs[k] = cn;
-        cs[d + k] = sn;
-    }
-    __syncthreads();
-    for (int m = threadIdx.x; m < d; m += blockDim.x) {
-        double acc = 0.0;
-        for (int k = 0; k < d; ++k) {
-            // exp(i*theta_k) * exp(+2 pi i k m / d); reduce k*m mod d to keep the angle small
-            const int km = (int)(((long long)k * m) % d);
-            double sn, cn;
-            sincospi(2.0 * (double)km / (double)d, &sn, &cn);
-            acc += cs[k] * cn - cs[d + k] * sn;
-        }
-        out[(size_t)p * d + m] = acc / (double)d;
-    }
-}
-
-// Normalise query rows (skip if norm < 1e-6) and write them group-tiled [g][k][32] in float for the scan.
-__global__ void k_decode_prep(const double* __restrict__ q, float* __restrict__ cx, long long n_q, int B, int d, int dpad,
-                              long long q0) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B) return;
-    float* cxg = cx + ((size_t)(t >> 5) * dpad) * 32 + (t & 31);
-    const long long row = q0 + t;
-    if (row >= n_q) {
-        for (int k = 0; k < dpad; ++k) cxg[(size_t)k * 32] = 0.f;
-        return;
-    }
-    double nrm = 0.0;
-    for (int k = 0; k < d; ++k) nrm += q[(size_t)row * d + k] * q[(size_t)row * d + k];
-    nrm = sqrt(nrm);
-    const double sc = nrm < 1e-6 ? 1.0 : 1.0 / nrm;
-    for (int k = 0; k < dpad; ++k) cxg[(size_t)k * 32] = k < d ? (float)(q[(size_t)row * d + k] * sc) : 0.f;
-}
+#include "ssb_common.cuh"
+#include "ssb_inputs.cuh"
+#include "ssb_ens_small.cuh"
+#include "ssb_ens_wide.cuh"
+#include "ssb_decode.cuh"
+#include "ssb_pes.cuh"
+#include "ssb_cleanup.cuh"
+#include "ssb_lin.cuh"
+#include "ssb_ssp.cuh"
