@@ -44,13 +44,22 @@ struct CleanupDev {
     bool tc = false;
     float* stc = nullptr;
     int kp = 0, n_tiles = 0, tr = 128;
+    // K-blocked tensor-core scan (k_cleanup_scan_tck) for operand widths whose tiles do not fit in shared memory
+    bool tck = false;
+    float* stck = nullptr;   // grid, pre-tiled per (tile, K block)
+    float* xt = nullptr;     // queries, tiled per (trial block, K block) by k_scan_xtiles every step
+    int n_kb = 0;
 };
 
 // grid rows per tensor-core tile: 128, or 64 when the operand tiles of 128 rows do not fit in shared memory; 0 = no fit
 int scan_tc_rows(int dpad) {
     const int kp = (dpad + 7) / 8 * 8;
+    // SSB_SCAN_TR=64: 64-row tiles even when 128 fit (114 KB instead of 172 KB of shared memory at d = 55, so a scan CTA
+    // can share its SM with a CTA of the streaming kernels)
+    const char* e = getenv("SSB_SCAN_TR");
+    const bool force64 = e && atoi(e) == 64;
     for (int tr : {128, 64})
-        if ((size_t)(2 * 128 + 4 * tr) * kp * sizeof(float) <= 216 * 1024) return tr;
+        if (!(force64 && tr == 128) && (size_t)(2 * 128 + 4 * tr) * kp * sizeof(float) <= 216 * 1024) return tr;
     return 0;
 }
 
@@ -60,6 +69,11 @@ bool scan_tc_allowed(int dpad) {
     const char* e = getenv("SSB_SCAN");
     if (e && std::string(e) == "ffma") return false;
     return scan_tc_rows(dpad) > 0;
+}
+
+bool scan_ffma_forced() {
+    const char* e = getenv("SSB_SCAN");
+    return e && std::string(e) == "ffma";
 }
 
 // Grid-scan geometry: a CTA scans rows_per_chunk grid rows in shared-memory tiles of tile_rows rows for 4 trial
@@ -74,6 +88,15 @@ void scan_geometry(int G, int dpad, int n_groups, CleanupDev* cd) {
         cd->n_tiles = (G + cd->tr - 1) / cd->tr;
         cd->n_chunks = std::max(1, std::min(std::min(cd->n_tiles, SSB_SCAN_MAX_CHUNKS), 148 / std::max(1, group_ctas)));
         cd->rows_per_chunk = cd->tile_rows = cd->tr;
+        return;
+    }
+    if (!scan_ffma_forced()) {     // wide operands (d = 649): both operands stream through K blocks of 32 columns
+        cd->tck = true;
+        cd->n_kb = (dpad + SSB_SCK_KB - 1) / SSB_SCK_KB;
+        cd->tr = 128;
+        cd->n_tiles = (G + 127) / 128;
+        cd->n_chunks = std::max(1, std::min(std::min(cd->n_tiles, SSB_SCAN_MAX_CHUNKS), 148 / std::max(1, group_ctas)));
+        cd->rows_per_chunk = cd->tile_rows = 128;
         return;
     }
     int want = std::max(1, (148 * 8 + group_ctas - 1) / group_ctas);
@@ -125,7 +148,8 @@ struct ssb_sim {
     // independent kernels of one dependency level run on side streams (fork/join with events; under
     // capture these become parallel branches of the step graph)
     bool parallel = true;
-    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};   // B, C, D, E
+    std::vector<int> level_deps;            // [n_levels][n_levels] producer-kind bits (lowering.py); empty = wait for everything
     cudaStream_t io_h2d = nullptr, io_d2h = nullptr;   // copy streams of ssb_run_steps_io (one per DMA direction)
     std::vector<cudaEvent_t> io_events;
     std::vector<cudaEvent_t> dep_pool;
@@ -341,6 +365,40 @@ int build_scan_tiles(const float* S32, int G, int dpad, CleanupDev* cd) {
     return 0;
 }
 
+// Grid rows -> per (tile, K block) operand blocks [hi | lo][KB/4][16][8][4]; also allocates the query tiles.
+int build_scan_tiles_k(const float* S32, int G, int dpad, int n_groups, CleanupDev* cd) {
+    const int n_kb = cd->n_kb, part = SSB_SCK_PART;
+    std::vector<float> t((size_t)cd->n_tiles * n_kb * 2 * part, 0.f);
+    for (int g = 0; g < G; ++g) {
+        const int tile = g / 128, r = g % 128;
+        for (int k = 0; k < dpad; ++k) {
+            const int kb = k / SSB_SCK_KB, kk = k % SSB_SCK_KB;
+            float* hi = &t[((size_t)tile * n_kb + kb) * 2 * part];
+            float* lo = hi + part;
+            const float x = S32[(size_t)g * dpad + k];
+            const float h = ssb_tf32_round(x);
+            const size_t off = ((size_t)(kk / 4) * 16 + r / 8) * 32 + (r % 8) * 4 + kk % 4;
+            hi[off] = h;
+            lo[off] = ssb_tf32_round(x - h);
+        }
+    }
+    SSB_CUDA(cudaMalloc((void**)&cd->stck, t.size() * sizeof(float)));
+    SSB_CUDA(cudaMemcpy(cd->stck, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t xt_floats = (size_t)((n_groups + 3) / 4) * n_kb * 2 * part;
+    SSB_CUDA(cudaMalloc((void**)&cd->xt, xt_floats * sizeof(float)));
+    SSB_CUDA(cudaMemset(cd->xt, 0, xt_floats * sizeof(float)));
+    return 0;
+}
+
+void launch_scan_tck(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const CleanupDev& cd, int n_groups) {
+    const int quads = (n_groups + 3) / 4;
+    if (csr) k_scan_xtiles<true><<<dim3(cd.n_kb, quads), 128, 0, st>>>(c, desc, cd.cx, cd.xt, cd.n_kb, n_groups);
+    else k_scan_xtiles<false><<<dim3(cd.n_kb, quads), 128, 0, st>>>(c, desc, cd.cx, cd.xt, cd.n_kb, n_groups);
+    const size_t smem = (size_t)SSB_SCK_NST * 4 * SSB_SCK_PART * sizeof(float);
+    k_cleanup_scan_tck<<<dim3(cd.n_chunks, quads), 320, smem, st>>>(desc, cd.stck, cd.xt, cd.pval, cd.pidx, cd.n_kb, cd.n_tiles,
+                                                                  n_groups, cd.n_chunks * SSB_TOPK * 2);
+}
+
 void launch_scan_tc(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const CleanupDev& cd, int n_groups) {
     dim3 grid(cd.n_chunks, (n_groups + 3) / 4);
     const size_t smem = (size_t)(2 * 128 + 4 * cd.tr) * cd.kp * sizeof(float);
@@ -358,10 +416,10 @@ void launch_scan_tc(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc,
 }
 
 // candidates per trial left by the scan (the tensor-core scan keeps two lists per chunk)
-int scan_n_cand(const CleanupDev& cd) { return cd.n_chunks * SSB_TOPK * (cd.tc ? 2 : 1); }
+int scan_n_cand(const CleanupDev& cd) { return cd.n_chunks * SSB_TOPK * ((cd.tc || cd.tck) ? 2 : 1); }
 
 // relative near-tie band of the fp64 re-score: fp32 FFMA bound, or the 3xTF32 bound (3 * 2^-22 + accumulation)
-float scan_eps_floor(const CleanupDev& cd) { return cd.tc ? 1.6e-5f : 0.f; }
+float scan_eps_floor(const CleanupDev& cd) { return (cd.tc || cd.tck) ? 1.6e-5f : 0.f; }
 
 template <int DP>
 void launch_scan(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const float* S, const CleanupDev& cd,
@@ -381,6 +439,7 @@ void launch_scan(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, co
 void dispatch_scan(cudaStream_t st, bool csr, int dpad, int n_groups, const SsbCtx& c, const int* desc, const float* S,
                    const CleanupDev& cd, int i_rel) {
     if (cd.tc) launch_scan_tc(st, csr, c, desc, cd, n_groups);
+    else if (cd.tck) launch_scan_tck(st, csr, c, desc, cd, n_groups);
     else if (dpad == 56) launch_scan<56>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
     else if (dpad == 100) launch_scan<100>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
     else launch_scan<0>(st, csr, c, desc, S, cd, dpad, n_groups, i_rel);
@@ -394,6 +453,8 @@ void scan_smem_optin() {
     cudaFuncSetAttribute(k_cleanup_scan_tc<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(k_cleanup_scan_tc<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(k_cleanup_scan_tc<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_cleanup_scan_tck, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(SSB_SCK_NST * 4 * SSB_SCK_PART * sizeof(float)));
 }
 
 // Wide ensembles of one level: one launch per (kernel flavour, width class); the items of a launch are
@@ -901,11 +962,19 @@ void launch_inputs(ssb_sim* s, cudaStream_t st, int i_rel) {
 
 // `have_inputs`: the previous step of this launch sequence already produced this step's input rows;
 // `prefetch_next`: produce the next step's input rows on stream C while this step runs (they go to the other parity copy).
+//
+// Level scheduling.  The lowering's level_deps[L][Lp] says which producer kinds of level Lp the sink rows of level L read
+// (bit 0 narrow ensembles, 1 static decoders, 2 clean-up nodes, 3 gate nodes).  The chain of a level (its k_lin rows and
+// its narrow ensembles) runs on stream A when it needs the narrow ensembles of an earlier level (stream order then
+// carries that dependency), otherwise on stream E, waiting only for the events of the producers it really reads — in
+// SLAM the landmark circular convolution (level 1) needs the clean-up index and the OVC decode, not the 14 000 VCO
+// neurons of level 0, so it overlaps them instead of queueing behind them.
 int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next = false) {
     const SsbCtx& c = s->ctx;
     const int G = s->n_groups;
     const bool par = s->parallel && (!s->profiling || s->timeline) && !s->debug_sync;
     cudaStream_t A = s->stream, B = par ? s->aux[0] : A, C = par ? s->aux[1] : A, D = par ? s->aux[2] : A;
+    cudaStream_t E = par ? s->aux[3] : A;
     const bool any_inputs = s->synth_on || s->nt > 0;
     if (any_inputs && !(have_inputs && par)) launch_inputs(s, A, i_rel);
     const bool prefetch = any_inputs && prefetch_next && par;
@@ -913,35 +982,50 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
         stream_dep(s, A, C);
         launch_inputs(s, C, i_rel + 1);
     }
-    bool pes_done = s->n_pes == 0, b_used = false;
-    for (int lvl = 0; lvl < s->n_levels; ++lvl) {
+    const int NL = s->n_levels;
+    // events of the producers of every level (null = that level has no such producer)
+    std::vector<cudaEvent_t> ev_small(NL, nullptr), ev_dec(NL, nullptr), ev_pick(NL, nullptr), ev_gate(NL, nullptr);
+    auto mark = [&](cudaStream_t st) {
+        cudaEvent_t e = dep_event(s);
+        cudaEventRecord(e, st);
+        return e;
+    };
+    auto wait_on = [&](cudaStream_t st, cudaEvent_t e) {
+        if (e) cudaStreamWaitEvent(st, e, 0);
+    };
+    bool pes_done = s->n_pes == 0, b_used = false, c_used = prefetch, d_used = false, e_used = false;
+    for (int lvl = 0; lvl < NL; ++lvl) {
         const int* st = &s->h_stages[lvl * 12];
         const LevelInfo& li = s->levels[lvl];
+        // which stream carries this level's chain, and what it waits for
+        cudaStream_t T = A;
+        if (lvl > 0 && par) {
+            int need_small = s->level_deps.empty() ? 1 : 0, any = 0;
+            for (int lp = 0; lp < lvl && !s->level_deps.empty(); ++lp) {
+                need_small |= s->level_deps[(size_t)lvl * NL + lp] & 1;
+                any |= s->level_deps[(size_t)lvl * NL + lp];
+            }
+            // (every event E waits for is downstream of this step's first k_lin on A, which orders E after the previous step)
+            if (!need_small && any) T = E;
+            for (int lp = 0; lp < lvl; ++lp) {
+                const int m = s->level_deps.empty() ? 15 : s->level_deps[(size_t)lvl * NL + lp];
+                if (m & 1) wait_on(T, ev_small[lp]);
+                if (m & 2) wait_on(T, ev_dec[lp]);
+                if (m & 4) wait_on(T, ev_pick[lp]);
+                if (m & 8) wait_on(T, ev_gate[lp]);
+            }
+            if (T == E) e_used = true;
+        }
         if (st[11] > 0) {   // materialise this level's sink rows (ensemble / node inputs, PES errors)
-            LaunchTimer t(s, K_LIN, A);
-            launch_lin(s, A, lvl, i_rel);
+            LaunchTimer t(s, K_LIN, T);
+            launch_lin(s, T, lvl, i_rel);
         }
         const bool pes_here = !pes_done && lvl == s->pes_level;
         const bool useB = li.n_voja > 0 || pes_here;
         const bool useC = st[7] > 0 || st[9] > 0;
         const bool useD = li.n_static > 0 || st[5] > 0;
-        if (useB) stream_dep(s, A, B);
-        if (useC) stream_dep(s, A, C);
-        if (useD) stream_dep(s, A, D);
-        b_used = b_used || useB;
-        if (li.n_voja > 0) {
-            LaunchTimer t(s, K_VOJA, B);
-            launch_wide(s, B, st, true, i_rel);
-        }
-        if (li.n_static > 0) {
-            LaunchTimer t(s, K_WIDE, D);
-            launch_wide(s, D, st, false, i_rel);
-        }
-        if (pes_here) {   // every PES pre-ensemble has produced its activities
-            if (s->pes_needs_static && li.n_static > 0) stream_dep(s, D, B);
-            launch_pes(s, B, i_rel);
-            pes_done = true;
-        }
+        // the clean-up chain goes first: its one-CTA-per-SM scan must not queue behind kernels that fill the SMs
+        if (useC) stream_dep(s, T, C);
         for (int i = 0; i < st[7]; ++i) {
             const int ci = st[6] + i;
             const int* d = &s->h_cleanup[ci * 6];
@@ -949,6 +1033,10 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
             {
                 LaunchTimer t(s, K_SCAN, C);
                 dispatch_scan(C, true, d[2], G, c, s->d_cleanup + ci * 6, s->d_W + d[3], cd, i_rel);
+                if (cd.tck) {                                    // + k_scan_xtiles
+                    s->kind_launches[K_EXTRA]++;
+                    s->total_launches++;
+                }
             }
             {
                 LaunchTimer t(s, K_PICK, C);
@@ -957,19 +1045,30 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
                                                  scan_eps_floor(cd));
             }
         }
+        if (st[7] > 0) ev_pick[lvl] = mark(C);
         if (st[9] > 0) {
             LaunchTimer t(s, K_GATE, C);
             dim3 grid(G, st[9]);
             k_gate<<<grid, 256, 0, C>>>(c, s->d_gate, st[8], i_rel);
+            ev_gate[lvl] = mark(C);
         }
-        if (st[1] > 0) {
-            LaunchTimer t(s, K_SMALL, A);
-            // items are sorted by neuron count (descending): the leading ones get a whole CTA per trial group
-            int n_split = 0;
-            while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
-            const int packed_warps = (st[1] - n_split) * G;
-            const int blocks = n_split * G + (packed_warps + 3) / 4;
-            k_ens_small<<<blocks, 128, 0, A>>>(c, s->d_small + st[0] * 9, st[1], n_split);
+        if (useD) stream_dep(s, T, D);
+        if (useB) stream_dep(s, T, B);
+        b_used = b_used || useB;
+        c_used = c_used || useC;
+        d_used = d_used || useD;
+        if (li.n_static > 0) {
+            LaunchTimer t(s, K_WIDE, D);
+            launch_wide(s, D, st, false, i_rel);
+        }
+        if (li.n_voja > 0) {
+            LaunchTimer t(s, K_VOJA, B);
+            launch_wide(s, B, st, true, i_rel);
+        }
+        if (pes_here) {   // every PES pre-ensemble has produced its activities
+            if (s->pes_needs_static && li.n_static > 0) stream_dep(s, D, B);
+            launch_pes(s, B, i_rel);
+            pes_done = true;
         }
         if (st[5] > 0) {
             if (li.dec_needs_voja) stream_dep(s, B, D);   // recorded after the Voja kernel (and k_pes, if any)
@@ -991,11 +1090,23 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
                     c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off);
             else
                 k_decode<<<grid, 128, smem, D>>>(c, s->d_dec, st[4]);
+            ev_dec[lvl] = mark(D);
         }
-        if (useC) stream_dep(s, C, A);
-        if (useD) stream_dep(s, D, A);
+        if (st[1] > 0) {
+            LaunchTimer t(s, K_SMALL, T);
+            // items are sorted by neuron count (descending): the leading ones get a whole CTA per trial group
+            int n_split = 0;
+            while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
+            const int packed_warps = (st[1] - n_split) * G;
+            const int blocks = n_split * G + (packed_warps + 3) / 4;
+            k_ens_small<<<blocks, 128, 0, T>>>(c, s->d_small + st[0] * 9, st[1], n_split);
+            ev_small[lvl] = mark(T);
+        }
     }
-    if (prefetch) stream_dep(s, C, A);
+    // the end-of-step rows read everything: join every stream that was used
+    if (c_used) stream_dep(s, C, A);
+    if (d_used) stream_dep(s, D, A);
+    if (e_used) stream_dep(s, E, A);
     if (b_used) stream_dep(s, B, A);
     if (!pes_done) launch_pes(s, A, i_rel);
     if (s->n_lin > 0) {
@@ -1067,9 +1178,13 @@ int ssb_create(int device, int n_trials, ssb_sim** out) {
     {   // the long HBM-streaming chain (B) and the decode chain (D) are scheduled ahead of the rest
         int pr_lo = 0, pr_hi = 0;
         SSB_CUDA(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
-        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[0], cudaStreamNonBlocking, pr_hi));
-        SSB_CUDA(cudaStreamCreateWithFlags(&s->aux[1], cudaStreamNonBlocking));
-        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[2], cudaStreamNonBlocking, pr_hi));
+        // the clean-up chain C (short, and its scan needs whole SMs) and the chain of the later levels E go first, then the
+        // long HBM-streaming chain B and the decode chain D; the narrow-ensemble kernels on A fill what is left
+        const int pr_mid = std::min(pr_lo, pr_hi + 1);
+        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[0], cudaStreamNonBlocking, pr_mid));
+        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[1], cudaStreamNonBlocking, pr_hi));
+        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[2], cudaStreamNonBlocking, pr_mid));
+        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[3], cudaStreamNonBlocking, pr_hi));
     }
     if (const char* e = getenv("SSB_SERIAL")) s->parallel = e[0] != '1';
     if (const char* e = getenv("SSB_PES_PAD")) s->pes_pad_smem = (size_t)atoi(e) * 1024;
@@ -1139,6 +1254,9 @@ int ssb_finalize(ssb_sim* s) {
     s->h_dec = host_ints(s, "dec");
     s->h_cleanup = host_ints(s, "cleanup");
     s->h_pes = host_ints(s, "pes");
+    s->level_deps = host_ints(s, "level_deps");
+    if (s->level_deps.size() != (size_t)s->n_levels * s->n_levels) s->level_deps.clear();
+    if (const char* e = getenv("SSB_LEVEL_DEPS")) if (e[0] == '0') s->level_deps.clear();   // A/B switch: level barriers
     if ((int)s->h_stages.size() != s->n_levels * 12) return fail(-1, "ssb_finalize: stages array has wrong size");
     if (int rc = setup_pes_defer(s)) return rc;        // decides whether k_pes_hist owns the PES activity traces
     if (int rc = build_lin_program(s)) return rc;
@@ -1209,9 +1327,10 @@ int ssb_finalize(ssb_sim* s) {
             cd.s64 = s->d_s64 + s64_off;
             s64_off += need;
         }
-        if (cd.tc) {
+        if (cd.tc || cd.tck) {
             const float* hW = reinterpret_cast<const float*>(s->arrays["weights"].bytes.data());
-            if (build_scan_tiles(hW + d[3], d[0], d[2], &cd)) return -2;
+            if (cd.tc ? build_scan_tiles(hW + d[3], d[0], d[2], &cd) : build_scan_tiles_k(hW + d[3], d[0], d[2], s->n_groups, &cd))
+                return -2;
         }
     }
     // opt-in to large dynamic shared memory for very wide ensembles (d = 649)
@@ -1610,6 +1729,8 @@ void ssb_destroy(ssb_sim* s) {
         if (cd.pval) cudaFree(cd.pval);
         if (cd.pidx) cudaFree(cd.pidx);
         if (cd.stc) cudaFree(cd.stc);
+        if (cd.stck) cudaFree(cd.stck);
+        if (cd.xt) cudaFree(cd.xt);
     }
     if (s->step_graph) cudaGraphExecDestroy(s->step_graph);
     for (auto e : s->dep_pool) cudaEventDestroy(e);
@@ -1762,6 +1883,7 @@ int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* q
     SSB_CUDA(cudaMalloc((void**)&didx, (size_t)B * sizeof(int)));
     SSB_CUDA(cudaMemcpy(dS32, s32.data(), s32.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (cd.tc && build_scan_tiles(s32.data(), G, dpad, &cd)) return -2;
+    if (cd.tck && build_scan_tiles_k(s32.data(), G, dpad, B / 32, &cd)) return -2;
     SSB_CUDA(cudaMemcpy(dS64, sample_ssps, (size_t)G * d * sizeof(double), cudaMemcpyHostToDevice));
     SSB_CUDA(cudaMemcpy(dq, queries, (size_t)n_q * d * sizeof(double), cudaMemcpyHostToDevice));
     scan_smem_optin();
@@ -1786,6 +1908,8 @@ int ssb_ssp_decode_argmax(int device, const double* sample_ssps, const double* q
         SSB_CUDA(cudaMemcpy(idx_out + q0, didx, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));
     }
     if (cd.stc) cudaFree(cd.stc);
+    if (cd.stck) cudaFree(cd.stck);
+    if (cd.xt) cudaFree(cd.xt);
     cudaFree(dS32);
     cudaFree(dS64);
     cudaFree(dq);

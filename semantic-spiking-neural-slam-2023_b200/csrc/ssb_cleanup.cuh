@@ -485,6 +485,211 @@ k_cleanup_pick(int dims, int dpad, int ncand, const float* __restrict__ cx, cons
 }
 
 // --------------------------------------------------------------------------------------
+// K-blocked tensor-core grid scan for operand widths that do not fit in shared memory (d = 649: BASELINE configs[4]).
+// Same GEMM, same 3xTF32 split, same top-4 epilogue as k_cleanup_scan_tc, but BOTH operands stream through a
+// three-stage ring of K blocks of SSB_SCK_KB = 32 columns and the accumulator stays in TMEM across the K blocks:
+//   k_scan_xtiles     X (the queries of 128 trials) -> hi | lo operand tiles in global memory, once per step:
+//                     Xt[trial block][K block][hi | lo][KB/4][16][8][4]  (32 KB per (trial block, K block))
+//   k_cleanup_scan_tck  CTA = (grid chunk, trial block); 10 warps:
+//                     warps 0-7  epilogue (two per TMEM lane quadrant, as in k_cleanup_scan_tc),
+//                     warp 8     TMA producer: per (grid tile, K block) one bulk copy of the X block and one of the
+//                                S block into the stage, as soon as the MMAs that read the stage have retired,
+//                     warp 9     MMA issuer: 4 x 3 tcgen05.mma (128 x 128 x 8, tf32) per stage; tcgen05.commit frees
+//                                the stage; after the last K block a second commit publishes the D buffer.
+//                     D (128 lanes x 128 columns) is double-buffered in TMEM: tile i+1 accumulates while tile i drains.
+// Stck: [n_tiles][n_kb][hi | lo][KB/4][16][8][4] floats (host pre-tiled).  dynamic smem: 3 x 64 KB.
+#define SSB_SCK_KB 32
+#define SSB_SCK_NST 3
+#define SSB_SCK_PART (128 * SSB_SCK_KB)          // floats of one operand part (hi or lo) of one K block
+
+// grid (n_kb, trial blocks) x 128: thread = one trial (row of the A tile), 32 columns.
+template <bool CSR_INPUT>
+__global__ void __launch_bounds__(128)
+k_scan_xtiles(SsbCtx c, const int* __restrict__ d, float* __restrict__ cx, float* __restrict__ Xt, int n_kb, int n_groups) {
+    const int dims = d[1], dpad = d[2], in_row0 = d[4];
+    const int lane = threadIdx.x & 31, quad = threadIdx.x >> 5;
+    const int kb = blockIdx.x, tb = blockIdx.y;
+    const int group = tb * 4 + quad;
+    const bool live = group < n_groups;
+    const int g = live ? group : 0;
+    const int r = quad * 32 + lane;
+    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
+    const float* src = CSR_INPUT ? vg + (size_t)in_row0 * 32 : cxg;
+    float* a_hi = Xt + ((size_t)tb * n_kb + kb) * 2 * SSB_SCK_PART + (r >> 3) * 32 + (r & 7) * 4;
+    float* a_lo = a_hi + SSB_SCK_PART;
+    const int k0 = kb * SSB_SCK_KB;
+    float x[SSB_SCK_KB];
+#pragma unroll
+    for (int e = 0; e < SSB_SCK_KB; ++e) x[e] = (live && k0 + e < dims) ? src[(size_t)(k0 + e) * 32] : 0.f;
+#pragma unroll
+    for (int q = 0; q < SSB_SCK_KB / 4; ++q) {
+        float4 hi, lo;
+        hi.x = ssb_tf32_round(x[4 * q + 0]);
+        hi.y = ssb_tf32_round(x[4 * q + 1]);
+        hi.z = ssb_tf32_round(x[4 * q + 2]);
+        hi.w = ssb_tf32_round(x[4 * q + 3]);
+        lo.x = ssb_tf32_round(x[4 * q + 0] - hi.x);
+        lo.y = ssb_tf32_round(x[4 * q + 1] - hi.y);
+        lo.z = ssb_tf32_round(x[4 * q + 2] - hi.z);
+        lo.w = ssb_tf32_round(x[4 * q + 3] - hi.w);
+        *reinterpret_cast<float4*>(a_hi + (size_t)q * 16 * 32) = hi;
+        *reinterpret_cast<float4*>(a_lo + (size_t)q * 16 * 32) = lo;
+    }
+    if (CSR_INPUT && live) {                     // the query copy k_cleanup_pick re-scores near-ties with
+#pragma unroll
+        for (int e = 0; e < SSB_SCK_KB; ++e)
+            if (k0 + e < dpad) cxg[(size_t)(k0 + e) * 32] = x[e];
+    }
+}
+
+// desc: G d dpad s_off in_row0 out_vec
+__global__ void __launch_bounds__(320, 1)
+k_cleanup_scan_tck(const int* __restrict__ d, const float* __restrict__ Stck, const float* __restrict__ Xt,
+                   float* __restrict__ pval, int* __restrict__ pidx, int n_kb, int n_tiles, int n_groups, int n_cand) {
+    extern __shared__ __align__(1024) float sm[];
+    __shared__ unsigned long long full[SSB_SCK_NST], empty[SSB_SCK_NST], dfull[2], dfree[2];
+    __shared__ uint32_t tmem_slot;
+    constexpr int TR = 128;
+    const int G = d[0];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x, n_chunks = gridDim.x, tb = blockIdx.y;
+    const int my_tiles = chunk < n_tiles ? (n_tiles - chunk + n_chunks - 1) / n_chunks : 0;
+    constexpr uint32_t blk_bytes = 2u * SSB_SCK_PART * 4u;          // hi + lo of one operand block: 32 KB
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ssb_smem(&tmem_slot)), "r"(2 * TR));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SSB_SCK_NST; ++i) {
+            ssb_mbar_init(&full[i], 1);
+            ssb_mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ssb_mbar_init(&dfull[i], 1);
+            ssb_mbar_init(&dfree[i], 8);                               // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    ssb_tc_fence_before();
+    __syncthreads();
+    ssb_tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int n_blocks = my_tiles * n_kb;                            // (tile, K block) pairs of this CTA, in order
+    if (warp == 8) {
+        // ---------------- TMA producer
+        if (lane == 0) {
+            for (int q = 0; q < n_blocks; ++q) {
+                const int st = q % SSB_SCK_NST, round = q / SSB_SCK_NST;
+                if (round > 0) ssb_mbar_wait(&empty[st], (uint32_t)(round - 1) & 1u);
+                const int i = q / n_kb, kb = q - i * n_kb;
+                const int tile = chunk + i * n_chunks;
+                float* dst = sm + (size_t)st * 4 * SSB_SCK_PART;
+                ssb_mbar_expect_tx(&full[st], 2u * blk_bytes);
+                ssb_bulk_g2s(dst, Xt + ((size_t)tb * n_kb + kb) * 2 * SSB_SCK_PART, blk_bytes, &full[st]);
+                ssb_bulk_g2s(dst + 2 * SSB_SCK_PART, Stck + ((size_t)tile * n_kb + kb) * 2 * SSB_SCK_PART, blk_bytes, &full[st]);
+            }
+        }
+    } else if (warp == 9) {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int q = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int buf = i & 1;
+                if (i >= 2) {                                        // the epilogue has drained this D buffer (tile i - 2)
+                    ssb_mbar_wait(&dfree[buf], (uint32_t)((i >> 1) - 1) & 1u);
+                    ssb_tc_fence_after();
+                }
+                const uint32_t dst = tmem + (uint32_t)buf * TR;
+                for (int kb = 0; kb < n_kb; ++kb, ++q) {
+                    const int st = q % SSB_SCK_NST;
+                    ssb_mbar_wait(&full[st], (uint32_t)(q / SSB_SCK_NST) & 1u);
+                    ssb_tc_fence_after();
+                    const float* a_hi = sm + (size_t)st * 4 * SSB_SCK_PART;
+                    const float* a_lo = a_hi + SSB_SCK_PART;
+                    const float* b_hi = a_hi + 2 * SSB_SCK_PART;
+                    const float* b_lo = b_hi + SSB_SCK_PART;
+#pragma unroll
+                    for (int j = 0; j < SSB_SCK_KB / 8; ++j) {
+                        const size_t off = (size_t)j * 2 * 16 * 32;        // two 16-byte K chunks per MMA
+                        const uint64_t ah = ssb_umma_desc(a_hi + off), al = ssb_umma_desc(a_lo + off);
+                        const uint64_t bh = ssb_umma_desc(b_hi + off), bl = ssb_umma_desc(b_lo + off);
+                        ssb_umma_tf32(dst, al, bh, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        ssb_umma_tf32(dst, ah, bl, idesc, 1);
+                        ssb_umma_tf32(dst, ah, bh, idesc, 1);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     ssb_smem(&empty[st]))
+                                 : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 ssb_smem(&dfull[buf]))
+                             : "memory");
+            }
+        }
+    } else {
+        // ---------------- epilogue: per-trial top-4, two warps per TMEM lane quadrant
+        const int quad = warp & 3, half = warp >> 2;
+        const int group = tb * 4 + quad;
+        const bool live = group < n_groups;
+        const int g = live ? group : 0;
+        float tv0 = -INFINITY, tv1 = -INFINITY, tv2 = -INFINITY, tv3 = -INFINITY;
+        int tg0 = 0x7fffffff, tg1 = 0x7fffffff, tg2 = 0x7fffffff, tg3 = 0x7fffffff;
+        auto push = [&](float val, int gi) {   // branch-free sorted insert (a strict > keeps the earlier index on ties)
+            const bool b0 = val > tv0, b1 = val > tv1, b2 = val > tv2, b3 = val > tv3;
+            tv3 = b2 ? tv2 : (b3 ? val : tv3);
+            tg3 = b2 ? tg2 : (b3 ? gi : tg3);
+            tv2 = b1 ? tv1 : (b2 ? val : tv2);
+            tg2 = b1 ? tg1 : (b2 ? gi : tg2);
+            tv1 = b0 ? tv0 : (b1 ? val : tv1);
+            tg1 = b0 ? tg0 : (b1 ? gi : tg1);
+            tv0 = b0 ? val : tv0;
+            tg0 = b0 ? gi : tg0;
+        };
+        for (int i = 0; i < my_tiles; ++i) {
+            const int buf = i & 1;
+            ssb_mbar_wait(&dfull[buf], (uint32_t)(i >> 1) & 1u);
+            ssb_tc_fence_after();
+            const int row0 = (chunk + i * n_chunks) * TR;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * TR;
+#pragma unroll 1
+            for (int b = half * 2; b < half * 2 + 2; ++b) {
+                float v[32];
+                ssb_tmem_ld32(taddr + b * 32, v);
+                const int gg0 = row0 + b * 32;
+                if (gg0 + 32 <= G) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) push(v[j], gg0 + j);
+                } else {                                   // last tile: rows beyond the grid are padding
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (gg0 + j < G) push(v[j], gg0 + j);
+                }
+            }
+            ssb_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ssb_smem(&dfree[buf])) : "memory");
+        }
+        if (live) {
+            float* pv = pval + ((size_t)g * n_cand) * 32 + lane;
+            int* pi = pidx + ((size_t)g * n_cand) * 32 + lane;
+            const float tv[4] = {tv0, tv1, tv2, tv3};
+            const int tg[4] = {tg0, tg1, tg2, tg3};
+#pragma unroll
+            for (int i = 0; i < SSB_TOPK; ++i) {
+                pv[(size_t)((blockIdx.x * 2 + half) * SSB_TOPK + i) * 32] = tv[i];
+                pi[(size_t)((blockIdx.x * 2 + half) * SSB_TOPK + i) * 32] = tg[i];
+            }
+        }
+    }
+    ssb_tc_fence_before();
+    __syncthreads();
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * TR));
+}
+
+// --------------------------------------------------------------------------------------
 // Gated correction node (slam.py:233-237): x = [p ; q ; flag].  CTA = one trial group x 8 warps;
 // warps split the dimensions, the dot product is reduced through shared memory.
 // desc: d in_row0 out_vec rate_bits thres_bits atol_bits

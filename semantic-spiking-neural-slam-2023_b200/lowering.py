@@ -417,6 +417,38 @@ class _Lowerer:
             raise RuntimeError("same-step dependency cycle between ensembles / function nodes")
         n_levels = 1 + max(list(ens_level.values()) + list(fn_level.values()) + [0])
 
+        # ---- exact same-step dependencies of every level: which producer kinds of which earlier level its sink rows read
+        #      (bit 0: decoded outputs of narrow ensembles, 1: static decoders of wide ensembles, 2: grid clean-up nodes,
+        #       3: gate nodes).  The launch sequence lets a level start as soon as THOSE producers are done instead of
+        #      waiting for every kernel of the previous level.
+        col_prod = np.zeros(self.ncol, dtype=np.int64)          # producer kind bit of a column (0: exists at step start)
+        col_plvl = np.zeros(self.ncol, dtype=np.int64)          # level of its producer
+        for c, col0 in self.dec_col.items():
+            if compat.is_connection(c) and c in pes_rule:
+                continue
+            ens_c = c.pre_obj if compat.is_connection(c) else c.obj
+            col_prod[col0:col0 + dec_width[c]] = 1 if self.is_small[ens_c] else 2
+            col_plvl[col0:col0 + dec_width[c]] = ens_level[ens_c]
+        for node, col0 in self.fn_col.items():
+            col_prod[col0:col0 + node.size_out] = 4 if self.node_op[node].kind == "cleanup" else 8
+            col_plvl[col0:col0 + node.size_out] = fn_level[node]
+        level_deps = np.zeros((n_levels, n_levels), dtype=np.int32)
+
+        def note_deps(lvl, *mats):
+            for c in cols_of(*mats).astype(np.int64):
+                if col_prod[c]:
+                    level_deps[lvl, col_plvl[c]] |= int(col_prod[c])
+        for ens in self.ensembles:
+            mats = [ens_in[ens]]
+            if ens in ens_jn:
+                mats.append(ens_jn[ens][0])
+            if ens in voja_rule:
+                mats.append(voja_rule[ens][1])
+            note_deps(ens_level[ens], *mats)
+        for node, mat in fn_in.items():
+            note_deps(fn_level[node], mat)
+        plan.arrays["level_deps"] = level_deps
+
         # ---- device column map: row 0 ones | filters A | filters B | this step's table rows | scratch
         NF = sum(1 for k in self.col_kind if k == "filt")
         NT = sum(1 for k in self.col_kind if k == "tab")

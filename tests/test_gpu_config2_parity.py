@@ -134,7 +134,10 @@ def _device_spike_counts(sim, n_steps, bounds):
     return out
 
 
-SPIKE_HORIZON = {"small": 150, "full": 40}      # steps over which every per-ensemble spike count is asserted equal
+# Steps over which every per-ensemble spike count is asserted equal.  Measured on B200 (round 2): the first differing
+# step was 106 (reduced size, trial 0) and 101 / none within 120 (full size, trials 1 / 0); one neuron of ~40 000 crossing
+# the threshold a step early is all it takes, after which the totals still agree to 1e-4 (20 of 303 066 spikes).
+SPIKE_HORIZON = {"small": 64, "full": 64}
 
 
 @pytest.mark.parametrize("size", ["small", "full"])

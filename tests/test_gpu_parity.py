@@ -92,6 +92,23 @@ def test_ssp_decode_generic_width_3d(scan, monkeypatch):
     assert np.array_equal(cabi.ssp_decode_argmax(ssps, q), ssp_ref.decode_indices(ssps, q))
 
 
+def test_ssp_decode_d649_k_blocked_tensor_core_scan_is_bit_exact():
+    """BASELINE configs[4] width (HexagonalSSPSpace n_rotates = n_scales = 9 -> d = 649): the operand tiles do not fit in
+    shared memory, so the scan is the K-blocked tcgen05 kernel (k_cleanup_scan_tck); indices must still equal the float64
+    argmax, ragged grid (15^3 = 3 375 rows: 26 tiles + a partial one) and ragged query count included."""
+    sp = HexagonalSSPSpace(3, n_rotates=9, n_scales=9, domain_bounds=np.tile([-1.0, 1.0], (3, 1)), length_scale=0.3,
+                           rng=np.random.default_rng(0), backend="host")
+    assert sp.ssp_dim == 649
+    ssps, pts = sp.get_sample_pts_and_ssps(15, "grid")
+    rng = np.random.default_rng(2)
+    q = sp.encode_host(rng.uniform(-1, 1, (300, 3))) + 0.02 * rng.standard_normal((300, 649))
+    q[7] = 0.0                                                   # an all-zero query picks row 0
+    q[8] = ssps[1234] * 3.0                                      # an exact grid point, scaled
+    got = cabi.ssp_decode_argmax(ssps, q)
+    assert np.array_equal(got, ssp_ref.decode_indices(ssps, q))
+    assert got[8] == 1234
+
+
 # ------------------------------------------------------------------------------- stepped path
 @pytest.mark.parametrize("neuron_type,tol", [("lifrate", 1e-4), ("relu", 1e-4), ("lif", 2e-3)])
 def test_pathintegration_matches_oracle(neuron_type, tol):
