@@ -173,6 +173,8 @@ struct ssb_sim {
     long long syn_step0 = 0;
     int syn_steps = 0;
     SsbPesDefer pes_h = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};   // deferred PES history (K = 0: off)
+    bool pes_fused = false;                 // the sparse decode runs inside k_wide_voja (every PES pre-ensemble is a Voja ensemble)
+    std::vector<int> pes_of_big;            // wide-ensemble descriptor -> PES descriptor it feeds, or -1
     int* d_pes_hdesc = nullptr;
     size_t pes_pad_smem = 0, voja_pad_smem = 0;   // experiment knobs: extra dynamic smem lowers residency
     std::map<int, int> wide_chunk_cache;   // launch geometry of the wide-ensemble kernels, decided once
@@ -506,6 +508,16 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
         k_wide_static<DP><<<grid, 128, smem_of(chunk), st>>>(s->ctx, s->d_big, items, chunk, i_rel);
     } else {
         int nwarps = 4, nb = SSB_VOJA_NB;
+        SsbPesFuse pf;
+        memset(&pf, 0, sizeof(pf));
+        pf.desc = s->d_pes;
+        pf.hdesc = s->d_pes_hdesc;
+        pf.h = s->pes_h;
+        bool fuse = false;
+        for (int k = 0; k < 15; ++k) {
+            pf.item[k] = (s->pes_fused && k < items.n) ? s->pes_of_big[items.idx[k]] : -1;
+            fuse = fuse || pf.item[k] >= 0;
+        }
         auto smem_of = [&](int nw) {
             return (size_t)(max_dpad * 32 + max_jn * 32 + nw * nb * max_dims * 32) * sizeof(float) + s->voja_pad_smem;
         };
@@ -518,7 +530,8 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
         int chunk = it == s->wide_chunk_cache.end() ? 0 : it->second;
         if (!chunk) {
             int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wide_voja<DP>, 32 * nwarps, smem_of(nwarps));
+            if (fuse) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wide_voja<DP, true>, 32 * nwarps, smem_of(nwarps));
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wide_voja<DP, false>, 32 * nwarps, smem_of(nwarps));
             const int slots = 148 * std::max(1, occ);
             const int per_unit = std::max(1, slots / std::max(1, units));
             chunk = (max_n + per_unit - 1) / per_unit;
@@ -527,7 +540,8 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
         }
         if (dry) return;
         dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
-        k_wide_voja<DP><<<grid, 32 * nwarps, smem_of(nwarps), st>>>(s->ctx, s->d_big, items, chunk, i_rel, nb);
+        if (fuse) k_wide_voja<DP, true><<<grid, 32 * nwarps, smem_of(nwarps), st>>>(s->ctx, s->d_big, items, chunk, i_rel, nb, pf);
+        else k_wide_voja<DP, false><<<grid, 32 * nwarps, smem_of(nwarps), st>>>(s->ctx, s->d_big, items, chunk, i_rel, nb, pf);
     }
 }
 
@@ -547,9 +561,12 @@ void wide_smem_optin() {
     cudaFuncSetAttribute(k_wide_static<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_wide_voja<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_wide_voja<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_wide_voja<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_voja<56, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_voja<100, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_voja<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_voja<56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_voja<100, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_wide_voja<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
 }
 
 cudaEvent_t dep_event(ssb_sim* s) {
@@ -582,7 +599,8 @@ int setup_pes_defer(ssb_sim* s) {
         hd.insert(hd.end(), {rows_e, rows_f, rows_p, i});
         rows_e += K * d[1];
         rows_f += K * d[0];
-        rows_p += d[10] * (d[1] + K);
+        // split-K partials: the PES kernel's own chunks, or (fused decode) the chunks of the Voja ensemble launch
+        rows_p += std::max(d[10], std::min(d[0], 592 / std::max(1, s->n_groups) + 1)) * (d[1] + K);
     }
     SsbPesDefer& h = s->pes_h;
     h.rows_e = rows_e;
@@ -633,7 +651,9 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
         pes_grid(s, &grid, &max_chunks);
         for (int i = 0; i < s->n_pes; ++i) max_rows = std::max(max_rows, s->h_pes[i * 13] + s->h_pes[i * 13 + 1]);
         dim3 dgrid(grid.x + 1, grid.y, grid.z);          // + one tile of history rows per (group, chunk)
-        if (s->pes_h.K == 4) k_pes_defer<4><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel);
+        if (s->pes_fused) {
+            // the sparse decode already ran inside the Voja ensemble kernel of this step
+        } else if (s->pes_h.K == 4) k_pes_defer<4><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel);
         else k_pes_defer<8><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel);
         k_pes_hist<<<dim3((max_rows + 3) / 4, s->n_groups, s->n_pes), 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, i_rel);
         // the host mirrors the step counter, so the fold is launched only after the last slot of a window
@@ -1282,6 +1302,33 @@ int ssb_finalize(ssb_sim* s) {
         if (lvl == s->pes_level)
             for (int i = 0; i < s->n_pes; ++i)
                 if (!act_is_voja(s->h_pes[i * 13 + 4])) s->pes_needs_static = true;
+    }
+    {   // fused deferred-PES decode: every PES descriptor must be fed by a Voja ensemble of the PES level, and one decoder
+        // pass (56 rows + K history rows per warp) must fit in the warp's encoder ring (nb * dims rows; nb >= 1)
+        const int n_big = (int)(s->h_big.size() / 16);
+        s->pes_of_big.assign(n_big + 1, -1);
+        const char* e = getenv("SSB_PES_FUSE");
+        bool ok = s->pes_h.K > 0 && s->n_pes > 0 && s->pes_level >= 0 && !(e && e[0] == '0');
+        for (int i = 0; ok && i < s->n_pes; ++i) {
+            const int* pd = &s->h_pes[i * 13];
+            const int* st = &s->h_stages[s->pes_level * 12];
+            int found = -1;
+            for (int b = st[2]; b < st[2] + st[3]; ++b) {
+                const int* d = &s->h_big[b * 16];
+                if ((d[9] & 1) && d[4] == pd[4] && d[0] == pd[0]) found = b;
+            }
+            if (found < 0) {
+                ok = false;
+                break;
+            }
+            const int* d = &s->h_big[found * 16];
+            int nb = SSB_VOJA_NB;                         // as launch_wide_class sizes the ring of a warp
+            while (nb > 1 && (size_t)(d[2] * 32 + d[11] * 32 + nb * d[1] * 32) * sizeof(float) > 200 * 1024) --nb;
+            if (std::min(pd[1], 56) + 8 > nb * d[1]) ok = false;
+            else s->pes_of_big[found] = i;
+        }
+        s->pes_fused = ok;
+        if (!ok) s->pes_of_big.assign(n_big + 1, -1);
     }
     for (size_t i = 0; i + 8 < s->h_small.size(); i += 9)
         if (s->h_small[i + 8] > SSB_SM_WMAX || (s->h_small[i + 8] & 3))

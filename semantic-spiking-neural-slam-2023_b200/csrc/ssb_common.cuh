@@ -372,3 +372,22 @@ __device__ __forceinline__ void ssb_tmem_ld16(uint32_t taddr, float (&v)[16]) {
 __device__ __forceinline__ void ssb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ssb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// --------------------------------------------------------------------------------------
+// Deferred-PES history arenas (see ssb_pes.cuh) and the hand-over that lets the Voja ensemble kernel decode through the
+// PES-learned decoders of its own neurons (k_wide_voja<.., true>): item[k] = PES descriptor fed by the k-th ensemble of the
+// launch, or -1.
+#define SSB_PES_KMAX 16
+struct SsbPesDefer {
+    float* hist_e;            // [G][rows_e][32]
+    float* hist_f;            // [G][rows_f][32]
+    float* part;              // [G][rows_p][32]
+    int* counters;
+    int rows_e, rows_f, rows_p, K;
+};
+
+struct SsbPesFuse {
+    const int* desc;          // PES descriptors (13 ints each)
+    const int* hdesc;         // e_row0 f_row0 part_row0 counter0 per PES descriptor
+    SsbPesDefer h;
+    int item[15];
+};

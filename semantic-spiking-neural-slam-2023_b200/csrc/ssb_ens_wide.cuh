@@ -334,9 +334,17 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
 // delta is row-sparse).  SimVoja: delta = alpha*L*(scale*outer(post, x) - post[:,None]*E), visible
 // to the next step.
 #define SSB_VOJA_NB 3         // encoder tiles in flight per warp (fewer when a tile is too large: very wide ensembles)
-template <int DP>
+// PES = true: the ensemble's activities feed a PES-learned connection whose decode is fused into this kernel (deferred-PES
+// form, see ssb_pes.cuh): after its neuron range a warp walks the neurons where some trial spiked and accumulates
+//   out[trial][j] += D_base[j][i][trial] * a[i][trial]      and      dots[trial][q] += f_q[i][trial] * a[i][trial]
+// in registers — lane = trial, so no cross-lane reduction, and a lane loads only where ITS trial spiked (32-byte sectors).
+// The four warps are added through shared memory, the CTA's partial goes to the PES partial arena, and the last CTA of the
+// (ensemble, trial group) adds the chunks in order and applies the K history terms.  This replaces k_pes_defer (a second
+// pass over flags, activities and decoder rows) on the longest dependency chain of the step.
+#define SSB_PESF_NJ 56        // decoder output rows accumulated per pass
+template <int DP, bool PES>
 __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restrict__ desc, SsbItemList items, int chunk,
-                                                    int i_rel, int nb) {
+                                                    int i_rel, int nb, SsbPesFuse pf) {
     extern __shared__ __align__(128) float sm[];
     __shared__ unsigned long long wbar[4][SSB_VOJA_NB];
     const int* d = desc + items.idx[blockIdx.z] * 16;
@@ -470,5 +478,125 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
         }
     }
     if (lane == 0) ssb_bulk_wait0();
+    if (!PES) return;
+    const int pit = pf.item[blockIdx.z];
+    if (pit < 0) return;
+    // ------------------------------------------------------------------ fused deferred-PES decode
+    __syncwarp();                                       // the warp's ring buffers are drained: reuse them for the reduction
+    __shared__ int pes_last;
+    const int* pd = pf.desc + pit * 13;
+    const int* hd = pf.hdesc + pit * 4;
+    const int size_out = pd[1], d_off = pd[2], a_off = pd[3], err_vec = pd[5], out_vec = pd[6];
+    const int K = pf.h.K;
+    const SsbStep stp = ssb_step(c, i_rel);
+    const int slot = (int)(stp.step % K);      // this step's term is not in the history yet: it is read at its source
+    const float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + (size_t)d_off * 32;
+    const float* __restrict__ hf = ssb_grp(pf.h.hist_f, pf.h.rows_f, g, lane) + (size_t)hd[1] * 32;
+    const float* __restrict__ fcur = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)(1 - stp.odd) * c.n_afilt + a_off) * 32;
+    const int prow = size_out + K;
+    const int n_chunks = (n + chunk - 1) / chunk;
+    float* pg = ssb_grp(pf.h.part, pf.h.rows_p, g, lane) + (size_t)hd[2] * 32;
+    float* red = ebuf;                                  // [SSB_PESF_NJ + 8][32] of this warp
+    for (int j0 = 0; j0 < size_out; j0 += SSB_PESF_NJ) {
+        const bool with_dots = j0 == 0;
+        float acc[SSB_PESF_NJ], dots[8];
+#pragma unroll
+        for (int j = 0; j < SSB_PESF_NJ; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dots[q] = 0.f;
+        for (int i = i_lo; i < i_hi; ++i) {
+            const float a = ag[(size_t)i * 32];         // written by this very thread above
+            const bool on = a != 0.f;
+            if (!__any_sync(0xffffffffu, on)) continue;
+            const size_t ni = (size_t)(n0 + i);
+            float w[SSB_PESF_NJ], f[8];
+#pragma unroll
+            for (int j = 0; j < SSB_PESF_NJ; ++j)
+                w[j] = (on && j0 + j < size_out) ? __ldcs(dp + ((size_t)(j0 + j) * n + ni) * 32) : 0.f;
+            if (with_dots) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    f[q] = (on && q < K) ? ((q == slot) ? fcur[ni * 32] : hf[((size_t)q * n + ni) * 32]) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dots[q] = fmaf(f[q], a, dots[q]);
+            }
+#pragma unroll
+            for (int j = 0; j < SSB_PESF_NJ; ++j) acc[j] = fmaf(w[j], a, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < SSB_PESF_NJ; ++j) red[j * 32 + lane] = acc[j];
+        if (with_dots) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) red[(SSB_PESF_NJ + q) * 32 + lane] = dots[q];
+        }
+        __syncthreads();
+        // CTA partial in warp order, parked in the partial arena [chunk][size_out + K]
+        const size_t wstride = (size_t)nb * dims * 32;  // distance between the warps' buffers
+        const float* red0 = us + (size_t)jn_m * 32;
+        const int nrow = SSB_PESF_NJ + (with_dots ? 8 : 0);
+        for (int r = warp; r < nrow; r += nwarps) {
+            const bool is_dot = r >= SSB_PESF_NJ;
+            const int row = is_dot ? size_out + (r - SSB_PESF_NJ) : j0 + r;
+            if (is_dot ? (r - SSB_PESF_NJ < K) : (row < size_out)) {
+                float t = 0.f;
+                for (int wq = 0; wq < nwarps; ++wq) t += red0[wq * wstride + r * 32 + lane];
+                pg[(size_t)(blockIdx.x * prow + row) * 32] = t;
+            }
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* cnt_p = pf.h.counters + hd[3] * c.G + g;
+        const int old = atomicAdd(cnt_p, 1);
+        const int last = old == n_chunks - 1;
+        if (last) *cnt_p = 0;
+        pes_last = last;
+    }
+    __syncthreads();
+    if (!pes_last) return;
+    __threadfence();
+    // the last CTA of this (ensemble, group): history dot products, then every output row (chunks added in order)
+    float dsum[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dsum[q] = 0.f;
+    for (int ck = 0; ck < n_chunks; ++ck) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = q < K ? __ldcg(pg + (size_t)(ck * prow + size_out + q) * 32) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dsum[q] += v[q];
+    }
+    const float* __restrict__ he = ssb_grp(pf.h.hist_e, pf.h.rows_e, g, lane) + (size_t)hd[0] * 32;
+    float* vgw = ssb_grp(c.vec, c.nv, g, lane);
+    const float alpha = stp.step > 0 ? __int_as_float(pd[7]) : 0.f;
+    for (int jb = warp * 8; jb < size_out; jb += nwarps * 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = 0.f;
+        for (int ck = 0; ck < n_chunks; ++ck) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (jb + u < size_out) ? __ldcg(pg + (size_t)(ck * prow + jb + u) * 32) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] += v[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (jb + u < size_out) {
+                float r = t[u];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (q < K) {
+                        const float e = (q == slot) ? alpha * vgw[(size_t)(err_vec + jb + u) * 32]
+                                                    : he[(size_t)(q * size_out + jb + u) * 32];
+                        r = fmaf(e, dsum[q], r);
+                    }
+                }
+                vgw[(size_t)(out_vec + jb + u) * 32] = r;
+            }
+        }
+    }
 }
 

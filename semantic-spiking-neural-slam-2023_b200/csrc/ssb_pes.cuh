@@ -128,14 +128,6 @@ __global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ d
 //   k_pes_fold   D_base += sum_s ae_s (x) f_s (runs when slot == K - 1, or when the host asks), then k_pes_clear zeroes
 //                the ae rows, so an empty history always contributes exactly 0
 // desc as k_pes; hdesc per decoder: e_row0 f_row0 part_row0 counter0 (rows of the hist_e / hist_f / pes_part arenas)
-#define SSB_PES_KMAX 16
-struct SsbPesDefer {
-    float* hist_e;            // [G][rows_e][32]
-    float* hist_f;            // [G][rows_f][32]
-    float* part;              // [G][rows_p][32]
-    int* counters;
-    int rows_e, rows_f, rows_p, K;
-};
 
 __global__ void __launch_bounds__(128) k_pes_hist(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
                                                     const int* __restrict__ hdesc, int i_rel) {
