@@ -163,6 +163,7 @@ struct ssb_sim {
     float* d_dec_wt = nullptr;              // static decoders pre-tiled for k_decode_tc (3xTF32 hi | lo)
     int* d_dec_wt_off = nullptr;
     int dec_tc_n = 64;                      // operand tile width of k_decode_tc (64 or 128 output columns)
+    int dec_tc_nt = 1;                      // column tiles per decoder
     std::vector<char> dec_tc_level;         // per level: every decoder of the level can use the tensor-core kernel
     // on-device input synthesis (ssb_synth_setup): replaces k_begin and the input tables
     bool synth_on = false;
@@ -557,7 +558,6 @@ void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int i
 void wide_smem_optin() {
     const int lim = 200 * 1024;
     cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_pes, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_wide_static<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -590,18 +590,28 @@ void stream_dep(ssb_sim* s, cudaStream_t from, cudaStream_t to) {
 // SSB_PES_DEFER=4|8 sets the window (default 8).
 int setup_pes_defer(ssb_sim* s) {
     int K = 8;
-    if (const char* e = getenv("SSB_PES_DEFER")) K = atoi(e);
-    if (s->n_pes == 0 || (K != 4 && K != 8)) return 0;
+    if (const char* e = getenv("SSB_PES_DEFER")) K = atoi(e) == 4 ? 4 : 8;
+    if (s->n_pes == 0) return 0;
+    // neuron chunks of the sparse decode: enough CTAs (chunks x groups x column tiles) for ~3 resident CTAs per SM
+    int tiles_total = 0;
+    for (int i = 0; i < s->n_pes; ++i) tiles_total += (ssb_pes_jp(s->h_pes[i * 13 + 1]) + SSB_PES_JT - 1) / SSB_PES_JT;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pes_defer<8>, 128, 0);
+    int chunks = 148 * std::max(1, occ) / std::max(1, tiles_total * s->n_groups);     // one wave of resident CTAs
+    chunks = std::max(1, std::min(chunks, 32));
+    if (const char* e = getenv("SSB_PES_CHUNKS")) chunks = std::max(1, std::min(atoi(e), 64));
     std::vector<int> hd;
     int rows_e = 0, rows_f = 0, rows_p = 0;
     for (int i = 0; i < s->n_pes; ++i) {
-        const int* d = &s->h_pes[i * 13];
+        int* d = &s->h_pes[i * 13];
+        d[10] = std::max(1, std::min(chunks, d[0] / 16));
         hd.insert(hd.end(), {rows_e, rows_f, rows_p, i});
         rows_e += K * d[1];
         rows_f += K * d[0];
-        // split-K partials: the PES kernel's own chunks, or (fused decode) the chunks of the Voja ensemble launch
+        // split-K partials: the decode kernel's own chunks, or (fused decode) the chunks of the Voja ensemble launch
         rows_p += std::max(d[10], std::min(d[0], 592 / std::max(1, s->n_groups) + 1)) * (d[1] + K);
     }
+    SSB_CUDA(cudaMemcpy(s->d_pes, s->h_pes.data(), s->h_pes.size() * sizeof(int), cudaMemcpyHostToDevice));
     SsbPesDefer& h = s->pes_h;
     h.rows_e = rows_e;
     h.rows_f = rows_f;
@@ -613,25 +623,20 @@ int setup_pes_defer(ssb_sim* s) {
     SSB_CUDA(cudaMalloc((void**)&s->d_pes_hdesc, hd.size() * sizeof(int)));
     SSB_CUDA(cudaMemcpy(s->d_pes_hdesc, hd.data(), hd.size() * sizeof(int), cudaMemcpyHostToDevice));
     h.K = K;
+    SSB_CUDA(cudaFuncSetAttribute(k_pes_fold<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SSB_PES_FT * 32 * (int)sizeof(float)));
+    SSB_CUDA(cudaFuncSetAttribute(k_pes_fold<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * SSB_PES_FT * 32 * (int)sizeof(float)));
     return 0;
 }
 
-void pes_grid(ssb_sim* s, dim3* grid, int* max_chunks) {
-    int max_out = 0;
-    *max_chunks = 1;
-    for (int i = 0; i < s->n_pes; ++i) {
-        max_out = std::max(max_out, s->h_pes[i * 13 + 1]);
-        *max_chunks = std::max(*max_chunks, s->h_pes[i * 13 + 10]);
-    }
-    *grid = dim3((max_out + 7) / 8, s->n_groups, s->n_pes * *max_chunks);
-}
-
 void launch_pes_fold(ssb_sim* s, cudaStream_t st, int i_rel, int force) {
-    dim3 grid;
-    int max_chunks;
-    pes_grid(s, &grid, &max_chunks);
-    if (s->pes_h.K == 4) k_pes_fold<4><<<grid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel, force);
-    else k_pes_fold<8><<<grid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel, force);
+    // neuron chunks of the streaming fold: ~4 CTAs per SM
+    int max_n = 0;
+    for (int i = 0; i < s->n_pes; ++i) max_n = std::max(max_n, s->h_pes[i * 13]);
+    const int chunks = std::max(1, std::min((148 * 4 + s->n_groups * s->n_pes - 1) / std::max(1, s->n_groups * s->n_pes), (max_n + 7) / 8));
+    dim3 grid(chunks, s->n_groups, s->n_pes);
+    const size_t smem = (size_t)s->pes_h.K * SSB_PES_FT * 32 * sizeof(float);
+    if (s->pes_h.K == 4) k_pes_fold<4><<<grid, 128, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks, i_rel, force);
+    else k_pes_fold<8><<<grid, 128, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks, i_rel, force);
     k_pes_clear<<<dim3((s->pes_h.rows_e + 3) / 4, s->n_groups), 128, 0, st>>>(s->ctx, s->pes_h, i_rel, force);
 }
 
@@ -645,35 +650,30 @@ int pes_flush(ssb_sim* s) {
 
 void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
     LaunchTimer t(s, K_PES, st);
-    if (s->pes_h.K > 0) {
-        dim3 grid;
-        int max_chunks, max_rows = 0;
-        pes_grid(s, &grid, &max_chunks);
-        for (int i = 0; i < s->n_pes; ++i) max_rows = std::max(max_rows, s->h_pes[i * 13] + s->h_pes[i * 13 + 1]);
-        dim3 dgrid(grid.x + 1, grid.y, grid.z);          // + one tile of history rows per (group, chunk)
-        if (s->pes_fused) {
-            // the sparse decode already ran inside the Voja ensemble kernel of this step
-        } else if (s->pes_h.K == 4) k_pes_defer<4><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel);
-        else k_pes_defer<8><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_chunks, i_rel);
-        k_pes_hist<<<dim3((max_rows + 3) / 4, s->n_groups, s->n_pes), 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, i_rel);
-        // the host mirrors the step counter, so the fold is launched only after the last slot of a window
-        // (a captured graph bakes this in; it is replayed only from steps with the same phase, see ssb_run_steps)
-        int extra = 1;                                   // k_pes_hist
-        if ((int)((s->steps_done + i_rel) % s->pes_h.K) == s->pes_h.K - 1) {
-            launch_pes_fold(s, st, i_rel, 1);
-            extra += 2;                                  // k_pes_fold + k_pes_clear
-        }
-        s->kind_launches[K_EXTRA] += extra;
-        s->total_launches += extra;
-        return;
-    }
-    int max_out = 0, max_chunks = 1;
+    int max_chunks = 1, max_rows = 0, max_jt = 1;
     for (int i = 0; i < s->n_pes; ++i) {
-        max_out = std::max(max_out, s->h_pes[i * 13 + 1]);
-        max_chunks = std::max(max_chunks, s->h_pes[i * 13 + 10]);
+        const int* d = &s->h_pes[i * 13];
+        max_chunks = std::max(max_chunks, d[10]);
+        max_rows = std::max(max_rows, d[0] + d[1]);
+        max_jt = std::max(max_jt, (ssb_pes_jp(d[1]) + SSB_PES_JT - 1) / SSB_PES_JT);
     }
-    dim3 grid((max_out + 7) / 8, s->n_groups, s->n_pes * max_chunks);
-    k_pes<<<grid, 128, s->pes_pad_smem, st>>>(s->ctx, s->d_pes, max_chunks, i_rel);
+    if (s->pes_fused) {
+        // the sparse decode already ran inside the Voja ensemble kernel of this step
+    } else {
+        dim3 dgrid(max_chunks, s->n_groups, s->n_pes * max_jt);
+        if (s->pes_h.K == 4) k_pes_defer<4><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
+        else k_pes_defer<8><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
+    }
+    k_pes_hist<<<dim3((max_rows + 3) / 4, s->n_groups, s->n_pes), 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, i_rel);
+    // the host mirrors the step counter, so the fold is launched only after the last slot of a window
+    // (a captured graph bakes this in; it is replayed only from steps with the same phase, see ssb_run_steps)
+    int extra = 1;                                   // k_pes_hist
+    if ((int)((s->steps_done + i_rel) % s->pes_h.K) == s->pes_h.K - 1) {
+        launch_pes_fold(s, st, i_rel, 1);
+        extra += 2;                                  // k_pes_fold + k_pes_clear
+    }
+    s->kind_launches[K_EXTRA] += extra;
+    s->total_launches += extra;
 }
 
 // SSB_ENCODE=tc selects the tensor-core wide-ensemble kernel.  Measured on B200 (BASELINE configs[1], 1024 trials):
@@ -777,9 +777,10 @@ int build_decode_tiles(ssb_sim* s) {
     if (n_dec == 0 || !decode_tc_allowed()) return 0;
     int max_jpad = 0;
     for (int i = 0; i < n_dec; ++i) max_jpad = std::max(max_jpad, s->h_dec[i * 9 + 2]);
-    if (max_jpad > 128) return 0;
     const int N = max_jpad <= 64 ? 64 : 128, KS = max_jpad <= 64 ? 64 : 32;
     s->dec_tc_n = N;
+    s->dec_tc_nt = (max_jpad + N - 1) / N;              // column tiles per decoder (1 up to 128 columns; 6 for d = 649)
+    const int n_nt = s->dec_tc_nt;
     const float* hW = reinterpret_cast<const float*>(s->arrays["weights"].bytes.data());
     std::vector<float> wt;
     std::vector<int> off(n_dec + 8, -1);
@@ -789,14 +790,15 @@ int build_decode_tiles(ssb_sim* s) {
         const int n = d[0], jpad = d[2], w_off = d[4];
         const int n_stages = (n + KS - 1) / KS;
         off[i] = (int)wt.size();
-        wt.resize(wt.size() + (size_t)n_stages * 2 * part, 0.f);
+        wt.resize(wt.size() + (size_t)n_nt * n_stages * 2 * part, 0.f);
         float* base = &wt[off[i]];
         for (int k = 0; k < n; ++k) {
             const int st = k / KS, kk = k % KS;
-            float* hi = base + (size_t)st * 2 * part;
-            float* lo = hi + part;
-            for (int j = 0; j < jpad; ++j) {
-                const float x = hW[(size_t)w_off + (size_t)k * jpad + j];
+            for (int jg = 0; jg < jpad; ++jg) {
+                const int j = jg % N;
+                float* hi = base + ((size_t)(jg / N) * n_stages + st) * 2 * part;
+                float* lo = hi + part;
+                const float x = hW[(size_t)w_off + (size_t)k * jpad + jg];
                 const float h = ssb_tf32_round(x);
                 const size_t o = ((size_t)(kk / 4) * (N / 8) + j / 8) * 32 + (j % 8) * 4 + kk % 4;
                 hi[o] = h;
@@ -1102,12 +1104,13 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
                 smem = std::max(smem, (per * d[2] + 4 * per * 32) * sizeof(float));
             }
             dim3 grid(max_chunks, (G + 3) / 4, st[5]);
+            if (s->dec_tc_level[lvl]) grid.z = st[5] * s->dec_tc_nt;
             if (s->dec_tc_level[lvl] && s->dec_tc_n == 64)
                 k_decode_tc<64, 64><<<grid, 256, (size_t)(4 * 128 * 64 + 4 * 64 * 64) * sizeof(float), D>>>(
-                    c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off);
+                    c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off, s->dec_tc_nt);
             else if (s->dec_tc_level[lvl])
                 k_decode_tc<128, 32><<<grid, 256, (size_t)(4 * 128 * 32 + 4 * 128 * 32) * sizeof(float), D>>>(
-                    c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off);
+                    c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off, s->dec_tc_nt);
             else
                 k_decode<<<grid, 128, smem, D>>>(c, s->d_dec, st[4]);
             ev_dec[lvl] = mark(D);
@@ -1308,7 +1311,9 @@ int ssb_finalize(ssb_sim* s) {
         const int n_big = (int)(s->h_big.size() / 16);
         s->pes_of_big.assign(n_big + 1, -1);
         const char* e = getenv("SSB_PES_FUSE");
-        bool ok = s->pes_h.K > 0 && s->n_pes > 0 && s->pes_level >= 0 && !(e && e[0] == '0');
+        // opt-in (SSB_PES_FUSE=1): measured on B200 the fused post-pass lengthens the bandwidth-bound Voja kernel by more
+        // than the separate sparse-decode kernel costs (too little memory-level parallelism on 2 CTAs per SM)
+        bool ok = s->pes_h.K > 0 && s->n_pes > 0 && s->pes_level >= 0 && (e && e[0] == '1');
         for (int i = 0; ok && i < s->n_pes; ++i) {
             const int* pd = &s->h_pes[i * 13];
             const int* st = &s->h_stages[s->pes_level * 12];
@@ -1436,7 +1441,13 @@ int ssb_upload(ssb_sim* s, const char* name, size_t row0, size_t n_rows, const f
     if ((long long)(row0 + n_rows) > a.rows) return fail(-1, "ssb_upload: rows out of range");
     SSB_CUDA(cudaSetDevice(s->device));
     if (a.ptr == s->ldec && pes_flush(s)) return -2;
-    if (a.tiled) {
+    if (a.ptr == s->ldec) {
+        // learned decoders are not row-per-trial-vector: a group's block is [neuron][trial][JP] (ssb_pes.cuh); the host
+        // passes the device order, [group][n_rows][32] floats, for the row range of one decoder
+        for (int g = 0; g < s->n_groups; ++g)
+            SSB_CUDA(cudaMemcpyAsync(a.ptr + ((size_t)g * a.rows + row0) * 32, host + (size_t)g * n_rows * 32,
+                                     n_rows * 32 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    } else if (a.tiled) {
         if (copy_rows(s, a.ptr, std::max(1LL, a.rows), row0, n_rows, const_cast<float*>(host), true)) return -2;
     } else {
         SSB_CUDA(cudaMemcpyAsync(a.ptr + row0 * s->B, host, n_rows * s->B * sizeof(float), cudaMemcpyHostToDevice, s->stream));
@@ -1452,7 +1463,11 @@ int ssb_download(ssb_sim* s, const char* name, size_t row0, size_t n_rows, float
     if ((long long)(row0 + n_rows) > a.rows) return fail(-1, "ssb_download: rows out of range");
     SSB_CUDA(cudaSetDevice(s->device));
     if (a.ptr == s->ldec && pes_flush(s)) return -2;
-    if (a.tiled) {
+    if (a.ptr == s->ldec) {
+        for (int g = 0; g < s->n_groups; ++g)
+            SSB_CUDA(cudaMemcpyAsync(host + (size_t)g * n_rows * 32, a.ptr + ((size_t)g * a.rows + row0) * 32,
+                                     n_rows * 32 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    } else if (a.tiled) {
         if (copy_rows(s, a.ptr, std::max(1LL, a.rows), row0, n_rows, host, false)) return -2;
     } else {
         SSB_CUDA(cudaMemcpyAsync(host, a.ptr + row0 * s->B, n_rows * s->B * sizeof(float), cudaMemcpyDeviceToHost, s->stream));

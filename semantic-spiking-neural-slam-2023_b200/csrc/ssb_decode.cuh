@@ -178,17 +178,22 @@ __global__ void __launch_bounds__(128) k_decode(SsbCtx c, const int* __restrict_
 // Instantiated for <N = 64 outputs, KS = 64 neurons per stage> and <N = 128, KS = 32> (wider decoders, e.g. d = 97).
 template <int SSB_DTC_N, int SSB_DTC_KS>
 __global__ void __launch_bounds__(256, 1)
-k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __restrict__ Wt_all, const int* __restrict__ wt_off) {
+k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __restrict__ Wt_all, const int* __restrict__ wt_off,
+            int n_nt) {
     extern __shared__ __align__(1024) float sm[];
     __shared__ unsigned long long full[2], done[2];
     __shared__ uint32_t tmem_slot;
     __shared__ int s_last[4];
-    const int* d = desc + (item0 + blockIdx.z) * 9;
+    // blockIdx.z = (decoder, tile of SSB_DTC_N output columns): decoders wider than one tile (d = 649) are covered by n_nt
+    // column tiles, each with its own operand tiles [n_stages][hi | lo] and its own split-K counter
+    const int zi = blockIdx.z / n_nt, nt = blockIdx.z - zi * n_nt;
+    const int* d = desc + (item0 + zi) * 9;
     const int n = d[0], size_out = d[1], act0 = d[3], out_vec = d[5], n_chunks = d[6], part_off = d[7];
-    const float* __restrict__ Wt = Wt_all + wt_off[item0 + blockIdx.z];
+    const int col0 = nt * SSB_DTC_N;
     const int chunk = blockIdx.x;
-    if (chunk >= n_chunks) return;
+    if (chunk >= n_chunks || col0 >= size_out) return;
     const int n_stages = (n + SSB_DTC_KS - 1) / SSB_DTC_KS;
+    const float* __restrict__ Wt = Wt_all + wt_off[item0 + zi] + (size_t)nt * n_stages * 2 * SSB_DTC_N * SSB_DTC_KS;
     const int spc = (n_stages + n_chunks - 1) / n_chunks;
     const int s_lo = chunk * spc, s_hi = min(n_stages, s_lo + spc);
     const int my = max(0, s_hi - s_lo);
@@ -295,7 +300,7 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
             if (live) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int jo = c0 + j;
+                    const int jo = col0 + c0 + j;
                     if (jo < size_out) {
                         if (n_chunks == 1) vg[(size_t)(out_vec + jo) * 32] = v[j];
                         else pg[(size_t)(part_off + chunk * size_out + jo) * 32] = v[j];
@@ -304,7 +309,7 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
             }
         }
     } else if (live && n_chunks > 1) {                  // an empty trailing chunk still owns its partial slot
-        for (int j = half * (SSB_DTC_N / 2); j < min(size_out, (half + 1) * (SSB_DTC_N / 2)); ++j)
+        for (int j = col0 + half * (SSB_DTC_N / 2); j < min(size_out, col0 + (half + 1) * (SSB_DTC_N / 2)); ++j)
             pg[(size_t)(part_off + chunk * size_out + j) * 32] = 0.f;
     }
     ssb_tc_fence_before();
@@ -317,7 +322,7 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
         if (lane == 0) {
             int last = 0;
             if (live) {
-                int* cnt_p = c.counters + d[8] * c.G + group;
+                int* cnt_p = c.counters + (d[8] + nt) * c.G + group;
                 const int old = atomicAdd(cnt_p, 1);
                 last = old == n_chunks - 1;
                 if (last) *cnt_p = 0;
@@ -328,7 +333,7 @@ k_decode_tc(SsbCtx c, const int* __restrict__ desc, int item0, const float* __re
     __syncthreads();
     if (!s_last[quad]) return;
     __threadfence();
-    for (int j = half * (SSB_DTC_N / 2); j < min(size_out, (half + 1) * (SSB_DTC_N / 2)); j += 8) {   // the two warps of a group split the outputs
+    for (int j = col0 + half * (SSB_DTC_N / 2); j < min(size_out, col0 + (half + 1) * (SSB_DTC_N / 2)); j += 8) {   // the two warps of a group split the outputs
         float t[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) t[u] = 0.f;

@@ -490,7 +490,8 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
     const int K = pf.h.K;
     const SsbStep stp = ssb_step(c, i_rel);
     const int slot = (int)(stp.step % K);      // this step's term is not in the history yet: it is read at its source
-    const float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + (size_t)d_off * 32;
+    const int JP = (size_out + 3) & ~3;                 // decoder block of neuron i: [trial lane][JP] (see ssb_pes.cuh)
+    const float* __restrict__ dl = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)lane * JP;
     const float* __restrict__ hf = ssb_grp(pf.h.hist_f, pf.h.rows_f, g, lane) + (size_t)hd[1] * 32;
     const float* __restrict__ fcur = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)(1 - stp.odd) * c.n_afilt + a_off) * 32;
     const int prow = size_out + K;
@@ -510,9 +511,15 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
             if (!__any_sync(0xffffffffu, on)) continue;
             const size_t ni = (size_t)(n0 + i);
             float w[SSB_PESF_NJ], f[8];
+            const float4* src4 = reinterpret_cast<const float4*>(dl + ni * JP * 32 + j0);
 #pragma unroll
-            for (int j = 0; j < SSB_PESF_NJ; ++j)
-                w[j] = (on && j0 + j < size_out) ? __ldcs(dp + ((size_t)(j0 + j) * n + ni) * 32) : 0.f;
+            for (int q4 = 0; q4 < SSB_PESF_NJ / 4; ++q4) {
+                const float4 t4 = (on && j0 + 4 * q4 < JP) ? __ldcs(src4 + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                w[4 * q4 + 0] = t4.x;
+                w[4 * q4 + 1] = t4.y;
+                w[4 * q4 + 2] = t4.z;
+                w[4 * q4 + 3] = t4.w;
+            }
             if (with_dots) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q)

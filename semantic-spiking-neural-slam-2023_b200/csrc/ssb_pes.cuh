@@ -1,133 +1,39 @@
-// sm_100a kernels of the SSP-SLAM step engine: PES-learned decoders: k_pes, deferred PES (k_pes_hist / k_pes_defer / k_pes_fold / k_pes_clear).
+// sm_100a kernels of the SSP-SLAM step engine: PES-learned decoders — deferred PES (k_pes_hist / k_pes_defer / k_pes_fold / k_pes_clear).
 // Included by ssb_kernels.cuh (after ssb_common.cuh); see that file for the layout rules.
 #pragma once
 #include "ssb_common.cuh"
 
 // --------------------------------------------------------------------------------------
-// PES-learned decoders (per trial): one streaming pass that applies the pending rank-1 delta,
-// decodes with the updated weights and writes them back:
-//   D <- D + outer(alpha*err_prev, a_prev)     (nengo: Copy(delta->weights, inc) at step start)
-//   out = D . act                               (DotInc)
-// err_prev / a_prev are the values the previous step read (the error rows are materialised from the
-// not-yet-overwritten filter half, the trace comes from the other half of its ping-pong buffer), which
-// is exactly SimPES' delta of the previous step.  For a fixed output row the weights of consecutive
-// neurons are consecutive 128-byte lines.  A neuron whose trace and activity are zero in all 32 trials
-// changes nothing and contributes nothing: its weights are neither read nor written (exact).
-// desc: n size_out d_off a_off act0 err_vec out_vec alpha_bits decay_bits onemdecay_bits n_chunks part_off counter0
-template <bool FULL>
-__device__ __forceinline__ void ssb_pes_body(const float* __restrict__ ap, const float* __restrict__ fp, float* __restrict__ dp,
-                                             int n, int jn, int i_lo, int i_hi, const float (&ae)[8], float (&acc)[8]) {
-    const int warp = threadIdx.x >> 5;
-    float* rowp[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rowp[j] = dp + (size_t)((FULL || j < jn) ? j : 0) * n * 32;
-    constexpr int U = 4;
-    // activities / traces of the NEXT batch are requested before this batch's weights, so the two dependent
-    // memory rounds of a batch (a, f -> vote -> weights) overlap across iterations
-    float an[U], fn[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int ii = i_lo + warp + 4 * u;
-        an[u] = 0.f;
-        fn[u] = 0.f;
-        if (ii < i_hi) {
-            an[u] = ap[(size_t)ii * 32];
-            fn[u] = fp[(size_t)ii * 32];
-        }
-    }
-    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
-        float a[U], f[U], w[U][8];
-        bool on[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            a[u] = an[u];
-            f[u] = fn[u];
-            const int ii = i + 4 * U + 4 * u;
-            an[u] = 0.f;
-            fn[u] = 0.f;
-            if (ii < i_hi) {
-                an[u] = ap[(size_t)ii * 32];
-                fn[u] = fp[(size_t)ii * 32];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            on[u] = __any_sync(0xffffffffu, a[u] != 0.f || f[u] != 0.f);
-            if (on[u]) {
-                const size_t off = (size_t)(i + 4 * u) * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (FULL || j < jn) w[u][j] = __ldcs(rowp[j] + off);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (on[u]) {
-                const size_t off = (size_t)(i + 4 * u) * 32;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (FULL || j < jn) {
-                        const float wn = fmaf(ae[j], f[u], w[u][j]);
-                        acc[j] = fmaf(wn, a[u], acc[j]);
-                        __stcs(rowp[j] + off, wn);
-                    }
-                }
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128) k_pes(SsbCtx c, const int* __restrict__ desc, int max_chunks, int i_rel) {
-    __shared__ float red[4][8][32];
-    __shared__ int flag;
-    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
-    const int* d = desc + item * 13;
-    const int n = d[0], size_out = d[1], d_off = d[2], a_off = d[3], act0 = d[4], err_vec = d[5], out_vec = d[6];
-    const int n_chunks = d[10];
-    const float alpha = __int_as_float(d[7]);
-    const int j0 = blockIdx.x * 8;
-    if (j0 >= size_out || chunk >= n_chunks) return;
-    const int per = (n + n_chunks - 1) / n_chunks;
-    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.y;
-    const SsbStep s = ssb_step(c, i_rel);
-    const int prev_buf = 1 - s.odd;  // afilt half that still holds what the previous step read
-    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    const int jn = min(8, size_out - j0);
-    float ae[8], acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        acc[j] = 0.f;
-        float e = 0.f;
-        if (j < jn) e = vg[(size_t)(err_vec + j0 + j) * 32];   // error of the previous step, materialised by k_lin
-        ae[j] = s.step > 0 ? alpha * e : 0.f;
-    }
-    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
-    const float* __restrict__ fp = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)prev_buf * c.n_afilt + a_off) * 32;
-    float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
-    if (jn == 8) ssb_pes_body<true>(ap, fp, dp, n, jn, i_lo, i_hi, ae, acc);
-    else ssb_pes_body<false>(ap, fp, dp, n, jn, i_lo, i_hi, ae, acc);
-    ssb_splitk_finish(c, red, &flag, acc, g, j0, size_out, out_vec, n_chunks, chunk, d[11],
-                      (d[12] + (int)blockIdx.x) * c.G + g);
-}
-
-// --------------------------------------------------------------------------------------
-// Deferred PES (default).  SimPES changes the decoders by one rank-1 term per step, D(t) = D(t-1) + ae(t) (x) f(t),
-// and the only per-step consumer is out(t) = D(t) . a(t) with a sparse spike vector a.  Instead of rewriting D every
-// step, the last K terms are kept as a history (ae_s: size_out rows, f_s: n rows per slot, slot = step mod K) and
+// PES-learned decoders (per trial).  nengo: SimPES computes delta = alpha * outer(err, a_filtered) as an update,
+// Copy(delta -> weights, inc) applies it at the start of the next step, DotInc decodes: out(t) = D(t) . a(t),
+// D(t) = D(t-1) + ae(t) (x) f(t) with ae = alpha * err and f the trace the previous step read.
+//
+// Deferred form.  The only per-step consumer of D is that decode, and a (the spikes) is sparse, so instead of rewriting D
+// every step the last K rank-1 terms are kept as a history (ae_s: size_out rows, f_s: n rows per slot, slot = step mod K):
 //     out(t) = D_base . a(t) + sum_s ae_s * (f_s . a(t)),
-// which reads D_base only where some trial of the group spiked and writes nothing; every K-th step (and before any
-// read-back of the decoders) the K terms are folded into D_base in one streaming pass.  Same arithmetic up to fp32
-// summation order; HBM traffic drops from 8 B to ~(active fraction * 4 + 8 / K) B per learned weight and step.
-//   k_pes_hist   appends this step's term (ae from the materialised error rows, f = the trace the previous step read);
-//                it runs AFTER the decode of its own step, which reads that term at its source
-//   k_pes_defer  the sparse decode; CTA = (8-row tile, trial group, neuron chunk); tile-0 CTAs also accumulate the K
-//                history dot products; the last CTA of a (decoder, group) adds partials in a fixed order and applies
-//                the history correction
-//   k_pes_fold   D_base += sum_s ae_s (x) f_s (runs when slot == K - 1, or when the host asks), then k_pes_clear zeroes
-//                the ae rows, so an empty history always contributes exactly 0
-// desc as k_pes; hdesc per decoder: e_row0 f_row0 part_row0 counter0 (rows of the hist_e / hist_f / pes_part arenas)
+// which reads D_base only where a trial spiked and writes nothing; every K-th step (and before any read-back of the
+// decoders) the K terms are folded into D_base in one streaming pass.  Same arithmetic up to fp32 summation order.
+//
+// Decoder layout in HBM: D_base of one trial group is [neuron i][trial lane][JP] floats (JP = size_out rounded up to 4),
+// i.e. the size_out weights that ONE spike of ONE trial needs are contiguous (224 bytes at d = 55: seven 32-byte sectors,
+// one DRAM page) instead of size_out sectors spread over size_out pages.  In units of 128-byte arena rows the block of a
+// neuron is JP rows: float offset = (d_off + i * JP) * 32 + lane * JP + j.
+//   k_pes_hist   appends this step's term (ae from the materialised error rows, f = the trace the previous step read) and
+//                updates the activity traces; it runs AFTER the decode of its own step, which reads that term at its source
+//   k_pes_defer  the sparse decode.  CTA = (neuron chunk, trial group, tile of 32 output columns); a warp walks the flag
+//                words of its quarter of the chunk (bit t = trial t spiked, written by the ensemble kernel), and per spiking
+//                (neuron, trial) the lane of that trial loads 8 x 16 bytes and accumulates 32 outputs in registers; the
+//                column-tile-0 CTAs also accumulate the K history dot products f_s . a.  Lane = trial, so there is no
+//                cross-lane reduction; warps are added through shared memory, chunks through the partial arena, and the
+//                last CTA of a (decoder, group) adds the partials in chunk order and applies the history correction.
+//   k_pes_fold   D_base += sum_s ae_s (x) f_s (when slot == K - 1, or when the host asks), then k_pes_clear zeroes the ae
+//                rows, so an empty history always contributes exactly 0
+// desc: n size_out d_off a_off act0 err_vec out_vec alpha_bits decay_bits onemdecay_bits n_chunks part_off counter0
+// hdesc per decoder: e_row0 f_row0 part_row0 counter0 (rows of the hist_e / hist_f / pes_part arenas)
+#define SSB_PES_JT 32          // output columns per k_pes_defer CTA
+#define SSB_PES_FT 64          // output columns per k_pes_fold shared-memory tile
+
+__host__ __device__ __forceinline__ int ssb_pes_jp(int size_out) { return (size_out + 3) & ~3; }
 
 __global__ void __launch_bounds__(128) k_pes_hist(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
                                                     const int* __restrict__ hdesc, int i_rel) {
@@ -159,57 +65,49 @@ __global__ void __launch_bounds__(128) k_pes_hist(SsbCtx c, SsbPesDefer h, const
     }
 }
 
+// Sparse decode of up to U spiking neurons at a time: registers w[U][JT] are all in flight before the first FMA.
 template <int K>
 __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
-                                                     const int* __restrict__ hdesc, int max_chunks, int i_rel) {
-    __shared__ float red[4][8][32];
+                                                     const int* __restrict__ hdesc, int n_jt_max, int i_rel) {
+    __shared__ float red[4][SSB_PES_JT + 8][32];
     __shared__ int flag;
-    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
+    const int item = blockIdx.z / n_jt_max, jt = blockIdx.z - item * n_jt_max;
     const int* d = desc + item * 13;
     const int* hd = hdesc + item * 4;
     const int n = d[0], size_out = d[1], d_off = d[2], a_off = d[3], act0 = d[4], err_vec = d[5], out_vec = d[6];
-    const int n_chunks = d[10];
-    const int n_jt = (size_out + 7) >> 3;
-    // blockIdx.x < n_jt: an 8-row tile of D_base; blockIdx.x == n_jt: the K history rows (f_s . a), same loop
-    const bool dots = (int)blockIdx.x == n_jt;
-    const int j0 = blockIdx.x * 8;
-    if ((int)blockIdx.x > n_jt || chunk >= n_chunks) return;
+    const int n_chunks = d[10], chunk = blockIdx.x;
+    const int JP = ssb_pes_jp(size_out);
+    const int n_jt = (JP + SSB_PES_JT - 1) / SSB_PES_JT;
+    if (jt >= n_jt || chunk >= n_chunks) return;
+    const int j0 = jt * SSB_PES_JT;
+    const int jw = min(SSB_PES_JT, JP - j0);                 // columns of this tile (a multiple of 4)
+    const bool dots = jt == 0;
     const int per = (n + n_chunks - 1) / n_chunks;
     const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.y;
-    const int jn = dots ? K : min(8, size_out - j0);
     const SsbStep s = ssb_step(c, i_rel);
     const int slot = (int)(s.step % K);       // this step's term is not in the history yet: it is read at its source
     const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
     const int* __restrict__ fl = c.aflag + (size_t)g * c.n_act + act0;
-    const float* rowp[8];
-    {
-        const float* dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
-        const float* hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
-        const float* fcur = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)(1 - s.odd) * c.n_afilt + a_off) * 32;
+    // this lane's trial: decoder block of neuron i starts at dl + i * JP * 32
+    const float* __restrict__ dl = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)lane * JP + j0;
+    const float* __restrict__ hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
+    const float* __restrict__ fcur = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)(1 - s.odd) * c.n_afilt + a_off) * 32;
+    float acc[SSB_PES_JT], dsum_l[K];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (dots) rowp[j] = (j == slot) ? fcur : hf + (size_t)(j < K ? j : 0) * n * 32;
-            else rowp[j] = dp + (size_t)(j < jn ? j : 0) * n * 32;
-        }
-    }
-    float acc[8];
+    for (int j = 0; j < SSB_PES_JT; ++j) acc[j] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // each warp owns a contiguous quarter of the chunk and walks only the neurons flagged active by their producer:
-    // 32 flags per coalesced load -> ballot -> up to U active neurons per batch with all their loads in flight
+    for (int q = 0; q < K; ++q) dsum_l[q] = 0.f;
     const int qn = (i_hi - i_lo + 3) >> 2;
     const int w_lo = i_lo + warp * qn, w_hi = min(i_hi, w_lo + qn);
     constexpr int U = 4;
     for (int base = w_lo; base < w_hi; base += 32) {
-        // the flag word of a neuron is the ballot of its producer: bit t = trial t has a non-zero activity
         const int myflag = (base + lane < w_hi) ? __ldg(fl + base + lane) : 0;
         unsigned m = __ballot_sync(0xffffffffu, myflag != 0);
         while (m) {
             int idx[U];
             unsigned bits[U];
-            float a[U], w[U][8];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 idx[u] = -1;
@@ -221,45 +119,62 @@ __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
                 }
                 bits[u] = (unsigned)__shfl_sync(0xffffffffu, myflag, src);
             }
+            float a[U];
+            float4 w[U][SSB_PES_JT / 4];
+            float f[U][K];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                a[u] = 0.f;
-                if (idx[u] >= 0) {
-                    const size_t off = (size_t)idx[u] * 32;
-                    // a lane whose trial is inactive contributes w * 0: it does not load at all, so only the 32-byte
-                    // sectors of the trials that spiked are fetched from DRAM (the flag ORs 32 trials); the predicate
-                    // comes from the flag word, not from the activity load, so the two stay in flight together
-                    const bool mine = (bits[u] >> lane) & 1u;
-                    a[u] = mine ? ap[off] : 0.f;
+                const bool mine = idx[u] >= 0 && ((bits[u] >> lane) & 1u);
+                const size_t ni = (size_t)(idx[u] >= 0 ? idx[u] : 0);
+                a[u] = mine ? ap[ni * 32] : 0.f;
+                const float4* src4 = reinterpret_cast<const float4*>(dl + ni * JP * 32);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) w[u][j] = (j < jn && mine) ? __ldcs(rowp[j] + off) : 0.f;
+                for (int q4 = 0; q4 < SSB_PES_JT / 4; ++q4)
+                    w[u][q4] = (mine && 4 * q4 < jw) ? __ldcs(src4 + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (dots) {
+#pragma unroll
+                    for (int q = 0; q < K; ++q)
+                        f[u][q] = mine ? ((q == slot) ? fcur[ni * 32] : hf[((size_t)q * n + ni) * 32]) : 0.f;
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (idx[u] >= 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[u][j], a[u], acc[j]);
+                for (int q4 = 0; q4 < SSB_PES_JT / 4; ++q4) {
+                    acc[4 * q4 + 0] = fmaf(w[u][q4].x, a[u], acc[4 * q4 + 0]);
+                    acc[4 * q4 + 1] = fmaf(w[u][q4].y, a[u], acc[4 * q4 + 1]);
+                    acc[4 * q4 + 2] = fmaf(w[u][q4].z, a[u], acc[4 * q4 + 2]);
+                    acc[4 * q4 + 3] = fmaf(w[u][q4].w, a[u], acc[4 * q4 + 3]);
+                }
+                if (dots) {
+#pragma unroll
+                    for (int q = 0; q < K; ++q) dsum_l[q] = fmaf(f[u][q], a[u], dsum_l[q]);
                 }
             }
         }
     }
     // CTA partial: ((w0 + w1) + (w2 + w3)) per row, parked in the partial arena [chunk][size_out + K]
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[warp][j][lane] = acc[j];
+    for (int j = 0; j < SSB_PES_JT; ++j) red[warp][j][lane] = acc[j];
+#pragma unroll
+    for (int q = 0; q < K; ++q) red[warp][SSB_PES_JT + q][lane] = dsum_l[q];
     __syncthreads();
     const int prow = size_out + K;
     float* pg = ssb_grp(h.part, h.rows_p, g, lane) + (size_t)hd[2] * 32;
-    for (int j = warp; j < jn; j += 4) {
-        const float t = (red[0][j][lane] + red[1][j][lane]) + (red[2][j][lane] + red[3][j][lane]);
-        pg[(size_t)(chunk * prow + (dots ? size_out : j0) + j) * 32] = t;
+    for (int r = warp; r < SSB_PES_JT + (dots ? K : 0); r += 4) {
+        const bool is_dot = r >= SSB_PES_JT;
+        const int row = is_dot ? size_out + (r - SSB_PES_JT) : j0 + r;
+        if (is_dot || row < size_out) {
+            const float t = (red[0][r][lane] + red[1][r][lane]) + (red[2][r][lane] + red[3][r][lane]);
+            pg[(size_t)(chunk * prow + row) * 32] = t;
+        }
     }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         int* cnt_p = h.counters + hd[3] * c.G + g;
         const int old = atomicAdd(cnt_p, 1);
-        const int last = old == (n_jt + 1) * n_chunks - 1;
+        const int last = old == n_jt * n_chunks - 1;
         if (last) *cnt_p = 0;
         flag = last;
     }
@@ -307,54 +222,56 @@ __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
     }
 }
 
-// launched by the host after the step whose slot is K - 1, and before any read-back of the decoders
+// launched by the host after the step whose slot is K - 1, and before any read-back of the decoders.
+// CTA = (neuron chunk, trial group, decoder); the ae rows of a tile of SSB_PES_FT output columns sit in shared memory
+// ([K][FT][32], lane-interleaved: conflict-free), each warp takes a neuron, each lane its own trial's contiguous weights.
 template <int K>
 __global__ void __launch_bounds__(128) k_pes_fold(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
                                                     const int* __restrict__ hdesc, int max_chunks, int i_rel, int force) {
-    const int item = blockIdx.z / max_chunks, chunk = blockIdx.z - item * max_chunks;
+    extern __shared__ __align__(16) float sm[];          // [K][SSB_PES_FT][32]
+    const int item = blockIdx.z, chunk = blockIdx.x;
     const int* d = desc + item * 13;
     const int* hd = hdesc + item * 4;
-    const int n = d[0], size_out = d[1], d_off = d[2], n_chunks = d[10];
-    const int j0 = blockIdx.x * 8;
-    if (j0 >= size_out || chunk >= n_chunks) return;
-    const int per = (n + n_chunks - 1) / n_chunks;
+    const int n = d[0], size_out = d[1], d_off = d[2];
+    const int JP = ssb_pes_jp(size_out);
+    const int per = (n + max_chunks - 1) / max_chunks;
     const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
+    if (i_lo >= i_hi) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.y;
-    const int jn = min(8, size_out - j0);
-    float* __restrict__ dp = ssb_grp(c.ldec, c.n_ldec, g, lane) + ((size_t)d_off + (size_t)j0 * n) * 32;
+    float* __restrict__ dl = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)lane * JP;
     const float* __restrict__ hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
     const float* __restrict__ he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
-    float ae[K][8];
-#pragma unroll
-    for (int q = 0; q < K; ++q)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ae[q][j] = (j < jn) ? he[(size_t)(q * size_out + j0 + j) * 32] : 0.f;
-    constexpr int U = 2;                     // two neurons per iteration: 2 * (K + 8) loads in flight per warp
-    for (int i = i_lo + warp; i < i_hi; i += 4 * U) {
-        float fv[U][K], w[U][8];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int ii = i + 4 * u;
-            const size_t off = (size_t)(ii < i_hi ? ii : i) * 32;
-#pragma unroll
-            for (int q = 0; q < K; ++q) fv[u][q] = hf[(size_t)q * n * 32 + off];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[u][j] = (j < jn) ? __ldcs(dp + (size_t)j * n * 32 + off) : 0.f;
+    for (int j0 = 0; j0 < JP; j0 += SSB_PES_FT) {
+        const int jw = min(SSB_PES_FT, JP - j0);
+        __syncthreads();
+        for (int r = warp; r < K * SSB_PES_FT; r += 4) {
+            const int q = r / SSB_PES_FT, j = r - q * SSB_PES_FT;
+            sm[r * 32 + lane] = (j0 + j < size_out) ? he[(size_t)(q * size_out + j0 + j) * 32] : 0.f;
         }
+        __syncthreads();
+        for (int i = i_lo + warp; i < i_hi; i += 4) {
+            float fv[K];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int ii = i + 4 * u;
-            if (ii < i_hi) {
-                const size_t off = (size_t)ii * 32;
+            for (int q = 0; q < K; ++q) fv[q] = hf[((size_t)q * n + i) * 32];
+            float4* w4 = reinterpret_cast<float4*>(dl + (size_t)i * JP * 32 + j0);
+            float4 w[SSB_PES_FT / 4];
 #pragma unroll
-                for (int q = 0; q < K; ++q)
+            for (int q4 = 0; q4 < SSB_PES_FT / 4; ++q4) w[q4] = (4 * q4 < jw) ? __ldcs(w4 + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) w[u][j] = fmaf(ae[q][j], fv[u][q], w[u][j]);
+            for (int q = 0; q < K; ++q) {
+                const float* aq = sm + (size_t)q * SSB_PES_FT * 32 + lane;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j < jn) __stcs(dp + (size_t)j * n * 32 + off, w[u][j]);
+                for (int q4 = 0; q4 < SSB_PES_FT / 4; ++q4) {
+                    w[q4].x = fmaf(aq[(4 * q4 + 0) * 32], fv[q], w[q4].x);
+                    w[q4].y = fmaf(aq[(4 * q4 + 1) * 32], fv[q], w[q4].y);
+                    w[q4].z = fmaf(aq[(4 * q4 + 2) * 32], fv[q], w[q4].z);
+                    w[q4].w = fmaf(aq[(4 * q4 + 3) * 32], fv[q], w[q4].w);
+                }
             }
+#pragma unroll
+            for (int q4 = 0; q4 < SSB_PES_FT / 4; ++q4)
+                if (4 * q4 < jw) __stcs(w4 + q4, w[q4]);
         }
     }
 }

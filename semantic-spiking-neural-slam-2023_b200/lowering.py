@@ -196,10 +196,12 @@ class _Lowerer:
                 else:                  # static decoders
                     jpad = -(-self._out_size(c) // DEC_TILE) * DEC_TILE
                     quads = -(-self.n_groups // 4)
-                    if max_jpad <= 2 * DEC_TC_WIDTH and os.environ.get("SSB_DECODE") != "ffma":
-                        # k_decode_tc: CTA = (decoder, 128 trials, K chunk of 64- (or 32-) neuron stages), one CTA per SM
+                    if os.environ.get("SSB_DECODE") != "ffma":
+                        # k_decode_tc: CTA = (decoder, tile of 128 output columns, 128 trials, K chunk of 64- (or 32-) neuron
+                        # stages), one CTA per SM; decoders wider than 128 columns (d = 649) take several column tiles
                         n_stages = -(-ens.n_neurons // (DEC_TC_STAGE if max_jpad <= DEC_TC_WIDTH else DEC_TC_STAGE // 2))
-                        self.dec_chunks[c] = int(max(1, min(n_stages, N_SM // max(1, n_static * quads))))
+                        n_nt = 1 if max_jpad <= DEC_TC_WIDTH else -(-max_jpad // (2 * DEC_TC_WIDTH))
+                        self.dec_chunks[c] = int(max(1, min(n_stages, N_SM // max(1, n_static * quads * n_nt))))
                         continue
                     # k_decode (FFMA): CTA = (decoder, quad of trial groups, neuron chunk), all outputs at once
                     per_max = max(1, DEC_SMEM_BYTES // (jpad * 4 + 4 * 128))   # weight tile + 4 activity tiles of a chunk
@@ -550,7 +552,7 @@ class _Lowerer:
         dec_desc = [[] for _ in range(n_levels)]
         pes_desc, cleanup_desc, gate_desc = [], [[] for _ in range(n_levels)], [[] for _ in range(n_levels)]
         pes_trace, cleanup_s64 = [], [[] for _ in range(n_levels)]
-        nn = n_act = n_lenc = n_ldec = n_afilt = 0
+        nn = n_act = n_lenc = n_ldec = n_afilt = n_ldec_words = 0
         n_small = n_big = 0
         n_part = n_jtiles = 0
         pes_level = -1
@@ -629,7 +631,10 @@ class _Lowerer:
                 if compat.is_connection(c) and c in pes_rule:
                     rin, lrt = pes_rule[c]
                     d_off = n_ldec
-                    n_ldec += size_out * n
+                    # device layout of a learned decoder (csrc/ssb_pes.cuh): per trial group [neuron][trial][JP] floats,
+                    # JP = size_out rounded up to 4 -> JP arena rows of 32 floats per neuron
+                    n_ldec += (-(-size_out // 4) * 4) * n
+                    n_ldec_words += size_out * n
                     plan.learned_dec[c] = (d_off, size_out, n)
                     a_off = n_afilt
                     n_afilt += n
@@ -784,7 +789,7 @@ class _Lowerer:
                                  chunk_cap=chunk_cap, n_part=n_part, n_jtiles=n_jtiles, pes_level=pes_level,
                                  lin0=lin0, n_lin=len(lin_rows) - lin0))
         n_static = int(sum(a.size for a in W))
-        plan.stats = dict(n_neurons=nn, n_filter_states=NF, n_learned=n_lenc + n_ldec, n_static_weights=n_static,
+        plan.stats = dict(n_neurons=nn, n_filter_states=NF, n_learned=n_lenc + n_ldec_words, n_static_weights=n_static,
                           n_table_words=NT, n_probe_words=n_probe_rows, n_small=n_small, n_big=n_big,
                           n_levels=n_levels, csr_nnz=len(csr_idx), n_afilt=n_afilt, n_act=n_act)
         n_small_neurons = int(sum(e.n_neurons for e in self.ensembles if self.is_small[e]))
@@ -795,7 +800,7 @@ class _Lowerer:
             "ens_small": 16 * n_small_neurons,
             "ens_wide": 16 * (nn - n_small_neurons - n_voja_neurons),
             "ens_voja": 16 * n_voja_neurons + 8 * n_lenc,
-            "pes": 8 * n_ldec,
+            "pes": 8 * n_ldec_words,
             "lin": 8 * (NF + n_afilt) + 4 * n_probe_rows,
             "inputs": 4 * NT,
         }

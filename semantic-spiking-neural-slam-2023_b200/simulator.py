@@ -170,6 +170,28 @@ class Simulator:
                    f"download {arena}")
         return out
 
+    # learned decoders: a trial group's block is [neuron][trial][JP] floats (csrc/ssb_pes.cuh), JP = size_out rounded up to 4
+    def _upload_decoders(self, conn, per_trial):
+        """``per_trial`` [n_trials, size_out, n] -> device order [group][n * JP rows][32]."""
+        row0, size_out, n = self.plan.learned_dec[conn]
+        jp = -(-size_out // 4) * 4
+        G = self.B // 32
+        full = np.zeros((self.B, jp, n), dtype=np.float32)
+        full[:self.n_trials, :size_out] = per_trial
+        dev = np.ascontiguousarray(full.reshape(G, 32, jp, n).transpose(0, 3, 1, 2))       # [G][n][32][jp]
+        dev = dev.reshape(G, n * jp, 32)
+        cabi.check(self._lib.ssb_upload(self._h, b"ldec", int(row0), int(n * jp), cabi._ptr(dev)), "upload ldec")
+
+    def _download_decoders(self, conn):
+        """Device decoder block -> [n_trials, size_out, n] float32."""
+        row0, size_out, n = self.plan.learned_dec[conn]
+        jp = -(-size_out // 4) * 4
+        G = self.B // 32
+        dev = np.empty((G, n * jp, 32), dtype=np.float32)
+        cabi.check(self._lib.ssb_download(self._h, b"ldec", int(row0), int(n * jp), cabi._ptr(dev)), "download ldec")
+        full = dev.reshape(G, n, 32, jp).transpose(0, 2, 3, 1).reshape(self.B, jp, n)
+        return np.ascontiguousarray(full[:self.n_trials, :size_out])
+
     def _init_state(self):
         m, plan = self.model, self.plan
         nn = int(plan.scalars["nn"])
@@ -182,8 +204,9 @@ class Simulator:
             self._upload("st", 0, v0)   # packed LIF state: s >= 0 is the voltage of a non-refractory neuron
         for ens, (row0, n, dims) in plan.learned_enc.items():
             self._upload("lenc", row0, self._rows(m.params[ens].scaled_encoders.reshape(-1)))
-        for conn, (row0, size_out, n) in plan.learned_dec.items():
-            self._upload("ldec", row0, self._rows(np.asarray(m.params[conn].weights).reshape(-1)))
+        for conn in plan.learned_dec:
+            w = np.asarray(m.params[conn].weights, dtype=np.float32)
+            self._upload_decoders(conn, np.broadcast_to(w[None], (self.n_trials,) + w.shape))
         # per "rows" probe: list of [samples, size, n_trials] float32 chunks, already decimated by the probe's period
         self._probe_rows = {info.probe: [] for info in plan.probes if info.kind == "rows"}
         self._probe_steps_flushed = 0
@@ -377,9 +400,7 @@ class Simulator:
 
     def _snapshot(self, info):
         if info.kind == "weights":
-            row0, size_out, n = self.plan.learned_dec[info.conn]
-            w = self._download("ldec", row0, size_out * n)[:, :self.n_trials]
-            return w.T.reshape(self.n_trials, size_out, n).astype(np.float64)
+            return self._download_decoders(info.conn).astype(np.float64)
         row0, n, dims = self.plan.learned_enc[info.ens]
         e = self._download("lenc", row0, n * dims)[:, :self.n_trials]
         return e.T.reshape(self.n_trials, n, dims).astype(np.float64)
@@ -422,8 +443,7 @@ class Simulator:
         return self._download("lenc", row0, n * dims)[:, :self.n_trials].T.reshape(self.n_trials, n, dims)
 
     def learned_decoders(self, conn):
-        row0, size_out, n = self.plan.learned_dec[conn]
-        return self._download("ldec", row0, size_out * n)[:, :self.n_trials].T.reshape(self.n_trials, size_out, n)
+        return self._download_decoders(conn)
 
     def cleanup_indices(self):
         """Last grid clean-up argmax per clean-up node: int array [n_nodes, n_trials]."""
