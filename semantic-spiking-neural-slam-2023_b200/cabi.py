@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssb.so")
 KERNEL_KINDS = ("ens_small", "ens_wide", "decode", "pes", "cleanup_scan", "cleanup_pick", "gate", "lin", "advance",
-                "begin", "ens_voja")
+                "begin", "ens_voja", "extra", "pes_hist", "pes_fold")
 
 _lib = None
 

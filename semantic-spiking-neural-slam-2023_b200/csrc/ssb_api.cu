@@ -27,7 +27,7 @@ int fail(int code, const std::string& msg) {
             return fail(-2, std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
     } while (0)
 
-enum Kind { K_SMALL = 0, K_WIDE, K_DEC, K_PES, K_SCAN, K_PICK, K_GATE, K_LIN, K_ADV, K_BEGIN, K_VOJA, K_EXTRA, K_NKINDS };   // K_EXTRA: further kernels of a multi-kernel scope
+enum Kind { K_SMALL = 0, K_WIDE, K_DEC, K_PES, K_SCAN, K_PICK, K_GATE, K_LIN, K_ADV, K_BEGIN, K_VOJA, K_EXTRA, K_PHIST, K_PFOLD, K_NKINDS };   // K_EXTRA: further kernels of a multi-kernel scope; K_PES = the sparse decode, K_PHIST / K_PFOLD the history append and the fold
 
 struct HostArray {
     std::vector<unsigned char> bytes;
@@ -649,7 +649,6 @@ int pes_flush(ssb_sim* s) {
 }
 
 void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
-    LaunchTimer t(s, K_PES, st);
     int max_chunks = 1, max_rows = 0, max_jt = 1;
     for (int i = 0; i < s->n_pes; ++i) {
         const int* d = &s->h_pes[i * 13];
@@ -657,23 +656,24 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
         max_rows = std::max(max_rows, d[0] + d[1]);
         max_jt = std::max(max_jt, (ssb_pes_jp(d[1]) + SSB_PES_JT - 1) / SSB_PES_JT);
     }
-    if (s->pes_fused) {
-        // the sparse decode already ran inside the Voja ensemble kernel of this step
-    } else {
+    if (!s->pes_fused) {     // (fused: the sparse decode already ran inside the Voja ensemble kernel of this step)
+        LaunchTimer t(s, K_PES, st);
         dim3 dgrid(max_chunks, s->n_groups, s->n_pes * max_jt);
         if (s->pes_h.K == 4) k_pes_defer<4><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
         else k_pes_defer<8><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
     }
-    k_pes_hist<<<dim3((max_rows + 3) / 4, s->n_groups, s->n_pes), 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, i_rel);
+    {
+        LaunchTimer t(s, K_PHIST, st);
+        k_pes_hist<<<dim3((max_rows + 3) / 4, s->n_groups, s->n_pes), 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, i_rel);
+    }
     // the host mirrors the step counter, so the fold is launched only after the last slot of a window
     // (a captured graph bakes this in; it is replayed only from steps with the same phase, see ssb_run_steps)
-    int extra = 1;                                   // k_pes_hist
     if ((int)((s->steps_done + i_rel) % s->pes_h.K) == s->pes_h.K - 1) {
+        LaunchTimer t(s, K_PFOLD, st);
         launch_pes_fold(s, st, i_rel, 1);
-        extra += 2;                                  // k_pes_fold + k_pes_clear
+        s->kind_launches[K_EXTRA] += 1;              // k_pes_clear
+        s->total_launches += 1;
     }
-    s->kind_launches[K_EXTRA] += extra;
-    s->total_launches += extra;
 }
 
 // SSB_ENCODE=tc selects the tensor-core wide-ensemble kernel.  Measured on B200 (BASELINE configs[1], 1024 trials):
