@@ -508,6 +508,24 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
         dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
         k_wide_static<DP><<<grid, 128, smem_of(chunk), st>>>(s->ctx, s->d_big, items, chunk, i_rel);
     } else {
+        if (DP == 0 && (size_t)max_dims * 128 * 2 > 96 * 1024) {
+            // very long encoder rows (d = 649): stream them through per-warp rings of sub-tiles (k_wide_voja_stream)
+            const size_t smem = (size_t)(max_dpad * 32 + max_jn * 32 + 8 * SSB_VS_NB * SSB_VS_SUB * 32) * sizeof(float);
+            const int key = (1 << 29) | (max_n << 6) | (units & 63);
+            auto it = s->wide_chunk_cache.find(key);
+            int chunk = it == s->wide_chunk_cache.end() ? 0 : it->second;
+            if (!chunk) {
+                cudaFuncSetAttribute(k_wide_voja_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                const int per_unit = std::max(1, 148 / std::max(1, units));        // one CTA per SM: one wave
+                chunk = (max_n + per_unit - 1) / per_unit;
+                chunk = std::max(8, (chunk + 7) / 8 * 8);
+                s->wide_chunk_cache[key] = chunk;
+            }
+            if (dry) return;
+            dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
+            k_wide_voja_stream<<<grid, 256, smem, st>>>(s->ctx, s->d_big, items, chunk, i_rel);
+            return;
+        }
         int nwarps = 4, nb = SSB_VOJA_NB;
         SsbPesFuse pf;
         memset(&pf, 0, sizeof(pf));
@@ -595,9 +613,8 @@ int setup_pes_defer(ssb_sim* s) {
     // neuron chunks of the sparse decode: enough CTAs (chunks x groups x column tiles) for ~3 resident CTAs per SM
     int tiles_total = 0;
     for (int i = 0; i < s->n_pes; ++i) tiles_total += (ssb_pes_jp(s->h_pes[i * 13 + 1]) + SSB_PES_JT - 1) / SSB_PES_JT;
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pes_defer<8>, 128, 0);
-    int chunks = 148 * std::max(1, occ) / std::max(1, tiles_total * s->n_groups);     // one wave of resident CTAs
+    // CTAs = chunks x 4 trial octets x groups x column tiles, 8 light warps each: aim at ~6 CTAs per SM
+    int chunks = (148 * 6) / std::max(1, 4 * tiles_total * s->n_groups);
     chunks = std::max(1, std::min(chunks, 32));
     if (const char* e = getenv("SSB_PES_CHUNKS")) chunks = std::max(1, std::min(atoi(e), 64));
     std::vector<int> hd;
@@ -632,11 +649,11 @@ void launch_pes_fold(ssb_sim* s, cudaStream_t st, int i_rel, int force) {
     // neuron chunks of the streaming fold: ~4 CTAs per SM
     int max_n = 0;
     for (int i = 0; i < s->n_pes; ++i) max_n = std::max(max_n, s->h_pes[i * 13]);
-    const int chunks = std::max(1, std::min((148 * 4 + s->n_groups * s->n_pes - 1) / std::max(1, s->n_groups * s->n_pes), (max_n + 7) / 8));
+    const int chunks = std::max(1, std::min((148 * 3 + s->n_groups * s->n_pes - 1) / std::max(1, s->n_groups * s->n_pes), (max_n + 7) / 8));
     dim3 grid(chunks, s->n_groups, s->n_pes);
     const size_t smem = (size_t)s->pes_h.K * SSB_PES_FT * 32 * sizeof(float);
-    if (s->pes_h.K == 4) k_pes_fold<4><<<grid, 128, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks, i_rel, force);
-    else k_pes_fold<8><<<grid, 128, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks, i_rel, force);
+    if (s->pes_h.K == 4) k_pes_fold<4><<<grid, 256, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks, i_rel, force);
+    else k_pes_fold<8><<<grid, 256, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks, i_rel, force);
     k_pes_clear<<<dim3((s->pes_h.rows_e + 3) / 4, s->n_groups), 128, 0, st>>>(s->ctx, s->pes_h, i_rel, force);
 }
 
@@ -649,18 +666,20 @@ int pes_flush(ssb_sim* s) {
 }
 
 void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
-    int max_chunks = 1, max_rows = 0, max_jt = 1;
+    int max_chunks = 1, max_rows = 0, max_jt = 1, max_per = 1;
     for (int i = 0; i < s->n_pes; ++i) {
         const int* d = &s->h_pes[i * 13];
         max_chunks = std::max(max_chunks, d[10]);
+        max_per = std::max(max_per, (d[0] + d[10] - 1) / d[10]);
         max_rows = std::max(max_rows, d[0] + d[1]);
         max_jt = std::max(max_jt, (ssb_pes_jp(d[1]) + SSB_PES_JT - 1) / SSB_PES_JT);
     }
     if (!s->pes_fused) {     // (fused: the sparse decode already ran inside the Voja ensemble kernel of this step)
         LaunchTimer t(s, K_PES, st);
-        dim3 dgrid(max_chunks, s->n_groups, s->n_pes * max_jt);
-        if (s->pes_h.K == 4) k_pes_defer<4><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
-        else k_pes_defer<8><<<dgrid, 128, 0, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
+        dim3 dgrid(max_chunks * 4, s->n_groups, s->n_pes * max_jt);
+        const size_t fsmem = (size_t)max_per * sizeof(int);                   // flag words of one neuron chunk
+        if (s->pes_h.K == 4) k_pes_defer<4><<<dgrid, 256, fsmem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
+        else k_pes_defer<8><<<dgrid, 256, fsmem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
     }
     {
         LaunchTimer t(s, K_PHIST, st);
@@ -1329,7 +1348,7 @@ int ssb_finalize(ssb_sim* s) {
             const int* d = &s->h_big[found * 16];
             int nb = SSB_VOJA_NB;                         // as launch_wide_class sizes the ring of a warp
             while (nb > 1 && (size_t)(d[2] * 32 + d[11] * 32 + nb * d[1] * 32) * sizeof(float) > 200 * 1024) --nb;
-            if (std::min(pd[1], 56) + 8 > nb * d[1]) ok = false;
+            if (std::min(pd[1], 56) + 8 > nb * d[1] || (size_t)d[1] * 128 * 2 > 96 * 1024) ok = false;   // (stream-class ensembles: no fusion)
             else s->pes_of_big[found] = i;
         }
         s->pes_fused = ok;

@@ -607,3 +607,130 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
     }
 }
 
+// --------------------------------------------------------------------------------------
+// Voja ensembles whose encoder rows are too long to keep whole tiles in shared memory (d = 649: one neuron's encoders of
+// one trial group are 83 KB).  The per-trial encoders of a warp's neuron range are ONE contiguous run of 128-byte rows
+// (row = neuron * dims + k), so each warp streams that run through a ring of SSB_VS_NB sub-tiles of SSB_VS_SUB rows,
+// irrespective of neuron boundaries; the dot product of a neuron is closed when its last row has passed.  Shared memory is
+// only read: for the (few) lanes that spiked, the Voja update re-reads the neuron's rows from L2 and writes back just
+// those lanes' words, so a spike costs 32-byte sector writes instead of a whole-tile write-back.
+// CTA = (neuron chunk, trial group, ensemble), 8 warps; dynamic smem: xs [dpad][32] | us [jn_m][32] | 8 rings.
+#define SSB_VS_NB 4
+#define SSB_VS_SUB 32
+__global__ void __launch_bounds__(256, 1) k_wide_voja_stream(SsbCtx c, const int* __restrict__ desc, SsbItemList items,
+                                                             int chunk, int i_rel) {
+    extern __shared__ __align__(128) float sm[];
+    __shared__ unsigned long long wbar[8][SSB_VS_NB];
+    const int* d = desc + items.idx[blockIdx.z] * 16;
+    const int n = d[0], dims = d[1], dpad = d[2], state0 = d[3], act0 = d[4], enc_off = d[5], bias_off = d[6];
+    const int in_row0 = d[7], jn_row0 = d[10], jn_m = d[11], jn_w = d[12], voja_row = d[13], scale_off = d[14];
+    const int n0 = blockIdx.x * chunk;
+    if (n0 >= n) return;
+    const int cnt = min(chunk, n - n0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = 8;
+    const int g = blockIdx.y;
+    const SsbNeuron nt = ssb_neuron(c, d[8]);
+    const bool stateful = nt.type == 0;
+    float* xs = sm;                                        // [dpad][32]
+    float* us = xs + (size_t)dpad * 32;                    // [jn_m][32]
+    float* ring = us + (size_t)jn_m * 32 + (size_t)warp * SSB_VS_NB * SSB_VS_SUB * 32;
+    const int per = (chunk + NW - 1) / NW;
+    const int i_lo = warp * per, i_hi = min(cnt, i_lo + per);
+    const long long n_rows = (long long)max(0, i_hi - i_lo) * dims;          // rows of this warp's run
+    const int n_tiles = (int)((n_rows + SSB_VS_SUB - 1) / SSB_VS_SUB);
+    float* eg = c.lenc + ((size_t)g * c.n_lenc + enc_off + (size_t)(n0 + i_lo) * dims) * 32;   // first row of the run
+    auto issue = [&](int t) {                              // lane 0: sub-tile t -> stage t % NB
+        const int b = t % SSB_VS_NB;
+        const uint32_t bytes = (uint32_t)min((long long)SSB_VS_SUB, n_rows - (long long)t * SSB_VS_SUB) * 128u;
+        ssb_mbar_expect_tx(&wbar[warp][b], bytes);
+        ssb_bulk_g2s(ring + (size_t)b * SSB_VS_SUB * 32, eg + (size_t)t * SSB_VS_SUB * 32, bytes, &wbar[warp][b]);
+    };
+    if (lane == 0) {
+        for (int t = 0; t < SSB_VS_NB; ++t) ssb_mbar_init(&wbar[warp][t], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int t = 0; t < SSB_VS_NB && t < n_tiles; ++t) issue(t);
+    }
+    const float* vg = ssb_grp(c.vec, c.nv, g, lane);
+    ssb_stage_rows(xs, vg, in_row0, dims, dpad, warp, NW, lane);
+    for (int m = warp; m < jn_m; m += NW) us[m * 32 + lane] = vg[(size_t)(jn_row0 + m) * 32];
+    const float aL = __int_as_float(d[15]) * vg[(size_t)voja_row * 32];
+    __syncthreads();
+    float* sp = ssb_grp(c.st, c.nn, g, lane) + (size_t)(state0 + n0) * 32;
+    float* ag = ssb_grp(c.act, c.n_act, g, lane) + (size_t)(act0 + n0) * 32;
+    uint32_t phases = 0;
+    int t_cur = 0, pos = 0, tile_rows = 0;                 // current sub-tile, next row inside it, rows it holds
+    const float* E = ring + lane;
+    if (n_tiles > 0) {
+        ssb_mbar_wait(&wbar[warp][0], 0);
+        phases ^= 1u;
+        tile_rows = (int)min((long long)SSB_VS_SUB, n_rows);
+    }
+    float sv_next = 0.f, bias_next = 0.f;
+    if (i_lo < i_hi) {
+        if (stateful) sv_next = __ldcs(sp + (size_t)i_lo * 32);
+        bias_next = __ldg(c.W + bias_off + n0 + i_lo);
+    }
+    for (int i = i_lo; i < i_hi; ++i) {
+        float sv = sv_next;
+        float J = bias_next;
+        if (i + 1 < i_hi) {
+            if (stateful) sv_next = __ldcs(sp + (size_t)(i + 1) * 32);
+            bias_next = __ldg(c.W + bias_off + n0 + i + 1);
+        }
+        for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + (n0 + i) * jn_m + m), us[m * 32 + lane], J);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int k = 0;
+        while (k < dims) {
+            if (pos == tile_rows) {                        // sub-tile consumed: refill its stage, move to the next one
+                __syncwarp();
+                if (lane == 0 && t_cur + SSB_VS_NB < n_tiles) issue(t_cur + SSB_VS_NB);
+                ++t_cur;
+                const int b = t_cur % SSB_VS_NB;
+                ssb_mbar_wait(&wbar[warp][b], (phases >> b) & 1u);
+                phases ^= 1u << b;
+                E = ring + (size_t)b * SSB_VS_SUB * 32 + lane;
+                pos = 0;
+                tile_rows = (int)min((long long)SSB_VS_SUB, n_rows - (long long)t_cur * SSB_VS_SUB);
+            }
+            const int seg = min(dims - k, tile_rows - pos);
+            const float* e = E + (size_t)pos * 32;
+            const float* x = xs + (size_t)k * 32 + lane;
+            int q = 0;
+            for (; q + 4 <= seg; q += 4) {
+                a0 = fmaf(e[(q + 0) * 32], x[(q + 0) * 32], a0);
+                a1 = fmaf(e[(q + 1) * 32], x[(q + 1) * 32], a1);
+                a2 = fmaf(e[(q + 2) * 32], x[(q + 2) * 32], a2);
+                a3 = fmaf(e[(q + 3) * 32], x[(q + 3) * 32], a3);
+            }
+            for (; q < seg; ++q) a0 = fmaf(e[q * 32], x[q * 32], a0);
+            k += seg;
+            pos += seg;
+        }
+        J += (a0 + a1) + (a2 + a3);
+        float out;
+        if (stateful) {
+            out = nt.fast ? ssb_lif_packed<true>(nt, J, sv) : ssb_lif_packed<false>(nt, J, sv);
+            __stcs(sp + (size_t)i * 32, sv);
+        } else {
+            out = ssb_rate(nt, J);
+        }
+        ag[(size_t)i * 32] = out;
+        const bool fired = out != 0.f;
+        const unsigned any_on = __ballot_sync(0xffffffffu, fired);
+        if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + n0 + i] = (int)any_on;
+        if (any_on) {                                      // Voja: only the lanes that spiked touch their words (L2 re-read)
+            const float sc = __ldg(c.W + scale_off + n0 + i);
+            float* Eg = eg + (size_t)(i - i_lo) * dims * 32 + lane;
+            for (int k0 = 0; k0 < dims; k0 += 8) {
+                float ev[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ev[u] = (fired && k0 + u < dims) ? __ldcg(Eg + (size_t)(k0 + u) * 32) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (fired && k0 + u < dims)
+                        Eg[(size_t)(k0 + u) * 32] = ev[u] + aL * (sc * (out * xs[(k0 + u) * 32 + lane]) - out * ev[u]);
+            }
+        }
+    }
+}

@@ -20,17 +20,16 @@
 // neuron is JP rows: float offset = (d_off + i * JP) * 32 + lane * JP + j.
 //   k_pes_hist   appends this step's term (ae from the materialised error rows, f = the trace the previous step read) and
 //                updates the activity traces; it runs AFTER the decode of its own step, which reads that term at its source
-//   k_pes_defer  the sparse decode.  CTA = (neuron chunk, trial group, tile of 32 output columns); a warp walks the flag
-//                words of its quarter of the chunk (bit t = trial t spiked, written by the ensemble kernel), and per spiking
-//                (neuron, trial) the lane of that trial loads 8 x 16 bytes and accumulates 32 outputs in registers; the
-//                column-tile-0 CTAs also accumulate the K history dot products f_s . a.  Lane = trial, so there is no
-//                cross-lane reduction; warps are added through shared memory, chunks through the partial arena, and the
-//                last CTA of a (decoder, group) adds the partials in chunk order and applies the history correction.
+//   k_pes_defer  the sparse decode.  CTA = (neuron chunk, 8 trials of a group, tile of 128 output columns); one warp per
+//                trial walks the flag words of the chunk (bit t = trial t spiked, written by the ensemble kernel) and, per
+//                spike of its trial, reads the contiguous weights with lanes = columns; the column-tile-0 CTAs also
+//                accumulate the K history dot products f_s . a (lane q = history slot q).  Chunks are combined through the
+//                partial arena; the last CTA of a (decoder, group) adds them in chunk order and applies the history terms.
 //   k_pes_fold   D_base += sum_s ae_s (x) f_s (when slot == K - 1, or when the host asks), then k_pes_clear zeroes the ae
 //                rows, so an empty history always contributes exactly 0
 // desc: n size_out d_off a_off act0 err_vec out_vec alpha_bits decay_bits onemdecay_bits n_chunks part_off counter0
 // hdesc per decoder: e_row0 f_row0 part_row0 counter0 (rows of the hist_e / hist_f / pes_part arenas)
-#define SSB_PES_JT 32          // output columns per k_pes_defer CTA
+#define SSB_PES_JT 128         // output columns per k_pes_defer CTA (4 per lane)
 #define SSB_PES_FT 64          // output columns per k_pes_fold shared-memory tile
 
 __host__ __device__ __forceinline__ int ssb_pes_jp(int size_out) { return (size_out + 3) & ~3; }
@@ -65,123 +64,105 @@ __global__ void __launch_bounds__(128) k_pes_hist(SsbCtx c, SsbPesDefer h, const
     }
 }
 
-// Sparse decode of up to U spiking neurons at a time: registers w[U][JT] are all in flight before the first FMA.
+// Sparse decode.  One WARP per trial (8 trials = 8 warps per CTA), lanes = output columns: the JP weights one spike of one
+// trial needs are contiguous, so a spike is one coalesced read per 32 columns and every lane of the warp works (with
+// lane = trial only the ~3 lanes whose trial spiked would).  The CTA stages the flag words of its neuron chunk in shared
+// memory; a warp enumerates the set bits of its trial (ballot over 32 neurons at a time) and keeps up to U spikes in flight.
+// grid (n_chunks * 4 trial octets, G, decoders * column tiles of SSB_PES_JT) x 256
 template <int K>
-__global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
+__global__ void __launch_bounds__(256) k_pes_defer(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
                                                      const int* __restrict__ hdesc, int n_jt_max, int i_rel) {
-    __shared__ float red[4][SSB_PES_JT + 8][32];
+    extern __shared__ int sflag[];                       // flag words of the chunk
+    __shared__ float red[SSB_PES_JT + 8][8];             // [column | history slot][trial of the octet]
     __shared__ int flag;
     const int item = blockIdx.z / n_jt_max, jt = blockIdx.z - item * n_jt_max;
     const int* d = desc + item * 13;
     const int* hd = hdesc + item * 4;
     const int n = d[0], size_out = d[1], d_off = d[2], a_off = d[3], act0 = d[4], err_vec = d[5], out_vec = d[6];
-    const int n_chunks = d[10], chunk = blockIdx.x;
+    const int n_chunks = d[10], chunk = blockIdx.x >> 2, oct = blockIdx.x & 3;
     const int JP = ssb_pes_jp(size_out);
     const int n_jt = (JP + SSB_PES_JT - 1) / SSB_PES_JT;
     if (jt >= n_jt || chunk >= n_chunks) return;
     const int j0 = jt * SSB_PES_JT;
-    const int jw = min(SSB_PES_JT, JP - j0);                 // columns of this tile (a multiple of 4)
     const bool dots = jt == 0;
     const int per = (n + n_chunks - 1) / n_chunks;
     const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.y;
+    const int t = oct * 8 + warp;                         // this warp's trial inside the group
     const SsbStep s = ssb_step(c, i_rel);
     const int slot = (int)(s.step % K);       // this step's term is not in the history yet: it is read at its source
-    const float* __restrict__ ap = ssb_grp(c.act, c.n_act, g, lane) + (size_t)act0 * 32;
     const int* __restrict__ fl = c.aflag + (size_t)g * c.n_act + act0;
-    // this lane's trial: decoder block of neuron i starts at dl + i * JP * 32
-    const float* __restrict__ dl = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)lane * JP + j0;
-    const float* __restrict__ hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
-    const float* __restrict__ fcur = ssb_grp(c.afilt, 2 * c.n_afilt, g, lane) + ((size_t)(1 - s.odd) * c.n_afilt + a_off) * 32;
-    float acc[SSB_PES_JT], dsum_l[K];
+    for (int i = i_lo + (int)threadIdx.x; i < i_hi; i += 256) sflag[i - i_lo] = __ldg(fl + i);
+    __syncthreads();
+    const float* __restrict__ ap = c.act + ((size_t)g * c.n_act + act0) * 32 + t;
+    const float* __restrict__ dl = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)t * JP + j0 + lane;
+    const float* __restrict__ hf = h.hist_f + ((size_t)g * h.rows_f + hd[1]) * 32 + t;
+    const float* __restrict__ fcur = c.afilt + ((size_t)g * 2 * c.n_afilt + (size_t)(1 - s.odd) * c.n_afilt + a_off) * 32 + t;
+    constexpr int NC = SSB_PES_JT / 32;                   // columns per lane
+    float acc[NC], dot = 0.f;
 #pragma unroll
-    for (int j = 0; j < SSB_PES_JT; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int q = 0; q < K; ++q) dsum_l[q] = 0.f;
-    const int qn = (i_hi - i_lo + 3) >> 2;
-    const int w_lo = i_lo + warp * qn, w_hi = min(i_hi, w_lo + qn);
-    constexpr int U = 4;
-    for (int base = w_lo; base < w_hi; base += 32) {
-        const int myflag = (base + lane < w_hi) ? __ldg(fl + base + lane) : 0;
-        unsigned m = __ballot_sync(0xffffffffu, myflag != 0);
-        while (m) {
+    for (int q = 0; q < NC; ++q) acc[q] = 0.f;
+    constexpr int U = 8;
+    for (int base = i_lo; base < i_hi; base += 32) {
+        const int fw = (base + lane < i_hi) ? sflag[base + lane - i_lo] : 0;
+        unsigned m = __ballot_sync(0xffffffffu, (fw >> t) & 1);
+        while (m) {                                        // warp-uniform: up to U spikes of this trial in flight
             int idx[U];
-            unsigned bits[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 idx[u] = -1;
-                int src = 0;
                 if (m) {
-                    src = __ffs(m) - 1;
-                    idx[u] = base + src;
+                    idx[u] = base + __ffs(m) - 1;
                     m &= m - 1;
                 }
-                bits[u] = (unsigned)__shfl_sync(0xffffffffu, myflag, src);
             }
-            float a[U];
-            float4 w[U][SSB_PES_JT / 4];
-            float f[U][K];
+            float a[U], w[U][NC], f[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const bool mine = idx[u] >= 0 && ((bits[u] >> lane) & 1u);
-                const size_t ni = (size_t)(idx[u] >= 0 ? idx[u] : 0);
-                a[u] = mine ? ap[ni * 32] : 0.f;
-                const float4* src4 = reinterpret_cast<const float4*>(dl + ni * JP * 32);
+                const bool on = idx[u] >= 0;
+                const size_t ni = (size_t)(on ? idx[u] : 0);
+                a[u] = on ? __ldg(ap + ni * 32) : 0.f;
 #pragma unroll
-                for (int q4 = 0; q4 < SSB_PES_JT / 4; ++q4)
-                    w[u][q4] = (mine && 4 * q4 < jw) ? __ldcs(src4 + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (dots) {
-#pragma unroll
-                    for (int q = 0; q < K; ++q)
-                        f[u][q] = mine ? ((q == slot) ? fcur[ni * 32] : hf[((size_t)q * n + ni) * 32]) : 0.f;
-                }
+                for (int q = 0; q < NC; ++q)
+                    w[u][q] = (on && j0 + q * 32 + lane < JP) ? __ldcs(dl + ni * JP * 32 + q * 32) : 0.f;
+                f[u] = 0.f;
+                if (dots && on && lane < K) f[u] = (lane == slot) ? fcur[ni * 32] : hf[((size_t)lane * n + ni) * 32];
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
 #pragma unroll
-                for (int q4 = 0; q4 < SSB_PES_JT / 4; ++q4) {
-                    acc[4 * q4 + 0] = fmaf(w[u][q4].x, a[u], acc[4 * q4 + 0]);
-                    acc[4 * q4 + 1] = fmaf(w[u][q4].y, a[u], acc[4 * q4 + 1]);
-                    acc[4 * q4 + 2] = fmaf(w[u][q4].z, a[u], acc[4 * q4 + 2]);
-                    acc[4 * q4 + 3] = fmaf(w[u][q4].w, a[u], acc[4 * q4 + 3]);
-                }
-                if (dots) {
-#pragma unroll
-                    for (int q = 0; q < K; ++q) dsum_l[q] = fmaf(f[u][q], a[u], dsum_l[q]);
-                }
+                for (int q = 0; q < NC; ++q) acc[q] = fmaf(w[u][q], a[u], acc[q]);
+                dot = fmaf(f[u], a[u], dot);
             }
         }
     }
-    // CTA partial: ((w0 + w1) + (w2 + w3)) per row, parked in the partial arena [chunk][size_out + K]
+    // CTA partial of the 8 trials -> partial arena [chunk][size_out + K] (32-byte runs: 8 consecutive trials per row)
 #pragma unroll
-    for (int j = 0; j < SSB_PES_JT; ++j) red[warp][j][lane] = acc[j];
-#pragma unroll
-    for (int q = 0; q < K; ++q) red[warp][SSB_PES_JT + q][lane] = dsum_l[q];
+    for (int q = 0; q < NC; ++q) red[q * 32 + lane][warp] = acc[q];
+    if (lane < 8) red[SSB_PES_JT + lane][warp] = dot;
     __syncthreads();
     const int prow = size_out + K;
-    float* pg = ssb_grp(h.part, h.rows_p, g, lane) + (size_t)hd[2] * 32;
-    for (int r = warp; r < SSB_PES_JT + (dots ? K : 0); r += 4) {
+    float* pgo = h.part + ((size_t)g * h.rows_p + hd[2]) * 32 + oct * 8;
+    for (int r = threadIdx.x >> 3; r < SSB_PES_JT + (dots ? K : 0); r += 32) {
         const bool is_dot = r >= SSB_PES_JT;
         const int row = is_dot ? size_out + (r - SSB_PES_JT) : j0 + r;
-        if (is_dot || row < size_out) {
-            const float t = (red[0][r][lane] + red[1][r][lane]) + (red[2][r][lane] + red[3][r][lane]);
-            pg[(size_t)(chunk * prow + row) * 32] = t;
-        }
+        if (is_dot || row < size_out) pgo[(size_t)(chunk * prow + row) * 32 + (threadIdx.x & 7)] = red[r][threadIdx.x & 7];
     }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         int* cnt_p = h.counters + hd[3] * c.G + g;
         const int old = atomicAdd(cnt_p, 1);
-        const int last = old == n_jt * n_chunks - 1;
+        const int last = old == n_jt * n_chunks * 4 - 1;
         if (last) *cnt_p = 0;
         flag = last;
     }
     __syncthreads();
     if (!flag) return;
     __threadfence();
-    // the last CTA of this (decoder, group): history dot products, then every output row
+    // the last CTA of this (decoder, group), lane = trial again: history dot products, then every output row
+    float* pg = ssb_grp(h.part, h.rows_p, g, lane) + (size_t)hd[2] * 32;
     float dsum[K];
 #pragma unroll
     for (int q = 0; q < K; ++q) dsum[q] = 0.f;
@@ -195,16 +176,16 @@ __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
     const float* __restrict__ he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
     float* vg = ssb_grp(c.vec, c.nv, g, lane);
     const float alpha = s.step > 0 ? __int_as_float(d[7]) : 0.f;
-    for (int jb = warp * 8; jb < size_out; jb += 32) {   // each warp takes 8 consecutive output rows at a time
-        float t[8];
+    for (int jb = warp * 8; jb < size_out; jb += 64) {   // each warp takes 8 consecutive output rows at a time
+        float tt[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = 0.f;
+        for (int u = 0; u < 8; ++u) tt[u] = 0.f;
         for (int ck = 0; ck < n_chunks; ++ck) {
             float v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = (jb + u < size_out) ? __ldcg(pg + (size_t)(ck * prow + jb + u) * 32) : 0.f;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] += v[u];
+            for (int u = 0; u < 8; ++u) tt[u] += v[u];
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -213,7 +194,7 @@ __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
 #pragma unroll
                 for (int q = 0; q < K; ++q)
                     e[q] = (q == slot) ? alpha * vg[(size_t)(err_vec + jb + u) * 32] : he[(size_t)(q * size_out + jb + u) * 32];
-                float r = t[u];
+                float r = tt[u];
 #pragma unroll
                 for (int q = 0; q < K; ++q) r = fmaf(e[q], dsum[q], r);
                 vg[(size_t)(out_vec + jb + u) * 32] = r;
@@ -222,13 +203,16 @@ __global__ void __launch_bounds__(128) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
     }
 }
 
-// launched by the host after the step whose slot is K - 1, and before any read-back of the decoders.
-// CTA = (neuron chunk, trial group, decoder); the ae rows of a tile of SSB_PES_FT output columns sit in shared memory
-// ([K][FT][32], lane-interleaved: conflict-free), each warp takes a neuron, each lane its own trial's contiguous weights.
+// launched by the host after the step whose slot is K - 1, and before any read-back of the decoders:
+//   D_base[i][t][j] += sum_q ae_q[j][t] * f_q[i][t].
+// CTA = (neuron chunk, trial group, decoder), 8 warps.  The ae rows of the group are staged in shared memory as
+// [q][trial][JP] (conflict-free when lanes walk j); a warp takes (neuron, pair of trials): its lanes are the 16-byte pieces
+// of the two trials' contiguous weights, so the read-modify-write is fully coalesced.  Output widths above SSB_PES_FT columns
+// are processed in column tiles.
 template <int K>
-__global__ void __launch_bounds__(128) k_pes_fold(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
+__global__ void __launch_bounds__(256) k_pes_fold(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
                                                     const int* __restrict__ hdesc, int max_chunks, int i_rel, int force) {
-    extern __shared__ __align__(16) float sm[];          // [K][SSB_PES_FT][32]
+    extern __shared__ __align__(16) float sm[];          // [K][32 trials][SSB_PES_FT]
     const int item = blockIdx.z, chunk = blockIdx.x;
     const int* d = desc + item * 13;
     const int* hd = hdesc + item * 4;
@@ -239,39 +223,42 @@ __global__ void __launch_bounds__(128) k_pes_fold(SsbCtx c, SsbPesDefer h, const
     if (i_lo >= i_hi) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.y;
-    float* __restrict__ dl = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)lane * JP;
-    const float* __restrict__ hf = ssb_grp(h.hist_f, h.rows_f, g, lane) + (size_t)hd[1] * 32;
-    const float* __restrict__ he = ssb_grp(h.hist_e, h.rows_e, g, lane) + (size_t)hd[0] * 32;
+    float* __restrict__ dg = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32;
+    const float* __restrict__ hf = h.hist_f + ((size_t)g * h.rows_f + hd[1]) * 32;
+    const float* __restrict__ he = h.hist_e + ((size_t)g * h.rows_e + hd[0]) * 32;
     for (int j0 = 0; j0 < JP; j0 += SSB_PES_FT) {
-        const int jw = min(SSB_PES_FT, JP - j0);
+        const int jw = min(SSB_PES_FT, JP - j0);          // columns of this tile (multiple of 4)
+        const int nq4 = jw >> 2;                          // 16-byte pieces per trial
         __syncthreads();
-        for (int r = warp; r < K * SSB_PES_FT; r += 4) {
-            const int q = r / SSB_PES_FT, j = r - q * SSB_PES_FT;
-            sm[r * 32 + lane] = (j0 + j < size_out) ? he[(size_t)(q * size_out + j0 + j) * 32] : 0.f;
+        for (int r = warp; r < K * jw; r += 8) {          // he row (q, j) -> sm[q][trial = lane][j]
+            const int q = r / jw, j = r - q * jw;
+            sm[((size_t)q * 32 + lane) * SSB_PES_FT + j] = (j0 + j < size_out) ? he[(size_t)(q * size_out + j0 + j) * 32 + lane] : 0.f;
         }
         __syncthreads();
-        for (int i = i_lo + warp; i < i_hi; i += 4) {
-            float fv[K];
+        const int tpw = 32 / nq4 > 0 ? 32 / nq4 : 1;      // trials per warp task (2 at d = 55)
+        const int active = tpw * nq4;
+        const int tasks_per_neuron = (32 + tpw - 1) / tpw;
+        const int n_tasks = (i_hi - i_lo) * tasks_per_neuron;
+        for (int task = warp; task < n_tasks; task += 8) {
+            const int i = i_lo + task / tasks_per_neuron;
+            const int t = (task % tasks_per_neuron) * tpw + lane / nq4;
+            const int q4 = lane % nq4;
+            if (lane < active && t < 32) {
+                float4* wp = reinterpret_cast<float4*>(dg + (size_t)i * JP * 32 + (size_t)t * JP + j0) + q4;
+                float4 w = __ldcs(wp);
+                float fv[K];
 #pragma unroll
-            for (int q = 0; q < K; ++q) fv[q] = hf[((size_t)q * n + i) * 32];
-            float4* w4 = reinterpret_cast<float4*>(dl + (size_t)i * JP * 32 + j0);
-            float4 w[SSB_PES_FT / 4];
+                for (int q = 0; q < K; ++q) fv[q] = __ldg(hf + ((size_t)q * n + i) * 32 + t);
 #pragma unroll
-            for (int q4 = 0; q4 < SSB_PES_FT / 4; ++q4) w[q4] = (4 * q4 < jw) ? __ldcs(w4 + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < K; ++q) {
-                const float* aq = sm + (size_t)q * SSB_PES_FT * 32 + lane;
-#pragma unroll
-                for (int q4 = 0; q4 < SSB_PES_FT / 4; ++q4) {
-                    w[q4].x = fmaf(aq[(4 * q4 + 0) * 32], fv[q], w[q4].x);
-                    w[q4].y = fmaf(aq[(4 * q4 + 1) * 32], fv[q], w[q4].y);
-                    w[q4].z = fmaf(aq[(4 * q4 + 2) * 32], fv[q], w[q4].z);
-                    w[q4].w = fmaf(aq[(4 * q4 + 3) * 32], fv[q], w[q4].w);
+                for (int q = 0; q < K; ++q) {
+                    const float4 e = *reinterpret_cast<const float4*>(sm + ((size_t)q * 32 + t) * SSB_PES_FT + 4 * q4);
+                    w.x = fmaf(e.x, fv[q], w.x);
+                    w.y = fmaf(e.y, fv[q], w.y);
+                    w.z = fmaf(e.z, fv[q], w.z);
+                    w.w = fmaf(e.w, fv[q], w.w);
                 }
+                __stcs(wp, w);
             }
-#pragma unroll
-            for (int q4 = 0; q4 < SSB_PES_FT / 4; ++q4)
-                if (4 * q4 < jw) __stcs(w4 + q4, w[q4]);
         }
     }
 }
