@@ -174,6 +174,16 @@ struct ssb_sim {
     long long syn_step0 = 0;
     int syn_steps = 0;
     SsbPesDefer pes_h = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};   // deferred PES history (K = 0: off)
+    // K-blocked tensor-core encode of static wide ensembles with very wide inputs (k_wide_static_tck), per level
+    struct TckLevel {
+        bool on = false;
+        SsbTckItems items;
+        int* d_desc6 = nullptr;
+        int n_kb = 0, n_tiles_max = 0;
+        long long xt_stride = 0;
+    };
+    std::vector<TckLevel> tck_levels;
+    float *d_etk = nullptr, *d_xtk = nullptr;
     bool pes_fused = false;                 // the sparse decode runs inside k_wide_voja (every PES pre-ensemble is a Voja ensemble)
     std::vector<int> pes_of_big;            // wide-ensemble descriptor -> PES descriptor it feeds, or -1
     int* d_pes_hdesc = nullptr;
@@ -395,8 +405,8 @@ int build_scan_tiles_k(const float* S32, int G, int dpad, int n_groups, CleanupD
 
 void launch_scan_tck(cudaStream_t st, bool csr, const SsbCtx& c, const int* desc, const CleanupDev& cd, int n_groups) {
     const int quads = (n_groups + 3) / 4;
-    if (csr) k_scan_xtiles<true><<<dim3(cd.n_kb, quads), 128, 0, st>>>(c, desc, cd.cx, cd.xt, cd.n_kb, n_groups);
-    else k_scan_xtiles<false><<<dim3(cd.n_kb, quads), 128, 0, st>>>(c, desc, cd.cx, cd.xt, cd.n_kb, n_groups);
+    if (csr) k_scan_xtiles<true><<<dim3(cd.n_kb, quads), 128, 0, st>>>(c, desc, cd.cx, cd.xt, cd.n_kb, n_groups, 0);
+    else k_scan_xtiles<false><<<dim3(cd.n_kb, quads), 128, 0, st>>>(c, desc, cd.cx, cd.xt, cd.n_kb, n_groups, 0);
     const size_t smem = (size_t)SSB_SCK_NST * 4 * SSB_SCK_PART * sizeof(float);
     k_cleanup_scan_tck<<<dim3(cd.n_chunks, quads), 320, smem, st>>>(desc, cd.stck, cd.xt, cd.pval, cd.pidx, cd.n_kb, cd.n_tiles,
                                                                   n_groups, cd.n_chunks * SSB_TOPK * 2);
@@ -566,8 +576,96 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
 
 bool launch_wide_tc(ssb_sim* s, cudaStream_t st, const int* stage, bool dry);
 
+// Static wide ensembles whose input is wider than the register-specialised / whole-K tensor-core kernels take (d = 649):
+// encoder tiles per (128-neuron tile, 32-column K block), one X tile buffer per ensemble.  A level is served by
+// k_wide_static_tck only if every static wide ensemble of the level qualifies.
+int build_encode_tiles_k(ssb_sim* s) {
+    s->tck_levels.assign(s->n_levels, ssb_sim::TckLevel());
+    const char* e = getenv("SSB_ENCODE");
+    if (e && std::string(e) == "ffma") return 0;
+    const float* hW = reinterpret_cast<const float*>(s->arrays["weights"].bytes.data());
+    const int quads = (s->n_groups + 3) / 4;
+    std::vector<float> etk;
+    size_t xt_floats = 0;
+    for (int lvl = 0; lvl < s->n_levels; ++lvl) {
+        const int* st = &s->h_stages[lvl * 12];
+        ssb_sim::TckLevel& L = s->tck_levels[lvl];
+        std::vector<int> idx;
+        bool ok = true;
+        int dpad0 = 0;
+        for (int i = 0; i < st[3]; ++i) {
+            const int b = st[2] + i;
+            const int* d = &s->h_big[b * 16];
+            if (d[9] & 1) continue;                               // Voja ensembles keep per-trial encoders
+            if (d[2] <= 104 || d[11] > 4 || (dpad0 && d[2] != dpad0)) ok = false;
+            dpad0 = d[2];
+            idx.push_back(b);
+        }
+        if (!ok || idx.empty() || idx.size() > 15) continue;
+        L.n_kb = (dpad0 + SSB_SCK_KB - 1) / SSB_SCK_KB;
+        L.xt_stride = (long long)quads * L.n_kb * 2 * SSB_SCK_PART;
+        L.items.n = (int)idx.size();
+        std::vector<int> desc6;
+        for (size_t k = 0; k < idx.size(); ++k) {
+            const int* d = &s->h_big[idx[k] * 16];
+            const int n = d[0], dims = d[1], dpad = d[2], enc_off = d[5];
+            const int n_tiles = (n + 127) / 128;
+            L.n_tiles_max = std::max(L.n_tiles_max, n_tiles);
+            L.items.idx[k] = idx[k];
+            L.items.e_off[k] = (long long)etk.size();
+            L.items.x_off[k] = (long long)(xt_floats + k * L.xt_stride);
+            etk.resize(etk.size() + (size_t)n_tiles * L.n_kb * 2 * SSB_SCK_PART, 0.f);
+            float* base = &etk[L.items.e_off[k]];
+            for (int nn = 0; nn < n; ++nn) {
+                const int tile = nn / 128, r = nn % 128;
+                for (int kk0 = 0; kk0 < dpad; ++kk0) {
+                    const int kb = kk0 / SSB_SCK_KB, kk = kk0 % SSB_SCK_KB;
+                    float* hi = base + ((size_t)tile * L.n_kb + kb) * 2 * SSB_SCK_PART;
+                    float* lo = hi + SSB_SCK_PART;
+                    const float x = hW[(size_t)enc_off + (size_t)nn * dpad + kk0];
+                    const float h = ssb_tf32_round(x);
+                    const size_t off = ((size_t)(kk / 4) * 16 + r / 8) * 32 + (r % 8) * 4 + kk % 4;
+                    hi[off] = h;
+                    lo[off] = ssb_tf32_round(x - h);
+                }
+            }
+            desc6.insert(desc6.end(), {n, dims, dpad, 0, d[7], 0});
+        }
+        xt_floats += idx.size() * (size_t)L.xt_stride;
+        SSB_CUDA(cudaMalloc((void**)&L.d_desc6, desc6.size() * sizeof(int)));
+        SSB_CUDA(cudaMemcpy(L.d_desc6, desc6.data(), desc6.size() * sizeof(int), cudaMemcpyHostToDevice));
+        L.on = true;
+    }
+    if (etk.empty()) return 0;
+    SSB_CUDA(cudaMalloc((void**)&s->d_etk, etk.size() * sizeof(float)));
+    SSB_CUDA(cudaMemcpy(s->d_etk, etk.data(), etk.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SSB_CUDA(cudaMalloc((void**)&s->d_xtk, std::max<size_t>(xt_floats, 8) * sizeof(float)));
+    SSB_CUDA(cudaMemset(s->d_xtk, 0, std::max<size_t>(xt_floats, 8) * sizeof(float)));
+    SSB_CUDA(cudaFuncSetAttribute(k_wide_static_tck, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SSB_SCK_NST * 4 * SSB_SCK_PART * sizeof(float))));
+    return 0;
+}
+
+bool launch_wide_tck(ssb_sim* s, cudaStream_t st, const int* stage, bool dry) {
+    if (!s->d_etk) return false;
+    const int lvl = (int)((stage - s->h_stages.data()) / 12);
+    if (lvl < 0 || lvl >= (int)s->tck_levels.size() || !s->tck_levels[lvl].on) return false;
+    if (dry) return true;
+    const ssb_sim::TckLevel& L = s->tck_levels[lvl];
+    const int quads = (s->n_groups + 3) / 4;
+    k_scan_xtiles<true><<<dim3(L.n_kb, quads, L.items.n), 128, 0, st>>>(s->ctx, L.d_desc6, nullptr, s->d_xtk + L.items.x_off[0],
+                                                                       L.n_kb, s->n_groups, L.xt_stride);
+    const int n_chunks = std::max(1, std::min(L.n_tiles_max, 148 / std::max(1, quads * L.items.n)));
+    const size_t smem = (size_t)SSB_SCK_NST * 4 * SSB_SCK_PART * sizeof(float);
+    k_wide_static_tck<<<dim3(n_chunks, quads, L.items.n), 320, smem, st>>>(s->ctx, s->d_big, L.items, s->d_etk, s->d_xtk, L.n_kb);
+    s->kind_launches[K_EXTRA]++;
+    s->total_launches++;
+    return true;
+}
+
 void launch_wide(ssb_sim* s, cudaStream_t st, const int* stage, bool voja, int i_rel, bool dry = false) {
     if (!voja && launch_wide_tc(s, st, stage, dry)) return;
+    if (!voja && launch_wide_tck(s, st, stage, dry)) return;
     launch_wide_class<56>(s, st, stage, voja, 0, i_rel, dry);
     launch_wide_class<100>(s, st, stage, voja, 1, i_rel, dry);
     launch_wide_class<0>(s, st, stage, voja, 2, i_rel, dry);
@@ -613,8 +711,11 @@ int setup_pes_defer(ssb_sim* s) {
     // neuron chunks of the sparse decode: enough CTAs (chunks x groups x column tiles) for ~3 resident CTAs per SM
     int tiles_total = 0;
     for (int i = 0; i < s->n_pes; ++i) tiles_total += (ssb_pes_jp(s->h_pes[i * 13 + 1]) + SSB_PES_JT - 1) / SSB_PES_JT;
-    // CTAs = chunks x 4 trial octets x groups x column tiles, 8 light warps each: aim at ~6 CTAs per SM
-    int chunks = (148 * 6) / std::max(1, 4 * tiles_total * s->n_groups);
+    // CTAs = chunks x 4 trial octets x groups x column tiles: one wave of resident CTAs (every warp then walks a long
+    // neuron range, whose spikes it compacts first, so the dependent round trips stay few)
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pes_defer<8>, 256, 4096);
+    int chunks = (148 * std::max(1, occ)) / std::max(1, 4 * tiles_total * s->n_groups);
     chunks = std::max(1, std::min(chunks, 32));
     if (const char* e = getenv("SSB_PES_CHUNKS")) chunks = std::max(1, std::min(atoi(e), 64));
     std::vector<int> hd;
@@ -677,7 +778,7 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
     if (!s->pes_fused) {     // (fused: the sparse decode already ran inside the Voja ensemble kernel of this step)
         LaunchTimer t(s, K_PES, st);
         dim3 dgrid(max_chunks * 4, s->n_groups, s->n_pes * max_jt);
-        const size_t fsmem = (size_t)max_per * sizeof(int);                   // flag words of one neuron chunk
+        const size_t fsmem = (size_t)max_per * 9 * sizeof(int);               // flag words of one neuron chunk + 8 spike lists
         if (s->pes_h.K == 4) k_pes_defer<4><<<dgrid, 256, fsmem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
         else k_pes_defer<8><<<dgrid, 256, fsmem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, max_jt, i_rel);
     }
@@ -1304,6 +1405,7 @@ int ssb_finalize(ssb_sim* s) {
     if (int rc = build_lin_program(s)) return rc;
     if (int rc = build_decode_tiles(s)) return rc;
     if (int rc = build_encode_tiles(s)) return rc;
+    if (int rc = build_encode_tiles_k(s)) return rc;
     s->levels.assign(s->n_levels, LevelInfo());
     for (int lvl = 0; lvl < s->n_levels; ++lvl) {
         const int* st = &s->h_stages[lvl * 12];
@@ -1801,7 +1903,7 @@ void ssb_destroy(ssb_sim* s) {
     void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
                     s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_enc_t, s->d_enc_t_off, s->pes_h.hist_e, s->pes_h.hist_f, s->pes_h.part,
                     s->pes_h.counters, s->d_pes_hdesc, s->aflag, s->syn_path, s->syn_vel, s->syn_lm, s->syn_phases, s->syn_lmsp,
-                    s->syn_cos, s->syn_sin, s->syn_idx, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->syn_cos, s->syn_sin, s->syn_idx, s->d_etk, s->d_xtk, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
                     s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1813,6 +1915,8 @@ void ssb_destroy(ssb_sim* s) {
         if (cd.stck) cudaFree(cd.stck);
         if (cd.xt) cudaFree(cd.xt);
     }
+    for (auto& L : s->tck_levels)
+        if (L.d_desc6) cudaFree(L.d_desc6);
     if (s->step_graph) cudaGraphExecDestroy(s->step_graph);
     for (auto e : s->dep_pool) cudaEventDestroy(e);
     for (auto e : s->io_events) cudaEventDestroy(e);

@@ -505,7 +505,11 @@ k_cleanup_pick(int dims, int dpad, int ncand, const float* __restrict__ cx, cons
 // grid (n_kb, trial blocks) x 128: thread = one trial (row of the A tile), 32 columns.
 template <bool CSR_INPUT>
 __global__ void __launch_bounds__(128)
-k_scan_xtiles(SsbCtx c, const int* __restrict__ d, float* __restrict__ cx, float* __restrict__ Xt, int n_kb, int n_groups) {
+k_scan_xtiles(SsbCtx c, const int* __restrict__ d0, float* __restrict__ cx, float* __restrict__ Xt0, int n_kb, int n_groups,
+              long long z_stride) {
+    // blockIdx.z: further (desc, tile buffer) pairs of one launch (the wide-ensemble encode tiles several inputs at once)
+    const int* d = d0 + blockIdx.z * 6;
+    float* Xt = Xt0 + (size_t)blockIdx.z * z_stride;
     const int dims = d[1], dpad = d[2], in_row0 = d[4];
     const int lane = threadIdx.x & 31, quad = threadIdx.x >> 5;
     const int kb = blockIdx.x, tb = blockIdx.y;
@@ -514,7 +518,7 @@ k_scan_xtiles(SsbCtx c, const int* __restrict__ d, float* __restrict__ cx, float
     const int g = live ? group : 0;
     const int r = quad * 32 + lane;
     const float* vg = ssb_grp(c.vec, c.nv, g, lane);
-    float* cxg = cx + ((size_t)g * dpad) * 32 + lane;
+    float* cxg = cx + ((size_t)g * dpad) * 32 + lane;        // (cx == nullptr: no query copy wanted, CSR input only)
     const float* src = CSR_INPUT ? vg + (size_t)in_row0 * 32 : cxg;
     float* a_hi = Xt + ((size_t)tb * n_kb + kb) * 2 * SSB_SCK_PART + (r >> 3) * 32 + (r & 7) * 4;
     float* a_lo = a_hi + SSB_SCK_PART;
@@ -536,7 +540,7 @@ k_scan_xtiles(SsbCtx c, const int* __restrict__ d, float* __restrict__ cx, float
         *reinterpret_cast<float4*>(a_hi + (size_t)q * 16 * 32) = hi;
         *reinterpret_cast<float4*>(a_lo + (size_t)q * 16 * 32) = lo;
     }
-    if (CSR_INPUT && live) {                     // the query copy k_cleanup_pick re-scores near-ties with
+    if (CSR_INPUT && live && cx != nullptr) {    // the query copy k_cleanup_pick re-scores near-ties with
 #pragma unroll
         for (int e = 0; e < SSB_SCK_KB; ++e)
             if (k0 + e < dpad) cxg[(size_t)(k0 + e) * 32] = x[e];

@@ -5,7 +5,8 @@
 //   ssb_ens_wide.cuh   k_wide_static, k_wide_static_tc, k_wide_voja
 //   ssb_decode.cuh     k_decode, k_decode_tc
 //   ssb_pes.cuh        k_pes, k_pes_hist, k_pes_defer, k_pes_fold, k_pes_clear
-//   ssb_cleanup.cuh    k_cleanup_scan, k_cleanup_scan_tc, k_cleanup_pick, k_gate
+//   ssb_cleanup.cuh    k_cleanup_scan, k_cleanup_scan_tc, k_scan_xtiles, k_cleanup_scan_tck, k_cleanup_pick, k_gate
+//   ssb_ens_wide_tck.cuh  k_wide_static_tck
 //   ssb_lin.cuh        k_lin, k_advance
 //   ssb_ssp.cuh        k_ssp_encode, k_decode_prep
 #pragma once
@@ -16,5 +17,6 @@
 #include "ssb_decode.cuh"
 #include "ssb_pes.cuh"
 #include "ssb_cleanup.cuh"
+#include "ssb_ens_wide_tck.cuh"
 #include "ssb_lin.cuh"
 #include "ssb_ssp.cuh"

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) k_pes_hist(SsbCtx c, SsbPesDefer h, const
 template <int K>
 __global__ void __launch_bounds__(256) k_pes_defer(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
                                                      const int* __restrict__ hdesc, int n_jt_max, int i_rel) {
-    extern __shared__ int sflag[];                       // flag words of the chunk
+    extern __shared__ int sflag[];                       // [per] flag words of the chunk | [8 warps][per] spike lists
     __shared__ float red[SSB_PES_JT + 8][8];             // [column | history slot][trial of the octet]
     __shared__ int flag;
     const int item = blockIdx.z / n_jt_max, jt = blockIdx.z - item * n_jt_max;
@@ -103,38 +103,38 @@ __global__ void __launch_bounds__(256) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
     float acc[NC], dot = 0.f;
 #pragma unroll
     for (int q = 0; q < NC; ++q) acc[q] = 0.f;
-    constexpr int U = 8;
+    // phase 1: the neurons of the chunk where THIS trial spiked, compacted into a list (flags are in shared memory, so this
+    // costs no memory round trip); phase 2: the list in batches of U with every load of a batch in flight - the number of
+    // dependent round trips is spikes / U instead of one per 32 neurons
+    int* list = sflag + per + warp * per;
+    int cnt = 0;
     for (int base = i_lo; base < i_hi; base += 32) {
         const int fw = (base + lane < i_hi) ? sflag[base + lane - i_lo] : 0;
-        unsigned m = __ballot_sync(0xffffffffu, (fw >> t) & 1);
-        while (m) {                                        // warp-uniform: up to U spikes of this trial in flight
-            int idx[U];
+        const bool on = (fw >> t) & 1;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) list[cnt + __popc(m & ((1u << lane) - 1u))] = base + lane;
+        cnt += __popc(m);
+    }
+    __syncwarp();
+    constexpr int U = 8;
+    for (int s0 = 0; s0 < cnt; s0 += U) {
+        float a[U], w[U][NC], f[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                idx[u] = -1;
-                if (m) {
-                    idx[u] = base + __ffs(m) - 1;
-                    m &= m - 1;
-                }
-            }
-            float a[U], w[U][NC], f[U];
+        for (int u = 0; u < U; ++u) {
+            const bool on = s0 + u < cnt;
+            const size_t ni = (size_t)(on ? list[s0 + u] : i_lo);
+            a[u] = on ? __ldg(ap + ni * 32) : 0.f;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool on = idx[u] >= 0;
-                const size_t ni = (size_t)(on ? idx[u] : 0);
-                a[u] = on ? __ldg(ap + ni * 32) : 0.f;
+            for (int q = 0; q < NC; ++q)
+                w[u][q] = (on && j0 + q * 32 + lane < JP) ? __ldcs(dl + ni * JP * 32 + q * 32) : 0.f;
+            f[u] = 0.f;
+            if (dots && on && lane < K) f[u] = (lane == slot) ? fcur[ni * 32] : hf[((size_t)lane * n + ni) * 32];
+        }
 #pragma unroll
-                for (int q = 0; q < NC; ++q)
-                    w[u][q] = (on && j0 + q * 32 + lane < JP) ? __ldcs(dl + ni * JP * 32 + q * 32) : 0.f;
-                f[u] = 0.f;
-                if (dots && on && lane < K) f[u] = (lane == slot) ? fcur[ni * 32] : hf[((size_t)lane * n + ni) * 32];
-            }
+        for (int u = 0; u < U; ++u) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-#pragma unroll
-                for (int q = 0; q < NC; ++q) acc[q] = fmaf(w[u][q], a[u], acc[q]);
-                dot = fmaf(f[u], a[u], dot);
-            }
+            for (int q = 0; q < NC; ++q) acc[q] = fmaf(w[u][q], a[u], acc[q]);
+            dot = fmaf(f[u], a[u], dot);
         }
     }
     // CTA partial of the 8 trials -> partial arena [chunk][size_out + K] (32-byte runs: 8 consecutive trials per row)
@@ -239,25 +239,38 @@ __global__ void __launch_bounds__(256) k_pes_fold(SsbCtx c, SsbPesDefer h, const
         const int active = tpw * nq4;
         const int tasks_per_neuron = (32 + tpw - 1) / tpw;
         const int n_tasks = (i_hi - i_lo) * tasks_per_neuron;
-        for (int task = warp; task < n_tasks; task += 8) {
-            const int i = i_lo + task / tasks_per_neuron;
-            const int t = (task % tasks_per_neuron) * tpw + lane / nq4;
-            const int q4 = lane % nq4;
-            if (lane < active && t < 32) {
-                float4* wp = reinterpret_cast<float4*>(dg + (size_t)i * JP * 32 + (size_t)t * JP + j0) + q4;
-                float4 w = __ldcs(wp);
-                float fv[K];
+        constexpr int TU = 4;                             // tasks in flight per warp (each is load -> 8 fma rounds -> store)
+        for (int task0 = warp * TU; task0 < n_tasks; task0 += 8 * TU) {
+            float4 w[TU];
+            float fv[TU][K];
+            float4* wp[TU];
+            int tt[TU];
+            bool ok[TU];
 #pragma unroll
-                for (int q = 0; q < K; ++q) fv[q] = __ldg(hf + ((size_t)q * n + i) * 32 + t);
+            for (int u = 0; u < TU; ++u) {
+                const int task = task0 + u;
+                const int i = i_lo + task / tasks_per_neuron;
+                tt[u] = (task % tasks_per_neuron) * tpw + lane / nq4;
+                ok[u] = task < n_tasks && lane < active && tt[u] < 32;
+                const int ts = ok[u] ? tt[u] : 0;
+                const int is = ok[u] ? i : i_lo;
+                wp[u] = reinterpret_cast<float4*>(dg + (size_t)is * JP * 32 + (size_t)ts * JP + j0) + (lane % nq4);
+                w[u] = ok[u] ? __ldcs(wp[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < K; ++q) fv[u][q] = ok[u] ? __ldg(hf + ((size_t)q * n + is) * 32 + ts) : 0.f;
+                tt[u] = ts;
+            }
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
 #pragma unroll
                 for (int q = 0; q < K; ++q) {
-                    const float4 e = *reinterpret_cast<const float4*>(sm + ((size_t)q * 32 + t) * SSB_PES_FT + 4 * q4);
-                    w.x = fmaf(e.x, fv[q], w.x);
-                    w.y = fmaf(e.y, fv[q], w.y);
-                    w.z = fmaf(e.z, fv[q], w.z);
-                    w.w = fmaf(e.w, fv[q], w.w);
+                    const float4 e = *reinterpret_cast<const float4*>(sm + ((size_t)q * 32 + tt[u]) * SSB_PES_FT + 4 * (lane % nq4));
+                    w[u].x = fmaf(e.x, fv[u][q], w[u].x);
+                    w[u].y = fmaf(e.y, fv[u][q], w[u].y);
+                    w[u].z = fmaf(e.z, fv[u][q], w[u].z);
+                    w[u].w = fmaf(e.w, fv[u][q], w[u].w);
                 }
-                __stcs(wp, w);
+                if (ok[u]) __stcs(wp[u], w[u]);
             }
         }
     }
