@@ -720,32 +720,20 @@ __global__ void __launch_bounds__(256, 1) k_wide_voja_stream(SsbCtx c, const int
         const unsigned any_on = __ballot_sync(0xffffffffu, fired);
         if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + n0 + i] = (int)any_on;
         if (any_on) {
-            // Voja for the trials that spiked, one trial at a time with lanes = encoder rows: every row of the neuron is in
-            // flight at once (the rows were just streamed, so they come from L2) and only that trial's words are written
+            // Voja: only the lanes that spiked touch their words (the rows were just streamed: L2 re-read, 32-byte sector
+            // writes).  Measured on B200 at d = 649: this lane = trial form 652 us per launch; a lanes = rows form (one
+            // spiking trial at a time, every row in flight) 1 275 us - uncoalesced sector accesses cost ~4 LSU cycles each,
+            // so the fewer sector operations win, not the fewer round trips.
             const float sc = __ldg(c.W + scale_off + n0 + i);
-            float* En = eg + (size_t)(i - i_lo) * dims * 32;
-            const float* xg = c.vec + ((size_t)g * c.nv + in_row0) * 32;
-            unsigned m = any_on;
-            while (m) {
-                const int f = __ffs(m) - 1;
-                m &= m - 1;
-                const float out_f = __shfl_sync(0xffffffffu, out, f);
-                const float aL_f = __shfl_sync(0xffffffffu, aL, f);
-                constexpr int R = 8;                         // 256 rows per pass
-                for (int k0 = 0; k0 < dims; k0 += 32 * R) {
-                    float ev[R], xv[R];
+            float* Eg = eg + (size_t)(i - i_lo) * dims * 32 + lane;
+            for (int k0 = 0; k0 < dims; k0 += 16) {
+                float ev[16];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int k = k0 + r * 32 + lane;
-                        ev[r] = k < dims ? __ldcg(En + (size_t)k * 32 + f) : 0.f;
-                        xv[r] = k < dims ? __ldg(xg + (size_t)k * 32 + f) : 0.f;
-                    }
+                for (int u = 0; u < 16; ++u) ev[u] = (fired && k0 + u < dims) ? __ldcg(Eg + (size_t)(k0 + u) * 32) : 0.f;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int k = k0 + r * 32 + lane;
-                        if (k < dims) En[(size_t)k * 32 + f] = ev[r] + aL_f * (sc * (out_f * xv[r]) - out_f * ev[r]);
-                    }
-                }
+                for (int u = 0; u < 16; ++u)
+                    if (fired && k0 + u < dims)
+                        Eg[(size_t)(k0 + u) * 32] = ev[u] + aL * (sc * (out * xs[(k0 + u) * 32 + lane]) - out * ev[u]);
             }
         }
     }
