@@ -13,7 +13,8 @@ cfg = os.environ.get("CONFIG", "slam55")
 import numpy as np
 DISTINCT = int(os.environ.get("DISTINCT", str(B)))
 if cfg == "pathint97":      # BASELINE configs[0]
-    sc = scenarios.make_pathint(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=97, pi_n_neurons=500, neuron_type="lif")
+    sc = scenarios.make_pathint(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=int(os.environ.get("SSP_DIM", "97")), pi_n_neurons=500,
+                                neuron_type="lif")
 elif cfg == "slamview97":   # BASELINE configs[3] sizes
     sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), ssp_dim=97, pi_n_neurons=800, mem_n_neurons=970,
                              circonv_n_neurons=100, n_landmarks=100, T=200.0, length_scale=0.3, view=True, distinct_tables=DISTINCT, table_dtype=np.float32)
@@ -24,11 +25,17 @@ elif cfg == "slam55loihi":  # run_slam.py --backend loihi-sim sizes: SLAMLoihiNe
     sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=DISTINCT, table_dtype=np.float32, loihi=True, dotprod_n_neurons=50)
 else:
     sc = scenarios.make_slam(n_trials=B, n_steps=steps * (reps + 3), T=200.0, distinct_tables=DISTINCT, table_dtype=np.float32)
-if os.environ.get("SYNTH"):      # on-device input synthesis instead of tables
+if os.environ.get("PER_TRIAL_SEEDS"):   # every trial its own network seed (narrow-ensemble networks): per-trial static weights
+    t0 = time.time()
+    n_seeds = int(os.environ["PER_TRIAL_SEEDS"])
+    sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, chunk_steps=steps,
+                    trial_network_seeds=[1000 + (i % n_seeds) for i in range(B)])
+    print(f"[perf] built {n_seeds} models + upload in {time.time() - t0:.1f} s", flush=True)
+elif os.environ.get("SYNTH"):      # on-device input synthesis instead of tables
     sim = Simulator(sc.network, dt=sc.dt, n_trials=B, input_synthesis=sc.extra["input_synthesis"], chunk_steps=steps)
 else:
     sim = Simulator(sc.network, dt=sc.dt, n_trials=B, trial_inputs=sc.trial_inputs, chunk_steps=steps)
-bytes_ts = lowering.algorithmic_bytes_per_trial_step(sim.plan.stats)
+bytes_ts = lowering.algorithmic_bytes_per_trial_step(sim.plan.stats, per_trial_weights=bool(os.environ.get("PER_TRIAL_SEEDS")))
 sim.run_steps(steps)
 out = []
 for rep in range(reps):

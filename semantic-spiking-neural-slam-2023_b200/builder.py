@@ -224,10 +224,14 @@ def _build_probe(model, probe, cache):
     model.params[probe] = None
 
 
-def build_model(network, dt=0.001, seed=None):
-    """Build every ensemble / connection / probe of ``network`` (and sub-networks)."""
+def build_model(network, dt=0.001, seed=None, seed_override=None):
+    """Build every ensemble / connection / probe of ``network`` (and sub-networks).
+
+    ``seed_override`` replaces the network's own seed: the same declared graph built as if the driver had been started
+    with another ``--seed`` (``nengo.Network(seed=args.seed)``, run_slam.py:151) - one built model per trial of a batch
+    whose trials have their own network seeds."""
     model = BuiltModel(network, dt)
-    top_seed = getattr(network, "seed", None)
+    top_seed = getattr(network, "seed", None) if seed_override is None else int(seed_override)
     if top_seed is None:
         top_seed = seed if seed is not None else np.random.randint(maxint)
     model.seeds[network] = int(top_seed)

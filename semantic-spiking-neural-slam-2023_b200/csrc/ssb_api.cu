@@ -199,6 +199,8 @@ struct ssb_sim {
     // arenas
     float *vec = nullptr, *tab = nullptr, *st = nullptr, *act = nullptr, *lenc = nullptr, *ldec = nullptr;
     float *afilt = nullptr, *probe = nullptr, *part = nullptr;
+    float* wpt = nullptr;                   // per-trial static weights [G][n_wpt][32] (scalar per_trial_weights = 1)
+    long long n_wpt = 0;
     int* counters = nullptr;
     int* aflag = nullptr;
     long long* dyn = nullptr;
@@ -271,6 +273,7 @@ int arena(ssb_sim* s, const char* name, ArenaRef* out) {
     else if (n == "ldec") *out = {s->ldec, s->n_ldec, true};
     else if (n == "afilt") *out = {s->afilt, 2 * s->n_afilt, true};
     else if (n == "vec") *out = {s->vec, s->nv, true};
+    else if (n == "wpt") *out = {s->wpt, s->n_wpt, true};
     else if (n == "cidx") *out = {reinterpret_cast<float*>(s->cidx), (long long)s->cleanups.size(), false};
     else return fail(-3, "unknown arena '" + n + "'");
     return 0;
@@ -741,8 +744,8 @@ int setup_pes_defer(ssb_sim* s) {
     SSB_CUDA(cudaMalloc((void**)&s->d_pes_hdesc, hd.size() * sizeof(int)));
     SSB_CUDA(cudaMemcpy(s->d_pes_hdesc, hd.data(), hd.size() * sizeof(int), cudaMemcpyHostToDevice));
     h.K = K;
-    SSB_CUDA(cudaFuncSetAttribute(k_pes_fold<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SSB_PES_FT * 32 * (int)sizeof(float)));
-    SSB_CUDA(cudaFuncSetAttribute(k_pes_fold<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * SSB_PES_FT * 32 * (int)sizeof(float)));
+    SSB_CUDA(cudaFuncSetAttribute(k_pes_fold<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SSB_PES_FS * 32 * (int)sizeof(float)));
+    SSB_CUDA(cudaFuncSetAttribute(k_pes_fold<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * SSB_PES_FS * 32 * (int)sizeof(float)));
     return 0;
 }
 
@@ -752,7 +755,7 @@ void launch_pes_fold(ssb_sim* s, cudaStream_t st, int i_rel, int force) {
     for (int i = 0; i < s->n_pes; ++i) max_n = std::max(max_n, s->h_pes[i * 13]);
     const int chunks = std::max(1, std::min((148 * 3 + s->n_groups * s->n_pes - 1) / std::max(1, s->n_groups * s->n_pes), (max_n + 7) / 8));
     dim3 grid(chunks, s->n_groups, s->n_pes);
-    const size_t smem = (size_t)s->pes_h.K * SSB_PES_FT * 32 * sizeof(float);
+    const size_t smem = (size_t)s->pes_h.K * SSB_PES_FS * 32 * sizeof(float);
     if (s->pes_h.K == 4) k_pes_fold<4><<<grid, 256, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks, i_rel, force);
     else k_pes_fold<8><<<grid, 256, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks, i_rel, force);
     k_pes_clear<<<dim3((s->pes_h.rows_e + 3) / 4, s->n_groups), 128, 0, st>>>(s->ctx, s->pes_h, i_rel, force);
@@ -1242,7 +1245,8 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
             while (n_split < st[1] && s->h_small[(st[0] + n_split) * 9] >= 128) ++n_split;
             const int packed_warps = (st[1] - n_split) * G;
             const int blocks = n_split * G + (packed_warps + 3) / 4;
-            k_ens_small<<<blocks, 128, 0, T>>>(c, s->d_small + st[0] * 9, st[1], n_split);
+            if (s->wpt) k_ens_small_pt<<<blocks, 128, 0, T>>>(c, s->d_small + st[0] * 9, st[1], n_split);
+            else k_ens_small<<<blocks, 128, 0, T>>>(c, s->d_small + st[0] * 9, st[1], n_split);
             ev_small[lvl] = mark(T);
         }
     }
@@ -1461,6 +1465,14 @@ int ssb_finalize(ssb_sim* s) {
             return fail(-1, "ssb_finalize: narrow-ensemble weight stride out of range");
 
     const int B = s->B;
+    if (iscalar(s, "per_trial_weights") != 0) {
+        // every trial has its own network seed: the static weights become one more per-trial arena.  Supported for plans
+        // made of narrow ensembles only (PathIntegration); wide ensembles / decoders would need per-trial GEMM operands.
+        if (!s->h_big.empty() || !s->h_dec.empty() || !s->h_cleanup.empty())
+            return fail(-1, "ssb_finalize: per-trial static weights are supported for narrow-ensemble plans only");
+        s->n_wpt = (long long)(s->arrays["weights"].bytes.size() / sizeof(float));
+        if (alloc_rows(&s->wpt, s->n_wpt, B)) return -2;
+    }
     if (alloc_rows(&s->vec, s->nv, B)) return -2;
     if (alloc_rows(&s->st, s->nn, B)) return -2;
     if (alloc_rows(&s->act, s->n_act, B)) return -2;
@@ -1545,6 +1557,8 @@ int ssb_finalize(ssb_sim* s) {
     c.part = s->part;
     c.counters = s->counters;
     c.W = s->d_W;
+    c.wpt = s->wpt;
+    c.n_wpt = (int)std::max(1LL, s->n_wpt);
     c.csr_ptr = s->d_csr_ptr;
     c.ent0 = s->d_ent0;
     c.ent1 = s->d_ent1;
@@ -1904,7 +1918,7 @@ void ssb_destroy(ssb_sim* s) {
                     s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_enc_t, s->d_enc_t_off, s->pes_h.hist_e, s->pes_h.hist_f, s->pes_h.part,
                     s->pes_h.counters, s->d_pes_hdesc, s->aflag, s->syn_path, s->syn_vel, s->syn_lm, s->syn_phases, s->syn_lmsp,
                     s->syn_cos, s->syn_sin, s->syn_idx, s->d_etk, s->d_xtk, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
-                    s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx};
+                    s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx, s->wpt};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& cd : s->cleanups) {

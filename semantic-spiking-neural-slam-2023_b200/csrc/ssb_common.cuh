@@ -42,6 +42,8 @@ struct SsbCtx {
     float* part;              // [G][n_part][32] split-K partial sums of decode / PES launches
     int* counters;            // split-K arrival counters, self-resetting
     const float* W;           // shared static weights
+    const float* wpt;         // [G][n_wpt][32] per-trial static weights (trials with their own network seed), or nullptr
+    int n_wpt;
     const int* csr_ptr;
     const int2* ent0;         // CSR entries (vec row, coefficient bits) resolved for even steps
     const int2* ent1;         //   ... and for odd steps (filter columns point at the other half)

@@ -31,6 +31,7 @@
 // hdesc per decoder: e_row0 f_row0 part_row0 counter0 (rows of the hist_e / hist_f / pes_part arenas)
 #define SSB_PES_JT 128         // output columns per k_pes_defer CTA (4 per lane)
 #define SSB_PES_FT 64          // output columns per k_pes_fold shared-memory tile
+#define SSB_PES_FS 68          // floats per (slot, trial) row of that tile: 16-byte aligned, 4-way instead of 32-way bank conflicts on the fill
 
 __host__ __device__ __forceinline__ int ssb_pes_jp(int size_out) { return (size_out + 3) & ~3; }
 
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(256) k_pes_defer(SsbCtx c, SsbPesDefer h, cons
 template <int K>
 __global__ void __launch_bounds__(256) k_pes_fold(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
                                                     const int* __restrict__ hdesc, int max_chunks, int i_rel, int force) {
-    extern __shared__ __align__(16) float sm[];          // [K][32 trials][SSB_PES_FT]
+    extern __shared__ __align__(16) float sm[];          // [K][32 trials][SSB_PES_FS]
     const int item = blockIdx.z, chunk = blockIdx.x;
     const int* d = desc + item * 13;
     const int* hd = hdesc + item * 4;
@@ -230,9 +231,18 @@ __global__ void __launch_bounds__(256) k_pes_fold(SsbCtx c, SsbPesDefer h, const
         const int jw = min(SSB_PES_FT, JP - j0);          // columns of this tile (multiple of 4)
         const int nq4 = jw >> 2;                          // 16-byte pieces per trial
         __syncthreads();
-        for (int r = warp; r < K * jw; r += 8) {          // he row (q, j) -> sm[q][trial = lane][j]
-            const int q = r / jw, j = r - q * jw;
-            sm[((size_t)q * 32 + lane) * SSB_PES_FT + j] = (j0 + j < size_out) ? he[(size_t)(q * size_out + j0 + j) * 32 + lane] : 0.f;
+        for (int r0 = warp; r0 < K * jw; r0 += 64) {      // he row (q, j) -> sm[q][trial = lane][j], 8 rows in flight per warp
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + 8 * u, q = r / jw, j = r - q * jw;
+                v[u] = (r < K * jw && j0 + j < size_out) ? he[(size_t)(q * size_out + j0 + j) * 32 + lane] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + 8 * u, q = r / jw, j = r - q * jw;
+                if (r < K * jw) sm[((size_t)q * 32 + lane) * SSB_PES_FS + j] = v[u];
+            }
         }
         __syncthreads();
         const int tpw = 32 / nq4 > 0 ? 32 / nq4 : 1;      // trials per warp task (2 at d = 55)
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(256) k_pes_fold(SsbCtx c, SsbPesDefer h, const
             for (int u = 0; u < TU; ++u) {
 #pragma unroll
                 for (int q = 0; q < K; ++q) {
-                    const float4 e = *reinterpret_cast<const float4*>(sm + ((size_t)q * 32 + tt[u]) * SSB_PES_FT + 4 * (lane % nq4));
+                    const float4 e = *reinterpret_cast<const float4*>(sm + ((size_t)q * 32 + tt[u]) * SSB_PES_FS + 4 * (lane % nq4));
                     w[u].x = fmaf(e.x, fv[u][q], w[u].x);
                     w[u].y = fmaf(e.y, fv[u][q], w[u].y);
                     w[u].z = fmaf(e.z, fv[u][q], w[u].z);

@@ -839,6 +839,31 @@ def lower(network, model: BuiltModel, chunk_cap=256, n_trials=1) -> DevicePlan:
     return _Lowerer(network, model, n_trials).lower(chunk_cap)
 
 
+def narrow_ensemble_weights(network, model: BuiltModel, n_trials=1) -> np.ndarray:
+    """The ``weights`` array of the plan of a network made of narrow ensembles only (PathIntegration), for another built
+    model of the same graph: packed ``[bias | scaled encoders | decoders]`` rows per neuron, in plan order.  Used to fill
+    the per-trial weight arena when every trial has its own network seed (the rest of the plan is seed-independent)."""
+    low = _Lowerer(network, model, n_trials)
+    low.classify_ensembles()
+    out = []
+    for ens in low.ensembles:
+        if not low.is_small[ens]:
+            raise NotImplementedError("per-trial static weights: narrow ensembles only")
+        p = model.params[ens]
+        outs = low.ens_dec_conns[ens]
+        nout = sum(low._out_size(c) for c in outs)
+        dims = ens.dimensions
+        stride = 1 + dims + nout
+        stride += (-stride) % 4
+        packed = np.zeros((ens.n_neurons, stride))
+        packed[:, 0] = p.bias
+        packed[:, 1:1 + dims] = p.scaled_encoders
+        if outs:
+            packed[:, 1 + dims:1 + dims + nout] = np.vstack([low._dec_weights(c) for c in outs]).T
+        out.append(np.ascontiguousarray(packed, dtype=np.float32).reshape(-1))
+    return np.concatenate(out + [np.zeros(8, dtype=np.float32)])
+
+
 def algorithmic_bytes_per_trial_step(stats, per_trial_weights=False):
     """SURVEY.md §8(d) traffic model (fp32): state R+W, filters R+W, learned R+W, inputs, probes."""
     b = 16 * stats["n_neurons"] + 8 * (stats["n_filter_states"] + stats["n_afilt"]) + 8 * stats["n_learned"]

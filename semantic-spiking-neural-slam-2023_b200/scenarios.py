@@ -34,24 +34,36 @@ def make_space(domain_dim=2, ssp_dim=55, length_scale=0.2, radius=1.0, backend="
                              rng=np.random.default_rng(0), backend=backend)
 
 
+class _PathintJob:
+    """Inputs of one path-integration trial (picklable, see ``_map_trials``)."""
+
+    def __init__(self, space, scale, T, dt, limit, seed, n_steps):
+        self.__dict__.update(locals())
+
+    def __call__(self, i):
+        path = inputs.random_path(self.T, self.dt, self.limit, self.seed + 1000 * i, 2)
+        vels = inputs.velocities(path, self.dt) * self.scale
+        n_keep = max(self.n_steps + 2, 4)
+        real = self.space.encode_host(path[:n_keep])
+        tb = inputs.pathint_tables(real, vels[:n_keep], self.n_steps, self.dt)
+        return tb, path[:n_keep], real[:self.n_steps], vels[:n_keep]
+
+
 def make_pathint(n_trials=1, n_steps=1000, ssp_dim=55, pi_n_neurons=500, T=20.0, limit=0.1, seed=0,
-                 neuron_type="lif", dt=0.001, tau=0.05, with_gcs=False, n_gcs=1000):
+                 neuron_type="lif", dt=0.001, tau=0.05, with_gcs=False, n_gcs=1000, distinct_tables=None, workers=None):
     """``run_pathint.py`` workload; trial i uses path seed ``seed + 1000*i``."""
     space = make_space(2, ssp_dim)
     d = space.ssp_dim
-    paths, ssps, tabs, full_paths, full_vels = [], [], [], [], []
-    scale = None
-    for i in range(n_trials):
-        path = inputs.random_path(T, dt, limit, seed + 1000 * i, 2)
-        vels = inputs.velocities(path, dt)
-        if scale is None:
-            scale = inputs.velocity_scale(space.phase_matrix, vels)   # shared static weights => one scale
-        real = space.encode_host(path)
-        tabs.append(inputs.pathint_tables(real, vels * scale, n_steps, dt))
-        paths.append(path[:n_steps])
-        ssps.append(real[:n_steps])
-        full_paths.append(path)
-        full_vels.append(vels * scale)
+    scale = inputs.velocity_scale(space.phase_matrix, inputs.velocities(inputs.random_path(T, dt, limit, seed, 2), dt))
+    n_distinct = n_trials if distinct_tables is None else min(n_trials, distinct_tables)
+    results = _map_trials(_PathintJob(space, scale, T, dt, limit, seed, n_steps), n_distinct, workers)
+    reps = -(-n_trials // n_distinct)
+    results = (results * reps)[:n_trials]
+    tabs = [r[0] for r in results]
+    paths = [r[1][:n_steps] for r in results]
+    ssps = [r[2] for r in results]
+    full_paths = [r[1] for r in results]
+    full_vels = [r[3] for r in results]
     vel0, init0 = tabs[0]["vel"], tabs[0]["init"]
     model = nengo.Network(seed=seed)
     model.config[nengo.Ensemble].neuron_type = _neuron_type(neuron_type)

@@ -45,19 +45,90 @@ class _SimData:
         return list(self._sim._probe_infos) + list(self._sim.model.params)
 
 
+def _build_one(args):
+    network, dt, s = args
+    return build_model(network, dt=dt, seed_override=s)
+
+
+def _build_models(network, dt, seeds, workers=None):
+    """One built model per network seed (identical seeds are built once), on a fork pool when there are many."""
+    import os
+    distinct = sorted(set(int(s) for s in seeds))
+    if workers is None:
+        workers = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 1
+    workers = max(1, min(int(workers), len(distinct) // 2))
+    if workers > 1:
+        import multiprocessing as mp
+        global _POOL_NET
+        _POOL_NET = (network, dt)
+        with mp.get_context("fork").Pool(workers) as pool:
+            built = [_unpack_model(network, dt, p) for p in pool.map(_build_pool_job, distinct, chunksize=1)]
+    else:
+        built = [build_model(network, dt=dt, seed_override=s) for s in distinct]
+    by_seed = dict(zip(distinct, built))
+    return [by_seed[int(s)] for s in seeds]
+
+
+_POOL_NET = None
+
+
+def _build_pool_job(seed):
+    network, dt = _POOL_NET
+    m = build_model(network, dt=dt, seed_override=seed)
+    # objects of the (forked) network are keys of the model's dicts: send back plain lists in traversal order
+    return _pack_model(network, m)
+
+
+def _model_objects(network):
+    objs = list(network.all_ensembles) + list(network.all_connections) + list(network.all_probes)
+    return objs, [network] + list(network.all_networks) + objs + list(network.all_nodes)
+
+
+def _unpack_model(network, dt, packed):
+    """Re-key a model built in a forked worker (whose keys are the worker's copies of the objects) by this process's objects."""
+    from .builder import BuiltModel
+    objs, seed_objs = _model_objects(network)
+    m = BuiltModel(network, dt)
+    m.seeds = {o: s for o, s in zip(seed_objs, packed["seeds"]) if s is not None}
+    m.params = dict(zip(objs, packed["params"]))
+    m.probe_conns = {p: v for p, v in zip(network.all_probes, packed["probe_conns"]) if v is not None}
+    return m
+
+
+def _pack_model(network, m):
+    objs, seed_objs = _model_objects(network)
+    return dict(seeds=[m.seeds.get(o) for o in seed_objs], params=[m.params.get(o) for o in objs],
+                probe_conns=[m.probe_conns.get(p) for p in network.all_probes])
+
+
 class Simulator:
     def __init__(self, network, dt=0.001, seed=None, model: BuiltModel | None = None, progress_bar=True,
                  optimize=True, n_trials=None, trial_inputs=None, trial_seeds=None, device=0, chunk_steps=256,
-                 input_synthesis=None, keep_probe_history=True):
+                 input_synthesis=None, keep_probe_history=True, trial_network_seeds=None, build_workers=None):
         self.network = network
         self.dt = float(dt)
         self.closed = False
         self._lib = cabi.load()  # raises if the CUDA library has not been built
-        self.model = model if model is not None else build_model(network, dt=self.dt, seed=seed)
         self._batched = n_trials is not None
         self.n_trials = int(n_trials) if self._batched else 1
         self.chunk_steps = int(chunk_steps)
+        self.models = None
+        if trial_network_seeds is not None:
+            # every trial is the driver started with its own --seed (run_slam.py:151): one built model per trial, per-trial
+            # static weights on the device (narrow-ensemble plans: PathIntegration)
+            if len(trial_network_seeds) != self.n_trials:
+                raise ValueError("trial_network_seeds must have one entry per trial")
+            self.models = _build_models(network, self.dt, list(trial_network_seeds), build_workers)
+            model = self.models[0]
+        self.model = model if model is not None else build_model(network, dt=self.dt, seed=seed)
         self.plan = lowering.lower(network, self.model, chunk_cap=self.chunk_steps, n_trials=self.n_trials)
+        if self.models is not None:
+            if self.plan.stats["n_big"] or len(self.plan.arrays["cleanup"]):
+                raise NotImplementedError("per-trial network seeds are supported for narrow-ensemble networks "
+                                          "(PathIntegration); wide ensembles share their static weights")
+            self.plan.scalars["per_trial_weights"] = 1.0
+            if trial_seeds is None:
+                trial_seeds = [None] * self.n_trials          # nengo's own start-voltage draw of every trial's model
         self._trial_inputs = dict(trial_inputs or {})
         if trial_seeds is None:
             trial_seeds = [None] + list(range(self.n_trials - 1)) if self._batched else [None]
@@ -195,10 +266,26 @@ class Simulator:
     def _init_state(self):
         m, plan = self.model, self.plan
         nn = int(plan.scalars["nn"])
+        if self.models is not None:
+            # per-trial static weights: the plan's weight array of every trial's model, [n_w, B]
+            w = np.zeros((plan.arrays["weights"].size, self.B), dtype=np.float32)
+            cache = {}
+            for t, mt in enumerate(self.models):
+                if id(mt) not in cache:
+                    cache[id(mt)] = lowering.narrow_ensemble_weights(self.network, mt, self.n_trials)
+                wt = cache[id(mt)]
+                if wt.size != w.shape[0]:
+                    raise RuntimeError("per-trial models lower to different weight layouts")
+                w[:, t] = wt
+            self._upload("wpt", 0, w)
         if nn:
             v0 = np.zeros((nn, self.B), dtype=np.float32)
             for ens, (row0, n) in plan.ens_state.items():
-                v0[row0:row0 + n, :self.n_trials] = m.initial_voltages(ens, self.trial_seeds).T
+                if self.models is not None:
+                    v0[row0:row0 + n, :self.n_trials] = np.stack(
+                        [mt.initial_voltage(ens, ts) for mt, ts in zip(self.models, self.trial_seeds)]).T
+                else:
+                    v0[row0:row0 + n, :self.n_trials] = m.initial_voltages(ens, self.trial_seeds).T
                 if self.B > self.n_trials:
                     v0[row0:row0 + n, self.n_trials:] = v0[row0:row0 + n, :1]
             self._upload("st", 0, v0)   # packed LIF state: s >= 0 is the voltage of a non-refractory neuron
