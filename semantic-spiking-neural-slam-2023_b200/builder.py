@@ -10,6 +10,8 @@ operator-level oracle (checker) so that both step *the same built model*.
 from __future__ import annotations
 
 import dataclasses
+import os
+
 import numpy as np
 
 from . import compat
@@ -146,6 +148,7 @@ class _DecoderCache:
         self.model = model
         self._acts = {}
         self._factor = {}
+        self._presolved = {}
 
     def activities(self, ens):
         if ens not in self._acts:
@@ -156,7 +159,46 @@ class _DecoderCache:
                 raise BuildError(f"all tuning curves of {ens!r} are zero")
         return self._acts[ens]
 
-    def solve(self, ens, solver, targets):
+    def presolve_on_device(self, network, device=0):
+        """every LstsqL2 system of the model on the GPU (``libssb_builder.so``), batched over the ensembles
+        of one shape; ``solve`` then only looks the decoders up.  Same arithmetic as the host path (float64 normal
+        equations + Cholesky), summation order aside."""
+        from . import cabi
+        jobs = {}                                     # (ens, reg) -> [(key object, targets)]
+        for conn in network.all_connections:
+            pre = conn.pre_obj
+            if compat.is_ensemble(pre) and compat.is_lstsq_l2(conn.solver) and not conn.solver.weights \
+                    and conn.eval_points is None and compat.neuron_kind(pre.neuron_type) != "direct":
+                jobs.setdefault((pre, float(conn.solver.reg)), []).append(
+                    (conn, _targets(conn, self.model.params[pre].eval_points)))
+        for probe in network.all_probes:
+            obj = probe.obj
+            if compat.is_ensemble(obj) and probe.attr == "decoded_output" and compat.is_lstsq_l2(probe.solver):
+                jobs.setdefault((obj, float(probe.solver.reg)), []).append((probe, self.model.params[obj].eval_points))
+        groups = {}                                   # (m, n, reg) -> [(ens, [(key, targets)])]
+        for (ens, reg), lst in jobs.items():
+            A = self.activities(ens)
+            if A.shape[0] >= A.shape[1]:              # (fewer evaluation points than neurons: host path)
+                groups.setdefault((A.shape[0], A.shape[1], reg), []).append((ens, lst))
+        for (m, n, reg), members in groups.items():
+            kmax = max(sum(t.shape[1] for _, t in lst) for _, lst in members)
+            A = np.stack([self.activities(ens) for ens, _ in members])
+            Y = np.zeros((len(members), m, kmax))
+            for s, (_, lst) in enumerate(members):
+                col = 0
+                for _, t in lst:
+                    Y[s, :, col:col + t.shape[1]] = t
+                    col += t.shape[1]
+            X = cabi.solve_decoders(A, Y, reg, device)
+            for s, (ens, lst) in enumerate(members):
+                col = 0
+                for key, t in lst:
+                    self._presolved[(ens, reg, key)] = X[s, :, col:col + t.shape[1]].copy()
+                    col += t.shape[1]
+
+    def solve(self, ens, solver, targets, key=None):
+        if compat.is_lstsq_l2(solver) and (ens, float(solver.reg), key) in self._presolved:
+            return self._presolved[(ens, float(solver.reg), key)]
         A = self.activities(ens)
         if not compat.is_lstsq_l2(solver):
             X, _ = solver(A, targets)
@@ -205,7 +247,7 @@ def _build_connection(model, conn, cache):
             else np.array(conn.eval_points, dtype=np.float64)
         if conn.eval_points is not None:
             raise NotImplementedError("per-connection eval_points are outside the hot path")
-        decoders = cache.solve(pre, conn.solver, _targets(conn, eval_points)).T  # size_mid x n
+        decoders = cache.solve(pre, conn.solver, _targets(conn, eval_points), key=conn).T  # size_mid x n
         weights = fold_transform(transform, decoders)
         model.params[conn] = BuiltConnection(eval_points, {}, transform, weights, decoders)
     elif compat.is_neurons(pre):
@@ -219,17 +261,20 @@ def _build_connection(model, conn, cache):
 def _build_probe(model, probe, cache):
     obj = probe.obj
     if compat.is_ensemble(obj) and probe.attr == "decoded_output":
-        dec = cache.solve(obj, probe.solver, model.params[obj].eval_points).T
+        dec = cache.solve(obj, probe.solver, model.params[obj].eval_points, key=probe).T
         model.probe_conns[probe] = dec[np.arange(obj.dimensions)[probe.slice]]
     model.params[probe] = None
 
 
-def build_model(network, dt=0.001, seed=None, seed_override=None):
+def build_model(network, dt=0.001, seed=None, seed_override=None, device_solver=None):
     """Build every ensemble / connection / probe of ``network`` (and sub-networks).
 
     ``seed_override`` replaces the network's own seed: the same declared graph built as if the driver had been started
     with another ``--seed`` (``nengo.Network(seed=args.seed)``, run_slam.py:151) - one built model per trial of a batch
-    whose trials have their own network seeds."""
+    whose trials have their own network seeds.
+
+    ``device_solver``: GPU index on which the decoder systems are solved (``libssb_builder.so``; default: environment
+    variable ``SSB_DEVICE_BUILDER``, else the host solver)."""
     model = BuiltModel(network, dt)
     top_seed = getattr(network, "seed", None) if seed_override is None else int(seed_override)
     if top_seed is None:
@@ -237,9 +282,36 @@ def build_model(network, dt=0.001, seed=None, seed_override=None):
     model.seeds[network] = int(top_seed)
     _assign_seeds(network, model.seeds)
 
+    with _blas_threads():
+        return _build_all(model, network, device_solver)
+
+
+class _blas_threads:
+    """The builder's matrices are small (<= 2 500 x 1 000): multi-threaded BLAS / LAPACK only thrashes on them (measured:
+    ``cho_factor`` of a 500 x 500 Gram matrix 121 ms with 8 threads, 2.2 ms with one).  ``SSB_BUILDER_THREADS`` overrides."""
+
+    def __enter__(self):
+        self._ctx = None
+        try:
+            from threadpoolctl import threadpool_limits
+            self._ctx = threadpool_limits(limits=int(os.environ.get("SSB_BUILDER_THREADS", "1")))
+        except Exception:
+            pass
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+
+
+def _build_all(model, network, device_solver):
     cache = _DecoderCache(model)
     for ens in network.all_ensembles:
         _build_ensemble(model, ens)
+    if device_solver is None and os.environ.get("SSB_DEVICE_BUILDER") not in (None, "", "off"):
+        device_solver = int(os.environ["SSB_DEVICE_BUILDER"])
+    if device_solver is not None:
+        cache.presolve_on_device(network, int(device_solver))
     for conn in network.all_connections:
         _build_connection(model, conn, cache)
     for probe in network.all_probes:

@@ -73,6 +73,42 @@ def load():
     return lib
 
 
+BUILDER_LIB_PATH = os.path.join(_HERE, "libssb_builder.so")
+BUILDER_EXPORTS = ("ssb_solve_decoders", "ssb_builder_last_error")
+_builder_lib = None
+
+
+def load_builder():
+    """``libssb_builder.so`` (include/sspslam_b200_builder.h): batched decoder solves on the device (cuBLAS / cuSOLVER)."""
+    global _builder_lib
+    if _builder_lib is not None:
+        return _builder_lib
+    if not os.path.isfile(BUILDER_LIB_PATH):
+        raise SsbError(f"{BUILDER_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(BUILDER_LIB_PATH)
+    lib.ssb_solve_decoders.restype = C.c_int
+    lib.ssb_solve_decoders.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                       C.c_void_p]
+    lib.ssb_builder_last_error.restype = C.c_char_p
+    lib.ssb_builder_last_error.argtypes = []
+    _builder_lib = lib
+    return lib
+
+
+def solve_decoders(A, Y, reg, device=0):
+    """Batched LstsqL2 on the device: ``A`` [n_sys, m, n], ``Y`` [n_sys, m, k] -> ``X`` [n_sys, n, k] (float64)."""
+    lib = load_builder()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    n_sys, m, n = A.shape
+    k = Y.shape[2]
+    X = np.empty((n_sys, n, k), dtype=np.float64)
+    rc = lib.ssb_solve_decoders(int(device), n_sys, m, n, k, _ptr(A), _ptr(Y), float(reg), _ptr(X))
+    if rc != 0:
+        raise SsbError(f"ssb_solve_decoders failed ({rc}): {lib.ssb_builder_last_error().decode(errors='replace')}")
+    return X
+
+
 EXPORTS = ("ssb_create", "ssb_set_array", "ssb_set_scalar", "ssb_finalize", "ssb_upload", "ssb_download",
            "ssb_set_tables", "ssb_rebase_tables", "ssb_run_steps", "ssb_run_steps_io", "ssb_io_wait", "ssb_synth_setup", "ssb_synth_steps", "ssb_read_probes", "ssb_n_steps",
            "ssb_n_trials_padded", "ssb_sync", "ssb_reset", "ssb_destroy", "ssb_set_profiling", "ssb_last_run_ms",

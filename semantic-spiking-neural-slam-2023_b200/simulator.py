@@ -268,22 +268,29 @@ class Simulator:
         nn = int(plan.scalars["nn"])
         if self.models is not None:
             # per-trial static weights: the plan's weight array of every trial's model, [n_w, B]
-            w = np.zeros((plan.arrays["weights"].size, self.B), dtype=np.float32)
-            cache = {}
-            for t, mt in enumerate(self.models):
-                if id(mt) not in cache:
-                    cache[id(mt)] = lowering.narrow_ensemble_weights(self.network, mt, self.n_trials)
-                wt = cache[id(mt)]
-                if wt.size != w.shape[0]:
-                    raise RuntimeError("per-trial models lower to different weight layouts")
-                w[:, t] = wt
+            distinct, which = {}, []
+            for mt in self.models:
+                if id(mt) not in distinct:
+                    wt = lowering.narrow_ensemble_weights(self.network, mt, self.n_trials)
+                    if wt.size != plan.arrays["weights"].size:
+                        raise RuntimeError("per-trial models lower to different weight layouts")
+                    distinct[id(mt)] = (len(distinct), wt)
+                which.append(distinct[id(mt)][0])
+            stacked = np.stack([wt for _, wt in sorted(distinct.values(), key=lambda p: p[0])])      # [n_models, n_w]
+            w = np.zeros((stacked.shape[1], self.B), dtype=np.float32)
+            w[:, :self.n_trials] = stacked.T[:, np.asarray(which)]
             self._upload("wpt", 0, w)
         if nn:
             v0 = np.zeros((nn, self.B), dtype=np.float32)
             for ens, (row0, n) in plan.ens_state.items():
                 if self.models is not None:
-                    v0[row0:row0 + n, :self.n_trials] = np.stack(
-                        [mt.initial_voltage(ens, ts) for mt, ts in zip(self.models, self.trial_seeds)]).T
+                    memo = {}
+                    cols = []
+                    for mt, ts in zip(self.models, self.trial_seeds):
+                        if (id(mt), ts) not in memo:
+                            memo[(id(mt), ts)] = mt.initial_voltage(ens, ts)
+                        cols.append(memo[(id(mt), ts)])
+                    v0[row0:row0 + n, :self.n_trials] = np.stack(cols).T
                 else:
                     v0[row0:row0 + n, :self.n_trials] = m.initial_voltages(ens, self.trial_seeds).T
                 if self.B > self.n_trials:

@@ -49,3 +49,16 @@ def test_library_is_in_tree_and_self_contained():
     from sspslam_b200 import cabi
     assert os.path.dirname(cabi.LIB_PATH) == os.path.join(ROOT, "semantic-spiking-neural-slam-2023_b200")
     ctypes.CDLL(cabi.LIB_PATH)   # loads without torch / python symbols
+
+
+def test_builder_library_exports_its_header(lib):
+    """libssb_builder.so (include/sspslam_b200_builder.h) loads without a GPU and exports what its header declares."""
+    from sspslam_b200 import cabi
+    with open(os.path.join(ROOT, "include", "sspslam_b200_builder.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(ssb_[a-z0-9_]+)\s*\(", text)))
+    blib = cabi.load_builder()
+    assert declared == sorted(cabi.BUILDER_EXPORTS)
+    for name in declared:
+        assert hasattr(blib, name)
+    assert isinstance(blib.ssb_builder_last_error(), bytes)
