@@ -133,7 +133,9 @@ struct ssb_sim {
     // dense blocks of the row program (rows sharing one column list), found at finalize
     int *d_dense_items = nullptr, *d_dense_desc = nullptr, *d_dense_cols = nullptr, *d_dense_rows = nullptr;
     float* d_dense_T = nullptr;
-    struct LinSeg { int csr_row0 = 0, n_csr = 0, item0 = 0, n_items = 0, rec0 = 0, n_recs = 0; };
+    struct LinSeg { int csr_row0 = 0, n_csr = 0, item0 = 0, n_items = 0, rec0 = 0, n_recs = 0, tc0 = 0, n_tc = 0, tc_max_kb = 0, tc_max_tiles = 0; };
+    SsbLinTcBlock* d_lin_tc = nullptr;      // large dense blocks served by k_lin_tck (tcgen05), per segment [tc0, tc0 + n_tc)
+    float *d_lin_ttk = nullptr, *d_lin_xt = nullptr;
     int* d_lin_recs = nullptr;
     std::vector<LinSeg> lin_segs;            // one per level + the end-of-step segment
     long long n_dense_rows = 0, n_dense_blocks = 0;
@@ -208,6 +210,7 @@ struct ssb_sim {
     int* cidx = nullptr;  // [n_cleanup][B] (trial-major, not tiled)
     // host mirrors of dyn
     long long steps_done = 0, tab_step0 = 0, probe_step0 = 0;
+    long long step_base = 0;                // absolute step of i_rel = 0 for the launches being issued (host mirror of dyn[])
     int tab_steps = 0;
     // timing
     bool profiling = false;
@@ -753,7 +756,12 @@ void launch_pes_fold(ssb_sim* s, cudaStream_t st, int i_rel, int force) {
     // neuron chunks of the streaming fold: ~4 CTAs per SM
     int max_n = 0;
     for (int i = 0; i < s->n_pes; ++i) max_n = std::max(max_n, s->h_pes[i * 13]);
-    const int chunks = std::max(1, std::min((148 * 3 + s->n_groups * s->n_pes - 1) / std::max(1, s->n_groups * s->n_pes), (max_n + 7) / 8));
+    // neuron chunks: one wave of resident CTAs (occupancy of the 69 KB / 256-thread kernel), so no partial second wave
+    const size_t fsm = (size_t)s->pes_h.K * SSB_PES_FS * 32 * sizeof(float);
+    int occ = 0;
+    if (s->pes_h.K == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pes_fold<4>, 256, fsm);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pes_fold<8>, 256, fsm);
+    const int chunks = std::max(1, std::min(148 * std::max(1, occ) / std::max(1, s->n_groups * s->n_pes), (max_n + 7) / 8));
     dim3 grid(chunks, s->n_groups, s->n_pes);
     const size_t smem = (size_t)s->pes_h.K * SSB_PES_FS * 32 * sizeof(float);
     if (s->pes_h.K == 4) k_pes_fold<4><<<grid, 256, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks, i_rel, force);
@@ -791,7 +799,7 @@ void launch_pes(ssb_sim* s, cudaStream_t st, int i_rel) {
     }
     // the host mirrors the step counter, so the fold is launched only after the last slot of a window
     // (a captured graph bakes this in; it is replayed only from steps with the same phase, see ssb_run_steps)
-    if ((int)((s->steps_done + i_rel) % s->pes_h.K) == s->pes_h.K - 1) {
+    if ((int)((s->step_base + i_rel) % s->pes_h.K) == s->pes_h.K - 1) {
         LaunchTimer t(s, K_PFOLD, st);
         launch_pes_fold(s, st, i_rel, 1);
         s->kind_launches[K_EXTRA] += 1;              // k_pes_clear
@@ -946,6 +954,16 @@ void launch_lin(ssb_sim* s, cudaStream_t st, int seg, int i_rel) {
     const int G = s->n_groups;
     const int rec_per_cta = 4 * SSB_REC_PER_WARP;
     const long long blocks = ((long long)L.n_items + (L.n_recs + rec_per_cta - 1) / rec_per_cta + (L.n_csr + 3) / 4) * G;
+    if (L.n_tc > 0) {      // the segment's large dense blocks: gather the source rows into operand tiles, then the tcgen05 GEMM
+        const int quads = (G + 3) / 4;
+        k_lin_xtiles<<<dim3(L.tc_max_kb, quads, L.n_tc), 128, 0, st>>>(s->ctx, s->d_lin_tc + L.tc0, s->d_dense_cols, s->d_lin_xt, i_rel);
+        const int n_chunks = std::max(1, std::min(L.tc_max_tiles, 148 / std::max(1, quads * L.n_tc)));
+        const size_t smem = (size_t)SSB_SCK_NST * 4 * SSB_SCK_PART * sizeof(float);
+        k_lin_tck<<<dim3(n_chunks, quads, L.n_tc), 320, smem, st>>>(s->ctx, s->d_lin_tc + L.tc0, s->d_lin_ttk, s->d_lin_xt,
+                                                                   s->d_dense_rows, i_rel);
+        s->kind_launches[K_EXTRA] += 2;
+        s->total_launches += 2;
+    }
     if (blocks <= 0) return;
     SsbLinArgs a;
     a.rows = s->d_lin_rows + (size_t)L.csr_row0 * 5;
@@ -973,7 +991,11 @@ int build_lin_program(ssb_sim* s) {
     const size_t n_rows = rows3.size() / 3;
     if ((size_t)(s->lin0 + s->n_lin) != n_rows) return fail(-1, "ssb_finalize: lin_rows segments do not add up");
     std::vector<int> rows5, items, ddesc, dcols, drows, recs;
-    std::vector<float> ab2, dT;
+    std::vector<float> ab2, dT, ttk;
+    std::vector<SsbLinTcBlock> tcb;
+    size_t xt_floats = 0;
+    const char* lin_env = getenv("SSB_LIN");
+    const bool lin_tc_on = !(lin_env && std::string(lin_env) == "ffma");
     s->lin_segs.assign(s->n_levels + 1, ssb_sim::LinSeg());
     for (int seg = 0; seg <= s->n_levels; ++seg) {
         const int r0 = seg < s->n_levels ? s->h_stages[seg * 12 + 10] : s->lin0;
@@ -981,6 +1003,7 @@ int build_lin_program(ssb_sim* s) {
         ssb_sim::LinSeg& L = s->lin_segs[seg];
         L.csr_row0 = (int)(rows5.size() / 5);
         L.item0 = (int)(items.size() / 8);
+        L.tc0 = (int)tcb.size();
         // group candidate rows by (view, column list)
         std::map<std::vector<int>, std::vector<int>> groups;
         for (int r = r0; r < r0 + nr; ++r) {
@@ -1002,6 +1025,7 @@ int build_lin_program(ssb_sim* s) {
             const int K = (int)kv.first.size() - 1;
             const int kpad = (K + SSB_DENSE_SLAB - 1) / SSB_DENSE_SLAB * SSB_DENSE_SLAB;
             const int R = (int)members.size();
+            const bool tc_block = lin_tc_on && R >= 128 && K >= 256;      // a real GEMM: K-blocked tcgen05 path
             const int block = (int)(ddesc.size() / 8);
             const int t_off = (int)dT.size(), cols_off = (int)dcols.size(), rows_off = (int)(drows.size() / 4);
             const int lo0 = ptr[rows3[members[0] * 3]];
@@ -1024,9 +1048,43 @@ int build_lin_program(ssb_sim* s) {
             }
             ddesc.insert(ddesc.end(), {R, kpad, t_off, cols_off, rows_off, 0, 0, 0});
             (void)block;
-            for (int row0 = 0; row0 < R; row0 += SSB_DENSE_RCH)
-                items.insert(items.end(), {t_off + row0 * kpad, cols_off, kpad, rows_off + row0, std::min(SSB_DENSE_RCH, R - row0),
-                                           kv.first[0], 0, 0});
+            if (tc_block) {
+                SsbLinTcBlock b;
+                b.R = R;
+                b.K = K;
+                b.n_kb = (K + SSB_SCK_KB - 1) / SSB_SCK_KB;
+                b.n_tiles = (R + 127) / 128;
+                b.cols_off = cols_off;
+                b.kpad = kpad;
+                b.view = kv.first[0];
+                b.rows_off = rows_off;
+                b.t_off = (long long)ttk.size();
+                b.x_off = (long long)xt_floats;
+                ttk.resize(ttk.size() + (size_t)b.n_tiles * b.n_kb * 2 * SSB_SCK_PART, 0.f);
+                float* base = &ttk[b.t_off];
+                for (int r = 0; r < R; ++r) {
+                    const int tile = r / 128, rr = r % 128;
+                    for (int k = 0; k < K; ++k) {
+                        const int kb = k / SSB_SCK_KB, kk = k % SSB_SCK_KB;
+                        float* hi = base + ((size_t)tile * b.n_kb + kb) * 2 * SSB_SCK_PART;
+                        float* lo = hi + SSB_SCK_PART;
+                        const float x = dT[(size_t)t_off + (size_t)r * kpad + k];
+                        const float h = ssb_tf32_round(x);
+                        const size_t off = ((size_t)(kk / 4) * 16 + rr / 8) * 32 + (rr % 8) * 4 + kk % 4;
+                        hi[off] = h;
+                        lo[off] = ssb_tf32_round(x - h);
+                    }
+                }
+                xt_floats += (size_t)((s->n_groups + 3) / 4) * b.n_kb * 2 * SSB_SCK_PART;
+                tcb.push_back(b);
+                L.n_tc++;
+                L.tc_max_kb = std::max(L.tc_max_kb, b.n_kb);
+                L.tc_max_tiles = std::max(L.tc_max_tiles, b.n_tiles);
+            } else {
+                for (int row0 = 0; row0 < R; row0 += SSB_DENSE_RCH)
+                    items.insert(items.end(), {t_off + row0 * kpad, cols_off, kpad, rows_off + row0,
+                                               std::min(SSB_DENSE_RCH, R - row0), kv.first[0], 0, 0});
+            }
             s->n_dense_rows += R;
             s->n_dense_blocks++;
         }
@@ -1074,6 +1132,16 @@ int build_lin_program(ssb_sim* s) {
     if (up_i(rows5, &s->d_lin_rows) || up_f(ab2, &s->d_lin_ab) || up_i(items, &s->d_dense_items) || up_i(ddesc, &s->d_dense_desc) ||
         up_i(dcols, &s->d_dense_cols) || up_i(drows, &s->d_dense_rows) || up_f(dT, &s->d_dense_T) || up_i(recs, &s->d_lin_recs))
         return fail(-2, "ssb_finalize: row program upload failed");
+    if (!tcb.empty()) {
+        SSB_CUDA(cudaMalloc((void**)&s->d_lin_tc, tcb.size() * sizeof(SsbLinTcBlock)));
+        SSB_CUDA(cudaMemcpy(s->d_lin_tc, tcb.data(), tcb.size() * sizeof(SsbLinTcBlock), cudaMemcpyHostToDevice));
+        SSB_CUDA(cudaMalloc((void**)&s->d_lin_ttk, ttk.size() * sizeof(float)));
+        SSB_CUDA(cudaMemcpy(s->d_lin_ttk, ttk.data(), ttk.size() * sizeof(float), cudaMemcpyHostToDevice));
+        SSB_CUDA(cudaMalloc((void**)&s->d_lin_xt, xt_floats * sizeof(float)));
+        SSB_CUDA(cudaMemset(s->d_lin_xt, 0, xt_floats * sizeof(float)));
+        SSB_CUDA(cudaFuncSetAttribute(k_lin_tck, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(SSB_SCK_NST * 4 * SSB_SCK_PART * sizeof(float))));
+    }
     return 0;
 }
 
@@ -1278,6 +1346,7 @@ int build_graph(ssb_sim* s, int n) {
     memcpy(saved, s->kind_launches, sizeof(saved));
     const long long saved_total = s->total_launches;
     s->dep_used = 0;
+    s->step_base = s->steps_done;
     s->graph_phase = s->pes_h.K > 0 ? (int)(s->steps_done % s->pes_h.K) : 0;
     SSB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < n; ++i) one_step(s, i, i > 0, i + 1 < n);
@@ -1665,6 +1734,7 @@ int ssb_run_steps(ssb_sim* s, int n_steps) {
     if (i < n_steps) {
         const int rest = n_steps - i;
         s->dep_used = 0;
+        s->step_base = s->steps_done + i;
         for (int r = 0; r < rest; ++r) {
             if (one_step(s, r, r > 0, r + 1 < rest)) return -2;
         }
@@ -1724,7 +1794,7 @@ int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* h
     for (int j = 0; j < n_sub; ++j) {
         const int j0 = j * sub, jn = std::min(sub, n_steps - j0);
         if (copy_tables) SSB_CUDA(cudaStreamWaitEvent(s->stream, s->io_events[2 * j], 0));
-        const bool phase_ok = s->pes_h.K == 0 || (int)(s->steps_done % s->pes_h.K) == s->graph_phase;
+        const bool phase_ok = s->pes_h.K == 0 || (int)((s->steps_done + j0) % s->pes_h.K) == s->graph_phase;
         if (graphs && s->step_graph && jn == s->graph_steps && phase_ok) {
             SSB_CUDA(cudaGraphLaunch(s->step_graph, s->stream));
             for (int k = 0; k < K_NKINDS; ++k) {
@@ -1733,6 +1803,7 @@ int ssb_run_steps_io(ssb_sim* s, const float* host_tables, int n_steps, float* h
             }
         } else {
             s->dep_used = 0;
+            s->step_base = s->steps_done + j0;
             for (int r = 0; r < jn; ++r)
                 if (one_step(s, r, r > 0, r + 1 < jn)) return -2;
             advance(s, jn);
@@ -1917,7 +1988,7 @@ void ssb_destroy(ssb_sim* s) {
     void* ptrs[] = {s->d_csr_ptr, s->d_ent0, s->d_ent1, s->d_W, s->d_small, s->d_big, s->d_dec, s->d_pes, s->d_cleanup,
                     s->d_gate, s->d_lin_rows, s->d_lin_ab, s->d_dense_items, s->d_dense_desc, s->d_dense_cols, s->d_dense_rows, s->d_dense_T, s->d_lin_recs, s->d_dec_wt, s->d_dec_wt_off, s->d_enc_t, s->d_enc_t_off, s->pes_h.hist_e, s->pes_h.hist_f, s->pes_h.part,
                     s->pes_h.counters, s->d_pes_hdesc, s->aflag, s->syn_path, s->syn_vel, s->syn_lm, s->syn_phases, s->syn_lmsp,
-                    s->syn_cos, s->syn_sin, s->syn_idx, s->d_etk, s->d_xtk, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
+                    s->syn_cos, s->syn_sin, s->syn_idx, s->d_etk, s->d_xtk, s->d_lin_tc, s->d_lin_ttk, s->d_lin_xt, s->d_ntypes, s->d_s64, s->vec, s->tab, s->st, s->act,
                     s->lenc, s->ldec, s->afilt, s->probe, s->part, s->counters, s->dyn, s->cidx, s->wpt};
     for (void* p : ptrs)
         if (p) cudaFree(p);

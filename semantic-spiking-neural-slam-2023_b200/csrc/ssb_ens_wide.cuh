@@ -388,10 +388,15 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
     uint32_t phases = 0;
     // the state row (HBM) and the bias of neuron i + 1 are requested while neuron i is computed: eight warps per SM do
     // not hide one memory round trip per neuron
+    // flags bit 2: every trial has its own network seed - bias and Voja scale are rows of the per-trial weight arena
+    const bool pt = (d[9] & 4) != 0;
+    const int pstride = pt ? 32 : 1;
+    const float* __restrict__ bias_p = pt ? c.wpt + ((size_t)g * c.n_wpt + bias_off + n0) * 32 + lane : c.W + bias_off + n0;
+    const float* __restrict__ scale_p = pt ? c.wpt + ((size_t)g * c.n_wpt + scale_off + n0) * 32 + lane : c.W + scale_off + n0;
     float sv_next = 0.f, bias_next = 0.f;
     if (i_lo < i_hi) {
         if (stateful) sv_next = __ldcs(sp + (size_t)i_lo * 32);
-        bias_next = __ldg(c.W + bias_off + n0 + i_lo);
+        bias_next = __ldg(bias_p + (size_t)i_lo * pstride);
     }
     for (int i = i_lo; i < i_hi; ++i) {
         const int t = i - i_lo, b = t % nb;
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
         float J = bias_next;
         if (i + 1 < i_hi) {
             if (stateful) sv_next = __ldcs(sp + (size_t)(i + 1) * 32);
-            bias_next = __ldg(c.W + bias_off + n0 + i + 1);
+            bias_next = __ldg(bias_p + (size_t)(i + 1) * pstride);
         }
         for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + (n0 + i) * jn_m + m), us[m * 32 + lane], J);
         ssb_mbar_wait(&wbar[warp][b], (phases >> b) & 1u);   // phases: one parity bit per buffer
@@ -438,8 +443,9 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
             const unsigned any_on = __ballot_sync(0xffffffffu, fired);
             if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + n0 + i] = (int)any_on;
         }
-        if (fired) {
-            const float sc = __ldg(c.W + scale_off + n0 + i);
+        const bool learn = fired && aL != 0.f;           // alpha = 0: a static ensemble with per-trial encoders
+        if (learn) {
+            const float sc = __ldg(scale_p + (size_t)i * pstride);
             if (DP > 0) {
 #pragma unroll
                 for (int k = 0; k < DP; ++k) {
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
                 }
             }
         }
-        const bool dirty = __any_sync(0xffffffffu, fired);
+        const bool dirty = __any_sync(0xffffffffu, learn);
         if (dirty) ssb_fence_async();
         __syncwarp();
         if (lane == 0) {
@@ -666,17 +672,22 @@ __global__ void __launch_bounds__(256, 1) k_wide_voja_stream(SsbCtx c, const int
         phases ^= 1u;
         tile_rows = (int)min((long long)SSB_VS_SUB, n_rows);
     }
+    // flags bit 2: every trial has its own network seed - bias and Voja scale are rows of the per-trial weight arena
+    const bool pt = (d[9] & 4) != 0;
+    const int pstride = pt ? 32 : 1;
+    const float* __restrict__ bias_p = pt ? c.wpt + ((size_t)g * c.n_wpt + bias_off + n0) * 32 + lane : c.W + bias_off + n0;
+    const float* __restrict__ scale_p = pt ? c.wpt + ((size_t)g * c.n_wpt + scale_off + n0) * 32 + lane : c.W + scale_off + n0;
     float sv_next = 0.f, bias_next = 0.f;
     if (i_lo < i_hi) {
         if (stateful) sv_next = __ldcs(sp + (size_t)i_lo * 32);
-        bias_next = __ldg(c.W + bias_off + n0 + i_lo);
+        bias_next = __ldg(bias_p + (size_t)i_lo * pstride);
     }
     for (int i = i_lo; i < i_hi; ++i) {
         float sv = sv_next;
         float J = bias_next;
         if (i + 1 < i_hi) {
             if (stateful) sv_next = __ldcs(sp + (size_t)(i + 1) * 32);
-            bias_next = __ldg(c.W + bias_off + n0 + i + 1);
+            bias_next = __ldg(bias_p + (size_t)(i + 1) * pstride);
         }
         for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + (n0 + i) * jn_m + m), us[m * 32 + lane], J);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -719,20 +730,21 @@ __global__ void __launch_bounds__(256, 1) k_wide_voja_stream(SsbCtx c, const int
         const bool fired = out != 0.f;
         const unsigned any_on = __ballot_sync(0xffffffffu, fired);
         if (lane == 0) c.aflag[(size_t)g * c.n_act + act0 + n0 + i] = (int)any_on;
-        if (any_on) {
+        const bool learn = fired && aL != 0.f;           // alpha = 0: a static ensemble with per-trial encoders
+        if (__any_sync(0xffffffffu, learn)) {
             // Voja: only the lanes that spiked touch their words (the rows were just streamed: L2 re-read, 32-byte sector
             // writes).  Measured on B200 at d = 649: this lane = trial form 652 us per launch; a lanes = rows form (one
             // spiking trial at a time, every row in flight) 1 275 us - uncoalesced sector accesses cost ~4 LSU cycles each,
             // so the fewer sector operations win, not the fewer round trips.
-            const float sc = __ldg(c.W + scale_off + n0 + i);
+            const float sc = __ldg(scale_p + (size_t)i * pstride);
             float* Eg = eg + (size_t)(i - i_lo) * dims * 32 + lane;
             for (int k0 = 0; k0 < dims; k0 += 16) {
                 float ev[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) ev[u] = (fired && k0 + u < dims) ? __ldcg(Eg + (size_t)(k0 + u) * 32) : 0.f;
+                for (int u = 0; u < 16; ++u) ev[u] = (learn && k0 + u < dims) ? __ldcg(Eg + (size_t)(k0 + u) * 32) : 0.f;
 #pragma unroll
                 for (int u = 0; u < 16; ++u)
-                    if (fired && k0 + u < dims)
+                    if (learn && k0 + u < dims)
                         Eg[(size_t)(k0 + u) * 32] = ev[u] + aL * (sc * (out * xs[(k0 + u) * 32 + lane]) - out * ev[u]);
             }
         }

@@ -8,6 +8,7 @@
 //   ssb_cleanup.cuh    k_cleanup_scan, k_cleanup_scan_tc, k_scan_xtiles, k_cleanup_scan_tck, k_cleanup_pick, k_gate
 //   ssb_ens_wide_tck.cuh  k_wide_static_tck
 //   ssb_lin.cuh        k_lin, k_advance
+//   ssb_lin_tck.cuh    k_lin_xtiles, k_lin_tck (large dense blocks of the row program on tcgen05)
 //   ssb_ssp.cuh        k_ssp_encode, k_decode_prep
 #pragma once
 #include "ssb_common.cuh"
@@ -19,4 +20,5 @@
 #include "ssb_cleanup.cuh"
 #include "ssb_ens_wide_tck.cuh"
 #include "ssb_lin.cuh"
+#include "ssb_lin_tck.cuh"
 #include "ssb_ssp.cuh"

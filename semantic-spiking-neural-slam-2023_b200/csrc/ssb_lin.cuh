@@ -56,7 +56,7 @@ struct SsbLinArgs {
     int n_recs;
 };
 
-__global__ void __launch_bounds__(128, 8) k_lin(SsbCtx c, SsbLinArgs L, int i_rel) {
+__global__ void __launch_bounds__(128, 6) k_lin(SsbCtx c, SsbLinArgs L, int i_rel) {
     __shared__ __align__(16) float s_t[4][SSB_DENSE_RCH][SSB_DENSE_SLAB];
     __shared__ float s_red[4][SSB_DENSE_RCH][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

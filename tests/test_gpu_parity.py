@@ -198,6 +198,35 @@ def test_generic_width_network_matches_oracle():
     assert _rel(got[1], _oracle(sc, sim, 1, 120).data[sc.probe]) < 1e-4
 
 
+@pytest.mark.parametrize("env", [{}, {"SSB_LIN": "ffma", "SSB_ENCODE": "ffma", "SSB_SCAN": "ffma", "SSB_DECODE": "ffma"}])
+def test_wide_d295_network_on_the_k_blocked_tensor_core_kernels(env, monkeypatch):
+    """d = 295 (2-D, 7 x 7 scale / rotation pairs) at reduced neuron counts: wide enough for every K-blocked tcgen05 path of
+    BASELINE configs[4] (d = 649) - grid scan (k_cleanup_scan_tck), static wide encode (k_wide_static_tck), column-tiled
+    decode (k_decode_tc with 3 tiles), the 592 x 295 / 295 x 592 dense blocks of the row program (k_lin_tck) - against the
+    oracle in rate mode, and the same network on the FFMA kernels."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n_steps = 60
+    sc = scenarios.make_slam(n_trials=3, n_steps=n_steps, ssp_dim=295, pi_n_neurons=30, mem_n_neurons=96,
+                             circonv_n_neurons=10, n_landmarks=8, T=20.0, neuron_type="lifrate", view_rad=0.6,
+                             grid_points_per_dim=40)
+    assert sc.ssp_space.ssp_dim == 295
+    slam = sc.extra["slam"]
+    with _Simulator()(sc.network, dt=sc.dt, n_trials=3, trial_inputs=sc.trial_inputs) as sim:
+        sim.run_steps(n_steps)
+        idx = sim.cleanup_indices()[0].copy()
+        dec = sim.learned_decoders(slam.assomemory.conn_out)
+    got = sim.data[sc.probe]
+    for trial in (0, 2):
+        ref = _oracle(sc, sim, trial, n_steps)
+        want = ref.data[sc.probe]
+        assert np.max(np.abs(want)) > 0.05
+        assert _rel(got[trial], want) < 1e-4
+        assert idx[trial] == ssp_ref.cleanup_index(slam.sample_ssps, ref.signals[slam.gridcells, "in"].a)
+        want_dec = ref.learned_weights(slam.assomemory.conn_out)
+        assert np.max(np.abs(dec[trial] - want_dec)) < 1e-4 * np.max(np.abs(want_dec)) + 1e-9
+
+
 @pytest.mark.parametrize("env", [{"SSB_SCAN": "ffma"}, {"SSB_DECODE": "ffma"}, {"SSB_ENCODE": "tc"},
                                  {"SSB_SCAN": "ffma", "SSB_DECODE": "ffma", "SSB_SERIAL": "1"},
                                  {"SSB_PES_DEFER": "4"}, {"SSB_PES_FUSE": "1"}, {"SSB_LEVEL_DEPS": "0"}])
