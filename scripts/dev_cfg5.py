@@ -14,7 +14,8 @@ steps = int(os.environ.get("STEPS", "16"))
 nt = os.environ.get("NT", "lifrate")
 t0 = time.time()
 sc = scenarios.make_slam(n_trials=B, n_steps=4 * steps + 4, ssp_dim=649, pi_n_neurons=500, mem_n_neurons=970,
-                         circonv_n_neurons=100, n_landmarks=50, T=20.0, domain_dim=3, grid_points_per_dim=30,
+                         circonv_n_neurons=100, n_landmarks=50, T=20.0, domain_dim=3,
+                         grid_points_per_dim=int(os.environ.get('GRID', '30')),
                          distinct_tables=int(os.environ.get('DISTINCT', '2')), neuron_type=nt, view_rad=0.6)
 print(f"[cfg5] scenario {time.time()-t0:.1f}s d={sc.ssp_space.ssp_dim}", flush=True)
 t0 = time.time()

@@ -203,6 +203,7 @@ struct ssb_sim {
     float *afilt = nullptr, *probe = nullptr, *part = nullptr;
     float* wpt = nullptr;                   // per-trial static weights [G][n_wpt][32] (scalar per_trial_weights = 1)
     long long n_wpt = 0;
+    bool per_trial = false;                 // plan lowered with per-trial static weights (wide ensembles: encoders in lenc, decoders in ldec)
     int* counters = nullptr;
     int* aflag = nullptr;
     long long* dyn = nullptr;
@@ -905,7 +906,7 @@ bool decode_tc_allowed() {
 int build_decode_tiles(ssb_sim* s) {
     const int n_dec = (int)(s->h_dec.size() / 9);
     s->dec_tc_level.assign(s->n_levels, 0);
-    if (n_dec == 0 || !decode_tc_allowed()) return 0;
+    if (n_dec == 0 || !decode_tc_allowed() || s->per_trial) return 0;      // per-trial decoders: no shared GEMM operand
     int max_jpad = 0;
     for (int i = 0; i < n_dec; ++i) max_jpad = std::max(max_jpad, s->h_dec[i * 9 + 2]);
     const int N = max_jpad <= 64 ? 64 : 128, KS = max_jpad <= 64 ? 64 : 32;
@@ -1296,7 +1297,12 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
             }
             dim3 grid(max_chunks, (G + 3) / 4, st[5]);
             if (s->dec_tc_level[lvl]) grid.z = st[5] * s->dec_tc_nt;
-            if (s->dec_tc_level[lvl] && s->dec_tc_n == 64)
+            if (s->per_trial) {
+                int max_jp = 4;
+                for (int i = 0; i < st[5]; ++i) max_jp = std::max(max_jp, (s->h_dec[(st[4] + i) * 9 + 1] + 3) & ~3);
+                const int n_jt = (max_jp + SSB_PES_JT - 1) / SSB_PES_JT;
+                k_decode_pt<<<dim3(4, G, st[5] * n_jt), 256, 0, D>>>(c, s->d_dec, st[4], n_jt);
+            } else if (s->dec_tc_level[lvl] && s->dec_tc_n == 64)
                 k_decode_tc<64, 64><<<grid, 256, (size_t)(4 * 128 * 64 + 4 * 64 * 64) * sizeof(float), D>>>(
                     c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off, s->dec_tc_nt);
             else if (s->dec_tc_level[lvl])
@@ -1474,6 +1480,7 @@ int ssb_finalize(ssb_sim* s) {
     if (s->level_deps.size() != (size_t)s->n_levels * s->n_levels) s->level_deps.clear();
     if (const char* e = getenv("SSB_LEVEL_DEPS")) if (e[0] == '0') s->level_deps.clear();   // A/B switch: level barriers
     if ((int)s->h_stages.size() != s->n_levels * 12) return fail(-1, "ssb_finalize: stages array has wrong size");
+    s->per_trial = iscalar(s, "per_trial_weights") != 0;
     if (int rc = setup_pes_defer(s)) return rc;        // decides whether k_pes_hist owns the PES activity traces
     if (int rc = build_lin_program(s)) return rc;
     if (int rc = build_decode_tiles(s)) return rc;
@@ -1534,12 +1541,15 @@ int ssb_finalize(ssb_sim* s) {
             return fail(-1, "ssb_finalize: narrow-ensemble weight stride out of range");
 
     const int B = s->B;
-    if (iscalar(s, "per_trial_weights") != 0) {
-        // every trial has its own network seed: the static weights become one more per-trial arena.  Supported for plans
-        // made of narrow ensembles only (PathIntegration); wide ensembles / decoders would need per-trial GEMM operands.
-        if (!s->h_big.empty() || !s->h_dec.empty() || !s->h_cleanup.empty())
-            return fail(-1, "ssb_finalize: per-trial static weights are supported for narrow-ensemble plans only");
-        s->n_wpt = (long long)(s->arrays["weights"].bytes.size() / sizeof(float));
+    if (s->per_trial) {
+        // every trial has its own network seed: the seed-dependent static weights (narrow ensembles' packed rows, wide
+        // ensembles' bias / Voja scale) become one more per-trial arena; wide encoders live in lenc, wide decoders in ldec
+        // (the lowering flags those ensembles and points the decoder descriptors at ldec rows).
+        if (!s->arrays.count("weights_pt")) return fail(-1, "ssb_finalize: per_trial_weights needs the weights_pt array");
+        for (size_t i = 0; i + 15 < s->h_big.size(); i += 16)
+            if (!(s->h_big[i + 9] & 1) || !(s->h_big[i + 9] & 4))
+                return fail(-1, "ssb_finalize: per-trial plan with a shared-weight wide ensemble");
+        s->n_wpt = (long long)(s->arrays["weights_pt"].bytes.size() / sizeof(float));
         if (alloc_rows(&s->wpt, s->n_wpt, B)) return -2;
     }
     if (alloc_rows(&s->vec, s->nv, B)) return -2;

@@ -393,6 +393,8 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
     const int pstride = pt ? 32 : 1;
     const float* __restrict__ bias_p = pt ? c.wpt + ((size_t)g * c.n_wpt + bias_off + n0) * 32 + lane : c.W + bias_off + n0;
     const float* __restrict__ scale_p = pt ? c.wpt + ((size_t)g * c.n_wpt + scale_off + n0) * 32 + lane : c.W + scale_off + n0;
+    const float* __restrict__ jn_p = pt ? c.wpt + ((size_t)g * c.n_wpt + jn_w + (size_t)n0 * jn_m) * 32 + lane
+                                        : c.W + jn_w + (size_t)n0 * jn_m;
     float sv_next = 0.f, bias_next = 0.f;
     if (i_lo < i_hi) {
         if (stateful) sv_next = __ldcs(sp + (size_t)i_lo * 32);
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(128) k_wide_voja(SsbCtx c, const int* __restri
             if (stateful) sv_next = __ldcs(sp + (size_t)(i + 1) * 32);
             bias_next = __ldg(bias_p + (size_t)(i + 1) * pstride);
         }
-        for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + (n0 + i) * jn_m + m), us[m * 32 + lane], J);
+        for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(jn_p + (size_t)(i * jn_m + m) * pstride), us[m * 32 + lane], J);
         ssb_mbar_wait(&wbar[warp][b], (phases >> b) & 1u);   // phases: one parity bit per buffer
         phases ^= 1u << b;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -677,6 +679,8 @@ __global__ void __launch_bounds__(256, 1) k_wide_voja_stream(SsbCtx c, const int
     const int pstride = pt ? 32 : 1;
     const float* __restrict__ bias_p = pt ? c.wpt + ((size_t)g * c.n_wpt + bias_off + n0) * 32 + lane : c.W + bias_off + n0;
     const float* __restrict__ scale_p = pt ? c.wpt + ((size_t)g * c.n_wpt + scale_off + n0) * 32 + lane : c.W + scale_off + n0;
+    const float* __restrict__ jn_p = pt ? c.wpt + ((size_t)g * c.n_wpt + jn_w + (size_t)n0 * jn_m) * 32 + lane
+                                        : c.W + jn_w + (size_t)n0 * jn_m;
     float sv_next = 0.f, bias_next = 0.f;
     if (i_lo < i_hi) {
         if (stateful) sv_next = __ldcs(sp + (size_t)i_lo * 32);
@@ -689,7 +693,7 @@ __global__ void __launch_bounds__(256, 1) k_wide_voja_stream(SsbCtx c, const int
             if (stateful) sv_next = __ldcs(sp + (size_t)(i + 1) * 32);
             bias_next = __ldg(bias_p + (size_t)(i + 1) * pstride);
         }
-        for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(c.W + jn_w + (n0 + i) * jn_m + m), us[m * 32 + lane], J);
+        for (int m = 0; m < jn_m; ++m) J = fmaf(__ldg(jn_p + (size_t)(i * jn_m + m) * pstride), us[m * 32 + lane], J);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int k = 0;
         while (k < dims) {

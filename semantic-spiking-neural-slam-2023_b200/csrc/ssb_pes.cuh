@@ -292,3 +292,78 @@ __global__ void __launch_bounds__(128) k_pes_clear(SsbCtx c, SsbPesDefer h, int 
     if (r < h.rows_e) ssb_grp(h.hist_e, h.rows_e, blockIdx.y, lane)[(size_t)r * 32] = 0.f;
 }
 
+
+// --------------------------------------------------------------------------------------
+// Static decoders when every trial has its own network seed (per-trial static weights): no GEMM is left - every trial has
+// its own Wd - so the decode takes the sparse form of k_pes_defer without the history: decoders live in the ldec arena in
+// the same [neuron][trial][JP] layout, one WARP per trial, lanes = output columns, the trial's spikes compacted from the
+// ensemble kernel's flag words (SSB_DPT_CH neurons at a time), 8 spikes in flight.  A warp walks ALL neurons of its
+// ensemble, so there is no split-K and the result is written straight to the decoded rows.
+// desc (the static-decoder descriptor): n size_out jpad act0 d_off out_vec - - -      (d_off = ldec arena row)
+// grid (4 trial octets, G, decoders * column tiles of SSB_PES_JT) x 256
+#define SSB_DPT_CH 1024
+__global__ void __launch_bounds__(256) k_decode_pt(SsbCtx c, const int* __restrict__ desc, int item0, int n_jt_max) {
+    __shared__ int sflag[SSB_DPT_CH];
+    __shared__ int slist[8][SSB_DPT_CH];
+    __shared__ float red[SSB_PES_JT][8];
+    const int item = blockIdx.z / n_jt_max, jt = blockIdx.z - item * n_jt_max;
+    const int* d = desc + (item0 + item) * 9;
+    const int n = d[0], size_out = d[1], act0 = d[3], d_off = d[4], out_vec = d[5];
+    const int JP = ssb_pes_jp(size_out);
+    const int j0 = jt * SSB_PES_JT;
+    if (j0 >= JP) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.y, oct = blockIdx.x;
+    const int t = oct * 8 + warp;                         // this warp's trial inside the group
+    const int* __restrict__ fl = c.aflag + (size_t)g * c.n_act + act0;
+    const float* __restrict__ ap = c.act + ((size_t)g * c.n_act + act0) * 32 + t;
+    const float* __restrict__ dl = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)t * JP + j0 + lane;
+    constexpr int NC = SSB_PES_JT / 32;
+    float acc[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) acc[q] = 0.f;
+    int* list = slist[warp];
+    for (int c0 = 0; c0 < n; c0 += SSB_DPT_CH) {
+        const int c1 = min(n, c0 + SSB_DPT_CH);
+        __syncthreads();                                  // the previous chunk's flag words are no longer read
+        for (int i = c0 + (int)threadIdx.x; i < c1; i += 256) sflag[i - c0] = __ldg(fl + i);
+        __syncthreads();
+        int cnt = 0;
+        for (int base = c0; base < c1; base += 32) {
+            const int fw = (base + lane < c1) ? sflag[base + lane - c0] : 0;
+            const bool on = (fw >> t) & 1;
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) list[cnt + __popc(m & ((1u << lane) - 1u))] = base + lane;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        constexpr int U = 8;
+        for (int s0 = 0; s0 < cnt; s0 += U) {
+            float a[U], w[U][NC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool on = s0 + u < cnt;
+                const size_t ni = (size_t)(on ? list[s0 + u] : c0);
+                a[u] = on ? __ldg(ap + ni * 32) : 0.f;
+#pragma unroll
+                for (int q = 0; q < NC; ++q)
+                    w[u][q] = (on && j0 + q * 32 + lane < JP) ? __ldcs(dl + ni * JP * 32 + q * 32) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int q = 0; q < NC; ++q) acc[q] = fmaf(w[u][q], a[u], acc[q]);
+            }
+        }
+        __syncwarp();
+    }
+    // transpose through shared memory so that the decoded rows get 32-byte runs (8 consecutive trials per row)
+#pragma unroll
+    for (int q = 0; q < NC; ++q) red[q * 32 + lane][warp] = acc[q];
+    __syncthreads();
+    float* vo = c.vec + ((size_t)g * c.nv + out_vec) * 32 + oct * 8;
+    for (int r = threadIdx.x >> 3; r < SSB_PES_JT; r += 32) {
+        const int row = j0 + r;
+        if (row < size_out) vo[(size_t)row * 32 + (threadIdx.x & 7)] = red[r][threadIdx.x & 7];
+    }
+}

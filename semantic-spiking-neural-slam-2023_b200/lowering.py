@@ -111,14 +111,18 @@ class DevicePlan:
         self.learned_enc: dict = {}     # ens -> (row0, n, dims)   rows are n*dims + k
         self.learned_dec: dict = {}     # conn -> (row0, size_out, n) rows are j*n + i
         self.static_dec: dict = {}      # conn -> (w_off, size_out, jpad, n) for big decoders
+        self.pt_enc: dict = {}          # per-trial plans: static wide ens -> (lenc row0, n, dims)
+        self.pt_dec: dict = {}          # per-trial plans: static wide decoder -> (ldec row0, size_out, n)
         self.filters: dict = {}         # conn/probe -> (filter_row0, size)
         self.launches: list = []        # human-readable launch order
         self.stats: dict = {}
 
 
 class _Lowerer:
-    def __init__(self, network, model: BuiltModel, n_trials=1):
+    def __init__(self, network, model: BuiltModel, n_trials=1, per_trial=False):
         self.net, self.model, self.dt = network, model, model.dt
+        # every trial has its own network seed: seed-dependent static weights go to per-trial arenas (see lower())
+        self.per_trial = bool(per_trial)
         self.n_groups = max(1, -(-int(n_trials) // 32))
         self.nodes = network.all_nodes
         self.ensembles = network.all_ensembles
@@ -193,6 +197,8 @@ class _Lowerer:
                                                       lambda per: N_SM * PES_CTAS_PER_SM, 1, k_max)
                     if os.environ.get("SSB_PES_CHUNKS"):          # tuning knob (scripts/dev_perf.py sweeps)
                         self.dec_chunks[c] = int(max(1, min(int(os.environ["SSB_PES_CHUNKS"]), k_max)))
+                elif self.per_trial:   # per-trial static decoders: k_decode_pt walks the whole ensemble per trial
+                    self.dec_chunks[c] = 1
                 else:                  # static decoders
                     jpad = -(-self._out_size(c) // DEC_TILE) * DEC_TILE
                     quads = -(-self.n_groups // 4)
@@ -527,6 +533,16 @@ class _Lowerer:
             w_len += a.size
             return off
 
+        # per-trial plans: the seed-dependent scalars / narrow-ensemble rows live in the per-trial weight arena instead;
+        # their offsets come from _pt_blocks (the same walk fills the arena for every trial's model)
+        pt_off = {}
+        if self.per_trial:
+            off = 0
+            for key, a in self._pt_blocks(self.model):
+                off += (-off) % 4
+                pt_off[key] = off
+                off += a.size
+
         ntypes, ntype_ids = [], {}
 
         def ntype_id(nt):
@@ -554,6 +570,7 @@ class _Lowerer:
         pes_trace, cleanup_s64 = [], [[] for _ in range(n_levels)]
         nn = n_act = n_lenc = n_ldec = n_afilt = n_ldec_words = 0
         n_small = n_big = 0
+        n_pt_enc = n_pt_dec = 0
         n_part = n_jtiles = 0
         pes_level = -1
 
@@ -589,7 +606,7 @@ class _Lowerer:
                 packed[:, 1:1 + dims] = p.scaled_encoders
                 if decs:
                     packed[:, 1 + dims:1 + dims + nout] = np.vstack(decs).T
-                w_off = add_w(packed)
+                w_off = pt_off[(ens, "packed")] if self.per_trial else add_w(packed)
                 out_vec = int(dev_col[self.dec_col[outs[0]]]) if outs else 0
                 # decoded slots of one ensemble are contiguous by construction
                 small_desc[lvl].append([n, dims, nout, state0, w_off, in_row0, out_vec, tid, stride])
@@ -611,16 +628,29 @@ class _Lowerer:
                 plan.learned_enc[ens] = (enc_off, n, dims)
                 voja_alpha = lrt.learning_rate * dt
                 voja_row = materialize(lrow, lvl)
-                scale_off = add_w(p.gain / ens.radius)
+                scale_off = pt_off[(ens, "scale")] if self.per_trial else add_w(p.gain / ens.radius)
+            elif self.per_trial:
+                # static encoders of a trial's own model: per-trial rows of the lenc arena, walked by the Voja kernel with
+                # alpha = 0 (flags bit 0), bias from the per-trial weight arena (flags bit 2)
+                flags |= 1
+                enc_off = n_lenc
+                n_lenc += n * dims
+                n_pt_enc += n * dims
+                plan.pt_enc[ens] = (enc_off, n, dims)
             else:
                 enc = np.zeros((n, dpad))
                 enc[:, :dims] = p.scaled_encoders
                 enc_off = add_w(enc)
-            bias_off = add_w(p.bias)
+            if self.per_trial:
+                flags |= 4
+                bias_off = pt_off[(ens, "bias")]
+            else:
+                bias_off = add_w(p.bias)
             jn_row0 = jn_m = jn_w = 0
             if ens in ens_jn:
                 u, G = ens_jn[ens]
-                jn_row0, jn_m, jn_w = materialize(u, lvl), u.shape[0], add_w(G)
+                jn_row0, jn_m = materialize(u, lvl), u.shape[0]
+                jn_w = pt_off[(ens, "jn")] if self.per_trial else add_w(G)
                 flags |= 2
             big_desc[lvl].append([n, dims, dpad, state0, act0, enc_off, bias_off, in_row0, tid, flags,
                                   jn_row0, jn_m, jn_w, voja_row, scale_off,
@@ -655,6 +685,13 @@ class _Lowerer:
                                      int(np.float32(alpha).view(np.int32)),
                                      int(np.float32(decay).view(np.int32)),
                                      int(np.float32(1.0 - decay).view(np.int32))] + splitk(c, size_out))
+                elif self.per_trial:
+                    jpad = size_out + ((-size_out) % DEC_TILE)
+                    d_off = n_ldec
+                    n_ldec += (-(-size_out // 4) * 4) * n            # [neuron][trial][JP], as the learned decoders
+                    n_pt_dec += size_out * n
+                    plan.pt_dec[c] = (d_off, size_out, n)
+                    dec_desc[lvl].append([n, size_out, jpad, act0, d_off, out_vec] + splitk(c, size_out))
                 else:
                     jpad = size_out + ((-size_out) % DEC_TILE)
                     Wd = np.zeros((n, jpad))
@@ -770,6 +807,7 @@ class _Lowerer:
             "csr_ent1": self._entries(csr_idx, csr_val, NF, NF, tab_row0, NT),
             # 8 floats of slack: bulk copies of bias / current weights round their length up to 16 bytes
             "weights": np.concatenate(W + [np.zeros(8, dtype=np.float32)]),
+            **({"weights_pt": self.trial_weights(self.model)} if self.per_trial else {}),
             "ens_small": arr(cat["small"], 9),
             "ens_big": arr(cat["big"], 16),
             "dec": arr(cat["dec"], 9),
@@ -789,7 +827,14 @@ class _Lowerer:
                                  chunk_cap=chunk_cap, n_part=n_part, n_jtiles=n_jtiles, pes_level=pes_level,
                                  lin0=lin0, n_lin=len(lin_rows) - lin0))
         n_static = int(sum(a.size for a in W))
-        plan.stats = dict(n_neurons=nn, n_filter_states=NF, n_learned=n_lenc + n_ldec_words, n_static_weights=n_static,
+        if self.per_trial:
+            plan.scalars["per_trial_weights"] = 1.0
+            # static weights a trial owns (read once per step, never written): narrow rows + bias / scale + wide enc / dec
+            n_pt_weights = int(plan.arrays["weights_pt"].size - 8) + n_pt_enc + n_pt_dec
+        else:
+            n_pt_weights = 0
+        plan.stats = dict(n_pt_weights=n_pt_weights, n_neurons=nn, n_filter_states=NF, n_learned=n_lenc - n_pt_enc + n_ldec_words,
+                          n_static_weights=n_static,
                           n_table_words=NT, n_probe_words=n_probe_rows, n_small=n_small, n_big=n_big,
                           n_levels=n_levels, csr_nnz=len(csr_idx), n_afilt=n_afilt, n_act=n_act)
         n_small_neurons = int(sum(e.n_neurons for e in self.ensembles if self.is_small[e]))
@@ -799,12 +844,55 @@ class _Lowerer:
         plan.stats["bytes_by_kind"] = {
             "ens_small": 16 * n_small_neurons,
             "ens_wide": 16 * (nn - n_small_neurons - n_voja_neurons),
-            "ens_voja": 16 * n_voja_neurons + 8 * n_lenc,
+            "ens_voja": 16 * n_voja_neurons + 8 * (n_lenc - n_pt_enc),
             "pes": 8 * n_ldec_words,
             "lin": 8 * (NF + n_afilt) + 4 * n_probe_rows,
             "inputs": 4 * NT,
         }
         return plan
+
+    def _pt_blocks(self, model):
+        """(key, float array) blocks of the per-trial weight arena in arena order: a narrow ensemble's packed
+        ``[bias | scaled encoders | decoders]`` rows; a wide ensemble's Voja scale (if learned), bias and direct neuron-current
+        weights."""
+        voja_posts = {c.post_obj for c in self.conns
+                      if c.learning_rule is not None and compat.rule_kind(c.learning_rule.learning_rule_type) == "voja"}
+        saved, self.model = self.model, model
+        try:
+            for ens in self.ensembles:
+                p = model.params[ens]
+                if self.is_small[ens]:
+                    outs = self.ens_dec_conns[ens]
+                    nout = sum(self._out_size(c) for c in outs)
+                    dims = ens.dimensions
+                    stride = 1 + dims + nout
+                    stride += (-stride) % 4
+                    packed = np.zeros((ens.n_neurons, stride))
+                    packed[:, 0] = p.bias
+                    packed[:, 1:1 + dims] = p.scaled_encoders
+                    if outs:
+                        packed[:, 1 + dims:1 + dims + nout] = np.vstack([self._dec_weights(c) for c in outs]).T
+                    yield (ens, "packed"), np.ascontiguousarray(packed, dtype=np.float32).reshape(-1)
+                else:
+                    if ens in voja_posts:
+                        yield (ens, "scale"), np.asarray(p.gain / ens.radius, dtype=np.float32).reshape(-1)
+                    yield (ens, "bias"), np.asarray(p.bias, dtype=np.float32).reshape(-1)
+                    trs = [compat.transform_of(c) for c in self.incoming.get(ens.neurons, [])]
+                    if trs:      # direct neuron currents: gain * transform, [n][m] (see ens_jn in lower())
+                        yield (ens, "jn"), np.asarray(p.gain[:, None] * np.hstack(trs), dtype=np.float32).reshape(-1)
+        finally:
+            self.model = saved
+
+    def trial_weights(self, model):
+        """The per-trial weight arena of ``model`` (one float per arena row), blocks aligned to 4 like the shared array."""
+        out, off = [], 0
+        for _, a in self._pt_blocks(model):
+            pad = (-off) % 4
+            if pad:
+                out.append(np.zeros(pad, dtype=np.float32))
+            out.append(a)
+            off += pad + a.size
+        return np.concatenate(out + [np.zeros(8, dtype=np.float32)])
 
     @staticmethod
     def _entries(idx, val, par, nf, tab_row0=0, nt=0):
@@ -834,40 +922,35 @@ class _Lowerer:
         return self.expr_out(obj)[_idx(probe.slice, obj.size_out)].tocsr()
 
 
-def lower(network, model: BuiltModel, chunk_cap=256, n_trials=1) -> DevicePlan:
-    """Network + built parameters -> :class:`DevicePlan` (``n_trials`` only tunes launch geometry)."""
-    return _Lowerer(network, model, n_trials).lower(chunk_cap)
+def lower(network, model: BuiltModel, chunk_cap=256, n_trials=1, per_trial=False) -> DevicePlan:
+    """Network + built parameters -> :class:`DevicePlan` (``n_trials`` only tunes launch geometry).  ``per_trial``: every
+    trial has its own network seed - seed-dependent static weights are laid out in per-trial arenas (``weights_pt``, wide
+    encoders in ``lenc``, wide decoders in ``ldec``); ``model`` then only provides the layout and trial 0's values."""
+    return _Lowerer(network, model, n_trials, per_trial).lower(chunk_cap)
 
 
-def narrow_ensemble_weights(network, model: BuiltModel, n_trials=1) -> np.ndarray:
-    """The ``weights`` array of the plan of a network made of narrow ensembles only (PathIntegration), for another built
-    model of the same graph: packed ``[bias | scaled encoders | decoders]`` rows per neuron, in plan order.  Used to fill
-    the per-trial weight arena when every trial has its own network seed (the rest of the plan is seed-independent)."""
-    low = _Lowerer(network, model, n_trials)
+def trial_weights(network, model: BuiltModel, n_trials=1):
+    """Seed-dependent static weights of another built model of the same graph, for a plan lowered with ``per_trial=True``:
+    ``(weights_pt array, {wide ens: scaled encoders [n, dims]}, {wide static decoder: weights [size_out, n]})``."""
+    low = _Lowerer(network, model, n_trials, True)
     low.classify_ensembles()
-    out = []
+    pes_conns = {c for c in low.conns
+                 if c.learning_rule is not None and compat.rule_kind(c.learning_rule.learning_rule_type) == "pes"}
+    enc, dec = {}, {}
     for ens in low.ensembles:
-        if not low.is_small[ens]:
-            raise NotImplementedError("per-trial static weights: narrow ensembles only")
-        p = model.params[ens]
-        outs = low.ens_dec_conns[ens]
-        nout = sum(low._out_size(c) for c in outs)
-        dims = ens.dimensions
-        stride = 1 + dims + nout
-        stride += (-stride) % 4
-        packed = np.zeros((ens.n_neurons, stride))
-        packed[:, 0] = p.bias
-        packed[:, 1:1 + dims] = p.scaled_encoders
-        if outs:
-            packed[:, 1 + dims:1 + dims + nout] = np.vstack([low._dec_weights(c) for c in outs]).T
-        out.append(np.ascontiguousarray(packed, dtype=np.float32).reshape(-1))
-    return np.concatenate(out + [np.zeros(8, dtype=np.float32)])
+        if low.is_small[ens]:
+            continue
+        enc[ens] = np.asarray(model.params[ens].scaled_encoders, dtype=np.float32)
+        for c in low.ens_dec_conns[ens]:
+            if c not in pes_conns:
+                dec[c] = np.asarray(low._dec_weights(c), dtype=np.float32)
+    return low.trial_weights(model), enc, dec
 
 
-def algorithmic_bytes_per_trial_step(stats, per_trial_weights=False):
-    """SURVEY.md §8(d) traffic model (fp32): state R+W, filters R+W, learned R+W, inputs, probes."""
+def algorithmic_bytes_per_trial_step(stats, per_trial_weights=None):
+    """SURVEY.md §8(d) traffic model (fp32): state R+W, filters R+W, learned R+W, inputs, probes; plans lowered with
+    per-trial static weights also read every weight a trial owns once per step (``stats['n_pt_weights']``)."""
     b = 16 * stats["n_neurons"] + 8 * (stats["n_filter_states"] + stats["n_afilt"]) + 8 * stats["n_learned"]
-    if per_trial_weights:
-        b += 4 * (stats["n_static_weights"] + stats["n_neurons"])
+    b += 4 * stats.get("n_pt_weights", 0)
     b += 4 * stats["n_table_words"] + 4 * stats["n_probe_words"]
     return int(b)

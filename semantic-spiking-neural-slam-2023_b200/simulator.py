@@ -115,18 +115,16 @@ class Simulator:
         self.models = None
         if trial_network_seeds is not None:
             # every trial is the driver started with its own --seed (run_slam.py:151): one built model per trial, per-trial
-            # static weights on the device (narrow-ensemble plans: PathIntegration)
+            # static weights on the device (narrow ensembles: per-trial weight arena; wide ensembles: encoders in the lenc
+            # arena, decoders in the ldec arena)
             if len(trial_network_seeds) != self.n_trials:
                 raise ValueError("trial_network_seeds must have one entry per trial")
             self.models = _build_models(network, self.dt, list(trial_network_seeds), build_workers)
             model = self.models[0]
         self.model = model if model is not None else build_model(network, dt=self.dt, seed=seed)
-        self.plan = lowering.lower(network, self.model, chunk_cap=self.chunk_steps, n_trials=self.n_trials)
+        self.plan = lowering.lower(network, self.model, chunk_cap=self.chunk_steps, n_trials=self.n_trials,
+                                   per_trial=self.models is not None)
         if self.models is not None:
-            if self.plan.stats["n_big"] or len(self.plan.arrays["cleanup"]):
-                raise NotImplementedError("per-trial network seeds are supported for narrow-ensemble networks "
-                                          "(PathIntegration); wide ensembles share their static weights")
-            self.plan.scalars["per_trial_weights"] = 1.0
             if trial_seeds is None:
                 trial_seeds = [None] * self.n_trials          # nengo's own start-voltage draw of every trial's model
         self._trial_inputs = dict(trial_inputs or {})
@@ -244,7 +242,7 @@ class Simulator:
     # learned decoders: a trial group's block is [neuron][trial][JP] floats (csrc/ssb_pes.cuh), JP = size_out rounded up to 4
     def _upload_decoders(self, conn, per_trial):
         """``per_trial`` [n_trials, size_out, n] -> device order [group][n * JP rows][32]."""
-        row0, size_out, n = self.plan.learned_dec[conn]
+        row0, size_out, n = conn if isinstance(conn, tuple) else self.plan.learned_dec[conn]
         jp = -(-size_out // 4) * 4
         G = self.B // 32
         full = np.zeros((self.B, jp, n), dtype=np.float32)
@@ -267,19 +265,27 @@ class Simulator:
         m, plan = self.model, self.plan
         nn = int(plan.scalars["nn"])
         if self.models is not None:
-            # per-trial static weights: the plan's weight array of every trial's model, [n_w, B]
+            # per-trial static weights: the weight arena / wide encoders / wide decoders of every trial's model
             distinct, which = {}, []
             for mt in self.models:
                 if id(mt) not in distinct:
-                    wt = lowering.narrow_ensemble_weights(self.network, mt, self.n_trials)
-                    if wt.size != plan.arrays["weights"].size:
+                    wt, enc, dec = lowering.trial_weights(self.network, mt, self.n_trials)
+                    if wt.size != plan.arrays["weights_pt"].size:
                         raise RuntimeError("per-trial models lower to different weight layouts")
-                    distinct[id(mt)] = (len(distinct), wt)
+                    distinct[id(mt)] = (len(distinct), wt, enc, dec)
                 which.append(distinct[id(mt)][0])
-            stacked = np.stack([wt for _, wt in sorted(distinct.values(), key=lambda p: p[0])])      # [n_models, n_w]
+            which = np.asarray(which)
+            per_model = sorted(distinct.values(), key=lambda p: p[0])
+            stacked = np.stack([p[1] for p in per_model])                                           # [n_models, n_w]
             w = np.zeros((stacked.shape[1], self.B), dtype=np.float32)
-            w[:, :self.n_trials] = stacked.T[:, np.asarray(which)]
+            w[:, :self.n_trials] = stacked.T[:, which]
             self._upload("wpt", 0, w)
+            for ens, (row0, n, dims) in plan.pt_enc.items():
+                e = np.stack([p[2][ens].reshape(-1) for p in per_model])                            # [n_models, n * dims]
+                self._upload("lenc", row0, self._rows(e[which]))
+            for conn, (row0, size_out, n) in plan.pt_dec.items():
+                d = np.stack([p[3][conn] for p in per_model])                                       # [n_models, size_out, n]
+                self._upload_decoders((row0, size_out, n), d[which])
         if nn:
             v0 = np.zeros((nn, self.B), dtype=np.float32)
             for ens, (row0, n) in plan.ens_state.items():
@@ -297,10 +303,18 @@ class Simulator:
                     v0[row0:row0 + n, self.n_trials:] = v0[row0:row0 + n, :1]
             self._upload("st", 0, v0)   # packed LIF state: s >= 0 is the voltage of a non-refractory neuron
         for ens, (row0, n, dims) in plan.learned_enc.items():
-            self._upload("lenc", row0, self._rows(m.params[ens].scaled_encoders.reshape(-1)))
+            if self.models is not None:
+                e = np.stack([mt.params[ens].scaled_encoders.reshape(-1) for mt in self.models])
+                self._upload("lenc", row0, self._rows(e))
+            else:
+                self._upload("lenc", row0, self._rows(m.params[ens].scaled_encoders.reshape(-1)))
         for conn in plan.learned_dec:
-            w = np.asarray(m.params[conn].weights, dtype=np.float32)
-            self._upload_decoders(conn, np.broadcast_to(w[None], (self.n_trials,) + w.shape))
+            if self.models is not None:
+                self._upload_decoders(conn, np.stack([np.asarray(mt.params[conn].weights, dtype=np.float32)
+                                                      for mt in self.models]))
+            else:
+                w = np.asarray(m.params[conn].weights, dtype=np.float32)
+                self._upload_decoders(conn, np.broadcast_to(w[None], (self.n_trials,) + w.shape))
         # per "rows" probe: list of [samples, size, n_trials] float32 chunks, already decimated by the probe's period
         self._probe_rows = {info.probe: [] for info in plan.probes if info.kind == "rows"}
         self._probe_steps_flushed = 0

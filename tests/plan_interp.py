@@ -23,6 +23,19 @@ class PlanInterpreter:
         self.ldec = np.zeros(max(1, int(sc["n_ldec"])), dtype)
         self.afilt = np.zeros((2, max(1, int(sc["n_afilt"]))), dtype)
         self.W = a["weights"].astype(dtype)
+        # plans lowered with per_trial=True: this trial's seed-dependent weights (its own model) in their arenas
+        self.per_trial = bool(sc.get("per_trial_weights", 0))
+        if self.per_trial:
+            from sspslam_b200 import lowering
+            wp, enc, dec = lowering.trial_weights(network, model)
+            assert wp.size == a["weights_pt"].size
+            self.Wp = wp.astype(dtype)
+            for ens, (row0, n, dims) in plan.pt_enc.items():
+                self.lenc[row0:row0 + n * dims] = enc[ens].reshape(-1)
+            for conn, (row0, so, n) in plan.pt_dec.items():
+                self.ldec[row0:row0 + so * n] = dec[conn].reshape(-1)
+        else:
+            self.Wp = self.W
         self.ptr = a["csr_ptr"]
         self.ent = [a["csr_ent0"], a["csr_ent1"]]          # (vec row, coefficient bits), per step parity
         self.val = np.ascontiguousarray(a["csr_ent0"][:, 1]).view(np.float32).astype(dtype)
@@ -103,7 +116,7 @@ class PlanInterpreter:
                 self.vec[dst] = self.rows(src, 1, 1 if kind == 4 else 0)[0]
             for d in a["ens_small"][st[0]:st[0] + st[1]]:
                 n, dims, nout, s0, w_off, in_row0, out_vec, tid, stride = (int(x) for x in d)
-                pk = W[w_off:w_off + n * stride].reshape(n, stride)
+                pk = self.Wp[w_off:w_off + n * stride].reshape(n, stride)
                 x = self.vec[in_row0:in_row0 + dims].copy()
                 out = self.neuron(tid, pk[:, 0] + pk[:, 1:1 + dims] @ x, s0, n)
                 self.vec[out_vec:out_vec + nout] = pk[:, 1 + dims:1 + dims + nout].T @ out
@@ -115,14 +128,15 @@ class PlanInterpreter:
                     E = self.lenc[enc_off:enc_off + n * dims].reshape(n, dims)
                 else:
                     E = W[enc_off:enc_off + n * dpad].reshape(n, dpad)[:, :dims]
-                J = W[bias_off:bias_off + n] + E @ x
+                Wb = self.Wp if flags & 4 else W       # bit 2: bias / Voja scale / neuron-current weights are per trial
+                J = Wb[bias_off:bias_off + n] + E @ x
                 if jn_m:
-                    J = J + W[jn_w:jn_w + n * jn_m].reshape(n, jn_m) @ self.vec[jn_row0:jn_row0 + jn_m]
+                    J = J + Wb[jn_w:jn_w + n * jn_m].reshape(n, jn_m) @ self.vec[jn_row0:jn_row0 + jn_m]
                 out = self.neuron(tid, J, s0, n)
                 self.act[act0:act0 + n] = out
                 if flags & 1:
                     aL = np.int32(alpha_bits).view(np.float32).astype(self.dt_) * self.vec[voja_row]
-                    sc = W[scale_off:scale_off + n]
+                    sc = Wb[scale_off:scale_off + n]
                     E += aL * (sc[:, None] * np.outer(out, x) - out[:, None] * E)   # E is a view of lenc
             for ci in range(st[6], st[6] + st[7]):
                 G, dims, dpad, s_off, in_row0, out_vec = (int(x) for x in a["cleanup"][ci])
@@ -139,7 +153,10 @@ class PlanInterpreter:
                 self.vec[out_vec:out_vec + dims] = rate * (p_ - q_) if open_ else 0.0
             for d in a["dec"][st[4]:st[4] + st[5]]:
                 n, so, jpad, act0, w_off, out_vec, nch = (int(x) for x in d[:7])
-                Wd = W[w_off:w_off + n * jpad].reshape(n, jpad)[:, :so]
+                if self.per_trial:                         # per-trial static decoder: ldec rows (k_decode_pt)
+                    Wd = self.ldec[w_off:w_off + so * n].reshape(so, n).T
+                else:
+                    Wd = W[w_off:w_off + n * jpad].reshape(n, jpad)[:, :so]
                 per = -(-n // nch)
                 total = np.zeros(so, self.dt_)
                 for c in range(nch):                       # split-K partial sums, added in chunk order
