@@ -544,6 +544,7 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
             return;
         }
         int nwarps = 4, nb = SSB_VOJA_NB;
+        if (const char* e = getenv("SSB_VOJA_NB")) nb = std::max(1, std::min(SSB_VOJA_NB, atoi(e)));    // tuning knob
         SsbPesFuse pf;
         memset(&pf, 0, sizeof(pf));
         pf.desc = s->d_pes;

@@ -38,7 +38,7 @@ def test_config5_full_size_rate_mode_matches_oracle(lib):
                            node_tables={node: arr[trial] for node, arr in sc.trial_inputs.items()})
         ref.run_steps(n_steps)
         want = ref.data[sc.probe]
-        assert np.max(np.abs(want)) > 0.05
+        assert np.max(np.abs(want)) > 0.02          # 24 steps from rest: the output filter has only started to charge
         assert np.max(np.abs(got[trial] - want)) < 1e-4 * np.max(np.abs(want))
         assert idx[trial] == ssp_ref.cleanup_index(slam.sample_ssps, ref.signals[slam.gridcells, "in"].a)
         want_dec = ref.learned_weights(slam.assomemory.conn_out)
