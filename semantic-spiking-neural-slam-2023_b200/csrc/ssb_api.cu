@@ -150,7 +150,7 @@ struct ssb_sim {
     // independent kernels of one dependency level run on side streams (fork/join with events; under
     // capture these become parallel branches of the step graph)
     bool parallel = true;
-    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};   // B, C, D, E
+    cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // B, C, D, E, F (input prefetch)
     std::vector<int> level_deps;            // [n_levels][n_levels] producer-kind bits (lowering.py); empty = wait for everything
     cudaStream_t io_h2d = nullptr, io_d2h = nullptr;   // copy streams of ssb_run_steps_io (one per DMA direction)
     std::vector<cudaEvent_t> io_events;
@@ -203,6 +203,7 @@ struct ssb_sim {
     float *afilt = nullptr, *probe = nullptr, *part = nullptr;
     float* wpt = nullptr;                   // per-trial static weights [G][n_wpt][32] (scalar per_trial_weights = 1)
     long long n_wpt = 0;
+    bool dec_sparse = false;                // SSB_DECODE=sparse: shared static decoders through the sparse per-trial walk (spiking runs)
     bool per_trial = false;                 // plan lowered with per-trial static weights (wide ensembles: encoders in lenc, decoders in ldec)
     int* counters = nullptr;
     int* aflag = nullptr;
@@ -543,7 +544,9 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
             k_wide_voja_stream<<<grid, 256, smem, st>>>(s->ctx, s->d_big, items, chunk, i_rel);
             return;
         }
-        int nwarps = 4, nb = SSB_VOJA_NB;
+        // tiles in flight per warp: measured on B200 (configs[1], 1 024 trials) 3 / 2 / 1 -> 65.2 / 62.7 / 62.1 us per launch,
+        // step 264.9 / 262.7 / 262.6 us (profiles/r02g_perf_voja_ring_depth.log): a shallower ring leaves room for more CTAs
+        int nwarps = 4, nb = 2;
         if (const char* e = getenv("SSB_VOJA_NB")) nb = std::max(1, std::min(SSB_VOJA_NB, atoi(e)));    // tuning knob
         SsbPesFuse pf;
         memset(&pf, 0, sizeof(pf));
@@ -907,6 +910,11 @@ bool decode_tc_allowed() {
 int build_decode_tiles(ssb_sim* s) {
     const int n_dec = (int)(s->h_dec.size() / 9);
     s->dec_tc_level.assign(s->n_levels, 0);
+    if (const char* e = getenv("SSB_DECODE")) s->dec_sparse = std::string(e) == "sparse" && !s->per_trial;
+    if (s->dec_sparse) {      // every decoder of the plan must not be split (the sparse walk writes the rows itself)
+        for (int i = 0; i < n_dec; ++i) s->h_dec[i * 9 + 6] = 1;
+        return 0;
+    }
     if (n_dec == 0 || !decode_tc_allowed() || s->per_trial) return 0;      // per-trial decoders: no shared GEMM operand
     int max_jpad = 0;
     for (int i = 0; i < n_dec; ++i) max_jpad = std::max(max_jpad, s->h_dec[i * 9 + 2]);
@@ -1189,13 +1197,14 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
     const int G = s->n_groups;
     const bool par = s->parallel && (!s->profiling || s->timeline) && !s->debug_sync;
     cudaStream_t A = s->stream, B = par ? s->aux[0] : A, C = par ? s->aux[1] : A, D = par ? s->aux[2] : A;
-    cudaStream_t E = par ? s->aux[3] : A;
+    cudaStream_t E = par ? s->aux[3] : A, F = par ? s->aux[4] : A;
     const bool any_inputs = s->synth_on || s->nt > 0;
     if (any_inputs && !(have_inputs && par)) launch_inputs(s, A, i_rel);
     const bool prefetch = any_inputs && prefetch_next && par;
     if (prefetch) {                 // everything of the previous step is behind A here, so the other copy is free
-        stream_dep(s, A, C);
-        launch_inputs(s, C, i_rel + 1);
+        // its own stream: on C the clean-up chain queued behind it (k_synth: one CTA per trial group, ~35 us of latency)
+        stream_dep(s, A, F);
+        launch_inputs(s, F, i_rel + 1);
     }
     const int NL = s->n_levels;
     // events of the producers of every level (null = that level has no such producer)
@@ -1208,7 +1217,7 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
     auto wait_on = [&](cudaStream_t st, cudaEvent_t e) {
         if (e) cudaStreamWaitEvent(st, e, 0);
     };
-    bool pes_done = s->n_pes == 0, b_used = false, c_used = prefetch, d_used = false, e_used = false;
+    bool pes_done = s->n_pes == 0, b_used = false, c_used = false, d_used = false, e_used = false;
     for (int lvl = 0; lvl < NL; ++lvl) {
         const int* st = &s->h_stages[lvl * 12];
         const LevelInfo& li = s->levels[lvl];
@@ -1302,7 +1311,12 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
                 int max_jp = 4;
                 for (int i = 0; i < st[5]; ++i) max_jp = std::max(max_jp, (s->h_dec[(st[4] + i) * 9 + 1] + 3) & ~3);
                 const int n_jt = (max_jp + SSB_PES_JT - 1) / SSB_PES_JT;
-                k_decode_pt<<<dim3(4, G, st[5] * n_jt), 256, 0, D>>>(c, s->d_dec, st[4], n_jt);
+                k_decode_pt<false><<<dim3(4, G, st[5] * n_jt), 256, 0, D>>>(c, s->d_dec, st[4], n_jt);
+            } else if (s->dec_sparse) {
+                int max_jp = 8;
+                for (int i = 0; i < st[5]; ++i) max_jp = std::max(max_jp, s->h_dec[(st[4] + i) * 9 + 2]);
+                const int n_jt = (max_jp + SSB_PES_JT - 1) / SSB_PES_JT;
+                k_decode_pt<true><<<dim3(4, G, st[5] * n_jt), 256, 0, D>>>(c, s->d_dec, st[4], n_jt);
             } else if (s->dec_tc_level[lvl] && s->dec_tc_n == 64)
                 k_decode_tc<64, 64><<<grid, 256, (size_t)(4 * 128 * 64 + 4 * 64 * 64) * sizeof(float), D>>>(
                     c, s->d_dec, st[4], s->d_dec_wt, s->d_dec_wt_off, s->dec_tc_nt);
@@ -1326,6 +1340,7 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
         }
     }
     // the end-of-step rows read everything: join every stream that was used
+    if (prefetch) stream_dep(s, F, A);
     if (c_used) stream_dep(s, C, A);
     if (d_used) stream_dep(s, D, A);
     if (e_used) stream_dep(s, E, A);
@@ -1408,6 +1423,7 @@ int ssb_create(int device, int n_trials, ssb_sim** out) {
         SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[1], cudaStreamNonBlocking, pr_hi));
         SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[2], cudaStreamNonBlocking, pr_mid));
         SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[3], cudaStreamNonBlocking, pr_hi));
+        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[4], cudaStreamNonBlocking, pr_mid));
     }
     if (const char* e = getenv("SSB_SERIAL")) s->parallel = e[0] != '1';
     if (const char* e = getenv("SSB_PES_PAD")) s->pes_pad_smem = (size_t)atoi(e) * 1024;
@@ -1529,7 +1545,7 @@ int ssb_finalize(ssb_sim* s) {
                 break;
             }
             const int* d = &s->h_big[found * 16];
-            int nb = SSB_VOJA_NB;                         // as launch_wide_class sizes the ring of a warp
+            int nb = 2;                                   // as launch_wide_class sizes the ring of a warp
             while (nb > 1 && (size_t)(d[2] * 32 + d[11] * 32 + nb * d[1] * 32) * sizeof(float) > 200 * 1024) --nb;
             if (std::min(pd[1], 56) + 8 > nb * d[1] || (size_t)d[1] * 128 * 2 > 96 * 1024) ok = false;   // (stream-class ensembles: no fusion)
             else s->pes_of_big[found] = i;

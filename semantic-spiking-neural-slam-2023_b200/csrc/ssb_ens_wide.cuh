@@ -333,7 +333,7 @@ k_wide_static_tc(SsbCtx c, const int* __restrict__ desc, SsbItemList items, cons
 // column in place and the tile is written back only if some lane spiked (post_synapse=None => the
 // delta is row-sparse).  SimVoja: delta = alpha*L*(scale*outer(post, x) - post[:,None]*E), visible
 // to the next step.
-#define SSB_VOJA_NB 3         // encoder tiles in flight per warp (fewer when a tile is too large: very wide ensembles)
+#define SSB_VOJA_NB 3         // most encoder tiles in flight per warp (ring barriers); the launch uses SSB_VOJA_NB_DEFAULT
 // PES = true: the ensemble's activities feed a PES-learned connection whose decode is fused into this kernel (deferred-PES
 // form, see ssb_pes.cuh): after its neuron range a warp walks the neurons where some trial spiked and accumulates
 //   out[trial][j] += D_base[j][i][trial] * a[i][trial]      and      dots[trial][q] += f_q[i][trial] * a[i][trial]

@@ -301,7 +301,11 @@ __global__ void __launch_bounds__(128) k_pes_clear(SsbCtx c, SsbPesDefer h, int 
 // ensemble, so there is no split-K and the result is written straight to the decoded rows.
 // desc (the static-decoder descriptor): n size_out jpad act0 d_off out_vec - - -      (d_off = ldec arena row)
 // grid (4 trial octets, G, decoders * column tiles of SSB_PES_JT) x 256
+// SHARED = true: the same sparse walk over the SHARED static decoders ([neuron][jpad] rows of the weight array, d_off = float
+// offset, L2-resident) - an alternative to the tensor-core decode for spiking runs (SSB_DECODE=sparse): ~36 KB of shared
+// memory and no operand conversion, so it co-resides with the other kernels of the step instead of owning whole SMs.
 #define SSB_DPT_CH 1024
+template <bool SHARED>
 __global__ void __launch_bounds__(256) k_decode_pt(SsbCtx c, const int* __restrict__ desc, int item0, int n_jt_max) {
     __shared__ int sflag[SSB_DPT_CH];
     __shared__ int slist[8][SSB_DPT_CH];
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(256) k_decode_pt(SsbCtx c, const int* __restri
     const int item = blockIdx.z / n_jt_max, jt = blockIdx.z - item * n_jt_max;
     const int* d = desc + (item0 + item) * 9;
     const int n = d[0], size_out = d[1], act0 = d[3], d_off = d[4], out_vec = d[5];
-    const int JP = ssb_pes_jp(size_out);
+    const int JP = SHARED ? d[2] : ssb_pes_jp(size_out);      // row length of one neuron's weights
     const int j0 = jt * SSB_PES_JT;
     if (j0 >= JP) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -317,7 +321,9 @@ __global__ void __launch_bounds__(256) k_decode_pt(SsbCtx c, const int* __restri
     const int t = oct * 8 + warp;                         // this warp's trial inside the group
     const int* __restrict__ fl = c.aflag + (size_t)g * c.n_act + act0;
     const float* __restrict__ ap = c.act + ((size_t)g * c.n_act + act0) * 32 + t;
-    const float* __restrict__ dl = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)t * JP + j0 + lane;
+    const float* __restrict__ dl = SHARED ? c.W + d_off + j0 + lane
+                                          : c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)t * JP + j0 + lane;
+    const size_t nstride = SHARED ? (size_t)JP : (size_t)JP * 32;      // floats between consecutive neurons
     constexpr int NC = SSB_PES_JT / 32;
     float acc[NC];
 #pragma unroll
@@ -347,7 +353,8 @@ __global__ void __launch_bounds__(256) k_decode_pt(SsbCtx c, const int* __restri
                 a[u] = on ? __ldg(ap + ni * 32) : 0.f;
 #pragma unroll
                 for (int q = 0; q < NC; ++q)
-                    w[u][q] = (on && j0 + q * 32 + lane < JP) ? __ldcs(dl + ni * JP * 32 + q * 32) : 0.f;
+                    w[u][q] = (on && j0 + q * 32 + lane < JP) ? (SHARED ? __ldg(dl + ni * nstride + q * 32)
+                                                                        : __ldcs(dl + ni * nstride + q * 32)) : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
