@@ -371,7 +371,8 @@ def run_b200(args):
     peak, peak_src = load_peaks()
     per_launch_bytes = by_kind[dom] * sim.B * chunk / max(dom_cnt, 1)
     achieved = per_launch_bytes / (dom_ms / max(dom_cnt, 1) * 1e-3) / 1e9
-    traffic = load_traffic(dom)
+    # the committed ncu capture is BASELINE configs[1] at 1 024 trials: its DRAM bytes say nothing about another workload / batch
+    traffic = load_traffic(dom) if (args.workload == "cfg2" and B == 1024) else None
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "frac_dram": None if traffic is None else traffic / (dom_ms / max(dom_cnt, 1) * 1e-3) / 1e9 / peak,
@@ -385,7 +386,7 @@ def run_b200(args):
                 "share_of_step": dom_ms / tot_ms,
                 "kernel_shares": {k: round(ms / tot_ms, 4) for k, (ms, c) in kt.items() if c}}
     step_gbs = bytes_ts * B * chunk * K / (value_ms * 1e-3) / 1e9
-    step_traffic, traffic_trials = load_step_traffic()
+    step_traffic, traffic_trials = load_step_traffic() if args.workload == "cfg2" else (None, None)
     step_dram_gbs = None
     if step_traffic is not None and traffic_trials:
         step_dram_gbs = step_traffic * (B / traffic_trials) * chunk * K / (value_ms * 1e-3) / 1e9

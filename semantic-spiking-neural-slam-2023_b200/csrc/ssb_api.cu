@@ -526,6 +526,32 @@ void launch_wide_class(ssb_sim* s, cudaStream_t st, const int* stage, bool voja,
         dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
         k_wide_static<DP><<<grid, 128, smem_of(chunk), st>>>(s->ctx, s->d_big, items, chunk, i_rel);
     } else {
+        // very long encoder rows (d = 649).  Default: the CTA-cooperative kernel (two whole-neuron tiles in shared memory,
+        // the input slice of each warp in registers) - as long as two tiles fit and a warp's slice is <= 96 rows (d <= 768);
+        // SSB_VOJA=stream selects the per-warp ring kernel, SSB_VOJA=cta forces the cooperative one for any generic width.
+        const char* vj = getenv("SSB_VOJA");
+        const bool vj_stream = vj && std::string(vj) == "stream", vj_cta = vj && std::string(vj) == "cta";
+        const size_t cta_smem = ((size_t)2 * max_dims * 32 + SSB_VC_NW * 32 + 32 + (size_t)max_jn * 32) * sizeof(float);
+        const bool cta_fits = cta_smem <= 220 * 1024 && (max_dims + SSB_VC_NW - 1) / SSB_VC_NW <= 96;
+        if (DP == 0 && cta_fits && !vj_stream && (vj_cta || (size_t)max_dims * 128 * 2 > 96 * 1024)) {
+            const int key = (3 << 28) | (max_n << 6) | (units & 63);
+            auto it = s->wide_chunk_cache.find(key);
+            int chunk = it == s->wide_chunk_cache.end() ? 0 : it->second;
+            if (!chunk) {
+                cudaFuncSetAttribute(k_wide_voja_cta<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                cudaFuncSetAttribute(k_wide_voja_cta<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                const int per_unit = std::max(1, 148 / std::max(1, units));        // one CTA per SM: one wave
+                chunk = std::max(2, (max_n + per_unit - 1) / per_unit);
+                s->wide_chunk_cache[key] = chunk;
+            }
+            if (dry) return;
+            dim3 grid((max_n + chunk - 1) / chunk, s->n_groups, items.n);
+            if ((max_dims + SSB_VC_NW - 1) / SSB_VC_NW <= 48)
+                k_wide_voja_cta<48><<<grid, 32 * (SSB_VC_NW + 1), cta_smem, st>>>(s->ctx, s->d_big, items, chunk, i_rel);
+            else
+                k_wide_voja_cta<96><<<grid, 32 * (SSB_VC_NW + 1), cta_smem, st>>>(s->ctx, s->d_big, items, chunk, i_rel);
+            return;
+        }
         if (DP == 0 && (size_t)max_dims * 128 * 2 > 96 * 1024) {
             // very long encoder rows (d = 649): stream them through per-warp rings of sub-tiles (k_wide_voja_stream)
             const size_t smem = (size_t)(max_dpad * 32 + max_jn * 32 + 8 * SSB_VS_NB * SSB_VS_SUB * 32) * sizeof(float);

@@ -16,8 +16,12 @@ from sspslam_b200 import scenarios
 pytestmark = pytest.mark.gpu
 
 
-def test_config5_full_size_rate_mode_matches_oracle(lib):
+@pytest.mark.parametrize("voja", ["cta", "stream"])
+def test_config5_full_size_rate_mode_matches_oracle(lib, voja, monkeypatch):
+    """``voja``: the memory ensemble (970 x 649 per-trial encoders) on the CTA-cooperative kernel (default) or on the per-warp
+    streaming kernel."""
     from sspslam_b200.simulator import Simulator
+    monkeypatch.setenv("SSB_VOJA", voja)
     n_steps, n_trials = 24, 32
     sc = scenarios.make_slam(n_trials=n_trials, n_steps=n_steps + 4, ssp_dim=649, pi_n_neurons=500, mem_n_neurons=970,
                              circonv_n_neurons=100, n_landmarks=50, T=20.0, domain_dim=3, grid_points_per_dim=30,
@@ -29,6 +33,7 @@ def test_config5_full_size_rate_mode_matches_oracle(lib):
         sim.run_steps(n_steps)
         idx = sim.cleanup_indices()[0].copy()
         dec = sim.learned_decoders(slam.assomemory.conn_out)
+        enc = sim.learned_encoders(slam.assomemory.memory)
         launches = sim.total_launches()
     got = sim.data[sc.probe]
     assert got.shape == (n_trials, n_steps, 649) and np.all(np.isfinite(got))
@@ -43,3 +48,5 @@ def test_config5_full_size_rate_mode_matches_oracle(lib):
         assert idx[trial] == ssp_ref.cleanup_index(slam.sample_ssps, ref.signals[slam.gridcells, "in"].a)
         want_dec = ref.learned_weights(slam.assomemory.conn_out)
         assert np.max(np.abs(dec[trial] - want_dec)) < 1e-4 * np.max(np.abs(want_dec)) + 1e-9
+        want_enc = ref.scaled_encoders(slam.assomemory.memory)
+        assert np.max(np.abs(enc[trial] - want_enc)) < 1e-4 * np.max(np.abs(want_enc))

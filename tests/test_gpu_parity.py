@@ -198,12 +198,14 @@ def test_generic_width_network_matches_oracle():
     assert _rel(got[1], _oracle(sc, sim, 1, 120).data[sc.probe]) < 1e-4
 
 
-@pytest.mark.parametrize("env", [{}, {"SSB_LIN": "ffma", "SSB_ENCODE": "ffma", "SSB_SCAN": "ffma", "SSB_DECODE": "ffma"}])
+@pytest.mark.parametrize("env", [{}, {"SSB_LIN": "ffma", "SSB_ENCODE": "ffma", "SSB_SCAN": "ffma", "SSB_DECODE": "ffma"},
+                                 {"SSB_VOJA": "cta"}])
 def test_wide_d295_network_on_the_k_blocked_tensor_core_kernels(env, monkeypatch):
     """d = 295 (2-D, 7 x 7 scale / rotation pairs) at reduced neuron counts: wide enough for every K-blocked tcgen05 path of
     BASELINE configs[4] (d = 649) - grid scan (k_cleanup_scan_tck), static wide encode (k_wide_static_tck), column-tiled
     decode (k_decode_tc with 3 tiles), the 592 x 295 / 295 x 592 dense blocks of the row program (k_lin_tck) - against the
-    oracle in rate mode, and the same network on the FFMA kernels."""
+    oracle in rate mode, and the same network on the FFMA kernels; SSB_VOJA=cta puts the memory ensemble on the
+    CTA-cooperative Voja kernel of d = 649 (k_wide_voja_cta, 48-row slices), incl. the learned encoders."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     n_steps = 60
@@ -216,6 +218,7 @@ def test_wide_d295_network_on_the_k_blocked_tensor_core_kernels(env, monkeypatch
         sim.run_steps(n_steps)
         idx = sim.cleanup_indices()[0].copy()
         dec = sim.learned_decoders(slam.assomemory.conn_out)
+        enc = sim.learned_encoders(slam.assomemory.memory)
     got = sim.data[sc.probe]
     for trial in (0, 2):
         ref = _oracle(sc, sim, trial, n_steps)
@@ -225,6 +228,9 @@ def test_wide_d295_network_on_the_k_blocked_tensor_core_kernels(env, monkeypatch
         assert idx[trial] == ssp_ref.cleanup_index(slam.sample_ssps, ref.signals[slam.gridcells, "in"].a)
         want_dec = ref.learned_weights(slam.assomemory.conn_out)
         assert np.max(np.abs(dec[trial] - want_dec)) < 1e-4 * np.max(np.abs(want_dec)) + 1e-9
+        want_enc = ref.scaled_encoders(slam.assomemory.memory)
+        assert not np.allclose(want_enc, sim.model.params[slam.assomemory.memory].scaled_encoders)      # Voja moved them
+        assert _rel(enc[trial], want_enc) < 1e-4
 
 
 @pytest.mark.parametrize("env", [{"SSB_SCAN": "ffma"}, {"SSB_DECODE": "ffma"}, {"SSB_ENCODE": "tc"},
