@@ -137,7 +137,7 @@ struct ssb_sim {
     SsbLinTcBlock* d_lin_tc = nullptr;      // large dense blocks served by k_lin_tck (tcgen05), per segment [tc0, tc0 + n_tc)
     float *d_lin_ttk = nullptr, *d_lin_xt = nullptr;
     int* d_lin_recs = nullptr;
-    std::vector<LinSeg> lin_segs;            // one per level + the end-of-step segment
+    std::vector<LinSeg> lin_segs;            // one per level + the early end-of-step rows (need only level-0 narrow ensembles) + the rest
     long long n_dense_rows = 0, n_dense_blocks = 0;
     float* d_ntypes = nullptr;
     double* d_s64 = nullptr;
@@ -150,7 +150,7 @@ struct ssb_sim {
     // independent kernels of one dependency level run on side streams (fork/join with events; under
     // capture these become parallel branches of the step graph)
     bool parallel = true;
-    cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // B, C, D, E, F (input prefetch)
+    cudaStream_t aux[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // B, C, D, E, F (input prefetch), G (early end-of-step rows)
     std::vector<int> level_deps;            // [n_levels][n_levels] producer-kind bits (lowering.py); empty = wait for everything
     cudaStream_t io_h2d = nullptr, io_d2h = nullptr;   // copy streams of ssb_run_steps_io (one per DMA direction)
     std::vector<cudaEvent_t> io_events;
@@ -193,7 +193,7 @@ struct ssb_sim {
     std::map<int, int> wide_chunk_cache;   // launch geometry of the wide-ensemble kernels, decided once
     long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
     std::vector<size_t> s64_offsets;
-    int n_levels = 0, n_lin = 0, lin0 = 0, n_pes = 0, n_small_total = 0;
+    int n_levels = 0, n_lin = 0, lin0 = 0, n_lin_early = 0, n_pes = 0, n_small_total = 0;
     // sizes
     long long nv = 0, nf = 0, nt = 0, nn = 0, n_act = 0, n_lenc = 0, n_ldec = 0, n_afilt = 0, n_probe = 0;
     long long tab_row0 = 0, n_part = 0, n_counters = 0;
@@ -1032,10 +1032,12 @@ int build_lin_program(ssb_sim* s) {
     size_t xt_floats = 0;
     const char* lin_env = getenv("SSB_LIN");
     const bool lin_tc_on = !(lin_env && std::string(lin_env) == "ffma");
-    s->lin_segs.assign(s->n_levels + 1, ssb_sim::LinSeg());
-    for (int seg = 0; seg <= s->n_levels; ++seg) {
-        const int r0 = seg < s->n_levels ? s->h_stages[seg * 12 + 10] : s->lin0;
-        const int nr = seg < s->n_levels ? s->h_stages[seg * 12 + 11] : s->n_lin;
+    s->lin_segs.assign(s->n_levels + 2, ssb_sim::LinSeg());
+    if (s->n_lin_early < 0 || s->n_lin_early > s->n_lin) return fail(-1, "ssb_finalize: n_lin_early out of range");
+    for (int seg = 0; seg <= s->n_levels + 1; ++seg) {
+        // final rows: [lin0, lin0 + n_lin_early) = early segment (index n_levels), the rest = end-of-step segment (n_levels + 1)
+        const int r0 = seg < s->n_levels ? s->h_stages[seg * 12 + 10] : (seg == s->n_levels ? s->lin0 : s->lin0 + s->n_lin_early);
+        const int nr = seg < s->n_levels ? s->h_stages[seg * 12 + 11] : (seg == s->n_levels ? s->n_lin_early : s->n_lin - s->n_lin_early);
         ssb_sim::LinSeg& L = s->lin_segs[seg];
         L.csr_row0 = (int)(rows5.size() / 5);
         L.item0 = (int)(items.size() / 8);
@@ -1223,7 +1225,8 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
     const int G = s->n_groups;
     const bool par = s->parallel && (!s->profiling || s->timeline) && !s->debug_sync;
     cudaStream_t A = s->stream, B = par ? s->aux[0] : A, C = par ? s->aux[1] : A, D = par ? s->aux[2] : A;
-    cudaStream_t E = par ? s->aux[3] : A, F = par ? s->aux[4] : A;
+    cudaStream_t E = par ? s->aux[3] : A, F = par ? s->aux[4] : A, Gs = par ? s->aux[5] : A;
+    bool early_used = false;
     const bool any_inputs = s->synth_on || s->nt > 0;
     if (any_inputs && !(have_inputs && par)) launch_inputs(s, A, i_rel);
     const bool prefetch = any_inputs && prefetch_next && par;
@@ -1364,6 +1367,17 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
             else k_ens_small<<<blocks, 128, 0, T>>>(c, s->d_small + st[0] * 9, st[1], n_split);
             ev_small[lvl] = mark(T);
         }
+        if (lvl == 0 && s->n_lin_early > 0) {
+            // end-of-step rows that need nothing but the step-start columns and level 0's narrow ensembles (the VCO filters):
+            // on their own stream, next to the other chains, instead of in the launch that waits for everything
+            if (par) {
+                cudaEvent_t e = ev_small[0] ? ev_small[0] : mark(T);
+                wait_on(Gs, e);
+            }
+            LaunchTimer t(s, K_LIN, Gs);
+            launch_lin(s, Gs, s->n_levels, i_rel);
+            early_used = par;
+        }
     }
     // the end-of-step rows read everything: join every stream that was used
     if (prefetch) stream_dep(s, F, A);
@@ -1372,9 +1386,10 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
     if (e_used) stream_dep(s, E, A);
     if (b_used) stream_dep(s, B, A);
     if (!pes_done) launch_pes(s, A, i_rel);
-    if (s->n_lin > 0) {
+    if (early_used) stream_dep(s, Gs, A);
+    if (s->n_lin - s->n_lin_early > 0) {
         LaunchTimer t(s, K_LIN, A);
-        launch_lin(s, A, s->n_levels, i_rel);
+        launch_lin(s, A, s->n_levels + 1, i_rel);
     }
     return 0;
 }
@@ -1450,6 +1465,7 @@ int ssb_create(int device, int n_trials, ssb_sim** out) {
         SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[2], cudaStreamNonBlocking, pr_mid));
         SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[3], cudaStreamNonBlocking, pr_hi));
         SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[4], cudaStreamNonBlocking, pr_mid));
+        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[5], cudaStreamNonBlocking, pr_mid));
     }
     if (const char* e = getenv("SSB_SERIAL")) s->parallel = e[0] != '1';
     if (const char* e = getenv("SSB_PES_PAD")) s->pes_pad_smem = (size_t)atoi(e) * 1024;
@@ -1511,6 +1527,7 @@ int ssb_finalize(ssb_sim* s) {
     if (upload_array(s, "gate", &s->d_gate)) return -2;
     s->lin0 = (int)iscalar(s, "lin0");
     s->n_lin = (int)iscalar(s, "n_lin");
+    s->n_lin_early = (int)iscalar(s, "n_lin_early");
     if (upload_array(s, "ntypes", &s->d_ntypes)) return -2;
     if (upload_array(s, "cleanup_s64", &s->d_s64)) return -2;
     s->h_stages = host_ints(s, "stages");

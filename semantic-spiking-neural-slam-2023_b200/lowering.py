@@ -720,8 +720,23 @@ class _Lowerer:
                                        int(np.float32(op.update_thres).view(np.int32)),
                                        int(np.float32(op.atol).view(np.int32))])
 
-        # ---- final stage rows: filters then probes
+        # ---- final stage rows: filters then probes.  A filter row that reads only step-start columns and decoded outputs of
+        #      LEVEL-0 narrow ensembles (in SLAM: every VCO filter) is "early": it can run as soon as that kernel is done,
+        #      next to the other chains of the step, instead of in the end-of-step launch that waits for everything.  (It
+        #      writes the filter half nobody reads in this step; the only readers of that half - the previous-view rows of
+        #      the PES error - are materialised by the very first launch of the step.)
+        def early_rows(mat):
+            ok = np.ones(mat.shape[0], dtype=bool)
+            late_col = ~((col_prod == 0) | ((col_prod == 1) & (col_plvl == 0)))
+            late_col |= col_level >= INF                     # PES-decoded columns
+            m = mat.tocsr()
+            for r in range(m.shape[0]):
+                cols = m.indices[m.indptr[r]:m.indptr[r + 1]]
+                ok[r] = not late_col[cols].any()
+            return ok
+
         lin_rows, lin_ab = [], []
+        lin_early, lin_early_ab = [], []
         for key, mat in filt_in.items():
             f0, size = plan.filters[key]
             tau = compat.synapse_tau(key.synapse)
@@ -730,9 +745,14 @@ class _Lowerer:
             r0 = add_rows(mat)
             if mat.shape[0] != size:
                 raise AssertionError("filter size mismatch")
+            early = early_rows(mat) if n_levels > 0 and os.environ.get("SSB_LIN_EARLY", "1") != "0" else np.zeros(size, bool)
             for i in range(size):
-                lin_rows.append([r0 + i, 0, f0 + i])
-                lin_ab.append([a, b])
+                if early[i]:
+                    lin_early.append([r0 + i, 0, f0 + i])
+                    lin_early_ab.append([a, b])
+                else:
+                    lin_rows.append([r0 + i, 0, f0 + i])
+                    lin_ab.append([a, b])
         for act0, a_off, n, a, b in pes_trace:  # PES pre-synaptic activity traces (Lowpass of the spikes)
             for i in range(n):
                 lin_rows.append([act0 + i, 2, a_off + i])
@@ -788,8 +808,8 @@ class _Lowerer:
             lin_rows += mat_rows[lvl]
             lin_ab += [[0.0, 1.0]] * len(mat_rows[lvl])
         lin0 = len(lin_rows)
-        lin_rows += lin_final
-        lin_ab += lin_final_ab
+        lin_rows += lin_early + lin_final                  # final rows: [early | late]
+        lin_ab += lin_early_ab + lin_final_ab
         stages = []  # per level counts/offsets into the concatenated descriptor arrays
         cat = {k: [] for k in ("small", "big", "dec", "cleanup", "gate")}
         for lvl in range(n_levels):
@@ -825,7 +845,7 @@ class _Lowerer:
         plan.scalars.update(dict(dt=dt, nv=NV, nf=NF, nt=NT, tab_row0=tab_row0, nn=nn, n_act=n_act, n_lenc=n_lenc,
                                  n_ldec=n_ldec, n_afilt=n_afilt, n_probe=n_probe_rows, n_levels=n_levels,
                                  chunk_cap=chunk_cap, n_part=n_part, n_jtiles=n_jtiles, pes_level=pes_level,
-                                 lin0=lin0, n_lin=len(lin_rows) - lin0))
+                                 lin0=lin0, n_lin=len(lin_rows) - lin0, n_lin_early=len(lin_early)))
         n_static = int(sum(a.size for a in W))
         if self.per_trial:
             plan.scalars["per_trial_weights"] = 1.0
