@@ -193,7 +193,7 @@ struct ssb_sim {
     std::map<int, int> wide_chunk_cache;   // launch geometry of the wide-ensemble kernels, decided once
     long long kind_per_graph[16] = {0};     // launches per graph replay by kind (counted while capturing)
     std::vector<size_t> s64_offsets;
-    int n_levels = 0, n_lin = 0, lin0 = 0, n_lin_early = 0, n_pes = 0, n_small_total = 0;
+    int n_levels = 0, n_lin = 0, lin0 = 0, n_lin_early = 0, n_lin_fused = 0, n_lvl0_res = 0, n_pes = 0, n_small_total = 0;
     // sizes
     long long nv = 0, nf = 0, nt = 0, nn = 0, n_act = 0, n_lenc = 0, n_ldec = 0, n_afilt = 0, n_probe = 0;
     long long tab_row0 = 0, n_part = 0, n_counters = 0;
@@ -203,6 +203,7 @@ struct ssb_sim {
     float *afilt = nullptr, *probe = nullptr, *part = nullptr;
     float* wpt = nullptr;                   // per-trial static weights [G][n_wpt][32] (scalar per_trial_weights = 1)
     long long n_wpt = 0;
+    bool lin_six = false;                   // SSB_LIN_MINB=6: always the 6-CTAs-per-SM variant of k_lin
     bool dec_sparse = false;                // SSB_DECODE=sparse: shared static decoders through the sparse per-trial walk (spiking runs)
     bool per_trial = false;                 // plan lowered with per-trial static weights (wide ensembles: encoders in lenc, decoders in ldec)
     int* counters = nullptr;
@@ -785,8 +786,30 @@ int setup_pes_defer(ssb_sim* s) {
 
 void launch_pes_fold(ssb_sim* s, cudaStream_t st, int i_rel, int force) {
     // neuron chunks of the streaming fold: ~4 CTAs per SM
-    int max_n = 0;
-    for (int i = 0; i < s->n_pes; ++i) max_n = std::max(max_n, s->h_pes[i * 13]);
+    int max_n = 0, max_jp = 4;
+    for (int i = 0; i < s->n_pes; ++i) {
+        max_n = std::max(max_n, s->h_pes[i * 13]);
+        max_jp = std::max(max_jp, (s->h_pes[i * 13 + 1] + 3) & ~3);
+    }
+    // SSB_PES_FOLD=cta (decoders up to 64 columns): the CTA-cooperative fold (ring of 4-neuron tiles by TMA, history terms in
+    // registers).  Correct (GPU suite) but measured SLOWER on B200 than the warp-task kernel below - 194 - 231 us vs 153 us
+    // per fold on configs[1] in three variants (profiles/r02i_perf_pes_fold_cta.log) - so it is not the default.
+    const char* fold_env = getenv("SSB_PES_FOLD");
+    const bool fold_cta = fold_env && std::string(fold_env) == "cta";
+    if (max_jp <= 64 && fold_cta) {
+        const size_t smem = (size_t)SSB_PFC_NT * SSB_PFC_NPT * 32 * max_jp * sizeof(float);
+        const int chunks = std::max(1, std::min(148 / std::max(1, s->n_groups * s->n_pes), (max_n + 15) / 16));
+        dim3 grid(chunks, s->n_groups, s->n_pes);
+        if (s->pes_h.K == 4) {
+            cudaFuncSetAttribute(k_pes_fold_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_pes_fold_cta<4><<<grid, 288, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks);
+        } else {
+            cudaFuncSetAttribute(k_pes_fold_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_pes_fold_cta<8><<<grid, 288, smem, st>>>(s->ctx, s->pes_h, s->d_pes, s->d_pes_hdesc, chunks);
+        }
+        k_pes_clear<<<dim3((s->pes_h.rows_e + 3) / 4, s->n_groups), 128, 0, st>>>(s->ctx, s->pes_h, i_rel, force);
+        return;
+    }
     // neuron chunks: one wave of resident CTAs (occupancy of the 69 KB / 256-thread kernel), so no partial second wave
     const size_t fsm = (size_t)s->pes_h.K * SSB_PES_FS * 32 * sizeof(float);
     int occ = 0;
@@ -1013,7 +1036,9 @@ void launch_lin(ssb_sim* s, cudaStream_t st, int seg, int i_rel) {
     a.drows = s->d_dense_rows;
     a.recs = s->d_lin_recs + (size_t)L.rec0 * 32;
     a.n_recs = L.n_recs;
-    k_lin<<<(unsigned)blocks, 128, 0, st>>>(s->ctx, a, i_rel);
+    const long long waves6 = (blocks + 148 * 6 - 1) / (148 * 6), waves8 = (blocks + 148 * 8 - 1) / (148 * 8);
+    if (waves8 < waves6 && !s->lin_six) k_lin<8><<<(unsigned)blocks, 128, 0, st>>>(s->ctx, a, i_rel);
+    else k_lin<6><<<(unsigned)blocks, 128, 0, st>>>(s->ctx, a, i_rel);
 }
 
 // Split the row program of every launch segment into dense blocks and CSR rows.  Rows (of one view) with an
@@ -1025,19 +1050,27 @@ int build_lin_program(ssb_sim* s) {
     const std::vector<int> e0 = host_ints(s, "csr_ent0"), e1 = host_ints(s, "csr_ent1");   // (row, coefficient bits) pairs
     const float* ab = s->arrays.count("lin_ab") ? reinterpret_cast<const float*>(s->arrays["lin_ab"].bytes.data()) : nullptr;
     const size_t n_rows = rows3.size() / 3;
-    if ((size_t)(s->lin0 + s->n_lin) != n_rows) return fail(-1, "ssb_finalize: lin_rows segments do not add up");
+    if ((size_t)(s->lin0 + s->n_lin + s->n_lin_fused) != n_rows) return fail(-1, "ssb_finalize: lin_rows segments do not add up");
     std::vector<int> rows5, items, ddesc, dcols, drows, recs;
     std::vector<float> ab2, dT, ttk;
     std::vector<SsbLinTcBlock> tcb;
     size_t xt_floats = 0;
     const char* lin_env = getenv("SSB_LIN");
     const bool lin_tc_on = !(lin_env && std::string(lin_env) == "ffma");
-    s->lin_segs.assign(s->n_levels + 2, ssb_sim::LinSeg());
+    s->lin_segs.assign(s->n_levels + 4, ssb_sim::LinSeg());
     if (s->n_lin_early < 0 || s->n_lin_early > s->n_lin) return fail(-1, "ssb_finalize: n_lin_early out of range");
-    for (int seg = 0; seg <= s->n_levels + 1; ++seg) {
-        // final rows: [lin0, lin0 + n_lin_early) = early segment (index n_levels), the rest = end-of-step segment (n_levels + 1)
-        const int r0 = seg < s->n_levels ? s->h_stages[seg * 12 + 10] : (seg == s->n_levels ? s->lin0 : s->lin0 + s->n_lin_early);
-        const int nr = seg < s->n_levels ? s->h_stages[seg * 12 + 11] : (seg == s->n_levels ? s->n_lin_early : s->n_lin - s->n_lin_early);
+    if (s->n_lin_fused > 0 && (s->n_levels < 1 || s->n_lvl0_res < 0 || s->n_lvl0_res > s->h_stages[11]))
+        return fail(-1, "ssb_finalize: fused row program without a level 0");
+    for (int seg = 0; seg <= s->n_levels + 3; ++seg) {
+        // segments after the levels: n_levels = early end-of-step rows [lin0, + n_lin_early); n_levels + 1 = the other
+        // end-of-step rows; n_levels + 2 = those AND the next step's level-0 rows (step fusion); n_levels + 3 = level 0's
+        // previous-view rows, the residual first launch of a step whose level-0 rows were evaluated by the previous step
+        int r0, nr;
+        if (seg < s->n_levels) r0 = s->h_stages[seg * 12 + 10], nr = s->h_stages[seg * 12 + 11];
+        else if (seg == s->n_levels) r0 = s->lin0, nr = s->n_lin_early;
+        else if (seg == s->n_levels + 1) r0 = s->lin0 + s->n_lin_early, nr = s->n_lin - s->n_lin_early;
+        else if (seg == s->n_levels + 2) r0 = s->lin0 + s->n_lin_early, nr = s->n_lin_fused > 0 ? s->n_lin - s->n_lin_early + s->n_lin_fused : 0;
+        else r0 = s->n_lin_fused > 0 ? s->h_stages[10] + s->h_stages[11] - s->n_lvl0_res : 0, nr = s->n_lin_fused > 0 ? s->n_lvl0_res : 0;
         ssb_sim::LinSeg& L = s->lin_segs[seg];
         L.csr_row0 = (int)(rows5.size() / 5);
         L.item0 = (int)(items.size() / 8);
@@ -1247,6 +1280,11 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
         if (e) cudaStreamWaitEvent(st, e, 0);
     };
     bool pes_done = s->n_pes == 0, b_used = false, c_used = false, d_used = false, e_used = false;
+    // step fusion: a step whose predecessor in this batch ran the fused end-of-step launch finds its level-0 sink rows
+    // materialised; only the previous-view rows (PES error) are left, and only the PES chain waits for them
+    const bool fused_prev = par && have_inputs && s->n_lin_fused > 0;
+    const bool fuse_next = par && prefetch_next && s->n_lin_fused > 0;
+    cudaEvent_t ev_res = nullptr;
     for (int lvl = 0; lvl < NL; ++lvl) {
         const int* st = &s->h_stages[lvl * 12];
         const LevelInfo& li = s->levels[lvl];
@@ -1269,7 +1307,15 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
             }
             if (T == E) e_used = true;
         }
-        if (st[11] > 0) {   // materialise this level's sink rows (ensemble / node inputs, PES errors)
+        if (lvl == 0 && fused_prev) {
+            if (s->n_lvl0_res > 0) {
+                stream_dep(s, A, Gs);
+                LaunchTimer t(s, K_LIN, Gs);
+                launch_lin(s, Gs, s->n_levels + 3, i_rel);
+                ev_res = mark(Gs);
+                early_used = true;
+            }
+        } else if (st[11] > 0) {   // materialise this level's sink rows (ensemble / node inputs, PES errors)
             LaunchTimer t(s, K_LIN, T);
             launch_lin(s, T, lvl, i_rel);
         }
@@ -1319,6 +1365,7 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
             launch_wide(s, B, st, true, i_rel);
         }
         if (pes_here) {   // every PES pre-ensemble has produced its activities
+            wait_on(B, ev_res);
             if (s->pes_needs_static && li.n_static > 0) stream_dep(s, D, B);
             launch_pes(s, B, i_rel);
             pes_done = true;
@@ -1385,9 +1432,12 @@ int one_step(ssb_sim* s, int i_rel, bool have_inputs = false, bool prefetch_next
     if (d_used) stream_dep(s, D, A);
     if (e_used) stream_dep(s, E, A);
     if (b_used) stream_dep(s, B, A);
-    if (!pes_done) launch_pes(s, A, i_rel);
     if (early_used) stream_dep(s, Gs, A);
-    if (s->n_lin - s->n_lin_early > 0) {
+    if (!pes_done) launch_pes(s, A, i_rel);
+    if (fuse_next) {            // end-of-step rows + the next step's level-0 rows in one launch (its tables were prefetched on F)
+        LaunchTimer t(s, K_LIN, A);
+        launch_lin(s, A, s->n_levels + 2, i_rel);
+    } else if (s->n_lin - s->n_lin_early > 0) {
         LaunchTimer t(s, K_LIN, A);
         launch_lin(s, A, s->n_levels + 1, i_rel);
     }
@@ -1460,14 +1510,17 @@ int ssb_create(int device, int n_trials, ssb_sim** out) {
         // the clean-up chain C (short, and its scan needs whole SMs) and the chain of the later levels E go first, then the
         // long HBM-streaming chain B and the decode chain D; the narrow-ensemble kernels on A fill what is left
         const int pr_mid = std::min(pr_lo, pr_hi + 1);
-        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[0], cudaStreamNonBlocking, pr_mid));
-        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[1], cudaStreamNonBlocking, pr_hi));
-        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[2], cudaStreamNonBlocking, pr_mid));
-        SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[3], cudaStreamNonBlocking, pr_hi));
+        // SSB_PRIOS = "b,c,d,e": distance of each chain's priority from the highest one (tuning knob; default 1,0,1,0)
+        int off[4] = {1, 0, 1, 0};
+        if (const char* e = getenv("SSB_PRIOS")) sscanf(e, "%d,%d,%d,%d", &off[0], &off[1], &off[2], &off[3]);
+        if (const char* pd = getenv("SSB_PRIO_D")) off[2] = pd[0] == '1' ? 0 : 1;
+        for (int i = 0; i < 4; ++i)
+            SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[i], cudaStreamNonBlocking, std::min(pr_lo, pr_hi + std::max(0, off[i]))));
         SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[4], cudaStreamNonBlocking, pr_mid));
         SSB_CUDA(cudaStreamCreateWithPriority(&s->aux[5], cudaStreamNonBlocking, pr_mid));
     }
     if (const char* e = getenv("SSB_SERIAL")) s->parallel = e[0] != '1';
+    if (const char* e = getenv("SSB_LIN_MINB")) s->lin_six = e[0] == '6';
     if (const char* e = getenv("SSB_PES_PAD")) s->pes_pad_smem = (size_t)atoi(e) * 1024;
     if (const char* e = getenv("SSB_VOJA_PAD")) s->voja_pad_smem = (size_t)atoi(e) * 1024;
     SSB_CUDA(cudaEventCreate(&s->ev_run0));
@@ -1528,6 +1581,8 @@ int ssb_finalize(ssb_sim* s) {
     s->lin0 = (int)iscalar(s, "lin0");
     s->n_lin = (int)iscalar(s, "n_lin");
     s->n_lin_early = (int)iscalar(s, "n_lin_early");
+    s->n_lin_fused = (int)iscalar(s, "n_lin_fused");
+    s->n_lvl0_res = (int)iscalar(s, "n_lvl0_res");
     if (upload_array(s, "ntypes", &s->d_ntypes)) return -2;
     if (upload_array(s, "cleanup_s64", &s->d_s64)) return -2;
     s->h_stages = host_ints(s, "stages");

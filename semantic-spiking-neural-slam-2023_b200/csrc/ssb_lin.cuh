@@ -56,7 +56,11 @@ struct SsbLinArgs {
     int n_recs;
 };
 
-__global__ void __launch_bounds__(128, 6) k_lin(SsbCtx c, SsbLinArgs L, int i_rel) {
+// MINB: resident CTAs per SM the register allocation aims at.  The launch is latency-bound and one to three waves long, so
+// the host picks the variant with fewer waves for the launch's CTA count (6 per SM: 80 registers, 8: 64 with a few spills).
+// (Walking the work units with a grid stride over one resident wave was measured slower: 18.4 vs 14.9 us per launch.)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_lin(SsbCtx c, SsbLinArgs L, int i_rel) {
     __shared__ __align__(16) float s_t[4][SSB_DENSE_RCH][SSB_DENSE_SLAB];
     __shared__ float s_red[4][SSB_DENSE_RCH][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -286,6 +286,136 @@ __global__ void __launch_bounds__(256) k_pes_fold(SsbCtx c, SsbPesDefer h, const
     }
 }
 
+// CTA-cooperative fold for decoders up to 56 columns (JP * (K + SSB_PFC_NT) * 128 bytes of shared memory must fit): the
+// warp-task form above keeps ~43 KB of loads in flight per SM and streams at 2.9 TB/s (154 us per fold on configs[1]).  Here a
+// neuron's decoder block ([32 trials][JP] floats = JP 128-byte rows, contiguous) is a TILE of a ring of SSB_PFC_NT shared-memory
+// buffers filled by TMA bulk copies (producer warp); the 8 consumer warps split the tile's 16-byte columns and keep THEIR
+// slice of the K x [32][JP] history terms ae in registers, so the tile is the only shared-memory traffic; f_q[i][trial] is one
+// coalesced load per (warp, slot) and reaches the lanes by shuffle.  A finished tile goes back with one bulk store; its
+// buffer is refilled once that store has read it (the producer lags SSB_PFC_LAG stores behind).
+// CTA = (neuron chunk, trial group, decoder), 288 threads, one CTA per SM.
+#define SSB_PFC_NT 6           // ring buffers
+#define SSB_PFC_NPT 4          // neurons per ring buffer (one bulk copy / store / fence / barrier round per 4 neurons)
+#define SSB_PFC_LAG 1
+template <int K>
+__global__ void __launch_bounds__(288, 1) k_pes_fold_cta(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
+                                                           const int* __restrict__ hdesc, int max_chunks) {
+    extern __shared__ __align__(128) float sm[];          // [SSB_PFC_NT][SSB_PFC_NPT][32 * JP]
+    __shared__ unsigned long long full[SSB_PFC_NT], done[SSB_PFC_NT];
+    const int item = blockIdx.z, chunk = blockIdx.x;
+    const int* d = desc + item * 13;
+    const int* hd = hdesc + item * 4;
+    const int n = d[0], size_out = d[1], d_off = d[2];
+    const int JP = ssb_pes_jp(size_out);
+    const int per = (n + max_chunks - 1) / max_chunks;
+    const int i_lo = chunk * per, i_hi = min(n, i_lo + per);
+    if (i_lo >= i_hi) return;
+    const int cnt = i_hi - i_lo;                          // neurons of this CTA
+    const int n_tiles = (cnt + SSB_PFC_NPT - 1) / SSB_PFC_NPT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.y;
+    const int neuron_f = 32 * JP, tile_f = SSB_PFC_NPT * neuron_f;
+    float* dg = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)i_lo * neuron_f;    // block of neuron i_lo
+    auto tile_bytes = [&](int t) { return (uint32_t)min(SSB_PFC_NPT, cnt - t * SSB_PFC_NPT) * (uint32_t)neuron_f * 4u; };
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < SSB_PFC_NT; ++b) {
+            ssb_mbar_init(&full[b], 1);
+            ssb_mbar_init(&done[b], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int t = 0; t < SSB_PFC_NT && t < n_tiles; ++t) {
+                ssb_mbar_expect_tx(&full[t], tile_bytes(t));
+                ssb_bulk_g2s(sm + (size_t)t * tile_f, dg + (size_t)t * tile_f, tile_bytes(t), &full[t]);
+            }
+            for (int t = 0; t < n_tiles; ++t) {
+                const int b = t % SSB_PFC_NT;
+                ssb_mbar_wait(&done[b], (uint32_t)(t / SSB_PFC_NT) & 1u);        // the 8 warps fenced their writes before arriving
+                ssb_bulk_s2g(dg + (size_t)t * tile_f, sm + (size_t)b * tile_f, tile_bytes(t));
+                ssb_bulk_commit();
+                const int tr = t - SSB_PFC_LAG;                                  // the store of tile tr has read its buffer
+                if (tr >= 0 && tr + SSB_PFC_NT < n_tiles) {
+                    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SSB_PFC_LAG) : "memory");
+                    const int br = tr % SSB_PFC_NT;
+                    ssb_mbar_expect_tx(&full[br], tile_bytes(tr + SSB_PFC_NT));
+                    ssb_bulk_g2s(sm + (size_t)br * tile_f, dg + (size_t)(tr + SSB_PFC_NT) * tile_f, tile_bytes(tr + SSB_PFC_NT),
+                                 &full[br]);
+                }
+            }
+            ssb_bulk_wait0();
+        }
+        return;
+    }
+    // consumers: warp w owns the 16-byte columns m = w, w + 8 (< JP / 4) of every neuron block: floats p = 128 m + 4 lane .. + 3,
+    // i.e. trial p / JP, columns p % JP .. + 3 of that trial
+    const float* __restrict__ hf = h.hist_f + ((size_t)g * h.rows_f + hd[1]) * 32 + lane;
+    const float* __restrict__ he = h.hist_e + ((size_t)g * h.rows_e + hd[0]) * 32;
+    const int nq = JP >> 2;
+    float4 e[2][K];
+    int tr_of[2], valid[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int m = warp + 8 * u;
+        valid[u] = m < nq;
+        const int p = 128 * m + 4 * lane;
+        const int trial = valid[u] ? p / JP : 0, j = valid[u] ? p - trial * JP : 0;
+        tr_of[u] = trial;
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                v[k] = (valid[u] && j + k < size_out) ? __ldg(he + (size_t)(q * size_out + j + k) * 32 + trial) : 0.f;
+            e[u][q] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    // f_q[i][trial] (lane = trial) is requested two neurons ahead: a dependent L2 round trip per neuron would otherwise be the
+    // pace of the whole CTA
+    float fa[K], fb[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        fa[q] = __ldg(hf + ((size_t)q * n + i_lo) * 32);
+        fb[q] = cnt > 1 ? __ldg(hf + ((size_t)q * n + i_lo + 1) * 32) : 0.f;
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+        const int b = t % SSB_PFC_NT;
+        ssb_mbar_wait(&full[b], (uint32_t)(t / SSB_PFC_NT) & 1u);
+        const int nn = min(SSB_PFC_NPT, cnt - t * SSB_PFC_NPT);
+        for (int r = 0; r < nn; ++r) {
+            const int i = t * SSB_PFC_NPT + r;
+            float fq[K];
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                fq[q] = fa[q];
+                fa[q] = fb[q];
+                fb[q] = i + 2 < cnt ? __ldg(hf + ((size_t)q * n + i_lo + i + 2) * 32) : 0.f;
+            }
+            float* W = sm + (size_t)b * tile_f + (size_t)r * neuron_f;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4* wp = reinterpret_cast<float4*>(W + 128 * (warp + 8 * u) + 4 * lane);
+                if (valid[u]) w = *wp;
+#pragma unroll
+                for (int q = 0; q < K; ++q) {
+                    const float f = __shfl_sync(0xffffffffu, fq[q], tr_of[u]);
+                    w.x = fmaf(e[u][q].x, f, w.x);
+                    w.y = fmaf(e[u][q].y, f, w.y);
+                    w.z = fmaf(e[u][q].z, f, w.z);
+                    w.w = fmaf(e[u][q].w, f, w.w);
+                }
+                if (valid[u]) *wp = w;
+            }
+        }
+        ssb_fence_async();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ssb_smem(&done[b])) : "memory");
+    }
+}
+
 __global__ void __launch_bounds__(128) k_pes_clear(SsbCtx c, SsbPesDefer h, int i_rel, int force) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x * 4 + warp;

@@ -46,6 +46,10 @@ DEC_TC_WIDTH = 64           # k_decode_tc: padded output width / neurons per sta
 DEC_TC_STAGE = 64
 
 
+FUSE_MAX_NNZ = 400_000   # largest composed level-0 program that is still fused into the end-of-step launch
+TABN_BASE = 1 << 28      # marker of 'table row of the next step' in the parity-0 CSR column list (resolved by _entries)
+
+
 def _best_chunks(n, units, slots_of, k_min, k_max, fixed=8, per_chunk=0.0):
     """Split a neuron range into k chunks so that the launch (units * k CTAs) wastes the least time on
     partial waves: minimise ceil(CTAs / resident slots) * neurons per chunk (+ the split-K reduce, which
@@ -116,6 +120,7 @@ class DevicePlan:
         self.filters: dict = {}         # conn/probe -> (filter_row0, size)
         self.launches: list = []        # human-readable launch order
         self.stats: dict = {}
+        self.stats_fusion: dict = {}    # nnz of level 0 / filter updates / their composition (step fusion), if considered
 
 
 class _Lowerer:
@@ -477,6 +482,10 @@ class _Lowerer:
                 dev_col[c] = next_scratch
                 next_scratch += 1
         NV = next_scratch
+        # logical columns ncol + k (k-th table column): the same input row of the NEXT step, i.e. the other parity's copy -
+        # used by the fused end-of-step rows that already evaluate the next step's level-0 sink rows (see below)
+        dev_col = np.concatenate([dev_col, TABN_BASE + np.arange(NT, dtype=np.int64)])
+        tab_ord = {c: k for k, c in enumerate(c for c in range(self.ncol) if self.col_kind[c] == "tab")}
         self.dev_col = dev_col
         for node, c0 in self.tab_col.items():
             plan.tables.append((node, int(dev_col[c0] - tab_row0), node.size_out))
@@ -507,6 +516,7 @@ class _Lowerer:
         # ---- sink rows are materialised once per level by k_lin-style passes (kinds 3 / 4) into vec scratch;
         #      the consumers' descriptors carry the vec row of their input
         mat_rows = [[] for _ in range(n_levels)]
+        mat_log = []          # (matrix, first vec row, level, previous_view) of every materialised block
 
         def materialize(mat, lvl, previous_view=False):
             nonlocal NV
@@ -515,6 +525,7 @@ class _Lowerer:
             NV += nrow
             for i in range(nrow):
                 mat_rows[lvl].append([r0 + i, 4 if previous_view else 3, v0 + i])
+            mat_log.append((mat.tocsr(), v0, lvl, previous_view))
             return v0
 
         # ---- weights + descriptors
@@ -737,15 +748,20 @@ class _Lowerer:
 
         lin_rows, lin_ab = [], []
         lin_early, lin_early_ab = [], []
+        filt_update = []      # (f0, size, a, b, U) of every Lowpass: y_new = a * y_old + b * (U . columns)
         for key, mat in filt_in.items():
             f0, size = plan.filters[key]
             tau = compat.synapse_tau(key.synapse)
             a64 = np.exp(-dt / tau) if tau > 0 else 0.0     # Lowpass(0) (slam_loihi.py:233): a pure one-step delay
             a, b = np.float32(a64), np.float32(1.0 - a64)
+            filt_update.append((f0, size, float(a), float(b), mat.tocsr()))
             r0 = add_rows(mat)
             if mat.shape[0] != size:
                 raise AssertionError("filter size mismatch")
-            early = early_rows(mat) if n_levels > 0 and os.environ.get("SSB_LIN_EARLY", "1") != "0" else np.zeros(size, bool)
+            # (single-level plans - PathIntegration - have no other chain to overlap with: the split would only add a launch;
+            #  measured on B200: SLAM 264.9 -> 260.3 us per step with the split, PathIntegration d = 97 74.0 -> 78.0 us)
+            early = (early_rows(mat) if n_levels > 1 and os.environ.get("SSB_LIN_EARLY", "1") != "0"
+                     else np.zeros(size, bool))
             for i in range(size):
                 if early[i]:
                     lin_early.append([r0 + i, 0, f0 + i])
@@ -800,6 +816,71 @@ class _Lowerer:
         def arr(rows, width):
             return np.asarray(rows, dtype=np.int32).reshape(-1, width)
 
+        # ---- step fusion: the level-0 sink rows of step t+1 read only constants, filter states and input tables, and the
+        #      new filter states are themselves linear in what step t has at its end (y_new = a y_old + b U v).  Composing
+        #      the two gives rows over step t's columns (+ the next step's table rows) that the END-OF-STEP launch of step t
+        #      can evaluate next to the filter updates - so the first launch of step t+1, on which every chain of the step
+        #      waits, disappears from the critical path.  Rows on the previous step's view (kind 4: the PES error) cannot be
+        #      moved; they stay in a small residual launch that only the PES chain waits for.
+        lin_fused = []
+        n_res = 0
+        # Measured on B200 and NOT the default (SSB_LIN_FUSE=1 enables it): the composed rows are 2.7x denser than level 0's
+        # own (configs[1]: 66 808 vs 24 648 entries), the fused launch takes as long as the two launches it replaces and the
+        # step gets slower - 273.0 vs 257.8 us (configs[1]), 75.1 vs 73.5 (PathIntegration d = 97), 389 vs 377 (SLAMView d = 97);
+        # profiles/r02h_perf_step_fusion.log.  A k_lin launch costs its latency chain, not its arithmetic.
+        if n_levels >= 1 and NF > 0 and os.environ.get("SSB_LIN_FUSE", "0") == "1":
+            ncol, ncx = self.ncol, self.ncol + NT
+            filt_cols = np.array([c for c in range(ncol) if self.col_kind[c] == "filt"], dtype=np.int64)
+            f_index = dev_col[filt_cols] - 1                                   # filter index of a logical filter column
+            rows_n, cols_n, vals_n = [], [], []
+            f_has = np.zeros(NF, dtype=bool)
+            for f0, size, a, b, U in filt_update:
+                U = U.tocoo()
+                rows_n += (f0 + U.row).tolist()
+                cols_n += U.col.tolist()
+                vals_n += (b * U.data).tolist()
+                f_has[f0:f0 + size] = True
+            # a * y_old: the logical column of filter f
+            col_of_f = np.zeros(NF, dtype=np.int64)
+            col_of_f[f_index] = filt_cols
+            a_of_f = np.zeros(NF)
+            for f0, size, a, b, U in filt_update:
+                a_of_f[f0:f0 + size] = a
+            rows_n += list(range(NF))
+            cols_n += col_of_f.tolist()
+            vals_n += a_of_f.tolist()
+            N = sp.csr_matrix((vals_n, (rows_n, cols_n)), shape=(NF, ncx))      # new filter states from step-t columns
+            sel_f = sp.csr_matrix((np.ones(len(filt_cols)), (filt_cols, f_index)), shape=(ncol, NF))
+            keep = np.array([self.col_kind[c] == "const" for c in range(ncol)])
+            tabs = np.array([c for c in range(ncol) if self.col_kind[c] == "tab"], dtype=np.int64)
+            sel_c = sp.csr_matrix((np.ones(int(keep.sum())), (np.flatnonzero(keep), np.flatnonzero(keep))), shape=(ncol, ncx))
+            sel_t = sp.csr_matrix((np.ones(len(tabs)), (tabs, ncol + np.array([tab_ord[c] for c in tabs], dtype=np.int64))),
+                                  shape=(ncol, ncx))
+            ok = bool(f_has.all())
+            blocks, nnz_in, nnz_out = [], 0, 0
+            for M, v0, lvl, prev in mat_log:
+                if lvl != 0 or prev:
+                    continue
+                kinds = {self.col_kind[c] for c in np.unique(M.indices)}
+                if not kinds <= {"const", "filt", "tab"}:
+                    ok = False
+                    break
+                comp = (M @ sel_f @ N + M @ sel_c + M @ sel_t).tocsr()
+                blocks.append((comp, v0))
+                nnz_in += M.nnz
+                nnz_out += comp.nnz
+            # fusion removes a LATENCY-bound launch; it composes matrices, so it must stay small: at d = 649 the level-0
+            # rows are 1 300 x 649 GEMMs (throughput-bound launches) and composing them with the inverse DFT doubles the work
+            plan.stats_fusion = dict(nnz_level0=int(nnz_in), nnz_filters=int(N.nnz), nnz_fused=int(nnz_out))
+            if ok and blocks and nnz_out <= 4 * (nnz_in + N.nnz) and nnz_out <= FUSE_MAX_NNZ:
+                for comp, v0 in blocks:
+                    r0 = add_rows(comp)
+                    for i in range(comp.shape[0]):
+                        lin_fused.append([r0 + i, 3, v0 + i])
+                # the residual launch of a fused step: level 0's previous-view rows, kept at the end of its segment
+                mat_rows[0].sort(key=lambda r: r[1] == 4)
+                n_res = sum(1 for r in mat_rows[0] if r[1] == 4)
+
         lin_final = lin_rows
         lin_final_ab = lin_ab
         lin_rows, lin_ab, level_rows = [], [], []
@@ -808,8 +889,8 @@ class _Lowerer:
             lin_rows += mat_rows[lvl]
             lin_ab += [[0.0, 1.0]] * len(mat_rows[lvl])
         lin0 = len(lin_rows)
-        lin_rows += lin_early + lin_final                  # final rows: [early | late]
-        lin_ab += lin_early_ab + lin_final_ab
+        lin_rows += lin_early + lin_final + lin_fused      # final rows: [early | late | next step's level-0 rows (fused)]
+        lin_ab += lin_early_ab + lin_final_ab + [[0.0, 1.0]] * len(lin_fused)
         stages = []  # per level counts/offsets into the concatenated descriptor arrays
         cat = {k: [] for k in ("small", "big", "dec", "cleanup", "gate")}
         for lvl in range(n_levels):
@@ -845,7 +926,8 @@ class _Lowerer:
         plan.scalars.update(dict(dt=dt, nv=NV, nf=NF, nt=NT, tab_row0=tab_row0, nn=nn, n_act=n_act, n_lenc=n_lenc,
                                  n_ldec=n_ldec, n_afilt=n_afilt, n_probe=n_probe_rows, n_levels=n_levels,
                                  chunk_cap=chunk_cap, n_part=n_part, n_jtiles=n_jtiles, pes_level=pes_level,
-                                 lin0=lin0, n_lin=len(lin_rows) - lin0, n_lin_early=len(lin_early)))
+                                 lin0=lin0, n_lin=len(lin_rows) - lin0 - len(lin_fused), n_lin_early=len(lin_early),
+                                 n_lin_fused=len(lin_fused), n_lvl0_res=n_res))
         n_static = int(sum(a.size for a in W))
         if self.per_trial:
             plan.scalars["per_trial_weights"] = 1.0
@@ -920,8 +1002,10 @@ class _Lowerer:
         the half that is read on steps of this parity (``par`` = 0 for even steps, ``nf`` for odd ones);
         input-table rows likewise point at the copy written for steps of this parity."""
         rows = np.asarray(idx, dtype=np.int64)
+        nxt = rows >= TABN_BASE                              # table rows of the NEXT step: the other parity's copy
         if par and nt:
             rows = np.where((rows >= tab_row0) & (rows < tab_row0 + nt), rows + nt, rows)
+        rows = np.where(nxt, rows - TABN_BASE + tab_row0 + (0 if par else nt), rows)
         rows = np.where((rows >= 1) & (rows <= nf), rows + par, rows)
         ent = np.empty((len(rows), 2), dtype=np.int32)
         ent[:, 0] = rows

@@ -10,6 +10,11 @@ Batching extension (not in the reference, which has no batch axis):
 ``Simulator(network, n_trials=B, trial_inputs={node: array[B, T, size]}, trial_seeds=[...])``
 runs B independent trials that share the static weights; learned PES/Voja matrices and
 all state are per trial.  ``sim.data[probe]`` then has a leading trial axis.
+``trial_seeds`` select the start voltages: ``None`` = nengo's own draw for the built model, an int = a hash of (ensemble
+seed, that int, neuron).  The default is ``[None, 0, 1, ...]`` so that trial 0 of a batch IS the unbatched nengo run; a
+sharded job passes ``sharding.trial_seeds`` (global trial ids) explicitly, so a trial's start state does not depend on
+how the batch is split over GPUs.  ``trial_network_seeds`` gives every trial its own NETWORK seed instead (one built model
+per distinct seed, per-trial static weights).
 
 ``input_synthesis=dict(...)`` (optional) evaluates the drivers' per-step input closures on the device from
 per-trial paths / landmarks (``slam.py:442-497``) instead of ``trial_inputs`` tables.

@@ -114,6 +114,11 @@ class PlanInterpreter:
             for src, kind, dst in a["lin_rows"][st[10]:st[10] + st[11]]:     # materialise this level's sink rows
                 assert kind in (3, 4)
                 self.vec[dst] = self.rows(src, 1, 1 if kind == 4 else 0)[0]
+                if getattr(self, "fused_next", None) is not None and kind == 3 and int(dst) in self.fused_next:
+                    want = self.vec[dst]                                     # what the previous step's fused row predicted
+                    got = self.fused_next.pop(int(dst))
+                    self.fused_err = max(getattr(self, "fused_err", 0.0), abs(got - want) / (abs(want) + 1e-3))
+                    self.fused_checked = getattr(self, "fused_checked", 0) + 1
             for d in a["ens_small"][st[0]:st[0] + st[1]]:
                 n, dims, nout, s0, w_off, in_row0, out_vec, tid, stride = (int(x) for x in d)
                 pk = self.Wp[w_off:w_off + n * stride].reshape(n, stride)
@@ -180,7 +185,8 @@ class PlanInterpreter:
         probe = np.zeros(int(self.p.scalars["n_probe"]), self.dt_)
         new_f = {}
         lin0 = int(self.p.scalars["lin0"])
-        for (src, kind, dst), (ca, cb) in zip(a["lin_rows"][lin0:], a["lin_ab"][lin0:].astype(self.dt_)):
+        n_lin = int(self.p.scalars["n_lin"])
+        for (src, kind, dst), (ca, cb) in zip(a["lin_rows"][lin0:lin0 + n_lin], a["lin_ab"][lin0:lin0 + n_lin].astype(self.dt_)):
             if kind == 0:
                 new_f[1 + dst + par_new] = cb * self.rows(src, 1)[0] + ca * self.vec[1 + dst + par_old]
             elif kind == 1:
@@ -190,6 +196,15 @@ class PlanInterpreter:
             else:
                 ob = s & 1
                 self.afilt[1 - ob, dst] = cb * self.act[src] + ca * self.afilt[ob, dst]
+        # fused end-of-step rows (lowering: step fusion): the NEXT step's level-0 sink rows evaluated now, from this step's
+        # columns and the next step's table rows (the other parity's copy, as the device's input prefetch leaves them)
+        n_fused = int(self.p.scalars.get("n_lin_fused", 0))
+        self.fused_next = None
+        if n_fused and self.nt and s + 1 < len(self.tables):
+            r1 = self.tab_row0 + (0 if s & 1 else self.nt)
+            self.vec[r1:r1 + self.nt] = self.tables[s + 1]
+            n_all = len(a["lin_rows"])
+            self.fused_next = {int(dst): self.rows(int(src), 1)[0] for src, kind, dst in a["lin_rows"][n_all - n_fused:]}
         for k, val in new_f.items():
             self.vec[k] = val
         self.probe_rows.append(probe)

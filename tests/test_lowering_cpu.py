@@ -24,6 +24,11 @@ def _compare(sc, n_steps, n_trials_hint=1, tol=2e-5):
     assert scale > 1e-3
     # the plan stores weights / CSR coefficients in float32 (the interpreter's arithmetic is float64)
     assert np.max(np.abs(got - want)) <= tol * scale
+    # step fusion: the rows the end-of-step launch evaluates for the NEXT step equal that step's own level-0 rows
+    if plan.scalars["n_lin_fused"]:
+        n0 = int(plan.arrays["stages"][0][11])
+        assert plan.scalars["n_lin_fused"] == n0 - plan.scalars["n_lvl0_res"]
+        assert it.fused_checked == plan.scalars["n_lin_fused"] * (n_steps - 1) and it.fused_err < 1e-4
     return plan, model, ref, it
 
 
@@ -202,3 +207,16 @@ def test_slamview_with_the_drivers_bound_view_input_matches_oracle():
     assert np.all((np.abs(norms - 1.0) < 1e-9) | (norms == 0)) and norms.max() > 0     # unit view vectors when in view
     assert sc.extra["input_synthesis"] is None
     _compare(sc, 60)
+
+
+def test_step_fusion_rows_equal_the_next_steps_level0_rows(monkeypatch):
+    """SSB_LIN_FUSE=1 (opt-in; measured slower on B200): the end-of-step launch also evaluates the next
+    step's level-0 sink rows from this step's columns; ``_compare`` checks every such row against the next step's own."""
+    monkeypatch.setenv("SSB_LIN_FUSE", "1")
+    sc = scenarios.make_slam(n_trials=1, n_steps=40, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=70,
+                             circonv_n_neurons=16, n_landmarks=6, T=20.0, neuron_type="lif", view_rad=0.6)
+    plan, *_ = _compare(sc, 40)
+    assert plan.scalars["n_lin_fused"] > 0 and plan.scalars["n_lvl0_res"] > 0
+    sc = scenarios.make_pathint(n_trials=1, n_steps=40, ssp_dim=19, pi_n_neurons=40, neuron_type="lifrate")
+    plan, *_ = _compare(sc, 40)
+    assert plan.scalars["n_lin_fused"] > 0 and plan.scalars["n_lvl0_res"] == 0
