@@ -26,7 +26,7 @@ res = {k: {"dram_bytes_per_launch": v["dram_bytes"] / v["launches"], "launches_c
            "ncu_time_us_per_launch": v["time_us"] / v["launches"]} for k, v in acc.items()}
 # whole-timestep DRAM bytes: mean bytes per launch of every kernel x its launches per timestep (a capture window rarely
 # starts and ends on a step boundary, so "sum / steps captured" over-counts the ragged ends).  BASELINE configs[1]: two
-# levels -> k_ens_small x 2, k_lin x 3 (level 0, level 1, end of step); the deferred-PES fold + clear every 8th step (their
+# levels -> k_ens_small x 2, k_lin x 4 (level 0, level 1, early end-of-step rows, end of step); the deferred-PES fold + clear every 8th step (their
 # bytes come from FOLD_MB when the window holds none: profiles/r02c_ncu_pes_summary.csv).
 all_acc = {}
 for r in rows[2:]:
@@ -35,7 +35,7 @@ for r in rows[2:]:
     a[0] += 1
     a[1] += float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
 import os
-PER_STEP = {"k_ens_small": 2.0, "k_lin": 3.0, "k_pes_fold": 0.125, "k_pes_clear": 0.125, "k_advance": 1.0 / 16}
+PER_STEP = {"k_ens_small": 2.0, "k_lin": 4.0, "k_pes_fold": 0.125, "k_pes_clear": 0.125, "k_advance": 1.0 / 16}
 per_step = {k: v[1] / v[0] * PER_STEP.get(k, 1.0) for k, v in all_acc.items()}
 if "k_pes_fold" not in per_step and os.environ.get("FOLD_MB"):
     per_step["k_pes_fold"] = float(os.environ["FOLD_MB"]) * 1e6 * 0.125

@@ -796,8 +796,8 @@ void launch_pes_fold(ssb_sim* s, cudaStream_t st, int i_rel, int force) {
     // per fold on configs[1] in three variants (profiles/r02i_perf_pes_fold_cta.log) - so it is not the default.
     const char* fold_env = getenv("SSB_PES_FOLD");
     const bool fold_cta = fold_env && std::string(fold_env) == "cta";
-    if (max_jp <= 64 && fold_cta) {
-        const size_t smem = (size_t)SSB_PFC_NT * SSB_PFC_NPT * 32 * max_jp * sizeof(float);
+    if (max_jp <= 56 && fold_cta) {
+        const size_t smem = (size_t)SSB_PFC_NT * SSB_PFC_NPT * 32 * (max_jp + s->pes_h.K) * sizeof(float);
         const int chunks = std::max(1, std::min(148 / std::max(1, s->n_groups * s->n_pes), (max_n + 15) / 16));
         dim3 grid(chunks, s->n_groups, s->n_pes);
         if (s->pes_h.K == 4) {

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) k_pes_fold(SsbCtx c, SsbPesDefer h, const
 template <int K>
 __global__ void __launch_bounds__(288, 1) k_pes_fold_cta(SsbCtx c, SsbPesDefer h, const int* __restrict__ desc,
                                                            const int* __restrict__ hdesc, int max_chunks) {
-    extern __shared__ __align__(128) float sm[];          // [SSB_PFC_NT][SSB_PFC_NPT][32 * JP]
+    extern __shared__ __align__(128) float sm[];          // [SSB_PFC_NT][SSB_PFC_NPT][32 * JP] | f ring [SSB_PFC_NT][K][SSB_PFC_NPT][32]
     __shared__ unsigned long long full[SSB_PFC_NT], done[SSB_PFC_NT];
     const int item = blockIdx.z, chunk = blockIdx.x;
     const int* d = desc + item * 13;
@@ -317,6 +317,19 @@ __global__ void __launch_bounds__(288, 1) k_pes_fold_cta(SsbCtx c, SsbPesDefer h
     const int neuron_f = 32 * JP, tile_f = SSB_PFC_NPT * neuron_f;
     float* dg = c.ldec + ((size_t)g * c.n_ldec + d_off) * 32 + (size_t)i_lo * neuron_f;    // block of neuron i_lo
     auto tile_bytes = [&](int t) { return (uint32_t)min(SSB_PFC_NPT, cnt - t * SSB_PFC_NPT) * (uint32_t)neuron_f * 4u; };
+    // the history factors f_q[i][trial] of a tile's neurons ride on the same barrier: for one slot q the rows of consecutive
+    // neurons are contiguous, so they are K more (small) bulk copies per tile - as plain loads they were a dependent L2 round
+    // trip per neuron and the pace of the whole CTA (231 / 194 us per fold without / with a two-neuron register prefetch)
+    float* fr = sm + (size_t)SSB_PFC_NT * tile_f;
+    const float* __restrict__ hfb = h.hist_f + ((size_t)g * h.rows_f + hd[1]) * 32;
+    auto load_tile = [&](int t, int b) {
+        const int nn = min(SSB_PFC_NPT, cnt - t * SSB_PFC_NPT);
+        ssb_mbar_expect_tx(&full[b], tile_bytes(t) + (uint32_t)(K * nn * 128));
+        ssb_bulk_g2s(sm + (size_t)b * tile_f, dg + (size_t)t * tile_f, tile_bytes(t), &full[b]);
+        for (int q = 0; q < K; ++q)
+            ssb_bulk_g2s(fr + ((size_t)(b * K + q) * SSB_PFC_NPT) * 32, hfb + ((size_t)q * n + i_lo + t * SSB_PFC_NPT) * 32,
+                         (uint32_t)nn * 128u, &full[b]);
+    };
     if (threadIdx.x == 0) {
         for (int b = 0; b < SSB_PFC_NT; ++b) {
             ssb_mbar_init(&full[b], 1);
@@ -327,10 +340,7 @@ __global__ void __launch_bounds__(288, 1) k_pes_fold_cta(SsbCtx c, SsbPesDefer h
     __syncthreads();
     if (warp == 8) {
         if (lane == 0) {
-            for (int t = 0; t < SSB_PFC_NT && t < n_tiles; ++t) {
-                ssb_mbar_expect_tx(&full[t], tile_bytes(t));
-                ssb_bulk_g2s(sm + (size_t)t * tile_f, dg + (size_t)t * tile_f, tile_bytes(t), &full[t]);
-            }
+            for (int t = 0; t < SSB_PFC_NT && t < n_tiles; ++t) load_tile(t, t);
             for (int t = 0; t < n_tiles; ++t) {
                 const int b = t % SSB_PFC_NT;
                 ssb_mbar_wait(&done[b], (uint32_t)(t / SSB_PFC_NT) & 1u);        // the 8 warps fenced their writes before arriving
@@ -339,10 +349,7 @@ __global__ void __launch_bounds__(288, 1) k_pes_fold_cta(SsbCtx c, SsbPesDefer h
                 const int tr = t - SSB_PFC_LAG;                                  // the store of tile tr has read its buffer
                 if (tr >= 0 && tr + SSB_PFC_NT < n_tiles) {
                     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SSB_PFC_LAG) : "memory");
-                    const int br = tr % SSB_PFC_NT;
-                    ssb_mbar_expect_tx(&full[br], tile_bytes(tr + SSB_PFC_NT));
-                    ssb_bulk_g2s(sm + (size_t)br * tile_f, dg + (size_t)(tr + SSB_PFC_NT) * tile_f, tile_bytes(tr + SSB_PFC_NT),
-                                 &full[br]);
+                    load_tile(tr + SSB_PFC_NT, tr % SSB_PFC_NT);
                 }
             }
             ssb_bulk_wait0();
@@ -351,7 +358,6 @@ __global__ void __launch_bounds__(288, 1) k_pes_fold_cta(SsbCtx c, SsbPesDefer h
     }
     // consumers: warp w owns the 16-byte columns m = w, w + 8 (< JP / 4) of every neuron block: floats p = 128 m + 4 lane .. + 3,
     // i.e. trial p / JP, columns p % JP .. + 3 of that trial
-    const float* __restrict__ hf = h.hist_f + ((size_t)g * h.rows_f + hd[1]) * 32 + lane;
     const float* __restrict__ he = h.hist_e + ((size_t)g * h.rows_e + hd[0]) * 32;
     const int nq = JP >> 2;
     float4 e[2][K];
@@ -372,27 +378,14 @@ __global__ void __launch_bounds__(288, 1) k_pes_fold_cta(SsbCtx c, SsbPesDefer h
             e[u][q] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    // f_q[i][trial] (lane = trial) is requested two neurons ahead: a dependent L2 round trip per neuron would otherwise be the
-    // pace of the whole CTA
-    float fa[K], fb[K];
-#pragma unroll
-    for (int q = 0; q < K; ++q) {
-        fa[q] = __ldg(hf + ((size_t)q * n + i_lo) * 32);
-        fb[q] = cnt > 1 ? __ldg(hf + ((size_t)q * n + i_lo + 1) * 32) : 0.f;
-    }
     for (int t = 0; t < n_tiles; ++t) {
         const int b = t % SSB_PFC_NT;
         ssb_mbar_wait(&full[b], (uint32_t)(t / SSB_PFC_NT) & 1u);
         const int nn = min(SSB_PFC_NPT, cnt - t * SSB_PFC_NPT);
         for (int r = 0; r < nn; ++r) {
-            const int i = t * SSB_PFC_NPT + r;
             float fq[K];
 #pragma unroll
-            for (int q = 0; q < K; ++q) {
-                fq[q] = fa[q];
-                fa[q] = fb[q];
-                fb[q] = i + 2 < cnt ? __ldg(hf + ((size_t)q * n + i_lo + i + 2) * 32) : 0.f;
-            }
+            for (int q = 0; q < K; ++q) fq[q] = fr[((size_t)(b * K + q) * SSB_PFC_NPT + r) * 32 + lane];      // lane = trial
             float* W = sm + (size_t)b * tile_f + (size_t)r * neuron_f;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
