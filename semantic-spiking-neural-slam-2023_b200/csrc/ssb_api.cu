@@ -791,11 +791,12 @@ void launch_pes_fold(ssb_sim* s, cudaStream_t st, int i_rel, int force) {
         max_n = std::max(max_n, s->h_pes[i * 13]);
         max_jp = std::max(max_jp, (s->h_pes[i * 13 + 1] + 3) & ~3);
     }
-    // SSB_PES_FOLD=cta (decoders up to 64 columns): the CTA-cooperative fold (ring of 4-neuron tiles by TMA, history terms in
-    // registers).  Correct (GPU suite) but measured SLOWER on B200 than the warp-task kernel below - 194 - 231 us vs 153 us
-    // per fold on configs[1] in three variants (profiles/r02i_perf_pes_fold_cta.log) - so it is not the default.
+    // decoders up to 56 columns: the CTA-cooperative fold (ring of 4-neuron tiles AND their history factors by TMA, history
+    // terms in registers): 85.8 us per fold on configs[1] = 5.2 TB/s, against 153 us for the warp-task kernel below, which
+    // stays for wider decoders and as SSB_PES_FOLD=tasks.  (With the factors as plain loads - a dependent L2 round trip per
+    // neuron - the same kernel took 194 - 231 us: profiles/r02i_perf_pes_fold_cta.log.)
     const char* fold_env = getenv("SSB_PES_FOLD");
-    const bool fold_cta = fold_env && std::string(fold_env) == "cta";
+    const bool fold_cta = !(fold_env && std::string(fold_env) == "tasks");
     if (max_jp <= 56 && fold_cta) {
         const size_t smem = (size_t)SSB_PFC_NT * SSB_PFC_NPT * 32 * (max_jp + s->pes_h.K) * sizeof(float);
         const int chunks = std::max(1, std::min(148 / std::max(1, s->n_groups * s->n_pes), (max_n + 15) / 16));

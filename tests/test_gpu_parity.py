@@ -236,7 +236,7 @@ def test_wide_d295_network_on_the_k_blocked_tensor_core_kernels(env, monkeypatch
 @pytest.mark.parametrize("env", [{"SSB_SCAN": "ffma"}, {"SSB_DECODE": "ffma"}, {"SSB_ENCODE": "tc"},
                                  {"SSB_SCAN": "ffma", "SSB_DECODE": "ffma", "SSB_SERIAL": "1"},
                                  {"SSB_PES_DEFER": "4"}, {"SSB_PES_FUSE": "1"}, {"SSB_LEVEL_DEPS": "0"},
-                                 {"SSB_DECODE": "sparse"}, {"SSB_VOJA_NB": "3"}, {"SSB_PES_FOLD": "cta"},
+                                 {"SSB_DECODE": "sparse"}, {"SSB_VOJA_NB": "3"}, {"SSB_PES_FOLD": "tasks"},
                                  {"SSB_LIN_FUSE": "1"}])
 def test_alternate_kernel_paths_match_oracle(env, monkeypatch):
     """Every shared-weight GEMM has an FFMA and a tcgen05 (3xTF32) kernel; whichever is selected, the
