@@ -175,6 +175,43 @@ def _oracle_for_trial(sc, model, trial):
     return RefSimulator(sc.network, dt=sc.dt, model=model, node_tables=tabs)
 
 
+def _merged_for_trial(sc, model, trial, plan=None):
+    """Operator-merged CPU executor (oracle/plan_cpu.py) of the lowered plan: the honest lower companion of the unmerged port."""
+    from oracle.plan_cpu import MergedPlanSimulator
+    from sspslam_b200 import lowering
+    if plan is None:
+        plan = lowering.lower(sc.network, model, chunk_cap=64, n_trials=1)
+    tabs = {node: arr[trial] for node, arr in sc.trial_inputs.items()}
+    return MergedPlanSimulator(plan, model, sc.network, tabs)
+
+
+MERGED_NOTE = ("operator-merged CPU executor of the same lowered plan (oracle/plan_cpu.py, float64: every group of like "
+               "operators is one vector operation, the glue algebra is collapsed) - an upper bound of what nengo's operator "
+               "merging reaches on one core; checked against the operator-level port in tests/test_plan_cpu.py")
+
+
+def cpu_baseline_merged(sc, model, n_steps, warm=40):
+    """One trial on one core with the merged executor (BLAS pinned to one thread); ``None`` if it cannot run."""
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
+    try:
+        sim = _merged_for_trial(sc, model, 0)
+        n_steps = int(min(n_steps, len(sim.tables) - warm - 1)) if sim.nt else int(n_steps)
+        sim.run_steps(warm)
+        t0 = time.perf_counter()
+        sim.run_steps(n_steps)
+        v = n_steps / (time.perf_counter() - t0)
+        return {"value": v, "unit": UNIT, "cores": 1, "kind": "port (operator-merged)",
+                "sample": f"1 trial x {n_steps} timesteps after {warm} warm-up steps; " + MERGED_NOTE}
+    except Exception as e:      # a companion number must never cost the bench line
+        return {"value": None, "error": repr(e)[:200]}
+    finally:
+        del limiter
+
+
 def cpu_baseline_single(sc, model, n_steps, warm=40):
     """One trial of the CPU port on one core: BLAS pinned to one thread (the headline row; the operators are tiny) and
     BLAS threads as NumPy finds them (BASELINE.md §4 asks for both)."""
@@ -193,6 +230,7 @@ def cpu_baseline_single(sc, model, n_steps, warm=40):
         pinned = timed(n_steps)
     return {"value": pinned, "unit": UNIT, "cores": 1, "kind": "port",
             "blas_unpinned": {"value": unpinned, "threads_available": len(os.sched_getaffinity(0))},
+            "op_merged": cpu_baseline_merged(sc, model, n_steps, warm),
             "host_cpu_count": os.cpu_count(),
             "sample": f"1 trial x {n_steps} timesteps of the same built network after {warm} warm-up steps "
                       f"(oracle/nengo_ref_sim.py, float64, unmerged operators: ~5 500 NumPy calls per timestep, so it is "
@@ -200,13 +238,14 @@ def cpu_baseline_single(sc, model, n_steps, warm=40):
 
 
 def _ref_worker(args):
-    sc, model, trial, warm, chunk, k, barrier, q = args
+    sc, model, trial, warm, chunk, k, barrier, q = args[:8]
+    plan = args[8] if len(args) > 8 else None
     try:
         from threadpoolctl import threadpool_limits
         limiter = threadpool_limits(limits=1)
     except Exception:
         limiter = None
-    ref = _oracle_for_trial(sc, model, trial)
+    ref = _merged_for_trial(sc, model, trial, plan) if plan is not None else _oracle_for_trial(sc, model, trial)
     ref.run_steps(warm * chunk)
     barrier.wait()
     t0 = time.perf_counter()
@@ -241,11 +280,30 @@ def run_reference(args):
     value = total / wall
     sample = (f"{cores} processes x 1 trial x {args.steps}x{args.ref_chunk} timesteps "
               f"(after {args.warmup}x{args.ref_chunk} warm-up), float64 NumPy operator port of nengo's reference simulator")
+    # companion: the operator-merged executor on the same trials and cores (never the line's value: it runs the product's
+    # lowering, the line's value is the operator-level port alone)
+    merged = None
+    try:
+        from sspslam_b200 import lowering
+        plan = lowering.lower(sc.network, model, chunk_cap=64, n_trials=1)
+        barrier2, q2 = ctx.Barrier(cores), ctx.Queue()
+        procs = [ctx.Process(target=_ref_worker, args=((sc, model, i, args.warmup, args.ref_chunk, args.steps, barrier2, q2, plan),))
+                 for i in range(cores)]
+        for p in procs:
+            p.start()
+        spans2 = [q2.get(timeout=600) for _ in procs]
+        for p in procs:
+            p.join()
+        wall2 = max(t1 for _, t1 in spans2) - min(t0 for t0, _ in spans2)
+        merged = {"value": total / wall2, "unit": UNIT, "cores": cores, "kind": "port (operator-merged)",
+                  "sample": f"{cores} processes x 1 trial x {args.steps}x{args.ref_chunk} timesteps; " + MERGED_NOTE}
+    except Exception as e:
+        merged = {"value": None, "error": repr(e)[:200]}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][0], "timesteps_per_step": args.ref_chunk, "trials": cores, "distinct_trials": cores},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "op_merged": merged},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
