@@ -220,3 +220,47 @@ def test_step_fusion_rows_equal_the_next_steps_level0_rows(monkeypatch):
     sc = scenarios.make_pathint(n_trials=1, n_steps=40, ssp_dim=19, pi_n_neurons=40, neuron_type="lifrate")
     plan, *_ = _compare(sc, 40)
     assert plan.scalars["n_lin_fused"] > 0 and plan.scalars["n_lvl0_res"] == 0
+
+
+def test_early_end_of_step_rows_read_only_what_exists_after_level0_narrow_ensembles():
+    """The launch sequence runs the 'early' end-of-step rows right after level 0's narrow-ensemble kernel, next to every
+    other chain of the step.  So none of their entries may point at a vec row that is produced later in the step: outputs
+    of later levels' narrow ensembles, of static / PES decoders, of clean-up or gate nodes; and they must be filter rows
+    (they write the half nobody reads in this step)."""
+    sc = scenarios.make_slam(n_trials=1, n_steps=10, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=70, circonv_n_neurons=16,
+                             n_landmarks=6, T=20.0, view_rad=0.6)
+    plan = lowering.lower(sc.network, build_model(sc.network, dt=sc.dt))
+    a, s = plan.arrays, plan.scalars
+    n_early, lin0 = int(s["n_lin_early"]), int(s["lin0"])
+    assert 0 < n_early < s["n_lin"] and s["n_levels"] == 2
+    late = set()
+    for lvl, st in enumerate(a["stages"]):
+        if lvl > 0:
+            for d in a["ens_small"][st[0]:st[0] + st[1]]:
+                late.update(range(int(d[6]), int(d[6]) + int(d[2])))
+        for d in a["dec"][st[4]:st[4] + st[5]]:
+            late.update(range(int(d[5]), int(d[5]) + int(d[1])))
+        for d in a["cleanup"][st[6]:st[6] + st[7]]:
+            late.update(range(int(d[5]), int(d[5]) + int(d[1])))
+        for d in a["gate"][st[8]:st[8] + st[9]]:
+            late.update(range(int(d[2]), int(d[2]) + int(d[0])))
+    for d in a["pes"]:
+        late.update(range(int(d[6]), int(d[6]) + int(d[1])))
+    assert late
+    ptr = a["csr_ptr"]
+    early, rest = a["lin_rows"][lin0:lin0 + n_early], a["lin_rows"][lin0 + n_early:lin0 + int(s["n_lin"])]
+    assert np.all(early[:, 1] == 0)
+    for ent in (a["csr_ent0"], a["csr_ent1"]):
+        for src, _, _ in early:
+            rows = ent[ptr[src]:ptr[src + 1], 0]
+            assert not late.intersection(int(r) for r in rows)
+    # and the split is not trivial: some remaining filter row does read a late-produced row
+    reads_late = False
+    for src, kind, _ in rest:
+        if kind == 0 and late.intersection(int(r) for r in a["csr_ent0"][ptr[src]:ptr[src + 1], 0]):
+            reads_late = True
+            break
+    assert reads_late
+    # a single-level plan keeps one end-of-step launch
+    pi = scenarios.make_pathint(n_trials=1, n_steps=10, ssp_dim=19, pi_n_neurons=40)
+    assert lowering.lower(pi.network, build_model(pi.network, dt=pi.dt)).scalars["n_lin_early"] == 0
