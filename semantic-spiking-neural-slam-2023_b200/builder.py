@@ -304,12 +304,90 @@ class _blas_threads:
             self._ctx.__exit__(*exc)
 
 
+def _builder_procs(n_ensembles):
+    """Worker processes of the host builder: ``SSB_BUILDER_PROCS`` (0 / 1 = in-process), else the cores this process may use
+    when the network is large enough to pay for the fork (and this process is not itself a pool worker)."""
+    import multiprocessing as mp
+    if mp.current_process().daemon:
+        return 1
+    env = os.environ.get("SSB_BUILDER_PROCS")
+    if env is not None:
+        return max(1, int(env))
+    if n_ensembles < 128 or not hasattr(os, "fork"):
+        return 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores //= max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))        # one process per GPU shares the host
+    return max(1, min(cores, 16, n_ensembles // 16))
+
+
+_PAR_CTX = None      # (model, ensembles, connections / probes grouped by their pre-ensemble) for the forked workers
+
+
+def _par_job(i):
+    model, ensembles, by_ens = _PAR_CTX
+    ens = ensembles[i]
+    _build_ensemble(model, ens)
+    cache = _DecoderCache(model)
+    conns, probes = by_ens.get(ens, ((), ()))
+    out_c, out_p = [], []
+    for ci, conn in conns:
+        _build_connection(model, conn, cache)
+        out_c.append((ci, model.params[conn]))
+    for pi, probe in probes:
+        _build_probe(model, probe, cache)
+        out_p.append((pi, model.probe_conns.get(probe)))
+    return model.params[ens], out_c, out_p
+
+
+def _build_parallel(model, network, procs):
+    """Every ensemble's sampling, tuning curves and decoder solves depend on its own seed only, so ensembles (with the
+    decoded connections and probes leaving them) are built by a fork pool; the parent stores the results in the order of
+    the in-process build, so the two are indistinguishable (tests/test_builder_parallel.py)."""
+    import multiprocessing as mp
+    global _PAR_CTX
+    ensembles, conns, probes = list(network.all_ensembles), list(network.all_connections), list(network.all_probes)
+    by_ens = {}
+    for ci, c in enumerate(conns):
+        if compat.is_ensemble(c.pre_obj):
+            by_ens.setdefault(c.pre_obj, ([], []))[0].append((ci, c))
+    for pi, p in enumerate(probes):
+        if compat.is_ensemble(p.obj) and p.attr == "decoded_output":
+            by_ens.setdefault(p.obj, ([], []))[1].append((pi, p))
+    _PAR_CTX = (model, ensembles, by_ens)
+    try:
+        with mp.get_context("fork").Pool(procs) as pool:
+            results = pool.map(_par_job, range(len(ensembles)), chunksize=max(1, len(ensembles) // (8 * procs)))
+    finally:
+        _PAR_CTX = None
+    built_c, built_p = {}, {}
+    for ens, (pe, out_c, out_p) in zip(ensembles, results):
+        model.params[ens] = pe
+        built_c.update(out_c)
+        built_p.update(out_p)
+    cache = _DecoderCache(model)
+    for ci, conn in enumerate(conns):
+        if ci in built_c:
+            model.params[conn] = built_c[ci]
+        else:
+            _build_connection(model, conn, cache)
+    for pi, probe in enumerate(probes):
+        if pi in built_p:
+            model.probe_conns[probe] = built_p[pi]
+            model.params[probe] = None
+        else:
+            _build_probe(model, probe, cache)
+    return model
+
+
 def _build_all(model, network, device_solver):
+    if device_solver is None and os.environ.get("SSB_DEVICE_BUILDER") not in (None, "", "off"):
+        device_solver = int(os.environ["SSB_DEVICE_BUILDER"])
+    procs = _builder_procs(len(network.all_ensembles)) if device_solver is None else 1
+    if procs > 1:
+        return _build_parallel(model, network, procs)
     cache = _DecoderCache(model)
     for ens in network.all_ensembles:
         _build_ensemble(model, ens)
-    if device_solver is None and os.environ.get("SSB_DEVICE_BUILDER") not in (None, "", "off"):
-        device_solver = int(os.environ["SSB_DEVICE_BUILDER"])
     if device_solver is not None:
         cache.presolve_on_device(network, int(device_solver))
     for conn in network.all_connections:
