@@ -448,9 +448,10 @@ class _Lowerer:
         level_deps = np.zeros((n_levels, n_levels), dtype=np.int32)
 
         def note_deps(lvl, *mats):
-            for c in cols_of(*mats).astype(np.int64):
-                if col_prod[c]:
-                    level_deps[lvl, col_plvl[c]] |= int(col_prod[c])
+            cols = cols_of(*mats).astype(np.int64)
+            cols = cols[col_prod[cols] != 0]
+            if cols.size:
+                np.bitwise_or.at(level_deps[lvl], col_plvl[cols], col_prod[cols].astype(np.int32))
         for ens in self.ensembles:
             mats = [ens_in[ens]]
             if ens in ens_jn:
