@@ -264,3 +264,13 @@ def test_early_end_of_step_rows_read_only_what_exists_after_level0_narrow_ensemb
     # a single-level plan keeps one end-of-step launch
     pi = scenarios.make_pathint(n_trials=1, n_steps=10, ssp_dim=19, pi_n_neurons=40)
     assert lowering.lower(pi.network, build_model(pi.network, dt=pi.dt)).scalars["n_lin_early"] == 0
+
+
+def test_level_dependencies_of_slam():
+    """Level 1 of SLAM (the landmark circular convolution) reads level 0's static decoders (bit 1: the OVC decode) and its
+    clean-up node (bit 2), not its narrow ensembles (bit 0) nor the gate (bit 3): that is what lets its chain start before
+    the 14 000 VCO neurons are done."""
+    sc = scenarios.make_slam(n_trials=1, n_steps=10, ssp_dim=19, pi_n_neurons=30, mem_n_neurons=70, circonv_n_neurons=16,
+                             n_landmarks=6, T=20.0, view_rad=0.6)
+    plan = lowering.lower(sc.network, build_model(sc.network, dt=sc.dt))
+    assert plan.arrays["level_deps"].tolist() == [[0, 0], [2 | 4, 0]]
