@@ -76,6 +76,8 @@ def _idx(key, size):
 
 def _place(rows, n_rows, mat):
     """Scatter the rows of ``mat`` to positions ``rows`` of an (n_rows x ncols) matrix."""
+    if len(rows) == n_rows and mat.shape[0] == n_rows and np.array_equal(rows, np.arange(n_rows)):
+        return mat                      # the whole input, in order (most connections): nothing to scatter
     sel = sp.csr_matrix((np.ones(len(rows)), (rows, np.arange(len(rows)))), shape=(n_rows, len(rows)))
     return sel @ mat
 
@@ -298,10 +300,11 @@ class _Lowerer:
 
     def expr_in(self, obj):
         size = obj.size_in
-        total = sp.csr_matrix((size, self.ncol))
+        total = None
         for conn in self.incoming.get(obj, []):
-            total = total + _place(_idx(conn.post_slice, size), size, self.conn_value(conn))
-        return total.tocsr()
+            term = _place(_idx(conn.post_slice, size), size, self.conn_value(conn))
+            total = term if total is None else total + term
+        return sp.csr_matrix((size, self.ncol)) if total is None else total.tocsr()
 
     def conn_value(self, conn):
         if conn.synapse is not None:
@@ -316,7 +319,8 @@ class _Lowerer:
             raise NotImplementedError("connections from ens.neurons are outside the hot path")
         src = self.expr_out(pre)
         rows = _idx(conn.pre_slice, pre.size_out)
-        src = src[rows]
+        if not (len(rows) == src.shape[0] and np.array_equal(rows, np.arange(src.shape[0]))):
+            src = src[rows]
         return _apply_transform(compat.transform_of(conn), src).tocsr()
 
     # ------------------------------------------------------------------ main
