@@ -161,3 +161,27 @@ def test_seeding_is_creation_order_dependent_and_reproducible():
     assert m1.seeds[a1] == m2.seeds[a2] and m1.seeds[a1] != m1.seeds[b1]
     assert np.array_equal(m1.params[a1].encoders, m2.params[a2].encoders)
     assert np.array_equal(m1.params[b1].gain, m2.params[b2].gain)
+
+
+def test_spiking_lif_rate_converges_to_the_published_rate_formula():
+    """A closed-form anchor that does not depend on our reading of nengo's step code: with the spike-time interpolation and
+    the fractional refractory bookkeeping, a LIF neuron driven by a constant current J fires at exactly the LIFRate
+    tuning-curve rate 1 / (tau_ref + tau_rc ln(1 + 1 / (J - 1))) (Eliasmith & Anderson 2003; nengo's documented
+    ``LIFRate``), up to the discretisation of the count: |spikes / T - rate| <= 1 / T.  A step without the interpolation
+    (spike only on step boundaries) misses this by several per cent at these rates."""
+    gains = np.array([1.0, 1.0, 1.0, 1.0])
+    biases = np.array([1.3, 2.0, 3.5, 8.0])                       # J = bias (input 0): 32 ... 214 Hz
+    with nengo.Network(seed=2) as net:
+        ens = nengo.Ensemble(4, 1, gain=gains, bias=biases, encoders=np.ones((4, 1)))
+        nengo.Probe(ens)
+    model = build_model(net)
+    sim = RefSimulator(net, model=model)
+    n_steps, dt, tau_rc, tau_ref = 4000, 0.001, 0.02, 0.002
+    counts = np.zeros(4)
+    for _ in range(n_steps):
+        sim.run_steps(1)
+        counts += sim.signals[ens, "out"].a > 0
+    T = n_steps * dt
+    rate = 1.0 / (tau_ref + tau_rc * np.log1p(1.0 / (biases - 1.0)))
+    assert np.all(np.abs(counts / T - rate) <= 1.0 / T + 1e-9), (counts / T, rate)
+    assert 30 < rate[0] < 35 and 200 < rate[3] < 230
